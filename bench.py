@@ -1,0 +1,289 @@
+"""bench.py — (l, Q)-grid log-likelihood evaluations per second at N = 1024, 6 orders (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one pass of the hot path over one grid: 128 length scales x 256 expansion parameters per GPU (config C4;
+weak scaling: with N GPUs the grid has 128*N length scales, dealt round-robin, one all-gather of the FP64 blocks and an
+on-device max-shift normalisation per step).  `value` times the device-resident call with CUDA events; `e2e` times the
+public API (TruncationGP.log_marginal_likelihood_grid) with host buffers in and out.  One JSON line on stdout.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS, N_ORDERS, N_LS_PER_GPU, N_Q = 1024, 6, 128, 256
+METRIC = "(l,Q) grid log-likelihood evals/sec at N=1024, 6 orders"
+
+
+def make_inputs(n_ls):
+    """X = linspace(0,1,1024); coefficients ~ GP(RBF(0.05) + 1e-6 I), Q = 0.5, ref = 1, seed 3."""
+    from sklearn.gaussian_process.kernels import RBF
+    rs = np.random.RandomState(3)
+    X = np.linspace(0, 1, N_POINTS)[:, None]
+    Lt = np.linalg.cholesky(RBF(0.05)(X) + 1e-6 * np.eye(N_POINTS))
+    coeffs = Lt @ rs.standard_normal((N_POINTS, N_ORDERS))
+    orders = np.arange(N_ORDERS)
+    y = np.cumsum(coeffs * 0.5 ** orders, axis=-1)
+    ls_vals = np.geomspace(0.005, 0.5, n_ls)
+    q_vals = np.linspace(0.2, 0.8, N_Q)
+    return X, y, orders, ls_vals, q_vals
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '', 1).isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_cells(X, y, orders, ls_vals, q_vals, cells):
+    """The reference's per-cell path (oracle port: same numpy/scipy/sklearn calls as gsum/models.py:1485 -> 912) on host cores."""
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    from oracle import gsum_oracle as o
+    kern = RBF(0.05) + WhiteKernel(1e-6, 'fixed')
+    pri = o.Priors(0, 0, 1, 1)
+    n = X.shape[0]
+    t0 = time.perf_counter()
+    out = [o.truncation_lml(kern, [np.log(ls_vals[b])], X, y, orders, q_vals[a] * np.ones(n), np.ones(n), pri) for a, b in cells]
+    return time.perf_counter() - t0, out
+
+
+def stratified_cells(n_q, n_ls, k):
+    qa = np.linspace(0, n_q - 1, k).round().astype(int)
+    lb = np.linspace(0, n_ls - 1, k).round().astype(int)
+    return [(int(a), int(b)) for a in qa for b in lb]
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    X, y, orders, ls_vals, q_vals = make_inputs(N_LS_PER_GPU)
+    cells = stratified_cells(N_Q, N_LS_PER_GPU, 3)[:8]            # 8 cells per step, spread over the grid (~2 s of CPU work)
+    for _ in range(args.warmup):
+        cpu_reference_cells(X, y, orders, ls_vals, q_vals, cells[:2])
+    total = 0.0
+    for _ in range(args.steps):
+        dt, _ = cpu_reference_cells(X, y, orders, ls_vals, q_vals, cells)
+        total += dt
+    value = len(cells) * args.steps / total
+    cores = blas_threads()
+    sample = f"{len(cells)} cells/step of the 256x128 grid (stratified), {args.steps} steps; one Cholesky + 4 cho_solve per cell as in the reference"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C4: N=1024, 6 orders, 128 l x 256 Q per GPU (CPU arm: bounded sample of cells)", "n_points": N_POINTS,
+                   "n_orders": N_ORDERS, "n_ls_per_gpu": N_LS_PER_GPU, "n_q": N_Q},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample,
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def measure_fp64_peak(torch, n=4096, reps=6):
+    """cuBLAS DGEMM throughput (TFLOP/s), best of `reps` — the FP64 roofline denominator (MEASURED_PEAKS.json has none)."""
+    a = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    b = torch.randn(n, n, dtype=torch.float64, device="cuda")
+    c = torch.empty_like(a)
+    torch.matmul(a, b, out=c)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(a, b, out=c); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * n ** 3 / best * 1e-9
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sklearn.gaussian_process.kernels import RBF, WhiteKernel
+    import gsum_b200 as gb
+    from gsum_b200 import _lib, ops
+    from gsum_b200.helpers import _order_differences
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_ls_total = N_LS_PER_GPU * world
+    X, y, orders, ls_vals, q_vals = make_inputs(n_ls_total)
+    mine = np.arange(rank, n_ls_total, world)
+    stream = torch.cuda.Stream(device=dev)                     # one non-default stream for torch, NCCL and the library
+    torch.cuda.set_stream(stream)
+    ctx = _lib.Context(local_rank, stream.cuda_stream)         # library work is enqueued on torch's current stream
+    assert stream.cuda_stream != 0
+
+    # ---- device-resident inputs (the `value` arm) ----
+    dy = np.ascontiguousarray(_order_differences(y))
+    detf = N_POINTS * float(orders.sum()) * np.log(np.abs(q_vals))
+    t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    dX, ddy, dref, dord = t(X), t(dy), t(np.ones(N_POINTS)), t(orders.astype(np.int32), torch.int32)
+    dls, dQ, ddetf = t(ls_vals[mine][:, None]), t(q_vals), t(detf)
+    ll_block = torch.empty((N_Q, len(mine)), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * N_Q, len(mine)), dtype=torch.float64, device=dev)
+    post = torch.empty_like(gathered)
+    lse = torch.empty(1, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    kw = dict(constant=1.0, noise=1e-6, nugget=1e-10, center0=0.0, disp0=0.0, df0=1.0, scale0=1.0)
+
+    def step_device():
+        ops.lml_grid_device(ctx, dX, ddy, dref, dord, dls, dQ, ddetf, ll_block, **kw)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, ll_block)
+            ops.grid_normalize_device(ctx, gathered, post, lse)
+        else:
+            ops.grid_normalize_device(ctx, ll_block, post, lse)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.profile(True)
+    launches0 = ctx.launch_count
+    evs = []
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()                                                       # L2 flush between timed iterations (untimed)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream); step_device(); e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    ms_total = sum(a.elapsed_time(b) for a, b in evs)
+    launches = ctx.launch_count - launches0
+    fact_ms, fact_flops, n_br = ctx.profile_read()
+    ctx.profile(False)
+    tt = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_total, launches = float(mx[0]), int(sm[1])
+    clocks = sampler.stop() if rank == 0 else None
+    cells_per_step = N_Q * n_ls_total
+    value = cells_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end arm: the public API with host buffers (H2D of inputs and D2H of the grid inside the timed region) ----
+    gp = gb.TruncationGP(RBF(0.05) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None)
+    gp.fit(X, y, orders=orders)
+    group = dist.group.WORLD if world > 1 else None
+    for _ in range(3):
+        ll_host = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=group)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ll_host = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=group)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev); dist.all_reduce(te, op=dist.ReduceOp.MAX); e2e_s = float(te[0])
+    e2e_value = cells_per_step * args.steps / e2e_s
+    h2d = 8 * (X.size + dy.size + N_POINTS + len(mine) + N_Q + N_Q) + 4 * N_ORDERS
+    d2h = 8 * (N_Q * len(mine) + len(mine)) + 4 * len(mine)
+    assert np.isfinite(ll_host).all() and ll_host.shape == (N_Q, n_ls_total)
+
+    if rank == 0:
+        # parity spot check of the timed configuration (not timed)
+        dt_cpu, want = cpu_reference_cells(X, y, orders, ls_vals, q_vals, [(0, 0), (100, 40 * world)])
+        got = [ll_host[0, 0], ll_host[100, 40 * world]]
+        parity = max(abs(g - w) / abs(w) for g, w in zip(got, want))
+        # roofline of the dominant kernels (the bordered Cholesky launches: chol_diag_kernel + chol_panel_kernel)
+        peak = measure_fp64_peak(torch)
+        achieved = fact_flops / (fact_ms * 1e-3) * 1e-12 if fact_ms > 0 else 0.0
+        # CPU baseline on a bounded sample (~10-20 s)
+        cells = stratified_cells(N_Q, n_ls_total, 6)
+        cpu_s, _ = cpu_reference_cells(X, y, orders, ls_vals, q_vals, cells)
+        out = {
+            "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "C4: N=1024, 6 orders, 128 l x 256 Q per GPU (configs[3] of BASELINE.json)", "n_points": N_POINTS,
+                       "n_orders": N_ORDERS, "n_ls_per_gpu": N_LS_PER_GPU, "n_q": N_Q, "grid_cells_per_step": cells_per_step,
+                       "timing": "CUDA events on the launch stream per step, max over ranks; L2 flushed (256 MB memset) between steps; "
+                                 "working set 1.1 GB/GPU > L2", "collective": "one NCCL all-gather of the FP64 blocks + device logsumexp" if world > 1 else "none (1 GPU); device logsumexp"},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "TruncationGP.log_marginal_likelihood_grid (numpy in, numpy out; pageable host buffers)", "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": None, "kernel": "chol_diag_kernel + chol_panel_kernel (FP64 DMMA bordered Cholesky, K2+K3)",
+                         "flops_per_step": fact_flops / max(args.steps, 1), "kernel_ms_per_step": fact_ms / max(args.steps, 1),
+                         "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; "
+                                        "profiles/r01_dgemm_peak.json: 35.5 TFLOP/s at 8192^3)"},
+            "cpu_baseline": {"value": len(cells) / cpu_s, "unit": "evals/s", "cores": blas_threads(), "kind": "port", "host_cpus": os.cpu_count(),
+                             "sample": f"{len(cells)} stratified cells of the {N_Q}x{n_ls_total} grid, per-cell reference algorithm "
+                                       f"(numpy/scipy/sklearn), {cpu_s:.1f} s"},
+            "clocks": clocks, "parity_spot_check_rel": parity,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

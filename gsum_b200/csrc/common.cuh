@@ -1,0 +1,113 @@
+// Shared device/host utilities for the gsum_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+
+#define GSUM_TILE 64            // tile edge of the blocked FP64 factorisation / solves
+#define GSUM_LDS 68             // padded smem row stride (doubles) for 64-wide tiles: 68 % 16 == 4 -> conflict-free DMMA fragment loads
+#define GSUM_KH 32              // K depth of one pipeline stage (half a tile)
+#define GSUM_LDH 36             // padded smem row stride for 32-wide half-slabs: 36 % 16 == 4
+
+struct gsum_ctx {
+    int device;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count;
+    char err[512];
+    // grow-only device workspace arena (ctx-scoped; freed by gsum_ctx_destroy)
+    void *ws[24];
+    size_t ws_bytes[24];
+    int64_t launches;           // kernels launched by this library on this context
+    int *d_flag;                // small device int scratch
+    // optional profiling of the factorisation phase (bench.py roofline): event pairs on ctx->stream
+    int prof_enabled, prof_count;
+    cudaEvent_t prof_ev[2 * 256];
+    double prof_flops;          // algorithmic flops of the bracketed factorisations
+    int64_t prof_border_rows;   // right-hand sides riding along with the current factorisation
+};
+
+static inline int gsum_fail(gsum_ctx *c, int code, const char *fmt, ...) {
+    if (c) {
+        va_list ap; va_start(ap, fmt);
+        vsnprintf(c->err, sizeof(c->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define GSUM_CUDA(ctx, call)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return gsum_fail((ctx), -100, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e),    \
+                             __FILE__, __LINE__, cudaGetErrorString(_e));                         \
+    } while (0)
+
+#define GSUM_TRY(expr)                 \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != 0) return _rc;      \
+    } while (0)
+
+// Workspace slot `slot` of at least `bytes` (grow-only, contents undefined).
+static inline int gsum_ws(gsum_ctx *c, int slot, size_t bytes, void **out) {
+    if (c->ws_bytes[slot] < bytes) {
+        if (c->ws[slot]) {
+            GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+            GSUM_CUDA(c, cudaFree(c->ws[slot]));
+            c->ws[slot] = nullptr; c->ws_bytes[slot] = 0;
+        }
+        size_t want = bytes + (bytes >> 3) + 256;
+        GSUM_CUDA(c, cudaMalloc(&c->ws[slot], want));
+        c->ws_bytes[slot] = want;
+    }
+    *out = c->ws[slot];
+    return 0;
+}
+
+static inline int64_t gsum_pad64(int64_t n) { return (n + GSUM_TILE - 1) / GSUM_TILE * GSUM_TILE; }
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// D(8x8) += A(8x4, row) * B(4x8, col)  — FP64 tensor-core MMA (SASS: DMMA.8x8x4).
+// Fragment ownership for lane = 4*g + t:  a = A[g][t],  b = B[t][g],  c0/c1 = C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block-wide sum (fixed tree order); result valid in every thread. `red` >= 32 doubles of smem.
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int i = 0; i < nw; i++) t += red[i];
+    return t;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,953 @@
+// C ABI of gsum_b200 (see include/gsum_b200.h).  Host-side orchestration only: every numerical step is a
+// kernel from cov.cuh / chol.cuh / lml.cuh / solve.cuh / diag.cuh.  There is no CPU fallback.
+#include "../../include/gsum_b200.h"
+#include "common.cuh"
+#include "cov.cuh"
+#include "chol.cuh"
+#include "lml.cuh"
+#include "solve.cuh"
+#include "diag.cuh"
+
+#define LAUNCHED(ctx, n) ((ctx)->launches += (n))
+
+enum {
+    WS_X = 0, WS_XS, WS_DY, WS_REF, WS_ORD, WS_LS, WS_Q, WS_DETF, WS_MAT, WS_RHS, WS_GRAM, WS_LOGDET, WS_INFO,
+    WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3
+};
+
+extern "C" int gsum_version(void) { return 100; }
+
+extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
+    if (!out) return -1;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return -2;      // no CUDA device: there is no CPU path
+    if (device < 0 || device >= count) return -3;
+    if (cudaSetDevice(device) != cudaSuccess) return -4;
+    gsum_ctx *c = new gsum_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    if (cuda_stream) { c->stream = (cudaStream_t)cuda_stream; c->own_stream = false; }
+    else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return -5; }
+        c->own_stream = true;
+    }
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    *out = c;
+    return 0;
+}
+
+extern "C" int gsum_ctx_destroy(gsum_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < 24; i++) if (c->ws[i]) cudaFree(c->ws[i]);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+extern "C" int gsum_ctx_synchronize(gsum_ctx *c) {
+    if (!c) return -1;
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int gsum_ctx_profile(gsum_ctx *c, int enable) {
+    if (!c) return -1;
+    c->prof_enabled = enable; c->prof_count = 0; c->prof_flops = 0.0;
+    return 0;
+}
+extern "C" int gsum_ctx_profile_read(gsum_ctx *c, double *ms_total, double *flops_total, int64_t *n_brackets) {
+    if (!c) return -1;
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    double ms = 0.0;
+    for (int i = 0; i < c->prof_count; i++) {
+        float t = 0.f;
+        GSUM_CUDA(c, cudaEventElapsedTime(&t, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+        ms += t;
+    }
+    if (ms_total) *ms_total = ms;
+    if (flops_total) *flops_total = c->prof_flops;
+    if (n_brackets) *n_brackets = c->prof_count;
+    c->prof_count = 0; c->prof_flops = 0.0;
+    return 0;
+}
+
+extern "C" const char *gsum_last_error(const gsum_ctx *c) { return c ? c->err : "null context"; }
+extern "C" int64_t gsum_launch_count(const gsum_ctx *c) { return c ? c->launches : 0; }
+
+// ---- buffer plumbing -------------------------------------------------------------------------------
+// Input: device-resident view of a caller buffer (copy through workspace `slot` when it lives on the host).
+static int dev_in(gsum_ctx *c, int slot, const void *p, size_t bytes, int mem_kind, const void **out) {
+    if (!p) { *out = nullptr; return 0; }
+    if (mem_kind == GSUM_MEM_DEVICE) { *out = p; return 0; }
+    void *d;
+    GSUM_TRY(gsum_ws(c, slot, bytes, &d));
+    GSUM_CUDA(c, cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream));
+    *out = d;
+    return 0;
+}
+// Output: device buffer to write into (the caller's when it is a device pointer, workspace otherwise).
+static int dev_out(gsum_ctx *c, int slot, void *p, size_t bytes, int mem_kind, void **out) {
+    if (!p) { *out = nullptr; return 0; }
+    if (mem_kind == GSUM_MEM_DEVICE) { *out = p; return 0; }
+    return gsum_ws(c, slot, bytes, out);
+}
+static int dev_out_finish(gsum_ctx *c, void *host, const void *dev, size_t bytes, int mem_kind) {
+    if (!host || mem_kind == GSUM_MEM_DEVICE) return 0;
+    GSUM_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+static int finish(gsum_ctx *c, int mem_kind) {
+    GSUM_CUDA(c, cudaPeekAtLastError());
+    GSUM_CUDA(c, cudaGetLastError());
+    if (mem_kind == GSUM_MEM_HOST) GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int scale_coords(gsum_ctx *c, const double *dX, const double *dls, double *dXS, int64_t n, int d, int ls_dim,
+                        int64_t batch) {
+    int64_t total = batch * n * d;
+    scale_coords_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(dX, dls, dXS, n, d, ls_dim, batch);
+    LAUNCHED(c, 1);
+    return 0;
+}
+
+// ---- K1 ---------------------------------------------------------------------------------------------
+extern "C" int gsum_kernel_matrix(gsum_ctx *c, const double *X1, int64_t n1, const double *X2, int64_t n2, int32_t d,
+                                  const double *ls, int32_t ls_dim, double constant, double noise, double *out,
+                                  int32_t mem_kind) {
+    if (!c || !X1 || !ls || !out || n1 <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d))
+        return gsum_fail(c, -1, "gsum_kernel_matrix: bad argument (d must be 1..%d, ls_dim 1 or d)", COV_MAXD);
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const bool sym = (X2 == nullptr);
+    if (sym) n2 = n1;
+    const void *dX1, *dX2 = nullptr, *dls;
+    GSUM_TRY(dev_in(c, WS_X, X1, sizeof(double) * n1 * d, mem_kind, &dX1));
+    if (!sym) GSUM_TRY(dev_in(c, WS_IO0, X2, sizeof(double) * n2 * d, mem_kind, &dX2));
+    GSUM_TRY(dev_in(c, WS_LS, ls, sizeof(double) * ls_dim, mem_kind, &dls));
+    void *xs;
+    GSUM_TRY(gsum_ws(c, WS_XS, sizeof(double) * (n1 + n2) * d, &xs));
+    double *xs1 = (double *)xs, *xs2 = xs1 + n1 * d;
+    scale_coords(c, (const double *)dX1, (const double *)dls, xs1, n1, d, ls_dim, 1);
+    if (!sym) scale_coords(c, (const double *)dX2, (const double *)dls, xs2, n2, d, ls_dim, 1);
+    void *dout;
+    GSUM_TRY(dev_out(c, WS_MAT, out, sizeof(double) * n1 * n2, mem_kind, &dout));
+    CrossArgs P;
+    P.XS1 = xs1; P.n1 = n1; P.XS2 = sym ? xs1 : xs2; P.n2 = n2; P.d = d;
+    P.constant = constant; P.diag_add = noise; P.sym_diag = sym ? 1 : 0;
+    P.out = (double *)dout; P.ldo = n2; P.rows_out = n1; P.cols_out = n2;
+    dim3 grid((unsigned)((n2 + 63) / 64), (unsigned)((n1 + 63) / 64));
+    cov_cross_kernel<<<grid, 256, 0, c->stream>>>(P);
+    LAUNCHED(c, 1);
+    GSUM_TRY(dev_out_finish(c, out, dout, sizeof(double) * n1 * n2, mem_kind));
+    return finish(c, mem_kind);
+}
+
+// ---- K2 ---------------------------------------------------------------------------------------------
+// contiguous (batch, n, n)  <->  bordered padded layout
+__global__ void pad_in_kernel(const double *__restrict__ src, int64_t n, double *__restrict__ dst, int64_t ld, int64_t bstride,
+                              int64_t rows) {
+    const int64_t b = blockIdx.z, r = blockIdx.y;
+    const double *s = src + b * n * n + r * n;
+    double *dr = dst + b * bstride + r * ld;
+    for (int64_t cidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cidx < ld; cidx += (int64_t)gridDim.x * blockDim.x)
+        dr[cidx] = (r < n && cidx < n) ? s[cidx] : (r == cidx ? 1.0 : 0.0);
+}
+__global__ void pad_out_lower_kernel(const double *__restrict__ src, int64_t ld, int64_t bstride, double *__restrict__ dst, int64_t n) {
+    const int64_t b = blockIdx.z, r = blockIdx.y;
+    const double *s = src + b * bstride + r * ld;
+    double *dr = dst + b * n * n + r * n;
+    for (int64_t cidx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cidx < n; cidx += (int64_t)gridDim.x * blockDim.x)
+        dr[cidx] = cidx <= r ? s[cidx] : 0.0;
+}
+__global__ void fill_kernel(double *p, int64_t n, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void add_diag_kernel(double *F, int64_t ld, int64_t n, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) F[i * ld + i] = __dadd_rn(F[i * ld + i], v);
+}
+// contiguous lower factor (n,n) -> padded (np x np): strict upper part forced to zero, identity padding
+__global__ void pad_lower_kernel(const double *__restrict__ L, int64_t n, double *__restrict__ F, int64_t np) {
+    const int64_t r = blockIdx.y;
+    for (int64_t cc = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; cc < np; cc += (int64_t)gridDim.x * blockDim.x)
+        F[r * np + cc] = (r < n && cc < n) ? (cc <= r ? L[r * n + cc] : 0.0) : (r == cc ? 1.0 : 0.0);
+}
+__global__ void logdet_sum_kernel(const double *__restrict__ part, int T, int64_t batch, double *__restrict__ out) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    double s = 0.0;
+    for (int k = 0; k < T; k++) s += part[b * T + k];
+    out[b] = s;
+}
+
+// Factor `batch` padded matrices already resident in workspace WS_MAT (bordered layout, Trows tile rows).
+static int factor_bordered(gsum_ctx *c, double *dA, int64_t n, int Trows, int64_t batch, int **dinfo_out, double **dpart_out) {
+    // c->prof_border_rows: right-hand sides riding along (set by the caller; 0 for a plain factorisation)
+    const int T = (int)(gsum_pad64(n) / GSUM_TILE);
+    void *dinfo, *dpart;
+    GSUM_TRY(gsum_ws(c, WS_INFO, sizeof(int) * batch, &dinfo));
+    GSUM_TRY(gsum_ws(c, WS_LOGDET, sizeof(double) * batch * T, &dpart));
+    GSUM_CUDA(c, cudaMemsetAsync(dinfo, 0, sizeof(int) * batch, c->stream));
+    BorderedBatch P;
+    P.A = dA; P.ld = (int64_t)T * GSUM_TILE; P.bstride = (int64_t)Trows * GSUM_TILE * P.ld;
+    P.W = dA + (int64_t)T * GSUM_TILE * P.ld; P.wstride = P.bstride;
+    P.T = T; P.Trows = Trows; P.info = (int *)dinfo; P.logdet_part = (double *)dpart; P.n = (int)n;
+    const bool prof = c->prof_enabled && c->prof_count < 256;
+    if (prof) {
+        if (!c->prof_ev[2 * c->prof_count]) { cudaEventCreate(&c->prof_ev[2 * c->prof_count]); cudaEventCreate(&c->prof_ev[2 * c->prof_count + 1]); }
+        cudaEventRecord(c->prof_ev[2 * c->prof_count], c->stream);
+    }
+    GSUM_TRY(chol_bordered_run(c, P, (int)batch));
+    if (prof) {
+        cudaEventRecord(c->prof_ev[2 * c->prof_count + 1], c->stream);
+        c->prof_count++;
+        // algorithmic work: N^3/3 per factorisation + N^2 per forward-solved border row, true (unpadded) sizes
+        c->prof_flops += (double)batch * ((double)n * n * n / 3.0 + (double)n * n * (double)c->prof_border_rows);
+    }
+    *dinfo_out = (int *)dinfo; *dpart_out = (double *)dpart;
+    return 0;
+}
+
+extern "C" int gsum_cholesky(gsum_ctx *c, double *A, int64_t n, int64_t batch, int32_t *info, double *logdet,
+                             int32_t mem_kind) {
+    if (!c || !A || n <= 0 || batch <= 0) return gsum_fail(c, -1, "gsum_cholesky: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int64_t np = gsum_pad64(n);
+    const int T = (int)(np / GSUM_TILE);
+    const void *dsrc;
+    GSUM_TRY(dev_in(c, WS_IO0, A, sizeof(double) * batch * n * n, mem_kind, &dsrc));
+    void *dmat;
+    GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * batch * np * np, &dmat));
+    dim3 g1((unsigned)((np + 255) / 256), (unsigned)np, (unsigned)batch);
+    pad_in_kernel<<<g1, 256, 0, c->stream>>>((const double *)dsrc, n, (double *)dmat, np, np * np, np);
+    LAUNCHED(c, 1);
+    int *dinfo; double *dpart;
+    GSUM_TRY(factor_bordered(c, (double *)dmat, n, T, batch, &dinfo, &dpart));
+    dim3 g2((unsigned)((n + 255) / 256), (unsigned)n, (unsigned)batch);
+    double *ddst = (double *)dsrc;       // in place: the caller's device buffer, or our staging copy
+    pad_out_lower_kernel<<<g2, 256, 0, c->stream>>>((const double *)dmat, np, np * np, ddst, n);
+    LAUNCHED(c, 1);
+    GSUM_TRY(dev_out_finish(c, A, ddst, sizeof(double) * batch * n * n, mem_kind));
+    if (info) {
+        if (mem_kind == GSUM_MEM_DEVICE) GSUM_CUDA(c, cudaMemcpyAsync(info, dinfo, sizeof(int) * batch, cudaMemcpyDeviceToDevice, c->stream));
+        else GSUM_CUDA(c, cudaMemcpyAsync(info, dinfo, sizeof(int) * batch, cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (logdet) {
+        void *dl;
+        GSUM_TRY(dev_out(c, WS_LL, logdet, sizeof(double) * batch, mem_kind, &dl));
+        logdet_sum_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, c->stream>>>(dpart, T, batch, (double *)dl);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, logdet, dl, sizeof(double) * batch, mem_kind));
+    }
+    return finish(c, mem_kind);
+}
+
+// ---- K1-K4 fused: the (Q, l) grid ---------------------------------------------------------------------
+template <int R>
+static void launch_gram(gsum_ctx *c, const double *A, int64_t ld, int64_t bstride, int T, int64_t n, double *G, int64_t nq_rows,
+                        int64_t batch) {
+    dim3 grid((unsigned)nq_rows, (unsigned)batch);
+    gram_rows_kernel<R><<<grid, 256, 0, c->stream>>>(A, ld, bstride, T, n, G, nq_rows);
+}
+
+extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *dy, int32_t n_c,
+                             const double *ref, const int32_t *orders, const double *ls, int64_t n_ls, int32_t ls_dim,
+                             const double *Q, int64_t n_q, int32_t q_x_dependent, const double *detf, double constant,
+                             double noise, double nugget, double center0, double disp0, double df0, double scale0,
+                             int32_t student, double *ll, double *logdet, int32_t *status, int32_t mem_kind) {
+    if (!c || !X || !dy || !ref || !orders || !ls || !Q || !ll)
+        return gsum_fail(c, -1, "gsum_lml_grid: null argument");
+    if (n <= 0 || n_ls <= 0 || n_q <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d) || n_c < 1 || n_c + 1 > LML_MAXR)
+        return gsum_fail(c, -1, "gsum_lml_grid: bad shape (d<=%d, n_c<=%d, ls_dim in {1,d})", COV_MAXD, LML_MAXR - 1);
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int R = n_c + 1;
+    const int64_t np = gsum_pad64(n);
+    const int T = (int)(np / GSUM_TILE);
+    const int64_t nq_rows = q_x_dependent ? n_q : 1;            // RHS blocks per matrix
+    const int64_t r_rhs = 1 + nq_rows * n_c;                    // border rows in use
+    const int64_t rp = gsum_pad64(r_rhs);
+    const int Trows = T + (int)(rp / GSUM_TILE);
+
+    const void *dX, *ddy, *dref, *dord, *dls, *dQ, *ddetf;
+    GSUM_TRY(dev_in(c, WS_X, X, sizeof(double) * n * d, mem_kind, &dX));
+    GSUM_TRY(dev_in(c, WS_DY, dy, sizeof(double) * n * n_c, mem_kind, &ddy));
+    GSUM_TRY(dev_in(c, WS_REF, ref, sizeof(double) * n, mem_kind, &dref));
+    GSUM_TRY(dev_in(c, WS_ORD, orders, sizeof(int32_t) * n_c, mem_kind, &dord));
+    GSUM_TRY(dev_in(c, WS_LS, ls, sizeof(double) * n_ls * ls_dim, mem_kind, &dls));
+    GSUM_TRY(dev_in(c, WS_Q, Q, sizeof(double) * n_q * (q_x_dependent ? n : 1), mem_kind, &dQ));
+    GSUM_TRY(dev_in(c, WS_DETF, detf, sizeof(double) * n_q, mem_kind, &ddetf));
+
+    // RHS rows (shared by every length scale): basis + coefficients, transposed
+    void *drhs;
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * r_rhs * n, &drhs));
+    {
+        dim3 grid((unsigned)((n + 255) / 256), (unsigned)r_rhs);
+        stage_rhs_kernel<<<grid, 256, 0, c->stream>>>((double *)drhs, n, (const double *)ddy, (const double *)dref,
+                                                      q_x_dependent ? (const double *)dQ : nullptr, (const int32_t *)dord, n,
+                                                      n_c, nq_rows);
+        LAUNCHED(c, 1);
+    }
+    void *dll;
+    GSUM_TRY(dev_out(c, WS_LL, ll, sizeof(double) * n_q * n_ls, mem_kind, &dll));
+    void *dlogdet = nullptr;
+    if (logdet) GSUM_TRY(dev_out(c, WS_MISC0, logdet, sizeof(double) * n_ls, mem_kind, &dlogdet));
+
+    // length scales are processed in chunks sized to a fixed HBM budget (whole grid at once for the BASELINE configs)
+    const int64_t per_mat = (int64_t)Trows * GSUM_TILE * np;                     // doubles
+    const int64_t budget = (int64_t)24 << 30;                                     // bytes
+    int64_t chunk = budget / (per_mat * 8);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_ls) chunk = n_ls;
+    void *dmat, *dxs, *dgram, *dinfo_all;
+    GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * chunk * per_mat, &dmat));
+    GSUM_TRY(gsum_ws(c, WS_XS, sizeof(double) * chunk * n * d, &dxs));
+    GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * chunk * nq_rows * R * R, &dgram));
+    GSUM_TRY(gsum_ws(c, WS_MISC1, sizeof(int) * n_ls, &dinfo_all));
+
+    for (int64_t l0 = 0; l0 < n_ls; l0 += chunk) {
+        const int64_t nb = (n_ls - l0 < chunk) ? (n_ls - l0) : chunk;
+        scale_coords(c, (const double *)dX, (const double *)dls + l0 * ls_dim, (double *)dxs, n, d, ls_dim, nb);
+        CovArgs CA;
+        CA.XS = (const double *)dxs; CA.n = n; CA.d = d; CA.constant = constant; CA.noise = noise; CA.nugget = nugget;
+        CA.A = (double *)dmat; CA.ld = np; CA.bstride = per_mat; CA.T = T;
+        dim3 gcov((unsigned)(T * (T + 1) / 2), (unsigned)nb);
+        cov_sym_kernel<<<gcov, 256, 0, c->stream>>>(CA);
+        dim3 gb((unsigned)rp, (unsigned)((np + 255) / 256), (unsigned)nb);
+        border_fill_kernel<<<gb, 256, 0, c->stream>>>((double *)dmat, np, per_mat, T, (int)rp, (const double *)drhs, (int)r_rhs, n, n);
+        LAUNCHED(c, 2);
+        int *dinfo; double *dpart;
+        c->prof_border_rows = r_rhs;
+        GSUM_TRY(factor_bordered(c, (double *)dmat, n, Trows, nb, &dinfo, &dpart));
+        c->prof_border_rows = 0;
+        switch (R) {
+#define GRAM_CASE(RR) case RR: launch_gram<RR>(c, (const double *)dmat, np, per_mat, T, n, (double *)dgram, nq_rows, nb); break;
+            GRAM_CASE(2) GRAM_CASE(3) GRAM_CASE(4) GRAM_CASE(5) GRAM_CASE(6) GRAM_CASE(7) GRAM_CASE(8)
+#undef GRAM_CASE
+            default: {
+                dim3 grid((unsigned)nq_rows, (unsigned)nb);
+                gram_rows_generic_kernel<<<grid, 256, 0, c->stream>>>((const double *)dmat, np, per_mat, T, n, (double *)dgram, nq_rows, R);
+            }
+        }
+        LAUNCHED(c, 1);
+        LmlCellArgs LA;
+        LA.G = (const double *)dgram; LA.logdet_part = dpart; LA.info = dinfo; LA.T = T; LA.R = R;
+        LA.n = n; LA.n_l = nb; LA.n_q = n_q; LA.separable = q_x_dependent ? 0 : 1;
+        LA.Q = (const double *)dQ; LA.orders = (const int32_t *)dord; LA.detf = (const double *)ddetf;
+        LA.center0 = center0; LA.disp0 = disp0; LA.df0 = df0; LA.scale0 = scale0; LA.student = student;
+        LA.ll = nullptr; LA.logdet_out = dlogdet ? (double *)dlogdet + l0 : nullptr; LA.post = nullptr;
+        // cells of this chunk go to columns [l0, l0+nb) of the (n_q, n_ls) grid
+        LA.ll = (double *)dll;
+        lml_cell_chunk_kernel<<<(unsigned)((nb * n_q + 127) / 128), 128, 0, c->stream>>>(LA, l0, n_ls);
+        LAUNCHED(c, 1);
+        GSUM_CUDA(c, cudaMemcpyAsync((int *)dinfo_all + l0, dinfo, sizeof(int) * nb, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    GSUM_TRY(dev_out_finish(c, ll, dll, sizeof(double) * n_q * n_ls, mem_kind));
+    GSUM_TRY(dev_out_finish(c, logdet, dlogdet, sizeof(double) * n_ls, mem_kind));
+    if (status) {
+        GSUM_CUDA(c, cudaMemcpyAsync(status, dinfo_all, sizeof(int) * n_ls,
+                                     mem_kind == GSUM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    }
+    return finish(c, mem_kind);
+}
+
+
+extern "C" int gsum_grid_normalize(gsum_ctx *c, const double *ll, int64_t count, double *post, double *lse, int32_t mem_kind) {
+    if (!c || !ll || count <= 0) return gsum_fail(c, -1, "gsum_grid_normalize: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const void *dll; void *dpost, *dlse;
+    GSUM_TRY(dev_in(c, WS_IO0, ll, sizeof(double) * count, mem_kind, &dll));
+    GSUM_TRY(dev_out(c, WS_IO1, post, sizeof(double) * count, mem_kind, &dpost));
+    GSUM_TRY(dev_out(c, WS_IO2, lse, sizeof(double), mem_kind, &dlse));
+    grid_normalize_kernel<<<1, 1024, 0, c->stream>>>((const double *)dll, count, (double *)dpost, (double *)dlse);
+    LAUNCHED(c, 1);
+    GSUM_TRY(dev_out_finish(c, post, dpost, sizeof(double) * count, mem_kind));
+    GSUM_TRY(dev_out_finish(c, lse, dlse, sizeof(double), mem_kind));
+    return finish(c, mem_kind);
+}
+
+// ---- shared plumbing for solves against an existing factor ------------------------------------------------
+static void launch_transpose_in(gsum_ctx *c, const double *src, int64_t n, int64_t m, const double *sub, const int32_t *perm,
+                                int flip, double sign, double *dst, int64_t dst_ld, int64_t rows_pad) {
+    dim3 grid((unsigned)((rows_pad + 31) / 32), (unsigned)((dst_ld + 31) / 32));
+    transpose_in_kernel<<<grid, 256, 0, c->stream>>>(src, n, m, sub, perm, flip, sign, dst, dst_ld, rows_pad);
+    LAUNCHED(c, 1);
+}
+static void launch_transpose_out(gsum_ctx *c, const double *src, int64_t src_ld, int64_t n, int64_t m, int flip, double scale,
+                                 const double *add, double *dst) {
+    dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
+    transpose_out_kernel<<<grid, 256, 0, c->stream>>>(src, src_ld, n, m, flip, scale, add, dst);
+    LAUNCHED(c, 1);
+}
+static BorderedBatch solve_desc(double *F, double *W, int64_t np, int T, int64_t rows_pad) {
+    BorderedBatch P;
+    P.A = F; P.ld = np; P.bstride = np * np; P.W = W; P.wstride = rows_pad * np;
+    P.T = T; P.Trows = T + (int)(rows_pad / GSUM_TILE); P.info = nullptr; P.logdet_part = nullptr; P.n = (int)np;
+    return P;
+}
+// contiguous factor L (n,n) -> padded (np x np) with identity padding
+static int pad_factor(gsum_ctx *c, const double *dL, int64_t n, double *dF) {
+    const int64_t np = gsum_pad64(n);
+    dim3 g((unsigned)((np + 255) / 256), (unsigned)np, 1);
+    pad_in_kernel<<<g, 256, 0, c->stream>>>(dL, n, dF, np, np * np, np);
+    LAUNCHED(c, 1);
+    return 0;
+}
+// Lt[i][j] = L[n-1-j][n-1-i]: the lower-triangular matrix whose forward substitution is L^T's back substitution
+__global__ void flip_transpose_kernel(const double *__restrict__ L, int64_t n, double *__restrict__ F, int64_t np) {
+    const int64_t i = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < np; j += (int64_t)gridDim.x * blockDim.x)
+        F[i * np + j] = (i < n && j < n) ? ((j <= i) ? L[(n - 1 - j) * n + (n - 1 - i)] : 0.0) : (i == j ? 1.0 : 0.0);
+}
+__global__ void flip_rows_kernel(const double *__restrict__ src, double *__restrict__ dst, int64_t ld, int64_t n) {
+    const int64_t r = blockIdx.x;
+    for (int64_t x = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; x < ld; x += (int64_t)gridDim.y * blockDim.x)
+        dst[r * ld + x] = x < n ? src[r * ld + (n - 1 - x)] : 0.0;
+}
+
+// ---- K3 -------------------------------------------------------------------------------------------------
+extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B, int64_t nrhs, int32_t forward_only,
+                              int32_t mem_kind) {
+    if (!c || !L || !B || n <= 0 || nrhs <= 0) return gsum_fail(c, -1, "gsum_cho_solve: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int64_t np = gsum_pad64(n), rp = gsum_pad64(nrhs);
+    const int T = (int)(np / GSUM_TILE);
+    const void *dL, *dB;
+    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, mem_kind, &dL));
+    GSUM_TRY(dev_in(c, WS_IO1, B, sizeof(double) * n * nrhs, mem_kind, &dB));
+    void *dF, *dW;
+    GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dF));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dW));
+    pad_factor(c, (const double *)dL, n, (double *)dF);
+    launch_transpose_in(c, (const double *)dB, n, nrhs, nullptr, nullptr, 0, 1.0, (double *)dW, np, rp);
+    GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    double *dBout = (double *)dB;     // in place (caller's device buffer or our staging copy)
+    if (forward_only) {
+        launch_transpose_out(c, (const double *)dW, np, n, nrhs, 0, 1.0, nullptr, dBout);
+    } else {
+        void *dW2;
+        GSUM_TRY(gsum_ws(c, WS_MISC2, sizeof(double) * rp * np, &dW2));
+        dim3 g1((unsigned)((np + 255) / 256), (unsigned)np);
+        flip_transpose_kernel<<<g1, 256, 0, c->stream>>>((const double *)dL, n, (double *)dF, np);
+        dim3 g2((unsigned)rp, (unsigned)((np + 255) / 256));
+        flip_rows_kernel<<<g2, 256, 0, c->stream>>>((const double *)dW, (double *)dW2, np, n);
+        LAUNCHED(c, 2);
+        GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW2, np, T, rp), 1));
+        launch_transpose_out(c, (const double *)dW2, np, n, nrhs, 1, 1.0, nullptr, dBout);
+    }
+    GSUM_TRY(dev_out_finish(c, B, dBout, sizeof(double) * n * nrhs, mem_kind));
+    return finish(c, mem_kind);
+}
+
+// ---- fit --------------------------------------------------------------------------------------------------
+struct gsum_fit {
+    gsum_ctx *ctx;
+    int64_t n, np; int d, n_c, T, ls_dim;
+    double ls[COV_MAXD];
+    double constant, noise, nugget;
+    double post[7];          // center, disp, df, scale, cov_factor, lml, logdet
+    double *dX, *dXS, *dy, *dL, *dls;   // device: X (n,d), X/ls, y (n,n_c), padded factor (np,np), ls
+};
+
+extern "C" int gsum_fit_destroy(gsum_fit *f) {
+    if (!f) return 0;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->dX); cudaFree(f->dXS); cudaFree(f->dy); cudaFree(f->dL); cudaFree(f->dls);
+    delete f;
+    return 0;
+}
+
+extern "C" int gsum_fit_create(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *y, int32_t n_c,
+                               const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                               double center0, double disp0, double df0, double scale0, int32_t student, double *out7,
+                               double *L_out, int32_t mem_kind, gsum_fit **fit) {
+    if (!c || !X || !y || !ls || !fit || n <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d) || n_c < 1 || n_c + 1 > LML_MAXR)
+        return gsum_fail(c, -1, "gsum_fit_create: bad argument");
+    *fit = nullptr;
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int64_t np = gsum_pad64(n);
+    const int T = (int)(np / GSUM_TILE), R = n_c + 1;
+    gsum_fit *f = new gsum_fit();
+    memset(f, 0, sizeof(*f));
+    f->ctx = c; f->n = n; f->np = np; f->d = d; f->n_c = n_c; f->T = T; f->ls_dim = ls_dim;
+    f->constant = constant; f->noise = noise; f->nugget = nugget;
+#define FIT_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { gsum_fit_destroy(f); return gsum_fail(c, -100, "CUDA error %s in gsum_fit_create", cudaGetErrorName(_e)); } } while (0)
+    FIT_CUDA(cudaMalloc(&f->dX, sizeof(double) * n * d));
+    FIT_CUDA(cudaMalloc(&f->dXS, sizeof(double) * n * d));
+    FIT_CUDA(cudaMalloc(&f->dy, sizeof(double) * n * n_c));
+    FIT_CUDA(cudaMalloc(&f->dls, sizeof(double) * ls_dim));
+    FIT_CUDA(cudaMalloc(&f->dL, sizeof(double) * (np + GSUM_TILE) * np));      // factor + one border tile row (basis, y)
+    const cudaMemcpyKind kin = mem_kind == GSUM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    FIT_CUDA(cudaMemcpyAsync(f->dX, X, sizeof(double) * n * d, kin, c->stream));
+    FIT_CUDA(cudaMemcpyAsync(f->dy, y, sizeof(double) * n * n_c, kin, c->stream));
+    FIT_CUDA(cudaMemcpyAsync(f->dls, ls, sizeof(double) * ls_dim, kin, c->stream));
+    if (mem_kind == GSUM_MEM_HOST) memcpy(f->ls, ls, sizeof(double) * ls_dim);
+    else FIT_CUDA(cudaMemcpyAsync(f->ls, ls, sizeof(double) * ls_dim, cudaMemcpyDeviceToHost, c->stream));
+    scale_coords(c, f->dX, f->dls, f->dXS, n, d, ls_dim, 1);
+    CovArgs CA;
+    CA.XS = f->dXS; CA.n = n; CA.d = d; CA.constant = constant; CA.noise = noise; CA.nugget = nugget;
+    CA.A = f->dL; CA.ld = np; CA.bstride = (np + GSUM_TILE) * np; CA.T = T;
+    cov_sym_kernel<<<dim3((unsigned)(T * (T + 1) / 2), 1), 256, 0, c->stream>>>(CA);
+    // border rows: basis (ones) then the n_c curves, transposed — same staging as the grid path with ref = 1, Q absent
+    void *dones, *dord, *drhs, *dgram, *dll, *dpost;
+    GSUM_TRY(gsum_ws(c, WS_REF, sizeof(double) * n, &dones));
+    GSUM_TRY(gsum_ws(c, WS_ORD, sizeof(int32_t) * n_c, &dord));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * R * n, &drhs));
+    GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * R * R, &dgram));
+    GSUM_TRY(gsum_ws(c, WS_LL, sizeof(double) * 2, &dll));
+    GSUM_TRY(gsum_ws(c, WS_MISC0, sizeof(double) * 8, &dpost));
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((double *)dones, n, 1.0);
+    FIT_CUDA(cudaMemsetAsync(dord, 0, sizeof(int32_t) * n_c, c->stream));
+    stage_rhs_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)R), 256, 0, c->stream>>>((double *)drhs, n, f->dy, (const double *)dones, nullptr,
+                                                                                             (const int32_t *)dord, n, n_c, 1);
+    border_fill_kernel<<<dim3(GSUM_TILE, (unsigned)((np + 255) / 256), 1), 256, 0, c->stream>>>(f->dL, np, (np + GSUM_TILE) * np, T, GSUM_TILE,
+                                                                                                (const double *)drhs, R, n, n);
+    LAUNCHED(c, 4);
+    int *dinfo; double *dpart;
+    c->prof_border_rows = R;
+    GSUM_TRY(factor_bordered(c, f->dL, n, T + 1, 1, &dinfo, &dpart));
+    c->prof_border_rows = 0;
+    switch (R) {
+#define GRAM_CASE(RR) case RR: launch_gram<RR>(c, f->dL, np, (np + GSUM_TILE) * np, T, n, (double *)dgram, 1, 1); break;
+        GRAM_CASE(2) GRAM_CASE(3) GRAM_CASE(4) GRAM_CASE(5) GRAM_CASE(6) GRAM_CASE(7) GRAM_CASE(8)
+#undef GRAM_CASE
+        default: gram_rows_generic_kernel<<<dim3(1, 1), 256, 0, c->stream>>>(f->dL, np, (np + GSUM_TILE) * np, T, n, (double *)dgram, 1, R);
+    }
+    LmlCellArgs LA;
+    LA.G = (const double *)dgram; LA.logdet_part = dpart; LA.info = dinfo; LA.T = T; LA.R = R; LA.n = n; LA.n_l = 1; LA.n_q = 1;
+    LA.separable = 0; LA.Q = nullptr; LA.orders = (const int32_t *)dord; LA.detf = nullptr;
+    LA.center0 = center0; LA.disp0 = disp0; LA.df0 = df0; LA.scale0 = scale0; LA.student = student;
+    LA.ll = (double *)dll; LA.logdet_out = (double *)dll + 1; LA.post = (double *)dpost;
+    lml_cell_chunk_kernel<<<1, 32, 0, c->stream>>>(LA, 0, 1);
+    LAUNCHED(c, 2);
+    int hinfo = 0; double hll[2], hpost[5];
+    FIT_CUDA(cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FIT_CUDA(cudaMemcpyAsync(hll, dll, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    FIT_CUDA(cudaMemcpyAsync(hpost, dpost, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->stream));
+    FIT_CUDA(cudaStreamSynchronize(c->stream));
+    if (hinfo != 0) {
+        gsum_fit_destroy(f);
+        return gsum_fail(c, hinfo, "gsum_fit_create: correlation matrix is not positive definite (leading minor %d)", hinfo);
+    }
+    f->post[0] = hpost[0]; f->post[1] = hpost[1]; f->post[2] = hpost[2]; f->post[3] = sqrt(hpost[3]); f->post[4] = hpost[4];
+    f->post[5] = hll[0]; f->post[6] = hll[1];
+    if (out7) {
+        if (mem_kind == GSUM_MEM_HOST) memcpy(out7, f->post, sizeof(f->post));
+        else FIT_CUDA(cudaMemcpyAsync(out7, f->post, sizeof(f->post), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (L_out) {
+        void *dLo;
+        GSUM_TRY(dev_out(c, WS_IO0, L_out, sizeof(double) * n * n, mem_kind, &dLo));
+        pad_out_lower_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n, 1), 256, 0, c->stream>>>(f->dL, np, 0, (double *)dLo, n);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, L_out, dLo, sizeof(double) * n * n, mem_kind));
+    }
+    // the factor's strict upper tiles are never read by the tile kernels, but draws / exports want exact zeros there
+    *fit = f;
+    return finish(c, GSUM_MEM_HOST);
+#undef FIT_CUDA
+}
+
+// ---- predict / process covariance ---------------------------------------------------------------------------
+static GeoSum make_geosum(const double *q, double start, double end, const int32_t *excluded, int n_excluded) {
+    GeoSum g; memset(&g, 0, sizeof(g));
+    g.enabled = q != nullptr; g.start = start; g.end = end;
+    g.n_excl = n_excluded > 8 ? 8 : (n_excluded < 0 ? 0 : n_excluded);
+    for (int i = 0; i < g.n_excl; i++) g.excl[i] = excluded[i];
+    return g;
+}
+static void launch_cross(gsum_ctx *c, const double *xs1, int64_t n1, const double *xs2, int64_t n2, int d, double constant, double diag_add,
+                         int sym_diag, double *out, int64_t ldo, int64_t rows_out, int64_t cols_out) {
+    CrossArgs P;
+    P.XS1 = xs1; P.n1 = n1; P.XS2 = xs2; P.n2 = n2; P.d = d; P.constant = constant; P.diag_add = diag_add; P.sym_diag = sym_diag;
+    P.out = out; P.ldo = ldo; P.rows_out = rows_out; P.cols_out = cols_out;
+    dim3 grid((unsigned)((cols_out + 63) / 64), (unsigned)((rows_out + 63) / 64));
+    cov_cross_kernel<<<grid, 256, 0, c->stream>>>(P);
+    LAUNCHED(c, 1);
+}
+static void launch_scale_cov(gsum_ctx *c, double *K, int64_t ld, int64_t rows, int64_t cols, const double *sr, const double *sc,
+                             const double *qr, const double *qc, const GeoSum &g, double factor, double kadd = 0.0) {
+    dim3 grid((unsigned)rows, (unsigned)((cols + 255) / 256));
+    scale_cov_kernel<<<grid, 256, 0, c->stream>>>(K, ld, rows, cols, sr, sc, qr, qc, g, factor, kadd);
+    LAUNCHED(c, 1);
+}
+__global__ void pad_identity_kernel(double *F, int64_t np, int64_t n) {
+    const int64_t i = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < np) F[i * np + i] = 1.0;
+}
+// var_out[j] = factor * (diag[j] - sq[j] + add)
+__global__ void finish_var_kernel(const double *__restrict__ sq, int64_t m, double diag_const, const double *__restrict__ sc,
+                                  const double *__restrict__ q, GeoSum g, double kfactor, double factor, double add, double *__restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double dj = diag_const;
+    if (sc || q) {                         // truncation: ((s s) gs(q q)) * (kfactor * c)
+        const double s = sc ? sc[j] : 1.0;
+        const double gs = (g.enabled && q) ? geo_sum(g, q[j] * q[j]) : 1.0;
+        dj = ((s * s) * gs) * (kfactor * diag_const);
+    } else dj = kfactor * diag_const;
+    out[j] = factor * ((dj - sq[j]) + add);
+}
+// out (m x m) <- factor * sym(C lower) (+ factor * add on the diagonal)
+__global__ void cov_out_kernel(const double *__restrict__ C, int64_t ldc, int64_t m, double factor, double add, double *__restrict__ out) {
+    const int64_t r = blockIdx.x;
+    for (int64_t cc = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; cc < m; cc += (int64_t)gridDim.y * blockDim.x) {
+        double v = r >= cc ? C[r * ldc + cc] : C[cc * ldc + r];
+        if (r == cc) v += add;
+        out[r * m + cc] = factor * v;
+    }
+}
+
+extern "C" int gsum_predict(gsum_ctx *c, gsum_fit *f, const gsum_predict_args *a, int32_t mem_kind) {
+    if (!c || !f || !a || !a->Xnew || a->m <= 0) return gsum_fail(c, -1, "gsum_predict: bad argument");
+    if (a->want != GSUM_PREDICT_MEAN && a->want != GSUM_PREDICT_VAR && a->want != GSUM_PREDICT_COV)
+        return gsum_fail(c, -1, "gsum_predict: bad `want`");
+    if ((a->want != GSUM_PREDICT_MEAN) && !a->var_out) return gsum_fail(c, -1, "gsum_predict: var_out is NULL");
+    if (a->yc && a->n_y < 1) return gsum_fail(c, -1, "gsum_predict: n_y < 1");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int d = f->d;
+    const int64_t m = a->m, mp = gsum_pad64(m);
+    const bool own_cond = a->Xc != nullptr;
+    const int64_t n = own_cond ? a->n_cond : f->n;
+    if (n <= 0) return gsum_fail(c, -1, "gsum_predict: n_cond <= 0");
+    const int64_t np = gsum_pad64(n);
+    const int T = (int)(np / GSUM_TILE);
+    const int trunc = a->truncation != 0;
+    const int n_y = a->yc ? a->n_y : f->n_c;
+    const int want_basis = a->cond_basis_out != nullptr;
+    const int64_t yrows = n_y + (want_basis ? 1 : 0);
+    const int64_t yp = gsum_pad64(yrows);
+    const double cov_factor = f->post[4];
+    const GeoSum g = make_geosum(a->q_old, a->gs_start, a->gs_end, a->excluded, a->n_excluded);
+
+    // inputs
+    const void *dXn, *dXc = nullptr, *dyc, *dmo, *dmn, *dbo, *dbn, *dso, *dsn, *dqo, *dqn;
+    GSUM_TRY(dev_in(c, WS_X, a->Xnew, sizeof(double) * m * d, mem_kind, &dXn));
+    if (own_cond) GSUM_TRY(dev_in(c, WS_IO0, a->Xc, sizeof(double) * n * d, mem_kind, &dXc));
+    GSUM_TRY(dev_in(c, WS_DY, a->yc, sizeof(double) * n * n_y, mem_kind, &dyc));
+    GSUM_TRY(dev_in(c, WS_REF, a->mean_old, sizeof(double) * n, mem_kind, &dmo));
+    GSUM_TRY(dev_in(c, WS_Q, a->mean_new, sizeof(double) * m, mem_kind, &dmn));
+    GSUM_TRY(dev_in(c, WS_DETF, a->basis_old, sizeof(double) * n, mem_kind, &dbo));
+    GSUM_TRY(dev_in(c, WS_ORD, a->basis_new, sizeof(double) * m, mem_kind, &dbn));
+    GSUM_TRY(dev_in(c, WS_IO1, a->sc_old, sizeof(double) * n, mem_kind, &dso));
+    GSUM_TRY(dev_in(c, WS_IO2, a->sc_new, sizeof(double) * m, mem_kind, &dsn));
+    GSUM_TRY(dev_in(c, WS_IO3, a->q_old, sizeof(double) * n, mem_kind, &dqo));
+    GSUM_TRY(dev_in(c, WS_MISC0, a->q_new, sizeof(double) * m, mem_kind, &dqn));
+    if (!a->yc) dyc = f->dy;
+    if (want_basis && (!a->basis_old || !a->basis_new)) return gsum_fail(c, -1, "gsum_predict: cond_basis_out needs basis_old and basis_new");
+
+    // scaled coordinates
+    void *dxs;
+    GSUM_TRY(gsum_ws(c, WS_XS, sizeof(double) * (m + n) * d, &dxs));
+    double *xsn = (double *)dxs, *xso = xsn + m * d;
+    scale_coords(c, (const double *)dXn, f->dls, xsn, m, d, f->ls_dim, 1);
+    const double *xs_old = f->dXS;
+    if (own_cond) { scale_coords(c, (const double *)dXc, f->dls, xso, n, d, f->ls_dim, 1); xs_old = xso; }
+
+    // conditioning factor
+    double *F;
+    if (!own_cond && !trunc) F = f->dL;
+    else {
+        void *dF;
+        GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dF));
+        F = (double *)dF;
+        if (trunc) {
+            launch_cross(c, xs_old, n, xs_old, n, d, f->constant, 0.0, 0, F, np, np, np);
+            launch_scale_cov(c, F, np, n, n, (const double *)dso, (const double *)dso, (const double *)dqo, (const double *)dqo, g, cov_factor, a->kernel_add);
+        } else {
+            // kernel_(Xc) + nugget I  (gsum/models.py:807): diagonal = (c + noise) + nugget
+            launch_cross(c, xs_old, n, xs_old, n, d, f->constant, f->noise, 1, F, np, np, np);
+            add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(F, np, n, f->nugget);
+            LAUNCHED(c, 1);
+        }
+        pad_identity_kernel<<<(unsigned)((np - n + 255) / 256 + 1), 256, 0, c->stream>>>(F, np, n);
+        LAUNCHED(c, 1);
+        int *dinfo; double *dpart;
+        GSUM_TRY(factor_bordered(c, F, n, T, 1, &dinfo, &dpart));
+        int hinfo = 0;
+        GSUM_CUDA(c, cudaMemcpyAsync(&hinfo, dinfo, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (hinfo != 0) return gsum_fail(c, hinfo, "gsum_predict: conditioning covariance is not positive definite (leading minor %d)", hinfo);
+    }
+
+    // border rows: K_no (m rows) | (yc - mean_old)^T | basis_old^T
+    const int64_t rows_pad = mp + yp;
+    void *dW;
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rows_pad * np, &dW));
+    double *W = (double *)dW, *Wy = W + mp * np;
+    launch_cross(c, xsn, m, xs_old, n, d, f->constant, 0.0, 0, W, np, mp, np);
+    if (trunc) launch_scale_cov(c, W, np, m, n, (const double *)dsn, (const double *)dso, (const double *)dqn, (const double *)dqo, g, cov_factor, a->kernel_add);
+    launch_transpose_in(c, (const double *)dyc, n, n_y, (const double *)dmo, nullptr, 0, 1.0, Wy, np, want_basis ? n_y : yp);
+    if (want_basis) launch_transpose_in(c, (const double *)dbo, n, 1, nullptr, nullptr, 0, 1.0, Wy + (int64_t)n_y * np, np, yp - n_y);
+    GSUM_TRY(chol_solve_border_run(c, solve_desc(F, W, np, T, rows_pad), 1));
+
+    // mean
+    if (a->mean_out) {
+        void *dmean;
+        GSUM_TRY(dev_out(c, WS_LL, a->mean_out, sizeof(double) * m * n_y, mem_kind, &dmean));
+        rows_dot_kernel<<<(unsigned)((m + 7) / 8), 256, 0, c->stream>>>(W, np, m, n, Wy, n_y, (const double *)dmn, 1.0, (double *)dmean, n_y);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, a->mean_out, dmean, sizeof(double) * m * n_y, mem_kind));
+    }
+    if (want_basis) {
+        void *dcb;
+        GSUM_TRY(dev_out(c, WS_MISC1, a->cond_basis_out, sizeof(double) * m, mem_kind, &dcb));
+        rows_dot_kernel<<<(unsigned)((m + 7) / 8), 256, 0, c->stream>>>(W, np, m, n, Wy + (int64_t)n_y * np, 1, (const double *)dbn, -1.0, (double *)dcb, 1);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, a->cond_basis_out, dcb, sizeof(double) * m, mem_kind));
+    }
+    const GeoSum gn = make_geosum(a->q_new, a->gs_start, a->gs_end, a->excluded, a->n_excluded);
+    const double out_factor = trunc ? 1.0 : cov_factor;
+    const double add = (a->pred_noise && !trunc) ? f->nugget : 0.0;
+    if (a->want == GSUM_PREDICT_VAR) {
+        void *dsq, *dvar;
+        GSUM_TRY(gsum_ws(c, WS_MISC2, sizeof(double) * m, &dsq));
+        GSUM_TRY(dev_out(c, WS_MISC3, a->var_out, sizeof(double) * m, mem_kind, &dvar));
+        rows_sqnorm_kernel<<<(unsigned)((m + 7) / 8), 256, 0, c->stream>>>(W, np, m, n, (double *)dsq);
+        const double diag_const = trunc ? (f->constant + a->kernel_add) : (f->constant + f->noise);
+        finish_var_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>((const double *)dsq, m, diag_const, trunc ? (const double *)dsn : nullptr,
+                                                                              trunc ? (const double *)dqn : nullptr, gn, trunc ? cov_factor : 1.0,
+                                                                              out_factor, add, (double *)dvar);
+        LAUNCHED(c, 2);
+        GSUM_TRY(dev_out_finish(c, a->var_out, dvar, sizeof(double) * m, mem_kind));
+    } else if (a->want == GSUM_PREDICT_COV) {
+        void *dC, *dcov;
+        GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * mp * mp, &dC));
+        GSUM_TRY(dev_out(c, WS_MISC3, a->var_out, sizeof(double) * m * m, mem_kind, &dcov));
+        if (trunc) {
+            launch_cross(c, xsn, m, xsn, m, d, f->constant, 0.0, 0, (double *)dC, mp, mp, mp);
+            launch_scale_cov(c, (double *)dC, mp, m, m, (const double *)dsn, (const double *)dsn, (const double *)dqn, (const double *)dqn, gn, cov_factor, a->kernel_add);
+        } else {
+            launch_cross(c, xsn, m, xsn, m, d, f->constant, f->noise, 1, (double *)dC, mp, mp, mp);
+        }
+        SchurArgs S;
+        S.W = W; S.ld = np; S.bstride = 0; S.T = T; S.C = (double *)dC; S.ldc = mp; S.cstride = 0; S.lower_only = 1;
+        GSUM_TRY(schur_run(c, S, (int)(mp / GSUM_TILE), 1));
+        cov_out_kernel<<<dim3((unsigned)m, (unsigned)((m + 255) / 256)), 256, 0, c->stream>>>((const double *)dC, mp, m, out_factor, add, (double *)dcov);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, a->var_out, dcov, sizeof(double) * m * m, mem_kind));
+    }
+    return finish(c, mem_kind);
+}
+
+extern "C" int gsum_process_cov(gsum_ctx *c, int32_t d, const double *ls, int32_t ls_dim, double constant, double noise,
+                                const double *X1, int64_t n1, const double *X2, int64_t n2, const double *sc1, const double *sc2, const double *q1, const double *q2, double gs_start,
+                                double gs_end, const int32_t *excluded, int32_t n_excluded, double factor, double kernel_add,
+                                double *out, int32_t mem_kind) {
+    if (!c || !ls || !X1 || !out || n1 <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d))
+        return gsum_fail(c, -1, "gsum_process_cov: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const bool sym = X2 == nullptr;
+    const void *dls;
+    GSUM_TRY(dev_in(c, WS_LS, ls, sizeof(double) * ls_dim, mem_kind, &dls));
+    if (sym) { n2 = n1; sc2 = sc1; q2 = q1; }
+    const void *dX1, *dX2 = nullptr, *ds1, *ds2, *dq1, *dq2;
+    GSUM_TRY(dev_in(c, WS_X, X1, sizeof(double) * n1 * d, mem_kind, &dX1));
+    if (!sym) GSUM_TRY(dev_in(c, WS_IO0, X2, sizeof(double) * n2 * d, mem_kind, &dX2));
+    GSUM_TRY(dev_in(c, WS_IO1, sc1, sizeof(double) * n1, mem_kind, &ds1));
+    GSUM_TRY(dev_in(c, WS_IO2, sc2, sizeof(double) * n2, mem_kind, &ds2));
+    GSUM_TRY(dev_in(c, WS_IO3, q1, sizeof(double) * n1, mem_kind, &dq1));
+    GSUM_TRY(dev_in(c, WS_MISC0, q2, sizeof(double) * n2, mem_kind, &dq2));
+    void *dxs, *dout;
+    GSUM_TRY(gsum_ws(c, WS_XS, sizeof(double) * (n1 + n2) * d, &dxs));
+    double *xs1 = (double *)dxs, *xs2 = xs1 + n1 * d;
+    scale_coords(c, (const double *)dX1, (const double *)dls, xs1, n1, d, ls_dim, 1);
+    if (!sym) scale_coords(c, (const double *)dX2, (const double *)dls, xs2, n2, d, ls_dim, 1);
+    GSUM_TRY(dev_out(c, WS_MAT, out, sizeof(double) * n1 * n2, mem_kind, &dout));
+    launch_cross(c, xs1, n1, sym ? xs1 : xs2, n2, d, constant, noise, sym ? 1 : 0, (double *)dout, n2, n1, n2);
+    const GeoSum g = make_geosum(q1, gs_start, gs_end, excluded, n_excluded);
+    launch_scale_cov(c, (double *)dout, n2, n1, n2, (const double *)ds1, (const double *)ds2, (const double *)dq1, (const double *)dq2, g, factor, kernel_add);
+    GSUM_TRY(dev_out_finish(c, out, dout, sizeof(double) * n1 * n2, mem_kind));
+    return finish(c, mem_kind);
+}
+
+// ---- diagnostics ---------------------------------------------------------------------------------------------
+extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, const double *mean, const double *Y,
+                                    int64_t n_curves, double *E, double *md2, int32_t mem_kind) {
+    if (!c || !L || !Y || n <= 0 || n_curves <= 0 || (!E && !md2)) return gsum_fail(c, -1, "gsum_cholesky_errors: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_curves);
+    const int T = (int)(np / GSUM_TILE);
+    const void *dL, *dmean, *dY;
+    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, mem_kind, &dL));
+    GSUM_TRY(dev_in(c, WS_REF, mean, sizeof(double) * n, mem_kind, &dmean));
+    GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * n_curves, mem_kind, &dY));
+    void *dF, *dW;
+    GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dF));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dW));
+    pad_factor(c, (const double *)dL, n, (double *)dF);
+    launch_transpose_in(c, (const double *)dY, n, n_curves, (const double *)dmean, nullptr, 0, 1.0, (double *)dW, np, rp);
+    GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    if (E) {
+        void *dE;
+        GSUM_TRY(dev_out(c, WS_IO2, E, sizeof(double) * n * n_curves, mem_kind, &dE));
+        launch_transpose_out(c, (const double *)dW, np, n, n_curves, 0, 1.0, nullptr, (double *)dE);
+        GSUM_TRY(dev_out_finish(c, E, dE, sizeof(double) * n * n_curves, mem_kind));
+    }
+    if (md2) {
+        void *dm;
+        GSUM_TRY(dev_out(c, WS_LL, md2, sizeof(double) * n_curves, mem_kind, &dm));
+        rows_sqnorm_kernel<<<(unsigned)((n_curves + 7) / 8), 256, 0, c->stream>>>((const double *)dW, np, n_curves, n, (double *)dm);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, md2, dm, sizeof(double) * n_curves, mem_kind));
+    }
+    return finish(c, mem_kind);
+}
+
+extern "C" int gsum_pivoted_cholesky(gsum_ctx *c, const double *M, int64_t n, double *Lp, int32_t *piv, int32_t *rank,
+                                     double *G_out, int32_t mem_kind) {
+    if (!c || !M || n <= 0) return gsum_fail(c, -1, "gsum_pivoted_cholesky: bad argument");
+    const size_t smem = sizeof(double) * (3 * n + PSTRF_NB + 32) + sizeof(int) * (32 + n);
+    if (smem > 220 * 1024) return gsum_fail(c, -1, "gsum_pivoted_cholesky: n = %lld exceeds the single-CTA panel limit (~8000)", (long long)n);
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    GSUM_TRY(chol_set_attrs(c));
+    GSUM_CUDA(c, cudaFuncSetAttribute(pstrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    const int64_t np = gsum_pad64(n);
+    const int T = (int)(np / GSUM_TILE);
+    const void *dM;
+    GSUM_TRY(dev_in(c, WS_IO0, M, sizeof(double) * n * n, mem_kind, &dM));
+    void *dAf, *dLb, *dpiv, *dst, *dPt;
+    GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * PSTRF_NB * np, &dPt));
+    GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dAf));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * np * np, &dLb));
+    GSUM_TRY(gsum_ws(c, WS_INFO, sizeof(int32_t) * n, &dpiv));
+    GSUM_TRY(gsum_ws(c, WS_MISC0, sizeof(PstrfState), &dst));
+    pad_in_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)np, 1), 256, 0, c->stream>>>((const double *)dM, n, (double *)dAf, np, np * np, np);
+    GSUM_CUDA(c, cudaMemsetAsync(dLb, 0, sizeof(double) * np * np, c->stream));
+    pstrf_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int32_t *)dpiv, (PstrfState *)dst, (int)n);
+    LAUNCHED(c, 2);
+    for (int k = 0; k < n; k += PSTRF_NB) {
+        pstrf_panel_kernel<<<1, PSTRF_THREADS, smem, c->stream>>>((const double *)dAf, (double *)dLb, (double *)dPt, np, (int)n, k, (int32_t *)dpiv, (PstrfState *)dst);
+        LAUNCHED(c, 1);
+        if (k + PSTRF_NB < n) {
+            // dsyrk: Af -= Lb[:, k:k+64] Lb[:, k:k+64]^T on the whole (symmetric, physically indexed) matrix
+            SchurArgs S;
+            S.W = (const double *)dLb + k; S.ld = np; S.bstride = 0; S.T = 1; S.C = (double *)dAf; S.ldc = np; S.cstride = 0; S.lower_only = 0;
+            GSUM_TRY(schur_run(c, S, T, 1));
+        }
+    }
+    PstrfState hst;
+    GSUM_CUDA(c, cudaMemcpyAsync(&hst, dst, sizeof(hst), cudaMemcpyDeviceToHost, c->stream));
+    if (Lp) {
+        void *dLp;
+        GSUM_TRY(dev_out(c, WS_IO1, Lp, sizeof(double) * n * n, mem_kind, &dLp));
+        pstrf_gather_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, c->stream>>>((const double *)dLb, np, (const int32_t *)dpiv, (int)n, (double *)dLp);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, Lp, dLp, sizeof(double) * n * n, mem_kind));
+    }
+    if (G_out) {
+        void *dG;
+        GSUM_TRY(dev_out(c, WS_IO2, G_out, sizeof(double) * n * n, mem_kind, &dG));
+        GSUM_CUDA(c, cudaMemcpy2DAsync(dG, sizeof(double) * n, dLb, sizeof(double) * np, sizeof(double) * n, n, cudaMemcpyDeviceToDevice, c->stream));
+        GSUM_TRY(dev_out_finish(c, G_out, dG, sizeof(double) * n * n, mem_kind));
+    }
+    if (piv) GSUM_CUDA(c, cudaMemcpyAsync(piv, dpiv, sizeof(int32_t) * n, mem_kind == GSUM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (rank) {
+        if (mem_kind == GSUM_MEM_HOST) *rank = hst.rank;
+        else GSUM_CUDA(c, cudaMemcpy(rank, &hst.rank, sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    GSUM_CUDA(c, cudaGetLastError());
+    if (hst.info != 0) return gsum_fail(c, 1, "M is not positive-semidefinite (pivoted Cholesky stopped at rank %d of %lld)", hst.rank, (long long)n);
+    return 0;
+}
+
+extern "C" int gsum_pc_errors(gsum_ctx *c, const double *Lp, const int32_t *piv, int64_t n, const double *mean,
+                              const double *Y, int64_t n_curves, double *E, int32_t mem_kind) {
+    if (!c || !Lp || !piv || !Y || !E || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_pc_errors: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_curves);
+    const int T = (int)(np / GSUM_TILE);
+    const void *dL, *dpiv, *dmean, *dY;
+    GSUM_TRY(dev_in(c, WS_IO0, Lp, sizeof(double) * n * n, mem_kind, &dL));
+    GSUM_TRY(dev_in(c, WS_INFO, piv, sizeof(int32_t) * n, mem_kind, &dpiv));
+    GSUM_TRY(dev_in(c, WS_REF, mean, sizeof(double) * n, mem_kind, &dmean));
+    GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * n_curves, mem_kind, &dY));
+    void *dF, *dW, *dE;
+    GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dF));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dW));
+    pad_factor(c, (const double *)dL, n, (double *)dF);
+    // solve(G, r) with G = Lp[p_inv]  <=>  Lp e = r[piv]: gather rows in pivot order, forward substitute (gsum/diagnostics.py:103-104)
+    launch_transpose_in(c, (const double *)dY, n, n_curves, (const double *)dmean, (const int32_t *)dpiv, 0, 1.0, (double *)dW, np, rp);
+    GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    GSUM_TRY(dev_out(c, WS_IO2, E, sizeof(double) * n * n_curves, mem_kind, &dE));
+    launch_transpose_out(c, (const double *)dW, np, n, n_curves, 0, 1.0, nullptr, (double *)dE);
+    GSUM_TRY(dev_out_finish(c, E, dE, sizeof(double) * n * n_curves, mem_kind));
+    return finish(c, mem_kind);
+}
+
+static int coverage_rows(gsum_ctx *c, const double *dYt, int64_t ld, int64_t n_rows, int64_t n, const double *lower, const double *upper,
+                         int n_alpha, double *coverage_out, int mem_kind) {
+    if (n_alpha < 1 || n_alpha > COVG_MAXA) return gsum_fail(c, -1, "coverage: n_alpha must be in 1..%d", COVG_MAXA);
+    const void *dlo, *dup; void *dcov;
+    GSUM_TRY(dev_in(c, WS_IO2, lower, sizeof(double) * n_alpha * n, mem_kind, &dlo));
+    GSUM_TRY(dev_in(c, WS_IO3, upper, sizeof(double) * n_alpha * n, mem_kind, &dup));
+    GSUM_TRY(dev_out(c, WS_LL, coverage_out, sizeof(double) * n_rows * n_alpha, mem_kind, &dcov));
+    const size_t smem = sizeof(double) * 2 * n_alpha * 32 + sizeof(int) * COVG_WARPS * n_alpha;
+    GSUM_CUDA(c, cudaFuncSetAttribute(coverage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    coverage_rows_kernel<<<(unsigned)((n_rows + COVG_WARPS - 1) / COVG_WARPS), COVG_WARPS * 32, smem, c->stream>>>(
+        dYt, ld, n_rows, (int)n, (const double *)dlo, (const double *)dup, n_alpha, (double *)dcov);
+    LAUNCHED(c, 1);
+    GSUM_TRY(dev_out_finish(c, coverage_out, dcov, sizeof(double) * n_rows * n_alpha, mem_kind));
+    return 0;
+}
+
+extern "C" int gsum_draws(gsum_ctx *c, const double *L, int64_t n, const double *mean, const double *Z, int64_t n_draws,
+                          uint64_t seed, double *draws_out, const double *lower, const double *upper, int32_t n_alpha,
+                          double *coverage_out, int32_t mem_kind) {
+    if (!c || !L || n <= 0 || n_draws <= 0) return gsum_fail(c, -1, "gsum_draws: bad argument");
+    if (coverage_out && (!lower || !upper)) return gsum_fail(c, -1, "gsum_draws: coverage needs lower and upper");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    GSUM_TRY(chol_set_attrs(c));
+    GSUM_CUDA(c, cudaFuncSetAttribute(draws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+    const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_draws);
+    const int T = (int)(np / GSUM_TILE);
+    const void *dL, *dmean, *dZ;
+    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, mem_kind, &dL));
+    GSUM_TRY(dev_in(c, WS_REF, mean, sizeof(double) * n, mem_kind, &dmean));
+    GSUM_TRY(dev_in(c, WS_IO1, Z, sizeof(double) * n * n_draws, mem_kind, &dZ));
+    void *dF, *dZn, *dYt;
+    GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dF));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dZn));
+    GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * rp * np, &dYt));
+    // factor with explicit zeros above the diagonal (the TRMM reads whole tiles)
+    pad_lower_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)np), 256, 0, c->stream>>>((const double *)dL, n, (double *)dF, np);
+    LAUNCHED(c, 1);
+    if (Z) launch_transpose_in(c, (const double *)dZ, n, n_draws, nullptr, nullptr, 0, -1.0, (double *)dZn, np, rp);
+    else {
+        normal_rows_kernel<<<dim3((unsigned)rp, (unsigned)((np / 2 + 255) / 256)), 256, 0, c->stream>>>((double *)dZn, np, rp, n_draws, (int)n, seed);
+        LAUNCHED(c, 1);
+    }
+    DrawArgs D;
+    D.Zn = (const double *)dZn; D.L = (const double *)dF; D.mean = (const double *)dmean; D.Yt = (double *)dYt; D.ld = np; D.n = (int)n;
+    draws_kernel<<<dim3((unsigned)T, (unsigned)(rp / GSUM_TILE)), CHOL_THREADS, CHOL_SMEM_BYTES, c->stream>>>(D);
+    LAUNCHED(c, 1);
+    if (draws_out) {
+        void *dD;
+        GSUM_TRY(dev_out(c, WS_MISC2, draws_out, sizeof(double) * n * n_draws, mem_kind, &dD));
+        launch_transpose_out(c, (const double *)dYt, np, n, n_draws, 0, 1.0, nullptr, (double *)dD);
+        GSUM_TRY(dev_out_finish(c, draws_out, dD, sizeof(double) * n * n_draws, mem_kind));
+    }
+    if (coverage_out) GSUM_TRY(coverage_rows(c, (const double *)dYt, np, n_draws, n, lower, upper, n_alpha, coverage_out, mem_kind));
+    return finish(c, mem_kind);
+}
+
+extern "C" int gsum_credible_interval(gsum_ctx *c, const double *Y, int64_t n, int64_t n_curves, const double *lower,
+                                      const double *upper, int32_t n_alpha, double *coverage_out, int32_t mem_kind) {
+    if (!c || !Y || !lower || !upper || !coverage_out || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_credible_interval: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_curves);
+    const void *dY; void *dYt;
+    GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * n_curves, mem_kind, &dY));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dYt));
+    launch_transpose_in(c, (const double *)dY, n, n_curves, nullptr, nullptr, 0, 1.0, (double *)dYt, np, rp);
+    GSUM_TRY(coverage_rows(c, (const double *)dYt, np, n_curves, n, lower, upper, n_alpha, coverage_out, mem_kind));
+    return finish(c, mem_kind);
+}

@@ -1,0 +1,664 @@
+"""Drop-in facade for the reference's conjugate-process and truncation classes (gsum/models.py).
+
+Same class names, constructor arguments, methods, fitted attributes and error behaviour as the
+reference on the hot path, but every linear-algebra step (kernel matrix, Cholesky, triangular solves,
+conjugate updates, likelihood, posterior moments) is one call into the C ABI / CUDA library — the
+Python here only marshals arguments.  What the device path does not cover raises NotImplementedError
+(`decomposition='eig'`, custom `basis`, analytic gradients, kernels other than [Constant*]RBF[+White]);
+nothing falls back to numpy/scipy.
+
+New, additive: ``TruncationProcess.log_marginal_likelihood_grid`` evaluates the whole (Q, l) grid of
+docs/notebooks/correlated_EFT_publication.ipynb cell 53 in one device call (optionally sharded over the
+ranks of a torch.distributed process group, see ``gsum_b200.distributed``).
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+from scipy.optimize import fmin_l_bfgs_b
+from sklearn.base import clone
+from sklearn.exceptions import ConvergenceWarning
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel
+from sklearn.utils import check_random_state
+
+from . import ops
+from ._lib import PREDICT_COV, PREDICT_MEAN, PREDICT_VAR
+from .helpers import _order_differences, coefficients, geometric_sum
+from .kernels import flatten_kernel
+
+__all__ = ["BaseConjugateProcess", "ConjugateGaussianProcess", "ConjugateStudentProcess", "TruncationProcess",
+           "TruncationGP", "TruncationTP"]
+
+
+def _scalar_prior(value, name):
+    a = np.asarray(value, dtype=np.float64)
+    if a.size != 1:
+        raise NotImplementedError(f"gsum_b200: only the default single-column basis is supported, so `{name}` must be scalar")
+    return float(a.reshape(-1)[0])
+
+
+class BaseConjugateProcess:
+    """Stochastic process with a normal-inverse-chi^2 conjugate prior (gsum/models.py:29-900).
+
+    Parameters are those of the reference: kernel, center, disp, df, scale, sd, basis, nugget, optimizer,
+    n_restarts_optimizer, copy_X_train, random_state, decomposition.
+    """
+
+    _student = False
+
+    def __init__(self, kernel=None, center=0, disp=0, df=1, scale=1, sd=None, basis=None, nugget=1e-10,
+                 optimizer='fmin_l_bfgs_b', n_restarts_optimizer=0, copy_X_train=True, random_state=None,
+                 decomposition='cholesky'):
+        self.kernel = kernel
+        self._center_0 = np.atleast_1d(center)
+        self._disp_0 = np.atleast_2d(disp)
+        if sd is not None:
+            self._df_0, self._scale_0 = np.inf, sd
+        else:
+            self._df_0, self._scale_0 = df, scale
+        self._fit = False
+        self.X_train_ = self.y_train_ = None
+        self.center_ = self.disp_ = self.df_ = self.scale_ = None
+        self.cov_factor_ = self.cbar_sq_mean_ = None
+        self.kernel_ = None
+        self._rng = None
+        self._handle = None
+        self._corr_L = self._corr = None
+        self.nugget = nugget
+        self.copy_X_train = copy_X_train
+        self.random_state = random_state
+        self.n_restarts_optimizer = n_restarts_optimizer
+        self.optimizer = optimizer
+        self.decomposition = decomposition
+        self._default_kernel = ConstantKernel(1.0, constant_value_bounds='fixed') * RBF(1.0, length_scale_bounds='fixed')
+        if basis is not None:
+            raise NotImplementedError("gsum_b200: a custom `basis` is not supported (the reference itself only ever "
+                                      "installs the constant basis, gsum/models.py:149-150)")
+        self.basis = lambda X: np.ones((X.shape[0], 1))
+        self.basis_train_ = None
+
+    # ---- priors (gsum/models.py:153-167) ----
+    @property
+    def center0(self):
+        return self._center_0
+
+    @property
+    def disp0(self):
+        return self._disp_0
+
+    @property
+    def df0(self):
+        return self._df_0
+
+    @property
+    def scale0(self):
+        return self._scale_0
+
+    def _priors(self):
+        return dict(center0=_scalar_prior(self._center_0, "center"), disp0=_scalar_prior(self._disp_0, "disp"),
+                    df0=float(self._df_0), scale0=float(self._scale_0))
+
+    def _check_decomposition(self):
+        if self.decomposition == 'cholesky':
+            return
+        if self.decomposition == 'eig':
+            raise NotImplementedError("gsum_b200: decomposition='eig' is not available on the device path")
+        raise ValueError('decomposition must be "cholesky" or "eig"')
+
+    def _active_kernel(self):
+        if self.kernel_ is not None:
+            return self.kernel_
+        return self._default_kernel if self.kernel is None else self.kernel
+
+    # ---- fitted quantities ----
+    @property
+    def corr_L_(self):
+        """Lower Cholesky factor of corr_ + nugget*I (fetched from the device on first access)."""
+        if self._handle is None:
+            return None
+        if self._corr_L is None:
+            self._refit(want_L=True)
+        return self._corr_L
+
+    corr_sqrt_ = corr_L_
+
+    @property
+    def corr_(self):
+        if self._handle is None:
+            return None
+        if self._corr is None:
+            k = flatten_kernel(self.kernel_)
+            self._corr = ops.kernel_matrix(self.X_train_, None, k.ls_for(self.X_train_.shape[1]), k.constant, k.noise)
+        return self._corr
+
+    def center(self):
+        """Posterior regression coefficients of the mean (gsum/models.py:505-516)."""
+        return self.center_
+
+    def disp(self):
+        return self.disp_
+
+    def df(self):
+        return self.df_
+
+    def scale(self):
+        return self.scale_
+
+    def mean(self, X):
+        """MAP mean of the process at X; does not interpolate (gsum/models.py:551-560)."""
+        center = self.center_ if self._fit else self.center0
+        return self.basis(X) @ center
+
+    def _cov_factor_and_kernel(self):
+        if not self._fit:
+            if self.df0 <= 2:
+                raise ValueError('df must be greater than 2 for the covariance to exist')
+            var = self.scale0 ** 2 if self.df0 == np.inf else self.df0 * self.scale0 ** 2 / (self.df0 - 2)
+            return var, (self._default_kernel if self.kernel is None else self.kernel)
+        return self.cov_factor_, self.kernel_
+
+    def cov(self, X, Xp=None):
+        """cov_factor * kernel(X, Xp) (gsum/models.py:562-599); not the conditional covariance."""
+        var, kernel = self._cov_factor_and_kernel()
+        X = np.atleast_2d(X)
+        k = flatten_kernel(kernel)
+        return ops.process_cov(X, Xp, k.ls_for(X.shape[1]), k.constant, k.noise, factor=var)
+
+    def underlying_properties(self, X, return_std=False, return_cov=False):
+        y_mean = self.mean(X)
+        if return_cov:
+            return y_mean, self.cov(X)
+        if return_std:
+            return y_mean, np.sqrt(np.diag(self.cov(X)))
+        return y_mean
+
+    # ---- fit (gsum/models.py:671-738) ----
+    def _refit(self, want_L=False):
+        k = flatten_kernel(self.kernel_)
+        X = np.atleast_2d(self.X_train_)
+        h = ops.FitHandle(X, self.y_train_, k.ls_for(X.shape[1]), k.constant, k.noise, self.nugget, student=self._student,
+                          want_L=want_L, **self._priors())
+        if self._handle is not None:
+            self._handle.close()
+        self._handle = h
+        if want_L:
+            self._corr_L = h.L
+        return h
+
+    def fit(self, X, y):
+        """Fit to (X, y): calibrate the kernel (if it has free hyperparameters and an optimizer is set), factor the
+        correlation matrix once on the device and update center/disp/df/scale."""
+        self._check_decomposition()
+        self.kernel_ = clone(self._default_kernel if self.kernel is None else self.kernel)
+        self._rng = check_random_state(self.random_state)
+        X, y = np.asarray(X, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        self.X_train_ = X.copy() if self.copy_X_train else X
+        self.y_train_ = y.copy() if self.copy_X_train else y
+        self.basis_train_ = self.basis(self.X_train_)
+        self._corr_L = self._corr = None
+        self._fit = False
+        self._calibrate_kernel()
+        h = self._refit()
+        self.center_ = np.array([h.center])
+        self.disp_ = np.array([[h.disp]])
+        self.df_ = h.df
+        self.scale_ = h.scale
+        self.cov_factor_ = self.cbar_sq_mean_ = h.cov_factor
+        self.log_marginal_likelihood_value_ = h.lml if self._lml_from_optimizer is None else self._lml_from_optimizer
+        self._fit = True
+        return self
+
+    def _calibrate_kernel(self):
+        """gsum/models.py:630-669.  The reference passes analytic gradients to L-BFGS; here the gradient of the device
+        objective is taken by central differences in log-theta (and the ragged-array crash of models.py:664 on
+        numpy >= 1.24 does not exist)."""
+        self._lml_from_optimizer = None
+        if self.optimizer is None or self.kernel_.n_dims == 0:
+            return
+
+        def obj_func(theta, eval_gradient=True):
+            f0 = -self.log_marginal_likelihood(theta)
+            if not eval_gradient:
+                return f0
+            grad = np.empty(len(theta))
+            h = 1e-4
+            for i in range(len(theta)):
+                tp, tm = np.array(theta, dtype=float), np.array(theta, dtype=float)
+                tp[i] += h
+                tm[i] -= h
+                grad[i] = (-self.log_marginal_likelihood(tp) + self.log_marginal_likelihood(tm)) / (2 * h)
+            return f0, grad
+
+        optima = [self._constrained_optimization(obj_func, self.kernel_.theta, self.kernel_.bounds)]
+        if self.n_restarts_optimizer > 0:
+            if not np.isfinite(self.kernel_.bounds).all():
+                raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all bounds are finite.")
+            bounds = self.kernel_.bounds
+            for _ in range(self.n_restarts_optimizer):
+                theta_initial = self._rng.uniform(bounds[:, 0], bounds[:, 1])
+                optima.append(self._constrained_optimization(obj_func, theta_initial, bounds))
+        best = int(np.argmin([o[1] for o in optima]))
+        self.kernel_.theta = optima[best][0]
+        self._lml_from_optimizer = -optima[best][1]
+
+    def _constrained_optimization(self, obj_func, initial_theta, bounds):
+        """gsum/models.py:884-900."""
+        if self.optimizer == "fmin_l_bfgs_b":
+            theta_opt, func_min, info = fmin_l_bfgs_b(obj_func, initial_theta, bounds=bounds)
+            if info["warnflag"] != 0:
+                warnings.warn("fmin_l_bfgs_b terminated abnormally with the  state: %s" % info, ConvergenceWarning)
+        elif callable(self.optimizer):
+            theta_opt, func_min = self.optimizer(obj_func, initial_theta, bounds=bounds)
+        else:
+            raise ValueError("Unknown optimizer %s." % self.optimizer)
+        return theta_opt, func_min
+
+    # ---- likelihood (gsum/models.py:912-1057 / 1184-1273) ----
+    def _lml(self, theta, eval_gradient, X, y):
+        if eval_gradient:
+            raise NotImplementedError("gsum_b200: analytic likelihood gradients are not implemented on the device path")
+        self._check_decomposition()
+        kernel = self._active_kernel().clone_with_theta(theta)
+        X = self.X_train_ if X is None else X
+        y = self.y_train_ if y is None else y
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None]
+        k = flatten_kernel(kernel)
+        ls = k.ls_for(X.shape[1])
+        ll = ops.lml_grid(X, y, 1.0, np.zeros(y.shape[1], dtype=np.int32), ls[None, :], np.ones(1), constant=k.constant,
+                          noise=k.noise, nugget=self.nugget, student=self._student, **self._priors())
+        return float(ll[0, 0])
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, X=None, y=None):
+        raise NotImplementedError
+
+    # ---- predict (gsum/models.py:753-845) ----
+    def _predict_parts(self, X, want, Xc, y, pred_noise, want_cond_basis=False):
+        """One device call: (mean (m, n_y), var|cov|None, conditional basis|None).
+
+        Xc=None conditions at the training inputs with the factor kept on the device by `fit` (gsum/models.py:797-803);
+        an explicit Xc is factored afresh with the nugget (models.py:806-809).  y=None means the y of `fit`."""
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        m = X.shape[0]
+        center = float(self.center_[0])
+        if Xc is not None and y is None:
+            y = self.y_train_
+        n_old = self.X_train_.shape[0] if Xc is None else np.atleast_2d(Xc).shape[0]
+        return self._handle.predict(X, want=want, Xc=Xc, yc=y, mean_old=np.full(n_old, center), mean_new=np.full(m, center),
+                                    basis_old=np.ones(n_old) if want_cond_basis else None,
+                                    basis_new=np.ones(m) if want_cond_basis else None,
+                                    pred_noise=pred_noise, want_cond_basis=want_cond_basis)
+
+    def predict(self, X, return_std=False, return_cov=False, Xc=None, y=None, pred_noise=False):
+        """Posterior mean / std / cov at X (gsum/models.py:753-845); the GP prior if `fit` has not been called."""
+        if return_std and return_cov:
+            raise RuntimeError('Only one of return_std or return_cov may be True')
+        if not self._fit:
+            return self.underlying_properties(X=X, return_std=return_std, return_cov=return_cov)
+        self._check_decomposition()
+        want = PREDICT_COV if return_cov else (PREDICT_VAR if return_std else PREDICT_MEAN)
+        mean, var, _ = self._predict_parts(X, want, Xc, y, pred_noise)
+        m_pred = np.squeeze(mean)
+        if return_std:
+            return m_pred, np.sqrt(var)
+        if return_cov:
+            return m_pred, np.squeeze(var)
+        return m_pred
+
+    def sample_y(self, X, n_samples=1, random_state=0, underlying=False):
+        """Draws from the (posterior or underlying) process at X (gsum/models.py:847-879).
+
+        The reference samples through numpy's SVD-based ``multivariate_normal``; here the covariance is factored
+        by the device pivoted Cholesky (rank revealing, so the singular posterior covariance at training points is
+        fine) and the draws are mean + G z on the device.  Same distribution, different random stream."""
+        rng = check_random_state(random_state)
+        if underlying:
+            y_mean, y_cov = self.underlying_properties(X=X, return_cov=True)
+        else:
+            y_mean, y_cov = self.predict(X, return_cov=True)
+        y_cov = np.atleast_2d(y_cov)
+        n = y_cov.shape[0]
+        _, Lp, piv, rank, _ = ops.pivoted_cholesky(y_cov)
+        Lp[:, rank:] = 0.0
+        inv = np.empty(n, dtype=np.int64)
+        inv[piv] = np.arange(n)
+
+        def draw(mean_vec):
+            z = rng.standard_normal((n, n_samples))
+            d, _ = ops.draws(Lp, np.zeros(n), Z=z)
+            return mean_vec[:, None] + d[inv]
+
+        if y_mean.ndim == 1:
+            return draw(y_mean)
+        return np.hstack([draw(y_mean[:, i])[:, np.newaxis] for i in range(y_mean.shape[1])])
+
+
+class ConjugateGaussianProcess(BaseConjugateProcess):
+    """Conjugacy-based Gaussian process (gsum/models.py:903-1087)."""
+
+    _student = False
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, X=None, y=None):
+        """Gaussian log-likelihood at the plug-in posterior-mean variance (gsum/models.py:912-1057)."""
+        if theta is None and self._fit:
+            if eval_gradient:
+                raise ValueError("Gradient can only be evaluated for theta!=None")
+            return self.log_marginal_likelihood_value_
+        return self._lml(theta, eval_gradient, X, y)
+
+
+class ConjugateStudentProcess(BaseConjugateProcess):
+    """Conjugacy-based Student-t process (gsum/models.py:1090-1273)."""
+
+    _student = True
+
+    def cov(self, X, Xp=None):
+        """var * (corr + B V Bᵀ) (gsum/models.py:1099-1125)."""
+        if not self._fit:
+            df, scale, disp = self.df0, self.scale0, float(self.disp0[0, 0])
+            kernel = self._default_kernel if self.kernel is None else self.kernel
+        else:
+            df, scale, disp, kernel = self.df_, self.scale_, float(self.disp_[0, 0]), self.kernel_
+        if df <= 2:
+            raise ValueError('df must be greater than 2 for the covariance to exist')
+        var = scale ** 2 if df == np.inf else df * scale ** 2 / (df - 2)
+        X = np.atleast_2d(X)
+        k = flatten_kernel(kernel)
+        return ops.process_cov(X, Xp, k.ls_for(X.shape[1]), k.constant, k.noise, factor=var, kernel_add=disp)
+
+    def predict(self, X, return_std=False, return_cov=False, Xc=None, y=None, pred_noise=False):
+        """gsum/models.py:1128-1182: the Gaussian prediction plus the mean-uncertainty term var * b V bᵀ with the
+        conditional basis b = B* - R_*o R^-1 B (std is *added*, not combined in quadrature — reference behaviour)."""
+        if return_std and return_cov:
+            raise RuntimeError('Only one of return_std or return_cov may be True')
+        if not self._fit:
+            pred = self.underlying_properties(X=X, return_std=return_std, return_cov=return_cov)
+            if not (return_std or return_cov):
+                return pred
+            disp = float(self.disp0[0, 0])
+            var = self.scale0 ** 2 if self.df0 == np.inf else self.df0 * self.scale0 ** 2 / (self.df0 - 2)
+            basis = np.ones(np.atleast_2d(X).shape[0])
+        else:
+            self._check_decomposition()
+            want = PREDICT_COV if return_cov else (PREDICT_VAR if return_std else PREDICT_MEAN)
+            mean, v, basis = self._predict_parts(X, want, Xc, y, pred_noise, want_cond_basis=return_std or return_cov)
+            m_pred = np.squeeze(mean)
+            if not (return_std or return_cov):
+                return m_pred
+            pred = (m_pred, np.sqrt(v)) if return_std else (m_pred, np.squeeze(v))
+            disp, var = float(self.disp_[0, 0]), self.cov_factor_
+        if return_std:
+            return pred[0], pred[1] + np.sqrt(var * disp * basis * basis)
+        return pred[0], pred[1] + var * disp * np.outer(basis, basis)
+
+    def log_marginal_likelihood(self, theta=None, eval_gradient=False, X=None, y=None):
+        """Exact normal-inverse-chi^2 evidence (gsum/models.py:1184-1273).  NB: like the reference, this does not
+        short-circuit on theta=None."""
+        return self._lml(theta, eval_gradient, X, y)
+
+
+class TruncationProcess:
+    """EFT truncation-error model on top of a conjugate coefficient process (gsum/models.py:1284-1507).
+
+    Parameters: kernel, ratio (scalar or callable), ref (scalar or callable), excluded, ratio_kws, and any
+    BaseConjugateProcess keyword.
+    """
+
+    _process_class = BaseConjugateProcess
+
+    def __init__(self, kernel=None, ratio=0.5, ref=1, excluded=None, ratio_kws=None, **kwargs):
+        self.ref = ref if callable(ref) else (lambda X, ref=ref: ref * np.ones(X.shape[0]))
+        self.ratio = ratio if callable(ratio) else (lambda X, ratio=ratio: ratio * np.ones(X.shape[0]))
+        self.coeffs_process = self._process_class(kernel=kernel, **kwargs)
+        self.kernel = kernel
+        self.excluded = excluded
+        self.ratio_kws = {} if ratio_kws is None else ratio_kws
+        self._fit = False
+        self.X_train_ = self.y_train_ = self.orders_ = None
+        self.dX_ = self.dy_ = None
+        self.coeffs_ = None
+
+    # ---- scaled moments of the underlying process (gsum/models.py:1337-1365) ----
+    def mean(self, X, start=0, end=np.inf):
+        coeff_mean = self.coeffs_process.mean(X=X)
+        ratio_sum = geometric_sum(x=self.ratio(X, **self.ratio_kws), start=start, end=end, excluded=self.excluded)
+        return self.ref(X) * ratio_sum * coeff_mean
+
+    def _kernel_add(self):
+        cp = self.coeffs_process
+        if not cp._student:
+            return 0.0
+        return float((cp.disp_ if cp._fit else cp.disp0)[0, 0])
+
+    def cov(self, X, Xp=None, start=0, end=np.inf):
+        cp = self.coeffs_process
+        if cp._student:
+            df = cp.df_ if cp._fit else cp.df0
+            if df <= 2:
+                raise ValueError('df must be greater than 2 for the covariance to exist')
+            scale = cp.scale_ if cp._fit else cp.scale0
+            var = scale ** 2 if df == np.inf else df * scale ** 2 / (df - 2)
+            kernel = cp.kernel_ if cp._fit else (cp._default_kernel if cp.kernel is None else cp.kernel)
+        else:
+            var, kernel = cp._cov_factor_and_kernel()
+        X = np.atleast_2d(X)
+        k = flatten_kernel(kernel)
+        q1, s1 = self.ratio(X, **self.ratio_kws), self.ref(X)
+        q2 = s2 = None
+        if Xp is not None:
+            Xp = np.atleast_2d(Xp)
+            q2, s2 = self.ratio(Xp, **self.ratio_kws), self.ref(Xp)
+        return ops.process_cov(X, Xp, k.ls_for(X.shape[1]), k.constant, k.noise, factor=var, sc1=s1, sc2=s2, q1=q1, q2=q2,
+                               gs_start=start, gs_end=end, excluded=self.excluded, kernel_add=self._kernel_add())
+
+    def basis(self, X, start=0, end=np.inf):
+        cn_basis = self.coeffs_process.basis(X=X)
+        ratio_sum = geometric_sum(x=self.ratio(X, **self.ratio_kws)[:, None], start=start, end=end, excluded=self.excluded)
+        return self.ref(X)[:, None] * ratio_sum * cn_basis
+
+    def underlying_properties(self, X, order, return_std=False, return_cov=False):
+        y_mean = self.mean(X, start=order + 1)
+        if return_cov:
+            return y_mean, self.cov(X, start=order + 1)
+        if return_std:
+            return y_mean, np.sqrt(np.diag(self.cov(X, start=order + 1)))
+        return y_mean
+
+    # ---- fit (gsum/models.py:1367-1387) ----
+    def fit(self, X, y, orders, dX=None, dy=None):
+        self.X_train_, self.y_train_, self.orders_ = X, y, orders
+        orders_mask = ~np.isin(orders, self.excluded)
+        self.dX_, self.dy_ = dX, dy
+        ratio, ref = self.ratio(X, **self.ratio_kws), self.ref(X)
+        if np.atleast_1d(ratio).ndim > 1:
+            raise ValueError('ratio must return a 1d array or a scalar')
+        if np.atleast_1d(ref).ndim > 1:
+            raise ValueError('ref must return a 1d array or a scalar')
+        self.coeffs_ = coefficients(y=y, ratio=ratio, ref=ref, orders=orders)[:, orders_mask]
+        self.coeffs_process.fit(X=X, y=self.coeffs_)
+        self._fit = True
+        return self
+
+    # ---- predict (gsum/models.py:1389-1483) ----
+    def _conditional(self, X, Xc, yc, start, end, want, want_cond_basis=False):
+        """One scaled GP conditional on the device: returns (mean (m,), var|cov|None, cond_basis|None)."""
+        cp = self.coeffs_process
+        X, Xc = np.atleast_2d(X), np.atleast_2d(Xc)
+        kw = self.ratio_kws
+        q_old, q_new = self.ratio(Xc, **kw), self.ratio(X, **kw)
+        s_old, s_new = self.ref(Xc), self.ref(X)
+        b_old = b_new = None
+        if want_cond_basis:
+            b_old, b_new = self.basis(Xc, start=start, end=end)[:, 0], self.basis(X, start=start, end=end)[:, 0]
+        mean, var, cb = cp._handle.predict(
+            X, want=want, Xc=Xc, yc=np.asarray(yc, dtype=np.float64), mean_old=self.mean(Xc, start=start, end=end),
+            mean_new=self.mean(X, start=start, end=end), basis_old=b_old, basis_new=b_new, sc_old=s_old, sc_new=s_new,
+            q_old=q_old, q_new=q_new, gs_start=start, gs_end=end, excluded=self.excluded, truncation=True,
+            want_cond_basis=want_cond_basis, kernel_add=self._kernel_add())
+        return mean[:, 0], var, cb
+
+    def _prior_part(self, X, start, end, want):
+        """Unconditioned truncation-error process: mean and (diagonal of the) covariance with Xp = X given
+        explicitly, i.e. without white noise (gsum/models.py:1460-1461, 1474-1477)."""
+        m = self.mean(X, start=start, end=end)
+        if want == PREDICT_MEAN:
+            return m, None
+        if want == PREDICT_COV:
+            return m, self.cov(X, Xp=X, start=start, end=end)
+        cp = self.coeffs_process
+        k = flatten_kernel(cp.kernel_)
+        q, s = self.ratio(X, **self.ratio_kws), self.ref(X)
+        gs = geometric_sum(q * q, start, end, self.excluded)
+        return m, ((s * s) * gs) * (cp.cov_factor_ * (k.constant + self._kernel_add()))
+
+    def predict(self, X, order, return_std=False, return_cov=False, Xc=None, y=None, pred_noise=False, kind='both'):
+        """Interpolating GP of the order-`order` partial sum plus the truncation-error GP (gsum/models.py:1389-1483).
+
+        As in the reference, K_oo carries no white noise / nugget here (kernel called with both arguments); the
+        reference solves with LU, the device path with a Cholesky factor of the same symmetric matrix."""
+        if not self._fit:
+            return self.underlying_properties(X, order, return_cov=return_cov, return_std=return_std)
+        if Xc is None:
+            Xc = self.X_train_
+        if y is None:
+            if order not in self.orders_:
+                raise ValueError('order must be in orders passed to `fit`')
+            y = self.y_train_ if self.y_train_.ndim == 1 else np.squeeze(self.y_train_[:, self.orders_ == order])
+        if kind not in ['both', 'interp', 'trunc']:
+            raise ValueError('kind must be one of "both", "interp" or "trunc"')
+        want = PREDICT_COV if return_cov else (PREDICT_VAR if return_std else PREDICT_MEAN)
+        m_pred, K_pred = 0, 0
+        if kind in ('both', 'interp'):
+            m, K, _ = self._conditional(X, Xc, y, 0, order, want)
+            m_pred = m_pred + m
+            if K is not None:
+                K_pred = K_pred + K
+        if kind in ('both', 'trunc'):
+            if self.dX_ is not None:
+                m, K, _ = self._conditional(X, self.dX_, self.dy_, order + 1, np.inf, want)
+            else:
+                m, K = self._prior_part(X, order + 1, np.inf, want)
+            m_pred = m_pred + m
+            if K is not None:
+                K_pred = K_pred + K
+        if return_cov:
+            return m_pred, K_pred
+        if return_std:
+            return m_pred, np.sqrt(K_pred)
+        return m_pred
+
+    # ---- likelihood (gsum/models.py:1485-1507) ----
+    def _grid_inputs(self, X, y, orders):
+        X = self.X_train_ if X is None else X
+        y = self.y_train_ if y is None else y
+        orders = self.orders_ if orders is None else orders
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        y = np.asarray(y, dtype=np.float64)
+        orders = np.asarray(orders)
+        if y.ndim != 2:
+            raise ValueError('y must be 2d')
+        if len(orders) != y.shape[-1]:
+            raise ValueError('partials and orders must have the same length')
+        mask = ~np.isin(orders, self.excluded)
+        dy = np.ascontiguousarray(_order_differences(y)[:, mask])
+        return X, dy, np.ascontiguousarray(orders[mask], dtype=np.int32)
+
+    def log_marginal_likelihood(self, theta, eval_gradient=False, X=None, y=None, orders=None, **ratio_kws):
+        """ll of the partial sums for kernel hyperparameters `theta` and ratio keyword(s) (gsum/models.py:1485-1507).
+
+        Like the reference, only the scalar is returned even when eval_gradient=True is requested there; here
+        eval_gradient=True raises (no analytic gradients on the device path)."""
+        if eval_gradient:
+            raise NotImplementedError("gsum_b200: analytic likelihood gradients are not implemented on the device path")
+        cp = self.coeffs_process
+        cp._check_decomposition()
+        X, dy, orders_in = self._grid_inputs(X, y, orders)
+        kernel = cp._active_kernel().clone_with_theta(theta)
+        k = flatten_kernel(kernel)
+        ref = np.asarray(self.ref(X), dtype=np.float64)
+        ratio = np.asarray(self.ratio(X, **ratio_kws), dtype=np.float64)
+        det_factor = np.sum(len(orders_in) * np.log(np.abs(ref)) + np.sum(orders_in) * np.log(np.abs(ratio)))
+        ll = ops.lml_grid(X, dy, ref, orders_in, k.ls_for(X.shape[1])[None, :], ratio[None, :], q_x_dependent=True,
+                          detf=np.array([det_factor]), constant=k.constant, noise=k.noise, nugget=cp.nugget,
+                          student=cp._student, **cp._priors())
+        return float(ll[0, 0])
+
+    def log_marginal_likelihood_grid(self, ls_vals, ratio_vals=None, ratio_kws_list=None, X=None, y=None, orders=None,
+                                     group=None, return_status=False):
+        """The whole (Q, l) likelihood surface in one device call — what the nested list comprehension of
+        docs/notebooks/correlated_EFT_publication.ipynb cell 53 computes cell by cell.
+
+        ls_vals : (n_ls,) or (n_ls, d) length scales (the kernel's other hyperparameters stay as they are).
+        ratio_vals : (n_q,) scalar expansion parameters (each length scale is factored once and reused for every Q), or
+        ratio_kws_list : list of keyword dicts for a callable `ratio` (x-dependent Q: one right-hand-side block per entry).
+        group : optional torch.distributed process group; the length scales are then sharded round-robin over its
+            ranks and the blocks all-gathered (see gsum_b200.distributed.lml_grid_sharded).
+        Returns ll with shape (n_q, n_ls), i.e. ``ll[i_ratio][i_ls]`` as in the notebook.
+        """
+        cp = self.coeffs_process
+        cp._check_decomposition()
+        X, dy, orders_in = self._grid_inputs(X, y, orders)
+        n = X.shape[0]
+        k = flatten_kernel(cp._active_kernel())
+        ls = np.asarray(ls_vals, dtype=np.float64)
+        ls = ls.reshape(ls.shape[0], -1)
+        if ls.shape[1] not in (1, X.shape[1]):
+            raise ValueError("ls_vals must have shape (n_ls,) or (n_ls, n_features)")
+        ref = np.asarray(self.ref(X), dtype=np.float64)
+        n_c, so = len(orders_in), float(np.sum(orders_in))
+        if (ratio_vals is None) == (ratio_kws_list is None):
+            raise ValueError("give exactly one of ratio_vals and ratio_kws_list")
+        if ratio_vals is not None:
+            Q = np.asarray(ratio_vals, dtype=np.float64)
+            detf = np.sum(n_c * np.log(np.abs(ref))) + n * so * np.log(np.abs(Q))
+            xdep = False
+        else:
+            Q = np.stack([np.asarray(self.ratio(X, **kw), dtype=np.float64) for kw in ratio_kws_list])
+            detf = np.sum(n_c * np.log(np.abs(ref))) + so * np.sum(np.log(np.abs(Q)), axis=1)
+            xdep = True
+        kw = dict(q_x_dependent=xdep, detf=detf, constant=k.constant, noise=k.noise, nugget=cp.nugget, student=cp._student,
+                  **cp._priors())
+        if group is not None:
+            from .distributed import lml_grid_sharded
+            return lml_grid_sharded(X, dy, ref, orders_in, ls, Q, group=group, **kw)
+        return ops.lml_grid(X, dy, ref, orders_in, ls, Q, return_status=return_status, **kw)
+
+
+class TruncationGP(TruncationProcess):
+    """Gaussian-process truncation model (gsum/models.py:1510-1516)."""
+    _process_class = ConjugateGaussianProcess
+
+
+class TruncationTP(TruncationProcess):
+    """Student-t-process truncation model (gsum/models.py:1519-1570)."""
+    _process_class = ConjugateStudentProcess
+
+    def predict(self, X, order, return_std=False, return_cov=False, Xc=None, y=None, pred_noise=False, kind='both'):
+        """gsum/models.py:1527-1570.  As in the reference, the Gaussian part is always evaluated with kind='both'
+        (the reference does not forward `kind` to the parent) and the mean-uncertainty std is added linearly."""
+        pred = super().predict(X=X, order=order, return_std=return_std, return_cov=return_cov, Xc=Xc, y=y,
+                               pred_noise=pred_noise)
+        if not return_std and not return_cov:
+            return pred
+        if Xc is None:
+            Xc = self.X_train_
+        cp = self.coeffs_process
+        var, disp = cp.cov_factor_, float(cp.disp_[0, 0])
+        m = np.atleast_2d(X).shape[0]
+        basis_lower, basis_trunc = np.zeros(m), np.zeros(m)
+        if kind in ('both', 'interp'):
+            yy = np.zeros(np.atleast_2d(Xc).shape[0])
+            _, _, basis_lower = self._conditional(X, Xc, yy, 0, order, PREDICT_MEAN, want_cond_basis=True)
+        if kind in ('both', 'trunc'):
+            if self.dX_ is not None:
+                yy = np.zeros(np.atleast_2d(self.dX_).shape[0])
+                _, _, basis_trunc = self._conditional(X, self.dX_, yy, order + 1, np.inf, PREDICT_MEAN, want_cond_basis=True)
+            else:
+                basis_trunc = self.basis(start=order + 1, end=np.inf, X=X)[:, 0]
+        b = basis_lower + basis_trunc
+        if return_std:
+            return pred[0], pred[1] + np.sqrt(var * disp * b * b)
+        return pred[0], pred[1] + var * disp * np.outer(b, b)

@@ -1,0 +1,352 @@
+"""numpy-in / numpy-out wrappers over the C ABI (one function per exported entry point).
+
+These are the calls the facade classes in ``models.py`` / ``diagnostics.py`` make and the calls the
+parity tests exercise.  Every array crosses as a host pointer (``GSUM_MEM_HOST``); ``*_device`` variants
+take torch CUDA tensors and enqueue on the context's stream.  No numerical work happens in Python here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import MEM_DEVICE, MEM_HOST, PREDICT_COV, PREDICT_MEAN, PREDICT_VAR, as_f64, default_context
+
+__all__ = [
+    "kernel_matrix", "cholesky", "cho_solve", "lml_grid", "grid_normalize", "FitHandle", "process_cov",
+    "cholesky_errors", "pivoted_cholesky", "pc_errors", "draws", "credible_interval",
+]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _vec(a, n, name):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,)))
+    if a.shape != (n,):
+        raise ValueError(f"{name} must have shape ({n},)")
+    return a
+
+
+def kernel_matrix(X1, X2, length_scale, constant=1.0, noise=0.0, ctx=None):
+    """c * RBF(X1, X2) (+ noise on the diagonal when X2 is None) — sklearn kernel ``__call__``."""
+    ctx = ctx or default_context()
+    X1 = as_f64(np.atleast_2d(X1))
+    n1, d = X1.shape
+    ls = np.ascontiguousarray(np.atleast_1d(length_scale), dtype=np.float64)
+    if X2 is None:
+        out = np.empty((n1, n1))
+        rc = ctx.lib.gsum_kernel_matrix(ctx.handle, _p(X1), n1, None, 0, d, _p(ls), ls.shape[0], constant, noise, _p(out), MEM_HOST)
+    else:
+        X2 = as_f64(np.atleast_2d(X2))
+        out = np.empty((n1, X2.shape[0]))
+        rc = ctx.lib.gsum_kernel_matrix(ctx.handle, _p(X1), n1, _p(X2), X2.shape[0], d, _p(ls), ls.shape[0], constant, noise,
+                                        _p(out), MEM_HOST)
+    ctx.check(rc, "gsum_kernel_matrix")
+    return out
+
+
+def cholesky(A, return_info=False, ctx=None):
+    """Lower Cholesky factor(s) of A (n,n) or (batch,n,n) — ``numpy.linalg.cholesky``.
+
+    Raises numpy.linalg.LinAlgError like numpy unless ``return_info`` (then returns L, info, logdet).
+    """
+    ctx = ctx or default_context()
+    A = np.asarray(A)
+    single = A.ndim == 2
+    L = as_f64(A[None] if single else A, copy=True)
+    batch, n, _ = L.shape
+    info = np.zeros(batch, dtype=np.int32)
+    logdet = np.zeros(batch)
+    ctx.check(ctx.lib.gsum_cholesky(ctx.handle, _p(L), n, batch, _p(info), _p(logdet), MEM_HOST), "gsum_cholesky")
+    if return_info:
+        return (L[0], info[0], logdet[0]) if single else (L, info, logdet)
+    if info.any():
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+    return L[0] if single else L
+
+
+def cho_solve(L, B, forward_only=False, ctx=None):
+    """``scipy.linalg.cho_solve((L, True), B)`` or, with forward_only, ``solve_triangular(L, B, lower=True)``."""
+    ctx = ctx or default_context()
+    L = as_f64(L)
+    B = np.asarray(B, dtype=np.float64)
+    vec = B.ndim == 1
+    X = as_f64(B[:, None] if vec else B, copy=True)
+    n, k = X.shape
+    ctx.check(ctx.lib.gsum_cho_solve(ctx.handle, _p(L), n, _p(X), k, 1 if forward_only else 0, MEM_HOST), "gsum_cho_solve")
+    return X[:, 0] if vec else X
+
+
+def lml_grid(X, dy, ref, orders, ls, Q, q_x_dependent=False, detf=None, constant=1.0, noise=0.0, nugget=1e-10,
+             center0=0.0, disp0=0.0, df0=1.0, scale0=1.0, student=False, return_status=False, ctx=None):
+    """The (Q, l) log-marginal-likelihood grid: returns ll with shape (n_q, n_ls) (``[ratio][ls]``)."""
+    ctx = ctx or default_context()
+    X = as_f64(np.atleast_2d(X))
+    n, d = X.shape
+    dy = as_f64(dy)
+    n_c = dy.shape[1]
+    ref = _vec(ref, n, "ref")
+    orders = np.ascontiguousarray(orders, dtype=np.int32)
+    ls = as_f64(np.asarray(ls, dtype=np.float64).reshape(len(ls), -1))
+    n_ls, ls_dim = ls.shape
+    Q = as_f64(Q)
+    if q_x_dependent:
+        if Q.ndim != 2 or Q.shape[1] != n:
+            raise ValueError("x-dependent Q must have shape (n_q, n)")
+    elif Q.ndim != 1:
+        raise ValueError("scalar Q must have shape (n_q,)")
+    n_q = Q.shape[0]
+    detf = None if detf is None else _vec(detf, n_q, "detf")
+    ll = np.empty((n_q, n_ls))
+    logdet = np.empty(n_ls)
+    status = np.zeros(n_ls, dtype=np.int32)
+    rc = ctx.lib.gsum_lml_grid(ctx.handle, _p(X), n, d, _p(dy), n_c, _p(ref), _p(orders), _p(ls), n_ls, ls_dim, _p(Q), n_q,
+                               1 if q_x_dependent else 0, _p(detf), float(constant), float(noise), float(nugget),
+                               float(center0), float(disp0), float(df0), float(scale0), 1 if student else 0, _p(ll),
+                               _p(logdet), _p(status), MEM_HOST)
+    ctx.check(rc, "gsum_lml_grid")
+    return (ll, logdet, status) if return_status else ll
+
+
+def grid_normalize(ll, ctx=None):
+    """exp(ll - max) and logsumexp(ll) on the device."""
+    ctx = ctx or default_context()
+    ll = as_f64(ll)
+    post = np.empty_like(ll)
+    lse = np.zeros(1)
+    ctx.check(ctx.lib.gsum_grid_normalize(ctx.handle, _p(ll), ll.size, _p(post), _p(lse), MEM_HOST), "gsum_grid_normalize")
+    return post, float(lse[0])
+
+
+class _PredictArgs(C.Structure):
+    _fields_ = [
+        ("Xnew", C.c_void_p), ("m", C.c_int64), ("Xc", C.c_void_p), ("n_cond", C.c_int64), ("yc", C.c_void_p), ("n_y", C.c_int32),
+        ("mean_old", C.c_void_p), ("mean_new", C.c_void_p), ("basis_old", C.c_void_p), ("basis_new", C.c_void_p),
+        ("sc_old", C.c_void_p), ("sc_new", C.c_void_p), ("q_old", C.c_void_p), ("q_new", C.c_void_p),
+        ("gs_start", C.c_double), ("gs_end", C.c_double), ("excluded", C.c_void_p), ("n_excluded", C.c_int32),
+        ("kernel_add", C.c_double), ("truncation", C.c_int32), ("want", C.c_int32), ("pred_noise", C.c_int32),
+        ("mean_out", C.c_void_p), ("var_out", C.c_void_p), ("cond_basis_out", C.c_void_p),
+    ]
+
+
+class FitHandle:
+    """Device-resident fit (``gsum_fit``): X, y and the lower factor stay in HBM between predict calls."""
+
+    def __init__(self, X, y, length_scale, constant=1.0, noise=0.0, nugget=1e-10, center0=0.0, disp0=0.0, df0=1.0,
+                 scale0=1.0, student=False, want_L=False, ctx=None):
+        self.ctx = ctx or default_context()
+        X = as_f64(np.atleast_2d(X))
+        y = as_f64(y if np.ndim(y) == 2 else np.asarray(y)[:, None])
+        self.n, self.d = X.shape
+        self.n_c = y.shape[1]
+        ls = np.ascontiguousarray(np.atleast_1d(length_scale), dtype=np.float64)
+        out7 = np.zeros(7)
+        L = np.empty((self.n, self.n)) if want_L else None
+        h = C.c_void_p()
+        rc = self.ctx.lib.gsum_fit_create(self.ctx.handle, _p(X), self.n, self.d, _p(y), self.n_c, _p(ls), ls.shape[0],
+                                          float(constant), float(noise), float(nugget), float(center0), float(disp0),
+                                          float(df0), float(scale0), 1 if student else 0, _p(out7), _p(L), MEM_HOST,
+                                          C.byref(h))
+        rc = self.ctx.check(rc, "gsum_fit_create")
+        if rc > 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        self.handle = h
+        self.center, self.disp, self.df, self.scale, self.cov_factor, self.lml, self.logdet = (float(v) for v in out7)
+        self.L = L
+        self.kernel_args = (ls, float(constant), float(noise))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.ctx.lib.gsum_fit_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def predict(self, Xnew, want=PREDICT_MEAN, Xc=None, yc=None, mean_old=None, mean_new=None, basis_old=None,
+                basis_new=None, sc_old=None, sc_new=None, q_old=None, q_new=None, gs_start=0.0, gs_end=np.inf,
+                excluded=None, truncation=False, pred_noise=False, want_cond_basis=False, kernel_add=0.0):
+        """One GP conditional (see ``gsum_predict_args`` in include/gsum_b200.h).  Returns (mean, var_or_cov, cond_basis)."""
+        Xnew = as_f64(np.atleast_2d(Xnew))
+        m = Xnew.shape[0]
+        a = _PredictArgs()
+        keep = [Xnew]
+        a.Xnew, a.m = _p(Xnew), m
+        n = self.n
+        if Xc is not None:
+            Xc = as_f64(np.atleast_2d(Xc))
+            n = Xc.shape[0]
+            a.Xc, a.n_cond = _p(Xc), n
+            keep.append(Xc)
+        n_y = self.n_c
+        if yc is not None:
+            yc = as_f64(yc if np.ndim(yc) == 2 else np.asarray(yc, dtype=np.float64)[:, None])
+            if yc.shape[0] != n:
+                raise ValueError("conditioning y must have one row per conditioning point")
+            n_y = yc.shape[1]
+            a.yc, a.n_y = _p(yc), n_y
+            keep.append(yc)
+        elif Xc is not None:
+            raise ValueError("y must be given together with Xc")
+
+        def vec(v, length, name):
+            v = _vec(v, length, name)
+            if v is not None:
+                keep.append(v)
+            return _p(v)
+
+        a.mean_old, a.mean_new = vec(mean_old, n, "mean_old"), vec(mean_new, m, "mean_new")
+        a.basis_old, a.basis_new = vec(basis_old, n, "basis_old"), vec(basis_new, m, "basis_new")
+        a.sc_old, a.sc_new = vec(sc_old, n, "sc_old"), vec(sc_new, m, "sc_new")
+        a.q_old, a.q_new = vec(q_old, n, "q_old"), vec(q_new, m, "q_new")
+        a.gs_start, a.gs_end = float(gs_start), float(gs_end)
+        if excluded is not None:
+            ex = np.ascontiguousarray(np.atleast_1d(excluded), dtype=np.int32)
+            if ex.size > 8:
+                raise NotImplementedError("gsum_b200: at most 8 excluded orders")
+            a.excluded, a.n_excluded = _p(ex), ex.size
+            keep.append(ex)
+        a.kernel_add = float(kernel_add)
+        a.truncation, a.want, a.pred_noise = int(bool(truncation)), int(want), int(bool(pred_noise))
+        mean = np.empty((m, n_y))
+        a.mean_out = _p(mean)
+        var = None
+        if want == PREDICT_VAR:
+            var = np.empty(m)
+        elif want == PREDICT_COV:
+            var = np.empty((m, m))
+        a.var_out = _p(var)
+        cb = np.empty(m) if want_cond_basis else None
+        a.cond_basis_out = _p(cb)
+        rc = self.ctx.check(self.ctx.lib.gsum_predict(self.ctx.handle, self.handle, C.byref(a), MEM_HOST), "gsum_predict")
+        if rc > 0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        return mean, var, cb
+
+
+def process_cov(X1, X2, length_scale, constant=1.0, noise=0.0, factor=1.0, sc1=None, sc2=None, q1=None, q2=None,
+                gs_start=0.0, gs_end=np.inf, excluded=None, kernel_add=0.0, ctx=None):
+    """factor * (kernel(X1, X2) + kernel_add) with the truncation scalings (gsum/models.py:562-599, 1342-1348)."""
+    ctx = ctx or default_context()
+    X1 = as_f64(np.atleast_2d(X1))
+    n1, d = X1.shape
+    ls = np.ascontiguousarray(np.atleast_1d(length_scale), dtype=np.float64)
+    X2c = None if X2 is None else as_f64(np.atleast_2d(X2))
+    n2 = n1 if X2c is None else X2c.shape[0]
+    sc1, q1 = _vec(sc1, n1, "sc1"), _vec(q1, n1, "q1")
+    sc2, q2 = (None, None) if X2c is None else (_vec(sc2, n2, "sc2"), _vec(q2, n2, "q2"))
+    ex = None if excluded is None else np.ascontiguousarray(np.atleast_1d(excluded), dtype=np.int32)
+    out = np.empty((n1, n2))
+    rc = ctx.lib.gsum_process_cov(ctx.handle, d, _p(ls), ls.shape[0], float(constant), float(noise), _p(X1), n1, _p(X2c), n2,
+                                  _p(sc1), _p(sc2), _p(q1), _p(q2), float(gs_start), float(gs_end), _p(ex),
+                                  0 if ex is None else ex.size, float(factor), float(kernel_add), _p(out), MEM_HOST)
+    ctx.check(rc, "gsum_process_cov")
+    return out
+
+
+def cholesky_errors(L, mean, Y, want_errors=True, want_md2=False, ctx=None):
+    """L^{-1}(Y - mean) for Y (n, n_curves) and/or the squared Mahalanobis distances (n_curves,)."""
+    ctx = ctx or default_context()
+    L = as_f64(L)
+    n = L.shape[0]
+    Y = as_f64(Y)
+    mean = _vec(mean, n, "mean")
+    E = np.empty_like(Y) if want_errors else None
+    md2 = np.empty(Y.shape[1]) if want_md2 else None
+    ctx.check(ctx.lib.gsum_cholesky_errors(ctx.handle, _p(L), n, _p(mean), _p(Y), Y.shape[1], _p(E), _p(md2), MEM_HOST),
+              "gsum_cholesky_errors")
+    return E, md2
+
+
+def pivoted_cholesky(M, ctx=None):
+    """LAPACK dpstrf(lower) on the device: returns (G, Lp, piv, rank, status); M = G G^T, P^T M P = Lp Lp^T."""
+    ctx = ctx or default_context()
+    M = as_f64(M)
+    n = M.shape[0]
+    Lp, G = np.empty((n, n)), np.empty((n, n))
+    piv = np.zeros(n, dtype=np.int32)
+    rank = C.c_int32(0)
+    rc = ctx.check(ctx.lib.gsum_pivoted_cholesky(ctx.handle, _p(M), n, _p(Lp), _p(piv), C.addressof(rank), _p(G), MEM_HOST),
+                   "gsum_pivoted_cholesky")
+    return G, Lp, piv, int(rank.value), rc
+
+
+def pc_errors(Lp, piv, mean, Y, ctx=None):
+    """solve(G, Y - mean) with G = Lp[p_inv] by permutation + forward substitution."""
+    ctx = ctx or default_context()
+    Lp = as_f64(Lp)
+    n = Lp.shape[0]
+    Y = as_f64(Y)
+    piv = np.ascontiguousarray(piv, dtype=np.int32)
+    mean = _vec(mean, n, "mean")
+    E = np.empty_like(Y)
+    ctx.check(ctx.lib.gsum_pc_errors(ctx.handle, _p(Lp), _p(piv), n, _p(mean), _p(Y), Y.shape[1], _p(E), MEM_HOST), "gsum_pc_errors")
+    return E
+
+
+def draws(L, mean, Z=None, n_draws=None, seed=0, lower=None, upper=None, want_draws=True, ctx=None):
+    """mean + L z for caller-supplied Z (n, n_draws) or device Philox normals; optional fused coverage.
+
+    Returns (draws (n, n_draws) or None, coverage (n_draws, n_alpha) or None)."""
+    ctx = ctx or default_context()
+    L = as_f64(L)
+    n = L.shape[0]
+    mean = _vec(mean, n, "mean")
+    if Z is not None:
+        Z = as_f64(Z)
+        n_draws = Z.shape[1]
+    if not n_draws:
+        raise ValueError("n_draws must be given when Z is None")
+    out = np.empty((n, n_draws)) if want_draws else None
+    cov, n_alpha = None, 0
+    if lower is not None:
+        lower, upper = as_f64(np.atleast_2d(lower)), as_f64(np.atleast_2d(upper))
+        n_alpha = lower.shape[0]
+        cov = np.empty((n_draws, n_alpha))
+    ctx.check(ctx.lib.gsum_draws(ctx.handle, _p(L), n, _p(mean), _p(Z), n_draws, int(seed), _p(out), _p(lower), _p(upper),
+                                 n_alpha, _p(cov), MEM_HOST), "gsum_draws")
+    return out, cov
+
+
+def credible_interval(Y, lower, upper, ctx=None):
+    """Coverage (n_curves, n_alpha) of curves Y (n, n_curves) for interval bounds lower/upper (n_alpha, n)."""
+    ctx = ctx or default_context()
+    Y = as_f64(Y)
+    n, k = Y.shape
+    lower, upper = as_f64(np.atleast_2d(lower)), as_f64(np.atleast_2d(upper))
+    out = np.empty((k, lower.shape[0]))
+    ctx.check(ctx.lib.gsum_credible_interval(ctx.handle, _p(Y), n, k, _p(lower), _p(upper), lower.shape[0], _p(out), MEM_HOST),
+              "gsum_credible_interval")
+    return out
+
+
+def lml_grid_device(ctx, X, dy, ref, orders, ls, Q, detf, ll_out, q_x_dependent=False, constant=1.0, noise=0.0,
+                    nugget=1e-10, center0=0.0, disp0=0.0, df0=1.0, scale0=1.0, student=False, logdet_out=None,
+                    status_out=None):
+    """Device-resident variant of :func:`lml_grid`: every argument is a contiguous torch CUDA tensor on the context's
+    device (float64; `orders` / `status_out` int32) and the call only enqueues work on the context's stream."""
+    n, d = X.shape
+    n_c = dy.shape[1]
+    n_ls, ls_dim = ls.shape
+    n_q = Q.shape[0]
+    rc = ctx.lib.gsum_lml_grid(ctx.handle, X.data_ptr(), n, d, dy.data_ptr(), n_c, ref.data_ptr(), orders.data_ptr(),
+                               ls.data_ptr(), n_ls, ls_dim, Q.data_ptr(), n_q, 1 if q_x_dependent else 0,
+                               None if detf is None else detf.data_ptr(), float(constant), float(noise), float(nugget),
+                               float(center0), float(disp0), float(df0), float(scale0), 1 if student else 0,
+                               ll_out.data_ptr(), None if logdet_out is None else logdet_out.data_ptr(),
+                               None if status_out is None else status_out.data_ptr(), MEM_DEVICE)
+    ctx.check(rc, "gsum_lml_grid")
+    return ll_out
+
+
+def grid_normalize_device(ctx, ll, post_out, lse_out):
+    ctx.check(ctx.lib.gsum_grid_normalize(ctx.handle, ll.data_ptr(), ll.numel(), post_out.data_ptr(), lse_out.data_ptr(),
+                                          MEM_DEVICE), "gsum_grid_normalize")

@@ -1,0 +1,190 @@
+/* gsum_b200 — C ABI of the B200-native conjugate-GP likelihood / prediction / diagnostics path.
+ *
+ * The reference (buqeye/gsum) is pure Python and has no FFI of its own: its hot path calls
+ * numpy.linalg / scipy.linalg / LAPACK / scikit-learn kernels directly.  Each entry point below replaces
+ * one family of those call sites (cited per function, paths relative to the reference checkout) and is
+ * what a ctypes binding inside gsum/models.py, gsum/helpers.py and gsum/diagnostics.py would bind (see
+ * INTEGRATION.md for the stubs).
+ *
+ * Conventions
+ *   - C linkage, plain C types only.  All matrices are FP64, row-major (numpy C order), contiguous.
+ *   - The caller owns every buffer passed in or out.  `mem_kind` says where they live:
+ *       GSUM_MEM_HOST    host pointers (numpy); the call copies in/out and returns after the result landed.
+ *       GSUM_MEM_DEVICE  device pointers on the context's GPU (torch .data_ptr()); the call only enqueues
+ *                        work on the context's stream and returns without synchronising.
+ *   - Return value: 0 ok; < 0 invalid argument / CUDA failure (reference: ValueError); > 0 numerical
+ *     failure (reference: numpy.linalg.LinAlgError), e.g. the 1-based index of the first non-positive
+ *     pivot.  gsum_last_error() returns a message for the last non-zero return on that context.
+ *   - A context is bound to one device and one stream and is not thread-safe; distinct contexts are
+ *     independent.  Nothing here falls back to the CPU: without a CUDA device every call fails.
+ */
+#ifndef GSUM_B200_H
+#define GSUM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSUM_MEM_HOST 0
+#define GSUM_MEM_DEVICE 1
+
+#define GSUM_PREDICT_MEAN 0
+#define GSUM_PREDICT_VAR 1
+#define GSUM_PREDICT_COV 2
+
+typedef struct gsum_ctx gsum_ctx;
+typedef struct gsum_fit gsum_fit;
+
+/* ABI version (major*100 + minor). */
+int gsum_version(void);
+
+/* Context: device + stream (+ ctx-scoped workspaces).  `cuda_stream` may be NULL (a private stream is created). */
+int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out);
+int gsum_ctx_destroy(gsum_ctx *ctx);
+int gsum_ctx_synchronize(gsum_ctx *ctx);
+const char *gsum_last_error(const gsum_ctx *ctx);
+/* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
+int64_t gsum_launch_count(const gsum_ctx *ctx);
+
+/* Optional profiling of the factorisation phase (K2+K3: every launch of the bordered Cholesky), used by bench.py for
+ * the roofline: CUDA events are recorded on the context's stream around each factorisation while enabled.
+ * gsum_ctx_profile_read synchronises, returns the summed device time (ms), the algorithmic flops of the bracketed work
+ * (batch * (N^3/3 + N^2 * rhs)) and the number of brackets, and resets the counters. */
+int gsum_ctx_profile(gsum_ctx *ctx, int enable);
+int gsum_ctx_profile_read(gsum_ctx *ctx, double *ms_total, double *flops_total, int64_t *n_brackets);
+
+/* K1 — kernel matrix  c * RBF_ls(X1, X2) [+ noise on the diagonal when X2 == NULL].
+ * Replaces sklearn kernel __call__ at gsum/models.py:599,708,807,822-824,960 (RBF, ConstantKernel*RBF,
+ * ... + WhiteKernel).  X1 (n1,d), X2 (n2,d) or NULL (symmetric k(X1), diagonal = c + noise exactly);
+ * ls (ls_dim,) with ls_dim in {1, d}; out (n1, n2 or n1). */
+int gsum_kernel_matrix(gsum_ctx *ctx, const double *X1, int64_t n1, const double *X2, int64_t n2, int32_t d,
+                       const double *ls, int32_t ls_dim, double constant, double noise, double *out,
+                       int32_t mem_kind);
+
+/* K2 — batched lower Cholesky, in place: A (batch, n, n) symmetric in -> L in the lower triangle, zeros above.
+ * Replaces numpy.linalg.cholesky at gsum/models.py:711,809,969,1211 and gsum/diagnostics.py:60.
+ * info (batch,) int32: 0 or the 1-based column of the first non-positive pivot (LAPACK potrf); logdet (batch,)
+ * = 2 * sum(log(diag L)) or NULL.  Returns 0 even if some matrices failed (inspect info). */
+int gsum_cholesky(gsum_ctx *ctx, double *A, int64_t n, int64_t batch, int32_t *info, double *logdet,
+                  int32_t mem_kind);
+
+/* K3 — triangular solves with the lower factor L (n,n), B (n, nrhs) overwritten:
+ *   forward_only != 0 :  B <- L^{-1} B        (scipy.linalg.solve_triangular(lower=True), gsum/helpers.py:505)
+ *   forward_only == 0 :  B <- L^{-T} L^{-1} B (scipy.linalg.cho_solve, gsum/models.py:479) */
+int gsum_cho_solve(gsum_ctx *ctx, const double *L, int64_t n, double *B, int64_t nrhs, int32_t forward_only,
+                   int32_t mem_kind);
+
+/* K1-K4 fused — the (Q, l) log-marginal-likelihood grid.
+ * Replaces the nested loop of docs/notebooks/correlated_EFT_publication.ipynb cell 53 over
+ * TruncationProcess.log_marginal_likelihood (gsum/models.py:1485-1507) ->
+ * ConjugateGaussianProcess / ConjugateStudentProcess.log_marginal_likelihood (models.py:912-1057 / 1184-1273)
+ * -> coefficients (helpers.py:71-101), compute_center/disp/df/scale_sq/cov_factor (models.py:169-503).
+ *
+ *   X (n,d); dy (n,n_c) = [y_0, diff(y)] of the retained orders (NOT yet divided by ref / Q**order);
+ *   ref (n,); orders (n_c,) the integer powers; ls (n_ls, ls_dim);
+ *   q_x_dependent == 0: Q (n_q,) scalar ratios — each length scale is factored once and its Gram is reused
+ *                       for every Q;  != 0: Q (n_q, n) ratio evaluated at every x (one RHS block per Q);
+ *   detf (n_q,) or NULL: the Jacobian sum_x [n_c log|ref| + sum(orders) log|Q|] subtracted per Q (models.py:1503-1506);
+ *   kernel = constant * RBF(ls) + noise * I, diagonal += nugget (models.py:963);
+ *   priors center0/disp0/df0/scale0 (df0 may be INFINITY); student != 0 selects the Student-t evidence.
+ * Outputs: ll (n_q, n_ls) — `[ratio][ls]` as in the notebook; logdet (n_ls,) or NULL; status (n_ls,) or NULL
+ * (non-zero where the Cholesky failed; those cells are -inf as in models.py:970-972). */
+int gsum_lml_grid(gsum_ctx *ctx, const double *X, int64_t n, int32_t d, const double *dy, int32_t n_c,
+                  const double *ref, const int32_t *orders, const double *ls, int64_t n_ls, int32_t ls_dim,
+                  const double *Q, int64_t n_q, int32_t q_x_dependent, const double *detf, double constant,
+                  double noise, double nugget, double center0, double disp0, double df0, double scale0,
+                  int32_t student, double *ll, double *logdet, int32_t *status, int32_t mem_kind);
+
+/* On-device normalisation of a gathered grid (docs/notebooks/correlated_EFT_publication.ipynb cell 54):
+ * post = exp(ll - max(ll)); lse = log(sum(exp(ll))).  ll, post: (count,); lse: 1 double or NULL. */
+int gsum_grid_normalize(gsum_ctx *ctx, const double *ll, int64_t count, double *post, double *lse, int32_t mem_kind);
+
+/* fit with fixed kernel hyperparameters (gsum/models.py:671-738, optimizer=None / 'fixed' bounds):
+ * factor R = c*RBF(X) + (noise + nugget) I once, keep X, y, L resident on the device, return the posterior
+ * hyperparameters out7 = [center, disp, df, scale, cov_factor, log_marginal_likelihood, logdet R].
+ * L_out (n,n) or NULL receives corr_L_.  Returns > 0 (LinAlgError) if R is not positive definite. */
+int gsum_fit_create(gsum_ctx *ctx, const double *X, int64_t n, int32_t d, const double *y, int32_t n_c,
+                    const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                    double center0, double disp0, double df0, double scale0, int32_t student, double *out7,
+                    double *L_out, int32_t mem_kind, gsum_fit **fit);
+int gsum_fit_destroy(gsum_fit *fit);
+
+/* predict (gsum/models.py:753-845; Student-t addition 1128-1182; truncation scaling 1337-1354, 1389-1483).
+ *
+ * One GP conditional:  mean = mean_new + K_no K_oo^{-1} (yc - mean_old),   K_pred = K_nn - K_no K_oo^{-1} K_on.
+ *   truncation == 0 (BaseConjugateProcess.predict, models.py:753-845): K = correlation R = c*RBF (+ noise I on
+ *     k(X) diagonals), conditioning factor = chol(R_oo + nugget I) (the one kept by fit when Xc == NULL), and the
+ *     returned (co)variance is cov_factor * R_pred (+ cov_factor * nugget on the diagonal if pred_noise).
+ *   truncation != 0 (TruncationProcess.predict, models.py:1439-1452 / 1460-1473): every block is
+ *     cov(X,X') = (sc[X] sc[X']) * gs(q[X] q[X']) * (cov_factor * c*RBF(X,X')) with NO white noise and NO nugget
+ *     (models.py:1342-1348, helpers.geometric_sum), and K_oo is factored afresh (the reference uses an LU solve;
+ *     K_oo is symmetric positive definite, so Cholesky gives the same result to rounding).
+ * Hyperparameters (length scale, c, noise, nugget, cov_factor) always come from `fit`.
+ * All pointers follow `mem_kind`; optional ones may be NULL. */
+typedef struct gsum_predict_args {
+    const double *Xnew; int64_t m;          /* (m, d) query points */
+    const double *Xc; int64_t n_cond;       /* (n_cond, d) conditioning points; NULL = the X given to fit */
+    const double *yc; int32_t n_y;          /* (n_cond, n_y) conditioning values; NULL = the y given to fit */
+    const double *mean_old;                 /* (n_cond,) prior mean at the conditioning points; NULL = 0 */
+    const double *mean_new;                 /* (m,) prior mean at the query points; NULL = 0 */
+    const double *basis_old;                /* (n_cond,) and */
+    const double *basis_new;                /* (m,): if cond_basis_out != NULL it receives basis_new - K_no K_oo^{-1} basis_old (models.py:1171, 1549) */
+    const double *sc_old, *sc_new;          /* truncation: ref(X) at old / new points; NULL = 1 */
+    const double *q_old, *q_new;            /* truncation: ratio(X) at old / new points; NULL = no geometric sum */
+    double gs_start, gs_end;                /* geometric sum range; gs_end may be INFINITY */
+    const int32_t *excluded; int32_t n_excluded;   /* host pointer, at most 8 entries */
+    double kernel_add;                      /* truncation: added to the kernel value before cov_factor (disp_ for the
+                                               Student-t process: cov = var * (corr + B V B^T), models.py:1124-1125); else 0 */
+    int32_t truncation;
+    int32_t want;                           /* GSUM_PREDICT_MEAN / _VAR / _COV */
+    int32_t pred_noise;
+    double *mean_out;                       /* (m, n_y) */
+    double *var_out;                        /* _VAR: (m,) diagonal of K_pred (variances; the facade takes sqrt); _COV: (m, m) */
+    double *cond_basis_out;                 /* (m,) or NULL */
+} gsum_predict_args;
+int gsum_predict(gsum_ctx *ctx, gsum_fit *fit, const gsum_predict_args *args, int32_t mem_kind);
+
+/* cov(X, Xp) of the (truncation) process without conditioning (gsum/models.py:562-599, 1342-1348): out (n1, n2).
+ * X2 == NULL evaluates k(X1) (WhiteKernel contributes on the diagonal, as sklearn does when Y is None).
+ * Kernel = constant * RBF(ls) + noise I.  sc1/sc2/q1/q2 as in gsum_predict_args (NULL = no scaling); `factor`
+ * multiplies (kernel + kernel_add) first: out = (sc sc') * gs(q q') * (factor * (k + kernel_add)). */
+int gsum_process_cov(gsum_ctx *ctx, int32_t d, const double *ls, int32_t ls_dim, double constant, double noise,
+                     const double *X1, int64_t n1, const double *X2, int64_t n2, const double *sc1, const double *sc2, const double *q1, const double *q2, double gs_start,
+                     double gs_end, const int32_t *excluded, int32_t n_excluded, double factor, double kernel_add,
+                     double *out, int32_t mem_kind);
+
+/* Diagnostics.
+ * gsum_cholesky_errors: E = L^{-1}(Y - mean)  (gsum/helpers.py:504-505, diagnostics.py:100-101); Y, E (n, n_curves);
+ *   md2 (n_curves,) or NULL receives the squared Mahalanobis distances (helpers.py:512-517, diagnostics.py:112-114). */
+int gsum_cholesky_errors(gsum_ctx *ctx, const double *L, int64_t n, const double *mean, const double *Y,
+                         int64_t n_curves, double *E, double *md2, int32_t mem_kind);
+
+/* gsum_pivoted_cholesky: LAPACK dpstrf(lower) semantics (gsum/helpers.py:185-199): M (n,n) symmetric PSD ->
+ *   Lp (n,n) lower factor of P^T M P, piv (n,) 0-based, rank; G_out (n,n) or NULL = Lp[p_inv] (M = G G^T).
+ *   Returns 1 (LinAlgError 'M is not positive-semidefinite') when rank < n, like helpers.py:189-190. */
+int gsum_pivoted_cholesky(gsum_ctx *ctx, const double *M, int64_t n, double *Lp, int32_t *piv, int32_t *rank,
+                          double *G_out, int32_t mem_kind);
+
+/* gsum_pc_errors: solve(G, Y - mean) with G = Lp[p_inv] (gsum/diagnostics.py:103-104) by permute + forward substitution. */
+int gsum_pc_errors(gsum_ctx *ctx, const double *Lp, const int32_t *piv, int64_t n, const double *mean,
+                   const double *Y, int64_t n_curves, double *E, int32_t mem_kind);
+
+/* gsum_draws: draws = mean + L z (gsum/diagnostics.py:82, models.py:872 up to the sampler's stream).
+ *   Z (n, n_draws) caller-supplied standard normals, or NULL to generate them on the device (Philox, `seed`).
+ *   draws_out (n, n_draws) or NULL.  Credible-interval coverage fused into the same pass
+ *   (gsum/diagnostics.py:148-171): lower, upper (n_alpha, n) interval bounds per point (or NULL to skip);
+ *   coverage_out (n_draws, n_alpha) = mean over points of 1[lower < y < upper]. */
+int gsum_draws(gsum_ctx *ctx, const double *L, int64_t n, const double *mean, const double *Z, int64_t n_draws,
+               uint64_t seed, double *draws_out, const double *lower, const double *upper, int32_t n_alpha,
+               double *coverage_out, int32_t mem_kind);
+
+/* gsum_credible_interval: coverage of given curves Y (n, n_curves) (gsum/diagnostics.py:148-171). */
+int gsum_credible_interval(gsum_ctx *ctx, const double *Y, int64_t n, int64_t n_curves, const double *lower,
+                           const double *upper, int32_t n_alpha, double *coverage_out, int32_t mem_kind);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSUM_B200_H */

@@ -443,7 +443,7 @@ def dpstrf_restated(M, nb=64):
         return A, piv.astype(np.int32), 0, 0
     if ajj <= 0 or np.isnan(ajj):
         return np.tril(A), piv.astype(np.int32), 0, 1
-    dstop = n * np.finfo(float).eps * ajj
+    dstop = n * (0.5 * np.finfo(float).eps) * ajj     # DLAMCH('Epsilon') = 2^-53 with rounding
     work = np.zeros(n)
     rank, info = n, 0
     k = 0

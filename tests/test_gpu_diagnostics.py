@@ -1,0 +1,140 @@
+"""GPU: Diagnostic (Mahalanobis, Cholesky / pivoted-Cholesky errors, draws, credible-interval coverage) vs the reference."""
+import numpy as np
+import pytest
+import scipy.stats as st
+from sklearn.gaussian_process.kernels import RBF
+
+import gsum_b200 as gb
+from gsum_b200 import ops
+from oracle import gsum_oracle as o
+from util import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c5_golden(ctx, golden):
+    g = golden("c5_diagnostics")
+    d = gb.Diagnostic(g["mean"], g["cov"], random_state=1)
+    Y = g["Y"]
+    assert relerr(d._chol, g["chol"]) < 1e-10
+    assert np.array_equal(d._piv, g["piv"])                                    # pivot order bit-exact vs LAPACK dpstrf
+    assert relerr(d._pchol, g["pchol"]) < 1e-10
+    assert relerr(d._pchol @ d._pchol.T, g["cov"]) < 1e-14
+    assert relerr(d.md_squared(Y), g["md2"]) < 1e-10
+    assert relerr(d.cholesky_errors(Y), g["chol_errors"]) < 1e-9
+    assert relerr(d.pivoted_cholesky_errors(Y), g["pc_errors"]) < 1e-8         # cond(cov) ~ 1e7: LU (reference) vs substitution
+    assert relerr(d.individual_errors(Y), g["ind_errors"]) < 1e-15
+    assert np.array_equal(d.credible_interval(Y, g["intervals"]), g["coverage"])   # integer counts / N: exact
+    assert d.md_squared(Y[:, 0]) == pytest.approx(float(g["md2_1d"]), rel=1e-10)
+    # 1-d y: the documented return shape is (n_intervals,).  (The reference transposes a 1-d y into N one-point "curves",
+    # gsum/diagnostics.py:168 `np.atleast_2d(y).T`, and returns an (N, n_intervals) array — a reference bug, not mirrored.)
+    assert g["coverage_1d"].shape == (len(g["mean"]), len(g["intervals"]))
+    assert np.array_equal(d.credible_interval(Y[:, 0], g["intervals"]), g["coverage"][0])
+    # property: sum of squared PC errors == MD^2 — an oracle-free cross-check of K6 against K7
+    assert relerr((d.pivoted_cholesky_errors(Y) ** 2).sum(0), d.md_squared(Y)) < 1e-9
+    assert relerr((d.cholesky_errors(Y) ** 2).sum(0), d.md_squared(Y)) < 1e-14
+
+
+def test_pivoted_cholesky_known_answers(ctx, golden):
+    """gsum/tests/test.py:75-122 (test_oracle_examples, atol 1e-4) and model_checking_tests.ipynb cell 6."""
+    g = golden("kat_pivoted_cholesky")
+    for i in range(3):
+        np.testing.assert_allclose(g[f"table{i}"], gb.pivoted_cholesky(g[f"M{i}"]), atol=1e-4)
+        np.testing.assert_allclose(g[f"G{i}"], gb.pivoted_cholesky(g[f"M{i}"]), atol=1e-12)
+    G, Lp, piv, rank, status = ops.pivoted_cholesky(g["M_nb"])
+    assert list(piv + 1) == [4, 1, 3, 2] and rank == 4 and status == 0
+    np.testing.assert_allclose(G, g["G_nb"], atol=1e-14)
+    assert np.all(np.triu(Lp, 1) == 0)
+
+
+@pytest.mark.parametrize("n", [64, 65, 200, 700])
+def test_pivoted_cholesky_vs_lapack(ctx, n):
+    """Pivots identical to LAPACK's on covariances with separated Schur diagonals (random points, varying amplitude);
+    blocked path (n > 64) included."""
+    rs = np.random.RandomState(n)
+    X = np.sort(rs.rand(n))[:, None]
+    amp = 1.0 + 0.5 * rs.rand(n)
+    cov = 1.3 * np.outer(amp, amp) * (RBF(0.2)(X) + 1e-5 * np.eye(n))
+    G, Lp, piv, rank, status = ops.pivoted_cholesky(cov)
+    Gr, pr = o.pivoted_cholesky(cov, return_pivots=True)
+    assert status == 0 and rank == n and np.array_equal(piv, pr)
+    assert relerr(G, Gr) < 1e-10 and relerr(G @ G.T, cov) < 1e-14
+    inv = np.argsort(piv)
+    assert np.array_equal(Lp[inv], G)
+
+
+def test_pivoted_cholesky_rank_deficient(ctx):
+    """info > 0 -> LinAlgError('M is not positive-semidefinite') like gsum/helpers.py:189-190; same rank and leading pivots."""
+    from scipy.linalg.lapack import dpstrf
+    A = np.random.RandomState(0).randn(100, 30)
+    M = A @ A.T
+    _, p, r, info = dpstrf(M, lower=True)
+    G, Lp, piv, rank, status = ops.pivoted_cholesky(M)
+    assert status == 1 and rank == r == 30 and np.array_equal(piv[:rank], (p - 1)[:r])
+    with pytest.raises(np.linalg.LinAlgError):
+        gb.pivoted_cholesky(M)
+    with pytest.raises(np.linalg.LinAlgError):
+        gb.Diagnostic(np.zeros(100), M)
+
+
+def test_symmetric_grid_ties_documented(ctx):
+    """On a regular grid the Schur-complement diagonals tie exactly by symmetry; rounding then decides and the order may
+    differ from LAPACK's.  The factorisation itself must still be a valid pivoted Cholesky."""
+    n = 256
+    X = np.linspace(0, 1, n)[:, None]
+    cov = 1.3 * (RBF(0.2)(X) + 1e-5 * np.eye(n))
+    G, Lp, piv, rank, status = ops.pivoted_cholesky(cov)
+    assert status == 0 and sorted(piv.tolist()) == list(range(n)) and piv[0] == 0 and piv[1] == n - 1
+    assert relerr(G @ G.T, cov) < 1e-14
+    d = np.diag(Lp)
+    assert np.all(d[:-1] >= d[1:] * (1 - 1e-9))          # pivoted Cholesky invariant: non-increasing diagonal
+
+
+def test_draws_with_supplied_z_and_helpers(ctx, golden):
+    g = golden("c5_diagnostics")
+    n = len(g["mean"])
+    Z = np.random.RandomState(0).standard_normal((n, 37))
+    D, _ = ops.draws(g["chol"], g["mean"], Z=Z)
+    assert relerr(D, o.draws_from_z(g["mean"], g["chol"], Z)) < 1e-14
+    assert relerr(gb.mahalanobis(D.T, g["mean"], g["chol"]), o.mahalanobis(D.T, g["mean"], g["chol"])) < 1e-10
+    assert relerr(gb.cholesky_errors(D.T, g["mean"], g["chol"]), o.cholesky_errors(D.T, g["mean"], g["chol"])) < 1e-9
+    assert gb.mahalanobis(D[:, 0], g["mean"], g["chol"]) == pytest.approx(o.mahalanobis(D[:, 0], g["mean"], g["chol"]), rel=1e-10)
+    # examples/model_checking_tests.ipynb cell 2: chol-based and pinv-based Mahalanobis distances agree
+    y = D[:, 3]
+    pin = np.linalg.pinv(g["cov"])
+    assert gb.mahalanobis(y, g["mean"], g["chol"]) == pytest.approx(np.sqrt((y - g["mean"]) @ pin @ (y - g["mean"])), rel=1e-5)
+
+
+def test_device_rng_draws_and_fused_coverage(ctx, golden):
+    """Philox draws: moments, MD^2 ~ chi2(N), and the fused coverage equals the separate coverage kernel bit for bit."""
+    g = golden("c5_diagnostics")
+    d = gb.Diagnostic(g["mean"], g["cov"], random_state=3)
+    n = len(g["mean"])
+    S = d.samples(4000, device_rng=True)
+    assert S.shape == (n, 4000)
+    sd = np.sqrt(np.diag(g["cov"]))
+    assert np.max(np.abs(S.mean(1) - g["mean"]) / sd) < 5 / np.sqrt(4000)
+    md2 = d.md_squared(S)
+    assert abs(md2.mean() - n) < 5 * np.sqrt(2 * n / 4000)
+    assert st.kstest(md2, st.chi2(n).cdf).pvalue > 1e-3
+    iv = g["intervals"]
+    cov_fused = d.sample_coverage(4000, iv)
+    assert np.array_equal(cov_fused, d.credible_interval(S, iv))
+    assert np.max(np.abs(cov_fused.mean(0) - iv)) < 0.01                      # calibrated: coverage ~ nominal level
+    assert np.array_equal(S, d.samples(4000, device_rng=True))                # counter-based: reproducible
+    host = d.samples(16)                                                       # numpy RandomState stream through m + L z
+    z = np.random.RandomState(3).standard_normal((n, 16))
+    assert relerr(host, o.draws_from_z(g["mean"], d._chol, z)) < 1e-13
+
+
+def test_large_draw_count_grid_limits(ctx):
+    """> 65535 draws: exercises the row-on-x launch geometry of the staging kernels."""
+    n = 96
+    X = np.linspace(0, 1, n)[:, None]
+    cov = RBF(0.3)(X) + 1e-3 * np.eye(n)
+    L = np.linalg.cholesky(cov)
+    iv = np.linspace(0.05, 0.95, 7)
+    sd = np.sqrt(np.diag(cov))
+    lower, upper = st.norm(loc=np.zeros(n), scale=sd).interval(np.atleast_2d(iv).T)
+    _, cv = ops.draws(L, np.zeros(n), n_draws=70000, seed=11, lower=lower, upper=upper, want_draws=False)
+    assert cv.shape == (70000, 7) and np.max(np.abs(cv.mean(0) - iv)) < 0.01

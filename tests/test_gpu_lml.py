@@ -1,0 +1,164 @@
+"""GPU: the (Q, l) likelihood grid through the C ABI against the oracle, the golden vectors generated from the real
+reference, and — at BASELINE.json's full size — size-independent properties."""
+import numpy as np
+import pytest
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, WhiteKernel
+
+import gsum_b200 as gb
+from gsum_b200 import ops
+from oracle import gsum_oracle as o
+from util import c4_inputs, lml_extended_precision, prior_kwargs, relerr
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10     # BASELINE.json north_star: rtol 1e-10 on log-likelihoods (FP64), on inputs with noise >= 1e-6
+
+
+def test_kat_notebook_grid(ctx, golden):
+    """Publication notebook cells 52-58: full 80 x 100 grid, argmax (36, 39).  Reference-default nugget 1e-10
+    (cond R ~ 1e11), where the reference's own cholesky/eig paths differ by ~1e-7 -> 1e-6."""
+    g = golden("kat_notebook_grid")
+    tgp = gb.TruncationGP(RBF(0.2) + WhiteKernel(1e-10, 'fixed'), ref=10, ratio=0.5, center=0, disp=0, df=1, scale=1,
+                          optimizer=None).fit(g["X"], g["y"], orders=g["orders"])
+    ll = tgp.log_marginal_likelihood_grid(g["ls_vals"], ratio_vals=g["ratio_vals"])
+    assert ll.shape == (80, 100)
+    assert np.unravel_index(np.argmax(ll), ll.shape) == (36, 39)
+    assert relerr(ll, g["ll"]) < 1e-6
+    assert ll.max() == pytest.approx(-49.682239225445784, rel=1e-8)
+    assert np.sqrt(tgp.coeffs_process.cov_factor_) == pytest.approx(float(g["sqrt_cov_factor"]), rel=1e-8)
+    # per-cell API of the reference (models.py:1485) agrees with the grid call
+    assert tgp.log_marginal_likelihood([np.log(g["ls_vals"][39])], ratio=g["ratio_vals"][36]) == pytest.approx(ll[36, 39], rel=1e-12)
+
+
+@pytest.mark.parametrize("ip", range(4))
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_c2_grid_all_priors(ctx, golden, ip, tag):
+    """N = 200, 6 orders, 8 x 8 sub-grid of config C2, every prior branch (disp0 = 0 / != 0, df0 = inf, center0 != 0),
+    Gaussian and Student-t evidence, against values produced by the reference itself."""
+    g = golden("c2_truncation_grid")
+    cls = gb.TruncationGP if tag == "g" else gb.TruncationTP
+    gp = cls(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, optimizer=None, **prior_kwargs(g["priors"][ip]))
+    gp.fit(g["X"], g["y"], orders=g["orders"])
+    ll = gp.log_marginal_likelihood_grid(g["ls_vals"], ratio_vals=g["q_vals"])
+    want = g[f"{tag}{ip}_ll"]
+    assert np.array_equal(np.isnan(ll), np.isnan(want))          # Student-t with df0 = inf is nan in the reference too
+    if not np.isfinite(want).all():
+        return
+    rel = np.abs(ll - want) / np.abs(want)
+    if not np.isinf(g["priors"][ip][2]):
+        assert rel.max() < RTOL
+        return
+    # df0 = inf: the variance is pinned, so ll is *linear* in the quadratic form y^T R^-1 y and inherits its conditioning
+    # (cond R ~ 1e8 at the long-l end with noise 1e-6) instead of seeing it through a logarithm.  Cells beyond 1e-10 are
+    # arbitrated in extended precision: the device result must be as close to the exact value as the reference's is.
+    assert rel.max() < 1e-8
+    from oracle import gsum_oracle as o
+    pk = prior_kwargs(g["priors"][ip])
+    for a, b in zip(*np.where(rel >= RTOL)):
+        q = g["q_vals"][a]
+        coeffs = o.coefficients(g["y"], q, 1.0, g["orders"])
+        exact = lml_extended_precision(g["X"], coeffs, [g["ls_vals"][b]], 1e-6, 1e-10, pk["center"], pk["disp"], pk["df"], pk["scale"])
+        exact -= len(g["X"]) * g["orders"].sum() * np.log(q)
+        assert abs(ll[a, b] - exact) <= 3 * abs(want[a, b] - exact) + RTOL * abs(exact)
+
+
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_c2_grid_x_dependent_ratio(ctx, golden, tag):
+    """x-dependent ref(x) and Q(x; lam), orders with a gap and an excluded order: one RHS block per ratio setting."""
+    g = golden("c2_truncation_grid")
+    cls = gb.TruncationGP if tag == "g" else gb.TruncationTP
+    gp = cls(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=lambda X, lam=1.0: (0.2 + 0.4 * X[:, 0]) / lam,
+             ref=lambda X: 1.0 + X[:, 0], excluded=[0], optimizer=None, **prior_kwargs(g["priors"][1]))
+    gp.fit(g["X"], g["y2"], orders=g["orders2"])
+    ll = gp.log_marginal_likelihood_grid(g["ls_vals"], ratio_kws_list=[dict(lam=l) for l in g["lams"]])
+    assert np.max(np.abs(ll - g[f"{tag}_xdep_ll"]) / np.abs(g[f"{tag}_xdep_ll"])) < RTOL
+    assert gp.log_marginal_likelihood([np.log(g["ls_vals"][3])], lam=g["lams"][2]) == pytest.approx(g[f"{tag}_xdep_ll"][2, 3], rel=RTOL)
+
+
+def test_c1_conjugate_lml(ctx, golden):
+    """ConjugateGaussianProcess / ConjugateStudentProcess.log_marginal_likelihood(theta) at 5 thetas (config C1)."""
+    g = golden("c1_conjugate")
+    for ip in range(4):
+        for tag, cls in (("g", gb.ConjugateGaussianProcess), ("t", gb.ConjugateStudentProcess)):
+            kern = C(1.5, 'fixed') * RBF(0.2) + WhiteKernel(1e-4, 'fixed')
+            gp = cls(kern, nugget=1e-10, optimizer=None, **prior_kwargs(g["priors"][ip])).fit(g["X"], g["y"])
+            lml = np.array([gp.log_marginal_likelihood(theta=[t]) for t in g["thetas"]])
+            want = g[f"{tag}{ip}_lml"]
+            assert np.array_equal(np.isnan(lml), np.isnan(want))
+            if np.isfinite(want).all():
+                assert np.max(np.abs(lml - want) / np.abs(want)) < RTOL
+
+
+def test_grid_matches_oracle_random_inputs_2d(ctx):
+    """Seeded 2-D inputs, anisotropic length scales, ragged N (not a multiple of the 64 tile)."""
+    rs = np.random.RandomState(7)
+    X = rs.rand(150, 2)
+    coeffs = rs.randn(150, 4)
+    orders = np.array([1, 2, 3, 5])
+    y = o.partials(coeffs, 0.45, 2.0, orders)
+    ls = np.array([[0.1, 0.2], [0.3, 0.15], [0.05, 0.05]])
+    qv = np.array([0.3, 0.45, 0.6])
+    pri = dict(center=0.2, disp=0.7, df=4, scale=1.1)
+    gp = gb.TruncationGP(C(2.0, 'fixed') * RBF([0.1, 0.2]) + WhiteKernel(1e-3, 'fixed'), ratio=0.45, ref=2.0, optimizer=None, **pri)
+    gp.fit(X, y, orders=orders)
+    ll = gp.log_marginal_likelihood_grid(ls, ratio_vals=qv)
+    for a, q in enumerate(qv):
+        for b in range(3):
+            kern = C(2.0, 'fixed') * RBF(ls[b]) + WhiteKernel(1e-3, 'fixed')
+            want = o.truncation_lml(kern, kern.theta, X, y, orders, q * np.ones(150), 2.0 * np.ones(150), o.Priors(**pri))
+            assert ll[a, b] == pytest.approx(want, rel=RTOL)
+
+
+def test_edge_cases(ctx):
+    """Single point, single curve, N = 1 tile exactly, non-PD row -> -inf with a status code (models.py:970-972)."""
+    X = np.array([[0.3]])
+    ll = ops.lml_grid(X, np.array([[0.7]]), 1.0, [0], [[0.2]], [0.5], noise=1e-6, nugget=0.0, df0=3.0)
+    want = o.truncation_lml(RBF(0.2) + WhiteKernel(1e-6), np.log([0.2, 1e-6]), X, np.array([[0.7]]), [0], np.array([0.5]), np.array([1.0]),
+                            o.Priors(df=3), nugget=0.0)
+    assert ll[0, 0] == pytest.approx(want, rel=1e-12)
+    X = np.linspace(0, 1, 64)[:, None]
+    y = np.sin(6 * X)
+    ll, logdet, status = ops.lml_grid(X, y, 1.0, [0], [[0.3], [0.1]], [1.0], noise=1e-6, nugget=0.0, return_status=True)
+    assert status.tolist() == [0, 0] and np.isfinite(ll).all()
+    # duplicated points and no noise: exactly singular -> Cholesky fails -> -inf for every Q of that length scale
+    Xd = np.concatenate([X, X[:5]])
+    yd = np.concatenate([y, y[:5]])
+    ll, logdet, status = ops.lml_grid(Xd, yd, 1.0, [0], [[0.3], [0.1]], [1.0, 0.5], noise=0.0, nugget=0.0, return_status=True)
+    assert (status != 0).all() and np.all(np.isneginf(ll)) and np.isnan(logdet).all()
+    with pytest.raises(Exception):
+        ops.lml_grid(X, np.zeros((64, 20)), 1.0, np.zeros(20, np.int32), [[0.3]], [1.0])       # too many curves -> bad argument
+
+
+def test_c4_full_size_properties(ctx):
+    """Config C4 at full size (N = 1024, 6 orders, 128 l x 256 Q): spot cells against the oracle, and properties
+    that do not need the oracle: Q-separability (scalar-Q Gram path == x-dependent-Q RHS path), invariance of a cell to
+    the rest of the grid, finite everywhere, and idempotence."""
+    X, y, orders = c4_inputs()
+    ls_vals = np.geomspace(0.005, 0.5, 128)
+    q_vals = np.linspace(0.2, 0.8, 256)
+    gp = gb.TruncationGP(RBF(0.05) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None)
+    gp.fit(X, y, orders=orders)
+    ll = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals)
+    assert ll.shape == (256, 128) and np.isfinite(ll).all()
+    assert np.array_equal(ll, gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals))       # deterministic
+    sub = gp.log_marginal_likelihood_grid(ls_vals[[3, 77]], ratio_vals=q_vals[[10, 200]])
+    assert np.array_equal(sub, ll[np.ix_([10, 200], [3, 77])])                                     # cells are independent
+    # separable path vs the generic x-dependent path (different kernels, same numbers)
+    gq = gb.TruncationGP(RBF(0.05) + WhiteKernel(1e-6, 'fixed'), ratio=lambda X, q=0.5: q * np.ones(len(X)), ref=1, center=0, disp=0,
+                         df=1, scale=1, optimizer=None).fit(X, y, orders=orders)
+    xdep = gq.log_marginal_likelihood_grid(ls_vals[::16], ratio_kws_list=[dict(q=q) for q in q_vals[::64]])
+    assert np.max(np.abs(xdep - ll[::64, ::16]) / np.abs(ll[::64, ::16])) < 1e-11
+    # oracle spot checks.  cond(R) reaches ~1e9 at the long-l end of this grid (noise 1e-6, N = 1024), where two
+    # backward-stable factorizations legitimately differ by ~cond * eps; the bound below scales accordingly.
+    kern = RBF(0.05) + WhiteKernel(1e-6, 'fixed')
+    for a, b, tol in [(0, 0, 1e-10), (100, 40, 1e-10), (255, 64, 1e-10), (17, 90, 2e-9), (128, 127, 5e-9)]:
+        want = o.truncation_lml(kern, [np.log(ls_vals[b])], X, y, orders, q_vals[a] * np.ones(1024), np.ones(1024), o.Priors(0, 0, 1, 1))
+        assert ll[a, b] == pytest.approx(want, rel=tol)
+
+
+def test_grid_normalize(ctx):
+    rs = np.random.RandomState(0)
+    ll = -1000 + 30 * rs.randn(64, 64)
+    post, lse = ops.grid_normalize(ll)
+    from scipy.special import logsumexp
+    assert relerr(post, np.exp(ll - ll.max())) < 1e-14 and lse == pytest.approx(logsumexp(ll), rel=1e-14)

@@ -1,0 +1,139 @@
+"""GPU: fit / predict / mean / cov of the conjugate and truncation processes against golden vectors from the reference."""
+import numpy as np
+import pytest
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, WhiteKernel
+
+import gsum_b200 as gb
+from util import prior_kwargs, relerr
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10        # posterior moments (BASELINE.json north_star); noise 1e-4 keeps cond(R) ~ 1e6
+
+
+@pytest.mark.parametrize("ip", range(4))
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_c1_fit_posteriors_and_predict(ctx, golden, ip, tag):
+    g = golden("c1_conjugate")
+    cls = gb.ConjugateGaussianProcess if tag == "g" else gb.ConjugateStudentProcess
+    kern = C(1.5, 'fixed') * RBF(0.2, 'fixed') + WhiteKernel(1e-4, 'fixed')
+    gp = cls(kern, nugget=1e-10, **prior_kwargs(g["priors"][ip])).fit(g["X"], g["y"])
+    post = np.array([gp.center_[0], gp.disp_[0, 0], gp.df_, gp.scale_, gp.cov_factor_, gp.log_marginal_likelihood_value_])
+    want = g[f"{tag}{ip}_post"]
+    assert gp.cbar_sq_mean_ == gp.cov_factor_ and gp.center_.shape == (1,) and gp.disp_.shape == (1, 1)
+    assert np.array_equal(np.isnan(post), np.isnan(want))
+    ok = np.isfinite(want) & (want != 0)
+    assert np.max(np.abs(post[ok] - want[ok]) / np.abs(want[ok])) < RTOL
+    assert np.all(post[want == 0] == 0)
+    if f"{tag}{ip}_mean" not in g:
+        return
+    Xn = g["Xn"]
+    m = gp.predict(Xn)
+    assert m.shape == g[f"{tag}{ip}_mean"].shape and relerr(m, g[f"{tag}{ip}_mean"]) < RTOL
+    m, s = gp.predict(Xn, return_std=True)
+    assert relerr(s, g[f"{tag}{ip}_std"]) < 1e-9                 # sqrt of a difference that cancels to ~1e-4 of its terms
+    m, cv = gp.predict(Xn[::4], return_cov=True, pred_noise=True)
+    assert relerr(cv, g[f"{tag}{ip}_cov"]) < 1e-9 and np.array_equal(cv, cv.T)
+    m, s = gp.predict(Xn, return_std=True, Xc=g["Xc"], y=g["yc"])
+    assert relerr(m, g[f"{tag}{ip}_mean_c"]) < RTOL and relerr(s, g[f"{tag}{ip}_std_c"]) < 1e-9
+    if ip == 0 and tag == "g":
+        assert relerr(gp.corr_L_, g["corr_L"]) < 1e-10 and np.all(np.triu(gp.corr_L_, 1) == 0)
+        assert np.max(np.abs(gp.corr_ - g["corr"])) < 1e-15
+        assert gp.corr_sqrt_ is gp.corr_L_
+
+
+def test_interpolation_property(ctx):
+    """gsum/tests/test.py:63-72 (test_cgp_interpolation, fixed kernel): with nugget=0 the posterior mean reproduces
+    y = x sin x at the training points (7 decimals) and the posterior variance vanishes there (10 decimals)."""
+    X = np.atleast_2d([1., 3., 5., 6., 7., 8.]).T
+    y = (X * np.sin(X)).ravel()
+    gpr = gb.ConjugateGaussianProcess(kernel=RBF(length_scale=1.0, length_scale_bounds="fixed"), nugget=0).fit(X, y)
+    y_pred, y_cov = gpr.predict(X, return_cov=True)
+    np.testing.assert_almost_equal(y_pred, y)
+    np.testing.assert_almost_equal(np.diag(y_cov), 0., decimal=10)
+
+
+def test_prior_predict_and_cov_before_fit(ctx):
+    gp = gb.ConjugateGaussianProcess(C(2.0) * RBF(0.3) + WhiteKernel(1e-3), center=0.4, df=5, scale=1.5)
+    X = np.linspace(0, 1, 30)[:, None]
+    var = 5 * 1.5 ** 2 / 3
+    kern = C(2.0) * RBF(0.3) + WhiteKernel(1e-3)
+    m, cv = gp.predict(X, return_cov=True)
+    assert np.array_equal(m, np.full(30, 0.4)) and relerr(cv, var * kern(X)) < 1e-14
+    assert relerr(gp.cov(X, X[:7]), var * kern(X, X[:7])) < 1e-14
+    m, s = gp.predict(X, return_std=True)
+    assert relerr(s, np.sqrt(np.diag(var * kern(X)))) < 1e-14
+
+
+@pytest.mark.parametrize("tag", ["g", "t"])
+@pytest.mark.parametrize("variant", ["const", "xdep"])
+def test_c3_truncation_predict(ctx, golden, tag, variant):
+    """TruncationGP / TruncationTP.predict (interp + truncation error), cov, mean on 2-D inputs; K_oo has no nugget in the
+    reference (cond(K_oo) is stored in the fixture), which solves by LU where the device path uses Cholesky."""
+    g = golden("c3_truncation_predict")
+    cls = gb.TruncationGP if tag == "g" else gb.TruncationTP
+    if variant == "const":
+        kw = dict(ratio=0.4, ref=1.0, excluded=None)
+    else:
+        kw = dict(ratio=lambda X: 0.3 + 0.2 * X[:, 1], ref=lambda X: 1.0 + 0.5 * X[:, 0], excluded=[0])
+    kern = RBF([0.05, 0.07], 'fixed') + WhiteKernel(1e-6, 'fixed')
+    gp = cls(kern, optimizer=None, **kw, **prior_kwargs(g["prior"])).fit(g["X"], g["y"], orders=g["orders"])
+    pre = f"{tag}_{variant}_"
+    tol = 50 * float(g[pre + "cond_Koo"]) * 2.2e-16 + 1e-12
+    Xn = g["Xn"]
+    for kind in (("both", "interp", "trunc") if tag == "g" else ("both",)):
+        m, s = gp.predict(Xn, order=5, return_std=True, kind=kind)
+        assert relerr(m, g[pre + kind + "_mean"]) < tol and relerr(s, g[pre + kind + "_std"]) < max(tol, 1e-9)
+        m3, cv = gp.predict(Xn[:40], order=3, return_cov=True, kind=kind)
+        assert relerr(m3, g[pre + kind + "_mean3"]) < tol and relerr(cv, g[pre + kind + "_cov3"]) < max(tol, 1e-9)
+        assert relerr(gp.predict(Xn, order=5, kind=kind), g[pre + kind + "_mean"]) < tol
+    m, s = gp.coeffs_process.predict(Xn, return_std=True)
+    assert relerr(m, g[pre + "cp_mean"]) < RTOL and relerr(s, g[pre + "cp_std"]) < 1e-9
+    assert relerr(gp.cov(Xn[:30], start=2, end=np.inf), g[pre + "cov_sym"]) < 1e-13
+    assert relerr(gp.cov(Xn[:30], Xp=g["X"][:25], start=0, end=4), g[pre + "cov_cross"]) < 1e-13
+    assert relerr(gp.mean(Xn, start=1, end=4), g[pre + "mean_fn"]) < 1e-13
+    with pytest.raises(ValueError):
+        gp.predict(Xn, order=17)
+    if tag == "g":      # TruncationTP.predict does not forward `kind` to its parent (gsum/models.py:1528-1531), so no check there
+        with pytest.raises(ValueError):
+            gp.predict(Xn, order=3, kind="nope")
+
+
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_c3_constrained_truncation_error(ctx, golden, tag):
+    """fit(..., dX, dy): the truncation-error process is conditioned on (dX, dy) (gsum/models.py:1463-1473)."""
+    g = golden("c3_truncation_predict")
+    cls = gb.TruncationGP if tag == "g" else gb.TruncationTP
+    kern = RBF([0.05, 0.07], 'fixed') + WhiteKernel(1e-6, 'fixed')
+    gp = cls(kern, optimizer=None, ratio=0.4, ref=1.0, **prior_kwargs(g["prior"])).fit(g["X"], g["y"], orders=g["orders"], dX=g["dX"], dy=g["dy"])
+    m, s = gp.predict(g["Xn"], order=4, return_std=True, kind='both')
+    assert relerr(m, g[f"{tag}_constr_mean"]) < 1e-9 and relerr(s, g[f"{tag}_constr_std"]) < 1e-9
+
+
+def test_fit_with_optimizer_recovers_length_scale(ctx):
+    """fit() with a free length scale and the default optimizer (the reference's own path crashes on numpy >= 1.24,
+    gsum/models.py:664).  Soft pin from the publication notebook (cells 33-37): RBF(length_scale ~ 0.199)."""
+    from scipy import stats
+    X = np.linspace(0, 1, 40)[:, None]
+    K = RBF(0.2)(X) + 1e-8 * np.eye(40)
+    y = stats.multivariate_normal(np.zeros(40), K, allow_singular=True).rvs(6, random_state=5).T
+    gp = gb.ConjugateGaussianProcess(RBF(0.5) + WhiteKernel(1e-6, 'fixed'), center=0, disp=0, df=1, scale=1)
+    gp.fit(X, y)
+    ls = gp.kernel_.k1.length_scale
+    assert 0.15 < ls < 0.27
+    grid = np.linspace(0.1, 0.4, 61)
+    best = grid[np.argmax([gp.log_marginal_likelihood([np.log(l)]) for l in grid])]
+    assert abs(ls - best) < 0.006
+    assert gp.log_marginal_likelihood_value_ == pytest.approx(gp.log_marginal_likelihood(gp.kernel_.theta), rel=1e-12)
+
+
+def test_sample_y_statistics(ctx):
+    X = np.linspace(0, 1, 25)[:, None]
+    y = np.sin(5 * X[:, 0])
+    gp = gb.ConjugateGaussianProcess(RBF(0.2, 'fixed') + WhiteKernel(1e-4, 'fixed'), df=10, scale=1).fit(X, y)
+    Xs = np.linspace(0.02, 0.98, 12)[:, None]
+    m, cv = gp.predict(Xs, return_cov=True)
+    S = gp.sample_y(Xs, n_samples=4000, random_state=1)
+    assert S.shape == (12, 4000)
+    assert np.max(np.abs(S.mean(1) - m)) < 5 * np.sqrt(np.max(np.diag(cv)) / 4000) + 1e-12
+    assert relerr(np.cov(S), cv) < 0.15

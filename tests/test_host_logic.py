@@ -1,0 +1,125 @@
+"""CPU: host-side logic of the facade — kernel flattening, series helpers, grid sharding over a gloo process group."""
+import os
+import sys
+
+import numpy as np
+import pytest
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, DotProduct, Matern, WhiteKernel
+
+from gsum_b200 import helpers
+from gsum_b200.distributed import assemble_blocks, shard_indices
+from gsum_b200.kernels import flatten_kernel
+from oracle import gsum_oracle as o
+from util import relerr
+
+
+def test_flatten_supported_kernels():
+    k = flatten_kernel(C(1.5) * RBF([0.2, 0.3]) + WhiteKernel(1e-6))
+    assert k.constant == 1.5 and k.noise == 1e-6 and k.length_scale.tolist() == [0.2, 0.3]
+    k = flatten_kernel(RBF(0.2))
+    assert k.constant == 1.0 and k.noise == 0.0 and k.length_scale.tolist() == [0.2]
+    k = flatten_kernel(WhiteKernel(1e-3) + RBF(0.4) * C(2.0) * C(3.0))
+    assert k.constant == 6.0 and k.noise == 1e-3
+    # theta round trip as the facade does it (models.py: clone_with_theta then flatten)
+    kern = RBF(0.2) + WhiteKernel(1e-6, 'fixed')
+    assert flatten_kernel(kern.clone_with_theta([np.log(0.37)])).length_scale[0] == pytest.approx(0.37)
+    with pytest.raises(ValueError):
+        k = flatten_kernel(RBF([0.1, 0.2, 0.3])); k.ls_for(2)
+
+
+@pytest.mark.parametrize("kern", [Matern(0.3), DotProduct(), RBF(0.1) + RBF(0.2), RBF(0.1) * RBF(0.2), C(1.0) + RBF(0.2)])
+def test_flatten_rejects_unsupported(kern):
+    with pytest.raises(NotImplementedError):
+        flatten_kernel(kern)
+
+
+def test_series_helpers_match_oracle():
+    rs = np.random.RandomState(1)
+    y = rs.randn(30, 6).cumsum(1)
+    q, ref, orders = 0.2 + 0.5 * rs.rand(30), 1 + rs.rand(30), np.array([0, 1, 3, 4, 5, 8])
+    assert np.array_equal(helpers.coefficients(y, q, ref, orders), o.coefficients(y, q, ref, orders))
+    assert np.array_equal(helpers.coefficients(y, 0.4, 2.0), o.coefficients(y, 0.4, 2.0))
+    c = rs.randn(30, 6)
+    assert np.array_equal(helpers.partials(c, q, ref, orders), o.partials(c, q, ref, orders))
+    x = rs.rand(5, 4) * 0.9
+    for s, e, ex in [(0, 3, None), (2, np.inf, None), (0, np.inf, [0, 2]), (1, 4, 3)]:
+        assert np.array_equal(helpers.geometric_sum(x, s, e, ex), o.geometric_sum(x, s, e, ex))
+    assert np.array_equal(helpers.cartesian(np.arange(3), np.arange(2)), o.cartesian(np.arange(3), np.arange(2)))
+    with pytest.raises(ValueError):
+        helpers.coefficients(y[:, 0], 0.5)
+    with pytest.raises(ValueError):
+        helpers.coefficients(y, 0.5, orders=np.arange(3))
+    with pytest.raises(ValueError):
+        helpers.geometric_sum(x, 4, 2)
+
+
+def test_shard_indices_cover_grid_exactly_once():
+    for n_ls in (1, 7, 128, 130):
+        for world in (1, 2, 3, 8):
+            seen = np.concatenate([shard_indices(n_ls, world, r) for r in range(world)])
+            assert sorted(seen.tolist()) == list(range(n_ls))
+            per = -(-n_ls // world)
+            blocks = []
+            for r in range(world):
+                idx = shard_indices(n_ls, world, r)
+                b = np.full((3, per), -np.inf)
+                b[:, :len(idx)] = idx[None, :] + 1000.0 * np.arange(3)[:, None]
+                blocks.append(b)
+            full = assemble_blocks(blocks, n_ls, world)
+            assert np.array_equal(full, np.arange(n_ls)[None, :] + 1000.0 * np.arange(3)[:, None])
+
+
+def _sharded_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from gsum_b200.distributed import lml_grid_sharded
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def evaluator(X, dy, ref, orders, ls, Q, **kw):          # stand-in for the device grid: a known function of (Q, ls)
+        return np.asarray(Q)[:, None] * 10.0 + np.asarray(ls)[:, 0][None, :]
+
+    ls = np.linspace(0.1, 1.3, 13)
+    Q = np.linspace(0.2, 0.8, 5)
+    full = lml_grid_sharded(None, None, None, None, ls, Q, _evaluator=evaluator)
+    q.put((rank, full))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_grid_gloo_world2():
+    """World-size-2 gloo run of the sharding + all-gather path (the NCCL run on GPUs uses the same code)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.linspace(0.2, 0.8, 5)[:, None] * 10.0 + np.linspace(0.1, 1.3, 13)[None, :]
+    assert np.array_equal(res[0], want) and np.array_equal(res[1], want)
+
+
+def test_facade_rejects_out_of_scope_options():
+    from gsum_b200 import ConjugateGaussianProcess, Diagnostic, TruncationGP
+    with pytest.raises(NotImplementedError):
+        ConjugateGaussianProcess(RBF(0.2), basis=lambda X: X)
+    gp = ConjugateGaussianProcess(RBF(0.2, 'fixed'), decomposition='eig')
+    with pytest.raises(NotImplementedError):
+        gp.fit(np.zeros((3, 1)), np.zeros(3))
+    gp = ConjugateGaussianProcess(RBF(0.2, 'fixed'), decomposition='lu')
+    with pytest.raises(ValueError):
+        gp.fit(np.zeros((3, 1)), np.zeros(3))
+    with pytest.raises(NotImplementedError):
+        Diagnostic(np.zeros(3), np.eye(3), df=5)
+    with pytest.raises(RuntimeError):
+        ConjugateGaussianProcess(RBF(0.2, 'fixed')).predict(np.zeros((2, 1)), return_std=True, return_cov=True)
+    tp = TruncationGP(RBF(0.2), ratio=0.5)
+    with pytest.raises(NotImplementedError):
+        tp.log_marginal_likelihood([0.0], eval_gradient=True)
+    with pytest.raises(ValueError):
+        ConjugateGaussianProcess(RBF(0.2), df=1).cov(np.zeros((2, 1)))      # df <= 2: covariance does not exist

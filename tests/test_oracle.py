@@ -1,0 +1,153 @@
+"""CPU: the oracle (oracle/gsum_oracle.py) against every golden vector generated from the real reference and against
+the reference's own known answers.  This is what pins the checker the GPU tests rely on."""
+import numpy as np
+import pytest
+from sklearn.gaussian_process.kernels import RBF, WhiteKernel, ConstantKernel as C
+
+from oracle import gsum_oracle as o
+from util import prior_kwargs, relerr
+
+TOL = 1e-12     # same algorithm, same BLAS: differences are memory-alignment noise of cho_solve (~1e-14)
+
+
+def test_kat_notebook_grid_argmax(golden):
+    """docs/notebooks/correlated_EFT_publication.ipynb cell 58: Best Q 0.4822784810126582, best ls 0.19757575757575757."""
+    g = golden("kat_notebook_grid")
+    assert tuple(g["argmax"]) == (36, 39)
+    assert g["ratio_vals"][36] == 0.4822784810126582 and g["ls_vals"][39] == 0.19757575757575757
+    assert g["ll"].max() == pytest.approx(-49.682239225445784, rel=1e-13)
+    kern = RBF(0.2) + WhiteKernel(1e-10, 'fixed')
+    sub_q, sub_l = [0, 36, 79], [5, 39, 99]
+    ll = o.lml_grid(kern, g["X"], g["y"], g["orders"], g["ls_vals"][sub_l], g["ratio_vals"][sub_q], 10.0, o.Priors(0, 0, 1, 1))
+    assert relerr(ll, g["ll"][np.ix_(sub_q, sub_l)]) < TOL
+
+
+@pytest.mark.parametrize("ip", range(4))
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_c1_fit_lml_predict(golden, ip, tag):
+    g = golden("c1_conjugate")
+    p = o.Priors(**prior_kwargs(g["priors"][ip]))
+    student = tag == "t"
+    kern = C(1.5, 'fixed') * RBF(0.2, 'fixed') + WhiteKernel(1e-4, 'fixed')
+    f = o.fit_conjugate(kern, g["X"], g["y"], p, nugget=1e-10, student=student)
+    post = np.array([f["center"][0], f["disp"][0, 0], f["df"], f["scale"], f["cov_factor"], f["lml"]])
+    want = g[f"{tag}{ip}_post"]
+    ok = np.isfinite(want)
+    assert np.array_equal(np.isnan(post), np.isnan(want))
+    assert relerr(post[ok & np.isfinite(post)], want[ok & np.isfinite(post)]) < TOL
+    kfree = C(1.5, 'fixed') * RBF(0.2) + WhiteKernel(1e-4, 'fixed')
+    lml_fn = o.student_lml if student else o.gaussian_lml
+    lml = np.array([lml_fn(kfree, [t], g["X"], g["y"], p, 1e-10) for t in g["thetas"]])
+    wl = g[f"{tag}{ip}_lml"]
+    assert np.array_equal(np.isnan(lml), np.isnan(wl))
+    if np.isfinite(wl).all():
+        assert relerr(lml, wl) < TOL
+    if f"{tag}{ip}_mean" in g:
+        pf = o.predict_student if student else o.predict_conjugate
+        m, s = pf(f, g["Xn"], return_std=True)
+        assert relerr(m, g[f"{tag}{ip}_mean"]) < TOL and relerr(s, g[f"{tag}{ip}_std"]) < 1e-9
+        _, cv = pf(f, g["Xn"][::4], return_cov=True, pred_noise=True)
+        assert relerr(cv, g[f"{tag}{ip}_cov"]) < 1e-9
+        m, s = pf(f, g["Xn"], return_std=True, Xc=g["Xc"], y=g["yc"])
+        assert relerr(m, g[f"{tag}{ip}_mean_c"]) < TOL and relerr(s, g[f"{tag}{ip}_std_c"]) < 1e-9
+
+
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_c2_truncation_grid(golden, tag):
+    g = golden("c2_truncation_grid")
+    kern = RBF(0.2) + WhiteKernel(1e-6, 'fixed')
+    for ip in range(4):
+        p = o.Priors(**prior_kwargs(g["priors"][ip]))
+        ll = o.lml_grid(kern, g["X"], g["y"], g["orders"], g["ls_vals"][::3], g["q_vals"][::3], 1.0, p, student=tag == "t")
+        want = g[f"{tag}{ip}_ll"][::3, ::3]
+        assert np.array_equal(np.isnan(ll), np.isnan(want))
+        if np.isfinite(want).all():
+            assert relerr(ll, want) < TOL
+    p = o.Priors(**prior_kwargs(g["priors"][1]))
+    X = g["X"]
+    ref = 1.0 + X[:, 0]
+    for a, lam in enumerate(g["lams"]):
+        q = (0.2 + 0.4 * X[:, 0]) / lam
+        for b in (0, 4, 7):
+            ll = o.truncation_lml(kern, [np.log(g["ls_vals"][b])], X, g["y2"], g["orders2"], q, ref, p, excluded=[0], student=tag == "t")
+            assert ll == pytest.approx(g[f"{tag}_xdep_ll"][a, b], rel=TOL)
+
+
+@pytest.mark.parametrize("variant", ["const", "xdep"])
+def test_c3_truncation_predict(golden, variant):
+    g = golden("c3_truncation_predict")
+    p = o.Priors(**prior_kwargs(g["prior"]))
+    X, Xn, y, orders = g["X"], g["Xn"], g["y"], g["orders"]
+    if variant == "const":
+        ratio_fn, ref_fn, excl = (lambda X: 0.4 * np.ones(len(X))), (lambda X: np.ones(len(X))), None
+    else:
+        ratio_fn, ref_fn, excl = (lambda X: 0.3 + 0.2 * X[:, 1]), (lambda X: 1.0 + 0.5 * X[:, 0]), [0]
+    mask = ~np.isin(orders, excl)
+    coeffs = o.coefficients(y, ratio_fn(X), ref_fn(X), orders)[:, mask]
+    kern = RBF([0.05, 0.07], 'fixed') + WhiteKernel(1e-6, 'fixed')
+    f = o.fit_conjugate(kern, X, coeffs, p)
+    for kind in ("both", "interp", "trunc"):
+        m, s = o.predict_truncation(f, Xn, 5, y[:, 5], ratio_fn, ref_fn, return_std=True, kind=kind, excluded=excl)
+        assert relerr(m, g[f"g_{variant}_{kind}_mean"]) < 1e-11 and relerr(s, g[f"g_{variant}_{kind}_std"]) < 1e-9
+    K = o.truncation_cov(f, Xn[:30], X[:25], ratio_fn, ref_fn, 0, 4, excl)
+    assert relerr(K, g[f"g_{variant}_cov_cross"]) < TOL
+
+
+def test_c5_diagnostics(golden):
+    g = golden("c5_diagnostics")
+    cov, mean, Y = g["cov"], g["mean"], g["Y"]
+    G, piv = o.pivoted_cholesky(cov, return_pivots=True)
+    assert np.array_equal(piv, g["piv"]) and np.array_equal(G, g["pchol"])
+    ch = np.linalg.cholesky(cov)
+    assert np.array_equal(ch, g["chol"])
+    assert relerr(o.md_squared(Y, mean, ch), g["md2"]) < TOL
+    assert relerr(o.pivoted_cholesky_errors(Y, mean, G), g["pc_errors"]) < TOL
+    assert relerr(o.cholesky_errors(Y.T, mean, ch).T, g["chol_errors"]) < TOL
+    assert np.array_equal(o.credible_interval(Y, mean, cov, g["intervals"]), g["coverage"])
+    assert relerr(o.individual_errors(Y, mean, cov), g["ind_errors"]) < TOL
+    # the restated dpstrf picks the same pivots as LAPACK and reproduces its factor
+    L, piv2, rank, info = o.dpstrf_restated(cov)
+    assert info == 0 and rank == cov.shape[0] and np.array_equal(piv2, g["piv"])
+    inv = np.argsort(piv2)
+    assert relerr(L[inv], g["pchol"]) < 1e-10
+    # property: sum of squared pivoted-Cholesky errors == squared Mahalanobis distance
+    assert relerr((g["pc_errors"] ** 2).sum(0), g["md2"]) < 1e-8
+
+
+def test_kat_pivoted_cholesky(golden):
+    """gsum/tests/test.py:75-122 (tabulated, atol 1e-4) and examples/model_checking_tests.ipynb cell 6 (pivots [4 1 3 2])."""
+    g = golden("kat_pivoted_cholesky")
+    for i in range(3):
+        G = o.pivoted_cholesky(g[f"M{i}"])
+        np.testing.assert_allclose(g[f"table{i}"], G, atol=1e-4)
+        L, piv, rank, info = o.dpstrf_restated(g[f"M{i}"])
+        np.testing.assert_allclose(L[np.argsort(piv)], G, atol=1e-12)
+    G, piv = o.pivoted_cholesky(g["M_nb"], return_pivots=True)
+    assert list(piv + 1) == [4, 1, 3, 2]
+    np.testing.assert_allclose(G[0], [0.27726151, 1.66047284, 0, 0], atol=1e-8)
+    L, piv2, _, _ = o.dpstrf_restated(g["M_nb"])
+    assert np.array_equal(piv2, piv)
+
+
+def test_dpstrf_restated_rank_deficient():
+    """Stop criterion N * DLAMCH('Epsilon') * max diag: same rank and leading pivots as LAPACK on a rank-30 matrix."""
+    from scipy.linalg.lapack import dpstrf
+    A = np.random.RandomState(0).randn(100, 30)
+    M = A @ A.T
+    _, p, r, info = dpstrf(M, lower=True)
+    L, piv, rank, info2 = o.dpstrf_restated(M)
+    assert info == info2 == 1 and rank == r == 30 and np.array_equal(piv[:rank], (p - 1)[:r])
+
+
+def test_series_helpers_roundtrip():
+    rs = np.random.RandomState(0)
+    c = rs.randn(20, 5)
+    q, ref, orders = 0.2 + 0.5 * rs.rand(20), 1 + rs.rand(20), np.array([0, 2, 3, 4, 6])
+    y = o.partials(c, q, ref, orders)
+    assert relerr(o.coefficients(y, q, ref, orders), c) < 1e-12
+    x = 0.37
+    assert o.geometric_sum(x, 2, 5) == pytest.approx(sum(x ** i for i in range(2, 6)))
+    assert o.geometric_sum(x, 0, np.inf, excluded=[1]) == pytest.approx(1 / (1 - x) - x)
+    with pytest.raises(ValueError):
+        o.geometric_sum(x, 3, 2)
+    assert o.cartesian(np.arange(2), np.arange(3)).tolist() == [[0, 0], [0, 1], [0, 2], [1, 0], [1, 1], [1, 2]]
