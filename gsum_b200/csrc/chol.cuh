@@ -56,27 +56,42 @@ __device__ __forceinline__ void chol_load_stage(double *st, const double *Ai, co
         }
     }
 }
+// A whole 64x64 tile (the diagonal factor L_kk needed by the epilogue) into one stage buffer, row stride GSUM_LDS.
+__device__ __forceinline__ void chol_load_tail(double *st, const double *src, int64_t ld, int tid) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        int c = tid + q * CHOL_THREADS;
+        int row = c >> 5, ch = (c & 31) * 2;
+        cp_async16(st + row * GSUM_LDS + ch, src + (int64_t)row * ld + ch);
+    }
+}
 
 // acc(64x64, warp tile 32x32) -= Ai[64 x 64*nslab] * Bk[64 x 64*nslab]^T     (acc preloaded by the caller)
-// `skip` lets a warp sit out the DMMA work (strict upper block of a diagonal tile) while still
-// taking part in the copies and barriers.
-__device__ __forceinline__ void tile_accumulate(double (&acc)[4][4][2], const double *Ai, const double *Bk,
-                                                int64_t lda, int64_t ldb, int nslab, bool same, bool skip,
-                                                double *smem) {
+// `skip` lets a warp sit out the DMMA work (strict upper block of a diagonal tile) while still taking part in the
+// copies and barriers.  `tail` (optional) is one more 64x64 tile streamed through the same ring right behind the last
+// operand slab — the epilogue's L_kk — so its latency hides under the main loop; the function returns the stage buffer
+// it landed in.  Fragments are double-buffered in registers so the LDS latency of step ks+1 hides under the DMMAs of ks.
+__device__ __forceinline__ double *tile_accumulate(double (&acc)[4][4][2], const double *Ai, const double *Bk,
+                                                   int64_t lda, int64_t ldb, int nslab, bool same, bool skip,
+                                                   double *smem, const double *tail = nullptr, int64_t tail_ld = 0) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
     const int nh = nslab * 2;
+    const int total = nh + (tail ? 1 : 0);
 #pragma unroll
     for (int s = 0; s < CHOL_NST - 1; s++) {
         if (s < nh) chol_load_stage(smem + s * CHOL_STAGE_DOUBLES, Ai, Bk, lda, ldb, s, same, tid);
+        else if (s < total) chol_load_tail(smem + s * CHOL_STAGE_DOUBLES, tail, tail_ld, tid);
         cp_async_commit();
     }
     for (int h = 0; h < nh; h++) {
         cp_async_wait<CHOL_NST - 2>();
         __syncthreads();
         {
-            int hn = h + CHOL_NST - 1;
-            if (hn < nh) chol_load_stage(smem + (hn % CHOL_NST) * CHOL_STAGE_DOUBLES, Ai, Bk, lda, ldb, hn, same, tid);
+            const int hn = h + CHOL_NST - 1;
+            double *dst = smem + (hn % CHOL_NST) * CHOL_STAGE_DOUBLES;
+            if (hn < nh) chol_load_stage(dst, Ai, Bk, lda, ldb, hn, same, tid);
+            else if (hn < total) chol_load_tail(dst, tail, tail_ld, tid);
             cp_async_commit();
         }
         if (!skip) {
@@ -84,22 +99,29 @@ __device__ __forceinline__ void tile_accumulate(double (&acc)[4][4][2], const do
             const double *Bs = same ? As : As + GSUM_TILE * GSUM_LDH;
             const double *ap = As + (wm * 32 + g) * GSUM_LDH + t;
             const double *bp = Bs + (wn * 32 + g) * GSUM_LDH + t;
+            double a[2][4], b[2][4];
+#pragma unroll
+            for (int mi = 0; mi < 4; mi++) { a[0][mi] = ap[mi * 8 * GSUM_LDH]; b[0][mi] = bp[mi * 8 * GSUM_LDH]; }
 #pragma unroll
             for (int ks = 0; ks < GSUM_KH / 4; ks++) {
-                double a[4], b[4];
+                const int cur = ks & 1, nxt = cur ^ 1;
+                if (ks + 1 < GSUM_KH / 4) {
 #pragma unroll
-                for (int mi = 0; mi < 4; mi++) a[mi] = -ap[mi * 8 * GSUM_LDH + ks * 4];
-#pragma unroll
-                for (int ni = 0; ni < 4; ni++) b[ni] = bp[ni * 8 * GSUM_LDH + ks * 4];
+                    for (int mi = 0; mi < 4; mi++) {
+                        a[nxt][mi] = ap[mi * 8 * GSUM_LDH + (ks + 1) * 4];
+                        b[nxt][mi] = bp[mi * 8 * GSUM_LDH + (ks + 1) * 4];
+                    }
+                }
 #pragma unroll
                 for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], a[mi], b[ni]);
+                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], -a[cur][mi], b[cur][ni]);
             }
         }
     }
     cp_async_wait<0>();
     __syncthreads();
+    return tail ? smem + (nh % CHOL_NST) * CHOL_STAGE_DOUBLES : nullptr;
 }
 
 __device__ __forceinline__ void tile_load_acc(double (&acc)[4][4][2], const double *C, int64_t ldc) {
@@ -126,34 +148,85 @@ __device__ __forceinline__ void tile_store_acc_smem(const double (&acc)[4][4][2]
         }
 }
 
-// ---- epilogue 1: unblocked right-looking POTRF of a 64x64 tile held in smem (stride 65) -------------
-// Column j: s = sqrt(d), column scaled by 1/s (LAPACK dpotf2 scales by the reciprocal as well), rank-1
-// update of the trailing lower triangle.  One barrier per column; lane <-> row so that every shared
-// access is conflict free with the odd stride.  Returns the failing column (1-based) or 0.
-#define POTRF_LDS 65
-__device__ __forceinline__ int tile_potrf_smem(double *S, double *dg) {
-    const int tid = threadIdx.x, r = tid & 63, half = tid >> 6;
-    double rs_prev = 0.0;
-    int fail = 0;
-    for (int j = 0; j < GSUM_TILE; j++) {
+// ---- epilogue 1: POTRF of a 64x64 tile held in smem (stride GSUM_LDS), blocked by 8 columns ------------------
+// Per 8-column block: (1) warp 0 factors the 8x8 diagonal block with its rows in registers (one lane per row, pivots and
+// column entries exchanged by shuffles; column scaled by the reciprocal as LAPACK dpotf2 does); (2) the rows below are
+// solved against it, one thread per row; (3) the trailing 8x8 blocks get a rank-8 DMMA update.  Writes dg = diag(L) and
+// the failing column (1-based, LAPACK potrf convention) to *s_fail (0 = ok; must be zeroed by the caller).
+__device__ __forceinline__ void tile_potrf_blocked(double *S, double *dg, int *s_fail) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    for (int cb = 0; cb < 8; cb++) {
+        const int c0 = cb * 8;
+        if (w == 0) {
+            const int r = lane & 7;                      // lanes >= 8 mirror lanes 0..7 (full-mask shuffles)
+            double row[8];
+#pragma unroll
+            for (int c = 0; c < 8; c++) row[c] = S[(c0 + r) * GSUM_LDS + c0 + c];
+            int fail = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double d = __shfl_sync(0xffffffffu, row[j], j);
+                if (!(d > 0.0) && fail == 0) fail = c0 + j + 1;
+                const double sj = sqrt(d);
+                const double rs = 1.0 / sj;
+                const double lj = row[j] * rs;
+                row[j] = (r == j) ? sj : lj;
+#pragma unroll
+                for (int m = j + 1; m < 8; m++) {
+                    const double lm = __shfl_sync(0xffffffffu, lj, m);
+                    row[m] = fma(-lj, lm, row[m]);
+                }
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int c = 0; c < 8; c++) S[(c0 + r) * GSUM_LDS + c0 + c] = row[c];
+                double dv = row[0];
+#pragma unroll
+                for (int c = 1; c < 8; c++) dv = (c == r) ? row[c] : dv;      // row[r] without a runtime-indexed register array
+                dg[c0 + r] = dv;
+            }
+            if (lane == 0 && fail && *s_fail == 0) *s_fail = fail;
+        }
         __syncthreads();
-        const double d = S[j * POTRF_LDS + j];
-        if (!(d > 0.0)) { fail = j + 1; break; }
-        if (j > 0 && half == 0 && r > j - 1) S[r * POTRF_LDS + (j - 1)] *= rs_prev;   // retire column j-1
-        const double s = sqrt(d);
-        const double rs = 1.0 / s;
-        if (tid == j) dg[j] = s;
-        if (r > j) {
-            const double lrj = S[r * POTRF_LDS + j] * rs;
-            for (int m = j + 1 + half; m <= r; m += 2) {
-                const double lmj = S[m * POTRF_LDS + j] * rs;
-                S[r * POTRF_LDS + m] -= lrj * lmj;
+        if (cb == 7) break;
+        {   // (2) rows below the diagonal block: X = S L_D^{-T}
+            const int rr = c0 + 8 + tid;
+            if (rr < GSUM_TILE) {
+                double *row = S + rr * GSUM_LDS + c0;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double v = row[c];
+                    const double *lrow = S + (c0 + c) * GSUM_LDS + c0;
+#pragma unroll
+                    for (int m = 0; m < c; m++) v = fma(-x[m], lrow[m], v);
+                    x[c] = v * (1.0 / dg[c0 + c]);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) row[c] = x[c];
             }
         }
-        rs_prev = rs;
+        __syncthreads();
+        {   // (3) trailing update of the 8x8 blocks (rb, cb2), cb < cb2 <= rb <= 7
+            const int nt = 7 - cb, nblk = nt * (nt + 1) / 2;
+            for (int blk = w; blk < nblk; blk += CHOL_THREADS / 32) {
+                int rbi = 0, rem = blk;
+                while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
+                const int rb = cb + 1 + rbi, cb2 = cb + 1 + rem;
+                double *cp = S + (rb * 8 + g) * GSUM_LDS + cb2 * 8 + 2 * t;
+                double cc0 = cp[0], cc1 = cp[1];
+#pragma unroll
+                for (int k0 = 0; k0 < 8; k0 += 4) {
+                    const double a = S[(rb * 8 + g) * GSUM_LDS + c0 + k0 + t];
+                    const double b = S[(cb2 * 8 + g) * GSUM_LDS + c0 + k0 + t];
+                    dmma884(cc0, cc1, -a, b);
+                }
+                cp[0] = cc0; cp[1] = cc1;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    return fail;
 }
 
 // ---- epilogue 2: X = S * Lkk^{-T} (rows independent; each warp owns 16 rows) --------------------------
@@ -205,75 +278,70 @@ __device__ __forceinline__ void tile_trsm_smem(double *S, const double *Lk, cons
     }
 }
 
-// ---- kernels (multi-launch schedule: per tile column k one diagonal launch + one panel launch) ---------
-__global__ void __launch_bounds__(CHOL_THREADS, 2) chol_diag_kernel(BorderedBatch P, int k) {
-    extern __shared__ __align__(16) double smem[];
-    const int b = blockIdx.x, tid = threadIdx.x, w = tid >> 5;
+// ---- one tile task (i, k) of matrix b: accumulate, then POTRF (i == k) or TRSM (i > k); tile written once ---------
+__device__ __forceinline__ void tile_task(const BorderedBatch &P, int i, int k, int b, double *smem) {
+    const int tid = threadIdx.x, w = tid >> 5;
     double *Ab = P.A + (int64_t)b * P.bstride;
+    double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
+                           : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
     const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
-    double *C = Ab + (int64_t)k * GSUM_TILE * P.ld + k * GSUM_TILE;
+    double *C = Ri + k * GSUM_TILE;
+    const bool diag = (i == k);
+    const bool skip = diag && (w == 1);                  // warp (wm=0, wn=1): strictly upper block of a diagonal tile
     double acc[4][4][2];
-    const bool skip = (w == 1);          // warp (wm=0, wn=1): strictly upper block
     if (!skip) tile_load_acc(acc, C, P.ld);
-    tile_accumulate(acc, Ak, Ak, P.ld, P.ld, k, true, skip, smem);
-    double *S = smem;                                  // 64 x 65
-    double *dg = smem + GSUM_TILE * POTRF_LDS;         // 64
-    if (!skip) tile_store_acc_smem(acc, S, POTRF_LDS);
-    const int fail = tile_potrf_smem(S, dg);
-    if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
-    // write L_kk: lower triangle, exact zeros above the diagonal (numpy.linalg.cholesky convention)
-    for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        double2 v;
-        v.x = (c < r) ? S[r * POTRF_LDS + c] : (c == r ? dg[r] : 0.0);
-        v.y = (c + 1 < r) ? S[r * POTRF_LDS + c + 1] : (c + 1 == r ? dg[r] : 0.0);
-        if (fail) { v.x = v.y = nan(""); }
-        *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
-    }
-    if (P.logdet_part && w == 0) {
-        // 2 * sum log(L_jj), same form as gsum/models.py:1015,1250; padding columns (>= n) contribute log 1 = 0
-        double v = 0.0;
-        for (int j = (tid & 31); j < GSUM_TILE; j += 32)
-            if (k * GSUM_TILE + j < P.n) v += log(dg[j]);
-        v = warp_sum(v);
-        if (tid == 0) P.logdet_part[(int64_t)b * P.T + k] = fail ? nan("") : 2.0 * v;
+    double *Lk = tile_accumulate(acc, Ri, Ak, P.ld, P.ld, k, diag, skip, smem, diag ? nullptr : Ak + k * GSUM_TILE, P.ld);
+    double *S = smem + ((2 * k + 1) % CHOL_NST) * CHOL_STAGE_DOUBLES;      // a stage buffer the ring is done with
+    double *dg = S + GSUM_TILE * GSUM_LDS;                                    // 64 doubles behind the tile
+    int *s_fail = reinterpret_cast<int *>(dg + 2 * GSUM_TILE);
+    if (!skip) tile_store_acc_smem(acc, S, GSUM_LDS);
+    if (diag) {
+        if (tid == 0) *s_fail = 0;
+        __syncthreads();
+        tile_potrf_blocked(S, dg, s_fail);
+        const int fail = *s_fail;
+        if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
+        // write L_kk: lower triangle, exact zeros above the diagonal (numpy.linalg.cholesky convention)
+        for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            double2 v;
+            v.x = (c <= r) ? S[r * GSUM_LDS + c] : 0.0;
+            v.y = (c + 1 <= r) ? S[r * GSUM_LDS + c + 1] : 0.0;
+            if (fail) { v.x = v.y = nan(""); }
+            *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
+        }
+        if (P.logdet_part && w == 0) {
+            // 2 * sum log(L_jj), same form as gsum/models.py:1015,1250; padding columns (>= n) contribute log 1 = 0
+            double v = 0.0;
+            for (int j = (tid & 31); j < GSUM_TILE; j += 32)
+                if (k * GSUM_TILE + j < P.n) v += log(dg[j]);
+            v = warp_sum(v);
+            if (tid == 0) P.logdet_part[(int64_t)b * P.T + k] = fail ? nan("") : 2.0 * v;
+        }
+    } else {
+        double *rdiag = dg;
+        if (tid < GSUM_TILE) rdiag[tid] = 1.0 / Lk[tid * GSUM_LDS + tid];
+        __syncthreads();
+        tile_trsm_smem(S, Lk, rdiag);
+        __syncthreads();
+        for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            double2 v; v.x = S[r * GSUM_LDS + c]; v.y = S[r * GSUM_LDS + c + 1];
+            *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
+        }
     }
 }
 
+// ---- multi-launch schedule: per tile column k one diagonal launch + one panel launch ------------------------------
+__global__ void __launch_bounds__(CHOL_THREADS, 2) chol_diag_kernel(BorderedBatch P, int k) {
+    extern __shared__ __align__(16) double smem[];
+    tile_task(P, k, k, blockIdx.x, smem);
+}
 // Tile rows i = i0 + blockIdx.x of tile column k (i0 = k+1 during a factorisation; i0 = T for a solve with an
 // existing factor).  Rows >= T live in the border block W.
 __global__ void __launch_bounds__(CHOL_THREADS, 2) chol_panel_kernel(BorderedBatch P, int k, int i0) {
     extern __shared__ __align__(16) double smem[];
-    const int i = i0 + blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    double *Ab = P.A + (int64_t)b * P.bstride;
-    double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
-                           : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
-    const double *Ai = Ri;
-    const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
-    double *C = Ri + k * GSUM_TILE;
-    double acc[4][4][2];
-    tile_load_acc(acc, C, P.ld);
-    tile_accumulate(acc, Ai, Ak, P.ld, P.ld, k, false, false, smem);
-    double *S = smem;                                   // 64 x 68
-    double *Lk = smem + GSUM_TILE * GSUM_LDS;           // 64 x 68
-    double *rdiag = Lk + GSUM_TILE * GSUM_LDS;          // 64
-    tile_store_acc_smem(acc, S, GSUM_LDS);
-    const double *Lg = Ak + k * GSUM_TILE;
-    for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        const double2 v = *reinterpret_cast<const double2 *>(Lg + (int64_t)r * P.ld + c);
-        Lk[r * GSUM_LDS + c] = v.x; Lk[r * GSUM_LDS + c + 1] = v.y;
-        if (c == r) rdiag[r] = 1.0 / v.x;
-        if (c + 1 == r) rdiag[r] = 1.0 / v.y;
-    }
-    __syncthreads();
-    tile_trsm_smem(S, Lk, rdiag);
-    __syncthreads();
-    for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        double2 v; v.x = S[r * GSUM_LDS + c]; v.y = S[r * GSUM_LDS + c + 1];
-        *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
-    }
+    tile_task(P, i0 + blockIdx.x, k, blockIdx.y, smem);
 }
 
 // Schur-complement tile over the border rows:  C(i,i') -= Wt_i Wt_i'^T  summed over all T factor columns.
