@@ -19,6 +19,8 @@
 #include "common.cuh"
 
 #define CHOL_THREADS 128
+// barrier over the 128 math threads only (the dataflow kernel adds a producer warp that must not take part)
+#define CONS_SYNC() asm volatile("bar.sync 1, 128;" ::: "memory")
 #define CHOL_NST 3
 #define CHOL_STAGE_DOUBLES (2 * GSUM_TILE * GSUM_LDH)                 // A half-slab + B half-slab
 #define CHOL_SMEM_BYTES (CHOL_NST * CHOL_STAGE_DOUBLES * 8)           // 110592 B -> 2 CTAs / SM
@@ -188,7 +190,7 @@ __device__ __forceinline__ void tile_potrf_blocked(double *S, double *dg, int *s
             }
             if (lane == 0 && fail && *s_fail == 0) *s_fail = fail;
         }
-        __syncthreads();
+        CONS_SYNC();
         if (cb == 7) break;
         {   // (2) rows below the diagonal block: X = S L_D^{-T}
             const int rr = c0 + 8 + tid;
@@ -207,7 +209,7 @@ __device__ __forceinline__ void tile_potrf_blocked(double *S, double *dg, int *s
                 for (int c = 0; c < 8; c++) row[c] = x[c];
             }
         }
-        __syncthreads();
+        CONS_SYNC();
         {   // (3) trailing update of the 8x8 blocks (rb, cb2), cb < cb2 <= rb <= 7
             const int nt = 7 - cb, nblk = nt * (nt + 1) / 2;
             for (int blk = w; blk < nblk; blk += CHOL_THREADS / 32) {
@@ -225,7 +227,7 @@ __device__ __forceinline__ void tile_potrf_blocked(double *S, double *dg, int *s
                 cp[0] = cc0; cp[1] = cc1;
             }
         }
-        __syncthreads();
+        CONS_SYNC();
     }
 }
 
@@ -279,25 +281,18 @@ __device__ __forceinline__ void tile_trsm_smem(double *S, const double *Lk, cons
 }
 
 // ---- one tile task (i, k) of matrix b: accumulate, then POTRF (i == k) or TRSM (i > k); tile written once ---------
-__device__ __forceinline__ void tile_task(const BorderedBatch &P, int i, int k, int b, double *smem) {
+// Epilogue shared by the multi-launch and the dataflow schedules: S (a free 64x68 smem buffer with 160 spare doubles
+// behind it), Lk = L_kk staged in smem (panel tasks).  Called by the 128 math threads.
+__device__ __forceinline__ void tile_epilogue(const BorderedBatch &P, int i, int k, int b, double (&acc)[4][4][2], double *S,
+                                              double *Lk, double *C, bool skip) {
     const int tid = threadIdx.x, w = tid >> 5;
-    double *Ab = P.A + (int64_t)b * P.bstride;
-    double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
-                           : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
-    const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
-    double *C = Ri + k * GSUM_TILE;
     const bool diag = (i == k);
-    const bool skip = diag && (w == 1);                  // warp (wm=0, wn=1): strictly upper block of a diagonal tile
-    double acc[4][4][2];
-    if (!skip) tile_load_acc(acc, C, P.ld);
-    double *Lk = tile_accumulate(acc, Ri, Ak, P.ld, P.ld, k, diag, skip, smem, diag ? nullptr : Ak + k * GSUM_TILE, P.ld);
-    double *S = smem + ((2 * k + 1) % CHOL_NST) * CHOL_STAGE_DOUBLES;      // a stage buffer the ring is done with
     double *dg = S + GSUM_TILE * GSUM_LDS;                                    // 64 doubles behind the tile
     int *s_fail = reinterpret_cast<int *>(dg + 2 * GSUM_TILE);
     if (!skip) tile_store_acc_smem(acc, S, GSUM_LDS);
     if (diag) {
         if (tid == 0) *s_fail = 0;
-        __syncthreads();
+        CONS_SYNC();
         tile_potrf_blocked(S, dg, s_fail);
         const int fail = *s_fail;
         if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
@@ -321,15 +316,32 @@ __device__ __forceinline__ void tile_task(const BorderedBatch &P, int i, int k, 
     } else {
         double *rdiag = dg;
         if (tid < GSUM_TILE) rdiag[tid] = 1.0 / Lk[tid * GSUM_LDS + tid];
-        __syncthreads();
+        CONS_SYNC();
         tile_trsm_smem(S, Lk, rdiag);
-        __syncthreads();
+        CONS_SYNC();
         for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
             const int r = e >> 5, c = (e & 31) * 2;
             double2 v; v.x = S[r * GSUM_LDS + c]; v.y = S[r * GSUM_LDS + c + 1];
             *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
         }
     }
+}
+
+
+__device__ __forceinline__ void tile_task(const BorderedBatch &P, int i, int k, int b, double *smem) {
+    const int tid = threadIdx.x, w = tid >> 5;
+    double *Ab = P.A + (int64_t)b * P.bstride;
+    double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
+                           : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
+    const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
+    double *C = Ri + k * GSUM_TILE;
+    const bool diag = (i == k);
+    const bool skip = diag && (w == 1);                  // warp (wm=0, wn=1): strictly upper block of a diagonal tile
+    double acc[4][4][2];
+    if (!skip) tile_load_acc(acc, C, P.ld);
+    double *Lk = tile_accumulate(acc, Ri, Ak, P.ld, P.ld, k, diag, skip, smem, diag ? nullptr : Ak + k * GSUM_TILE, P.ld);
+    double *S = smem + ((2 * k + 1) % CHOL_NST) * CHOL_STAGE_DOUBLES;      // a stage buffer the ring is done with
+    tile_epilogue(P, i, k, b, acc, S, Lk, C, skip);
 }
 
 // ---- multi-launch schedule: per tile column k one diagonal launch + one panel launch ------------------------------

@@ -28,6 +28,12 @@ struct gsum_ctx {
     cudaEvent_t prof_ev[2 * 256];
     double prof_flops;          // algorithmic flops of the bracketed factorisations
     int64_t prof_border_rows;   // right-hand sides riding along with the current factorisation
+    // dataflow schedule: cached task list (device) and its key, flags, sticky abort indicator
+    void *df_tasks; size_t df_tasks_cap; int df_key[4]; int df_ntasks;
+    void *df_flags; size_t df_flags_cap;
+    int *df_ctl;                // [0] task counter, [1] abort flag, [2] sticky abort (device)
+    int df_grid;                // co-resident CTAs of the dataflow kernel (0 = not yet queried)
+    int use_multilaunch;        // GSUM_B200_SCHEDULE=multilaunch: per-column launches instead (debug / comparison)
 };
 
 static inline int gsum_fail(gsum_ctx *c, int code, const char *fmt, ...) {

@@ -1,0 +1,304 @@
+// Persistent dataflow schedule of the bordered Cholesky (K2 + K3 in ONE launch).
+//
+// Every tile task (i, k, b) of the whole batch sits in one host-built list, ordered so that a task's dependencies
+// always precede it; CTAs (two per SM, all co-resident: cooperative launch) claim tasks in list order from a global
+// counter and synchronise through per-tile "done" flags in global memory — no kernel boundary between tile columns,
+// so one matrix's latency-bound diagonal tile overlaps the DMMA-bound panel tiles of all the others.
+//
+// CTA = 4 math warps + 1 producer warp.  The producer waits on the dependency flags (acquire), then streams the
+// operand half-slabs with 16-byte async copies (cp.async.cg -> SASS LDGSTS, L2 only) into a 3-stage shared-memory ring
+// guarded by full/empty mbarriers (completion via cp.async.mbarrier.arrive); the math warps never issue a global load
+// for operands and never spin on a flag.  The epilogue's L_kk rides through the same ring as the last stage.
+// (Measured, profiles/r01_notes.md: feeding the ring with 1-D bulk copies of one 256-byte row each — cp.async.bulk /
+// UBLKCP — costs ~73 cycles per request on the TMA unit and starves the math warps 50 % of the time; row-sized
+// requests are too small for the TMA engine, and the padded, bank-conflict-free smem layout rules out tiled tensor maps.)
+//
+// Deadlock freedom: tasks are claimed in list order and a task only waits for tasks earlier in the list, which are
+// therefore already claimed by resident CTAs; the earliest unfinished task never waits.  Every wait loop is bounded by
+// a watchdog (abort flag) so a logic error surfaces as an error code, not as a hung GPU.
+#pragma once
+#include "chol.cuh"
+
+#define DF_THREADS 160
+#define DF_PRODUCER_WARP 4
+#define DF_WATCHDOG_CYCLES (4000000000LL)       // ~2 s at 1.9 GHz
+
+struct DataflowArgs {
+    BorderedBatch P;
+    const int4 *tasks;      // (i, k, b, -) in schedule order
+    int ntasks;
+    int *counter;           // next task to claim (zeroed before launch)
+    int *flags;             // done flag per (b, i, k): index (b * Trows + i) * T + k  (zeroed before launch)
+    int *abort_flag;        // set by any thread whose wait exceeded the watchdog
+    long long *stats;       // optional per-CTA cycle counters [grid][8] (dev instrumentation; nullptr = off)
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (count pre-charged at init: .noinc)
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Bounded mbarrier wait; returns false if the kernel is aborting.
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, unsigned parity, const int *abort_flag) {
+    int spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 1023) == 0 && ld_acquire(abort_flag)) return false;
+    }
+    return true;
+}
+// Bounded wait for a done flag (one lane polls).  Returns false on abort / watchdog.
+__device__ __forceinline__ bool flag_wait(const int *flag, int *abort_flag) {
+    if (ld_acquire(flag)) return true;
+    const long long t0 = clock64();
+    while (!ld_acquire(flag)) {
+        __nanosleep(64);
+        if (ld_acquire(abort_flag)) return false;
+        if (clock64() - t0 > DF_WATCHDOG_CYCLES) { atomicExch(abort_flag, 1); return false; }
+    }
+    return true;
+}
+
+// AND-reduction + barrier over the 128 math threads (named barrier 2)
+__device__ __forceinline__ bool cons_sync_and(bool v) {
+    unsigned r;
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, 2, 128, q;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"((unsigned)v) : "memory");
+    return r != 0;
+}
+
+struct RingState { int stage; unsigned phase; };
+__device__ __forceinline__ void ring_advance(RingState &r) {
+    if (++r.stage == CHOL_NST) { r.stage = 0; r.phase ^= 1u; }
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DataflowArgs D) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[CHOL_NST], empty_bar[CHOL_NST];
+    __shared__ int s_task;
+    const BorderedBatch &P = D.P;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < CHOL_NST; s++) { mbar_init(&full_bar[s], 32); mbar_init(&empty_bar[s], CHOL_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    RingState ring = {0, 0u};           // advanced identically by the producer and the math warps
+    long long st_wait_full = 0, st_wait_flag = 0, st_wait_empty = 0, st_epi = 0, st_ntask = 0, st_acc0 = 0;
+    const long long st_t0 = clock64();
+    const bool st_on = D.stats != nullptr;
+    bool alive = true;
+    for (;;) {
+        if (tid == 0) s_task = atomicAdd(D.counter, 1);
+        __syncthreads();
+        const int tix = s_task;
+        if (tix >= D.ntasks || !alive) break;
+        const int4 tk = D.tasks[tix];
+        const int i = tk.x, k = tk.y, b = tk.z;
+        const bool diag = (i == k);
+        double *Ab = P.A + (int64_t)b * P.bstride;
+        double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
+                               : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
+        const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
+        const int nh = 2 * k;
+        const int *frow_i = D.flags + ((int64_t)b * P.Trows + i) * P.T;
+        const int *frow_k = D.flags + ((int64_t)b * P.Trows + k) * P.T;
+
+        if (w == DF_PRODUCER_WARP) {
+            // ======================= producer: dependency flags -> bulk copies into the ring =======================
+            for (int h = 0; h < nh && alive; h++) {
+                const int j = h >> 1;
+                if ((h & 1) == 0) {               // new slab j: tiles (i, j) and (k, j) must be final
+                    int ok = 1;
+                    long long tq = st_on ? clock64() : 0;
+                    if (lane == 0) ok = flag_wait(frow_i + j, D.abort_flag) && (diag || flag_wait(frow_k + j, D.abort_flag));
+                    if (st_on) st_wait_flag += clock64() - tq;
+                    alive = __shfl_sync(0xffffffffu, ok, 0) != 0;
+                    if (!alive) break;
+                }
+                if (lane == 0) {
+                    long long tq = st_on ? clock64() : 0;
+                    alive = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, D.abort_flag);
+                    if (st_on) st_wait_empty += clock64() - tq;
+                }
+                alive = __shfl_sync(0xffffffffu, (int)alive, 0) != 0;
+                if (!alive) break;
+                double *As = smem + ring.stage * CHOL_STAGE_DOUBLES, *Bs = As + GSUM_TILE * GSUM_LDH;
+                const int col0 = j * GSUM_TILE + (h & 1) * GSUM_KH;
+                // 64 rows x 256 B per operand = 1024 16-byte chunks; a warp-wide LDGSTS moves two rows
+#pragma unroll 8
+                for (int q = 0; q < 32; q++) {
+                    const int c = lane + 32 * q, row = c >> 4, ch = (c & 15) * 2;
+                    cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
+                }
+                if (!diag) {
+#pragma unroll 8
+                    for (int q = 0; q < 32; q++) {
+                        const int c = lane + 32 * q, row = c >> 4, ch = (c & 15) * 2;
+                        cp_async16(Bs + row * GSUM_LDH + ch, Ak + (int64_t)row * P.ld + col0 + ch);
+                    }
+                }
+                cp_async_mbar_arrive(&full_bar[ring.stage]);
+                ring_advance(ring);
+            }
+            if (!diag && alive) {                 // tail: L_kk for the triangular solve
+                int ok = 1;
+                if (lane == 0) {
+                    ok = flag_wait(frow_k + k, D.abort_flag);
+                    if (ok) ok = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, D.abort_flag);
+                }
+                alive = __shfl_sync(0xffffffffu, ok, 0) != 0;
+                if (alive) {
+                    double *Ls = smem + ring.stage * CHOL_STAGE_DOUBLES;
+                    const double *Lg = Ak + k * GSUM_TILE;
+#pragma unroll 8
+                    for (int q = 0; q < 64; q++) {
+                        const int c = lane + 32 * q, row = c >> 5, ch = (c & 31) * 2;
+                        cp_async16(Ls + row * GSUM_LDS + ch, Lg + (int64_t)row * P.ld + ch);
+                    }
+                    cp_async_mbar_arrive(&full_bar[ring.stage]);
+                    ring_advance(ring);
+                }
+            }
+        } else {
+            // ======================= math warps: DMMA main loop + epilogue ==========================================
+            const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
+            const bool skip = diag && (w == 1);
+            double *C = Ri + k * GSUM_TILE;
+            double acc[4][4][2];
+            long long tq0 = st_on ? clock64() : 0;
+            if (!skip) tile_load_acc(acc, C, P.ld);
+            if (st_on) { st_acc0 += clock64() - tq0; st_ntask++; }
+            for (int h = 0; h < nh && alive; h++) {
+                long long tq = st_on ? clock64() : 0;
+                alive = mbar_wait(&full_bar[ring.stage], ring.phase, D.abort_flag);
+                if (st_on) st_wait_full += clock64() - tq;
+                if (!alive) break;
+                if (!skip) {
+                    const double *As = smem + ring.stage * CHOL_STAGE_DOUBLES;
+                    const double *Bs = diag ? As : As + GSUM_TILE * GSUM_LDH;
+                    const double *ap = As + (wm * 32 + g) * GSUM_LDH + t;
+                    const double *bp = Bs + (wn * 32 + g) * GSUM_LDH + t;
+                    double a[2][4], bb[2][4];
+#pragma unroll
+                    for (int mi = 0; mi < 4; mi++) { a[0][mi] = ap[mi * 8 * GSUM_LDH]; bb[0][mi] = bp[mi * 8 * GSUM_LDH]; }
+#pragma unroll
+                    for (int ks = 0; ks < GSUM_KH / 4; ks++) {
+                        const int cur = ks & 1, nxt = cur ^ 1;
+                        if (ks + 1 < GSUM_KH / 4) {
+#pragma unroll
+                            for (int mi = 0; mi < 4; mi++) {
+                                a[nxt][mi] = ap[mi * 8 * GSUM_LDH + (ks + 1) * 4];
+                                bb[nxt][mi] = bp[mi * 8 * GSUM_LDH + (ks + 1) * 4];
+                            }
+                        }
+#pragma unroll
+                        for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+                            for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], -a[cur][mi], bb[cur][ni]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
+                ring_advance(ring);
+            }
+            double *Lk = nullptr;
+            int tail_stage = -1;
+            if (!diag && alive) {
+                long long tq = st_on ? clock64() : 0;
+                alive = mbar_wait(&full_bar[ring.stage], ring.phase, D.abort_flag);
+                if (st_on) st_wait_full += clock64() - tq;
+                Lk = smem + ring.stage * CHOL_STAGE_DOUBLES;
+                tail_stage = ring.stage;
+                ring_advance(ring);
+            }
+            // the block must agree on `alive` before the barriers inside the epilogue
+            alive = cons_sync_and(alive);
+            if (alive) {
+                // every filled stage has been consumed, so any buffer but the tail's is free for the output tile
+                const int s_stage = (tail_stage + 1 + (tail_stage < 0 ? 1 : 0)) % CHOL_NST;
+                double *S = smem + s_stage * CHOL_STAGE_DOUBLES;
+                long long tq = st_on ? clock64() : 0;
+                tile_epilogue(P, i, k, b, acc, S, Lk, C, skip);
+                if (st_on) st_epi += clock64() - tq;
+                __threadfence();                              // tile stores visible device-wide before the flag
+                CONS_SYNC();
+                if (tid == 0) st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
+                if (tail_stage >= 0 && lane == 0) mbar_arrive(&empty_bar[tail_stage]);     // release the tail's stage
+            }
+        }
+        // both roles learn whether anyone aborted; also separates tasks
+        alive = __syncthreads_and(alive ? 1 : 0) != 0;
+        if (!alive) break;
+    }
+    if (st_on && (tid == 0 || tid == DF_PRODUCER_WARP * 32)) {
+        long long *o = D.stats + (int64_t)blockIdx.x * 8;
+        if (tid == 0) { o[0] = clock64() - st_t0; o[1] = st_wait_full; o[2] = st_epi; o[3] = st_ntask; o[4] = st_acc0; }
+        else { o[5] = st_wait_flag; o[6] = st_wait_empty; }
+    }
+}
+
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+__global__ void df_init_kernel(int *flags, int *counter_abort, int64_t batch, int Trows, int T, int factor_done) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 2) counter_abort[idx] = 0;
+    if (idx >= batch * Trows * T) return;
+    const int i = (int)((idx / T) % Trows);
+    flags[idx] = (factor_done && i < T) ? 1 : 0;
+}
+// After the run: a watchdog abort marks every matrix as failed so that no caller consumes half-factored data.
+__global__ void df_check_kernel(const int *abort_flag, int *info, int64_t batch, int *sticky) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (*abort_flag == 0) return;
+    if (b == 0 && sticky) *sticky = 1;
+    if (info && b < batch) info[b] = 0x7fffffff;
+}
+
+#include <vector>
+// Task list in dependency order with one column of look-ahead: right after the first sub-diagonal tile of column k comes
+// the diagonal tile of column k+1, so that the (latency-bound) POTRF chain runs ahead of the bulk of column k.
+static inline void df_build_tasks(std::vector<int4> &out, int T, int Trows, int batch, bool solve_only) {
+    out.clear();
+    if (solve_only) {
+        for (int k = 0; k < T; k++)
+            for (int i = T; i < Trows; i++)
+                for (int b = 0; b < batch; b++) out.push_back(make_int4(i, k, b, 0));
+        return;
+    }
+    for (int k = 0; k < T; k++) {
+        if (k == 0) for (int b = 0; b < batch; b++) out.push_back(make_int4(0, 0, b, 0));
+        if (k + 1 < Trows) for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k, b, 0));
+        if (k + 1 < T) for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k + 1, b, 0));
+        for (int b = 0; b < batch; b++)
+            for (int i = k + 2; i < Trows; i++) out.push_back(make_int4(i, k, b, 0));
+    }
+}

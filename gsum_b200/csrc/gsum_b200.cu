@@ -7,6 +7,8 @@
 #include "lml.cuh"
 #include "solve.cuh"
 #include "diag.cuh"
+#include "dataflow.cuh"
+#include <cstdlib>
 
 #define LAUNCHED(ctx, n) ((ctx)->launches += (n))
 
@@ -34,6 +36,8 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    const char *sched = getenv("GSUM_B200_SCHEDULE");
+    c->use_multilaunch = (sched && strcmp(sched, "multilaunch") == 0) ? 1 : 0;
     *out = c;
     return 0;
 }
@@ -43,6 +47,9 @@ extern "C" int gsum_ctx_destroy(gsum_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 24; i++) if (c->ws[i]) cudaFree(c->ws[i]);
+    if (c->df_tasks) cudaFree(c->df_tasks);
+    if (c->df_flags) cudaFree(c->df_flags);
+    if (c->df_ctl) cudaFree(c->df_ctl);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -105,7 +112,17 @@ static int dev_out_finish(gsum_ctx *c, void *host, const void *dev, size_t bytes
 static int finish(gsum_ctx *c, int mem_kind) {
     GSUM_CUDA(c, cudaPeekAtLastError());
     GSUM_CUDA(c, cudaGetLastError());
-    if (mem_kind == GSUM_MEM_HOST) GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (mem_kind == GSUM_MEM_HOST) {
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->df_ctl) {
+            int sticky = 0;
+            GSUM_CUDA(c, cudaMemcpy(&sticky, c->df_ctl + 2, sizeof(int), cudaMemcpyDeviceToHost));
+            if (sticky) {
+                cudaMemset(c->df_ctl + 2, 0, sizeof(int));
+                return gsum_fail(c, -101, "dataflow Cholesky aborted by its watchdog (dependency wait exceeded %lld cycles)", (long long)DF_WATCHDOG_CYCLES);
+            }
+        }
+    }
     return 0;
 }
 
@@ -115,6 +132,80 @@ static int scale_coords(gsum_ctx *c, const double *dX, const double *dls, double
     scale_coords_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(dX, dls, dXS, n, d, ls_dim, batch);
     LAUNCHED(c, 1);
     return 0;
+}
+
+// ---- dataflow schedule of the bordered factorisation / border solve (one cooperative launch) ------------------------
+static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
+    GSUM_TRY(chol_set_attrs(c));
+    if (c->df_grid == 0) {
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+        int per_sm = 0;
+        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_dataflow_kernel, DF_THREADS, CHOL_SMEM_BYTES));
+        if (per_sm < 1) return gsum_fail(c, -102, "dataflow kernel does not fit on an SM");
+        c->df_grid = per_sm * c->sm_count;
+    }
+    const int key[4] = {P.T, P.Trows, batch, solve_only ? 1 : 0};
+    if (memcmp(key, c->df_key, sizeof(key)) != 0 || !c->df_tasks) {
+        std::vector<int4> tasks;
+        df_build_tasks(tasks, P.T, P.Trows, batch, solve_only);
+        const size_t bytes = tasks.size() * sizeof(int4);
+        if (c->df_tasks_cap < bytes) {
+            GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+            if (c->df_tasks) GSUM_CUDA(c, cudaFree(c->df_tasks));
+            GSUM_CUDA(c, cudaMalloc(&c->df_tasks, bytes + 4096));
+            c->df_tasks_cap = bytes + 4096;
+        }
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // the previous list may still be in use
+        GSUM_CUDA(c, cudaMemcpy(c->df_tasks, tasks.data(), bytes, cudaMemcpyHostToDevice));
+        memcpy(c->df_key, key, sizeof(key));
+        c->df_ntasks = (int)tasks.size();
+    }
+    const size_t fbytes = sizeof(int) * (size_t)batch * P.Trows * P.T;
+    if (c->df_flags_cap < fbytes) {
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->df_flags) GSUM_CUDA(c, cudaFree(c->df_flags));
+        GSUM_CUDA(c, cudaMalloc(&c->df_flags, fbytes + 4096));
+        c->df_flags_cap = fbytes + 4096;
+    }
+    if (!c->df_ctl) {
+        GSUM_CUDA(c, cudaMalloc((void **)&c->df_ctl, 4 * sizeof(int)));
+        GSUM_CUDA(c, cudaMemsetAsync(c->df_ctl, 0, 4 * sizeof(int), c->stream));
+    }
+    const int64_t nflags = (int64_t)batch * P.Trows * P.T;
+    df_init_kernel<<<(unsigned)((nflags + 255) / 256 + 1), 256, 0, c->stream>>>((int *)c->df_flags, c->df_ctl, batch, P.Trows, P.T, solve_only ? 1 : 0);
+    DataflowArgs D;
+    D.P = P; D.tasks = (const int4 *)c->df_tasks; D.ntasks = c->df_ntasks; D.counter = c->df_ctl; D.flags = (int *)c->df_flags;
+    D.abort_flag = c->df_ctl + 1;
+    D.stats = nullptr;
+    static long long *dbg_stats = nullptr;
+    if (getenv("GSUM_B200_DF_STATS")) {
+        if (!dbg_stats) cudaMalloc((void **)&dbg_stats, sizeof(long long) * 8 * 1024);
+        cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * 8 * 1024, c->stream);
+        D.stats = dbg_stats;
+    }
+    int grid = c->df_grid < D.ntasks ? c->df_grid : D.ntasks;
+    void *args[] = {&D};
+    GSUM_CUDA(c, cudaLaunchCooperativeKernel((const void *)chol_dataflow_kernel, dim3(grid), dim3(DF_THREADS), args, CHOL_SMEM_BYTES, c->stream));
+    df_check_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, c->stream>>>(c->df_ctl + 1, P.info, batch, c->df_ctl + 2);
+    c->launches += 3;
+    GSUM_CUDA(c, cudaPeekAtLastError());
+    if (D.stats) {       // dev instrumentation: print the per-CTA cycle split of this launch
+        std::vector<long long> h(8 * grid);
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
+        double tot = 0, wf = 0, ep = 0, nt = 0, a0 = 0, fl = 0, em = 0;
+        for (int g = 0; g < grid; g++) { tot += h[8*g]; wf += h[8*g+1]; ep += h[8*g+2]; nt += h[8*g+3]; a0 += h[8*g+4]; fl += h[8*g+5]; em += h[8*g+6]; }
+        fprintf(stderr, "[df] grid %d tasks %.0f  avg cycles/CTA: total %.0f | math: wait_full %.0f (%.0f%%) epilogue %.0f (%.0f%%) acc_load %.0f (%.0f%%) | producer: wait_flag %.0f (%.0f%%) wait_empty %.0f (%.0f%%)\n",
+                grid, nt, tot / grid, wf / grid, 100 * wf / tot, ep / grid, 100 * ep / tot, a0 / grid, 100 * a0 / tot, fl / grid, 100 * fl / tot, em / grid, 100 * em / tot);
+    }
+    return 0;
+}
+static int factor_run(gsum_ctx *c, const BorderedBatch &P, int batch) {
+    return c->use_multilaunch ? chol_bordered_run(c, P, batch) : dataflow_run(c, P, batch, false);
+}
+static int solve_run(gsum_ctx *c, const BorderedBatch &P, int batch) {
+    if (P.Trows - P.T <= 0) return 0;
+    return c->use_multilaunch ? chol_solve_border_run(c, P, batch) : dataflow_run(c, P, batch, true);
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------------
@@ -204,7 +295,7 @@ static int factor_bordered(gsum_ctx *c, double *dA, int64_t n, int Trows, int64_
         if (!c->prof_ev[2 * c->prof_count]) { cudaEventCreate(&c->prof_ev[2 * c->prof_count]); cudaEventCreate(&c->prof_ev[2 * c->prof_count + 1]); }
         cudaEventRecord(c->prof_ev[2 * c->prof_count], c->stream);
     }
-    GSUM_TRY(chol_bordered_run(c, P, (int)batch));
+    GSUM_TRY(factor_run(c, P, (int)batch));
     if (prof) {
         cudaEventRecord(c->prof_ev[2 * c->prof_count + 1], c->stream);
         c->prof_count++;
@@ -426,7 +517,7 @@ extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B
     GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dW));
     pad_factor(c, (const double *)dL, n, (double *)dF);
     launch_transpose_in(c, (const double *)dB, n, nrhs, nullptr, nullptr, 0, 1.0, (double *)dW, np, rp);
-    GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
     double *dBout = (double *)dB;     // in place (caller's device buffer or our staging copy)
     if (forward_only) {
         launch_transpose_out(c, (const double *)dW, np, n, nrhs, 0, 1.0, nullptr, dBout);
@@ -438,7 +529,7 @@ extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B
         dim3 g2((unsigned)rp, (unsigned)((np + 255) / 256));
         flip_rows_kernel<<<g2, 256, 0, c->stream>>>((const double *)dW, (double *)dW2, np, n);
         LAUNCHED(c, 2);
-        GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW2, np, T, rp), 1));
+        GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW2, np, T, rp), 1));
         launch_transpose_out(c, (const double *)dW2, np, n, nrhs, 1, 1.0, nullptr, dBout);
     }
     GSUM_TRY(dev_out_finish(c, B, dBout, sizeof(double) * n * nrhs, mem_kind));
@@ -686,7 +777,7 @@ extern "C" int gsum_predict(gsum_ctx *c, gsum_fit *f, const gsum_predict_args *a
     if (trunc) launch_scale_cov(c, W, np, m, n, (const double *)dsn, (const double *)dso, (const double *)dqn, (const double *)dqo, g, cov_factor, a->kernel_add);
     launch_transpose_in(c, (const double *)dyc, n, n_y, (const double *)dmo, nullptr, 0, 1.0, Wy, np, want_basis ? n_y : yp);
     if (want_basis) launch_transpose_in(c, (const double *)dbo, n, 1, nullptr, nullptr, 0, 1.0, Wy + (int64_t)n_y * np, np, yp - n_y);
-    GSUM_TRY(chol_solve_border_run(c, solve_desc(F, W, np, T, rows_pad), 1));
+    GSUM_TRY(solve_run(c, solve_desc(F, W, np, T, rows_pad), 1));
 
     // mean
     if (a->mean_out) {
@@ -784,7 +875,7 @@ extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, con
     GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dW));
     pad_factor(c, (const double *)dL, n, (double *)dF);
     launch_transpose_in(c, (const double *)dY, n, n_curves, (const double *)dmean, nullptr, 0, 1.0, (double *)dW, np, rp);
-    GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
     if (E) {
         void *dE;
         GSUM_TRY(dev_out(c, WS_IO2, E, sizeof(double) * n * n_curves, mem_kind, &dE));
@@ -876,7 +967,7 @@ extern "C" int gsum_pc_errors(gsum_ctx *c, const double *Lp, const int32_t *piv,
     pad_factor(c, (const double *)dL, n, (double *)dF);
     // solve(G, r) with G = Lp[p_inv]  <=>  Lp e = r[piv]: gather rows in pivot order, forward substitute (gsum/diagnostics.py:103-104)
     launch_transpose_in(c, (const double *)dY, n, n_curves, (const double *)dmean, (const int32_t *)dpiv, 0, 1.0, (double *)dW, np, rp);
-    GSUM_TRY(chol_solve_border_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
     GSUM_TRY(dev_out(c, WS_IO2, E, sizeof(double) * n * n_curves, mem_kind, &dE));
     launch_transpose_out(c, (const double *)dW, np, n, n_curves, 0, 1.0, nullptr, (double *)dE);
     GSUM_TRY(dev_out_finish(c, E, dE, sizeof(double) * n * n_curves, mem_kind));
