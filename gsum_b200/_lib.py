@@ -14,7 +14,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsum_b200.so")
+LIB_PATH = os.environ.get("GSUM_B200_LIB") or os.path.join(_HERE, "libgsum_b200.so")    # override: A/B builds during development
 
 MEM_HOST, MEM_DEVICE = 0, 1
 PREDICT_MEAN, PREDICT_VAR, PREDICT_COV = 0, 1, 2

@@ -21,7 +21,12 @@
 #define CHOL_THREADS 128
 // barrier over the 128 math threads only (the dataflow kernel adds a producer warp that must not take part)
 #define CONS_SYNC() asm volatile("bar.sync 1, 128;" ::: "memory")
+#ifndef CHOL_NST
 #define CHOL_NST 3
+#endif
+#ifndef CHOL_CTAS_PER_SM
+#define CHOL_CTAS_PER_SM 2
+#endif
 #define CHOL_STAGE_DOUBLES (2 * GSUM_TILE * GSUM_LDH)                 // A half-slab + B half-slab
 #define CHOL_SMEM_BYTES (CHOL_NST * CHOL_STAGE_DOUBLES * 8)           // 110592 B -> 2 CTAs / SM
 
@@ -36,6 +41,7 @@ struct BorderedBatch {
     int *info;          // per-matrix status: 0 ok, j+1 = first non-positive pivot (LAPACK potrf convention)
     double *logdet_part;  // (batch, T): sum_j 2*log(L_jj) over the 64 columns of diagonal tile k
     int n;              // true order N (columns >= n are identity padding and excluded from logdet)
+    int border_used;    // border rows in use, counted from the first border row (0 = unknown: every border tile row is full)
 };
 
 // ---- operand staging ---------------------------------------------------------------------
@@ -68,16 +74,57 @@ __device__ __forceinline__ void chol_load_tail(double *st, const double *src, in
     }
 }
 
-// acc(64x64, warp tile 32x32) -= Ai[64 x 64*nslab] * Bk[64 x 64*nslab]^T     (acc preloaded by the caller)
-// `skip` lets a warp sit out the DMMA work (strict upper block of a diagonal tile) while still taking part in the
-// copies and barriers.  `tail` (optional) is one more 64x64 tile streamed through the same ring right behind the last
-// operand slab — the epilogue's L_kk — so its latency hides under the main loop; the function returns the stage buffer
-// it landed in.  Fragments are double-buffered in registers so the LDS latency of step ks+1 hides under the DMMAs of ks.
-__device__ __forceinline__ double *tile_accumulate(double (&acc)[4][4][2], const double *Ai, const double *Bk,
-                                                   int64_t lda, int64_t ldb, int nslab, bool same, bool skip,
-                                                   double *smem, const double *tail = nullptr, int64_t tail_ld = 0) {
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
+// ---- warp tile ------------------------------------------------------------------------------------------------
+// Each of the 4 math warps owns 16 rows x 64 columns of the 64x64 CTA tile, held as DMMA C fragments:
+//     acc[mt][nt][e]  <->  row = 16*w + 8*mt + g,  col = 8*nt + 2*t + e        (lane = 4*g + t)
+// A whole tile row per warp is what lets the triangular solve of the epilogue run in registers (rows are independent).
+typedef double Acc[2][8][2];
+
+// One pipeline stage (K depth 32): acc -= A[16 rows of this warp] * B[8*ntm rows]^T.  `ntm` = n-tiles this warp needs
+// (8 everywhere except on a diagonal tile, where warp w only owns columns < 16*(w+1)); FULL drops the predicates.
+// Issue order: two k-steps at a time, accumulators in groups of DMMA_GROUP — so a DMMA depends on the one DMMA_GROUP
+// instructions earlier and the warp never has more than ~DMMA_GROUP of them queued in the FP64 pipe.  (Measured,
+// tools/fp64_latency.cu: a warp streaming 16 independent DMMAs keeps the pipe's queue full and every FP64 instruction
+// of another warp on the same SM sub-partition — the epilogues' dependent chains — then takes ~275 cycles instead of 32.)
+#ifndef DMMA_GROUP
+#define DMMA_GROUP 4
+#endif
+template <bool FULL>
+__device__ __forceinline__ void stage_mma(Acc &acc, const double *As, const double *Bs, int ntm) {
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 3, g = lane >> 2, t = lane & 3;
+    const double *ap = As + (w * 16 + g) * GSUM_LDH + t;
+    const double *bp = Bs + g * GSUM_LDH + t;
+    constexpr int NTG = DMMA_GROUP / 2;                  // n tiles per group (x 2 m tiles)
+#pragma unroll
+    for (int ks = 0; ks < GSUM_KH / 4; ks += 2) {
+        double a[2][2], b[2][8];
+#pragma unroll
+        for (int kk = 0; kk < 2; kk++) {
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) a[kk][mt] = -ap[mt * 8 * GSUM_LDH + (ks + kk) * 4];
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++) if (FULL || nt < ntm) b[kk][nt] = bp[nt * 8 * GSUM_LDH + (ks + kk) * 4];
+        }
+#pragma unroll
+        for (int n0 = 0; n0 < 8; n0 += NTG)
+#pragma unroll
+            for (int kk = 0; kk < 2; kk++)
+#pragma unroll
+                for (int nt = n0; nt < n0 + NTG; nt++)
+                    if (FULL || nt < ntm) {
+#pragma unroll
+                        for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[kk][mt], b[kk][nt]);
+                    }
+    }
+}
+
+// acc -= Ai[64 x 64*nslab] * Bk[64 x 64*nslab]^T     (acc preloaded by the caller; all 128 threads copy and sync)
+// `tail` (optional) is one more 64x64 tile streamed through the same ring right behind the last operand slab — the
+// epilogue's L_kk — so its latency hides under the main loop; the function returns the stage buffer it landed in.
+__device__ __forceinline__ double *tile_accumulate(Acc &acc, const double *Ai, const double *Bk, int64_t lda, int64_t ldb, int nslab,
+                                                   bool same, int ntm, double *smem, const double *tail = nullptr,
+                                                   int64_t tail_ld = 0) {
+    const int tid = threadIdx.x;
     const int nh = nslab * 2;
     const int total = nh + (tail ? 1 : 0);
 #pragma unroll
@@ -96,204 +143,303 @@ __device__ __forceinline__ double *tile_accumulate(double (&acc)[4][4][2], const
             else if (hn < total) chol_load_tail(dst, tail, tail_ld, tid);
             cp_async_commit();
         }
-        if (!skip) {
-            const double *As = smem + (h % CHOL_NST) * CHOL_STAGE_DOUBLES;
-            const double *Bs = same ? As : As + GSUM_TILE * GSUM_LDH;
-            const double *ap = As + (wm * 32 + g) * GSUM_LDH + t;
-            const double *bp = Bs + (wn * 32 + g) * GSUM_LDH + t;
-            double a[2][4], b[2][4];
-#pragma unroll
-            for (int mi = 0; mi < 4; mi++) { a[0][mi] = ap[mi * 8 * GSUM_LDH]; b[0][mi] = bp[mi * 8 * GSUM_LDH]; }
-#pragma unroll
-            for (int ks = 0; ks < GSUM_KH / 4; ks++) {
-                const int cur = ks & 1, nxt = cur ^ 1;
-                if (ks + 1 < GSUM_KH / 4) {
-#pragma unroll
-                    for (int mi = 0; mi < 4; mi++) {
-                        a[nxt][mi] = ap[mi * 8 * GSUM_LDH + (ks + 1) * 4];
-                        b[nxt][mi] = bp[mi * 8 * GSUM_LDH + (ks + 1) * 4];
-                    }
-                }
-#pragma unroll
-                for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                    for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], -a[cur][mi], b[cur][ni]);
-            }
-        }
+        const double *As = smem + (h % CHOL_NST) * CHOL_STAGE_DOUBLES;
+        const double *Bs = same ? As : As + GSUM_TILE * GSUM_LDH;
+        if (ntm == 8) stage_mma<true>(acc, As, Bs, 8);
+        else stage_mma<false>(acc, As, Bs, ntm);
     }
     cp_async_wait<0>();
     __syncthreads();
     return tail ? smem + (nh % CHOL_NST) * CHOL_STAGE_DOUBLES : nullptr;
 }
 
-__device__ __forceinline__ void tile_load_acc(double (&acc)[4][4][2], const double *C, int64_t ldc) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void tile_load_acc(Acc &acc, const double *C, int64_t ldc, int ntm = 8) {
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 3, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++)
+    for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-            const double2 v = *reinterpret_cast<const double2 *>(C + (int64_t)(wm * 32 + mi * 8 + g) * ldc + wn * 32 + ni * 8 + 2 * t);
-            acc[mi][ni][0] = v.x; acc[mi][ni][1] = v.y;
+        for (int nt = 0; nt < 8; nt++) {
+            if (nt < ntm) {
+                const double2 v = *reinterpret_cast<const double2 *>(C + (int64_t)(w * 16 + mt * 8 + g) * ldc + nt * 8 + 2 * t);
+                acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y;
+            } else { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
         }
 }
-
-__device__ __forceinline__ void tile_store_acc_smem(const double (&acc)[4][4][2], double *S, int lds) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void tile_store_acc(const Acc &acc, double *C, int64_t ldc) {
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 3, g = lane >> 2, t = lane & 3;
 #pragma unroll
-    for (int mi = 0; mi < 4; mi++)
+    for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-            double *p = S + (wm * 32 + mi * 8 + g) * lds + wn * 32 + ni * 8 + 2 * t;
-            p[0] = acc[mi][ni][0]; p[1] = acc[mi][ni][1];
+        for (int nt = 0; nt < 8; nt++) {
+            double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
+            *reinterpret_cast<double2 *>(C + (int64_t)(w * 16 + mt * 8 + g) * ldc + nt * 8 + 2 * t) = v;
         }
 }
 
 // ---- epilogue 1: POTRF of a 64x64 tile held in smem (stride GSUM_LDS), blocked by 8 columns ------------------
-// Per 8-column block: (1) warp 0 factors the 8x8 diagonal block with its rows in registers (one lane per row, pivots and
-// column entries exchanged by shuffles; column scaled by the reciprocal as LAPACK dpotf2 does); (2) the rows below are
-// solved against it, one thread per row; (3) the trailing 8x8 blocks get a rank-8 DMMA update.  Writes dg = diag(L) and
-// the failing column (1-based, LAPACK potrf convention) to *s_fail (0 = ok; must be zeroed by the caller).
-__device__ __forceinline__ void tile_potrf_blocked(double *S, double *dg, int *s_fail) {
+// Per 8-column block: (1) every thread that owns a row below the block factors the 8x8 diagonal block redundantly in
+// registers (no shuffles, no barrier: the dependent chain per column is rsqrt -> mul -> fma) and forward-substitutes its
+// own row against it; warp 3 does the same factorisation and writes the block, diag(L) and the failure column back;
+// (2) the trailing 8x8 blocks get a rank-8 DMMA update.  The column is scaled by the reciprocal square root, as LAPACK
+// dpotf2 scales by the reciprocal of the pivot's square root.  *s_fail: failing column (1-based, LAPACK potrf
+// convention), 0 = ok; must be zeroed by the caller.
+__device__ __noinline__ void tile_potrf_blocked(double *S, double *dg, int *s_fail) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
+#pragma unroll 1
     for (int cb = 0; cb < 8; cb++) {
         const int c0 = cb * 8;
-        if (w == 0) {
-            const int r = lane & 7;                      // lanes >= 8 mirror lanes 0..7 (full-mask shuffles)
-            double row[8];
+        const int rr = c0 + 8 + tid;
+        const bool solver = rr < GSUM_TILE;
+        const bool writer = (tid == 96);            // one otherwise idle thread writes the factored block back
+        if (solver || writer) {
+            double a[8][8], x[8];
+            const double *blk = S + c0 * GSUM_LDS + c0;
+            double *row = S + (solver ? rr : 0) * GSUM_LDS + c0;
 #pragma unroll
-            for (int c = 0; c < 8; c++) row[c] = S[(c0 + r) * GSUM_LDS + c0 + c];
+            for (int m = 0; m < 8; m++)
+#pragma unroll
+                for (int n = 0; n <= m; n += 2) {                   // 16-byte loads where both entries are in the lower triangle
+                    if (n + 1 <= m) {
+                        const double2 v = *reinterpret_cast<const double2 *>(blk + m * GSUM_LDS + n);
+                        a[m][n] = v.x; a[m][n + 1] = v.y;
+                    } else a[m][n] = blk[m * GSUM_LDS + n];
+                }
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(row + c);
+                x[c] = v.x; x[c + 1] = v.y;
+            }
             int fail = 0;
+            // column by column: factor column j of the block, then eliminate it from this thread's row (right-looking, so
+            // a factor column is dead as soon as it has been applied)
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const double d = __shfl_sync(0xffffffffu, row[j], j);
+                const double d = a[j][j];
                 if (!(d > 0.0) && fail == 0) fail = c0 + j + 1;
-                const double sj = sqrt(d);
-                const double rs = 1.0 / sj;
-                const double lj = row[j] * rs;
-                row[j] = (r == j) ? sj : lj;
+                const double rs = rsqrt(d);
+                x[j] *= rs;
+                if (writer) { S[(c0 + j) * GSUM_LDS + c0 + j] = d * rs; dg[c0 + j] = d * rs; }
 #pragma unroll
                 for (int m = j + 1; m < 8; m++) {
-                    const double lm = __shfl_sync(0xffffffffu, lj, m);
-                    row[m] = fma(-lj, lm, row[m]);
+                    a[m][j] *= rs;
+                    if (writer) S[(c0 + m) * GSUM_LDS + c0 + j] = a[m][j];
+                    x[m] = fma(-x[j], a[m][j], x[m]);
+                }
+#pragma unroll
+                for (int m = j + 1; m < 8; m++)
+#pragma unroll
+                    for (int n = j + 1; n <= m; n++) a[m][n] = fma(-a[m][j], a[n][j], a[m][n]);
+            }
+            if (solver) {
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    double2 v; v.x = x[c]; v.y = x[c + 1];
+                    *reinterpret_cast<double2 *>(row + c) = v;
                 }
             }
-            if (lane < 8) {
-#pragma unroll
-                for (int c = 0; c < 8; c++) S[(c0 + r) * GSUM_LDS + c0 + c] = row[c];
-                double dv = row[0];
-#pragma unroll
-                for (int c = 1; c < 8; c++) dv = (c == r) ? row[c] : dv;      // row[r] without a runtime-indexed register array
-                dg[c0 + r] = dv;
-            }
-            if (lane == 0 && fail && *s_fail == 0) *s_fail = fail;
+            if (writer && fail && *s_fail == 0) *s_fail = fail;
         }
-        CONS_SYNC();
         if (cb == 7) break;
-        {   // (2) rows below the diagonal block: X = S L_D^{-T}
-            const int rr = c0 + 8 + tid;
-            if (rr < GSUM_TILE) {
-                double *row = S + rr * GSUM_LDS + c0;
-                double x[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    double v = row[c];
-                    const double *lrow = S + (c0 + c) * GSUM_LDS + c0;
-#pragma unroll
-                    for (int m = 0; m < c; m++) v = fma(-x[m], lrow[m], v);
-                    x[c] = v * (1.0 / dg[c0 + c]);
-                }
-#pragma unroll
-                for (int c = 0; c < 8; c++) row[c] = x[c];
-            }
-        }
         CONS_SYNC();
-        {   // (3) trailing update of the 8x8 blocks (rb, cb2), cb < cb2 <= rb <= 7
+        {   // trailing update of the 8x8 blocks (rb, cb2), cb < cb2 <= rb <= 7; warp w takes blocks w, w+4, ... (4 in flight)
             const int nt = 7 - cb, nblk = nt * (nt + 1) / 2;
-            for (int blk = w; blk < nblk; blk += CHOL_THREADS / 32) {
-                int rbi = 0, rem = blk;
-                while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
-                const int rb = cb + 1 + rbi, cb2 = cb + 1 + rem;
-                double *cp = S + (rb * 8 + g) * GSUM_LDS + cb2 * 8 + 2 * t;
-                double cc0 = cp[0], cc1 = cp[1];
+#pragma unroll 1
+            for (int q0 = 0; w + 4 * q0 < nblk; q0 += 4) {
+                double cc[4][2], fa[4][2], fb[4][2];
+                int off[4];
 #pragma unroll
-                for (int k0 = 0; k0 < 8; k0 += 4) {
-                    const double a = S[(rb * 8 + g) * GSUM_LDS + c0 + k0 + t];
-                    const double b = S[(cb2 * 8 + g) * GSUM_LDS + c0 + k0 + t];
-                    dmma884(cc0, cc1, -a, b);
+                for (int q = 0; q < 4; q++) {
+                    const int blk = w + 4 * (q0 + q);
+                    if (blk < nblk) {
+                        int rbi = 0, rem = blk;
+                        while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
+                        const int rb = cb + 1 + rbi, cb2 = cb + 1 + rem;
+                        off[q] = (rb * 8 + g) * GSUM_LDS + cb2 * 8 + 2 * t;
+                        const double2 v = *reinterpret_cast<const double2 *>(S + off[q]);
+                        cc[q][0] = v.x; cc[q][1] = v.y;
+                        fa[q][0] = S[(rb * 8 + g) * GSUM_LDS + c0 + t]; fa[q][1] = S[(rb * 8 + g) * GSUM_LDS + c0 + 4 + t];
+                        fb[q][0] = S[(cb2 * 8 + g) * GSUM_LDS + c0 + t]; fb[q][1] = S[(cb2 * 8 + g) * GSUM_LDS + c0 + 4 + t];
+                    }
                 }
-                cp[0] = cc0; cp[1] = cc1;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (w + 4 * (q0 + q) < nblk) {
+                        dmma884(cc[q][0], cc[q][1], -fa[q][0], fb[q][0]);
+                        dmma884(cc[q][0], cc[q][1], -fa[q][1], fb[q][1]);
+                    }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (w + 4 * (q0 + q) < nblk) {
+                        double2 v; v.x = cc[q][0]; v.y = cc[q][1];
+                        *reinterpret_cast<double2 *>(S + off[q]) = v;
+                    }
             }
         }
         CONS_SYNC();
     }
+    CONS_SYNC();
 }
 
-// ---- epilogue 2: X = S * Lkk^{-T} (rows independent; each warp owns 16 rows) --------------------------
-// Blocked by 8 columns: DMMA update with the already-solved columns, then an 8x8 forward substitution
-// per row.  True substitution (no explicit inverse of the diagonal tile): keeps the row-wise backward
-// stability the rtol 1e-10 parity relies on.
-__device__ __forceinline__ void tile_trsm_smem(double *S, const double *Lk, const double *rdiag) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const int r0 = w * 16;
+// ---- epilogue 2: X = T * Lk^{-T} on a warp's 16 x 64 register block (rows are independent) ---------------------
+// Right-looking over 8-column blocks: (1) forward-substitute the 8x8 diagonal block — a row's 8 entries live in the 4
+// lanes of a quad, so each solved entry is broadcast with one quad shuffle and applied by fma (true substitution, no
+// explicit inverse: keeps the row-wise backward stability the rtol 1e-10 parity relies on); (2) re-layout the solved
+// block from C- to A-fragments with quad shuffles; (3) update the later column blocks with DMMAs (two per block and m
+// tile, all independent).  Lk: L_kk in smem (stride GSUM_LDS), rdiag[j] = 1 / L_kk[j][j].  MT = m-tiles in use.
+template <int MT>
+__device__ __forceinline__ void trsm_regs(Acc &T, const double *Lk, const double *rdiag) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const unsigned FULLMASK = 0xffffffffu;
+#pragma unroll
     for (int cb = 0; cb < 8; cb++) {
-        if (cb > 0) {
-            double c[2][2];
+        const int c0 = cb * 8;
+        asm volatile("" ::: "memory");         // keep the smem loads of later blocks from being hoisted (register pressure)
+        // rows 2t and 2t+1 of the diagonal block (entries left of the diagonal) and their reciprocal pivots
+        double l0[8], l1[8];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-                const double *p = S + (r0 + mt * 8 + g) * GSUM_LDS + cb * 8 + 2 * t;
-                c[mt][0] = p[0]; c[mt][1] = p[1];
-            }
-            for (int k0 = 0; k0 < cb * 8; k0 += 4) {
-                const double b = Lk[(cb * 8 + g) * GSUM_LDS + k0 + t];
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++) {
-                    const double a = -S[(r0 + mt * 8 + g) * GSUM_LDS + k0 + t];
-                    dmma884(c[mt][0], c[mt][1], a, b);
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++) {
-                double *p = S + (r0 + mt * 8 + g) * GSUM_LDS + cb * 8 + 2 * t;
-                p[0] = c[mt][0]; p[1] = c[mt][1];
-            }
-            __syncwarp();
+        for (int m = 0; m < 8; m += 2) {
+            const double2 u = *reinterpret_cast<const double2 *>(Lk + (c0 + 2 * t) * GSUM_LDS + c0 + m);
+            const double2 v = *reinterpret_cast<const double2 *>(Lk + (c0 + 2 * t + 1) * GSUM_LDS + c0 + m);
+            l0[m] = u.x; l0[m + 1] = u.y; l1[m] = v.x; l1[m + 1] = v.y;
         }
-        if (lane < 16) {
-            double *row = S + (r0 + lane) * GSUM_LDS + cb * 8;
-            double x[8];
+        const double2 rd = *reinterpret_cast<const double2 *>(rdiag + c0 + 2 * t);
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                double v = row[c];
-                const double *lrow = Lk + (cb * 8 + c) * GSUM_LDS + cb * 8;
+        for (int c = 0; c < 8; c++) {
+            const int owner = c >> 1, e = c & 1;
 #pragma unroll
-                for (int m = 0; m < c; m++) v -= x[m] * lrow[m];
-                x[c] = v * rdiag[cb * 8 + c];
+            for (int mt = 0; mt < MT; mt++) {
+                const double xv = T[mt][cb][e] * (e ? rd.y : rd.x);
+                const double xc = __shfl_sync(FULLMASK, xv, owner, 4);
+                if (t == owner) T[mt][cb][e] = xc;
+                if (2 * t > c) T[mt][cb][0] = fma(-xc, l0[c], T[mt][cb][0]);
+                if (2 * t + 1 > c) T[mt][cb][1] = fma(-xc, l1[c], T[mt][cb][1]);
             }
+        }
+        if (cb == 7) break;
+        double a0[MT], a1[MT];
 #pragma unroll
-            for (int c = 0; c < 8; c++) row[c] = x[c];
+        for (int mt = 0; mt < MT; mt++) {
+            const double p0 = __shfl_sync(FULLMASK, T[mt][cb][0], t >> 1, 4), p1 = __shfl_sync(FULLMASK, T[mt][cb][1], t >> 1, 4);
+            const double q0 = __shfl_sync(FULLMASK, T[mt][cb][0], 2 + (t >> 1), 4), q1 = __shfl_sync(FULLMASK, T[mt][cb][1], 2 + (t >> 1), 4);
+            a0[mt] = -((t & 1) ? p1 : p0);
+            a1[mt] = -((t & 1) ? q1 : q0);
+        }
+#pragma unroll
+        for (int j = cb + 1; j < 8; j++) {
+            const double b0 = Lk[(j * 8 + g) * GSUM_LDS + c0 + t], b1 = Lk[(j * 8 + g) * GSUM_LDS + c0 + 4 + t];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                dmma884(T[mt][j][0], T[mt][j][1], a0[mt], b0);
+                dmma884(T[mt][j][0], T[mt][j][1], a1[mt], b1);
+            }
+        }
+    }
+}
+
+// Row-per-thread variant of the same solve.  DFMA latency on B200 is 32 cycles and a quad shuffle of a double 54, so the
+// substitution chain is shortest when one thread owns a whole row of the 8-column block: per block the warp drops its
+// 16 x 8 slice into a per-warp smem scratch (C-fragment layout -> row major), 16 lanes substitute one row each against
+// the PRESCALED diagonal block  Lp[c][m] = L[c][m] / L[c][c]  (x_c = s_c / L_cc - sum_m x_m Lp[c][m]: one fma per step
+// on the chain instead of fma + mul; still a true substitution), and the solved block comes back both as C fragments
+// and — straight from the row-major scratch — as the A fragments of the DMMA update of the later blocks.
+//   Lp:    [8 blocks][8][8] prescaled strictly-lower entries (smem), rdiag[64] = 1 / L_jj (smem)
+//   scr:   this warp's scratch, 16 rows x TRSM_SCR_LD doubles
+#define TRSM_SCR_LD 10
+template <int MT>
+__device__ __forceinline__ void trsm_rows(Acc &T, const double *Lk, const double *Lp, const double *rdiag, double *scr) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int cb = 0; cb < 8; cb++) {
+        const int c0 = cb * 8;
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double2 v; v.x = T[mt][cb][0]; v.y = T[mt][cb][1];
+            *reinterpret_cast<double2 *>(scr + (mt * 8 + g) * TRSM_SCR_LD + 2 * t) = v;
         }
         __syncwarp();
+        if (lane < 8 * MT) {
+            double *row = scr + lane * TRSM_SCR_LD;
+            const double *lp = Lp + cb * 64;
+            double x[8];
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(row + c);
+                const double2 r = *reinterpret_cast<const double2 *>(rdiag + c0 + c);
+                x[c] = v.x * r.x; x[c + 1] = v.y * r.y;
+            }
+#pragma unroll
+            for (int c = 1; c < 8; c++) {
+                double v = x[c];
+#pragma unroll
+                for (int m = 0; m < c; m++) v = fma(-x[m], lp[c * 8 + m], v);
+                x[c] = v;
+            }
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+                double2 v; v.x = x[c]; v.y = x[c + 1];
+                *reinterpret_cast<double2 *>(row + c) = v;
+            }
+        }
+        __syncwarp();
+        double a0[MT], a1[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const double2 v = *reinterpret_cast<const double2 *>(scr + (mt * 8 + g) * TRSM_SCR_LD + 2 * t);
+            T[mt][cb][0] = v.x; T[mt][cb][1] = v.y;
+            a0[mt] = -scr[(mt * 8 + g) * TRSM_SCR_LD + t];
+            a1[mt] = -scr[(mt * 8 + g) * TRSM_SCR_LD + 4 + t];
+        }
+        __syncwarp();
+        if (cb == 7) break;
+#pragma unroll
+        for (int j = cb + 1; j < 8; j++) {
+            const double b0 = Lk[(j * 8 + g) * GSUM_LDS + c0 + t], b1 = Lk[(j * 8 + g) * GSUM_LDS + c0 + 4 + t];
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                dmma884(T[mt][j][0], T[mt][j][1], a0[mt], b0);
+                dmma884(T[mt][j][0], T[mt][j][1], a1[mt], b1);
+            }
+        }
+    }
+}
+// rdiag[j] = 1 / L_jj and the prescaled diagonal blocks, by the 128 math threads (caller syncs afterwards)
+__device__ __forceinline__ void trsm_prepare(const double *Lk, double *Lp, double *rdiag) {
+    const int tid = threadIdx.x;
+    if (tid < GSUM_TILE) rdiag[tid] = 1.0 / Lk[tid * GSUM_LDS + tid];
+    for (int e = tid; e < 512; e += CHOL_THREADS) {
+        const int cb = e >> 6, c = (e >> 3) & 7, m = e & 7;
+        const double d = Lk[(cb * 8 + c) * GSUM_LDS + cb * 8 + c];
+        Lp[e] = m < c ? Lk[(cb * 8 + c) * GSUM_LDS + cb * 8 + m] * (1.0 / d) : 0.0;
     }
 }
 
 // ---- one tile task (i, k) of matrix b: accumulate, then POTRF (i == k) or TRSM (i > k); tile written once ---------
-// Epilogue shared by the multi-launch and the dataflow schedules: S (a free 64x68 smem buffer with 160 spare doubles
-// behind it), Lk = L_kk staged in smem (panel tasks).  Called by the 128 math threads.
-__device__ __forceinline__ void tile_epilogue(const BorderedBatch &P, int i, int k, int b, double (&acc)[4][4][2], double *S,
-                                              double *Lk, double *C, bool skip) {
-    const int tid = threadIdx.x, w = tid >> 5;
+// Epilogue shared by the multi-launch and the dataflow schedules.  S: a free 64x68 smem buffer with 160 spare doubles
+// behind it (diagonal tasks stage the tile there; panel tasks only use the spare doubles), Lk = L_kk staged in smem
+// (panel tasks).  Called by the 128 math threads.  `es`: optional dev instrumentation (cycle counters).
+__device__ __forceinline__ void tile_epilogue(const BorderedBatch &P, int i, int k, int b, Acc &acc, double *S, double *Lk, double *C,
+                                              long long *es = nullptr) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const bool diag = (i == k);
     double *dg = S + GSUM_TILE * GSUM_LDS;                                    // 64 doubles behind the tile
     int *s_fail = reinterpret_cast<int *>(dg + 2 * GSUM_TILE);
-    if (!skip) tile_store_acc_smem(acc, S, GSUM_LDS);
+    const long long e0 = es ? clock64() : 0;
     if (diag) {
+        // stage the lower part: warp w owns rows 16w.., columns < 16(w+1)
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 8; nt++)
+                if (nt < 2 * (w + 1)) {
+                    double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
+                    *reinterpret_cast<double2 *>(S + (w * 16 + mt * 8 + g) * GSUM_LDS + nt * 8 + 2 * t) = v;
+                }
         if (tid == 0) *s_fail = 0;
         CONS_SYNC();
+        const long long e1 = es ? clock64() : 0;
         tile_potrf_blocked(S, dg, s_fail);
+        const long long e2 = es ? clock64() : 0;
         const int fail = *s_fail;
         if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
         // write L_kk: lower triangle, exact zeros above the diagonal (numpy.linalg.cholesky convention)
@@ -313,45 +459,44 @@ __device__ __forceinline__ void tile_epilogue(const BorderedBatch &P, int i, int
             v = warp_sum(v);
             if (tid == 0) P.logdet_part[(int64_t)b * P.T + k] = fail ? nan("") : 2.0 * v;
         }
+        if (es && tid == 0) { es[0] += e1 - e0; es[1] += e2 - e1; es[2] += clock64() - e2; es[3] += 1; }
     } else {
-        double *rdiag = dg;
-        if (tid < GSUM_TILE) rdiag[tid] = 1.0 / Lk[tid * GSUM_LDS + tid];
+        // panel tasks never stage the tile: S only carries rdiag, the prescaled diagonal blocks and the per-warp scratch
+        double *rdiag = S, *Lp = S + GSUM_TILE, *scr = S + GSUM_TILE + 512 + w * (16 * TRSM_SCR_LD);
+        trsm_prepare(Lk, Lp, rdiag);
         CONS_SYNC();
-        tile_trsm_smem(S, Lk, rdiag);
-        CONS_SYNC();
-        for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
-            const int r = e >> 5, c = (e & 31) * 2;
-            double2 v; v.x = S[r * GSUM_LDS + c]; v.y = S[r * GSUM_LDS + c + 1];
-            *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
-        }
+        const long long e1 = es ? clock64() : 0;
+        trsm_rows<2>(acc, Lk, Lp, rdiag, scr);
+        const long long e2 = es ? clock64() : 0;
+        tile_store_acc(acc, C, P.ld);
+        if (es && tid == 0) { es[4] += e1 - e0; es[5] += e2 - e1; es[6] += clock64() - e2; es[7] += 1; }
     }
 }
 
-
 __device__ __forceinline__ void tile_task(const BorderedBatch &P, int i, int k, int b, double *smem) {
-    const int tid = threadIdx.x, w = tid >> 5;
+    const int w = threadIdx.x >> 5;
     double *Ab = P.A + (int64_t)b * P.bstride;
     double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
                            : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
     const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
     double *C = Ri + k * GSUM_TILE;
     const bool diag = (i == k);
-    const bool skip = diag && (w == 1);                  // warp (wm=0, wn=1): strictly upper block of a diagonal tile
-    double acc[4][4][2];
-    if (!skip) tile_load_acc(acc, C, P.ld);
-    double *Lk = tile_accumulate(acc, Ri, Ak, P.ld, P.ld, k, diag, skip, smem, diag ? nullptr : Ak + k * GSUM_TILE, P.ld);
+    const int ntm = diag ? 2 * (w + 1) : 8;              // diagonal tile: warp w owns columns < 16 (w + 1)
+    Acc acc;
+    tile_load_acc(acc, C, P.ld, ntm);
+    double *Lk = tile_accumulate(acc, Ri, Ak, P.ld, P.ld, k, diag, ntm, smem, diag ? nullptr : Ak + k * GSUM_TILE, P.ld);
     double *S = smem + ((2 * k + 1) % CHOL_NST) * CHOL_STAGE_DOUBLES;      // a stage buffer the ring is done with
-    tile_epilogue(P, i, k, b, acc, S, Lk, C, skip);
+    tile_epilogue(P, i, k, b, acc, S, Lk, C);
 }
 
 // ---- multi-launch schedule: per tile column k one diagonal launch + one panel launch ------------------------------
-__global__ void __launch_bounds__(CHOL_THREADS, 2) chol_diag_kernel(BorderedBatch P, int k) {
+__global__ void __launch_bounds__(CHOL_THREADS, CHOL_CTAS_PER_SM) chol_diag_kernel(BorderedBatch P, int k) {
     extern __shared__ __align__(16) double smem[];
     tile_task(P, k, k, blockIdx.x, smem);
 }
 // Tile rows i = i0 + blockIdx.x of tile column k (i0 = k+1 during a factorisation; i0 = T for a solve with an
 // existing factor).  Rows >= T live in the border block W.
-__global__ void __launch_bounds__(CHOL_THREADS, 2) chol_panel_kernel(BorderedBatch P, int k, int i0) {
+__global__ void __launch_bounds__(CHOL_THREADS, CHOL_CTAS_PER_SM) chol_panel_kernel(BorderedBatch P, int k, int i0) {
     extern __shared__ __align__(16) double smem[];
     tile_task(P, i0 + blockIdx.x, k, blockIdx.y, smem);
 }
@@ -366,25 +511,17 @@ struct SchurArgs {
     int64_t ldc, cstride;
     int lower_only;       // skip tiles with i' > i
 };
-__global__ void __launch_bounds__(CHOL_THREADS, 2) schur_kernel(SchurArgs P) {
+__global__ void __launch_bounds__(CHOL_THREADS, CHOL_CTAS_PER_SM) schur_kernel(SchurArgs P) {
     extern __shared__ __align__(16) double smem[];
     const int i = blockIdx.y, ip = blockIdx.x, b = blockIdx.z;
     if (P.lower_only && ip > i) return;
     const double *Wi = P.W + (int64_t)b * P.bstride + (int64_t)i * GSUM_TILE * P.ld;
     const double *Wp = P.W + (int64_t)b * P.bstride + (int64_t)ip * GSUM_TILE * P.ld;
     double *C = P.C + (int64_t)b * P.cstride + (int64_t)i * GSUM_TILE * P.ldc + ip * GSUM_TILE;
-    double acc[4][4][2];
+    Acc acc;
     tile_load_acc(acc, C, P.ldc);
-    tile_accumulate(acc, Wi, Wp, P.ld, P.ld, P.T, i == ip, false, smem);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-            double2 v; v.x = acc[mi][ni][0]; v.y = acc[mi][ni][1];
-            *reinterpret_cast<double2 *>(C + (int64_t)(wm * 32 + mi * 8 + g) * P.ldc + wn * 32 + ni * 8 + 2 * t) = v;
-        }
+    tile_accumulate(acc, Wi, Wp, P.ld, P.ld, P.T, i == ip, 8, smem);
+    tile_store_acc(acc, C, P.ldc);
 }
 
 static inline int chol_set_attrs(gsum_ctx *ctx);

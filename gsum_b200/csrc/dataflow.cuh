@@ -21,16 +21,17 @@
 
 #define DF_THREADS 160
 #define DF_PRODUCER_WARP 4
+#define DF_NSTAT 24
 #define DF_WATCHDOG_CYCLES (4000000000LL)       // ~2 s at 1.9 GHz
 
 struct DataflowArgs {
     BorderedBatch P;
-    const int4 *tasks;      // (i, k, b, -) in schedule order
+    const int4 *tasks;      // (i, k, b, flags) in schedule order; flags bit 0: thin border task (<= 8 rows in use)
     int ntasks;
     int *counter;           // next task to claim (zeroed before launch)
     int *flags;             // done flag per (b, i, k): index (b * Trows + i) * T + k  (zeroed before launch)
     int *abort_flag;        // set by any thread whose wait exceeded the watchdog
-    long long *stats;       // optional per-CTA cycle counters [grid][8] (dev instrumentation; nullptr = off)
+    long long *stats;       // optional per-CTA cycle counters [grid][DF_NSTAT] (dev instrumentation; nullptr = off)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -100,7 +101,8 @@ __device__ __forceinline__ void ring_advance(RingState &r) {
     if (++r.stage == CHOL_NST) { r.stage = 0; r.phase ^= 1u; }
 }
 
-__global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DataflowArgs D) {
+template <bool STATS>
+__global__ void __launch_bounds__(DF_THREADS, CHOL_CTAS_PER_SM) chol_dataflow_kernel(DataflowArgs D) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t full_bar[CHOL_NST], empty_bar[CHOL_NST];
     __shared__ int s_task;
@@ -112,18 +114,22 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DataflowAr
     }
     __syncthreads();
     RingState ring = {0, 0u};           // advanced identically by the producer and the math warps
-    long long st_wait_full = 0, st_wait_flag = 0, st_wait_empty = 0, st_epi = 0, st_ntask = 0, st_acc0 = 0;
-    const long long st_t0 = clock64();
-    const bool st_on = D.stats != nullptr;
+    long long st_wait_full = 0, st_wait_flag = 0, st_wait_empty = 0, st_epi = 0, st_ntask = 0, st_acc0 = 0, st_fence = 0, st_claim = 0;
+    long long es[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long st_t0 = STATS ? clock64() : 0;
+    const bool st_on = STATS && D.stats != nullptr;
     bool alive = true;
     for (;;) {
+        const long long tc0 = st_on ? clock64() : 0;
         if (tid == 0) s_task = atomicAdd(D.counter, 1);
         __syncthreads();
+        if (st_on) st_claim += clock64() - tc0;
         const int tix = s_task;
         if (tix >= D.ntasks || !alive) break;
         const int4 tk = D.tasks[tix];
         const int i = tk.x, k = tk.y, b = tk.z;
         const bool diag = (i == k);
+        const bool thin = (tk.w & 1) != 0;          // border tile row with <= 8 rows in use: 8 x 64 task
         double *Ab = P.A + (int64_t)b * P.bstride;
         double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
                                : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
@@ -154,10 +160,18 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DataflowAr
                 double *As = smem + ring.stage * CHOL_STAGE_DOUBLES, *Bs = As + GSUM_TILE * GSUM_LDH;
                 const int col0 = j * GSUM_TILE + (h & 1) * GSUM_KH;
                 // 64 rows x 256 B per operand = 1024 16-byte chunks; a warp-wide LDGSTS moves two rows
+                if (thin) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int c = lane + 32 * q, row = c >> 4, ch = (c & 15) * 2;
+                        cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
+                    }
+                } else {
 #pragma unroll 8
-                for (int q = 0; q < 32; q++) {
-                    const int c = lane + 32 * q, row = c >> 4, ch = (c & 15) * 2;
-                    cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
+                    for (int q = 0; q < 32; q++) {
+                        const int c = lane + 32 * q, row = c >> 4, ch = (c & 15) * 2;
+                        cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
+                    }
                 }
                 if (!diag) {
 #pragma unroll 8
@@ -190,42 +204,39 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DataflowAr
             }
         } else {
             // ======================= math warps: DMMA main loop + epilogue ==========================================
-            const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
-            const bool skip = diag && (w == 1);
+            const int g = lane >> 2, t = lane & 3;
+            const int ntm = diag ? 2 * (w + 1) : 8;            // diagonal tile: warp w owns columns < 16 (w + 1)
             double *C = Ri + k * GSUM_TILE;
-            double acc[4][4][2];
+            Acc acc;                                            // thin task: acc[k-step parity][n tile 0..1] only
             long long tq0 = st_on ? clock64() : 0;
-            if (!skip) tile_load_acc(acc, C, P.ld);
+            if (!thin) tile_load_acc(acc, C, P.ld, ntm);
+            else {
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++) {
+                    const double2 v = *reinterpret_cast<const double2 *>(C + (int64_t)g * P.ld + w * 16 + nt * 8 + 2 * t);
+                    acc[0][nt][0] = v.x; acc[0][nt][1] = v.y; acc[1][nt][0] = 0.0; acc[1][nt][1] = 0.0;
+                }
+            }
             if (st_on) { st_acc0 += clock64() - tq0; st_ntask++; }
             for (int h = 0; h < nh && alive; h++) {
                 long long tq = st_on ? clock64() : 0;
                 alive = mbar_wait(&full_bar[ring.stage], ring.phase, D.abort_flag);
                 if (st_on) st_wait_full += clock64() - tq;
                 if (!alive) break;
-                if (!skip) {
-                    const double *As = smem + ring.stage * CHOL_STAGE_DOUBLES;
-                    const double *Bs = diag ? As : As + GSUM_TILE * GSUM_LDH;
-                    const double *ap = As + (wm * 32 + g) * GSUM_LDH + t;
-                    const double *bp = Bs + (wn * 32 + g) * GSUM_LDH + t;
-                    double a[2][4], bb[2][4];
-#pragma unroll
-                    for (int mi = 0; mi < 4; mi++) { a[0][mi] = ap[mi * 8 * GSUM_LDH]; bb[0][mi] = bp[mi * 8 * GSUM_LDH]; }
+                const double *As = smem + ring.stage * CHOL_STAGE_DOUBLES;
+                const double *Bs = diag ? As : As + GSUM_TILE * GSUM_LDH;
+                if (thin) {
+                    const double *ap = As + g * GSUM_LDH + t;
+                    const double *bp = Bs + (w * 16 + g) * GSUM_LDH + t;
 #pragma unroll
                     for (int ks = 0; ks < GSUM_KH / 4; ks++) {
-                        const int cur = ks & 1, nxt = cur ^ 1;
-                        if (ks + 1 < GSUM_KH / 4) {
+                        const double a = -ap[ks * 4];
 #pragma unroll
-                            for (int mi = 0; mi < 4; mi++) {
-                                a[nxt][mi] = ap[mi * 8 * GSUM_LDH + (ks + 1) * 4];
-                                bb[nxt][mi] = bp[mi * 8 * GSUM_LDH + (ks + 1) * 4];
-                            }
-                        }
-#pragma unroll
-                        for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-                            for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], -a[cur][mi], bb[cur][ni]);
+                        for (int nt = 0; nt < 2; nt++)
+                            dmma884(acc[ks & 1][nt][0], acc[ks & 1][nt][1], a, bp[nt * 8 * GSUM_LDH + ks * 4]);
                     }
-                }
+                } else if (diag) stage_mma<false>(acc, As, Bs, ntm);
+                else stage_mma<true>(acc, As, Bs, 8);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
                 ring_advance(ring);
@@ -243,15 +254,41 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DataflowAr
             // the block must agree on `alive` before the barriers inside the epilogue
             alive = cons_sync_and(alive);
             if (alive) {
-                // every filled stage has been consumed, so any buffer but the tail's is free for the output tile
+                // every filled stage has been consumed, so any buffer but the tail's is free for the epilogue's scratch
                 const int s_stage = (tail_stage + 1 + (tail_stage < 0 ? 1 : 0)) % CHOL_NST;
                 double *S = smem + s_stage * CHOL_STAGE_DOUBLES;
                 long long tq = st_on ? clock64() : 0;
-                tile_epilogue(P, i, k, b, acc, S, Lk, C, skip);
+                if (!thin) tile_epilogue(P, i, k, b, acc, S, Lk, C, st_on ? es : nullptr);
+                else {
+                    // 8 x 64 tile: gather the four 8 x 16 pieces in smem, then warp 0 solves the rows in registers
+                    double *rdiag = S + 8 * GSUM_LDS, *Lp = rdiag + GSUM_TILE, *scr = Lp + 512;       // behind the 8 staged rows
+#pragma unroll
+                    for (int nt = 0; nt < 2; nt++) {
+                        double2 v; v.x = acc[0][nt][0] + acc[1][nt][0]; v.y = acc[0][nt][1] + acc[1][nt][1];
+                        *reinterpret_cast<double2 *>(S + g * GSUM_LDS + w * 16 + nt * 8 + 2 * t) = v;
+                    }
+                    trsm_prepare(Lk, Lp, rdiag);
+                    CONS_SYNC();
+                    if (w == 0) {
+#pragma unroll
+                        for (int nt = 0; nt < 8; nt++) {
+                            const double2 v = *reinterpret_cast<const double2 *>(S + g * GSUM_LDS + nt * 8 + 2 * t);
+                            acc[0][nt][0] = v.x; acc[0][nt][1] = v.y; acc[1][nt][0] = 0.0; acc[1][nt][1] = 0.0;
+                        }
+                        trsm_rows<1>(acc, Lk, Lp, rdiag, scr);
+#pragma unroll
+                        for (int nt = 0; nt < 8; nt++) {
+                            double2 v; v.x = acc[0][nt][0]; v.y = acc[0][nt][1];
+                            *reinterpret_cast<double2 *>(C + (int64_t)g * P.ld + nt * 8 + 2 * t) = v;
+                        }
+                    }
+                }
                 if (st_on) st_epi += clock64() - tq;
+                const long long tf = st_on ? clock64() : 0;
                 __threadfence();                              // tile stores visible device-wide before the flag
                 CONS_SYNC();
                 if (tid == 0) st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
+                if (st_on) st_fence += clock64() - tf;
                 if (tail_stage >= 0 && lane == 0) mbar_arrive(&empty_bar[tail_stage]);     // release the tail's stage
             }
         }
@@ -260,9 +297,11 @@ __global__ void __launch_bounds__(DF_THREADS, 2) chol_dataflow_kernel(DataflowAr
         if (!alive) break;
     }
     if (st_on && (tid == 0 || tid == DF_PRODUCER_WARP * 32)) {
-        long long *o = D.stats + (int64_t)blockIdx.x * 8;
-        if (tid == 0) { o[0] = clock64() - st_t0; o[1] = st_wait_full; o[2] = st_epi; o[3] = st_ntask; o[4] = st_acc0; }
-        else { o[5] = st_wait_flag; o[6] = st_wait_empty; }
+        long long *o = D.stats + (int64_t)blockIdx.x * DF_NSTAT;
+        if (tid == 0) {
+            o[0] = clock64() - st_t0; o[1] = st_wait_full; o[2] = st_epi; o[3] = st_ntask; o[4] = st_acc0; o[7] = st_fence; o[8] = st_claim;
+            for (int q = 0; q < 8; q++) o[9 + q] = es[q];
+        } else { o[5] = st_wait_flag; o[6] = st_wait_empty; }
     }
 }
 
@@ -286,19 +325,20 @@ __global__ void df_check_kernel(const int *abort_flag, int *info, int64_t batch,
 #include <vector>
 // Task list in dependency order with one column of look-ahead: right after the first sub-diagonal tile of column k comes
 // the diagonal tile of column k+1, so that the (latency-bound) POTRF chain runs ahead of the bulk of column k.
-static inline void df_build_tasks(std::vector<int4> &out, int T, int Trows, int batch, bool solve_only) {
+static inline void df_build_tasks(std::vector<int4> &out, int T, int Trows, int batch, bool solve_only, bool thin_last) {
     out.clear();
+    auto flags = [&](int i) { return (thin_last && i == Trows - 1 && i >= T) ? 1 : 0; };
     if (solve_only) {
         for (int k = 0; k < T; k++)
             for (int i = T; i < Trows; i++)
-                for (int b = 0; b < batch; b++) out.push_back(make_int4(i, k, b, 0));
+                for (int b = 0; b < batch; b++) out.push_back(make_int4(i, k, b, flags(i)));
         return;
     }
     for (int k = 0; k < T; k++) {
         if (k == 0) for (int b = 0; b < batch; b++) out.push_back(make_int4(0, 0, b, 0));
-        if (k + 1 < Trows) for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k, b, 0));
+        if (k + 1 < Trows) for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k, b, flags(k + 1)));
         if (k + 1 < T) for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k + 1, b, 0));
         for (int b = 0; b < batch; b++)
-            for (int i = k + 2; i < Trows; i++) out.push_back(make_int4(i, k, b, 0));
+            for (int i = k + 2; i < Trows; i++) out.push_back(make_int4(i, k, b, flags(i)));
     }
 }

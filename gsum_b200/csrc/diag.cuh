@@ -153,26 +153,18 @@ __global__ void __launch_bounds__(CHOL_THREADS, 2) draws_kernel(DrawArgs P) {
     const int i = blockIdx.x, dr = blockIdx.y;
     const double *Zi = P.Zn + (int64_t)dr * GSUM_TILE * P.ld;
     const double *Li = P.L + (int64_t)i * GSUM_TILE * P.ld;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int wm = w >> 1, wn = w & 1, g = lane >> 2, t = lane & 3;
-    double acc[4][4][2];
+    const int lane = threadIdx.x & 31, t = lane & 3;
+    Acc acc;
 #pragma unroll
-    for (int ni = 0; ni < 4; ni++) {
-        const int c = i * GSUM_TILE + wn * 32 + ni * 8 + 2 * t;
+    for (int nt = 0; nt < 8; nt++) {
+        const int c = i * GSUM_TILE + nt * 8 + 2 * t;
         const double m0 = (P.mean && c < P.n) ? P.mean[c] : 0.0;
         const double m1 = (P.mean && c + 1 < P.n) ? P.mean[c + 1] : 0.0;
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++) { acc[mi][ni][0] = m0; acc[mi][ni][1] = m1; }
+        for (int mt = 0; mt < 2; mt++) { acc[mt][nt][0] = m0; acc[mt][nt][1] = m1; }
     }
-    tile_accumulate(acc, Zi, Li, P.ld, P.ld, i + 1, false, false, smem);
-    double *C = P.Yt + (int64_t)dr * GSUM_TILE * P.ld + i * GSUM_TILE;
-#pragma unroll
-    for (int mi = 0; mi < 4; mi++)
-#pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-            double2 v; v.x = acc[mi][ni][0]; v.y = acc[mi][ni][1];
-            *reinterpret_cast<double2 *>(C + (int64_t)(wm * 32 + mi * 8 + g) * P.ld + wn * 32 + ni * 8 + 2 * t) = v;
-        }
+    tile_accumulate(acc, Zi, Li, P.ld, P.ld, i + 1, false, 8, smem);
+    tile_store_acc(acc, P.Yt + (int64_t)dr * GSUM_TILE * P.ld + i * GSUM_TILE, P.ld);
 }
 
 // Philox4x32-10 counter-based generator + Box-Muller: rows of -z (z ~ N(0,1)), zero beyond (n_draws, n).

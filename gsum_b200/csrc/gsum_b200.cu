@@ -38,6 +38,8 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     const char *sched = getenv("GSUM_B200_SCHEDULE");
     c->use_multilaunch = (sched && strcmp(sched, "multilaunch") == 0) ? 1 : 0;
+    const char *thin = getenv("GSUM_B200_THIN");
+    c->use_thin = (thin && strcmp(thin, "0") == 0) ? 0 : 1;
     *out = c;
     return 0;
 }
@@ -138,16 +140,23 @@ static int scale_coords(gsum_ctx *c, const double *dX, const double *dls, double
 static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
     GSUM_TRY(chol_set_attrs(c));
     if (c->df_grid == 0) {
-        GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
-        int per_sm = 0;
-        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_dataflow_kernel, DF_THREADS, CHOL_SMEM_BYTES));
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+        int per_sm = 0, per_sm_stats = 0;
+        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_dataflow_kernel<false>, DF_THREADS, CHOL_SMEM_BYTES));
+        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_stats, chol_dataflow_kernel<true>, DF_THREADS, CHOL_SMEM_BYTES));
+        if (per_sm_stats < per_sm) per_sm = per_sm_stats;
         if (per_sm < 1) return gsum_fail(c, -102, "dataflow kernel does not fit on an SM");
         c->df_grid = per_sm * c->sm_count;
     }
-    const int key[4] = {P.T, P.Trows, batch, solve_only ? 1 : 0};
+    // a last border tile row with at most 8 rows in use runs as thin (8 x 64) tasks
+    const int nbt = P.Trows - P.T;
+    const bool thin_last = c->use_thin && nbt > 0 && P.border_used > 0 && P.border_used - (nbt - 1) * GSUM_TILE <= 8 &&
+                           P.border_used > (nbt - 1) * GSUM_TILE;
+    const int key[4] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0)};
     if (memcmp(key, c->df_key, sizeof(key)) != 0 || !c->df_tasks) {
         std::vector<int4> tasks;
-        df_build_tasks(tasks, P.T, P.Trows, batch, solve_only);
+        df_build_tasks(tasks, P.T, P.Trows, batch, solve_only, thin_last);
         const size_t bytes = tasks.size() * sizeof(int4);
         if (c->df_tasks_cap < bytes) {
             GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -179,24 +188,28 @@ static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool sol
     D.stats = nullptr;
     static long long *dbg_stats = nullptr;
     if (getenv("GSUM_B200_DF_STATS")) {
-        if (!dbg_stats) cudaMalloc((void **)&dbg_stats, sizeof(long long) * 8 * 1024);
-        cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * 8 * 1024, c->stream);
+        if (!dbg_stats) cudaMalloc((void **)&dbg_stats, sizeof(long long) * DF_NSTAT * 1024);
+        cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * DF_NSTAT * 1024, c->stream);
         D.stats = dbg_stats;
     }
     int grid = c->df_grid < D.ntasks ? c->df_grid : D.ntasks;
     void *args[] = {&D};
-    GSUM_CUDA(c, cudaLaunchCooperativeKernel((const void *)chol_dataflow_kernel, dim3(grid), dim3(DF_THREADS), args, CHOL_SMEM_BYTES, c->stream));
+    const void *kfn = D.stats ? (const void *)chol_dataflow_kernel<true> : (const void *)chol_dataflow_kernel<false>;
+    GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(DF_THREADS), args, CHOL_SMEM_BYTES, c->stream));
     df_check_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, c->stream>>>(c->df_ctl + 1, P.info, batch, c->df_ctl + 2);
     c->launches += 3;
     GSUM_CUDA(c, cudaPeekAtLastError());
     if (D.stats) {       // dev instrumentation: print the per-CTA cycle split of this launch
-        std::vector<long long> h(8 * grid);
+        std::vector<long long> h(DF_NSTAT * grid);
         cudaStreamSynchronize(c->stream);
-        cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * 8 * grid, cudaMemcpyDeviceToHost);
-        double tot = 0, wf = 0, ep = 0, nt = 0, a0 = 0, fl = 0, em = 0;
-        for (int g = 0; g < grid; g++) { tot += h[8*g]; wf += h[8*g+1]; ep += h[8*g+2]; nt += h[8*g+3]; a0 += h[8*g+4]; fl += h[8*g+5]; em += h[8*g+6]; }
-        fprintf(stderr, "[df] grid %d tasks %.0f  avg cycles/CTA: total %.0f | math: wait_full %.0f (%.0f%%) epilogue %.0f (%.0f%%) acc_load %.0f (%.0f%%) | producer: wait_flag %.0f (%.0f%%) wait_empty %.0f (%.0f%%)\n",
-                grid, nt, tot / grid, wf / grid, 100 * wf / tot, ep / grid, 100 * ep / tot, a0 / grid, 100 * a0 / tot, fl / grid, 100 * fl / tot, em / grid, 100 * em / tot);
+        cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * DF_NSTAT * grid, cudaMemcpyDeviceToHost);
+        double a[DF_NSTAT] = {0};
+        for (int g = 0; g < grid; g++) for (int q = 0; q < DF_NSTAT; q++) a[q] += (double)h[DF_NSTAT * g + q];
+        const double tot = a[0];
+        fprintf(stderr, "[df] grid %d tasks %.0f  avg cycles/CTA: total %.0f | math: claim %.1f%% acc_load %.1f%% wait_full %.1f%% epilogue %.1f%% fence+flag %.1f%% | producer: wait_flag %.1f%% wait_empty %.1f%%\n",
+                grid, a[3], tot / grid, 100 * a[8] / tot, 100 * a[4] / tot, 100 * a[1] / tot, 100 * a[2] / tot, 100 * a[7] / tot, 100 * a[5] / tot, 100 * a[6] / tot);
+        fprintf(stderr, "[df]   epilogue cycles/task: diag (n=%.0f) store %.0f potrf %.0f write %.0f | panel (n=%.0f) store %.0f trsm %.0f write %.0f\n",
+                a[12], a[9] / (a[12] + 1e-9), a[10] / (a[12] + 1e-9), a[11] / (a[12] + 1e-9), a[16], a[13] / (a[16] + 1e-9), a[14] / (a[16] + 1e-9), a[15] / (a[16] + 1e-9));
     }
     return 0;
 }
@@ -290,6 +303,7 @@ static int factor_bordered(gsum_ctx *c, double *dA, int64_t n, int Trows, int64_
     P.A = dA; P.ld = (int64_t)T * GSUM_TILE; P.bstride = (int64_t)Trows * GSUM_TILE * P.ld;
     P.W = dA + (int64_t)T * GSUM_TILE * P.ld; P.wstride = P.bstride;
     P.T = T; P.Trows = Trows; P.info = (int *)dinfo; P.logdet_part = (double *)dpart; P.n = (int)n;
+    P.border_used = (int)c->prof_border_rows;
     const bool prof = c->prof_enabled && c->prof_count < 256;
     if (prof) {
         if (!c->prof_ev[2 * c->prof_count]) { cudaEventCreate(&c->prof_ev[2 * c->prof_count]); cudaEventCreate(&c->prof_ev[2 * c->prof_count + 1]); }
@@ -476,8 +490,9 @@ static void launch_transpose_out(gsum_ctx *c, const double *src, int64_t src_ld,
     transpose_out_kernel<<<grid, 256, 0, c->stream>>>(src, src_ld, n, m, flip, scale, add, dst);
     LAUNCHED(c, 1);
 }
-static BorderedBatch solve_desc(double *F, double *W, int64_t np, int T, int64_t rows_pad) {
+static BorderedBatch solve_desc(double *F, double *W, int64_t np, int T, int64_t rows_pad, int64_t rows_used = 0) {
     BorderedBatch P;
+    P.border_used = (int)rows_used;
     P.A = F; P.ld = np; P.bstride = np * np; P.W = W; P.wstride = rows_pad * np;
     P.T = T; P.Trows = T + (int)(rows_pad / GSUM_TILE); P.info = nullptr; P.logdet_part = nullptr; P.n = (int)np;
     return P;
@@ -517,7 +532,7 @@ extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B
     GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dW));
     pad_factor(c, (const double *)dL, n, (double *)dF);
     launch_transpose_in(c, (const double *)dB, n, nrhs, nullptr, nullptr, 0, 1.0, (double *)dW, np, rp);
-    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp, nrhs), 1));
     double *dBout = (double *)dB;     // in place (caller's device buffer or our staging copy)
     if (forward_only) {
         launch_transpose_out(c, (const double *)dW, np, n, nrhs, 0, 1.0, nullptr, dBout);
@@ -529,7 +544,7 @@ extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B
         dim3 g2((unsigned)rp, (unsigned)((np + 255) / 256));
         flip_rows_kernel<<<g2, 256, 0, c->stream>>>((const double *)dW, (double *)dW2, np, n);
         LAUNCHED(c, 2);
-        GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW2, np, T, rp), 1));
+        GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW2, np, T, rp, nrhs), 1));
         launch_transpose_out(c, (const double *)dW2, np, n, nrhs, 1, 1.0, nullptr, dBout);
     }
     GSUM_TRY(dev_out_finish(c, B, dBout, sizeof(double) * n * nrhs, mem_kind));
@@ -875,7 +890,7 @@ extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, con
     GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dW));
     pad_factor(c, (const double *)dL, n, (double *)dF);
     launch_transpose_in(c, (const double *)dY, n, n_curves, (const double *)dmean, nullptr, 0, 1.0, (double *)dW, np, rp);
-    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp, n_curves), 1));
     if (E) {
         void *dE;
         GSUM_TRY(dev_out(c, WS_IO2, E, sizeof(double) * n * n_curves, mem_kind, &dE));
@@ -967,7 +982,7 @@ extern "C" int gsum_pc_errors(gsum_ctx *c, const double *Lp, const int32_t *piv,
     pad_factor(c, (const double *)dL, n, (double *)dF);
     // solve(G, r) with G = Lp[p_inv]  <=>  Lp e = r[piv]: gather rows in pivot order, forward substitute (gsum/diagnostics.py:103-104)
     launch_transpose_in(c, (const double *)dY, n, n_curves, (const double *)dmean, (const int32_t *)dpiv, 0, 1.0, (double *)dW, np, rp);
-    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp), 1));
+    GSUM_TRY(solve_run(c, solve_desc((double *)dF, (double *)dW, np, T, rp, n_curves), 1));
     GSUM_TRY(dev_out(c, WS_IO2, E, sizeof(double) * n * n_curves, mem_kind, &dE));
     launch_transpose_out(c, (const double *)dW, np, n, n_curves, 0, 1.0, nullptr, (double *)dE);
     GSUM_TRY(dev_out_finish(c, E, dE, sizeof(double) * n * n_curves, mem_kind));
