@@ -19,8 +19,10 @@
 #include "common.cuh"
 
 #define CHOL_THREADS 128
-// barrier over the 128 math threads only (the dataflow kernel adds a producer warp that must not take part)
-#define CONS_SYNC() asm volatile("bar.sync 1, 128;" ::: "memory")
+// Barrier over one 128-thread group: the math threads (0..127) of the multi-launch / dataflow kernels use id 1, the
+// epilogue groups of the pipeline kernel (threads 128.., 256..) ids 2, 3.  EPI_TID: thread index within the group.
+#define CONS_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory")
+#define EPI_TID ((int)(threadIdx.x & 127))
 #ifndef CHOL_NST
 #define CHOL_NST 3
 #endif
@@ -183,8 +185,8 @@ __device__ __forceinline__ void tile_store_acc(const Acc &acc, double *C, int64_
 // (2) the trailing 8x8 blocks get a rank-8 DMMA update.  The column is scaled by the reciprocal square root, as LAPACK
 // dpotf2 scales by the reciprocal of the pivot's square root.  *s_fail: failing column (1-based, LAPACK potrf
 // convention), 0 = ok; must be zeroed by the caller.
-__device__ __noinline__ void tile_potrf_blocked(double *S, double *dg, int *s_fail) {
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+__device__ __forceinline__ void tile_potrf_blocked_inl(double *S, double *dg, int *s_fail) {
+    const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
     for (int cb = 0; cb < 8; cb++) {
@@ -280,6 +282,11 @@ __device__ __noinline__ void tile_potrf_blocked(double *S, double *dg, int *s_fa
     }
     CONS_SYNC();
 }
+
+// Out-of-line copy for kernels whose register budget (168 at two CTAs per SM) the block step would overrun: the call
+// costs one save/restore of the callee-saved registers per diagonal tile.  NOT for use under setmaxnreg (the pipeline
+// kernel): caller regions compiled for a larger register count and this function disagree on the callee-saved set.
+__device__ __noinline__ void tile_potrf_blocked(double *S, double *dg, int *s_fail) { tile_potrf_blocked_inl(S, dg, s_fail); }
 
 // ---- epilogue 2: X = T * Lk^{-T} on a warp's 16 x 64 register block (rows are independent) ---------------------
 // Right-looking over 8-column blocks: (1) forward-substitute the 8x8 diagonal block — a row's 8 entries live in the 4
@@ -405,7 +412,7 @@ __device__ __forceinline__ void trsm_rows(Acc &T, const double *Lk, const double
 }
 // rdiag[j] = 1 / L_jj and the prescaled diagonal blocks, by the 128 math threads (caller syncs afterwards)
 __device__ __forceinline__ void trsm_prepare(const double *Lk, double *Lp, double *rdiag) {
-    const int tid = threadIdx.x;
+    const int tid = EPI_TID;
     if (tid < GSUM_TILE) rdiag[tid] = 1.0 / Lk[tid * GSUM_LDS + tid];
     for (int e = tid; e < 512; e += CHOL_THREADS) {
         const int cb = e >> 6, c = (e >> 3) & 7, m = e & 7;
@@ -418,9 +425,10 @@ __device__ __forceinline__ void trsm_prepare(const double *Lk, double *Lp, doubl
 // Epilogue shared by the multi-launch and the dataflow schedules.  S: a free 64x68 smem buffer with 160 spare doubles
 // behind it (diagonal tasks stage the tile there; panel tasks only use the spare doubles), Lk = L_kk staged in smem
 // (panel tasks).  Called by the 128 math threads.  `es`: optional dev instrumentation (cycle counters).
+template <bool INLINE_POTRF = false>
 __device__ __forceinline__ void tile_epilogue(const BorderedBatch &P, int i, int k, int b, Acc &acc, double *S, double *Lk, double *C,
                                               long long *es = nullptr) {
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
+    const int tid = EPI_TID, lane = tid & 31, w = tid >> 5, g = lane >> 2, t = lane & 3;
     const bool diag = (i == k);
     double *dg = S + GSUM_TILE * GSUM_LDS;                                    // 64 doubles behind the tile
     int *s_fail = reinterpret_cast<int *>(dg + 2 * GSUM_TILE);
@@ -438,7 +446,7 @@ __device__ __forceinline__ void tile_epilogue(const BorderedBatch &P, int i, int
         if (tid == 0) *s_fail = 0;
         CONS_SYNC();
         const long long e1 = es ? clock64() : 0;
-        tile_potrf_blocked(S, dg, s_fail);
+        if (INLINE_POTRF) tile_potrf_blocked_inl(S, dg, s_fail); else tile_potrf_blocked(S, dg, s_fail);
         const long long e2 = es ? clock64() : 0;
         const int fail = *s_fail;
         if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;

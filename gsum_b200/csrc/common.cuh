@@ -34,6 +34,8 @@ struct gsum_ctx {
     int *df_ctl;                // [0] task counter, [1] abort flag, [2] sticky abort (device)
     int df_grid;                // co-resident CTAs of the dataflow kernel (0 = not yet queried)
     int use_multilaunch;        // GSUM_B200_SCHEDULE=multilaunch: per-column launches instead (debug / comparison)
+    int use_pipeline;           // GSUM_B200_SCHEDULE=pipeline: warp-specialised one-CTA-per-SM schedule (pipeline.cuh)
+    int pl_grid;                // co-resident CTAs of the pipeline kernel (0 = not yet queried)
     int use_thin;               // GSUM_B200_THIN=0 disables the 8-row border tasks (debug / comparison)
 };
 

@@ -64,6 +64,13 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Polling load: L2-coherent, no L1 invalidate (ld.acquire.gpu compiles to LD + CCTL.IVALL, ~1000 cycles a poll).
+// Enough for the flags: whatever a set flag guards is read afterwards with cp.async.cg / from L2, never through L1.
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -72,27 +79,27 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, unsigned parity, const int *abort_flag) {
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023) == 0 && ld_acquire(abort_flag)) return false;
+        if ((++spins & 1023) == 0 && ld_relaxed(abort_flag)) return false;
     }
     return true;
 }
 // Bounded wait for a done flag (one lane polls).  Returns false on abort / watchdog.
 __device__ __forceinline__ bool flag_wait(const int *flag, int *abort_flag) {
-    if (ld_acquire(flag)) return true;
+    if (ld_relaxed(flag)) return true;
     const long long t0 = clock64();
-    while (!ld_acquire(flag)) {
+    while (!ld_relaxed(flag)) {
         __nanosleep(64);
-        if (ld_acquire(abort_flag)) return false;
+        if (ld_relaxed(abort_flag)) return false;
         if (clock64() - t0 > DF_WATCHDOG_CYCLES) { atomicExch(abort_flag, 1); return false; }
     }
     return true;
 }
 
-// AND-reduction + barrier over the 128 math threads (named barrier 2)
+// AND-reduction + barrier over one 128-thread group (named barrier 8 + group index)
 __device__ __forceinline__ bool cons_sync_and(bool v) {
     unsigned r;
-    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, 2, 128, q;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(r) : "r"((unsigned)v) : "memory");
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, %2, 128, q;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"((unsigned)v), "r"(8 + (int)(threadIdx.x >> 7)) : "memory");
     return r != 0;
 }
 

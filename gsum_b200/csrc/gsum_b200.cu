@@ -8,6 +8,7 @@
 #include "solve.cuh"
 #include "diag.cuh"
 #include "dataflow.cuh"
+#include "pipeline.cuh"
 #include <cstdlib>
 
 #define LAUNCHED(ctx, n) ((ctx)->launches += (n))
@@ -38,6 +39,9 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     const char *sched = getenv("GSUM_B200_SCHEDULE");
     c->use_multilaunch = (sched && strcmp(sched, "multilaunch") == 0) ? 1 : 0;
+    // default: the warp-specialised pipeline kernel; "dataflow" (two all-in-one CTAs per SM) and "multilaunch" (one launch
+    // per tile column) are kept for comparison and as cross-checks of one another
+    c->use_pipeline = (sched && (strcmp(sched, "dataflow") == 0 || strcmp(sched, "multilaunch") == 0)) ? 0 : 1;
     const char *thin = getenv("GSUM_B200_THIN");
     c->use_thin = (thin && strcmp(thin, "0") == 0) ? 0 : 1;
     *out = c;
@@ -139,6 +143,14 @@ static int scale_coords(gsum_ctx *c, const double *dX, const double *dls, double
 // ---- dataflow schedule of the bordered factorisation / border solve (one cooperative launch) ------------------------
 static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
     GSUM_TRY(chol_set_attrs(c));
+    if (c->use_pipeline && c->pl_grid == 0) {
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES));
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES));
+        int per_sm = 0;
+        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_pipeline_kernel<false>, PL_THREADS, PL_SMEM_BYTES));
+        if (per_sm < 1) return gsum_fail(c, -102, "pipeline kernel does not fit on an SM");
+        c->pl_grid = per_sm * c->sm_count;
+    }
     if (c->df_grid == 0) {
         GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
         GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
@@ -194,8 +206,14 @@ static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool sol
     }
     int grid = c->df_grid < D.ntasks ? c->df_grid : D.ntasks;
     void *args[] = {&D};
-    const void *kfn = D.stats ? (const void *)chol_dataflow_kernel<true> : (const void *)chol_dataflow_kernel<false>;
-    GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(DF_THREADS), args, CHOL_SMEM_BYTES, c->stream));
+    if (c->use_pipeline) {
+        grid = c->pl_grid < D.ntasks ? c->pl_grid : D.ntasks;
+        const void *kfn = D.stats ? (const void *)chol_pipeline_kernel<true> : (const void *)chol_pipeline_kernel<false>;
+        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(PL_THREADS), args, PL_SMEM_BYTES, c->stream));
+    } else {
+        const void *kfn = D.stats ? (const void *)chol_dataflow_kernel<true> : (const void *)chol_dataflow_kernel<false>;
+        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(DF_THREADS), args, CHOL_SMEM_BYTES, c->stream));
+    }
     df_check_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, c->stream>>>(c->df_ctl + 1, P.info, batch, c->df_ctl + 2);
     c->launches += 3;
     GSUM_CUDA(c, cudaPeekAtLastError());
@@ -206,10 +224,17 @@ static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool sol
         double a[DF_NSTAT] = {0};
         for (int g = 0; g < grid; g++) for (int q = 0; q < DF_NSTAT; q++) a[q] += (double)h[DF_NSTAT * g + q];
         const double tot = a[0];
+        if (c->use_pipeline) {
+            fprintf(stderr, "[pl] grid %d cycles/CTA %.0f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% | math (P tasks/CTA %.1f): wait_queue %.1f%% wait_operands %.1f%% wait_pbuf %.1f%%\n",
+                    grid, a[0] / grid, 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], a[8] / grid, 100 * a[5] / a[4], 100 * a[6] / a[4], 100 * a[7] / a[4]);
+            fprintf(stderr, "[pl]   epilogue: wait_queue %.1f%% wait_Lkk_flag %.1f%% wait_product %.1f%% | diag %.1f%% (%.0f cyc/task) panel %.1f%% thin %.1f%% fence+flag %.1f%%\n",
+                    100 * a[10] / a[9], 100 * a[11] / a[9], 100 * a[12] / a[9], 100 * a[13] / a[9], a[13] / (a[16] + 1e-9), 100 * a[14] / a[9], 100 * a[15] / a[9], 100 * a[17] / a[9]);
+        } else {
         fprintf(stderr, "[df] grid %d tasks %.0f  avg cycles/CTA: total %.0f | math: claim %.1f%% acc_load %.1f%% wait_full %.1f%% epilogue %.1f%% fence+flag %.1f%% | producer: wait_flag %.1f%% wait_empty %.1f%%\n",
                 grid, a[3], tot / grid, 100 * a[8] / tot, 100 * a[4] / tot, 100 * a[1] / tot, 100 * a[2] / tot, 100 * a[7] / tot, 100 * a[5] / tot, 100 * a[6] / tot);
         fprintf(stderr, "[df]   epilogue cycles/task: diag (n=%.0f) store %.0f potrf %.0f write %.0f | panel (n=%.0f) store %.0f trsm %.0f write %.0f\n",
                 a[12], a[9] / (a[12] + 1e-9), a[10] / (a[12] + 1e-9), a[11] / (a[12] + 1e-9), a[16], a[13] / (a[16] + 1e-9), a[14] / (a[16] + 1e-9), a[15] / (a[16] + 1e-9));
+        }
     }
     return 0;
 }

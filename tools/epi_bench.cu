@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(256, 1) epi_kernel(int mode, int hog, const do
         for (int mt = 0; mt < 2; mt++) for (int nt = 0; nt < 8; nt++) { acc[mt][nt][0] = 0; acc[mt][nt][1] = 0; }
         long long n = 0;
         while (!done) { stage_mma<true>(acc, ops, ops + 64 * GSUM_LDH, 8); n++; }
-        sink[tid] = acc[0][0][0] + acc[1][7][1];
+        double sum = 0;
+        for (int mt = 0; mt < 2; mt++) for (int nt = 0; nt < 8; nt++) sum += acc[mt][nt][0] + acc[mt][nt][1];
+        sink[tid] = sum;
         if (tid == 128) out[1] = n;
     }
 }

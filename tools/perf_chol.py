@@ -12,7 +12,7 @@ from bench import make_inputs, N_POINTS, N_Q
 from gsum_b200 import _lib, ops
 from gsum_b200.helpers import _order_differences
 
-modes = [a for a in sys.argv[1:] if a in ("dataflow", "multilaunch")] or ["dataflow", "multilaunch"]
+modes = [a for a in sys.argv[1:] if a in ("dataflow", "multilaunch", "pipeline")] or ["dataflow", "multilaunch"]
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 10
 n_ls = int(sys.argv[sys.argv.index("--nls") + 1]) if "--nls" in sys.argv else 128
 dev = torch.device("cuda", 0)
@@ -27,7 +27,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 results = {}
 for mode in modes:
     os.environ["GSUM_B200_SCHEDULE"] = mode
-    if "--stats" in sys.argv and mode == "dataflow":
+    if "--stats" in sys.argv and mode in ("dataflow", "pipeline"):
         os.environ["GSUM_B200_DF_STATS"] = "1"
     else:
         os.environ.pop("GSUM_B200_DF_STATS", None)
@@ -52,6 +52,7 @@ for mode in modes:
         print(f"{mode:12s} grid ms: min {min(tot):.3f} med {np.median(tot):.3f} | factor bracket {ms / nb:.3f} ms  "
               f"{fl / ms * 1e-9:.2f} TFLOP/s (algorithmic)  launches/step {ctx.launch_count // (reps + 3)}", flush=True)
         ctx.close()
-if len(results) == 2:
-    a, b = results["dataflow"], results["multilaunch"]
-    print("schedules bit-identical:", np.array_equal(a, b), "max rel diff", np.max(np.abs(a - b) / np.abs(b)))
+names = list(results)
+for other in names[1:]:
+    a, b = results[names[0]], results[other]
+    print(f"{names[0]} vs {other}: bit-identical {np.array_equal(a, b)}  max rel diff {np.max(np.abs(a - b) / np.abs(b)):.3e}")
