@@ -138,3 +138,26 @@ def test_large_draw_count_grid_limits(ctx):
     lower, upper = st.norm(loc=np.zeros(n), scale=sd).interval(np.atleast_2d(iv).T)
     _, cv = ops.draws(L, np.zeros(n), n_draws=70000, seed=11, lower=lower, upper=upper, want_draws=False)
     assert cv.shape == (70000, 7) and np.max(np.abs(cv.mean(0) - iv)) < 0.01
+
+
+def test_c5_full_size_properties(ctx):
+    """Config C5 at full size (N = 4096; 64 held-out curves; 1e5 draws): pivot vector bit-exact against LAPACK dpstrf,
+    G G^T = cov, sum of squared PC errors == MD^2 == sum of squared Cholesky errors, MD^2 ~ chi2(N), and the fused
+    draw + coverage pass is calibrated (coverage of 1e5 draws within 0.2 % of the nominal level at 101 levels)."""
+    from scipy.linalg.lapack import dpstrf
+    n = 4096
+    X = np.linspace(0, 1, n)[:, None]
+    cov = 1.3 * (RBF(0.2)(X) + 1e-5 * np.eye(n))
+    mean = np.zeros(n)
+    d = gb.Diagnostic(mean, cov, random_state=4)
+    c_, p_, r_, info = dpstrf(cov, lower=True)
+    assert info == 0 and r_ == n and np.array_equal(d._piv, p_ - 1)
+    assert relerr(d._pchol @ d._pchol.T, cov) < 1e-13
+    Y = d.samples(64)
+    md2 = d.md_squared(Y)
+    E, Ep = d.cholesky_errors(Y), d.pivoted_cholesky_errors(Y)
+    assert relerr((E ** 2).sum(0), md2) < 1e-12 and relerr((Ep ** 2).sum(0), md2) < 1e-8
+    assert abs(md2.mean() - n) < 6 * np.sqrt(2 * n / 64)
+    iv = np.linspace(0, 1, 101)
+    cv = d.sample_coverage(100000, iv)
+    assert cv.shape == (100000, 101) and np.max(np.abs(cv.mean(0) - iv)) < 2e-3

@@ -4,6 +4,7 @@ import pytest
 from sklearn.gaussian_process.kernels import RBF, ConstantKernel as C, WhiteKernel
 
 import gsum_b200 as gb
+from oracle import gsum_oracle as o
 from util import prior_kwargs, relerr
 
 pytestmark = pytest.mark.gpu
@@ -137,3 +138,32 @@ def test_sample_y_statistics(ctx):
     assert S.shape == (12, 4000)
     assert np.max(np.abs(S.mean(1) - m)) < 5 * np.sqrt(np.max(np.diag(cv)) / 4000) + 1e-12
     assert relerr(np.cov(S), cv) < 0.15
+
+
+def test_c3_full_size_properties(ctx):
+    """Config C3 at full size (2-D 50 x 50 = 2500 training points, 10 000 test points): the oracle on a slice of the
+    test points, and size-independent properties — predictions are pointwise (a slice of the result equals the result
+    of the slice), interpolation at the training points, std >= 0 and finite everywhere."""
+    rs = np.random.RandomState(2)
+    g1 = np.linspace(0, 1, 50)
+    X = o.cartesian(g1, g1)
+    n = len(X)
+    Xt = rs.rand(10000, 2)
+    kern = RBF([0.02, 0.03], 'fixed') + WhiteKernel(1e-6, 'fixed')
+    coeffs = np.linalg.cholesky(RBF([0.02, 0.03])(X) + 1e-8 * np.eye(n)) @ rs.randn(n, 6)
+    orders = np.arange(6)
+    y = o.partials(coeffs, 0.4, 1.0, orders)
+    gp = gb.TruncationGP(kern, ratio=0.4, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None).fit(X, y, orders=orders)
+    m, s = gp.coeffs_process.predict(Xt, return_std=True)
+    assert m.shape == (10000, 6) and s.shape == (10000,) and np.isfinite(m).all() and np.isfinite(s).all() and (s >= 0).all()
+    f = o.fit_conjugate(kern, X, o.coefficients(y, 0.4, 1.0, orders), o.Priors(0, 0, 1, 1))
+    mr, sr = o.predict_conjugate(f, Xt[:256], return_std=True)
+    assert relerr(m[:256], mr) < RTOL and relerr(s[:256], sr) < 1e-9
+    m2, s2 = gp.coeffs_process.predict(Xt[4000:4256], return_std=True)
+    assert np.array_equal(m2, m[4000:4256]) and np.array_equal(s2, s[4000:4256])          # pointwise
+    mi, si = gp.coeffs_process.predict(X[::7], return_std=True)                              # interpolation (noise 1e-6)
+    assert np.max(np.abs(mi - gp.coeffs_[::7])) < 1e-3 * np.max(np.abs(gp.coeffs_)) and si.max() < 2e-3 * np.sqrt(gp.coeffs_process.cov_factor_) * 10
+    mt, st_ = gp.predict(Xt, order=5, return_std=True, kind='both')
+    assert mt.shape == (10000,) and np.isfinite(mt).all() and np.isfinite(st_).all()
+    mt2, st2 = gp.predict(Xt[:128], order=5, return_std=True, kind='both')
+    assert np.array_equal(mt2, mt[:128]) and np.array_equal(st2, st_[:128])
