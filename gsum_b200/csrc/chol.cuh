@@ -84,39 +84,35 @@ typedef double Acc[2][8][2];
 
 // One pipeline stage (K depth 32): acc -= A[16 rows of this warp] * B[8*ntm rows]^T.  `ntm` = n-tiles this warp needs
 // (8 everywhere except on a diagonal tile, where warp w only owns columns < 16*(w+1)); FULL drops the predicates.
-// Issue order: two k-steps at a time, accumulators in groups of DMMA_GROUP — so a DMMA depends on the one DMMA_GROUP
-// instructions earlier and the warp never has more than ~DMMA_GROUP of them queued in the FP64 pipe.  (Measured,
-// tools/fp64_latency.cu: a warp streaming 16 independent DMMAs keeps the pipe's queue full and every FP64 instruction
-// of another warp on the same SM sub-partition — the epilogues' dependent chains — then takes ~275 cycles instead of 32.)
-#ifndef DMMA_GROUP
-#define DMMA_GROUP 4
+// MMA_PASSES > 1 walks the stage in passes over the n tiles (every accumulator then is a dependent chain over the 8
+// k-steps and the warp has at most 16 / MMA_PASSES DMMAs in flight).  Kept as a switch for the record: measured
+// (profiles/r01_fp64_latency.txt) it changes neither the stage time (2441 cycles) nor what a co-resident warp's FP64
+// chain suffers beside the main loop — that is arbitration at the pipe, not queue depth.
+#ifndef MMA_PASSES
+#define MMA_PASSES 1
 #endif
 template <bool FULL>
 __device__ __forceinline__ void stage_mma(Acc &acc, const double *As, const double *Bs, int ntm) {
     const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 3, g = lane >> 2, t = lane & 3;
     const double *ap = As + (w * 16 + g) * GSUM_LDH + t;
     const double *bp = Bs + g * GSUM_LDH + t;
-    constexpr int NTG = DMMA_GROUP / 2;                  // n tiles per group (x 2 m tiles)
+    constexpr int NTP = 8 / MMA_PASSES;                  // n tiles per pass
 #pragma unroll
-    for (int ks = 0; ks < GSUM_KH / 4; ks += 2) {
-        double a[2][2], b[2][8];
+    for (int n0 = 0; n0 < 8; n0 += NTP) {
 #pragma unroll
-        for (int kk = 0; kk < 2; kk++) {
+        for (int ks = 0; ks < GSUM_KH / 4; ks++) {
+            double a[2], b[NTP];
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++) a[kk][mt] = -ap[mt * 8 * GSUM_LDH + (ks + kk) * 4];
+            for (int mt = 0; mt < 2; mt++) a[mt] = -ap[mt * 8 * GSUM_LDH + ks * 4];
 #pragma unroll
-            for (int nt = 0; nt < 8; nt++) if (FULL || nt < ntm) b[kk][nt] = bp[nt * 8 * GSUM_LDH + (ks + kk) * 4];
+            for (int q = 0; q < NTP; q++) if (FULL || n0 + q < ntm) b[q] = bp[(n0 + q) * 8 * GSUM_LDH + ks * 4];
+#pragma unroll
+            for (int q = 0; q < NTP; q++)
+                if (FULL || n0 + q < ntm) {
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][n0 + q][0], acc[mt][n0 + q][1], a[mt], b[q]);
+                }
         }
-#pragma unroll
-        for (int n0 = 0; n0 < 8; n0 += NTG)
-#pragma unroll
-            for (int kk = 0; kk < 2; kk++)
-#pragma unroll
-                for (int nt = n0; nt < n0 + NTG; nt++)
-                    if (FULL || nt < ntm) {
-#pragma unroll
-                        for (int mt = 0; mt < 2; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[kk][mt], b[kk][nt]);
-                    }
     }
 }
 

@@ -76,10 +76,18 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 }
 
 // Bounded mbarrier wait; returns false if the kernel is aborting.
-__device__ __forceinline__ bool mbar_wait(uint64_t *bar, unsigned parity, const int *abort_flag) {
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, unsigned parity, int *abort_flag) {
+    if (mbar_try_wait(bar, parity)) return true;
     int spins = 0;
+    long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 1023) == 0 && ld_relaxed(abort_flag)) return false;
+        if ((++spins & 1023) == 0) {
+            if (ld_relaxed(abort_flag)) return false;
+            // the intra-CTA handshakes are covered by the same watchdog as the flags: a protocol error must surface as an
+            // error code, never as a hung GPU
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > DF_WATCHDOG_CYCLES) { atomicExch(abort_flag, 1); return false; }
+        }
     }
     return true;
 }
@@ -330,22 +338,34 @@ __global__ void df_check_kernel(const int *abort_flag, int *info, int64_t batch,
 }
 
 #include <vector>
-// Task list in dependency order with one column of look-ahead: right after the first sub-diagonal tile of column k comes
-// the diagonal tile of column k+1, so that the (latency-bound) POTRF chain runs ahead of the bulk of column k.
-static inline void df_build_tasks(std::vector<int4> &out, int T, int Trows, int batch, bool solve_only, bool thin_last) {
+// Task list in dependency order with one column of look-ahead.  Column k: first the sub-diagonal tiles (k+1, k, b) of
+// every matrix — the only fresh operand of the next diagonal tile — then `DF_DIAG_DELAY` of the other tiles of the
+// column, then the diagonal tiles (k+1, k+1, b), then the rest.  The diagonal tiles thus start as early as they can
+// without stalling their CTA on the flag of a tile that is still being computed (the POTRF chain is the critical path).
+#ifndef DF_DIAG_DELAY
+#define DF_DIAG_DELAY 1184
+#endif
+static inline void df_build_tasks(std::vector<int4> &out, int T, int Trows, int batch, bool solve_only, bool thin_last, int diag_delay = DF_DIAG_DELAY) {
     out.clear();
     auto flags = [&](int i) { return (thin_last && i == Trows - 1 && i >= T) ? 1 : 0; };
     if (solve_only) {
         for (int k = 0; k < T; k++)
             for (int i = T; i < Trows; i++)
-                for (int b = 0; b < batch; b++) out.push_back(make_int4(i, k, b, flags(i)));
+                for (int b = 0; b < batch; b++) out.push_back(make_int4(i, k, b, 0 | flags(i)));
         return;
     }
     for (int k = 0; k < T; k++) {
         if (k == 0) for (int b = 0; b < batch; b++) out.push_back(make_int4(0, 0, b, 0));
         if (k + 1 < Trows) for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k, b, flags(k + 1)));
-        if (k + 1 < T) for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k + 1, b, 0));
-        for (int b = 0; b < batch; b++)
-            for (int i = k + 2; i < Trows; i++) out.push_back(make_int4(i, k, b, flags(i)));
+        int emitted = 0;
+        bool diag_done = !(k + 1 < T);
+        auto emit_diag = [&]() { for (int b = 0; b < batch; b++) out.push_back(make_int4(k + 1, k + 1, b, 0)); diag_done = true; };
+        for (int i = k + 2; i < Trows; i++)
+            for (int b = 0; b < batch; b++) {
+                if (!diag_done && emitted >= diag_delay) emit_diag();
+                out.push_back(make_int4(i, k, b, flags(i)));
+                emitted++;
+            }
+        if (!diag_done) emit_diag();
     }
 }

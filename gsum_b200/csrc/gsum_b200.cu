@@ -168,7 +168,7 @@ static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool sol
     const int key[4] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0)};
     if (memcmp(key, c->df_key, sizeof(key)) != 0 || !c->df_tasks) {
         std::vector<int4> tasks;
-        df_build_tasks(tasks, P.T, P.Trows, batch, solve_only, thin_last);
+        df_build_tasks(tasks, P.T, P.Trows, batch, solve_only, thin_last, getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : DF_DIAG_DELAY);
         const size_t bytes = tasks.size() * sizeof(int4);
         if (c->df_tasks_cap < bytes) {
             GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -227,6 +227,8 @@ static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool sol
         if (c->use_pipeline) {
             fprintf(stderr, "[pl] grid %d cycles/CTA %.0f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% | math (P tasks/CTA %.1f): wait_queue %.1f%% wait_operands %.1f%% wait_pbuf %.1f%%\n",
                     grid, a[0] / grid, 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], a[8] / grid, 100 * a[5] / a[4], 100 * a[6] / a[4], 100 * a[7] / a[4]);
+            fprintf(stderr, "[pl]   math wait_operands split: first stage of a full task %.1f%%, thin tasks %.1f%%, later stages of diagonal tasks %.1f%%, of panel tasks %.1f%%\n",
+                    100 * a[18] / a[4], 100 * a[19] / a[4], 100 * a[20] / a[4], 100 * (a[6] - a[18] - a[19] - a[20]) / a[4]);
             fprintf(stderr, "[pl]   epilogue: wait_queue %.1f%% wait_Lkk_flag %.1f%% wait_product %.1f%% | diag %.1f%% (%.0f cyc/task) panel %.1f%% thin %.1f%% fence+flag %.1f%%\n",
                     100 * a[10] / a[9], 100 * a[11] / a[9], 100 * a[12] / a[9], 100 * a[13] / a[9], a[13] / (a[16] + 1e-9), 100 * a[14] / a[9], 100 * a[15] / a[9], 100 * a[17] / a[9]);
         } else {

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) chol_pipeline_kernel(DataflowAr
                 for (int nt = 0; nt < 8; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
             bool alive = true;
             for (int h = 0; h < 2 * k; h++) {
-                { PL_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, D.abort_flag); PL_ACC(1); }
+                { PL_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, D.abort_flag); PL_ACC(1); if (thin) PL_ACC(5); else if (h == 0) PL_ACC(4); else if (diag) PL_ACC(6); }
                 if (!alive) break;
                 const double *As = ring_base + ring.stage * CHOL_STAGE_DOUBLES;
                 const double *Bs = diag ? As : As + GSUM_TILE * GSUM_LDH;
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(PL_THREADS, 1) chol_pipeline_kernel(DataflowAr
             if (lane == 0) mbar_arrive(&p_full[pb]);
             pcount++;
         }
-        if (st_on && tid == 0) { long long *o = D.stats + (int64_t)blockIdx.x * DF_NSTAT; o[4] = clock64() - st_t0; o[5] = st[0]; o[6] = st[1]; o[7] = st[2]; o[8] = st[3]; }
+        if (st_on && tid == 0) { long long *o = D.stats + (int64_t)blockIdx.x * DF_NSTAT; o[4] = clock64() - st_t0; o[5] = st[0]; o[6] = st[1]; o[7] = st[2]; o[8] = st[3]; o[18] = st[4]; o[19] = st[5]; o[20] = st[6]; }
     } else {
 #ifndef PL_NO_SETMAXNREG
         asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");

@@ -83,7 +83,7 @@ int main() {
             epi_kernel<<<1, 256, smem>>>(mode, hog, dA, dL, 20, out, sink);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
-            printf("%-34s %s: %8lld cycles   (DMMA_GROUP %d, hog stages %lld)\n", names[mode], hog ? "under a DMMA main loop" : "alone                 ", out[0], DMMA_GROUP, out[1]);
+            printf("%-34s %s: %8lld cycles   (MMA_PASSES %d, hog stages %lld)\n", names[mode], hog ? "under a DMMA main loop" : "alone                 ", out[0], MMA_PASSES, out[1]);
         }
     return 0;
 }

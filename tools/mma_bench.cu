@@ -26,14 +26,14 @@ int main() {
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4608 * 8);
     for (int grid : {1, 148})
         for (int nw : {1, 4, 8})
-            for (int iters : {200, 800}) {
+            for (int iters : {800}) {
                 cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
                 cudaEventRecord(e0);
                 k<<<grid, 256, 2 * 4608 * 8>>>(nw, iters, out, sink);
                 cudaEventRecord(e1);
                 if (cudaDeviceSynchronize() != cudaSuccess) { printf("error\n"); return 1; }
                 float ms; cudaEventElapsedTime(&ms, e0, e1);
-                printf("grid %3d  %d warps/CTA  iters %3d: %.0f cycles per stage per warp | kernel %.3f ms -> %.2f TFLOP/s\n", grid, nw, iters,
+                printf("MMA_PASSES %d grid %3d  %d warps/CTA  iters %3d: %.0f cycles per stage per warp | kernel %.3f ms -> %.2f TFLOP/s\n", MMA_PASSES, grid, nw, iters,
                        (double)out[0] / iters, ms, (double)grid * nw * iters * 128 * 512 / (ms * 1e-3) * 1e-12);
             }
     return 0;
