@@ -37,6 +37,11 @@ struct gsum_ctx {
     int use_pipeline;           // GSUM_B200_SCHEDULE=pipeline: warp-specialised one-CTA-per-SM schedule (pipeline.cuh)
     int pl_grid;                // co-resident CTAs of the pipeline kernel (0 = not yet queried)
     int use_thin;               // GSUM_B200_THIN=0 disables the 8-row border tasks (debug / comparison)
+    // heterogeneous schedule (hetero.cuh, the default): two cached claim lists
+    int use_hetero;
+    void *ht_gtasks, *ht_ftasks; size_t ht_gcap, ht_fcap; int ht_key[5]; int ht_ng, ht_nf;
+    int ht_ready;               // function attributes set / co-residency checked
+    int ht_factor_ctas;         // GSUM_B200_FACTOR_CTAS (default HT_FACTOR_CTAS)
 };
 
 static inline int gsum_fail(gsum_ctx *c, int code, const char *fmt, ...) {

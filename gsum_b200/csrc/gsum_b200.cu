@@ -9,13 +9,14 @@
 #include "diag.cuh"
 #include "dataflow.cuh"
 #include "pipeline.cuh"
+#include "hetero.cuh"
 #include <cstdlib>
 
 #define LAUNCHED(ctx, n) ((ctx)->launches += (n))
 
 enum {
     WS_X = 0, WS_XS, WS_DY, WS_REF, WS_ORD, WS_LS, WS_Q, WS_DETF, WS_MAT, WS_RHS, WS_GRAM, WS_LOGDET, WS_INFO,
-    WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3
+    WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_MKK
 };
 
 extern "C" int gsum_version(void) { return 100; }
@@ -42,6 +43,10 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     // default: the warp-specialised pipeline kernel; "dataflow" (two all-in-one CTAs per SM) and "multilaunch" (one launch
     // per tile column) are kept for comparison and as cross-checks of one another
     c->use_pipeline = (sched && (strcmp(sched, "dataflow") == 0 || strcmp(sched, "multilaunch") == 0)) ? 0 : 1;
+    // default schedule: heterogeneous (hetero.cuh); "pipeline" / "dataflow" / "multilaunch" select the older ones
+    c->use_hetero = (sched && strcmp(sched, "hetero") == 0) ? 1 : 0;
+    const char *fc = getenv("GSUM_B200_FACTOR_CTAS");
+    c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
     const char *thin = getenv("GSUM_B200_THIN");
     c->use_thin = (thin && strcmp(thin, "0") == 0) ? 0 : 1;
     *out = c;
@@ -54,6 +59,8 @@ extern "C" int gsum_ctx_destroy(gsum_ctx *c) {
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 24; i++) if (c->ws[i]) cudaFree(c->ws[i]);
     if (c->df_tasks) cudaFree(c->df_tasks);
+    if (c->ht_gtasks) cudaFree(c->ht_gtasks);
+    if (c->ht_ftasks) cudaFree(c->ht_ftasks);
     if (c->df_flags) cudaFree(c->df_flags);
     if (c->df_ctl) cudaFree(c->df_ctl);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -240,12 +247,113 @@ static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool sol
     }
     return 0;
 }
+// ---- heterogeneous schedule (hetero.cuh): GEMM CTAs + factor CTAs in one cooperative launch --------------------------
+static int ht_upload(gsum_ctx *c, void **buf, size_t *cap, const std::vector<int4> &v) {
+    const size_t bytes = v.size() * sizeof(int4);
+    if (*cap < bytes || !*buf) {
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (*buf) GSUM_CUDA(c, cudaFree(*buf));
+        GSUM_CUDA(c, cudaMalloc(buf, bytes + 4096));
+        *cap = bytes + 4096;
+    }
+    if (bytes) GSUM_CUDA(c, cudaMemcpy(*buf, v.data(), bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
+    if (!c->ht_ready) {
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
+        int per_sm = 0;
+        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_hetero_kernel<false>, HT_THREADS, HT_SMEM_BYTES));
+        if (per_sm < 1) return gsum_fail(c, -102, "hetero kernel does not fit on an SM");
+        c->ht_ready = 1;
+    }
+    const int nbt = P.Trows - P.T;
+    const bool thin_last = c->use_thin && nbt > 0 && P.border_used > 0 && P.border_used - (nbt - 1) * GSUM_TILE <= 8 &&
+                           P.border_used > (nbt - 1) * GSUM_TILE;
+    const int delay = getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : HT_DIAG_DELAY;
+    const int key[5] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0), delay};
+    if (memcmp(key, c->ht_key, sizeof(key)) != 0 || !c->ht_gtasks) {
+        std::vector<int4> gt, ft;
+        ht_build_tasks(gt, ft, P.T, P.Trows, batch, solve_only, thin_last, delay);
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // the previous lists may still be in use
+        GSUM_TRY(ht_upload(c, &c->ht_gtasks, &c->ht_gcap, gt));
+        GSUM_TRY(ht_upload(c, &c->ht_ftasks, &c->ht_fcap, ft));
+        memcpy(c->ht_key, key, sizeof(key));
+        c->ht_ng = (int)gt.size(); c->ht_nf = (int)ft.size();
+    }
+    const size_t fbytes = sizeof(int) * (size_t)batch * P.Trows * P.T;
+    if (c->df_flags_cap < fbytes) {
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->df_flags) GSUM_CUDA(c, cudaFree(c->df_flags));
+        GSUM_CUDA(c, cudaMalloc(&c->df_flags, fbytes + 4096));
+        c->df_flags_cap = fbytes + 4096;
+    }
+    if (!c->df_ctl) {
+        GSUM_CUDA(c, cudaMalloc((void **)&c->df_ctl, 4 * sizeof(int)));
+        GSUM_CUDA(c, cudaMemsetAsync(c->df_ctl, 0, 4 * sizeof(int), c->stream));
+    }
+    void *dM;
+    GSUM_TRY(gsum_ws(c, WS_MKK, sizeof(double) * (size_t)batch * P.T * GSUM_TILE * GSUM_TILE, &dM));
+    const int64_t nflags = (int64_t)batch * P.Trows * P.T;
+    ht_init_kernel<<<(unsigned)((nflags + 255) / 256 + 1), 256, 0, c->stream>>>((int *)c->df_flags, c->df_ctl, batch, P.Trows, P.T, solve_only ? 1 : 0);
+    c->launches += 1;
+    if (solve_only) {
+        ht_mkk_from_factor_kernel<<<dim3(P.T, batch), CHOL_THREADS, 0, c->stream>>>(P, (double *)dM);
+        c->launches += 1;
+    }
+    HeteroArgs D;
+    D.P = P; D.gtasks = (const int4 *)c->ht_gtasks; D.ngtasks = c->ht_ng; D.ftasks = (const int4 *)c->ht_ftasks; D.nftasks = c->ht_nf;
+    D.ctl = c->df_ctl; D.flags = (int *)c->df_flags; D.M = (double *)dM; D.stats = nullptr;
+    // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
+    int nf = 0;
+    if (c->ht_nf > 0) {
+        nf = c->ht_factor_ctas;
+        const int cap = (c->ht_nf + 2) / 3;
+        if (nf > cap) nf = cap;
+        if (nf > c->sm_count / 2) nf = c->sm_count / 2;
+        if (nf < 1) nf = 1;
+    }
+    int ng = c->sm_count - nf;
+    if (ng > c->ht_ng) ng = c->ht_ng;
+    D.nfactor_ctas = nf;
+    const int grid = nf + ng;
+    if (grid <= 0) return 0;
+    static long long *dbg_stats = nullptr;
+    if (getenv("GSUM_B200_DF_STATS")) {
+        if (!dbg_stats) cudaMalloc((void **)&dbg_stats, sizeof(long long) * HT_NSTAT * 1024);
+        cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * HT_NSTAT * 1024, c->stream);
+        D.stats = dbg_stats;
+    }
+    void *args[] = {&D};
+    const void *kfn = D.stats ? (const void *)chol_hetero_kernel<true> : (const void *)chol_hetero_kernel<false>;
+    GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HT_THREADS), args, HT_SMEM_BYTES, c->stream));
+    df_check_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, c->stream>>>(c->df_ctl + 1, P.info, batch, c->df_ctl + 2);
+    c->launches += 2;
+    GSUM_CUDA(c, cudaPeekAtLastError());
+    if (D.stats) {
+        std::vector<long long> h(HT_NSTAT * grid);
+        cudaStreamSynchronize(c->stream);
+        cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * HT_NSTAT * grid, cudaMemcpyDeviceToHost);
+        double f[4] = {0, 0, 0, 0}, a[HT_NSTAT] = {0};
+        for (int g = 0; g < nf; g++) for (int wk = 0; wk < 3; wk++) for (int q = 0; q < 4; q++) f[q] += (double)h[HT_NSTAT * g + wk * 4 + q];
+        for (int g = nf; g < grid; g++) for (int q = 0; q < HT_NSTAT; q++) a[q] += (double)h[HT_NSTAT * g + q];
+        if (nf) fprintf(stderr, "[ht] factor CTAs %d: cycles/worker %.0f | wait_S %.1f%% | busy %.1f%% (%.0f cycles per diagonal tile, %.1f tiles per worker)\n",
+                        nf, f[0] / (3 * nf), 100 * f[1] / f[0], 100 * f[2] / f[0], f[2] / (f[3] + 1e-9), f[3] / (3 * nf));
+        if (ng) fprintf(stderr, "[ht] GEMM CTAs %d: cycles/CTA %.0f, tasks/CTA %.1f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% wait_Mkk %.1f%% | math: wait_queue %.1f%% wait_operands %.1f%% wait_Mkk %.1f%% trsm %.1f%% fence+flag %.1f%%\n",
+                        ng, a[5] / ng, a[11] / ng, 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0],
+                        100 * a[6] / a[5], 100 * a[7] / a[5], 100 * a[8] / a[5], 100 * a[9] / a[5], 100 * a[10] / a[5]);
+    }
+    return 0;
+}
 static int factor_run(gsum_ctx *c, const BorderedBatch &P, int batch) {
-    return c->use_multilaunch ? chol_bordered_run(c, P, batch) : dataflow_run(c, P, batch, false);
+    if (c->use_multilaunch) return chol_bordered_run(c, P, batch);
+    return c->use_hetero ? hetero_run(c, P, batch, false) : dataflow_run(c, P, batch, false);
 }
 static int solve_run(gsum_ctx *c, const BorderedBatch &P, int batch) {
     if (P.Trows - P.T <= 0) return 0;
-    return c->use_multilaunch ? chol_solve_border_run(c, P, batch) : dataflow_run(c, P, batch, true);
+    if (c->use_multilaunch) return chol_solve_border_run(c, P, batch);
+    return c->use_hetero ? hetero_run(c, P, batch, true) : dataflow_run(c, P, batch, true);
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------------

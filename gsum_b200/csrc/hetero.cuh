@@ -1,0 +1,559 @@
+// Heterogeneous persistent schedule of the bordered Cholesky (K2 + K3 in ONE launch): the default factorisation kernel.
+//
+// What the measurements of the earlier schedules say (profiles/r01_notes.md, tools/fp64_latency.cu, tools/mma_bench.cu):
+//   * one DMMA-streaming warp per SM sub-partition reaches 84 % of the FP64 tensor issue rate, two reach 99.5 %;
+//   * any FP64 dependency chain (POTRF, row substitution) that shares a sub-partition with a streaming warp is starved
+//     (275 cycles per dependent instruction beside one stream, ~10^4 beside two).
+// So the latency chains and the streams must not share an SM, and whatever stays next to the streams must itself be DMMA:
+//
+//   GEMM CTAs   (most SMs; 8 math warps = two per sub-partition, 4 producer warps).  A task (i, k, b) runs
+//               S = C_ik - sum_j L_ij L_kj^T with 16x32 warp tiles, operands streamed by the producers through an
+//               mbarrier ring (cp.async.cg), then
+//                 i >  k : the triangular solve X = S L_kk^{-T} as DMMAs only — block substitution over 8-column blocks
+//                          against M_kk, the tile L_kk whose 8x8 diagonal blocks were replaced by their inverses (8
+//                          dependent steps of two DMMAs each, warp-local on an 8x64 row block, no FP64 scalar chain).
+//                          Inverting only the 8x8 diagonal blocks keeps the accuracy of a true substitution (measured
+//                          against extended precision: same error as LAPACK's dtrsm, where a full 64x64 inverse loses a
+//                          digit);
+//                 i == k : S goes back to global memory, flag := 1 (the SYRK half of a diagonal task).
+//   factor CTAs (a few SMs, three independent 128-thread workers each) take the diagonal tiles: wait for S, POTRF in
+//               shared memory (chol.cuh), write L_kk, invert the eight 8x8 diagonal blocks, write M_kk, flag := 2.
+//               Nothing else runs on their SM, so the chain sees the bare 32-cycle DFMA latency.
+//
+// Both roles claim their tasks in order from two lists derived from ONE topologically ordered list (df_build_tasks), so
+// the earliest unfinished task of the joint order is always claimed and never waits: no deadlock with all CTAs
+// co-resident (cooperative launch).  Every wait is bounded by the watchdog / abort flag of dataflow.cuh.
+#pragma once
+#include "dataflow.cuh"
+
+#define HT_THREADS 384                  // GEMM CTA: 8 math warps | 4 producer warps;  factor CTA: 3 workers x 128 threads
+#define HT_MATH_WARPS 8
+#define HT_PRODUCER_WARP 8
+#ifndef HT_NST
+#define HT_NST 4                        // ring stages (36 KiB each: an operand half-slab pair, or one whole 64x64 tile)
+#endif
+#define HT_QD 4                         // task queue depth
+#define HT_STAGE_DOUBLES CHOL_STAGE_DOUBLES
+#define HT_SBUF_DOUBLES (GSUM_TILE * GSUM_LDS)
+#define HT_SMEM_DOUBLES (HT_NST * HT_STAGE_DOUBLES + HT_SBUF_DOUBLES)
+#define HT_SMEM_BYTES (HT_SMEM_DOUBLES * 8)
+#define HT_WORKER_DOUBLES (GSUM_TILE * GSUM_LDS + 3 * GSUM_TILE)     // factor worker: tile + diag + scratch ints
+#define HT_NSTAT 16
+#ifndef HT_FACTOR_CTAS
+#define HT_FACTOR_CTAS 16               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
+#endif
+#ifndef HT_DIAG_DELAY
+#define HT_DIAG_DELAY 1184
+#endif
+
+struct HeteroArgs {
+    BorderedBatch P;
+    const int4 *gtasks;     // GEMM tasks (i, k, b, flags) in schedule order; flags bit 0: thin border task (<= 8 rows in use)
+    int ngtasks;
+    const int4 *ftasks;     // factor tasks (k, b, 0, 0) in schedule order
+    int nftasks;
+    int *ctl;               // [0] GEMM task counter, [1] abort flag, [2] sticky abort, [3] factor task counter
+    int *flags;             // per (b, i, k): index (b * Trows + i) * T + k.  i > k: 1 = tile final.  i == k: 1 = S ready, 2 = L_kk and M_kk final
+    double *M;              // (batch, T, 64, 64): L_kk with its 8x8 diagonal blocks inverted
+    int nfactor_ctas;       // CTAs [0, nfactor_ctas) are factor CTAs
+    long long *stats;       // optional per-CTA cycle counters [grid][HT_NSTAT]
+};
+
+__device__ __forceinline__ bool flag_wait_ge(const int *flag, int want, int *abort_flag) {
+    if (ld_relaxed(flag) >= want) return true;
+    const long long t0 = clock64();
+    while (ld_relaxed(flag) < want) {
+        __nanosleep(64);
+        if (ld_relaxed(abort_flag)) return false;
+        if (clock64() - t0 > DF_WATCHDOG_CYCLES) { atomicExch(abort_flag, 1); return false; }
+    }
+    return true;
+}
+// barriers over the 256 math threads of a GEMM CTA
+#define HT_MATH_SYNC() asm volatile("bar.sync 6, 256;" ::: "memory")
+__device__ __forceinline__ bool ht_math_sync_and(bool v) {
+    unsigned r;
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, 7, 256, q;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"((unsigned)v) : "memory");
+    return r != 0;
+}
+__device__ __forceinline__ void ht_ring_advance(RingState &r) {
+    if (++r.stage == HT_NST) { r.stage = 0; r.phase ^= 1u; }
+}
+
+// 16 x 32 warp tile of the 64 x 64 CTA tile: rows 16*wr + 8*mt + g, columns 32*wc + 8*nt + 2t + e.
+typedef double Acc32[2][4][2];
+
+// One ring stage (K depth 32): acc += A[rows of this warp] * B[columns of this warp]^T  (sign handled by the caller:
+// the accumulator starts at -C).  ntm = n tiles in use (diagonal tasks skip the blocks above the diagonal).
+template <int MT, bool FULL>
+__device__ __forceinline__ void ht_stage_mma(Acc32 &acc, const double *As, const double *Bs, int wr, int wc, int ntm, int g, int t) {
+    const double *ap = As + (wr * 16 + g) * GSUM_LDH + t;
+    const double *bp = Bs + (wc * 32 + g) * GSUM_LDH + t;
+#pragma unroll
+    for (int ks = 0; ks < GSUM_KH / 4; ks++) {
+        double a[MT], b[4];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) a[mt] = ap[mt * 8 * GSUM_LDH + ks * 4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) if (FULL || nt < ntm) b[nt] = bp[nt * 8 * GSUM_LDH + ks * 4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+            if (FULL || nt < ntm) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+            }
+    }
+}
+
+// X = S * L_kk^{-T} for this warp's 8 x 64 row block held as C fragments  T[nt][e] <-> row g, column 8 nt + 2t + e.
+// Ms: M_kk in shared memory (row stride GSUM_LDS).  Right-looking over 8-column blocks:
+//   X_cb = S_cb * Dinv_cb^T  (two DMMAs),   S_j -= X_cb * L[j, cb]^T  for the later blocks j (two DMMAs each, independent).
+// The C -> A fragment re-layouts are quad shuffles.
+__device__ __forceinline__ void ht_trsm_dinv(double (&T)[8][2], const double *Ms, int g, int t) {
+    const unsigned FULLMASK = 0xffffffffu;
+#pragma unroll
+    for (int cb = 0; cb < 8; cb++) {
+        const int c0 = cb * 8;
+        const double b0 = Ms[(c0 + g) * GSUM_LDS + c0 + t], b1 = Ms[(c0 + g) * GSUM_LDS + c0 + 4 + t];
+        double a0, a1;
+        {
+            const double p0 = __shfl_sync(FULLMASK, T[cb][0], t >> 1, 4), p1 = __shfl_sync(FULLMASK, T[cb][1], t >> 1, 4);
+            const double q0 = __shfl_sync(FULLMASK, T[cb][0], 2 + (t >> 1), 4), q1 = __shfl_sync(FULLMASK, T[cb][1], 2 + (t >> 1), 4);
+            a0 = (t & 1) ? p1 : p0;
+            a1 = (t & 1) ? q1 : q0;
+        }
+        double x0 = 0.0, x1 = 0.0;
+        dmma884(x0, x1, a0, b0);
+        dmma884(x0, x1, a1, b1);
+        T[cb][0] = x0; T[cb][1] = x1;
+        if (cb == 7) break;
+        {
+            const double p0 = __shfl_sync(FULLMASK, x0, t >> 1, 4), p1 = __shfl_sync(FULLMASK, x1, t >> 1, 4);
+            const double q0 = __shfl_sync(FULLMASK, x0, 2 + (t >> 1), 4), q1 = __shfl_sync(FULLMASK, x1, 2 + (t >> 1), 4);
+            a0 = -((t & 1) ? p1 : p0);
+            a1 = -((t & 1) ? q1 : q0);
+        }
+#pragma unroll
+        for (int j = cb + 1; j < 8; j++) {
+            const double l0 = Ms[(j * 8 + g) * GSUM_LDS + c0 + t], l1 = Ms[(j * 8 + g) * GSUM_LDS + c0 + 4 + t];
+            dmma884(T[j][0], T[j][1], a0, l0);
+            dmma884(T[j][0], T[j][1], a1, l1);
+        }
+    }
+}
+
+// In-place inversion of the eight 8x8 diagonal blocks of the factored tile S (smem, stride GSUM_LDS), by one 128-thread
+// group: thread (cb, j) solves  L_blk x = e_j  by substitution; zeros above the diagonal.  Group barrier: CONS_SYNC.
+__device__ __forceinline__ void ht_invert_diag_blocks(double *S) {
+    const int tid = EPI_TID;
+    double x[8];
+    const int cb = (tid >> 3) & 7, j = tid & 7;
+    double *blk = S + (cb * 8) * GSUM_LDS + cb * 8;
+    if (tid < 64) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) {
+            double s = (m == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int n = 0; n < m; n++) s = fma(-blk[m * GSUM_LDS + n], x[n], s);
+            x[m] = (m >= j) ? s / blk[m * GSUM_LDS + m] : 0.0;
+        }
+    }
+    CONS_SYNC();
+    if (tid < 64) {
+#pragma unroll
+        for (int m = 0; m < 8; m++) blk[m * GSUM_LDS + j] = x[m];
+    }
+    CONS_SYNC();
+}
+// M tile (dense 64 x 64, ld 64) from the smem tile whose diagonal blocks already hold the inverses
+__device__ __forceinline__ void ht_write_mkk(const double *S, double *Mt, bool fail) {
+    const int tid = EPI_TID;
+    for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
+        const int r = e >> 5, c = (e & 31) * 2;
+        double2 v;
+        const bool below = (c >> 3) <= (r >> 3);            // c and c + 1 share an 8-block
+        v.x = below ? S[r * GSUM_LDS + c] : 0.0;
+        v.y = below ? S[r * GSUM_LDS + c + 1] : 0.0;
+        if (fail) { v.x = v.y = nan(""); }
+        *reinterpret_cast<double2 *>(Mt + r * GSUM_TILE + c) = v;
+    }
+}
+
+// ---- factor worker: one 128-thread group of a factor CTA ------------------------------------------------------------
+__device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S, long long *st) {
+    const BorderedBatch &P = D.P;
+    const int tid = EPI_TID;
+    double *dg = S + GSUM_TILE * GSUM_LDS;
+    int *s_fail = reinterpret_cast<int *>(dg + 2 * GSUM_TILE);
+    int *s_tk = s_fail + 2;
+    for (;;) {
+        if (tid == 0) s_tk[0] = atomicAdd(D.ctl + 3, 1);
+        CONS_SYNC();
+        const int tix = s_tk[0];
+        if (tix >= D.nftasks) break;
+        const int4 tk = D.ftasks[tix];
+        const int k = tk.x, b = tk.y;
+        double *C = P.A + (int64_t)b * P.bstride + (int64_t)k * GSUM_TILE * P.ld + k * GSUM_TILE;
+        int *flag = D.flags + ((int64_t)b * P.Trows + k) * P.T + k;
+        int ok = 1;
+        const long long t0 = st ? clock64() : 0;
+        if (k > 0 && tid == 0) ok = flag_wait_ge(flag, 1, D.ctl + 1) ? 1 : 0;
+        if (!cons_sync_and(ok != 0)) break;
+        const long long t1 = st ? clock64() : 0;
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int c = tid + q * CHOL_THREADS, row = c >> 5, ch = (c & 31) * 2;
+            cp_async16(S + row * GSUM_LDS + ch, C + (int64_t)row * P.ld + ch);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        if (tid == 0) *s_fail = 0;
+        CONS_SYNC();
+        tile_potrf_blocked_inl(S, dg, s_fail);
+        const int fail = *s_fail;
+        if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
+        // L_kk: lower triangle, exact zeros above the diagonal (numpy.linalg.cholesky convention)
+        for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            double2 v;
+            v.x = (c <= r) ? S[r * GSUM_LDS + c] : 0.0;
+            v.y = (c + 1 <= r) ? S[r * GSUM_LDS + c + 1] : 0.0;
+            if (fail) { v.x = v.y = nan(""); }
+            *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
+        }
+        if (P.logdet_part && tid < 32) {
+            // 2 * sum log(L_jj), same form as gsum/models.py:1015,1250; padding columns (>= n) contribute log 1 = 0
+            double v = 0.0;
+            for (int j = tid; j < GSUM_TILE; j += 32)
+                if (k * GSUM_TILE + j < P.n) v += log(dg[j]);
+            v = warp_sum(v);
+            if (tid == 0) P.logdet_part[(int64_t)b * P.T + k] = fail ? nan("") : 2.0 * v;
+        }
+        CONS_SYNC();
+        ht_invert_diag_blocks(S);
+        ht_write_mkk(S, D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), fail != 0);
+        __threadfence();
+        CONS_SYNC();
+        if (tid == 0) st_release(flag, 2);
+        if (st && tid == 0) { st[0] += t1 - t0; st[1] += clock64() - t1; st[2] += 1; }
+    }
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t full_bar[HT_NST], empty_bar[HT_NST], tq_full[HT_QD], tq_empty[HT_QD];
+    __shared__ int4 tq[HT_QD];
+    const BorderedBatch &P = D.P;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const bool st_on = STATS && D.stats != nullptr;
+    long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long st_t0 = STATS ? clock64() : 0;
+#define HT_T0() const long long _t = st_on ? clock64() : 0
+#define HT_ACC(q) do { if (st_on) st[q] += clock64() - _t; } while (0)
+
+    if ((int)blockIdx.x < D.nfactor_ctas) {
+        // ============================ factor CTA ================================================================
+        ht_factor_worker(D, smem + (tid >> 7) * HT_WORKER_DOUBLES, st_on ? st : nullptr);
+        if (st_on && (tid & 127) == 0) {
+            long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + (tid >> 7) * 4;
+            o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2];
+        }
+        return;
+    }
+
+    double *ring_base = smem;
+    double *Sbuf = smem + HT_NST * HT_STAGE_DOUBLES;
+    if (tid == 0) {
+        for (int s = 0; s < HT_NST; s++) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], HT_MATH_WARPS); }
+        for (int s = 0; s < HT_QD; s++) { mbar_init(&tq_full[s], 1); mbar_init(&tq_empty[s], HT_MATH_WARPS + 3); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int *abort_flag = D.ctl + 1;
+
+    if (w >= HT_PRODUCER_WARP) {
+        // ============================ producer warps =========================================================
+        const int pw = w - HT_PRODUCER_WARP;
+        RingState ring = {0, 0u};
+        for (int n = 0;; n++) {
+            const int slot = n % HT_QD;
+            int4 tk = make_int4(-1, 0, 0, 0);
+            int ok = 1;
+            if (pw == 0) {
+                if (lane == 0) {
+                    { HT_T0(); ok = mbar_wait(&tq_empty[slot], (((unsigned)(n / HT_QD)) & 1u) ^ 1u, abort_flag); HT_ACC(0); }
+                    if (ok) {
+                        const int tix = atomicAdd(D.ctl, 1);
+                        if (tix < D.ngtasks) tk = D.gtasks[tix];
+                        tq[slot] = tk;
+                        mbar_arrive(&tq_full[slot]);
+                    }
+                }
+                ok = __shfl_sync(0xffffffffu, ok, 0);
+                tk.x = __shfl_sync(0xffffffffu, tk.x, 0); tk.y = __shfl_sync(0xffffffffu, tk.y, 0);
+                tk.z = __shfl_sync(0xffffffffu, tk.z, 0); tk.w = __shfl_sync(0xffffffffu, tk.w, 0);
+            } else {
+                ok = mbar_wait(&tq_full[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag);
+                if (ok) {
+                    tk = tq[slot];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tq_empty[slot]);
+                }
+            }
+            if (!ok || tk.x < 0) break;
+            const int i = tk.x, k = tk.y, b = tk.z;
+            const bool diag = (i == k), thin = (tk.w & 1) != 0;
+            const double *Ab = P.A + (int64_t)b * P.bstride;
+            const double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
+                                         : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
+            const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
+            const int *frow_i = D.flags + ((int64_t)b * P.Trows + i) * P.T;
+            const int *frow_k = D.flags + ((int64_t)b * P.Trows + k) * P.T;
+            bool alive = true;
+            // ---- stage 0 of the task: the C tile (original data, written before the launch) ----------------------
+            {
+                int good = 1;
+                if (lane == 0) { HT_T0(); good = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
+                alive = __shfl_sync(0xffffffffu, good, 0) != 0;
+                if (!alive) break;
+                double *Cs = ring_base + ring.stage * HT_STAGE_DOUBLES;
+                const double *C = Ri + k * GSUM_TILE;
+                if (!thin) {
+#pragma unroll
+                    for (int q = 0; q < 16; q++) {
+                        const int row = pw * 16 + q, ch = lane * 2;
+                        cp_async16(Cs + row * GSUM_LDS + ch, C + (int64_t)row * P.ld + ch);
+                    }
+                } else if (pw == 0) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cp_async16(Cs + q * GSUM_LDS + lane * 2, C + (int64_t)q * P.ld + lane * 2);
+                }
+                cp_async_mbar_arrive(&full_bar[ring.stage]);
+                ht_ring_advance(ring);
+            }
+            // ---- operand half-slabs ----------------------------------------------------------------------------
+            const int r0 = pw * 16 + (lane >> 4), ch = (lane & 15) * 2;
+            // A finished tile (r, k-1) implies every (r, j < k-1): they were its operands.
+            int done_i = 1, done_k = 1;
+            if (lane == 0 && k > 0) {
+                done_i = ld_relaxed(frow_i + k - 1) >= 1;
+                done_k = diag ? done_i : (ld_relaxed(frow_k + k - 1) >= 1);
+            }
+            for (int h = 0; h < 2 * k && alive; h++) {
+                const int j = h >> 1;
+                int good = 1;
+                if (lane == 0) {
+                    if ((h & 1) == 0 && !(done_i && done_k)) {
+                        HT_T0();
+                        good = (done_i || flag_wait(frow_i + j, abort_flag)) && (diag || done_k || flag_wait(frow_k + j, abort_flag));
+                        HT_ACC(1);
+                    }
+                    if (good) { HT_T0(); good = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
+                }
+                alive = __shfl_sync(0xffffffffu, good, 0) != 0;
+                if (!alive) break;
+                double *As = ring_base + ring.stage * HT_STAGE_DOUBLES, *Bs = As + GSUM_TILE * GSUM_LDH;
+                const int col0 = j * GSUM_TILE + (h & 1) * GSUM_KH;
+                if (!thin) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int row = r0 + 2 * q;
+                        cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
+                    }
+                } else if (pw == 0) {                      // thin task: rows 0..7 of the A operand only
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int row = (lane >> 4) + 2 * q;
+                        cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
+                    }
+                }
+                if (!diag) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        const int row = r0 + 2 * q;
+                        cp_async16(Bs + row * GSUM_LDH + ch, Ak + (int64_t)row * P.ld + col0 + ch);
+                    }
+                }
+                cp_async_mbar_arrive(&full_bar[ring.stage]);
+                ht_ring_advance(ring);
+            }
+            if (!alive) break;
+            // ---- last stage of a panel task: M_kk -----------------------------------------------------------------
+            if (!diag) {
+                int good = 1;
+                if (lane == 0) {
+                    { HT_T0(); good = flag_wait_ge(frow_k + k, 2, abort_flag) ? 1 : 0; HT_ACC(3); }
+                    if (good) { HT_T0(); good = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
+                }
+                alive = __shfl_sync(0xffffffffu, good, 0) != 0;
+                if (!alive) break;
+                double *Ms = ring_base + ring.stage * HT_STAGE_DOUBLES;
+                const double *Mg = D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE);
+#pragma unroll
+                for (int q = 0; q < 16; q++) {
+                    const int row = pw * 16 + q;
+                    cp_async16(Ms + row * GSUM_LDS + lane * 2, Mg + row * GSUM_TILE + lane * 2);
+                }
+                cp_async_mbar_arrive(&full_bar[ring.stage]);
+                ht_ring_advance(ring);
+            }
+        }
+        cp_async_wait<0>();
+        if (st_on && pw == 0 && lane == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT; o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; }
+    } else {
+        // ============================ math warps ============================================================
+        const int g = lane >> 2, t = lane & 3, wr = w & 3, wc = w >> 2;
+        RingState ring = {0, 0u};
+        for (int n = 0;; n++) {
+            const int slot = n % HT_QD;
+            bool alive;
+            { HT_T0(); alive = mbar_wait(&tq_full[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag); HT_ACC(0); }
+            int4 tk = make_int4(-1, 0, 0, 0);
+            if (alive) {
+                tk = tq[slot];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tq_empty[slot]);
+            }
+            // the math warps leave together: a warp that gave up on the queue (abort) must not strand the others at a barrier
+            alive = ht_math_sync_and(alive);
+            if (!alive || tk.x < 0) break;
+            const int i = tk.x, k = tk.y, b = tk.z;
+            const bool diag = (i == k), thin = (tk.w & 1) != 0;
+            double *Ab = P.A + (int64_t)b * P.bstride;
+            double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
+                                   : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
+            double *C = Ri + k * GSUM_TILE;
+            // diagonal task: blocks above the diagonal are skipped (row blocks 2wr, 2wr+1; column blocks 4wc + nt)
+            int ntm = 4;
+            if (diag) { ntm = 2 * wr + 2 - 4 * wc; ntm = ntm < 0 ? 0 : (ntm > 4 ? 4 : ntm); }
+            const bool active = !thin || wr == 0;          // thin task: only rows 0..7 are in use
+            // ---- acc = -C ------------------------------------------------------------------------------------------
+            Acc32 acc;
+            {
+                { HT_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
+                const double *Cs = ring_base + ring.stage * HT_STAGE_DOUBLES;
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+                        if (nt < ntm && active && (!thin || mt == 0)) {
+                            const double2 v = *reinterpret_cast<const double2 *>(Cs + (wr * 16 + mt * 8 + g) * GSUM_LDS + wc * 32 + nt * 8 + 2 * t);
+                            acc[mt][nt][0] = -v.x; acc[mt][nt][1] = -v.y;
+                        } else { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+                    }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
+                ht_ring_advance(ring);
+            }
+            // ---- main loop ---------------------------------------------------------------------------------------
+            for (int h = 0; h < 2 * k; h++) {
+                { HT_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
+                const double *As = ring_base + ring.stage * HT_STAGE_DOUBLES;
+                const double *Bs = diag ? As : As + GSUM_TILE * GSUM_LDH;
+                if (thin) { if (active) ht_stage_mma<1, true>(acc, As, Bs, wr, wc, 4, g, t); }
+                else if (diag) ht_stage_mma<2, false>(acc, As, Bs, wr, wc, ntm, g, t);
+                else ht_stage_mma<2, true>(acc, As, Bs, wr, wc, 4, g, t);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
+                ht_ring_advance(ring);
+            }
+            if (diag) {
+                // ---- S = -(acc) back in place; the factor CTAs take it from there --------------------------------
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+                        if (nt < ntm) {
+                            double2 v; v.x = -acc[mt][nt][0]; v.y = -acc[mt][nt][1];
+                            *reinterpret_cast<double2 *>(C + (int64_t)(wr * 16 + mt * 8 + g) * P.ld + wc * 32 + nt * 8 + 2 * t) = v;
+                        }
+            } else {
+                // ---- 16x32 warp tiles -> 8x64 row blocks through shared memory, then the triangular solve --------
+                if (active) {
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++) {
+                            double2 v; v.x = -acc[mt][nt][0]; v.y = -acc[mt][nt][1];
+                            *reinterpret_cast<double2 *>(Sbuf + (wr * 16 + mt * 8 + g) * GSUM_LDS + wc * 32 + nt * 8 + 2 * t) = v;
+                        }
+                }
+                HT_MATH_SYNC();
+                double T[8][2];
+                const bool solver = !thin || w == 0;
+                if (solver) {
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        const double2 v = *reinterpret_cast<const double2 *>(Sbuf + (w * 8 + g) * GSUM_LDS + nt * 8 + 2 * t);
+                        T[nt][0] = v.x; T[nt][1] = v.y;
+                    }
+                }
+                { HT_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(2); }
+                if (solver) {
+                    HT_T0();
+                    ht_trsm_dinv(T, ring_base + ring.stage * HT_STAGE_DOUBLES, g, t);
+                    HT_ACC(3);
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        double2 v; v.x = T[nt][0]; v.y = T[nt][1];
+                        *reinterpret_cast<double2 *>(C + (int64_t)(w * 8 + g) * P.ld + nt * 8 + 2 * t) = v;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
+                ht_ring_advance(ring);
+            }
+            { HT_T0();
+            __threadfence();                              // tile stores visible device-wide before the flag
+            alive = ht_math_sync_and(alive);
+            if (alive && tid == 0) st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
+            HT_ACC(4); }
+            if (!alive) break;
+            st[5] += 1;
+        }
+        if (st_on && tid == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT; o[5] = clock64() - st_t0; o[6] = st[0]; o[7] = st[1]; o[8] = st[2]; o[9] = st[3]; o[10] = st[4]; o[11] = st[5]; }
+    }
+#undef HT_T0
+#undef HT_ACC
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------------
+// flags for a fresh factorisation: all zero.  With an existing factor (solve_only): tiles i < T are final (1), diagonal
+// tiles carry 2 (L_kk and M_kk final).
+__global__ void ht_init_kernel(int *flags, int *ctl, int64_t batch, int Trows, int T, int factor_done) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 2) ctl[idx] = 0;
+    if (idx == 3) ctl[3] = 0;
+    if (idx >= batch * Trows * T) return;
+    const int k = (int)(idx % T), i = (int)((idx / T) % Trows);
+    flags[idx] = (factor_done && i < T) ? (i == k ? 2 : 1) : 0;
+}
+// M_kk tiles from an existing factor (solve_only calls): one 128-thread CTA per diagonal tile
+__global__ void __launch_bounds__(CHOL_THREADS) ht_mkk_from_factor_kernel(BorderedBatch P, double *M) {
+    __shared__ __align__(16) double S[GSUM_TILE * GSUM_LDS];
+    const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const double *C = P.A + (int64_t)b * P.bstride + (int64_t)k * GSUM_TILE * P.ld + k * GSUM_TILE;
+    for (int e = tid; e < GSUM_TILE * GSUM_TILE; e += CHOL_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        S[r * GSUM_LDS + c] = C[(int64_t)r * P.ld + c];
+    }
+    __syncthreads();
+    ht_invert_diag_blocks(S);
+    ht_write_mkk(S, M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), false);
+}
+
+// Split the joint topological order into the two claim lists.
+static inline void ht_build_tasks(std::vector<int4> &gemm, std::vector<int4> &fact, int T, int Trows, int batch, bool solve_only,
+                                  bool thin_last, int diag_delay) {
+    std::vector<int4> all;
+    df_build_tasks(all, T, Trows, batch, solve_only, thin_last, diag_delay);
+    gemm.clear(); fact.clear();
+    for (const int4 &tk : all) {
+        if (tk.x == tk.y) {
+            if (tk.y > 0) gemm.push_back(tk);                    // SYRK half (column 0 needs none: S = C)
+            fact.push_back(make_int4(tk.y, tk.z, 0, 0));
+        } else gemm.push_back(tk);
+    }
+}
