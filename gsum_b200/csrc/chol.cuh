@@ -21,7 +21,11 @@
 #define CHOL_THREADS 128
 // Barrier over one 128-thread group: the math threads (0..127) of the multi-launch / dataflow kernels use id 1, the
 // epilogue groups of the pipeline kernel (threads 128.., 256..) ids 2, 3.  EPI_TID: thread index within the group.
-#define CONS_SYNC() asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory")
+// bar.sync is the ALIGNED barrier: every lane of a warp has to execute it together.  The callers reach it from code with
+// lane-divergent work (a single writer lane, a partial warp of solvers); nothing obliges the compiler to reconverge a
+// warp in front of an inline-asm barrier, and a warp that arrives with lanes missing releases the barrier early (seen
+// as sporadic non-positive pivots in late 8-column blocks).  __syncwarp() makes the convergence explicit.
+#define CONS_SYNC() do { __syncwarp(); asm volatile("bar.sync %0, 128;" ::"r"(1 + (int)(threadIdx.x >> 7)) : "memory"); } while (0)
 #define EPI_TID ((int)(threadIdx.x & 127))
 #ifndef CHOL_NST
 #define CHOL_NST 3
@@ -184,6 +188,7 @@ __device__ __forceinline__ void tile_store_acc(const Acc &acc, double *C, int64_
 __device__ __forceinline__ void tile_potrf_blocked_inl(double *S, double *dg, int *s_fail) {
     const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
+    double *wb = dg + GSUM_TILE;                        // 8x8 scratch for the factored diagonal block (behind diag(L))
 #pragma unroll 1
     for (int cb = 0; cb < 8; cb++) {
         const int c0 = cb * 8;
@@ -217,11 +222,11 @@ __device__ __forceinline__ void tile_potrf_blocked_inl(double *S, double *dg, in
                 if (!(d > 0.0) && fail == 0) fail = c0 + j + 1;
                 const double rs = rsqrt(d);
                 x[j] *= rs;
-                if (writer) { S[(c0 + j) * GSUM_LDS + c0 + j] = d * rs; dg[c0 + j] = d * rs; }
+                if (writer) { wb[j * 8 + j] = d * rs; dg[c0 + j] = d * rs; }
 #pragma unroll
                 for (int m = j + 1; m < 8; m++) {
                     a[m][j] *= rs;
-                    if (writer) S[(c0 + m) * GSUM_LDS + c0 + j] = a[m][j];
+                    if (writer) wb[m * 8 + j] = a[m][j];
                     x[m] = fma(-x[j], a[m][j], x[m]);
                 }
 #pragma unroll
@@ -238,8 +243,12 @@ __device__ __forceinline__ void tile_potrf_blocked_inl(double *S, double *dg, in
             }
             if (writer && fail && *s_fail == 0) *s_fail = fail;
         }
-        if (cb == 7) break;
         CONS_SYNC();
+        // The factored block goes back only now: the solvers read the unfactored block at the start of the step, and a
+        // writer that stored straight into it could overtake a solver warp that is still loading (seen with three POTRFs
+        // sharing an SM: sporadic garbage rows -> non-positive pivots in later blocks).
+        if (tid < 64 && (tid & 7) <= (tid >> 3)) S[(c0 + (tid >> 3)) * GSUM_LDS + c0 + (tid & 7)] = wb[tid];
+        if (cb == 7) break;
         {   // trailing update of the 8x8 blocks (rb, cb2), cb < cb2 <= rb <= 7; warp w takes blocks w, w+4, ... (4 in flight)
             const int nt = 7 - cb, nblk = nt * (nt + 1) / 2;
 #pragma unroll 1

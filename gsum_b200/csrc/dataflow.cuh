@@ -106,6 +106,7 @@ __device__ __forceinline__ bool flag_wait(const int *flag, int *abort_flag) {
 // AND-reduction + barrier over one 128-thread group (named barrier 8 + group index)
 __device__ __forceinline__ bool cons_sync_and(bool v) {
     unsigned r;
+    __syncwarp();                       // aligned barrier: the warp arrives converged (see CONS_SYNC)
     asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, %2, 128, q;\n selp.u32 %0, 1, 0, p;\n}"
                  : "=r"(r) : "r"((unsigned)v), "r"(8 + (int)(threadIdx.x >> 7)) : "memory");
     return r != 0;

@@ -44,7 +44,7 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     // per tile column) are kept for comparison and as cross-checks of one another
     c->use_pipeline = (sched && (strcmp(sched, "dataflow") == 0 || strcmp(sched, "multilaunch") == 0)) ? 0 : 1;
     // default schedule: heterogeneous (hetero.cuh); "pipeline" / "dataflow" / "multilaunch" select the older ones
-    c->use_hetero = (sched && strcmp(sched, "hetero") == 0) ? 1 : 0;
+    c->use_hetero = (!sched || strcmp(sched, "hetero") == 0) ? 1 : 0;
     const char *fc = getenv("GSUM_B200_FACTOR_CTAS");
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
     const char *thin = getenv("GSUM_B200_THIN");
@@ -307,9 +307,13 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     D.ctl = c->df_ctl; D.flags = (int *)c->df_flags; D.M = (double *)dM; D.stats = nullptr;
     // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
     int nf = 0;
+    int nwk = getenv("GSUM_B200_FACTOR_WORKERS") ? atoi(getenv("GSUM_B200_FACTOR_WORKERS")) : 3;
+    if (nwk < 1) nwk = 1;
+    if (nwk > 3) nwk = 3;
+    D.nworkers = nwk;
     if (c->ht_nf > 0) {
         nf = c->ht_factor_ctas;
-        const int cap = (c->ht_nf + 2) / 3;
+        const int cap = (c->ht_nf + nwk - 1) / nwk;
         if (nf > cap) nf = cap;
         if (nf > c->sm_count / 2) nf = c->sm_count / 2;
         if (nf < 1) nf = 1;
@@ -335,13 +339,13 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         std::vector<long long> h(HT_NSTAT * grid);
         cudaStreamSynchronize(c->stream);
         cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * HT_NSTAT * grid, cudaMemcpyDeviceToHost);
-        double f[4] = {0, 0, 0, 0}, a[HT_NSTAT] = {0};
-        for (int g = 0; g < nf; g++) for (int wk = 0; wk < 3; wk++) for (int q = 0; q < 4; q++) f[q] += (double)h[HT_NSTAT * g + wk * 4 + q];
-        for (int g = nf; g < grid; g++) for (int q = 0; q < HT_NSTAT; q++) a[q] += (double)h[HT_NSTAT * g + q];
-        if (nf) fprintf(stderr, "[ht] factor CTAs %d: cycles/worker %.0f | wait_S %.1f%% | busy %.1f%% (%.0f cycles per diagonal tile, %.1f tiles per worker)\n",
-                        nf, f[0] / (3 * nf), 100 * f[1] / f[0], 100 * f[2] / f[0], f[2] / (f[3] + 1e-9), f[3] / (3 * nf));
-        if (ng) fprintf(stderr, "[ht] GEMM CTAs %d: cycles/CTA %.0f, tasks/CTA %.1f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% wait_Mkk %.1f%% | math: wait_queue %.1f%% wait_operands %.1f%% wait_Mkk %.1f%% trsm %.1f%% fence+flag %.1f%%\n",
-                        ng, a[5] / ng, a[11] / ng, 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0],
+        double f[6] = {0, 0, 0, 0, 0, 0}, a[HT_NSTAT] = {0};
+        for (int g = 0; g < nf; g++) for (int wk = 0; wk < nwk; wk++) for (int q = 0; q < 6; q++) f[q] += (double)h[HT_NSTAT * g + wk * 6 + q];
+        for (int g = nf; g < grid; g++) for (int grp = 0; grp < 2; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
+        if (nf) fprintf(stderr, "[ht] factor CTAs %d: cycles/worker %.0f | wait_S %.1f%% | busy %.1f%% (%.0f cycles per diagonal tile: load %.0f, potrf %.0f; %.1f tiles per worker)\n",
+                        nf, f[0] / (nwk * nf), 100 * f[1] / f[0], 100 * f[2] / f[0], f[2] / (f[3] + 1e-9), f[4] / (f[3] + 1e-9), f[5] / (f[3] + 1e-9), f[3] / (nwk * nf));
+        if (ng) fprintf(stderr, "[ht] GEMM CTAs %d (2 groups each): cycles/group %.0f, tasks/group %.1f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% wait_Mkk %.1f%% | math: wait_queue %.1f%% wait_operands %.1f%% wait_Mkk %.1f%% trsm %.1f%% fence+flag %.1f%%\n",
+                        ng, a[5] / (2 * ng), a[11] / (2 * ng), 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0],
                         100 * a[6] / a[5], 100 * a[7] / a[5], 100 * a[8] / a[5], 100 * a[9] / a[5], 100 * a[10] / a[5]);
     }
     return 0;

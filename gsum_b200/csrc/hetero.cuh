@@ -26,24 +26,30 @@
 #pragma once
 #include "dataflow.cuh"
 
-#define HT_THREADS 384                  // GEMM CTA: 8 math warps | 4 producer warps;  factor CTA: 3 workers x 128 threads
-#define HT_MATH_WARPS 8
-#define HT_PRODUCER_WARP 8
+#ifndef HT_PW
+#define HT_PW 2                         // producer warps per group
+#endif
+#define HT_THREADS (256 + 64 * HT_PW)   // GEMM CTA: 2 groups x (4 math warps + HT_PW producer warps);  factor CTA: 3 workers x 128 threads
 #ifndef HT_NST
-#define HT_NST 4                        // ring stages (36 KiB each: an operand half-slab pair, or one whole 64x64 tile)
+#define HT_NST 3                        // ring stages per group (36 KiB each: an operand half-slab pair, or one whole 64x64 tile)
 #endif
 #define HT_QD 4                         // task queue depth
 #define HT_STAGE_DOUBLES CHOL_STAGE_DOUBLES
-#define HT_SBUF_DOUBLES (GSUM_TILE * GSUM_LDS)
-#define HT_SMEM_DOUBLES (HT_NST * HT_STAGE_DOUBLES + HT_SBUF_DOUBLES)
+#define HT_SMEM_DOUBLES (2 * HT_NST * HT_STAGE_DOUBLES)
 #define HT_SMEM_BYTES (HT_SMEM_DOUBLES * 8)
 #define HT_WORKER_DOUBLES (GSUM_TILE * GSUM_LDS + 3 * GSUM_TILE)     // factor worker: tile + diag + scratch ints
-#define HT_NSTAT 16
+#define HT_NSTAT 24
+#ifndef HT_FENCE_GEMM
+#define HT_FENCE_GEMM 0
+#endif
+#ifndef HT_FENCE_FACTOR
+#define HT_FENCE_FACTOR 0
+#endif
 #ifndef HT_FACTOR_CTAS
 #define HT_FACTOR_CTAS 16               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
 #endif
 #ifndef HT_DIAG_DELAY
-#define HT_DIAG_DELAY 1184
+#define HT_DIAG_DELAY 0
 #endif
 
 struct HeteroArgs {
@@ -56,6 +62,7 @@ struct HeteroArgs {
     int *flags;             // per (b, i, k): index (b * Trows + i) * T + k.  i > k: 1 = tile final.  i == k: 1 = S ready, 2 = L_kk and M_kk final
     double *M;              // (batch, T, 64, 64): L_kk with its 8x8 diagonal blocks inverted
     int nfactor_ctas;       // CTAs [0, nfactor_ctas) are factor CTAs
+    int nworkers;           // 128-thread workers per factor CTA (1..3)
     long long *stats;       // optional per-CTA cycle counters [grid][HT_NSTAT]
 };
 
@@ -69,36 +76,33 @@ __device__ __forceinline__ bool flag_wait_ge(const int *flag, int want, int *abo
     }
     return true;
 }
-// barriers over the 256 math threads of a GEMM CTA
-#define HT_MATH_SYNC() asm volatile("bar.sync 6, 256;" ::: "memory")
-__device__ __forceinline__ bool ht_math_sync_and(bool v) {
+// AND-reduction + barrier over the 128 math threads of group q of a GEMM CTA (named barrier 6 + q)
+__device__ __forceinline__ bool ht_group_sync_and(bool v, int q) {
     unsigned r;
-    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, 7, 256, q;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(r) : "r"((unsigned)v) : "memory");
+    __syncwarp();                       // aligned barrier: the warp arrives converged (see CONS_SYNC)
+    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, %2, 128, q;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(r) : "r"((unsigned)v), "r"(6 + q) : "memory");
     return r != 0;
 }
 __device__ __forceinline__ void ht_ring_advance(RingState &r) {
     if (++r.stage == HT_NST) { r.stage = 0; r.phase ^= 1u; }
 }
 
-// 16 x 32 warp tile of the 64 x 64 CTA tile: rows 16*wr + 8*mt + g, columns 32*wc + 8*nt + 2t + e.
-typedef double Acc32[2][4][2];
-
-// One ring stage (K depth 32): acc += A[rows of this warp] * B[columns of this warp]^T  (sign handled by the caller:
-// the accumulator starts at -C).  ntm = n tiles in use (diagonal tasks skip the blocks above the diagonal).
+// One ring stage (K depth 32) on a 16 x 64 warp tile (chol.cuh Acc): acc += A[rows 16 wg ..] * B[8 ntm rows]^T.  The sign
+// is the caller's business (the accumulator starts at -C), so the loop is loads and DMMAs only.
 template <int MT, bool FULL>
-__device__ __forceinline__ void ht_stage_mma(Acc32 &acc, const double *As, const double *Bs, int wr, int wc, int ntm, int g, int t) {
-    const double *ap = As + (wr * 16 + g) * GSUM_LDH + t;
-    const double *bp = Bs + (wc * 32 + g) * GSUM_LDH + t;
+__device__ __forceinline__ void ht_stage_mma(Acc &acc, const double *As, const double *Bs, int wg, int ntm, int g, int t) {
+    const double *ap = As + (wg * 16 + g) * GSUM_LDH + t;
+    const double *bp = Bs + g * GSUM_LDH + t;
 #pragma unroll
     for (int ks = 0; ks < GSUM_KH / 4; ks++) {
-        double a[MT], b[4];
+        double a[MT], b[8];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) a[mt] = ap[mt * 8 * GSUM_LDH + ks * 4];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++) if (FULL || nt < ntm) b[nt] = bp[nt * 8 * GSUM_LDH + ks * 4];
+        for (int nt = 0; nt < 8; nt++) if (FULL || nt < ntm) b[nt] = bp[nt * 8 * GSUM_LDH + ks * 4];
 #pragma unroll
-        for (int nt = 0; nt < 4; nt++)
+        for (int nt = 0; nt < 8; nt++)
             if (FULL || nt < ntm) {
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
@@ -106,77 +110,84 @@ __device__ __forceinline__ void ht_stage_mma(Acc32 &acc, const double *As, const
     }
 }
 
-// X = S * L_kk^{-T} for this warp's 8 x 64 row block held as C fragments  T[nt][e] <-> row g, column 8 nt + 2t + e.
-// Ms: M_kk in shared memory (row stride GSUM_LDS).  Right-looking over 8-column blocks:
+// X = S * L_kk^{-T} on this warp's MT row blocks of 8 x 64, held as C fragments  T[mt][nt][e] <-> row 8 mt + g, column
+// 8 nt + 2t + e.  Ms: M_kk in shared memory (row stride GSUM_LDS).  Right-looking over 8-column blocks:
 //   X_cb = S_cb * Dinv_cb^T  (two DMMAs),   S_j -= X_cb * L[j, cb]^T  for the later blocks j (two DMMAs each, independent).
-// The C -> A fragment re-layouts are quad shuffles.
-__device__ __forceinline__ void ht_trsm_dinv(double (&T)[8][2], const double *Ms, int g, int t) {
+// The C -> A fragment re-layouts are quad shuffles; the MT row blocks are independent chains that interleave.
+template <int MT>
+__device__ __forceinline__ void ht_trsm_dinv(Acc &T, const double *Ms, int g, int t) {
     const unsigned FULLMASK = 0xffffffffu;
+    const int s0 = t >> 1, s1 = 2 + (t >> 1);
+    const bool odd = (t & 1) != 0;
 #pragma unroll
     for (int cb = 0; cb < 8; cb++) {
         const int c0 = cb * 8;
         const double b0 = Ms[(c0 + g) * GSUM_LDS + c0 + t], b1 = Ms[(c0 + g) * GSUM_LDS + c0 + 4 + t];
-        double a0, a1;
-        {
-            const double p0 = __shfl_sync(FULLMASK, T[cb][0], t >> 1, 4), p1 = __shfl_sync(FULLMASK, T[cb][1], t >> 1, 4);
-            const double q0 = __shfl_sync(FULLMASK, T[cb][0], 2 + (t >> 1), 4), q1 = __shfl_sync(FULLMASK, T[cb][1], 2 + (t >> 1), 4);
-            a0 = (t & 1) ? p1 : p0;
-            a1 = (t & 1) ? q1 : q0;
+        double a0[MT], a1[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const double p0 = __shfl_sync(FULLMASK, T[mt][cb][0], s0, 4), p1 = __shfl_sync(FULLMASK, T[mt][cb][1], s0, 4);
+            const double q0 = __shfl_sync(FULLMASK, T[mt][cb][0], s1, 4), q1 = __shfl_sync(FULLMASK, T[mt][cb][1], s1, 4);
+            a0[mt] = odd ? p1 : p0;
+            a1[mt] = odd ? q1 : q0;
         }
-        double x0 = 0.0, x1 = 0.0;
-        dmma884(x0, x1, a0, b0);
-        dmma884(x0, x1, a1, b1);
-        T[cb][0] = x0; T[cb][1] = x1;
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            double x0 = 0.0, x1 = 0.0;
+            dmma884(x0, x1, a0[mt], b0);
+            dmma884(x0, x1, a1[mt], b1);
+            T[mt][cb][0] = x0; T[mt][cb][1] = x1;
+        }
         if (cb == 7) break;
-        {
-            const double p0 = __shfl_sync(FULLMASK, x0, t >> 1, 4), p1 = __shfl_sync(FULLMASK, x1, t >> 1, 4);
-            const double q0 = __shfl_sync(FULLMASK, x0, 2 + (t >> 1), 4), q1 = __shfl_sync(FULLMASK, x1, 2 + (t >> 1), 4);
-            a0 = -((t & 1) ? p1 : p0);
-            a1 = -((t & 1) ? q1 : q0);
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const double p0 = __shfl_sync(FULLMASK, T[mt][cb][0], s0, 4), p1 = __shfl_sync(FULLMASK, T[mt][cb][1], s0, 4);
+            const double q0 = __shfl_sync(FULLMASK, T[mt][cb][0], s1, 4), q1 = __shfl_sync(FULLMASK, T[mt][cb][1], s1, 4);
+            a0[mt] = -(odd ? p1 : p0);
+            a1[mt] = -(odd ? q1 : q0);
         }
 #pragma unroll
         for (int j = cb + 1; j < 8; j++) {
             const double l0 = Ms[(j * 8 + g) * GSUM_LDS + c0 + t], l1 = Ms[(j * 8 + g) * GSUM_LDS + c0 + 4 + t];
-            dmma884(T[j][0], T[j][1], a0, l0);
-            dmma884(T[j][0], T[j][1], a1, l1);
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                dmma884(T[mt][j][0], T[mt][j][1], a0[mt], l0);
+                dmma884(T[mt][j][0], T[mt][j][1], a1[mt], l1);
+            }
         }
     }
 }
 
-// In-place inversion of the eight 8x8 diagonal blocks of the factored tile S (smem, stride GSUM_LDS), by one 128-thread
-// group: thread (cb, j) solves  L_blk x = e_j  by substitution; zeros above the diagonal.  Group barrier: CONS_SYNC.
-__device__ __forceinline__ void ht_invert_diag_blocks(double *S) {
+// M_kk (dense 64 x 64, ld 64) from the factored tile S (smem, stride GSUM_LDS; dg[j] = L_jj): L_kk below the 8x8
+// diagonal blocks, the INVERSES of the diagonal blocks on them, zeros above.  Threads 64..127 copy the off-diagonal
+// part while thread (cb, j) < 64 solves  L_blk x = e_j  by substitution in registers (reciprocal pivots, one multiply
+// per step on the chain) and stores its column.  S is not modified.
+__device__ __forceinline__ void ht_write_mkk(const double *S, const double *dg, double *Mt, bool fail) {
     const int tid = EPI_TID;
-    double x[8];
-    const int cb = (tid >> 3) & 7, j = tid & 7;
-    double *blk = S + (cb * 8) * GSUM_LDS + cb * 8;
     if (tid < 64) {
+        const int cb = tid >> 3, j = tid & 7;
+        const double *blk = S + (cb * 8) * GSUM_LDS + cb * 8;
+        double x[8];
 #pragma unroll
         for (int m = 0; m < 8; m++) {
             double s = (m == j) ? 1.0 : 0.0;
 #pragma unroll
             for (int n = 0; n < m; n++) s = fma(-blk[m * GSUM_LDS + n], x[n], s);
-            x[m] = (m >= j) ? s / blk[m * GSUM_LDS + m] : 0.0;
+            x[m] = (m >= j) ? s * (1.0 / dg[cb * 8 + m]) : 0.0;
         }
-    }
-    CONS_SYNC();
-    if (tid < 64) {
 #pragma unroll
-        for (int m = 0; m < 8; m++) blk[m * GSUM_LDS + j] = x[m];
-    }
-    CONS_SYNC();
-}
-// M tile (dense 64 x 64, ld 64) from the smem tile whose diagonal blocks already hold the inverses
-__device__ __forceinline__ void ht_write_mkk(const double *S, double *Mt, bool fail) {
-    const int tid = EPI_TID;
-    for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        double2 v;
-        const bool below = (c >> 3) <= (r >> 3);            // c and c + 1 share an 8-block
-        v.x = below ? S[r * GSUM_LDS + c] : 0.0;
-        v.y = below ? S[r * GSUM_LDS + c + 1] : 0.0;
-        if (fail) { v.x = v.y = nan(""); }
-        *reinterpret_cast<double2 *>(Mt + r * GSUM_TILE + c) = v;
+        for (int m = 0; m < 8; m++) Mt[(cb * 8 + m) * GSUM_TILE + cb * 8 + j] = fail ? nan("") : x[m];
+    } else {
+        for (int e = tid - 64; e < GSUM_TILE * GSUM_TILE / 2; e += 64) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            if ((c >> 3) == (r >> 3)) continue;            // diagonal block: written by the solvers
+            double2 v;
+            const bool below = (c >> 3) < (r >> 3);
+            v.x = below ? S[r * GSUM_LDS + c] : 0.0;
+            v.y = below ? S[r * GSUM_LDS + c + 1] : 0.0;
+            if (fail) { v.x = v.y = nan(""); }
+            *reinterpret_cast<double2 *>(Mt + r * GSUM_TILE + c) = v;
+        }
     }
 }
 
@@ -210,8 +221,18 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
         cp_async_wait<0>();
         if (tid == 0) *s_fail = 0;
         CONS_SYNC();
+        const long long t2 = st ? clock64() : 0;
         tile_potrf_blocked_inl(S, dg, s_fail);
+        const long long t3 = st ? clock64() : 0;
         const int fail = *s_fail;
+        // Critical path first: M_kk (what the panel tasks of this column wait for), then the flag; L_kk itself, the
+        // log-determinant and the status are outputs nobody inside the launch reads.
+        ht_write_mkk(S, dg, D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), fail != 0);
+#if HT_FENCE_FACTOR
+        __threadfence();
+#endif
+        CONS_SYNC();                                  // every thread's M stores are ordered before the release below
+        if (tid == 0) st_release(flag, 2);
         if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
         // L_kk: lower triangle, exact zeros above the diagonal (numpy.linalg.cholesky convention)
         for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += CHOL_THREADS) {
@@ -230,21 +251,16 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
             v = warp_sum(v);
             if (tid == 0) P.logdet_part[(int64_t)b * P.T + k] = fail ? nan("") : 2.0 * v;
         }
-        CONS_SYNC();
-        ht_invert_diag_blocks(S);
-        ht_write_mkk(S, D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), fail != 0);
-        __threadfence();
-        CONS_SYNC();
-        if (tid == 0) st_release(flag, 2);
-        if (st && tid == 0) { st[0] += t1 - t0; st[1] += clock64() - t1; st[2] += 1; }
+        CONS_SYNC();                                  // S and dg are reused by the next tile
+        if (st && tid == 0) { st[0] += t1 - t0; st[1] += clock64() - t1; st[2] += 1; st[3] += t2 - t1; st[4] += t3 - t2; }
     }
 }
 
 template <bool STATS>
 __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t full_bar[HT_NST], empty_bar[HT_NST], tq_full[HT_QD], tq_empty[HT_QD];
-    __shared__ int4 tq[HT_QD];
+    __shared__ __align__(8) uint64_t full_bar[2][HT_NST], empty_bar[2][HT_NST], tq_full[2][HT_QD], tq_empty[2][HT_QD];
+    __shared__ int4 tq[2][HT_QD];
     const BorderedBatch &P = D.P;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool st_on = STATS && D.stats != nullptr;
@@ -255,27 +271,36 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
 
     if ((int)blockIdx.x < D.nfactor_ctas) {
         // ============================ factor CTA ================================================================
+        if (tid >= 128 * D.nworkers) return;         // up to three 128-thread workers
         ht_factor_worker(D, smem + (tid >> 7) * HT_WORKER_DOUBLES, st_on ? st : nullptr);
         if (st_on && (tid & 127) == 0) {
-            long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + (tid >> 7) * 4;
-            o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2];
+            long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + (tid >> 7) * 6;
+            o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; o[5] = st[4];
         }
         return;
     }
 
-    double *ring_base = smem;
-    double *Sbuf = smem + HT_NST * HT_STAGE_DOUBLES;
+    // ============================ GEMM CTA: two independent groups ==============================================
+    // Group q = 4 math warps (one per sub-partition: warps 4q .. 4q+3) + HT_PW producer warps, with its own task queue
+    // and operand ring.  The groups run different tasks and drift apart, so while one sits in a task's latency-bound
+    // parts (accumulator load, triangular solve, stores, fence, flag) the other keeps the FP64 tensor pipe streaming.
+    const int q = (w < 8) ? (w >> 2) : ((w - 8) / HT_PW);
+    double *ring_base = smem + q * (HT_NST * HT_STAGE_DOUBLES);
+    uint64_t *fullb = full_bar[q], *emptyb = empty_bar[q], *tqf = tq_full[q], *tqe = tq_empty[q];
+    int4 *tqs = tq[q];
     if (tid == 0) {
-        for (int s = 0; s < HT_NST; s++) { mbar_init(&full_bar[s], 128); mbar_init(&empty_bar[s], HT_MATH_WARPS); }
-        for (int s = 0; s < HT_QD; s++) { mbar_init(&tq_full[s], 1); mbar_init(&tq_empty[s], HT_MATH_WARPS + 3); }
+        for (int qq = 0; qq < 2; qq++) {
+            for (int s = 0; s < HT_NST; s++) { mbar_init(&full_bar[qq][s], 32 * HT_PW); mbar_init(&empty_bar[qq][s], 4); }
+            for (int s = 0; s < HT_QD; s++) { mbar_init(&tq_full[qq][s], 1); mbar_init(&tq_empty[qq][s], 4 + HT_PW - 1); }
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     int *abort_flag = D.ctl + 1;
 
-    if (w >= HT_PRODUCER_WARP) {
+    if (w >= 8) {
         // ============================ producer warps =========================================================
-        const int pw = w - HT_PRODUCER_WARP;
+        const int pw = (w - 8) % HT_PW;
         RingState ring = {0, 0u};
         for (int n = 0;; n++) {
             const int slot = n % HT_QD;
@@ -283,23 +308,23 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
             int ok = 1;
             if (pw == 0) {
                 if (lane == 0) {
-                    { HT_T0(); ok = mbar_wait(&tq_empty[slot], (((unsigned)(n / HT_QD)) & 1u) ^ 1u, abort_flag); HT_ACC(0); }
+                    { HT_T0(); ok = mbar_wait(&tqe[slot], (((unsigned)(n / HT_QD)) & 1u) ^ 1u, abort_flag); HT_ACC(0); }
                     if (ok) {
                         const int tix = atomicAdd(D.ctl, 1);
                         if (tix < D.ngtasks) tk = D.gtasks[tix];
-                        tq[slot] = tk;
-                        mbar_arrive(&tq_full[slot]);
+                        tqs[slot] = tk;
+                        mbar_arrive(&tqf[slot]);
                     }
                 }
                 ok = __shfl_sync(0xffffffffu, ok, 0);
                 tk.x = __shfl_sync(0xffffffffu, tk.x, 0); tk.y = __shfl_sync(0xffffffffu, tk.y, 0);
                 tk.z = __shfl_sync(0xffffffffu, tk.z, 0); tk.w = __shfl_sync(0xffffffffu, tk.w, 0);
             } else {
-                ok = mbar_wait(&tq_full[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag);
+                ok = mbar_wait(&tqf[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag);
                 if (ok) {
-                    tk = tq[slot];
+                    tk = tqs[slot];
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tq_empty[slot]);
+                    if (lane == 0) mbar_arrive(&tqe[slot]);
                 }
             }
             if (!ok || tk.x < 0) break;
@@ -311,30 +336,31 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
             const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
             const int *frow_i = D.flags + ((int64_t)b * P.Trows + i) * P.T;
             const int *frow_k = D.flags + ((int64_t)b * P.Trows + k) * P.T;
+            constexpr int RPW = GSUM_TILE / HT_PW;          // tile rows per producer warp
             bool alive = true;
             // ---- stage 0 of the task: the C tile (original data, written before the launch) ----------------------
             {
                 int good = 1;
-                if (lane == 0) { HT_T0(); good = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
+                if (lane == 0) { HT_T0(); good = mbar_wait(&emptyb[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
                 alive = __shfl_sync(0xffffffffu, good, 0) != 0;
                 if (!alive) break;
                 double *Cs = ring_base + ring.stage * HT_STAGE_DOUBLES;
                 const double *C = Ri + k * GSUM_TILE;
                 if (!thin) {
-#pragma unroll
-                    for (int q = 0; q < 16; q++) {
-                        const int row = pw * 16 + q, ch = lane * 2;
-                        cp_async16(Cs + row * GSUM_LDS + ch, C + (int64_t)row * P.ld + ch);
+#pragma unroll 8
+                    for (int r = 0; r < RPW; r++) {
+                        const int row = pw * RPW + r;
+                        cp_async16(Cs + row * GSUM_LDS + lane * 2, C + (int64_t)row * P.ld + lane * 2);
                     }
                 } else if (pw == 0) {
 #pragma unroll
-                    for (int q = 0; q < 8; q++) cp_async16(Cs + q * GSUM_LDS + lane * 2, C + (int64_t)q * P.ld + lane * 2);
+                    for (int r = 0; r < 8; r++) cp_async16(Cs + r * GSUM_LDS + lane * 2, C + (int64_t)r * P.ld + lane * 2);
                 }
-                cp_async_mbar_arrive(&full_bar[ring.stage]);
+                cp_async_mbar_arrive(&fullb[ring.stage]);
                 ht_ring_advance(ring);
             }
-            // ---- operand half-slabs ----------------------------------------------------------------------------
-            const int r0 = pw * 16 + (lane >> 4), ch = (lane & 15) * 2;
+            // ---- operand half-slabs: a warp-wide copy moves two rows of 256 bytes -------------------------------
+            const int r0 = pw * RPW + (lane >> 4), ch = (lane & 15) * 2;
             // A finished tile (r, k-1) implies every (r, j < k-1): they were its operands.
             int done_i = 1, done_k = 1;
             if (lane == 0 && k > 0) {
@@ -350,33 +376,33 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
                         good = (done_i || flag_wait(frow_i + j, abort_flag)) && (diag || done_k || flag_wait(frow_k + j, abort_flag));
                         HT_ACC(1);
                     }
-                    if (good) { HT_T0(); good = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
+                    if (good) { HT_T0(); good = mbar_wait(&emptyb[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
                 }
                 alive = __shfl_sync(0xffffffffu, good, 0) != 0;
                 if (!alive) break;
                 double *As = ring_base + ring.stage * HT_STAGE_DOUBLES, *Bs = As + GSUM_TILE * GSUM_LDH;
                 const int col0 = j * GSUM_TILE + (h & 1) * GSUM_KH;
                 if (!thin) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int row = r0 + 2 * q;
+#pragma unroll 8
+                    for (int r = 0; r < RPW / 2; r++) {
+                        const int row = r0 + 2 * r;
                         cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
                     }
                 } else if (pw == 0) {                      // thin task: rows 0..7 of the A operand only
 #pragma unroll
-                    for (int q = 0; q < 4; q++) {
-                        const int row = (lane >> 4) + 2 * q;
+                    for (int r = 0; r < 4; r++) {
+                        const int row = (lane >> 4) + 2 * r;
                         cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
                     }
                 }
                 if (!diag) {
-#pragma unroll
-                    for (int q = 0; q < 8; q++) {
-                        const int row = r0 + 2 * q;
+#pragma unroll 8
+                    for (int r = 0; r < RPW / 2; r++) {
+                        const int row = r0 + 2 * r;
                         cp_async16(Bs + row * GSUM_LDH + ch, Ak + (int64_t)row * P.ld + col0 + ch);
                     }
                 }
-                cp_async_mbar_arrive(&full_bar[ring.stage]);
+                cp_async_mbar_arrive(&fullb[ring.stage]);
                 ht_ring_advance(ring);
             }
             if (!alive) break;
@@ -385,39 +411,39 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
                 int good = 1;
                 if (lane == 0) {
                     { HT_T0(); good = flag_wait_ge(frow_k + k, 2, abort_flag) ? 1 : 0; HT_ACC(3); }
-                    if (good) { HT_T0(); good = mbar_wait(&empty_bar[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
+                    if (good) { HT_T0(); good = mbar_wait(&emptyb[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
                 }
                 alive = __shfl_sync(0xffffffffu, good, 0) != 0;
                 if (!alive) break;
                 double *Ms = ring_base + ring.stage * HT_STAGE_DOUBLES;
                 const double *Mg = D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE);
-#pragma unroll
-                for (int q = 0; q < 16; q++) {
-                    const int row = pw * 16 + q;
+#pragma unroll 8
+                for (int r = 0; r < RPW; r++) {
+                    const int row = pw * RPW + r;
                     cp_async16(Ms + row * GSUM_LDS + lane * 2, Mg + row * GSUM_TILE + lane * 2);
                 }
-                cp_async_mbar_arrive(&full_bar[ring.stage]);
+                cp_async_mbar_arrive(&fullb[ring.stage]);
                 ht_ring_advance(ring);
             }
         }
         cp_async_wait<0>();
-        if (st_on && pw == 0 && lane == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT; o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; }
+        if (st_on && pw == 0 && lane == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; }
     } else {
         // ============================ math warps ============================================================
-        const int g = lane >> 2, t = lane & 3, wr = w & 3, wc = w >> 2;
+        const int g = lane >> 2, t = lane & 3, wg = w & 3;
         RingState ring = {0, 0u};
         for (int n = 0;; n++) {
             const int slot = n % HT_QD;
             bool alive;
-            { HT_T0(); alive = mbar_wait(&tq_full[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag); HT_ACC(0); }
+            { HT_T0(); alive = mbar_wait(&tqf[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag); HT_ACC(0); }
             int4 tk = make_int4(-1, 0, 0, 0);
             if (alive) {
-                tk = tq[slot];
+                tk = tqs[slot];
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tq_empty[slot]);
+                if (lane == 0) mbar_arrive(&tqe[slot]);
             }
-            // the math warps leave together: a warp that gave up on the queue (abort) must not strand the others at a barrier
-            alive = ht_math_sync_and(alive);
+            // the math warps of a group leave together: a warp that gave up on the queue (abort) must not strand the others
+            alive = ht_group_sync_and(alive, q);
             if (!alive || tk.x < 0) break;
             const int i = tk.x, k = tk.y, b = tk.z;
             const bool diag = (i == k), thin = (tk.w & 1) != 0;
@@ -425,95 +451,86 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
             double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
                                    : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
             double *C = Ri + k * GSUM_TILE;
-            // diagonal task: blocks above the diagonal are skipped (row blocks 2wr, 2wr+1; column blocks 4wc + nt)
-            int ntm = 4;
-            if (diag) { ntm = 2 * wr + 2 - 4 * wc; ntm = ntm < 0 ? 0 : (ntm > 4 ? 4 : ntm); }
-            const bool active = !thin || wr == 0;          // thin task: only rows 0..7 are in use
+            const int ntm = diag ? 2 * (wg + 1) : 8;        // diagonal task: warp wg owns columns < 16 (wg + 1)
+            const bool active = !thin || wg == 0;           // thin task (rows 0..7 in use): warp 0 of the group alone
             // ---- acc = -C ------------------------------------------------------------------------------------------
-            Acc32 acc;
+            Acc acc;
             {
-                { HT_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
+                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
                 const double *Cs = ring_base + ring.stage * HT_STAGE_DOUBLES;
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++) {
+                    for (int nt = 0; nt < 8; nt++) {
                         if (nt < ntm && active && (!thin || mt == 0)) {
-                            const double2 v = *reinterpret_cast<const double2 *>(Cs + (wr * 16 + mt * 8 + g) * GSUM_LDS + wc * 32 + nt * 8 + 2 * t);
+                            const double2 v = *reinterpret_cast<const double2 *>(Cs + (wg * 16 + mt * 8 + g) * GSUM_LDS + nt * 8 + 2 * t);
                             acc[mt][nt][0] = -v.x; acc[mt][nt][1] = -v.y;
                         } else { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
                     }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
+                if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 ht_ring_advance(ring);
             }
             // ---- main loop ---------------------------------------------------------------------------------------
             for (int h = 0; h < 2 * k; h++) {
-                { HT_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
+                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
                 const double *As = ring_base + ring.stage * HT_STAGE_DOUBLES;
                 const double *Bs = diag ? As : As + GSUM_TILE * GSUM_LDH;
-                if (thin) { if (active) ht_stage_mma<1, true>(acc, As, Bs, wr, wc, 4, g, t); }
-                else if (diag) ht_stage_mma<2, false>(acc, As, Bs, wr, wc, ntm, g, t);
-                else ht_stage_mma<2, true>(acc, As, Bs, wr, wc, 4, g, t);
+                if (thin) { if (active) ht_stage_mma<1, true>(acc, As, Bs, wg, 8, g, t); }
+                else if (diag) ht_stage_mma<2, false>(acc, As, Bs, wg, ntm, g, t);
+                else ht_stage_mma<2, true>(acc, As, Bs, wg, 8, g, t);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
+                if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 ht_ring_advance(ring);
             }
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++) { acc[mt][nt][0] = -acc[mt][nt][0]; acc[mt][nt][1] = -acc[mt][nt][1]; }
             if (diag) {
-                // ---- S = -(acc) back in place; the factor CTAs take it from there --------------------------------
+                // ---- S back in place; the factor CTAs take it from there ------------------------------------------
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                    for (int nt = 0; nt < 4; nt++)
+                    for (int nt = 0; nt < 8; nt++)
                         if (nt < ntm) {
-                            double2 v; v.x = -acc[mt][nt][0]; v.y = -acc[mt][nt][1];
-                            *reinterpret_cast<double2 *>(C + (int64_t)(wr * 16 + mt * 8 + g) * P.ld + wc * 32 + nt * 8 + 2 * t) = v;
+                            double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
+                            *reinterpret_cast<double2 *>(C + (int64_t)(wg * 16 + mt * 8 + g) * P.ld + nt * 8 + 2 * t) = v;
                         }
             } else {
-                // ---- 16x32 warp tiles -> 8x64 row blocks through shared memory, then the triangular solve --------
+                // ---- the triangular solve, warp-local on the 16 x 64 row block ------------------------------------
+                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(2); }
                 if (active) {
+                    HT_T0();
+                    const double *Ms = ring_base + ring.stage * HT_STAGE_DOUBLES;
+                    if (thin) ht_trsm_dinv<1>(acc, Ms, g, t); else ht_trsm_dinv<2>(acc, Ms, g, t);
+                    HT_ACC(3);
 #pragma unroll
                     for (int mt = 0; mt < 2; mt++)
 #pragma unroll
-                        for (int nt = 0; nt < 4; nt++) {
-                            double2 v; v.x = -acc[mt][nt][0]; v.y = -acc[mt][nt][1];
-                            *reinterpret_cast<double2 *>(Sbuf + (wr * 16 + mt * 8 + g) * GSUM_LDS + wc * 32 + nt * 8 + 2 * t) = v;
-                        }
-                }
-                HT_MATH_SYNC();
-                double T[8][2];
-                const bool solver = !thin || w == 0;
-                if (solver) {
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        const double2 v = *reinterpret_cast<const double2 *>(Sbuf + (w * 8 + g) * GSUM_LDS + nt * 8 + 2 * t);
-                        T[nt][0] = v.x; T[nt][1] = v.y;
-                    }
-                }
-                { HT_T0(); alive = mbar_wait(&full_bar[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(2); }
-                if (solver) {
-                    HT_T0();
-                    ht_trsm_dinv(T, ring_base + ring.stage * HT_STAGE_DOUBLES, g, t);
-                    HT_ACC(3);
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        double2 v; v.x = T[nt][0]; v.y = T[nt][1];
-                        *reinterpret_cast<double2 *>(C + (int64_t)(w * 8 + g) * P.ld + nt * 8 + 2 * t) = v;
-                    }
+                        for (int nt = 0; nt < 8; nt++)
+                            if (!thin || mt == 0) {
+                                double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
+                                *reinterpret_cast<double2 *>(C + (int64_t)(wg * 16 + mt * 8 + g) * P.ld + nt * 8 + 2 * t) = v;
+                            }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[ring.stage]);
+                if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 ht_ring_advance(ring);
             }
             { HT_T0();
-            __threadfence();                              // tile stores visible device-wide before the flag
-            alive = ht_math_sync_and(alive);
-            if (alive && tid == 0) st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
+            // barrier, then one release store: the release is cumulative over what the barrier ordered before it (the
+            // CUTLASS semaphore idiom), so the tile stores of all 128 threads are visible before the flag
+#if HT_FENCE_GEMM
+            __threadfence();
+#endif
+            alive = ht_group_sync_and(alive, q);
+            if (alive && (tid & 127) == 0) st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
             HT_ACC(4); }
             if (!alive) break;
             st[5] += 1;
         }
-        if (st_on && tid == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT; o[5] = clock64() - st_t0; o[6] = st[0]; o[7] = st[1]; o[8] = st[2]; o[9] = st[3]; o[10] = st[4]; o[11] = st[5]; }
+        if (st_on && (tid & 127) == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[5] = clock64() - st_t0; o[6] = st[0]; o[7] = st[1]; o[8] = st[2]; o[9] = st[3]; o[10] = st[4]; o[11] = st[5]; }
     }
 #undef HT_T0
 #undef HT_ACC
@@ -533,15 +550,16 @@ __global__ void ht_init_kernel(int *flags, int *ctl, int64_t batch, int Trows, i
 // M_kk tiles from an existing factor (solve_only calls): one 128-thread CTA per diagonal tile
 __global__ void __launch_bounds__(CHOL_THREADS) ht_mkk_from_factor_kernel(BorderedBatch P, double *M) {
     __shared__ __align__(16) double S[GSUM_TILE * GSUM_LDS];
+    __shared__ double dg[GSUM_TILE];
     const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const double *C = P.A + (int64_t)b * P.bstride + (int64_t)k * GSUM_TILE * P.ld + k * GSUM_TILE;
     for (int e = tid; e < GSUM_TILE * GSUM_TILE; e += CHOL_THREADS) {
         const int r = e >> 6, c = e & 63;
         S[r * GSUM_LDS + c] = C[(int64_t)r * P.ld + c];
     }
+    if (tid < GSUM_TILE) dg[tid] = C[(int64_t)tid * P.ld + tid];
     __syncthreads();
-    ht_invert_diag_blocks(S);
-    ht_write_mkk(S, M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), false);
+    ht_write_mkk(S, dg, M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), false);
 }
 
 // Split the joint topological order into the two claim lists.
