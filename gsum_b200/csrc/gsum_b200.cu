@@ -341,11 +341,11 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * HT_NSTAT * grid, cudaMemcpyDeviceToHost);
         double f[6] = {0, 0, 0, 0, 0, 0}, a[HT_NSTAT] = {0};
         for (int g = 0; g < nf; g++) for (int wk = 0; wk < nwk; wk++) for (int q = 0; q < 6; q++) f[q] += (double)h[HT_NSTAT * g + wk * 6 + q];
-        for (int g = nf; g < grid; g++) for (int grp = 0; grp < 2; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
+        for (int g = nf; g < grid; g++) for (int grp = 0; grp < HT_NG; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
         if (nf) fprintf(stderr, "[ht] factor CTAs %d: cycles/worker %.0f | wait_S %.1f%% | busy %.1f%% (%.0f cycles per diagonal tile: load %.0f, potrf %.0f; %.1f tiles per worker)\n",
                         nf, f[0] / (nwk * nf), 100 * f[1] / f[0], 100 * f[2] / f[0], f[2] / (f[3] + 1e-9), f[4] / (f[3] + 1e-9), f[5] / (f[3] + 1e-9), f[3] / (nwk * nf));
-        if (ng) fprintf(stderr, "[ht] GEMM CTAs %d (2 groups each): cycles/group %.0f, tasks/group %.1f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% wait_Mkk %.1f%% | math: wait_queue %.1f%% wait_operands %.1f%% wait_Mkk %.1f%% trsm %.1f%% fence+flag %.1f%%\n",
-                        ng, a[5] / (2 * ng), a[11] / (2 * ng), 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0],
+        if (ng) fprintf(stderr, "[ht] GEMM CTAs %d x %d groups: cycles/group %.0f, tasks/group %.1f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% wait_Mkk %.1f%% | math: wait_queue %.1f%% wait_operands %.1f%% wait_Mkk %.1f%% trsm %.1f%% fence+flag %.1f%%\n",
+                        ng, HT_NG, a[5] / (HT_NG * ng), a[11] / (HT_NG * ng), 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0],
                         100 * a[6] / a[5], 100 * a[7] / a[5], 100 * a[8] / a[5], 100 * a[9] / a[5], 100 * a[10] / a[5]);
     }
     return 0;

@@ -26,19 +26,32 @@
 #pragma once
 #include "dataflow.cuh"
 
+#ifndef HT_NG
+#define HT_NG 2                         // independent math groups per GEMM CTA (each: 4 math warps, one per sub-partition)
+#endif
 #ifndef HT_PW
 #define HT_PW 2                         // producer warps per group
 #endif
-#define HT_THREADS (256 + 64 * HT_PW)   // GEMM CTA: 2 groups x (4 math warps + HT_PW producer warps);  factor CTA: 3 workers x 128 threads
+#define HT_MATH_WARPS (4 * HT_NG)
+// GEMM CTA: HT_NG x (4 math warps + HT_PW producer warps), rounded up to whole warpgroups;  factor CTA: 3 workers x 128 threads
+#define HT_THREADS (128 * ((HT_MATH_WARPS + HT_NG * HT_PW + 3) / 4))
 #ifndef HT_NST
 #define HT_NST 3                        // ring stages per group (36 KiB each: an operand half-slab pair, or one whole 64x64 tile)
 #endif
 #define HT_QD 4                         // task queue depth
 #define HT_STAGE_DOUBLES CHOL_STAGE_DOUBLES
-#define HT_SMEM_DOUBLES (2 * HT_NST * HT_STAGE_DOUBLES)
+#define HT_SMEM_DOUBLES (HT_NG * HT_NST * HT_STAGE_DOUBLES)
+// Register split (setmaxnreg, warpgroup granular) for three groups: the launch bound leaves 128 (512 threads) or 96 (640)
+// registers per thread; the producer warpgroups keep 40 and the three math / factor warpgroups take HT_MATH_REGS.
+#ifndef HT_SETMAXNREG
+#define HT_SETMAXNREG (HT_MATH_WARPS == 12 && HT_THREADS == 512)
+#endif
+#define HT_MATH_REGS 152
+#define HT_STR2(x) #x
+#define HT_STR(x) HT_STR2(x)
 #define HT_SMEM_BYTES (HT_SMEM_DOUBLES * 8)
 #define HT_WORKER_DOUBLES (GSUM_TILE * GSUM_LDS + 3 * GSUM_TILE)     // factor worker: tile + diag + scratch ints
-#define HT_NSTAT 24
+#define HT_NSTAT 40
 #ifndef HT_FENCE_GEMM
 #define HT_FENCE_GEMM 0
 #endif
@@ -49,7 +62,7 @@
 #define HT_FACTOR_CTAS 16               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
 #endif
 #ifndef HT_DIAG_DELAY
-#define HT_DIAG_DELAY 0
+#define HT_DIAG_DELAY 64
 #endif
 
 struct HeteroArgs {
@@ -107,6 +120,27 @@ __device__ __forceinline__ void ht_stage_mma(Acc &acc, const double *As, const d
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
             }
+    }
+}
+
+// Diagonal (SYRK) task: only the 36 blocks on and below the diagonal are needed.  Warp wg takes the block rows wg and
+// 7 - wg (wg + 1 and 8 - wg blocks: nine per warp, so the four sub-partitions carry the same load):
+//     acc[0][nt] <-> block (wg, nt), nt <= wg;      acc[1][nt] <-> block (7 - wg, nt), nt <= 7 - wg.
+__device__ __forceinline__ void ht_stage_syrk(Acc &acc, const double *As, int wg, int g, int t) {
+    const double *ap0 = As + (wg * 8 + g) * GSUM_LDH + t;
+    const double *ap1 = As + ((7 - wg) * 8 + g) * GSUM_LDH + t;
+    const double *bp = As + g * GSUM_LDH + t;
+#pragma unroll
+    for (int ks = 0; ks < GSUM_KH / 4; ks++) {
+        double b[8];
+        const double a0 = ap0[ks * 4], a1 = ap1[ks * 4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) if (nt <= 4 || nt <= 7 - wg) b[nt] = bp[nt * 8 * GSUM_LDH + ks * 4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            if (nt <= 3 && nt <= wg) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
+            if (nt <= 4 || nt <= 7 - wg) dmma884(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
+        }
     }
 }
 
@@ -259,8 +293,9 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
 template <bool STATS>
 __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D) {
     extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t full_bar[2][HT_NST], empty_bar[2][HT_NST], tq_full[2][HT_QD], tq_empty[2][HT_QD];
-    __shared__ int4 tq[2][HT_QD];
+    __shared__ __align__(8) uint64_t full_bar[HT_NG][HT_NST], empty_bar[HT_NG][HT_NST], tq_full[HT_NG][HT_QD], tq_empty[HT_NG][HT_QD];
+    __shared__ int4 tq[HT_NG][HT_QD];
+    __shared__ int done_cnt[HT_NG][HT_QD];
     const BorderedBatch &P = D.P;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool st_on = STATS && D.stats != nullptr;
@@ -271,6 +306,11 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
 
     if ((int)blockIdx.x < D.nfactor_ctas) {
         // ============================ factor CTA ================================================================
+#if HT_SETMAXNREG
+        // same register split as in a GEMM CTA: warpgroup 3 (idle here) hands its registers to the three workers
+        if (w >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); return; }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HT_MATH_REGS) ";");
+#endif
         if (tid >= 128 * D.nworkers) return;         // up to three 128-thread workers
         ht_factor_worker(D, smem + (tid >> 7) * HT_WORKER_DOUBLES, st_on ? st : nullptr);
         if (st_on && (tid & 127) == 0) {
@@ -284,12 +324,13 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
     // Group q = 4 math warps (one per sub-partition: warps 4q .. 4q+3) + HT_PW producer warps, with its own task queue
     // and operand ring.  The groups run different tasks and drift apart, so while one sits in a task's latency-bound
     // parts (accumulator load, triangular solve, stores, fence, flag) the other keeps the FP64 tensor pipe streaming.
-    const int q = (w < 8) ? (w >> 2) : ((w - 8) / HT_PW);
+    const int q = (w < HT_MATH_WARPS) ? (w >> 2) : ((w - HT_MATH_WARPS) / HT_PW);
     double *ring_base = smem + q * (HT_NST * HT_STAGE_DOUBLES);
     uint64_t *fullb = full_bar[q], *emptyb = empty_bar[q], *tqf = tq_full[q], *tqe = tq_empty[q];
     int4 *tqs = tq[q];
     if (tid == 0) {
-        for (int qq = 0; qq < 2; qq++) {
+        for (int qq = 0; qq < HT_NG; qq++) {
+            for (int s = 0; s < HT_QD; s++) done_cnt[qq][s] = 0;
             for (int s = 0; s < HT_NST; s++) { mbar_init(&full_bar[qq][s], 32 * HT_PW); mbar_init(&empty_bar[qq][s], 4); }
             for (int s = 0; s < HT_QD; s++) { mbar_init(&tq_full[qq][s], 1); mbar_init(&tq_empty[qq][s], 4 + HT_PW - 1); }
         }
@@ -298,9 +339,13 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
     __syncthreads();
     int *abort_flag = D.ctl + 1;
 
-    if (w >= 8) {
+    if (w >= HT_MATH_WARPS) {
+#if HT_SETMAXNREG
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
+        if (w >= HT_MATH_WARPS + HT_NG * HT_PW) return;      // padding warps of the last warpgroup
         // ============================ producer warps =========================================================
-        const int pw = (w - 8) % HT_PW;
+        const int pw = (w - HT_MATH_WARPS) % HT_PW;
         RingState ring = {0, 0u};
         for (int n = 0;; n++) {
             const int slot = n % HT_QD;
@@ -430,6 +475,9 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
         if (st_on && pw == 0 && lane == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; }
     } else {
         // ============================ math warps ============================================================
+#if HT_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HT_MATH_REGS) ";");
+#endif
         const int g = lane >> 2, t = lane & 3, wg = w & 3;
         RingState ring = {0, 0u};
         for (int n = 0;; n++) {
@@ -442,28 +490,29 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tqe[slot]);
             }
-            // the math warps of a group leave together: a warp that gave up on the queue (abort) must not strand the others
-            alive = ht_group_sync_and(alive, q);
-            if (!alive || tk.x < 0) break;
+            if (!alive || tk.x < 0) break;             // no CTA-level barrier anywhere in this role: a warp may leave alone
             const int i = tk.x, k = tk.y, b = tk.z;
             const bool diag = (i == k), thin = (tk.w & 1) != 0;
             double *Ab = P.A + (int64_t)b * P.bstride;
             double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
                                    : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
             double *C = Ri + k * GSUM_TILE;
-            const int ntm = diag ? 2 * (wg + 1) : 8;        // diagonal task: warp wg owns columns < 16 (wg + 1)
             const bool active = !thin || wg == 0;           // thin task (rows 0..7 in use): warp 0 of the group alone
+            // rows of this warp's two m tiles: 16 wg, 16 wg + 8 — or, on a diagonal task, the block rows wg and 7 - wg
+            const int row0 = diag ? wg * 8 : wg * 16, row1 = diag ? (7 - wg) * 8 : wg * 16 + 8;
+            const int n0 = diag ? wg + 1 : 8, n1 = diag ? 8 - wg : 8;           // n tiles in use per m tile
             // ---- acc = -C ------------------------------------------------------------------------------------------
             Acc acc;
             {
-                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
+                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(1); }
+                if (!alive) break;
                 const double *Cs = ring_base + ring.stage * HT_STAGE_DOUBLES;
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 8; nt++) {
-                        if (nt < ntm && active && (!thin || mt == 0)) {
-                            const double2 v = *reinterpret_cast<const double2 *>(Cs + (wg * 16 + mt * 8 + g) * GSUM_LDS + nt * 8 + 2 * t);
+                        if (nt < (mt ? n1 : n0) && active && (!thin || mt == 0)) {
+                            const double2 v = *reinterpret_cast<const double2 *>(Cs + ((mt ? row1 : row0) + g) * GSUM_LDS + nt * 8 + 2 * t);
                             acc[mt][nt][0] = -v.x; acc[mt][nt][1] = -v.y;
                         } else { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
                     }
@@ -473,16 +522,17 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
             }
             // ---- main loop ---------------------------------------------------------------------------------------
             for (int h = 0; h < 2 * k; h++) {
-                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(1); }
+                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(1); }
+                if (!alive) break;
                 const double *As = ring_base + ring.stage * HT_STAGE_DOUBLES;
-                const double *Bs = diag ? As : As + GSUM_TILE * GSUM_LDH;
-                if (thin) { if (active) ht_stage_mma<1, true>(acc, As, Bs, wg, 8, g, t); }
-                else if (diag) ht_stage_mma<2, false>(acc, As, Bs, wg, ntm, g, t);
-                else ht_stage_mma<2, true>(acc, As, Bs, wg, 8, g, t);
+                if (thin) { if (active) ht_stage_mma<1, true>(acc, As, As + GSUM_TILE * GSUM_LDH, wg, 8, g, t); }
+                else if (diag) ht_stage_syrk(acc, As, wg, g, t);
+                else ht_stage_mma<2, true>(acc, As, As + GSUM_TILE * GSUM_LDH, wg, 8, g, t);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 ht_ring_advance(ring);
             }
+            if (!alive) break;
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
 #pragma unroll
@@ -493,13 +543,14 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
                 for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 8; nt++)
-                        if (nt < ntm) {
+                        if (nt < (mt ? n1 : n0)) {
                             double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
-                            *reinterpret_cast<double2 *>(C + (int64_t)(wg * 16 + mt * 8 + g) * P.ld + nt * 8 + 2 * t) = v;
+                            *reinterpret_cast<double2 *>(C + (int64_t)((mt ? row1 : row0) + g) * P.ld + nt * 8 + 2 * t) = v;
                         }
             } else {
                 // ---- the triangular solve, warp-local on the 16 x 64 row block ------------------------------------
-                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag) && alive; HT_ACC(2); }
+                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(2); }
+                if (!alive) break;
                 if (active) {
                     HT_T0();
                     const double *Ms = ring_base + ring.stage * HT_STAGE_DOUBLES;
@@ -518,16 +569,20 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
                 if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 ht_ring_advance(ring);
             }
+            // ---- publish the tile: no barrier — the last of the four warps to get here stores the flag.  Each warp's lane 0
+            // joins with an acq_rel atomic at CTA scope (after __syncwarp: the warp's stores happen-before it), so the
+            // release store of the last arriver is cumulative over the tile stores of all four warps.
             { HT_T0();
-            // barrier, then one release store: the release is cumulative over what the barrier ordered before it (the
-            // CUTLASS semaphore idiom), so the tile stores of all 128 threads are visible before the flag
-#if HT_FENCE_GEMM
-            __threadfence();
-#endif
-            alive = ht_group_sync_and(alive, q);
-            if (alive && (tid & 127) == 0) st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
+            __syncwarp();
+            if (lane == 0) {
+                int old;
+                asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&done_cnt[q][slot])) : "memory");
+                if (old == 3) {
+                    done_cnt[q][slot] = 0;
+                    st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
+                }
+            }
             HT_ACC(4); }
-            if (!alive) break;
             st[5] += 1;
         }
         if (st_on && (tid & 127) == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[5] = clock64() - st_t0; o[6] = st[0]; o[7] = st[1]; o[8] = st[2]; o[9] = st[3]; o[10] = st[4]; o[11] = st[5]; }
