@@ -1,6 +1,7 @@
 // K7/K8: pivoted Cholesky (LAPACK dpstrf semantics), batched posterior draws  m + L z  and fused
 // credible-interval coverage counting.
 #pragma once
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include "chol.cuh"
 
@@ -236,6 +237,49 @@ __global__ void __launch_bounds__(COVG_WARPS * 32) coverage_rows_kernel(const do
 }
 
 // max-shift normalisation of a log-likelihood grid (notebook cell 54): post = exp(ll - max), lse = max + log(sum post)
+// Cluster version of the normalisation below: 8 CTAs of one thread-block cluster split the grid, exchange their partial
+// maxima / sums through distributed shared memory (every CTA writes its partial into every peer's array) and meet at
+// cluster barriers — one launch, no global scratch, fixed summation order.
+#define GN_CLUSTER 8
+__global__ void __cluster_dims__(GN_CLUSTER, 1, 1) __launch_bounds__(1024)
+grid_normalize_cluster_kernel(const double *__restrict__ ll, int64_t count, double *__restrict__ post, double *__restrict__ lse) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double red[32];
+    __shared__ double part_max[GN_CLUSTER], part_sum[GN_CLUSTER];
+    const unsigned rank = cluster.block_rank();
+    const int64_t stride = (int64_t)GN_CLUSTER * 1024, first = (int64_t)rank * 1024 + threadIdx.x;
+    double mx = -INFINITY;
+    for (int64_t i = first; i < count; i += stride) { const double v = ll[i]; if (v > mx) mx = v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x < GN_CLUSTER) {
+        double m = red[0];
+        for (int i = 1; i < 32; i++) m = fmax(m, red[i]);
+        *cluster.map_shared_rank(&part_max[rank], threadIdx.x) = m;
+    }
+    cluster.sync();
+    mx = part_max[0];
+#pragma unroll
+    for (int i = 1; i < GN_CLUSTER; i++) mx = fmax(mx, part_max[i]);
+    double s = 0.0;
+    for (int64_t i = first; i < count; i += stride) {
+        const double e = exp(ll[i] - mx);
+        if (post) post[i] = e;
+        s += e;
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x < GN_CLUSTER) *cluster.map_shared_rank(&part_sum[rank], threadIdx.x) = s;
+    cluster.sync();
+    if (lse && rank == 0 && threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < GN_CLUSTER; i++) t += part_sum[i];
+        *lse = mx + log(t);
+    }
+}
+
 __global__ void __launch_bounds__(1024) grid_normalize_kernel(const double *__restrict__ ll, int64_t count, double *__restrict__ post,
                                                               double *__restrict__ lse) {
     __shared__ double red[32];

@@ -563,8 +563,11 @@ extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d,
         CA.A = (double *)dmat; CA.ld = np; CA.bstride = per_mat; CA.T = T;
         dim3 gcov((unsigned)(T * (T + 1) / 2), (unsigned)nb);
         cov_sym_kernel<<<gcov, 256, 0, c->stream>>>(CA);
-        dim3 gb((unsigned)rp, (unsigned)((np + 255) / 256), (unsigned)nb);
-        border_fill_kernel<<<gb, 256, 0, c->stream>>>((double *)dmat, np, per_mat, T, (int)rp, (const double *)drhs, (int)r_rhs, n, n);
+        // a last border tile row that runs as thin (8-row) tasks is only ever touched in its first 8 rows
+        int64_t fill_rows = rp;
+        if (c->use_thin && !c->use_multilaunch && r_rhs - (rp - GSUM_TILE) <= 8) fill_rows = rp - GSUM_TILE + 8;
+        dim3 gb((unsigned)fill_rows, (unsigned)((np + 255) / 256), (unsigned)nb);
+        border_fill_kernel<<<gb, 256, 0, c->stream>>>((double *)dmat, np, per_mat, T, (int)fill_rows, (const double *)drhs, (int)r_rhs, n, n);
         LAUNCHED(c, 2);
         int *dinfo; double *dpart;
         c->prof_border_rows = r_rhs;
@@ -609,7 +612,10 @@ extern "C" int gsum_grid_normalize(gsum_ctx *c, const double *ll, int64_t count,
     GSUM_TRY(dev_in(c, WS_IO0, ll, sizeof(double) * count, mem_kind, &dll));
     GSUM_TRY(dev_out(c, WS_IO1, post, sizeof(double) * count, mem_kind, &dpost));
     GSUM_TRY(dev_out(c, WS_IO2, lse, sizeof(double), mem_kind, &dlse));
-    grid_normalize_kernel<<<1, 1024, 0, c->stream>>>((const double *)dll, count, (double *)dpost, (double *)dlse);
+    if (count >= 8192)      // one 8-CTA cluster (DSMEM exchange); tiny grids stay on the single-CTA kernel
+        grid_normalize_cluster_kernel<<<GN_CLUSTER, 1024, 0, c->stream>>>((const double *)dll, count, (double *)dpost, (double *)dlse);
+    else
+        grid_normalize_kernel<<<1, 1024, 0, c->stream>>>((const double *)dll, count, (double *)dpost, (double *)dlse);
     LAUNCHED(c, 1);
     GSUM_TRY(dev_out_finish(c, post, dpost, sizeof(double) * count, mem_kind));
     GSUM_TRY(dev_out_finish(c, lse, dlse, sizeof(double), mem_kind));
