@@ -270,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
         dt_cpu, want = cpu_reference_cells(X, y, orders, ls_vals, q_vals, [(0, 0), (100, 40 * world)])
         got = [ll_host[0, 0], ll_host[100, 40 * world]]
         parity = max(abs(g - w) / abs(w) for g, w in zip(got, want))
-        # roofline of the dominant kernel (the bordered Cholesky launch, chol_hetero_kernel)
+        # roofline of the dominant kernel (the bordered Cholesky launch, chol_hetero_tma_kernel)
         peak = measure_fp64_peak(torch)
         achieved = fact_flops / (fact_ms * 1e-3) * 1e-12 if fact_ms > 0 else 0.0
         # CPU baseline on a bounded sample (~10-15 s)
@@ -291,9 +291,9 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": NCU_TRAFFIC_BYTES * (n_ls_total // world) / 128.0,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one chol_hetero_kernel launch at 128 l per GPU, "
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one chol_hetero_tma_kernel launch at 128 l per GPU, "
                                            "ncu --set full (profiles/r01_ncu_hetero.txt)",
-                         "kernel": "chol_hetero_kernel (FP64 DMMA bordered Cholesky + forward solves, K2+K3; one cooperative launch per step)",
+                         "kernel": "chol_hetero_tma_kernel (FP64 DMMA bordered Cholesky + forward solves, K2+K3; one cooperative launch per step)",
                          "flops_per_step": fact_flops / max(args.steps, 1), "kernel_ms_per_step": fact_ms / max(args.steps, 1),
                          "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "profiles/r01_dgemm_peak.json: 35.5 TFLOP/s at 8192^3)"},

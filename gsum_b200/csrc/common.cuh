@@ -41,6 +41,7 @@ struct gsum_ctx {
     int use_hetero;
     void *ht_gtasks, *ht_ftasks; size_t ht_gcap, ht_fcap; int ht_key[5]; int ht_ng, ht_nf;
     int ht_ready;               // function attributes set / co-residency checked
+    int use_tma, hx_ready;      // GSUM_B200_SCHEDULE=hetero_tma: TMA-fed variant (hetero_tma.cuh)
     int ht_factor_ctas;         // GSUM_B200_FACTOR_CTAS (default HT_FACTOR_CTAS)
 };
 

@@ -10,6 +10,7 @@
 #include "dataflow.cuh"
 #include "pipeline.cuh"
 #include "hetero.cuh"
+#include "hetero_tma.cuh"
 #include <cstdlib>
 
 #define LAUNCHED(ctx, n) ((ctx)->launches += (n))
@@ -44,7 +45,9 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     // per tile column) are kept for comparison and as cross-checks of one another
     c->use_pipeline = (sched && (strcmp(sched, "dataflow") == 0 || strcmp(sched, "multilaunch") == 0)) ? 0 : 1;
     // default schedule: heterogeneous (hetero.cuh); "pipeline" / "dataflow" / "multilaunch" select the older ones
-    c->use_hetero = (!sched || strcmp(sched, "hetero") == 0) ? 1 : 0;
+    c->use_hetero = (!sched || strcmp(sched, "hetero") == 0 || strcmp(sched, "hetero_tma") == 0) ? 1 : 0;
+    // the TMA-fed variant (hetero_tma.cuh) is the default; "hetero" selects the cp.async-fed one
+    c->use_tma = (!sched || strcmp(sched, "hetero_tma") == 0) ? 1 : 0;
     const char *fc = getenv("GSUM_B200_FACTOR_CTAS");
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
     const char *thin = getenv("GSUM_B200_THIN");
@@ -259,6 +262,30 @@ static int ht_upload(gsum_ctx *c, void **buf, size_t *cap, const std::vector<int
     if (bytes) GSUM_CUDA(c, cudaMemcpy(*buf, v.data(), bytes, cudaMemcpyHostToDevice));
     return 0;
 }
+// ---- tensor maps for the TMA-fed variant (driver entry point through the runtime: no -lcuda) -----------------------
+typedef CUresult (*gsum_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int ht_make_map(gsum_ctx *c, CUtensorMap *m, const void *base, uint64_t rows, uint64_t cols, uint64_t ld_elems, uint32_t box_rows) {
+    static gsum_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        GSUM_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+        if (!p || qres != cudaDriverEntryPointSuccess) return gsum_fail(c, -103, "cuTensorMapEncodeTiled not available");
+        fn = (gsum_encode_tiled_fn)p;
+    }
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {ld_elems * sizeof(double)};
+    const cuuint32_t box[2] = {16, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return gsum_fail(c, -103, "cuTensorMapEncodeTiled failed (%d): rows %llu cols %llu ld %llu", (int)r,
+                                            (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld_elems);
+    return 0;
+}
+
 static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
     if (!c->ht_ready) {
         GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
@@ -329,9 +356,29 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * HT_NSTAT * 1024, c->stream);
         D.stats = dbg_stats;
     }
-    void *args[] = {&D};
-    const void *kfn = D.stats ? (const void *)chol_hetero_kernel<true> : (const void *)chol_hetero_kernel<false>;
-    GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HT_THREADS), args, HT_SMEM_BYTES, c->stream));
+    if (c->use_tma) {
+        if (!c->hx_ready) {
+            GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HX_SMEM_BYTES));
+            GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HX_SMEM_BYTES));
+            c->hx_ready = 1;
+        }
+        HeteroMaps maps;
+        const uint64_t rowsA = (uint64_t)(P.bstride / P.ld), rowsW = (uint64_t)(P.wstride / P.ld);
+        GSUM_TRY(ht_make_map(c, &maps.A, P.A, (uint64_t)(batch - 1) * rowsA + (uint64_t)P.T * GSUM_TILE, (uint64_t)P.ld, (uint64_t)P.ld, GSUM_TILE));
+        if (P.Trows > P.T) {
+            const uint64_t wr = (uint64_t)(batch - 1) * rowsW + (uint64_t)(P.Trows - P.T) * GSUM_TILE;
+            GSUM_TRY(ht_make_map(c, &maps.W, P.W, wr, (uint64_t)P.ld, (uint64_t)P.ld, GSUM_TILE));
+            GSUM_TRY(ht_make_map(c, &maps.W8, P.W, wr, (uint64_t)P.ld, (uint64_t)P.ld, 8));
+        } else { maps.W = maps.A; maps.W8 = maps.A; }
+        GSUM_TRY(ht_make_map(c, &maps.M, dM, (uint64_t)batch * P.T * GSUM_TILE, GSUM_TILE, GSUM_TILE, GSUM_TILE));
+        void *args[] = {&D, &maps};
+        const void *kfn = D.stats ? (const void *)chol_hetero_tma_kernel<true> : (const void *)chol_hetero_tma_kernel<false>;
+        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HX_THREADS), args, HX_SMEM_BYTES, c->stream));
+    } else {
+        void *args[] = {&D};
+        const void *kfn = D.stats ? (const void *)chol_hetero_kernel<true> : (const void *)chol_hetero_kernel<false>;
+        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HT_THREADS), args, HT_SMEM_BYTES, c->stream));
+    }
     df_check_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, c->stream>>>(c->df_ctl + 1, P.info, batch, c->df_ctl + 2);
     c->launches += 2;
     GSUM_CUDA(c, cudaPeekAtLastError());
@@ -340,12 +387,13 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         cudaStreamSynchronize(c->stream);
         cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * HT_NSTAT * grid, cudaMemcpyDeviceToHost);
         double f[6] = {0, 0, 0, 0, 0, 0}, a[HT_NSTAT] = {0};
+        const int ngrp = c->use_tma ? HX_NG : HT_NG;
         for (int g = 0; g < nf; g++) for (int wk = 0; wk < nwk; wk++) for (int q = 0; q < 6; q++) f[q] += (double)h[HT_NSTAT * g + wk * 6 + q];
-        for (int g = nf; g < grid; g++) for (int grp = 0; grp < HT_NG; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
+        for (int g = nf; g < grid; g++) for (int grp = 0; grp < ngrp; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
         if (nf) fprintf(stderr, "[ht] factor CTAs %d: cycles/worker %.0f | wait_S %.1f%% | busy %.1f%% (%.0f cycles per diagonal tile: load %.0f, potrf %.0f; %.1f tiles per worker)\n",
                         nf, f[0] / (nwk * nf), 100 * f[1] / f[0], 100 * f[2] / f[0], f[2] / (f[3] + 1e-9), f[4] / (f[3] + 1e-9), f[5] / (f[3] + 1e-9), f[3] / (nwk * nf));
         if (ng) fprintf(stderr, "[ht] GEMM CTAs %d x %d groups: cycles/group %.0f, tasks/group %.1f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% wait_Mkk %.1f%% | math: wait_queue %.1f%% wait_operands %.1f%% wait_Mkk %.1f%% trsm %.1f%% fence+flag %.1f%%\n",
-                        ng, HT_NG, a[5] / (HT_NG * ng), a[11] / (HT_NG * ng), 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0],
+                        ng, ngrp, a[5] / (ngrp * ng), a[11] / (ngrp * ng), 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], 100 * a[4] / a[0],
                         100 * a[6] / a[5], 100 * a[7] / a[5], 100 * a[8] / a[5], 100 * a[9] / a[5], 100 * a[10] / a[5]);
     }
     return 0;

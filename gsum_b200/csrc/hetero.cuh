@@ -52,6 +52,9 @@
 #define HT_SMEM_BYTES (HT_SMEM_DOUBLES * 8)
 #define HT_WORKER_DOUBLES (GSUM_TILE * GSUM_LDS + 3 * GSUM_TILE)     // factor worker: tile + diag + scratch ints
 #define HT_NSTAT 40
+#ifndef HT_LEAN_POTRF
+#define HT_LEAN_POTRF 1
+#endif
 #ifndef HT_FENCE_GEMM
 #define HT_FENCE_GEMM 0
 #endif
@@ -225,6 +228,131 @@ __device__ __forceinline__ void ht_write_mkk(const double *S, const double *dg, 
     }
 }
 
+// POTRF of a 64x64 tile in shared memory (stride GSUM_LDS) by one 128-thread group, blocked by 8 columns, in three
+// short phases per block — written so that neither its speed nor its correctness depends on how ptxas schedules it
+// (tile_potrf_blocked_inl keeps 36 + 8 doubles live per thread and wants ~180 registers; in a kernel whose register
+// target is lower, ptxas serialises its dependency chain and the tile takes 2x longer):
+//   F  warp 3 factors the 8x8 diagonal block in registers (every lane redundantly; chain rsqrt -> mul -> fma per column)
+//      and leaves the block, its reciprocal pivots and diag(L) in a scratch area;
+//   S  one thread per row below the block substitutes its 8 entries against the scratch block (64-cycle steps);
+//   B  rank-8 DMMA update of the trailing 8x8 blocks.
+// Scratch behind the tile: dg[0..63] diag(L), dg[64..127] the factored block (row major 8x8), dg[136..143] 1 / L_jj.
+// *s_fail: failing column (1-based, LAPACK potrf convention), 0 = ok; zeroed by the caller.
+__device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fail) {
+    const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
+#pragma unroll 1
+    for (int cb = 0; cb < 8; cb++) {
+        const int c0 = cb * 8;
+        if (w == 3) {
+            // ---- F ----
+            double a[8][8];
+            const double *blk = S + c0 * GSUM_LDS + c0;
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+#pragma unroll
+                for (int n = 0; n <= m; n += 2) {
+                    if (n + 1 <= m) {
+                        const double2 v = *reinterpret_cast<const double2 *>(blk + m * GSUM_LDS + n);
+                        a[m][n] = v.x; a[m][n + 1] = v.y;
+                    } else a[m][n] = blk[m * GSUM_LDS + n];
+                }
+            int fail = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const double d = a[j][j];
+                if (!(d > 0.0) && fail == 0) fail = c0 + j + 1;
+                const double rs = rsqrt(d);
+                a[j][j] = d * rs;
+                if (lane == j) { rsd[j] = rs; dg[c0 + j] = d * rs; }
+#pragma unroll
+                for (int m = j + 1; m < 8; m++) a[m][j] *= rs;
+#pragma unroll
+                for (int m = j + 1; m < 8; m++)
+#pragma unroll
+                    for (int n = j + 1; n <= m; n++) a[m][n] = fma(-a[m][j], a[n][j], a[m][n]);
+            }
+            // lane m < 8 writes row m of the factored block (scratch and tile)
+#pragma unroll
+            for (int m = 0; m < 8; m++)
+                if (lane == m) {
+#pragma unroll
+                    for (int n = 0; n < 8; n++) {
+                        const double v = n <= m ? a[m][n] : 0.0;
+                        wb[m * 8 + n] = v;
+                        if (n <= m) S[(c0 + m) * GSUM_LDS + c0 + n] = v;
+                    }
+                }
+            if (lane == 0 && fail && *s_fail == 0) *s_fail = fail;
+        }
+        if (cb == 7) break;
+        CONS_SYNC();
+        {
+            // ---- S ----  row rr = c0 + 8 + tid
+            const int rr = c0 + 8 + tid;
+            if (rr < GSUM_TILE) {
+                double *row = S + rr * GSUM_LDS + c0;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(row + c);
+                    x[c] = v.x; x[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double v = x[c];
+#pragma unroll
+                    for (int m = 0; m < c; m++) v = fma(-x[m], wb[c * 8 + m], v);
+                    x[c] = v * rsd[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    double2 v; v.x = x[c]; v.y = x[c + 1];
+                    *reinterpret_cast<double2 *>(row + c) = v;
+                }
+            }
+        }
+        CONS_SYNC();
+        {   // ---- B ----  trailing update of the 8x8 blocks (rb, cb2), cb < cb2 <= rb <= 7; warp w takes blocks w, w+4, ...
+            const int nt = 7 - cb, nblk = nt * (nt + 1) / 2;
+#pragma unroll 1
+            for (int q0 = 0; w + 4 * q0 < nblk; q0 += 4) {
+                double cc[4][2], fa[4][2], fb[4][2];
+                int off[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int blk = w + 4 * (q0 + q);
+                    if (blk < nblk) {
+                        int rbi = 0, rem = blk;
+                        while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
+                        const int rb = cb + 1 + rbi, cb2 = cb + 1 + rem;
+                        off[q] = (rb * 8 + g) * GSUM_LDS + cb2 * 8 + 2 * t;
+                        const double2 v = *reinterpret_cast<const double2 *>(S + off[q]);
+                        cc[q][0] = v.x; cc[q][1] = v.y;
+                        fa[q][0] = S[(rb * 8 + g) * GSUM_LDS + c0 + t]; fa[q][1] = S[(rb * 8 + g) * GSUM_LDS + c0 + 4 + t];
+                        fb[q][0] = S[(cb2 * 8 + g) * GSUM_LDS + c0 + t]; fb[q][1] = S[(cb2 * 8 + g) * GSUM_LDS + c0 + 4 + t];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (w + 4 * (q0 + q) < nblk) {
+                        dmma884(cc[q][0], cc[q][1], -fa[q][0], fb[q][0]);
+                        dmma884(cc[q][0], cc[q][1], -fa[q][1], fb[q][1]);
+                    }
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    if (w + 4 * (q0 + q) < nblk) {
+                        double2 v; v.x = cc[q][0]; v.y = cc[q][1];
+                        *reinterpret_cast<double2 *>(S + off[q]) = v;
+                    }
+            }
+        }
+        CONS_SYNC();
+    }
+    CONS_SYNC();
+}
+
 // ---- factor worker: one 128-thread group of a factor CTA ------------------------------------------------------------
 __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S, long long *st) {
     const BorderedBatch &P = D.P;
@@ -256,7 +384,11 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
         if (tid == 0) *s_fail = 0;
         CONS_SYNC();
         const long long t2 = st ? clock64() : 0;
+#if HT_LEAN_POTRF
+        tile_potrf_lean(S, dg, s_fail);
+#else
         tile_potrf_blocked_inl(S, dg, s_fail);
+#endif
         const long long t3 = st ? clock64() : 0;
         const int fail = *s_fail;
         // Critical path first: M_kk (what the panel tasks of this column wait for), then the flag; L_kk itself, the

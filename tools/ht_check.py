@@ -13,9 +13,10 @@ def grid(mode, reps=1):
     gp = gb.TruncationGP(RBF(0.05) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None)
     gp.fit(X, y, orders=orders)
     return [gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals) for _ in range(reps)]
+mode = os.environ.get("HT_MODE", "hetero")
 ref = grid("pipeline")[0]
 print("pipeline finite:", np.isfinite(ref).all())
-outs = grid("hetero", int(sys.argv[1]) if len(sys.argv) > 1 else 6)
+outs = grid(mode, int(sys.argv[1]) if len(sys.argv) > 1 else 6)
 for r, o in enumerate(outs):
     bad = ~np.isfinite(o)
     d = np.abs(o - ref) / np.abs(ref)

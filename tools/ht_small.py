@@ -1,7 +1,7 @@
 import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["GSUM_B200_SCHEDULE"] = "hetero"
+os.environ["GSUM_B200_SCHEDULE"] = os.environ.get("HT_MODE", "hetero")
 from gsum_b200 import ops
 from sklearn.gaussian_process.kernels import RBF
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256

@@ -12,7 +12,7 @@ from bench import make_inputs, N_POINTS, N_Q
 from gsum_b200 import _lib, ops
 from gsum_b200.helpers import _order_differences
 
-modes = [a for a in sys.argv[1:] if a in ("dataflow", "multilaunch", "pipeline", "hetero")] or ["dataflow", "multilaunch"]
+modes = [a for a in sys.argv[1:] if a in ("dataflow", "multilaunch", "pipeline", "hetero", "hetero_tma")] or ["dataflow", "multilaunch"]
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 10
 n_ls = int(sys.argv[sys.argv.index("--nls") + 1]) if "--nls" in sys.argv else 128
 dev = torch.device("cuda", 0)
@@ -27,7 +27,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 results = {}
 for mode in modes:
     os.environ["GSUM_B200_SCHEDULE"] = mode
-    if "--stats" in sys.argv and mode in ("dataflow", "pipeline", "hetero"):
+    if "--stats" in sys.argv and mode in ("dataflow", "pipeline", "hetero", "hetero_tma"):
         os.environ["GSUM_B200_DF_STATS"] = "1"
     else:
         os.environ.pop("GSUM_B200_DF_STATS", None)

@@ -1,6 +1,8 @@
-run() { echo "== $*"; env "$@" timeout 40 python tools/perf_chol.py hetero --stats --reps 5 2>&1 | tail -3; }
-export GSUM_B200_LIB=$PWD/build/lib_ng3pw2.so
-timeout 40 python tools/ht_check.py 2 | tail -2 || exit 1
-run GSUM_B200_DIAG_DELAY=64
-run GSUM_B200_DIAG_DELAY=64 GSUM_B200_FACTOR_CTAS=20
-timeout 40 python tools/solve_bench.py 2>&1 | tail -2
+run() { echo "== $*"; env "$@" timeout 60 python tools/perf_chol.py $M --stats --reps 5 2>&1 | tail -3; }
+for M in hetero_tma; do export M
+HT_MODE=$M timeout 40 python tools/ht_small.py 256 64 2 2>&1 | tail -2
+HT_MODE=$M timeout 40 python tools/ht_check.py 2 2>&1 | tail -2
+run GSUM_B200_FACTOR_CTAS=16
+run GSUM_B200_FACTOR_CTAS=12
+run GSUM_B200_FACTOR_CTAS=10
+done
