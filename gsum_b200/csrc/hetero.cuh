@@ -62,10 +62,10 @@
 #define HT_FENCE_FACTOR 0
 #endif
 #ifndef HT_FACTOR_CTAS
-#define HT_FACTOR_CTAS 16               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
+#define HT_FACTOR_CTAS 14               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
 #endif
 #ifndef HT_DIAG_DELAY
-#define HT_DIAG_DELAY 64
+#define HT_DIAG_DELAY 0
 #endif
 
 struct HeteroArgs {
@@ -228,65 +228,79 @@ __device__ __forceinline__ void ht_write_mkk(const double *S, const double *dg, 
     }
 }
 
-// POTRF of a 64x64 tile in shared memory (stride GSUM_LDS) by one 128-thread group, blocked by 8 columns, in three
-// short phases per block — written so that neither its speed nor its correctness depends on how ptxas schedules it
-// (tile_potrf_blocked_inl keeps 36 + 8 doubles live per thread and wants ~180 registers; in a kernel whose register
-// target is lower, ptxas serialises its dependency chain and the tile takes 2x longer):
+// POTRF of a 64x64 tile in shared memory (stride GSUM_LDS) by one 128-thread group, blocked by 8 columns, written so
+// that neither its speed nor its correctness depends on how ptxas schedules it (tile_potrf_blocked_inl keeps 36 + 8
+// doubles live per thread and wants ~180 registers; in a kernel whose register target is lower, ptxas serialises its
+// dependency chain and the tile takes 2x longer).  Per 8-column block:
 //   F  warp 3 factors the 8x8 diagonal block in registers (every lane redundantly; chain rsqrt -> mul -> fma per column)
 //      and leaves the block, its reciprocal pivots and diag(L) in a scratch area;
 //   S  one thread per row below the block substitutes its 8 entries against the scratch block (64-cycle steps);
-//   B  rank-8 DMMA update of the trailing 8x8 blocks.
+//   B  rank-8 DMMA update of the trailing 8x8 blocks — with one block of look-ahead: warp 3 updates the NEXT diagonal
+//      block first and factors it (F of the next step) while warps 0-2 update the rest.
 // Scratch behind the tile: dg[0..63] diag(L), dg[64..127] the factored block (row major 8x8), dg[136..143] 1 / L_jj.
 // *s_fail: failing column (1-based, LAPACK potrf convention), 0 = ok; zeroed by the caller.
+__device__ __forceinline__ void potrf_lean_factor_block(double *S, double *dg, int *s_fail, int cb, int lane) {
+    const int c0 = cb * 8;
+    double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
+    double a[8][8];
+    const double *blk = S + c0 * GSUM_LDS + c0;
+#pragma unroll
+    for (int m = 0; m < 8; m++)
+#pragma unroll
+        for (int n = 0; n <= m; n += 2) {
+            if (n + 1 <= m) {
+                const double2 v = *reinterpret_cast<const double2 *>(blk + m * GSUM_LDS + n);
+                a[m][n] = v.x; a[m][n + 1] = v.y;
+            } else a[m][n] = blk[m * GSUM_LDS + n];
+        }
+    int fail = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const double d = a[j][j];
+        if (!(d > 0.0) && fail == 0) fail = c0 + j + 1;
+        const double rs = rsqrt(d);
+        a[j][j] = d * rs;
+        if (lane == j) { rsd[j] = rs; dg[c0 + j] = d * rs; }
+#pragma unroll
+        for (int m = j + 1; m < 8; m++) a[m][j] *= rs;
+#pragma unroll
+        for (int m = j + 1; m < 8; m++)
+#pragma unroll
+            for (int n = j + 1; n <= m; n++) a[m][n] = fma(-a[m][j], a[n][j], a[m][n]);
+    }
+    // lane m < 8 writes row m of the factored block (scratch and tile)
+#pragma unroll
+    for (int m = 0; m < 8; m++)
+        if (lane == m) {
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+                const double v = n <= m ? a[m][n] : 0.0;
+                wb[m * 8 + n] = v;
+                if (n <= m) S[(c0 + m) * GSUM_LDS + c0 + n] = v;
+            }
+        }
+    if (lane == 0 && fail && *s_fail == 0) *s_fail = fail;
+}
+// rank-8 update of the 8x8 block (rb, cb2) by column block cb: one DMMA pair per warp
+__device__ __forceinline__ void potrf_lean_update_block(double *S, int cb, int rb, int cb2, int g, int t) {
+    const int c0 = cb * 8, off = (rb * 8 + g) * GSUM_LDS + cb2 * 8 + 2 * t;
+    const double2 v = *reinterpret_cast<const double2 *>(S + off);
+    double c0v = v.x, c1v = v.y;
+    const double fa0 = S[(rb * 8 + g) * GSUM_LDS + c0 + t], fa1 = S[(rb * 8 + g) * GSUM_LDS + c0 + 4 + t];
+    const double fb0 = S[(cb2 * 8 + g) * GSUM_LDS + c0 + t], fb1 = S[(cb2 * 8 + g) * GSUM_LDS + c0 + 4 + t];
+    dmma884(c0v, c1v, -fa0, fb0);
+    dmma884(c0v, c1v, -fa1, fb1);
+    double2 o; o.x = c0v; o.y = c1v;
+    *reinterpret_cast<double2 *>(S + off) = o;
+}
 __device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fail) {
     const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
-    double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
+    const double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
+    if (w == 3) potrf_lean_factor_block(S, dg, s_fail, 0, lane);
 #pragma unroll 1
-    for (int cb = 0; cb < 8; cb++) {
+    for (int cb = 0; cb < 7; cb++) {
         const int c0 = cb * 8;
-        if (w == 3) {
-            // ---- F ----
-            double a[8][8];
-            const double *blk = S + c0 * GSUM_LDS + c0;
-#pragma unroll
-            for (int m = 0; m < 8; m++)
-#pragma unroll
-                for (int n = 0; n <= m; n += 2) {
-                    if (n + 1 <= m) {
-                        const double2 v = *reinterpret_cast<const double2 *>(blk + m * GSUM_LDS + n);
-                        a[m][n] = v.x; a[m][n + 1] = v.y;
-                    } else a[m][n] = blk[m * GSUM_LDS + n];
-                }
-            int fail = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const double d = a[j][j];
-                if (!(d > 0.0) && fail == 0) fail = c0 + j + 1;
-                const double rs = rsqrt(d);
-                a[j][j] = d * rs;
-                if (lane == j) { rsd[j] = rs; dg[c0 + j] = d * rs; }
-#pragma unroll
-                for (int m = j + 1; m < 8; m++) a[m][j] *= rs;
-#pragma unroll
-                for (int m = j + 1; m < 8; m++)
-#pragma unroll
-                    for (int n = j + 1; n <= m; n++) a[m][n] = fma(-a[m][j], a[n][j], a[m][n]);
-            }
-            // lane m < 8 writes row m of the factored block (scratch and tile)
-#pragma unroll
-            for (int m = 0; m < 8; m++)
-                if (lane == m) {
-#pragma unroll
-                    for (int n = 0; n < 8; n++) {
-                        const double v = n <= m ? a[m][n] : 0.0;
-                        wb[m * 8 + n] = v;
-                        if (n <= m) S[(c0 + m) * GSUM_LDS + c0 + n] = v;
-                    }
-                }
-            if (lane == 0 && fail && *s_fail == 0) *s_fail = fail;
-        }
-        if (cb == 7) break;
         CONS_SYNC();
         {
             // ---- S ----  row rr = c0 + 8 + tid
@@ -314,41 +328,20 @@ __device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fa
             }
         }
         CONS_SYNC();
-        {   // ---- B ----  trailing update of the 8x8 blocks (rb, cb2), cb < cb2 <= rb <= 7; warp w takes blocks w, w+4, ...
+        // ---- B with look-ahead ----  blocks (rb, cb2), cb < cb2 <= rb <= 7, numbered row by row; block 0 = (cb+1, cb+1)
+        if (w == 3) {
+            potrf_lean_update_block(S, cb, cb + 1, cb + 1, g, t);
+            __syncwarp();
+            potrf_lean_factor_block(S, dg, s_fail, cb + 1, lane);
+        } else {
             const int nt = 7 - cb, nblk = nt * (nt + 1) / 2;
 #pragma unroll 1
-            for (int q0 = 0; w + 4 * q0 < nblk; q0 += 4) {
-                double cc[4][2], fa[4][2], fb[4][2];
-                int off[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int blk = w + 4 * (q0 + q);
-                    if (blk < nblk) {
-                        int rbi = 0, rem = blk;
-                        while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
-                        const int rb = cb + 1 + rbi, cb2 = cb + 1 + rem;
-                        off[q] = (rb * 8 + g) * GSUM_LDS + cb2 * 8 + 2 * t;
-                        const double2 v = *reinterpret_cast<const double2 *>(S + off[q]);
-                        cc[q][0] = v.x; cc[q][1] = v.y;
-                        fa[q][0] = S[(rb * 8 + g) * GSUM_LDS + c0 + t]; fa[q][1] = S[(rb * 8 + g) * GSUM_LDS + c0 + 4 + t];
-                        fb[q][0] = S[(cb2 * 8 + g) * GSUM_LDS + c0 + t]; fb[q][1] = S[(cb2 * 8 + g) * GSUM_LDS + c0 + 4 + t];
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (w + 4 * (q0 + q) < nblk) {
-                        dmma884(cc[q][0], cc[q][1], -fa[q][0], fb[q][0]);
-                        dmma884(cc[q][0], cc[q][1], -fa[q][1], fb[q][1]);
-                    }
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    if (w + 4 * (q0 + q) < nblk) {
-                        double2 v; v.x = cc[q][0]; v.y = cc[q][1];
-                        *reinterpret_cast<double2 *>(S + off[q]) = v;
-                    }
+            for (int blk = 1 + w; blk < nblk; blk += 3) {
+                int rbi = 0, rem = blk;
+                while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
+                potrf_lean_update_block(S, cb, cb + 1 + rbi, cb + 1 + rem, g, t);
             }
         }
-        CONS_SYNC();
     }
     CONS_SYNC();
 }
