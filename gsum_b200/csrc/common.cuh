@@ -12,6 +12,7 @@
 #define GSUM_KH 32              // K depth of one pipeline stage (half a tile)
 #define GSUM_LDH 36             // padded smem row stride for 32-wide half-slabs: 36 % 16 == 4
 
+#define GSUM_NWS 32             // workspace slots
 struct gsum_ctx {
     int device;
     cudaStream_t stream;
@@ -19,8 +20,8 @@ struct gsum_ctx {
     int sm_count;
     char err[512];
     // grow-only device workspace arena (ctx-scoped; freed by gsum_ctx_destroy)
-    void *ws[24];
-    size_t ws_bytes[24];
+    void *ws[GSUM_NWS];
+    size_t ws_bytes[GSUM_NWS];
     int64_t launches;           // kernels launched by this library on this context
     int *d_flag;                // small device int scratch
     // optional profiling of the factorisation phase (bench.py roofline): event pairs on ctx->stream

@@ -7,6 +7,7 @@
 #include "lml.cuh"
 #include "solve.cuh"
 #include "diag.cuh"
+#include "grad.cuh"
 #include "dataflow.cuh"
 #include "pipeline.cuh"
 #include "hetero.cuh"
@@ -17,7 +18,7 @@
 
 enum {
     WS_X = 0, WS_XS, WS_DY, WS_REF, WS_ORD, WS_LS, WS_Q, WS_DETF, WS_MAT, WS_RHS, WS_GRAM, WS_LOGDET, WS_INFO,
-    WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_MKK
+    WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_MKK, WS_G0, WS_G1, WS_G2, WS_G3, WS_G4, WS_G5
 };
 
 extern "C" int gsum_version(void) { return 100; }
@@ -60,7 +61,7 @@ extern "C" int gsum_ctx_destroy(gsum_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    for (int i = 0; i < 24; i++) if (c->ws[i]) cudaFree(c->ws[i]);
+    for (int i = 0; i < GSUM_NWS; i++) if (c->ws[i]) cudaFree(c->ws[i]);
     if (c->df_tasks) cudaFree(c->df_tasks);
     if (c->ht_gtasks) cudaFree(c->ht_gtasks);
     if (c->ht_ftasks) cudaFree(c->ht_ftasks);
@@ -741,6 +742,61 @@ extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B
         launch_transpose_out(c, (const double *)dW2, np, n, nrhs, 1, 1.0, nullptr, dBout);
     }
     GSUM_TRY(dev_out_finish(c, B, dBout, sizeof(double) * n * nrhs, mem_kind));
+    return finish(c, mem_kind);
+}
+
+// ---- gradient terms of the likelihood (gsum/models.py:957-1056) ------------------------------------------------
+extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
+                                   const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                                   double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind) {
+    if (!c || !X || !RHS || !ls || !G || !H || !tr || !logdet || !info)
+        return gsum_fail(c, -1, "gsum_lml_grad_terms: null argument");
+    if (n <= 0 || d <= 0 || d > COV_MAXD || r < 1 || r > GRAD_MAXR || (ls_dim != 1 && ls_dim != d))
+        return gsum_fail(c, -1, "gsum_lml_grad_terms: bad shape (d<=%d, r<=%d, ls_dim in {1,d})", COV_MAXD, GRAD_MAXR);
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int P = ls_dim + 2;
+    const void *dX, *dRHS, *dls;
+    GSUM_TRY(dev_in(c, WS_G0, X, sizeof(double) * n * d, mem_kind, &dX));
+    GSUM_TRY(dev_in(c, WS_G1, RHS, sizeof(double) * n * r, mem_kind, &dRHS));
+    GSUM_TRY(dev_in(c, WS_G2, ls, sizeof(double) * ls_dim, mem_kind, &dls));
+    void *dR, *dB, *dsm;
+    const int64_t ldz = r + n;
+    GSUM_TRY(gsum_ws(c, WS_G3, sizeof(double) * n * n, &dR));
+    GSUM_TRY(gsum_ws(c, WS_G4, sizeof(double) * n * ldz, &dB));
+    // small outputs and per-row partials: G (r*r) | H (P*r*r) | tr (P) | logdet (1) | Y (P*n*GRAD_MAXR) | trow (P*n) | info
+    const size_t nsmall = (size_t)r * r + (size_t)P * r * r + P + 1;
+    GSUM_TRY(gsum_ws(c, WS_G5, sizeof(double) * (nsmall + (size_t)P * n * GRAD_MAXR + (size_t)P * n) + 64, &dsm));
+    double *dG = (double *)dsm, *dH = dG + r * r, *dtr = dH + (size_t)P * r * r, *dld = dtr + P, *dY = dld + 1,
+           *dtrow = dY + (size_t)P * n * GRAD_MAXR;
+    int32_t *dinfo = (int32_t *)(dtrow + (size_t)P * n);
+    // R = c * rbf + noise I (diagonal exactly c + noise), then + nugget, as gsum/models.py:960-963
+    GSUM_TRY(gsum_kernel_matrix(c, (const double *)dX, n, nullptr, 0, d, (const double *)dls, ls_dim, constant, noise, (double *)dR, GSUM_MEM_DEVICE));
+    add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((double *)dR, n, n, nugget);
+    LAUNCHED(c, 1);
+    GSUM_TRY(gsum_cholesky(c, (double *)dR, n, 1, dinfo, dld, GSUM_MEM_DEVICE));
+    grad_stage_kernel<<<dim3((unsigned)((ldz + 255) / 256), (unsigned)n), 256, 0, c->stream>>>((const double *)dRHS, n, r, (double *)dB);
+    LAUNCHED(c, 1);
+    GSUM_TRY(gsum_cho_solve(c, (const double *)dR, n, (double *)dB, ldz, 0, GSUM_MEM_DEVICE));       // [Z | R^{-1}]
+    // scaled coordinates (gsum_kernel_matrix left X / ls in WS_XS)
+    const double *dXS = (const double *)c->ws[WS_XS];
+    const size_t shbytes = sizeof(double) * (128 * COV_MAXD + 128 * GRAD_MAXR);
+    grad_rows_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)P), 128, shbytes, c->stream>>>(dXS, n, d, ls_dim, constant, noise, (const double *)dB,
+                                                                                               ldz, r, dY, dtrow);
+    grad_reduce_kernel<<<P + 1, 256, 0, c->stream>>>((const double *)dB, ldz, (const double *)dRHS, dY, dtrow, n, r, P, dH, dtr, dG);
+    LAUNCHED(c, 2);
+    if (mem_kind == GSUM_MEM_DEVICE) {
+        GSUM_CUDA(c, cudaMemcpyAsync(G, dG, sizeof(double) * r * r, cudaMemcpyDeviceToDevice, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(H, dH, sizeof(double) * P * r * r, cudaMemcpyDeviceToDevice, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(tr, dtr, sizeof(double) * P, cudaMemcpyDeviceToDevice, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(logdet, dld, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(info, dinfo, sizeof(int32_t), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+        GSUM_CUDA(c, cudaMemcpyAsync(G, dG, sizeof(double) * r * r, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(H, dH, sizeof(double) * P * r * r, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(tr, dtr, sizeof(double) * P, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(logdet, dld, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(info, dinfo, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    }
     return finish(c, mem_kind);
 }
 

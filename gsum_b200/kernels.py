@@ -16,7 +16,7 @@ from dataclasses import dataclass
 import numpy as np
 from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Product, Sum, WhiteKernel
 
-__all__ = ["KernelDesc", "flatten_kernel"]
+__all__ = ["KernelDesc", "flatten_kernel", "theta_layout"]
 
 
 @dataclass
@@ -70,3 +70,33 @@ def flatten_kernel(kernel) -> KernelDesc:
     if ls is None:
         raise NotImplementedError(f"gsum_b200: kernel {kernel!r} has no RBF factor")
     return KernelDesc(constant=c, length_scale=ls, noise=noise)
+
+
+def theta_layout(kernel, d):
+    """For every entry of ``kernel.theta`` (sklearn order: the tree is walked k1 before k2, fixed hyperparameters are
+    skipped): ``(slot, weight)`` with slot 0 = constant, 1 + q = length scale q (q = 0 when isotropic), 1 + ls_dim =
+    noise level — the order of the device's derivative matrices — and d/dtheta_i = weight * d/d(slot).  The weight is 1
+    except for one of several WhiteKernel terms (its share of the total noise level)."""
+    desc = flatten_kernel(kernel)
+    ls_dim = desc.ls_for(d).shape[0]
+    out = []
+
+    def walk(k):
+        if isinstance(k, (Sum, Product)):
+            walk(k.k1)
+            walk(k.k2)
+            return
+        for hp in k.hyperparameters:
+            if hp.fixed:
+                continue
+            if type(k) is ConstantKernel:
+                out.append((0, 1.0))
+            elif type(k) is RBF:
+                out.extend((1 + q, 1.0) for q in range(hp.n_elements))
+            elif isinstance(k, WhiteKernel):
+                out.append((1 + ls_dim, float(k.noise_level) / desc.noise if desc.noise > 0 else 0.0))
+            else:
+                raise NotImplementedError(f"gsum_b200: no analytic gradient for {k!r}")
+
+    walk(kernel)
+    return out

@@ -25,7 +25,7 @@ from sklearn.utils import check_random_state
 from . import ops
 from ._lib import PREDICT_COV, PREDICT_MEAN, PREDICT_VAR
 from .helpers import _order_differences, coefficients, geometric_sum
-from .kernels import flatten_kernel
+from .kernels import flatten_kernel, theta_layout
 
 __all__ = ["BaseConjugateProcess", "ConjugateGaussianProcess", "ConjugateStudentProcess", "TruncationProcess",
            "TruncationGP", "TruncationTP"]
@@ -210,17 +210,21 @@ class BaseConjugateProcess:
         return self
 
     def _calibrate_kernel(self):
-        """gsum/models.py:630-669.  The reference passes analytic gradients to L-BFGS; here the gradient of the device
-        objective is taken by central differences in log-theta (and the ragged-array crash of models.py:664 on
-        numpy >= 1.24 does not exist)."""
+        """gsum/models.py:630-669: L-BFGS on -log_marginal_likelihood with the analytic gradient (device contractions,
+        _lml_gradient).  The Student-t evidence has no analytic gradient on the device path yet: its objective is
+        differentiated by central differences in log-theta.  (The ragged-array crash of models.py:664 on numpy >= 1.24
+        does not exist here.)"""
         self._lml_from_optimizer = None
         if self.optimizer is None or self.kernel_.n_dims == 0:
             return
 
         def obj_func(theta, eval_gradient=True):
-            f0 = -self.log_marginal_likelihood(theta)
             if not eval_gradient:
-                return f0
+                return -self.log_marginal_likelihood(theta)
+            if not self._student:
+                lml, grad = self.log_marginal_likelihood(theta, eval_gradient=True)
+                return -lml, -grad
+            f0 = -self.log_marginal_likelihood(theta)
             grad = np.empty(len(theta))
             h = 1e-4
             for i in range(len(theta)):
@@ -255,9 +259,80 @@ class BaseConjugateProcess:
         return theta_opt, func_min
 
     # ---- likelihood (gsum/models.py:912-1057 / 1184-1273) ----
+    def _lml_gradient(self, theta, X, y):
+        """(log-likelihood, gradient) of the Gaussian conjugate likelihood, gsum/models.py:957-1056 (eval_gradient=True).
+
+        The device returns the Gram G = RHS^T R^-1 RHS of RHS = [basis | curves], the contractions H_p = Z^T dR_p Z
+        (Z = R^-1 RHS) and t_p = trace(R^-1 dR_p) for the derivative of R with respect to each log-hyperparameter
+        (ops.lml_grad_terms); every vector the reference contracts with dR is R^-1 (RHS a) for a small coefficient
+        vector a, so its formulas become quadratic forms in G and H_p:
+          compute_center  models.py:201-230,  compute_scale_sq  419-455,  compute_cov_factor  501-503,
+          dK = var dR + dvar R  1024-1025,  0.5 (alpha alpha^T - K^-1) : dK - dmean^T alpha  1041-1056."""
+        if self._student:
+            raise NotImplementedError("gsum_b200: the analytic gradient of the Student-t evidence (gsum/models.py:1260-1271) "
+                                      "is not implemented on the device path")
+        self._check_decomposition()
+        theta = np.asarray(theta, dtype=np.float64)
+        kernel = self._active_kernel().clone_with_theta(theta)
+        X = self.X_train_ if X is None else X
+        y = self.y_train_ if y is None else y
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None]
+        N, nc = y.shape
+        k = flatten_kernel(kernel)
+        layout = theta_layout(kernel, X.shape[1])
+        if len(layout) != len(theta):
+            raise ValueError("theta does not match the kernel's free hyperparameters")
+        rhs = np.concatenate([np.ones((N, 1)), y], axis=1)
+        G, H, tr, logdet, info = ops.lml_grad_terms(X, rhs, k.ls_for(X.shape[1]), constant=k.constant, noise=k.noise, nugget=self.nugget)
+        if info != 0:
+            return -np.inf, np.zeros_like(theta)                                  # models.py:970-972
+        pri = self._priors()
+        eta0, V0, df0, scale0 = pri["center0"], pri["disp0"], pri["df0"], pri["scale0"]
+        r = nc + 1
+        eB = np.zeros(r); eB[0] = 1.0
+        eavg = np.zeros(r); eavg[1:] = 1.0 / nc
+        E = np.eye(r)[1:]                                                         # coefficient vectors of the curves
+        quad_form = lambda M, a, b: a @ M @ b
+        # posterior dispersion / center and d(center) (models.py:201-230, 260-277)
+        if V0 == 0:
+            V, eta = 0.0, eta0
+            dcenter = np.zeros(len(H))
+        else:
+            V = 1.0 / (1.0 / V0 + nc * G[0, 0])
+            eta = V * (eta0 / V0 + nc * quad_form(G, eB, eavg))
+            dcenter = np.array([nc * V * quad_form(Hp, eB, eta * eB - eavg) for Hp in H])
+        df = df0 + N * nc
+        # scale^2 and its derivative (models.py:419-455)
+        if np.isinf(df0):
+            scale2, dscale2 = scale0 ** 2, np.zeros(len(H))
+        else:
+            Ec = E - eavg[None, :]                                                # centred curves
+            quad = sum(quad_form(G, e, e) for e in Ec)
+            ac = eavg - eta0 * eB                                                 # avg_y - B center0
+            aw = nc * (ac - nc * V * quad_form(G, eB, ac) * eB)                   # mat_invR_avg_yc = Z aw
+            quad2 = quad_form(G, ac, aw)
+            scale2 = (df0 * scale0 ** 2 + quad + quad2) / df
+            dscale2 = np.array([-(sum(quad_form(Hp, e, e) for e in Ec) + quad_form(Hp, aw, aw) / nc) / df for Hp in H])
+        cov_factor = (lambda s2: s2) if np.isinf(df) else (lambda s2: df * s2 / (df - 2))
+        var, dvar = cov_factor(scale2), cov_factor(dscale2)
+        Bk = E - eta * eB[None, :]                                                # y_train_k = RHS b_k
+        yKy = sum(quad_form(G, b, b) for b in Bk) / var                           # sum_k y_k^T K^-1 y_k
+        ll = -0.5 * yKy - 0.5 * nc * (N * np.log(var) + logdet) - 0.5 * nc * N * np.log(2 * np.pi)
+        grad_dev = np.empty(len(H))
+        for p_, Hp in enumerate(H):
+            aKa = sum(quad_form(Hp, b, b) for b in Bk) / var + dvar[p_] * yKy / var          # sum_k alpha^T dK alpha
+            trK = tr[p_] + dvar[p_] * N / var                                                 # trace(K^-1 dK)
+            dmean_alpha = dcenter[p_] * sum(quad_form(G, eB, b) for b in Bk) / var            # sum_k dmean^T alpha_k
+            grad_dev[p_] = 0.5 * aKa - 0.5 * nc * trK - dmean_alpha
+        grad = np.array([w * grad_dev[slot] for slot, w in layout])
+        return float(ll), grad
+
     def _lml(self, theta, eval_gradient, X, y):
         if eval_gradient:
-            raise NotImplementedError("gsum_b200: analytic likelihood gradients are not implemented on the device path")
+            return self._lml_gradient(theta, X, y)
         self._check_decomposition()
         kernel = self._active_kernel().clone_with_theta(theta)
         X = self.X_train_ if X is None else X
@@ -569,10 +644,8 @@ class TruncationProcess:
     def log_marginal_likelihood(self, theta, eval_gradient=False, X=None, y=None, orders=None, **ratio_kws):
         """ll of the partial sums for kernel hyperparameters `theta` and ratio keyword(s) (gsum/models.py:1485-1507).
 
-        Like the reference, only the scalar is returned even when eval_gradient=True is requested there; here
-        eval_gradient=True raises (no analytic gradients on the device path)."""
-        if eval_gradient:
-            raise NotImplementedError("gsum_b200: analytic likelihood gradients are not implemented on the device path")
+        Like the reference (models.py:1498-1507), only the scalar is returned even when eval_gradient=True is
+        requested: the reference computes the coefficient process' gradient and drops it."""
         cp = self.coeffs_process
         cp._check_decomposition()
         X, dy, orders_in = self._grid_inputs(X, y, orders)

@@ -97,6 +97,17 @@ int gsum_lml_grid(gsum_ctx *ctx, const double *X, int64_t n, int32_t d, const do
                   double noise, double nugget, double center0, double disp0, double df0, double scale0,
                   int32_t student, double *ll, double *logdet, int32_t *status, int32_t mem_kind);
 
+/* Gradient terms of the conjugate-GP likelihood — the device half of log_marginal_likelihood(theta, eval_gradient=True)
+ * (gsum/models.py:957-1056: `kernel(X, eval_gradient=True)`, `cho_solve(L, eye(N))` at 1045, the einsum contractions of
+ * compute_center 227-229, compute_scale_sq 451-454 and 1047-1048).  With RHS = [basis | y_1..y_nc] (n, r),
+ * Z = R^{-1} RHS and dR_p = dR/dlog(theta_p), p = [constant, length scale(s), noise level] (P = ls_dim + 2):
+ *   G (r, r) = RHS^T Z,   H (P, r, r) = Z^T dR_p Z,   tr (P,) = trace(R^{-1} dR_p),   logdet = log det R,
+ *   info = 0 or the first non-positive pivot (then the other outputs are undefined; the reference returns -inf, 0).
+ * R = constant * RBF_ls(X) + (noise + nugget) I as in gsum_lml_grid. */
+int gsum_lml_grad_terms(gsum_ctx *ctx, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
+                        const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                        double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind);
+
 /* On-device normalisation of a gathered grid (docs/notebooks/correlated_EFT_publication.ipynb cell 54):
  * post = exp(ll - max(ll)); lse = log(sum(exp(ll))).  ll, post: (count,); lse: 1 double or NULL. */
 int gsum_grid_normalize(gsum_ctx *ctx, const double *ll, int64_t count, double *post, double *lse, int32_t mem_kind);

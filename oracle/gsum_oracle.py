@@ -204,6 +204,66 @@ def gaussian_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis
     return ll.sum(-1)                                           # :1039
 
 
+def gaussian_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis):
+    """gsum/models.py:912-1057 with eval_gradient=True (decomposition='cholesky'): (log-likelihood, d/dtheta).
+
+    The kernel gradient comes from sklearn (`kernel(X, eval_gradient=True)`, models.py:957-958); the conjugate updates
+    carry their own derivatives: compute_center (models.py:222-230), compute_scale_sq (450-455), compute_cov_factor
+    applied to d(scale^2) (997), and the chain rule of models.py:1024-1025, 1041-1056."""
+    k = kernel.clone_with_theta(theta)
+    R, dR = k(X, eval_gradient=True)                            # :957-958
+    R[np.diag_indices_from(R)] += nugget                        # :963
+    try:
+        L_R = cholesky(R)
+    except np.linalg.LinAlgError:
+        return -np.inf, np.zeros_like(theta)                    # :970-972
+    if y.ndim == 1:
+        y = y[:, None]
+    p = priors
+    df = compute_df(y, p.df0)
+    basis = basis_fn(X)
+    ny, N = _num_y(y), R.shape[0]
+    # compute_center with gradient (:201-230)
+    if np.all(p.disp0 == 0):
+        center, grad_center = np.copy(p.center0), np.zeros((*p.center0.shape, dR.shape[-1]))
+    else:
+        center = compute_center(y, L_R, basis, p.center0, p.disp0)
+        disp = compute_disp(y, L_R, basis, p.disp0)
+        invR_basis = solve_sqrt(L_R, basis)
+        invR_diff = solve_sqrt(L_R, basis @ center - _avg_y(y))
+        grad_center = ny * disp @ np.einsum('ji,jkp,k->ip', invR_basis, dR, invR_diff)
+    # compute_scale_sq with gradient (:419-455)
+    scale2 = compute_scale_sq(y, L_R, basis, p.center0, p.disp0, p.df0, p.scale0)
+    if p.df0 == np.inf:
+        dscale2 = np.zeros(dR.shape[-1])
+    else:
+        avg_y = _avg_y(y)
+        y_centered = y - avg_y[:, None]
+        invR_yc = solve_sqrt(L_R, y_centered)
+        avg_y_centered = avg_y - basis @ p.center0
+        disp = compute_disp(y, L_R, basis, p.disp0)
+        mat = np.eye(N) - ny * solve_sqrt(L_R, basis) @ disp @ basis.T
+        mat_invR_avg_yc = ny * mat @ solve_sqrt(L_R, avg_y_centered)
+        dscale2 = -np.einsum('ji,jkp,ki->p', invR_yc, dR, invR_yc)
+        dscale2 -= np.einsum('i,ijp,j->p', mat_invR_avg_yc, dR, mat_invR_avg_yc) / ny
+        dscale2 /= df
+    grad_var = compute_cov_factor(dscale2, df)                  # :997
+    grad_mean = basis @ grad_center                             # :999
+    mean = basis @ center
+    var = compute_cov_factor(scale2, df)
+    L = np.sqrt(var) * L_R
+    logdet_K = 2 * np.log(np.diag(L)).sum()
+    K_gradient = var * dR + grad_var * R[:, :, None]            # :1024-1025
+    y_train = y - mean[:, None]
+    alpha = solve_sqrt(L, y_train)
+    ll = -0.5 * np.einsum("ik,ik->k", y_train, alpha) - 0.5 * logdet_K - N / 2 * np.log(2 * np.pi)
+    tmp = np.einsum("ik,jk->ijk", alpha, alpha)                 # :1042
+    tmp -= solve_sqrt(L, np.eye(N))[:, :, np.newaxis]           # :1045
+    grad_dims = 0.5 * np.einsum("ijl,ijk->kl", tmp, K_gradient)  # :1049-1050
+    grad_dims -= grad_mean.T @ alpha                            # :1053
+    return ll.sum(-1), grad_dims.sum(-1)                        # :1056
+
+
 def student_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis):
     """gsum/models.py:1184-1273 (eval_gradient=False) — exact normal-inverse-χ² evidence."""
     ny = _num_y(y)

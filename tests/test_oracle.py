@@ -151,3 +151,47 @@ def test_series_helpers_roundtrip():
     with pytest.raises(ValueError):
         o.geometric_sum(x, 3, 2)
     assert o.cartesian(np.arange(2), np.arange(3)).tolist() == [[0, 0], [0, 1], [0, 2], [1, 0], [1, 1], [1, 2]]
+
+
+# ---- analytic likelihood gradient (gsum/models.py:957-1056) ------------------------------------------
+@pytest.mark.parametrize("ip", range(4))
+def test_c1_gradient_oracle(golden, ip):
+    """The oracle's restatement of log_marginal_likelihood(theta, eval_gradient=True) against the reference's own output,
+    all three hyperparameters of C * RBF + White free, every prior branch."""
+    g = golden("c1_gradient")
+    p = o.Priors(**prior_kwargs(g["priors"][ip]))
+    kern = C(1.5) * RBF(0.2) + WhiteKernel(1e-4)
+    for t, lml, grad in zip(g["thetas"], g[f"g{ip}_lml"], g[f"g{ip}_grad"]):
+        ll, gr = o.gaussian_lml_gradient(kern, t, g["X"], g["y"], p, 1e-10)
+        assert ll == pytest.approx(lml, rel=1e-12)
+        assert relerr(gr, grad) < 1e-9
+        # and the value agrees with the gradient-free path
+        assert ll == pytest.approx(o.gaussian_lml(kern, t, g["X"], g["y"], p, 1e-10), rel=1e-12)
+
+
+def test_gradient_oracle_aniso_and_finite_difference(golden):
+    g = golden("c1_gradient")
+    p = o.Priors(**prior_kwargs(g["priors"][2]))
+    kern = C(1.2) * RBF([0.3, 0.15]) + WhiteKernel(1e-4)
+    for t, lml, grad in zip(g["aniso_thetas"], g["aniso_lml"], g["aniso_grad"]):
+        ll, gr = o.gaussian_lml_gradient(kern, t, g["X2"], g["y2"], p, 1e-10)
+        assert ll == pytest.approx(lml, rel=1e-12) and relerr(gr, grad) < 1e-9
+    # the analytic gradient is the derivative of the likelihood (central differences in log-theta)
+    t0 = g["aniso_thetas"][1]
+    _, gr = o.gaussian_lml_gradient(kern, t0, g["X2"], g["y2"], p, 1e-10)
+    for i in range(len(t0)):
+        tp, tm = t0.copy(), t0.copy()
+        tp[i] += 1e-4
+        tm[i] -= 1e-4
+        fd = (o.gaussian_lml(kern, tp, g["X2"], g["y2"], p, 1e-10) - o.gaussian_lml(kern, tm, g["X2"], g["y2"], p, 1e-10)) / 2e-4
+        assert gr[i] == pytest.approx(fd, rel=1e-3)      # difference quotient of an ill-conditioned likelihood: ~1e-4 noise
+
+
+def test_theta_layout_matches_sklearn_order():
+    """The host-side map from kernel.theta entries to the device's derivative slots follows sklearn's ordering."""
+    from gsum_b200.kernels import theta_layout
+    assert theta_layout(C(1.5) * RBF(0.2) + WhiteKernel(1e-4), 1) == [(0, 1.0), (1, 1.0), (2, 1.0)]
+    assert theta_layout(C(1.5, 'fixed') * RBF(0.2) + WhiteKernel(1e-4, 'fixed'), 1) == [(1, 1.0)]
+    assert theta_layout(RBF([0.3, 0.1]) * C(2.0) + WhiteKernel(1e-4), 2) == [(1, 1.0), (2, 1.0), (0, 1.0), (3, 1.0)]
+    k = C(1.5) * RBF(0.2) + WhiteKernel(1e-4)
+    assert len(theta_layout(k, 1)) == len(k.theta)
