@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 N_POINTS, N_ORDERS, N_LS_PER_GPU, N_Q = 1024, 6, 128, 256
 METRIC = "(l,Q) grid log-likelihood evals/sec at N=1024, 6 orders"
-NCU_TRAFFIC_BYTES = 4.518814e9 + 651.884288e6      # profiles/r01_ncu_hetero.txt
+NCU_TRAFFIC_BYTES = 4.536592e9 + 655.293696e6      # profiles/r01_ncu_hetero_tma.txt
 
 
 def make_inputs(n_ls):
@@ -292,7 +292,7 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                          "traffic": NCU_TRAFFIC_BYTES * (n_ls_total // world) / 128.0,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one chol_hetero_tma_kernel launch at 128 l per GPU, "
-                                           "ncu --set full (profiles/r01_ncu_hetero.txt)",
+                                           "ncu --set full (profiles/r01_ncu_hetero_tma.txt)",
                          "kernel": "chol_hetero_tma_kernel (FP64 DMMA bordered Cholesky + forward solves, K2+K3; one cooperative launch per step)",
                          "flops_per_step": fact_flops / max(args.steps, 1), "kernel_ms_per_step": fact_ms / max(args.steps, 1),
                          "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; "

@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(256) cov_sym_kernel(CovArgs P) {
 #pragma unroll
         for (int u = 0; u < 2; u++) {
             const int64_t cc = gc + u;
-            const double ex = P.constant * exp(-0.5 * rbf_sqdist(xr + r * COV_MAXD, xc + (c + u) * COV_MAXD, P.d));
+            // exp underflows to exactly 0 below -745.14; skipping the call there changes no bit and saves both the
+            // evaluation and libm's slow path for huge arguments (short length scales: most of the matrix)
+            const double arg = -0.5 * rbf_sqdist(xr + r * COV_MAXD, xc + (c + u) * COV_MAXD, P.d);
+            const double ex = arg < -746.0 ? 0.0 : P.constant * exp(arg);
             if (gr >= P.n || cc >= P.n) v[u] = (gr == cc) ? 1.0 : 0.0;
             else if (gr == cc) v[u] = dval;
             else v[u] = ex;
