@@ -43,11 +43,17 @@ struct gsum_ctx {
     void *ht_gtasks, *ht_ftasks; size_t ht_gcap, ht_fcap; int ht_key[5]; int ht_ng, ht_nf;
     int ht_ready;               // function attributes set / co-residency checked
     int use_tma, hx_ready;      // GSUM_B200_SCHEDULE=hetero_tma: TMA-fed variant (hetero_tma.cuh)
+    // pinned staging arena for host-memory callers: small inputs go host -> pinned -> device with a truly asynchronous copy,
+    // outputs come back device -> pinned and are handed to the caller after the call's single stream synchronisation
+    char *pin; size_t pin_cap, pin_off;
+    struct { void *dst; const void *src; size_t bytes; } pend[16];
+    int npend;
     int ht_factor_ctas;         // GSUM_B200_FACTOR_CTAS (default HT_FACTOR_CTAS)
 };
 
 static inline int gsum_fail(gsum_ctx *c, int code, const char *fmt, ...) {
     if (c) {
+        c->npend = 0; c->pin_off = 0;           // a failed call delivers nothing
         va_list ap; va_start(ap, fmt);
         vsnprintf(c->err, sizeof(c->err), fmt, ap);
         va_end(ap);

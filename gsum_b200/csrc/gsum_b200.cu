@@ -40,6 +40,7 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaMallocHost((void **)&c->pin, (size_t)8 << 20) == cudaSuccess) c->pin_cap = (size_t)8 << 20; else { c->pin = nullptr; cudaGetLastError(); }
     const char *sched = getenv("GSUM_B200_SCHEDULE");
     c->use_multilaunch = (sched && strcmp(sched, "multilaunch") == 0) ? 1 : 0;
     // default: the warp-specialised pipeline kernel; "dataflow" (two all-in-one CTAs per SM) and "multilaunch" (one launch
@@ -67,6 +68,7 @@ extern "C" int gsum_ctx_destroy(gsum_ctx *c) {
     if (c->ht_ftasks) cudaFree(c->ht_ftasks);
     if (c->df_flags) cudaFree(c->df_flags);
     if (c->df_ctl) cudaFree(c->df_ctl);
+    if (c->pin) cudaFreeHost(c->pin);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -111,7 +113,12 @@ static int dev_in(gsum_ctx *c, int slot, const void *p, size_t bytes, int mem_ki
     if (mem_kind == GSUM_MEM_DEVICE) { *out = p; return 0; }
     void *d;
     GSUM_TRY(gsum_ws(c, slot, bytes, &d));
-    GSUM_CUDA(c, cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream));
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (c->pin && c->pin_off + need <= c->pin_cap) {
+        memcpy(c->pin + c->pin_off, p, bytes);
+        GSUM_CUDA(c, cudaMemcpyAsync(d, c->pin + c->pin_off, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->pin_off += need;
+    } else GSUM_CUDA(c, cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream));
     *out = d;
     return 0;
 }
@@ -123,14 +130,26 @@ static int dev_out(gsum_ctx *c, int slot, void *p, size_t bytes, int mem_kind, v
 }
 static int dev_out_finish(gsum_ctx *c, void *host, const void *dev, size_t bytes, int mem_kind) {
     if (!host || mem_kind == GSUM_MEM_DEVICE) return 0;
-    GSUM_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (c->pin && c->npend < 16 && c->pin_off + need <= c->pin_cap) {
+        GSUM_CUDA(c, cudaMemcpyAsync(c->pin + c->pin_off, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        c->pend[c->npend].dst = host; c->pend[c->npend].src = c->pin + c->pin_off; c->pend[c->npend].bytes = bytes;
+        c->npend++;
+        c->pin_off += need;
+    } else GSUM_CUDA(c, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
     return 0;
+}
+// hand the staged outputs to the caller (after a stream synchronisation)
+static void flush_pending(gsum_ctx *c) {
+    for (int i = 0; i < c->npend; i++) memcpy(c->pend[i].dst, c->pend[i].src, c->pend[i].bytes);
+    c->npend = 0; c->pin_off = 0;
 }
 static int finish(gsum_ctx *c, int mem_kind) {
     GSUM_CUDA(c, cudaPeekAtLastError());
     GSUM_CUDA(c, cudaGetLastError());
     if (mem_kind == GSUM_MEM_HOST) {
         GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        flush_pending(c);
         if (c->df_ctl) {
             int sticky = 0;
             GSUM_CUDA(c, cudaMemcpy(&sticky, c->df_ctl + 2, sizeof(int), cudaMemcpyDeviceToHost));
@@ -1205,6 +1224,7 @@ extern "C" int gsum_pivoted_cholesky(gsum_ctx *c, const double *M, int64_t n, do
     }
     if (piv) GSUM_CUDA(c, cudaMemcpyAsync(piv, dpiv, sizeof(int32_t) * n, mem_kind == GSUM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (mem_kind == GSUM_MEM_HOST) flush_pending(c);
     if (rank) {
         if (mem_kind == GSUM_MEM_HOST) *rank = hst.rank;
         else GSUM_CUDA(c, cudaMemcpy(rank, &hst.rank, sizeof(int32_t), cudaMemcpyHostToDevice));

@@ -47,12 +47,14 @@ def lml_grid_sharded(X, dy, ref, orders, ls, Q, group=None, normalize=False, **k
     n_ls, n_q = ls.shape[0], np.asarray(Q).shape[0]
     mine = shard_indices(n_ls, world, rank)
     per = -(-n_ls // world)                                   # ceil: every rank sends the same count
+    backend = dist.get_backend(group)
+    if backend == "nccl" and "_evaluator" not in kw:
+        return _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normalize, kw)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     block = np.full((n_q, per), -np.inf)
     if len(mine):
         evaluator = kw.pop("_evaluator", ops.lml_grid)
         block[:, :len(mine)] = evaluator(X, dy, ref, orders, ls[mine], Q, **kw)
-    backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     send = torch.from_numpy(block).to(dev)
     recv = torch.empty((world * n_q, per), dtype=torch.float64, device=dev)   # rank-major concatenation along dim 0
     dist.all_gather_into_tensor(recv, send, group=group)     # the single collective of the path
@@ -61,3 +63,49 @@ def lml_grid_sharded(X, dy, ref, orders, ls, Q, group=None, normalize=False, **k
         post, lse = ops.grid_normalize(full)
         return full, post, lse
     return full
+
+
+_stream_ctx = {}
+
+
+def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normalize, kw):
+    """NCCL path: this rank's block never leaves the device between the likelihood kernels and the all-gather — inputs go
+    up once, the kernels and the collective are enqueued on torch's current stream, the round-robin deal is undone by a
+    permute on the device, and ONE device-to-host copy returns the grid."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    stream = torch.cuda.current_stream(dev)
+    key = (dev.index, stream.cuda_stream)
+    ctx = _stream_ctx.get(key)
+    if ctx is None:
+        ctx = _stream_ctx[key] = _lib.Context(dev.index, stream.cuda_stream)
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    n = X.shape[0]
+    Q = np.asarray(Q, dtype=np.float64)
+    n_q, n_ls = Q.shape[0], ls.shape[0]
+    up = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    detf = kw.get("detf")
+    send = torch.full((n_q, per), float("-inf"), dtype=torch.float64, device=dev)
+    if len(mine):
+        out = send if len(mine) == per else torch.empty((n_q, len(mine)), dtype=torch.float64, device=dev)
+        ops.lml_grid_device(ctx, up(X), up(dy), up(np.broadcast_to(np.asarray(ref, dtype=np.float64), (n,))),
+                            up(np.asarray(orders, dtype=np.int32), torch.int32), up(ls[mine]), up(Q),
+                            None if detf is None else up(np.broadcast_to(np.asarray(detf, dtype=np.float64), (n_q,))), out,
+                            q_x_dependent=bool(kw.get("q_x_dependent", False)), constant=kw.get("constant", 1.0),
+                            noise=kw.get("noise", 0.0), nugget=kw.get("nugget", 1e-10), center0=kw.get("center0", 0.0),
+                            disp0=kw.get("disp0", 0.0), df0=kw.get("df0", 1.0), scale0=kw.get("scale0", 1.0),
+                            student=bool(kw.get("student", False)))
+        if out is not send:
+            send[:, :len(mine)] = out
+    recv = torch.empty((world * n_q, per), dtype=torch.float64, device=dev)   # rank-major concatenation along dim 0
+    dist.all_gather_into_tensor(recv, send, group=group)                      # the single collective of the path
+    # rank r's local column j is length scale r + j * world: (world, n_q, per) -> (n_q, per, world) -> (n_q, per * world)
+    full_d = recv.view(world, n_q, per).permute(1, 2, 0).reshape(n_q, per * world)[:, :n_ls].contiguous()
+    if normalize:
+        post_d, lse_d = torch.empty_like(full_d), torch.empty(1, dtype=torch.float64, device=dev)
+        ops.grid_normalize_device(ctx, full_d, post_d, lse_d)
+        return full_d.cpu().numpy(), post_d.cpu().numpy(), float(lse_d.cpu()[0])
+    return full_d.cpu().numpy()
