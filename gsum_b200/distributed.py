@@ -86,14 +86,25 @@ def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normaliz
     n = X.shape[0]
     Q = np.asarray(Q, dtype=np.float64)
     n_q, n_ls = Q.shape[0], ls.shape[0]
-    up = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
     detf = kw.get("detf")
     send = torch.full((n_q, per), float("-inf"), dtype=torch.float64, device=dev)
     if len(mine):
+        # every input in ONE host buffer -> one host-to-device copy; the device tensors are views into it
+        orders32 = np.asarray(orders, dtype=np.int32)
+        parts = [X.ravel(), np.asarray(dy, dtype=np.float64).ravel(), np.broadcast_to(np.asarray(ref, dtype=np.float64), (n,)),
+                 ls[mine].ravel(), Q.ravel(),
+                 np.zeros(n_q) if detf is None else np.broadcast_to(np.asarray(detf, dtype=np.float64), (n_q,))]
+        sizes = [p.size for p in parts] + [(orders32.size + 1) // 2]
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        host = np.empty(int(offs[-1]), dtype=np.float64)
+        for p_, o in zip(parts, offs):
+            host[o:o + p_.size] = p_
+        host[offs[6]:].view(np.int32)[:orders32.size] = orders32
+        buf = torch.from_numpy(host).to(dev)
+        v = [buf[int(offs[i]):int(offs[i + 1])] for i in range(7)]
         out = send if len(mine) == per else torch.empty((n_q, len(mine)), dtype=torch.float64, device=dev)
-        ops.lml_grid_device(ctx, up(X), up(dy), up(np.broadcast_to(np.asarray(ref, dtype=np.float64), (n,))),
-                            up(np.asarray(orders, dtype=np.int32), torch.int32), up(ls[mine]), up(Q),
-                            None if detf is None else up(np.broadcast_to(np.asarray(detf, dtype=np.float64), (n_q,))), out,
+        ops.lml_grid_device(ctx, v[0].view(n, -1), v[1].view(n, -1), v[2], v[6].view(torch.int32)[:orders32.size], v[3].view(len(mine), -1),
+                            v[4].view(Q.shape), None if detf is None else v[5], out,
                             q_x_dependent=bool(kw.get("q_x_dependent", False)), constant=kw.get("constant", 1.0),
                             noise=kw.get("noise", 0.0), nugget=kw.get("nugget", 1e-10), center0=kw.get("center0", 0.0),
                             disp0=kw.get("disp0", 0.0), df0=kw.get("df0", 1.0), scale0=kw.get("scale0", 1.0),

@@ -169,3 +169,33 @@ def test_grid_normalize(ctx):
     post, lse = ops.grid_normalize(ll)
     from scipy.special import logsumexp
     assert relerr(post, np.exp(ll - ll.max())) < 1e-14 and lse == pytest.approx(logsumexp(ll), rel=1e-14)
+
+
+def test_sharded_nccl_path_single_rank(ctx):
+    """The NCCL branch of the sharded grid (device-resident block, all-gather, permute, one D2H) on a one-rank group:
+    bit-identical to the plain call, including a grid whose length-scale count is not a multiple of the world size."""
+    import os
+    import torch
+    import torch.distributed as dist
+    rs = np.random.RandomState(5)
+    n = 130
+    X = np.linspace(0, 1, n)[:, None]
+    coeffs = np.linalg.cholesky(RBF(0.2)(X) + 1e-6 * np.eye(n)) @ rs.randn(n, 4)
+    orders = np.arange(4)
+    y = o.partials(coeffs, 0.5, 1.0, orders)
+    gp = gb.TruncationGP(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0.1, disp=0.5, df=3, scale=1.2,
+                         optimizer=None).fit(X, y, orders=orders)
+    ls_vals, q_vals = np.linspace(0.05, 0.4, 7), np.linspace(0.3, 0.7, 5)
+    want = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29600 + os.getpid() % 300))
+    torch.cuda.set_device(0)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        got = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=dist.group.WORLD)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    assert np.array_equal(got, want)
