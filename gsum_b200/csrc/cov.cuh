@@ -11,6 +11,8 @@
 #pragma once
 #include "common.cuh"
 
+#define COV_MAXD 8              // input dimensions supported by the device kernels
+
 // XS[b][n][d] = X[n][d] / ls[b][d or 0]
 __global__ void scale_coords_kernel(const double *__restrict__ X, const double *__restrict__ ls, double *__restrict__ XS,
                                     int64_t n, int d, int ls_dim, int64_t batch) {
@@ -42,48 +44,85 @@ struct CovArgs {
     int T;                // tile rows/cols of the factor part (n padded to 64)
 };
 
+// One 64x64 tile with every row and column inside the matrix.  Thread = two adjacent columns (kept in registers) x eight
+// rows (row coordinates are warp-wide broadcasts from shared memory); same arithmetic order as the general loop.
+template <int D>
+__device__ __forceinline__ void cov_tile_inside(const double *xr, const double *xc, double constant, double dval, bool diag_tile,
+                                                double *At, int64_t ld, int tid) {
+    const int c = (tid & 31) * 2, rbase = tid >> 5;
+    double c0[D], c1[D];
+#pragma unroll
+    for (int q = 0; q < D; q++) { c0[q] = xc[c * COV_MAXD + q]; c1[q] = xc[(c + 1) * COV_MAXD + q]; }
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int r = rbase + 8 * it;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int q = 0; q < D; q++) {
+            const double x = xr[r * COV_MAXD + q];
+            const double d0 = __dsub_rn(x, c0[q]), d1 = __dsub_rn(x, c1[q]);
+            s0 = __dadd_rn(s0, __dmul_rn(d0, d0));
+            s1 = __dadd_rn(s1, __dmul_rn(d1, d1));
+        }
+        const double a0 = -0.5 * s0, a1 = -0.5 * s1;
+        double v0 = a0 < -746.0 ? 0.0 : constant * exp(a0);
+        double v1 = a1 < -746.0 ? 0.0 : constant * exp(a1);
+        if (diag_tile) { if (r == c) v0 = dval; if (r == c + 1) v1 = dval; }
+        *reinterpret_cast<double2 *>(At + (int64_t)r * ld + c) = make_double2(v0, v1);
+    }
+}
+
 // Symmetric build: lower tiles (i >= k) of each matrix in the batch; identity in the padding.
 // One CTA (256 threads) per 64x64 tile; each thread produces 8 adjacent pairs -> 16-byte coalesced stores.
-#define COV_MAXD 8
+#define COV_TILES_PER_CTA 8     // a 64x64 tile is ~1 us of work: one tile per CTA ran at the block-launch rate (17k CTAs in 0.30 ms)
 __global__ void __launch_bounds__(256) cov_sym_kernel(CovArgs P) {
     __shared__ double xr[GSUM_TILE * COV_MAXD], xc[GSUM_TILE * COV_MAXD];
-    // decode lower-triangular tile index
-    int tix = blockIdx.x;
-    int i = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
-    while ((i + 1) * (i + 2) / 2 <= tix) i++;
-    while (i * (i + 1) / 2 > tix) i--;
-    const int k = tix - i * (i + 1) / 2;
     const int64_t b = blockIdx.y;
     const double *XS = P.XS + b * P.n * P.d;
     const int tid = threadIdx.x;
-    for (int e = tid; e < GSUM_TILE * P.d; e += 256) {
-        int r = e / P.d, q = e % P.d;
-        int64_t gr = (int64_t)i * GSUM_TILE + r, gc = (int64_t)k * GSUM_TILE + r;
-        xr[r * COV_MAXD + q] = gr < P.n ? XS[gr * P.d + q] : 0.0;
-        xc[r * COV_MAXD + q] = gc < P.n ? XS[gc * P.d + q] : 0.0;
-    }
-    __syncthreads();
     double *A = P.A + b * P.bstride;
     const double dval = __dadd_rn(__dadd_rn(P.constant, P.noise), P.nugget);
-    // 8 row steps per thread, unrolled by 4: eight independent exp chains in flight per thread (the kernel is bound by the
-    // FP64 pipe's latency, not by the 3.7 TB/s it writes)
-#pragma unroll 4
-    for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += 256) {
-        const int r = e >> 5, c = (e & 31) * 2;
-        const int64_t gr = (int64_t)i * GSUM_TILE + r, gc = (int64_t)k * GSUM_TILE + c;
-        double v[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int64_t cc = gc + u;
-            // exp underflows to exactly 0 below -745.14; skipping the call there changes no bit and saves both the
-            // evaluation and libm's slow path for huge arguments (short length scales: most of the matrix)
-            const double arg = -0.5 * rbf_sqdist(xr + r * COV_MAXD, xc + (c + u) * COV_MAXD, P.d);
-            const double ex = arg < -746.0 ? 0.0 : P.constant * exp(arg);
-            if (gr >= P.n || cc >= P.n) v[u] = (gr == cc) ? 1.0 : 0.0;
-            else if (gr == cc) v[u] = dval;
-            else v[u] = ex;
+    const int ntri = P.T * (P.T + 1) / 2;
+    for (int tix = blockIdx.x * COV_TILES_PER_CTA; tix < ntri && tix < (blockIdx.x + 1) * COV_TILES_PER_CTA; tix++) {
+        // decode lower-triangular tile index
+        int i = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= tix) i++;
+        while (i * (i + 1) / 2 > tix) i--;
+        const int k = tix - i * (i + 1) / 2;
+        __syncthreads();                                   // the previous tile's coordinates are no longer in use
+        for (int e = tid; e < GSUM_TILE * P.d; e += 256) {
+            int r = e / P.d, q = e % P.d;
+            int64_t gr = (int64_t)i * GSUM_TILE + r, gc = (int64_t)k * GSUM_TILE + r;
+            xr[r * COV_MAXD + q] = gr < P.n ? XS[gr * P.d + q] : 0.0;
+            xc[r * COV_MAXD + q] = gc < P.n ? XS[gc * P.d + q] : 0.0;
         }
-        *reinterpret_cast<double2 *>(A + gr * P.ld + gc) = make_double2(v[0], v[1]);
+        __syncthreads();
+        // Tiles that lie entirely inside the matrix (all of them when N is a multiple of 64) take a path without bounds
+        // checks whose inner loop is the arithmetic only.
+        if ((int64_t)(i + 1) * GSUM_TILE <= P.n && P.d <= 3) {
+            double *At = A + (int64_t)i * GSUM_TILE * P.ld + (int64_t)k * GSUM_TILE;
+            if (P.d == 1) cov_tile_inside<1>(xr, xc, P.constant, dval, i == k, At, P.ld, tid);
+            else if (P.d == 2) cov_tile_inside<2>(xr, xc, P.constant, dval, i == k, At, P.ld, tid);
+            else cov_tile_inside<3>(xr, xc, P.constant, dval, i == k, At, P.ld, tid);
+            continue;
+        }
+#pragma unroll 4
+        for (int e = tid; e < GSUM_TILE * GSUM_TILE / 2; e += 256) {
+            const int r = e >> 5, c = (e & 31) * 2;
+            const int64_t gr = (int64_t)i * GSUM_TILE + r, gc = (int64_t)k * GSUM_TILE + c;
+            double v[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int64_t cc = gc + u;
+                // exp underflows to exactly 0 below -745.14; skipping the call there changes no bit
+                const double arg = -0.5 * rbf_sqdist(xr + r * COV_MAXD, xc + (c + u) * COV_MAXD, P.d);
+                const double ex = arg < -746.0 ? 0.0 : P.constant * exp(arg);
+                if (gr >= P.n || cc >= P.n) v[u] = (gr == cc) ? 1.0 : 0.0;
+                else if (gr == cc) v[u] = dval;
+                else v[u] = ex;
+            }
+            *reinterpret_cast<double2 *>(A + gr * P.ld + gc) = make_double2(v[0], v[1]);
+        }
     }
 }
 

@@ -1,9 +1,14 @@
-run() { echo "== $*"; env "$@" timeout 60 python tools/perf_chol.py $M --stats --reps 5 2>&1 | tail -3; }
-for M in hetero_tma; do export M
-HT_MODE=$M timeout 40 python tools/ht_small.py 256 64 2 2>&1 | tail -2
-HT_MODE=$M timeout 40 python tools/ht_small.py 64 100 1 2>&1 | tail -1
-HT_MODE=$M timeout 40 python tools/ht_check.py 2 2>&1 | tail -2
-run GSUM_B200_FACTOR_CTAS=16
-run GSUM_B200_FACTOR_CTAS=12
-run GSUM_B200_FACTOR_CTAS=14 GSUM_B200_DIAG_DELAY=0
-done
+for v in COV_EXP_OFF COV_STORE_OFF; do echo "== $v"; GSUM_B200_LIB=$PWD/build/lib_$v.so timeout 60 python tools/perf_chol.py hetero_tma --reps 6 2>&1 | tail -1; done
+echo "== default"; timeout 60 python tools/perf_chol.py hetero_tma --reps 6 2>&1 | tail -1
+python - <<'PY'
+import torch, time
+x = torch.empty(1070*1024*1024//8, dtype=torch.float64, device="cuda")
+for _ in range(3): x.zero_()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): x.fill_(1.5)
+e1.record(); e1.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print("fill 1.07 GiB: %.3f ms -> %.2f TB/s" % (ms, x.numel()*8/ms*1e-9))
+PY
