@@ -74,7 +74,10 @@ __device__ __forceinline__ void cov_tile_inside(const double *xr, const double *
 
 // Symmetric build: lower tiles (i >= k) of each matrix in the batch; identity in the padding.
 // One CTA (256 threads) per 64x64 tile; each thread produces 8 adjacent pairs -> 16-byte coalesced stores.
-#define COV_TILES_PER_CTA 8     // a 64x64 tile is ~1 us of work: one tile per CTA ran at the block-launch rate (17k CTAs in 0.30 ms)
+// Tiles per CTA (measured on C4: 1 -> 0.30 ms with the general loop, 4 -> 0.185 ms, 8 -> 0.195, 34 -> 0.24)
+#ifndef COV_TILES_PER_CTA
+#define COV_TILES_PER_CTA 4
+#endif
 __global__ void __launch_bounds__(256) cov_sym_kernel(CovArgs P) {
     __shared__ double xr[GSUM_TILE * COV_MAXD], xc[GSUM_TILE * COV_MAXD];
     const int64_t b = blockIdx.y;
