@@ -219,8 +219,8 @@ static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool sol
         c->df_flags_cap = fbytes + 4096;
     }
     if (!c->df_ctl) {
-        GSUM_CUDA(c, cudaMalloc((void **)&c->df_ctl, 4 * sizeof(int)));
-        GSUM_CUDA(c, cudaMemsetAsync(c->df_ctl, 0, 4 * sizeof(int), c->stream));
+        GSUM_CUDA(c, cudaMalloc((void **)&c->df_ctl, 8 * sizeof(int)));
+        GSUM_CUDA(c, cudaMemsetAsync(c->df_ctl, 0, 8 * sizeof(int), c->stream));
     }
     const int64_t nflags = (int64_t)batch * P.Trows * P.T;
     df_init_kernel<<<(unsigned)((nflags + 255) / 256 + 1), 256, 0, c->stream>>>((int *)c->df_flags, c->df_ctl, batch, P.Trows, P.T, solve_only ? 1 : 0);
@@ -337,8 +337,8 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         c->df_flags_cap = fbytes + 4096;
     }
     if (!c->df_ctl) {
-        GSUM_CUDA(c, cudaMalloc((void **)&c->df_ctl, 4 * sizeof(int)));
-        GSUM_CUDA(c, cudaMemsetAsync(c->df_ctl, 0, 4 * sizeof(int), c->stream));
+        GSUM_CUDA(c, cudaMalloc((void **)&c->df_ctl, 8 * sizeof(int)));
+        GSUM_CUDA(c, cudaMemsetAsync(c->df_ctl, 0, 8 * sizeof(int), c->stream));
     }
     void *dM;
     GSUM_TRY(gsum_ws(c, WS_MKK, sizeof(double) * (size_t)batch * P.T * GSUM_TILE * GSUM_TILE, &dM));
@@ -351,6 +351,7 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     }
     HeteroArgs D;
     D.P = P; D.gtasks = (const int4 *)c->ht_gtasks; D.ngtasks = c->ht_ng; D.ftasks = (const int4 *)c->ht_ftasks; D.nftasks = c->ht_nf;
+    D.nf0 = (!solve_only && c->ht_nf >= batch) ? batch : 0;          // df_build_tasks emits the column-0 diagonal tiles first
     D.ctl = c->df_ctl; D.flags = (int *)c->df_flags; D.M = (double *)dM; D.stats = nullptr;
     // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
     int nf = 0;

@@ -62,7 +62,7 @@
 #define HT_FENCE_FACTOR 0
 #endif
 #ifndef HT_FACTOR_CTAS
-#define HT_FACTOR_CTAS 14               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
+#define HT_FACTOR_CTAS 12               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
 #endif
 #ifndef HT_DIAG_DELAY
 #define HT_DIAG_DELAY 0
@@ -74,7 +74,8 @@ struct HeteroArgs {
     int ngtasks;
     const int4 *ftasks;     // factor tasks (k, b, 0, 0) in schedule order
     int nftasks;
-    int *ctl;               // [0] GEMM task counter, [1] abort flag, [2] sticky abort, [3] factor task counter
+    int nf0;                // leading entries of ftasks that belong to tile column 0 (no dependencies)
+    int *ctl;               // [0] GEMM task counter, [1] abort flag, [2] sticky abort, [3] factor task counter, [4] column-0 factor counter
     int *flags;             // per (b, i, k): index (b * Trows + i) * T + k.  i > k: 1 = tile final.  i == k: 1 = S ready, 2 = L_kk and M_kk final
     double *M;              // (batch, T, 64, 64): L_kk with its 8x8 diagonal blocks inverted
     int nfactor_ctas;       // CTAs [0, nfactor_ctas) are factor CTAs
@@ -347,17 +348,24 @@ __device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fa
 }
 
 // ---- factor worker: one 128-thread group of a factor CTA ------------------------------------------------------------
-__device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S, long long *st) {
+// The first nf0 entries of the factor list are the column-0 tiles: nothing precedes them, so at the start of the launch
+// EVERY CTA can take some (phase 0, own counter; `helper` = a math group of a GEMM CTA, which leaves after that phase)
+// — the whole batch's first POTRFs then run in one round instead of queueing on the few factor CTAs while the GEMM CTAs
+// have nothing to do.  Phase 1 is the rest of the list, factor workers only.
+__device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S, long long *st, bool helper = false) {
     const BorderedBatch &P = D.P;
     const int tid = EPI_TID;
     double *dg = S + GSUM_TILE * GSUM_LDS;
     int *s_fail = reinterpret_cast<int *>(dg + 2 * GSUM_TILE);
     int *s_tk = s_fail + 2;
+    bool dead = false;
+    for (int phase = 0; phase < (helper ? 1 : 2) && !dead; phase++)
     for (;;) {
-        if (tid == 0) s_tk[0] = atomicAdd(D.ctl + 3, 1);
+        if (tid == 0) s_tk[0] = (phase == 0) ? atomicAdd(D.ctl + 4, 1) : D.nf0 + atomicAdd(D.ctl + 3, 1);
         CONS_SYNC();
         const int tix = s_tk[0];
-        if (tix >= D.nftasks) break;
+        CONS_SYNC();                                  // everyone has read the claim before thread 0 writes the next one
+        if (tix >= (phase == 0 ? D.nf0 : D.nftasks)) break;
         const int4 tk = D.ftasks[tix];
         const int k = tk.x, b = tk.y;
         double *C = P.A + (int64_t)b * P.bstride + (int64_t)k * GSUM_TILE * P.ld + k * GSUM_TILE;
@@ -365,7 +373,7 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
         int ok = 1;
         const long long t0 = st ? clock64() : 0;
         if (k > 0 && tid == 0) ok = flag_wait_ge(flag, 1, D.ctl + 1) ? 1 : 0;
-        if (!cons_sync_and(ok != 0)) break;
+        if (!cons_sync_and(ok != 0)) { dead = true; break; }
         const long long t1 = st ? clock64() : 0;
 #pragma unroll
         for (int q = 0; q < 16; q++) {
@@ -722,7 +730,7 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
 __global__ void ht_init_kernel(int *flags, int *ctl, int64_t batch, int Trows, int T, int factor_done) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < 2) ctl[idx] = 0;
-    if (idx == 3) ctl[3] = 0;
+    if (idx == 3 || idx == 4) ctl[idx] = 0;
     if (idx >= batch * Trows * T) return;
     const int k = (int)(idx % T), i = (int)((idx / T) % Trows);
     flags[idx] = (factor_done && i < T) ? (i == k ? 2 : 1) : 0;

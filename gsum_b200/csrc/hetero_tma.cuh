@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
     __shared__ __align__(8) uint64_t full_bar[HX_NG][HX_NST], empty_bar[HX_NG][HX_NST], tq_full[HX_NG][HT_QD], tq_empty[HX_NG][HT_QD];
     __shared__ int4 tq[HX_NG][HT_QD];
     __shared__ int done_cnt[HX_NG][HT_QD];
+    __shared__ int helper_done;
     const BorderedBatch &P = D.P;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool st_on = STATS && D.stats != nullptr;
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
     const int q = (w < 4 * HX_NG) ? (w >> 2) : (w - 4 * HX_NG);
     if (tid == 0) {
         for (int qq = 0; qq < HX_NG; qq++) {
+            helper_done = 0;
             for (int s = 0; s < HT_QD; s++) done_cnt[qq][s] = 0;
             for (int s = 0; s < HX_NST; s++) { mbar_init(&full_bar[qq][s], 1); mbar_init(&empty_bar[qq][s], 4); }
             for (int s = 0; s < HT_QD; s++) { mbar_init(&tq_full[qq][s], 1); mbar_init(&tq_empty[qq][s], 4); }
@@ -164,6 +166,14 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
         uint64_t *fullb = full_bar[q], *emptyb = empty_bar[q], *tqf = tq_full[q], *tqe = tq_empty[q];
         int4 *tqs = tq[q];
         const int rowsA = (int)(P.bstride / P.ld), rowsW = (int)(P.wstride / P.ld);
+        if (q == 0 && D.nf0 > 0) {                           // group 0's ring is the scratch of its column-0 POTRFs first
+            const long long t0 = clock64();
+            while (*reinterpret_cast<volatile int *>(&helper_done) == 0) {
+                __nanosleep(200);
+                if (clock64() - t0 > DF_WATCHDOG_CYCLES) { atomicExch(abort_flag, 1); break; }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
         RingState ring = {0, 0u};
         for (int n = 0;; n++) {
             const int slot = n % HT_QD;
@@ -250,6 +260,11 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
         double *ring_base = smem + q * (HX_NST * HX_STAGE_DOUBLES);
         uint64_t *fullb = full_bar[q], *emptyb = empty_bar[q], *tqf = tq_full[q], *tqe = tq_empty[q];
         int4 *tqs = tq[q];
+        if (q == 0 && D.nf0 > 0) {
+            // column-0 diagonal tiles: this group factors some of them before its first GEMM task (see ht_factor_worker)
+            ht_factor_worker(D, ring_base, nullptr, true);
+            if (tid == 0) { __threadfence_block(); *reinterpret_cast<volatile int *>(&helper_done) = 1; }
+        }
         const int g = lane >> 2, t = lane & 3, wg = w & 3;
         int oa[4], om[2][2], oc[2];
         {
