@@ -211,9 +211,8 @@ class BaseConjugateProcess:
 
     def _calibrate_kernel(self):
         """gsum/models.py:630-669: L-BFGS on -log_marginal_likelihood with the analytic gradient (device contractions,
-        _lml_gradient).  The Student-t evidence has no analytic gradient on the device path yet: its objective is
-        differentiated by central differences in log-theta.  (The ragged-array crash of models.py:664 on numpy >= 1.24
-        does not exist here.)"""
+        _lml_gradient), for the Gaussian likelihood and the Student-t evidence alike.  (The ragged-array crash of
+        models.py:664 on numpy >= 1.24 does not exist here.)"""
         self._lml_from_optimizer = None
         if self.optimizer is None or self.kernel_.n_dims == 0:
             return
@@ -221,18 +220,8 @@ class BaseConjugateProcess:
         def obj_func(theta, eval_gradient=True):
             if not eval_gradient:
                 return -self.log_marginal_likelihood(theta)
-            if not self._student:
-                lml, grad = self.log_marginal_likelihood(theta, eval_gradient=True)
-                return -lml, -grad
-            f0 = -self.log_marginal_likelihood(theta)
-            grad = np.empty(len(theta))
-            h = 1e-4
-            for i in range(len(theta)):
-                tp, tm = np.array(theta, dtype=float), np.array(theta, dtype=float)
-                tp[i] += h
-                tm[i] -= h
-                grad[i] = (-self.log_marginal_likelihood(tp) + self.log_marginal_likelihood(tm)) / (2 * h)
-            return f0, grad
+            lml, grad = self.log_marginal_likelihood(theta, eval_gradient=True)
+            return -lml, -grad
 
         optima = [self._constrained_optimization(obj_func, self.kernel_.theta, self.kernel_.bounds)]
         if self.n_restarts_optimizer > 0:
@@ -260,7 +249,8 @@ class BaseConjugateProcess:
 
     # ---- likelihood (gsum/models.py:912-1057 / 1184-1273) ----
     def _lml_gradient(self, theta, X, y):
-        """(log-likelihood, gradient) of the Gaussian conjugate likelihood, gsum/models.py:957-1056 (eval_gradient=True).
+        """(log-likelihood, gradient): the Gaussian conjugate likelihood, gsum/models.py:957-1056 (eval_gradient=True), or
+        the Student-t evidence, models.py:1199-1271.
 
         The device returns the Gram G = RHS^T R^-1 RHS of RHS = [basis | curves], the contractions H_p = Z^T dR_p Z
         (Z = R^-1 RHS) and t_p = trace(R^-1 dR_p) for the derivative of R with respect to each log-hyperparameter
@@ -268,9 +258,6 @@ class BaseConjugateProcess:
         vector a, so its formulas become quadratic forms in G and H_p:
           compute_center  models.py:201-230,  compute_scale_sq  419-455,  compute_cov_factor  501-503,
           dK = var dR + dvar R  1024-1025,  0.5 (alpha alpha^T - K^-1) : dK - dmean^T alpha  1041-1056."""
-        if self._student:
-            raise NotImplementedError("gsum_b200: the analytic gradient of the Student-t evidence (gsum/models.py:1260-1271) "
-                                      "is not implemented on the device path")
         self._check_decomposition()
         theta = np.asarray(theta, dtype=np.float64)
         kernel = self._active_kernel().clone_with_theta(theta)
@@ -316,6 +303,24 @@ class BaseConjugateProcess:
             quad2 = quad_form(G, ac, aw)
             scale2 = (df0 * scale0 ** 2 + quad + quad2) / df
             dscale2 = np.array([-(sum(quad_form(Hp, e, e) for e in Ec) + quad_form(Hp, aw, aw) / nc) / df for Hp in H])
+        if self._student:
+            # exact normal-inverse-chi^2 evidence and its gradient (models.py:1241-1271); compute_disp's derivative is
+            # dV = n_c V (B^T R^-1 dR R^-1 B) V  (models.py:270-277)
+            from scipy.special import loggamma
+
+            def log_norm(df_, scale2_, disp_):
+                norm = loggamma(df_ / 2.0) - df_ / 2.0 * np.log(df_ * scale2_ / 2.0)
+                if disp_ > 0:
+                    norm += 0.5 * np.log(2 * np.pi * disp_)
+                return norm
+
+            ll = log_norm(df, scale2, V) - log_norm(df0, scale0 ** 2, V0) - nc / 2.0 * (N * np.log(2 * np.pi) + logdet)
+            grad_dev = -(nc / 2.0) * tr - (df / 2.0) * dscale2 / scale2
+            if V != 0:
+                dV = np.array([nc * V * V * quad_form(Hp, eB, eB) for Hp in H])
+                grad_dev = grad_dev + 0.5 * dV / V
+            grad = np.array([w * grad_dev[slot] for slot, w in layout])
+            return float(ll), grad
         cov_factor = (lambda s2: s2) if np.isinf(df) else (lambda s2: df * s2 / (df - 2))
         var, dvar = cov_factor(scale2), cov_factor(dscale2)
         Bk = E - eta * eB[None, :]                                                # y_train_k = RHS b_k

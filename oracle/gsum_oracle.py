@@ -292,6 +292,58 @@ def student_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis)
         - ny / 2.0 * (N * np.log(2 * np.pi) + logdet_R)          # :1257-1258
 
 
+def student_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis):
+    """gsum/models.py:1184-1273 with eval_gradient=True: (evidence, d/dtheta).  compute_disp carries its derivative
+    (models.py:270-277), compute_scale_sq as in the Gaussian case (450-455); chain rule at 1260-1271."""
+    ny = _num_y(y)
+    k = kernel.clone_with_theta(theta)
+    R, dR = k(X, eval_gradient=True)
+    R[np.diag_indices_from(R)] += nugget
+    N = R.shape[0]
+    try:
+        L_R = cholesky(R)
+    except np.linalg.LinAlgError:
+        return -np.inf, np.zeros_like(theta)
+    p = priors
+    df = compute_df(y, p.df0)
+    basis = basis_fn(X)
+    disp = compute_disp(y, L_R, basis, p.disp0)
+    if np.all(p.disp0 == 0):
+        grad_disp = np.zeros((*p.disp0.shape, dR.shape[-1]))
+    else:
+        invRBV = solve_sqrt(L_R, basis) @ disp
+        grad_disp = ny * np.einsum('ji,jkp,kl->ilp', invRBV, dR, invRBV)       # :275
+    scale_sq = compute_scale_sq(y, L_R, basis, p.center0, p.disp0, p.df0, p.scale0)
+    if p.df0 == np.inf:
+        grad_scale_sq = np.zeros(dR.shape[-1])
+    else:
+        avg_y = _avg_y(y)
+        y_centered = y - avg_y[:, None]
+        invR_yc = solve_sqrt(L_R, y_centered)
+        avg_y_centered = avg_y - basis @ p.center0
+        mat = np.eye(N) - ny * solve_sqrt(L_R, basis) @ disp @ basis.T
+        mat_invR_avg_yc = ny * mat @ solve_sqrt(L_R, avg_y_centered)
+        grad_scale_sq = -np.einsum('ji,jkp,ki->p', invR_yc, dR, invR_yc)
+        grad_scale_sq -= np.einsum('i,ijp,j->p', mat_invR_avg_yc, dR, mat_invR_avg_yc) / ny
+        grad_scale_sq /= df
+    scale = np.sqrt(scale_sq)
+
+    def log_norm(df_, scale_, disp_):
+        norm = loggamma(df_ / 2.0) - df_ / 2.0 * np.log(df_ * scale_ ** 2 / 2.0)
+        log_det = np.linalg.slogdet(2 * np.pi * disp_)[1]
+        if log_det != -np.inf:
+            norm += 0.5 * log_det
+        return norm
+
+    logdet_R = 2 * np.log(np.diag(L_R)).sum()
+    ll = log_norm(df, scale, disp) - log_norm(p.df0, p.scale0, p.disp0) - ny / 2.0 * (N * np.log(2 * np.pi) + logdet_R)
+    grad = -(ny / 2.0) * np.trace(solve_sqrt(L_R, dR.reshape(N, -1)).reshape(dR.shape), axis1=0, axis2=1)     # :1262-1264
+    grad -= (df / 2.0) * grad_scale_sq / scale_sq                # :1265
+    if not np.all(disp == 0):
+        grad += 0.5 * np.einsum('ij,ijp->p', inv(disp), grad_disp)   # :1268
+    return ll, grad
+
+
 def truncation_lml(kernel, theta, X, y, orders, ratio, ref, priors, nugget=1e-10, excluded=None,
                    student=False):
     """gsum/models.py:1485-1507 — ll_y = ll_c(coefficients(y; Q, ref)) − Σ_x[n log|ref| + (Σ orders) log|Q|].

@@ -91,3 +91,25 @@ def test_fit_with_free_hyperparameters(ctx):
     # predictions from the calibrated process work as usual
     m, s = gp.predict(X[::10], return_std=True)
     assert np.all(np.isfinite(m)) and np.all(s >= 0)
+
+
+@pytest.mark.parametrize("ip", range(3))
+def test_student_gradient(ctx, golden, ip):
+    """Student-t evidence and gradient (models.py:1184-1273) against the oracle (the reference's own gradient branch
+    crashes in sklearn: models.py:1200), plus an L-BFGS fit of a ConjugateStudentProcess with a free length scale."""
+    g = golden("c1_gradient")
+    pk = prior_kwargs(g["priors"][ip])
+    kern = C(1.5) * RBF(0.2) + WhiteKernel(1e-4)
+    tp = gb.ConjugateStudentProcess(kern, nugget=1e-10, optimizer=None, **pk).fit(g["X"], g["y"])
+    for t in g["thetas"]:
+        ll, gr = tp.log_marginal_likelihood(theta=t, eval_gradient=True)
+        lo, go = o.student_lml_gradient(kern, t, g["X"], g["y"], o.Priors(**pk), 1e-10)
+        assert ll == pytest.approx(lo, rel=RTOL_LML)
+        assert relerr(gr, go) < RTOL_GRAD
+        assert ll == pytest.approx(tp.log_marginal_likelihood(theta=t), rel=1e-10)
+    if ip == 1:
+        k2 = RBF(0.5, length_scale_bounds=(0.02, 2.0)) + WhiteKernel(1e-4, 'fixed')
+        fitted = gb.ConjugateStudentProcess(k2, nugget=1e-10, **pk).fit(g["X"], g["y"])
+        start = gb.ConjugateStudentProcess(k2, nugget=1e-10, optimizer=None, **pk).fit(g["X"], g["y"])
+        assert fitted.log_marginal_likelihood_value_ >= start.log_marginal_likelihood_value_
+        assert 0.05 < float(np.exp(fitted.kernel_.theta[0])) < 0.6

@@ -118,9 +118,5 @@ def test_facade_rejects_out_of_scope_options():
         Diagnostic(np.zeros(3), np.eye(3), df=5)
     with pytest.raises(RuntimeError):
         ConjugateGaussianProcess(RBF(0.2, 'fixed')).predict(np.zeros((2, 1)), return_std=True, return_cov=True)
-    from gsum_b200 import ConjugateStudentProcess
-    sp = ConjugateStudentProcess(RBF(0.2))
-    with pytest.raises(NotImplementedError):                                # Student-t evidence: no analytic gradient yet
-        sp.log_marginal_likelihood([0.0], eval_gradient=True, X=np.zeros((3, 1)), y=np.zeros(3))
     with pytest.raises(ValueError):
         ConjugateGaussianProcess(RBF(0.2), df=1).cov(np.zeros((2, 1)))      # df <= 2: covariance does not exist

@@ -195,3 +195,21 @@ def test_theta_layout_matches_sklearn_order():
     assert theta_layout(RBF([0.3, 0.1]) * C(2.0) + WhiteKernel(1e-4), 2) == [(1, 1.0), (2, 1.0), (0, 1.0), (3, 1.0)]
     k = C(1.5) * RBF(0.2) + WhiteKernel(1e-4)
     assert len(theta_layout(k, 1)) == len(k.theta)
+
+
+@pytest.mark.parametrize("ip", range(3))
+def test_student_gradient_oracle_is_the_derivative(golden, ip):
+    """The reference's Student-t gradient branch crashes (models.py:1200 passes eval_gradient as Y), so there is no golden
+    vector: the oracle's restatement of models.py:1260-1271 is pinned as the derivative of the (golden-pinned) evidence."""
+    g = golden("c1_gradient")
+    p = o.Priors(**prior_kwargs(g["priors"][ip]))
+    kern = C(1.5) * RBF(0.2) + WhiteKernel(1e-4)
+    t0 = g["thetas"][1]
+    ll, gr = o.student_lml_gradient(kern, t0, g["X"], g["y"], p, 1e-10)
+    assert ll == pytest.approx(o.student_lml(kern, t0, g["X"], g["y"], p, 1e-10), rel=1e-12)
+    for i in range(len(t0)):
+        tp, tm = t0.copy(), t0.copy()
+        tp[i] += 1e-4
+        tm[i] -= 1e-4
+        fd = (o.student_lml(kern, tp, g["X"], g["y"], p, 1e-10) - o.student_lml(kern, tm, g["X"], g["y"], p, 1e-10)) / 2e-4
+        assert gr[i] == pytest.approx(fd, rel=1e-3, abs=1e-3)
