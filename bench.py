@@ -40,36 +40,49 @@ def make_inputs(n_ls):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed regions (B200_PROFILING.md recipe).  The sampler runs
+    from before the warm-up (nvidia-smi needs ~0.1 s to start) at a 20 ms period; every row is stamped when it is read
+    and only rows that fall inside a timed window (`mark_start` / `mark_end`) are reported."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.windows, self._t0 = index, [], None, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_start(self):
+        self._t0 = time.perf_counter()
+
+    def mark_end(self):
+        if self._t0 is not None:
+            self.windows.append((self._t0, time.perf_counter()))
+            self._t0 = None
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '', 1).isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
+        inside = [r for ts, r in self.rows if any(a <= ts <= b + 0.02 for a, b in self.windows)]
+        rows = inside if inside else [r for _, r in self.rows]
+        sm = [float(r[0]) for r in rows if r and r[0].replace('.', '', 1).isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '', 1).isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        reasons = sorted({names[i] for r in rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "window": "timed regions (device-resident steps and end-to-end steps)" if inside else
+                "whole run (no sample fell inside the timed regions)"}
 
 
 def cpu_reference_cells(X, y, orders, ls_vals, q_vals, cells):
@@ -217,22 +230,24 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
     ctx.profile(True)
     launches0 = ctx.launch_count
     evs = []
     barrier()
+    sampler.mark_start()
     for _ in range(args.steps):
         flush.zero_()                                                       # L2 flush between timed iterations (untimed)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream); step_device(); e1.record(stream)
         evs.append((e0, e1))
     barrier()
+    sampler.mark_end()
     ms_total = sum(a.elapsed_time(b) for a, b in evs)
     launches = ctx.launch_count - launches0
     fact_ms, fact_flops, n_br = ctx.profile_read()
@@ -242,7 +257,6 @@ def run_ours(args, rank, world, local_rank):
         mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         ms_total, launches = float(mx[0]), int(sm[1])
-    clocks = sampler.stop() if rank == 0 else None
     cells_per_step = N_Q * n_ls_total
     value = cells_per_step * args.steps / (ms_total * 1e-3)
 
@@ -253,11 +267,14 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(3):
         ll_host = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=group)
     barrier()
+    sampler.mark_start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         ll_host = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=group)
     barrier()
     e2e_s = time.perf_counter() - t0
+    sampler.mark_end()
+    clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev); dist.all_reduce(te, op=dist.ReduceOp.MAX); e2e_s = float(te[0])
     e2e_value = cells_per_step * args.steps / e2e_s
