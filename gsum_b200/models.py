@@ -632,6 +632,14 @@ class TruncationProcess:
 
     # ---- likelihood (gsum/models.py:1485-1507) ----
     def _grid_inputs(self, X, y, orders):
+        if X is None and y is None and orders is None:
+            # the training data: converted once per fit (the grid is usually evaluated many times on the same data)
+            key = (id(self.X_train_), id(self.y_train_), id(self.orders_))
+            cached = getattr(self, "_grid_inputs_cache", None)
+            if cached is None or cached[0] != key:
+                cached = (key, self._grid_inputs(self.X_train_, self.y_train_, self.orders_))
+                self._grid_inputs_cache = cached
+            return cached[1]
         X = self.X_train_ if X is None else X
         y = self.y_train_ if y is None else y
         orders = self.orders_ if orders is None else orders
