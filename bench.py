@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 N_POINTS, N_ORDERS, N_LS_PER_GPU, N_Q = 1024, 6, 128, 256
 METRIC = "(l,Q) grid log-likelihood evals/sec at N=1024, 6 orders"
-NCU_TRAFFIC_BYTES = 4.536592e9 + 655.293696e6      # profiles/r01_ncu_hetero_tma.txt
+NCU_TRAFFIC_BYTES = 4.518408e9 + 660.972288e6      # profiles/r01_ncu_hetero_tma.txt
 
 
 def make_inputs(n_ls):
