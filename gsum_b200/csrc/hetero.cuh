@@ -41,12 +41,9 @@
 #define HT_QD 4                         // task queue depth
 #define HT_STAGE_DOUBLES CHOL_STAGE_DOUBLES
 #define HT_SMEM_DOUBLES (HT_NG * HT_NST * HT_STAGE_DOUBLES)
-// Register split (setmaxnreg, warpgroup granular) for three groups: the launch bound leaves 128 (512 threads) or 96 (640)
-// registers per thread; the producer warpgroups keep 40 and the three math / factor warpgroups take HT_MATH_REGS.
-#ifndef HT_SETMAXNREG
-#define HT_SETMAXNREG (HT_MATH_WARPS == 12 && HT_THREADS == 512)
+#if HT_NG != 2
+#error "the cp.async-fed variant runs two math groups (three need the TMA-fed kernel, hetero_tma.cuh)"
 #endif
-#define HT_MATH_REGS 152
 #define HT_STR2(x) #x
 #define HT_STR(x) HT_STR2(x)
 #define HT_SMEM_BYTES (HT_SMEM_DOUBLES * 8)
@@ -54,12 +51,6 @@
 #define HT_NSTAT 40
 #ifndef HT_LEAN_POTRF
 #define HT_LEAN_POTRF 1
-#endif
-#ifndef HT_FENCE_GEMM
-#define HT_FENCE_GEMM 0
-#endif
-#ifndef HT_FENCE_FACTOR
-#define HT_FENCE_FACTOR 0
 #endif
 #ifndef HT_FACTOR_CTAS
 #define HT_FACTOR_CTAS 12               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
@@ -92,14 +83,6 @@ __device__ __forceinline__ bool flag_wait_ge(const int *flag, int want, int *abo
         if (clock64() - t0 > DF_WATCHDOG_CYCLES) { atomicExch(abort_flag, 1); return false; }
     }
     return true;
-}
-// AND-reduction + barrier over the 128 math threads of group q of a GEMM CTA (named barrier 6 + q)
-__device__ __forceinline__ bool ht_group_sync_and(bool v, int q) {
-    unsigned r;
-    __syncwarp();                       // aligned barrier: the warp arrives converged (see CONS_SYNC)
-    asm volatile("{\n .reg .pred p, q;\n setp.ne.u32 q, %1, 0;\n bar.red.and.pred p, %2, 128, q;\n selp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(r) : "r"((unsigned)v), "r"(6 + q) : "memory");
-    return r != 0;
 }
 __device__ __forceinline__ void ht_ring_advance(RingState &r) {
     if (++r.stage == HT_NST) { r.stage = 0; r.phase ^= 1u; }
@@ -395,9 +378,6 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
         // Critical path first: M_kk (what the panel tasks of this column wait for), then the flag; L_kk itself, the
         // log-determinant and the status are outputs nobody inside the launch reads.
         ht_write_mkk(S, dg, D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), fail != 0);
-#if HT_FENCE_FACTOR
-        __threadfence();
-#endif
         CONS_SYNC();                                  // every thread's M stores are ordered before the release below
         if (tid == 0) st_release(flag, 2);
         if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
@@ -439,11 +419,6 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
 
     if ((int)blockIdx.x < D.nfactor_ctas) {
         // ============================ factor CTA ================================================================
-#if HT_SETMAXNREG
-        // same register split as in a GEMM CTA: warpgroup 3 (idle here) hands its registers to the three workers
-        if (w >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;"); return; }
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HT_MATH_REGS) ";");
-#endif
         if (tid >= 128 * D.nworkers) return;         // up to three 128-thread workers
         ht_factor_worker(D, smem + (tid >> 7) * HT_WORKER_DOUBLES, st_on ? st : nullptr);
         if (st_on && (tid & 127) == 0) {
@@ -473,9 +448,6 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
     int *abort_flag = D.ctl + 1;
 
     if (w >= HT_MATH_WARPS) {
-#if HT_SETMAXNREG
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-#endif
         if (w >= HT_MATH_WARPS + HT_NG * HT_PW) return;      // padding warps of the last warpgroup
         // ============================ producer warps =========================================================
         const int pw = (w - HT_MATH_WARPS) % HT_PW;
@@ -608,9 +580,6 @@ __global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D
         if (st_on && pw == 0 && lane == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; }
     } else {
         // ============================ math warps ============================================================
-#if HT_SETMAXNREG
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HT_MATH_REGS) ";");
-#endif
         const int g = lane >> 2, t = lane & 3, wg = w & 3;
         RingState ring = {0, 0u};
         for (int n = 0;; n++) {
