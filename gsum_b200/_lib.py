@@ -53,8 +53,8 @@ _SIGNATURES = {
     "gsum_cholesky_errors": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32]),
     "gsum_pivoted_cholesky": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int32]),
     "gsum_pc_errors": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int32]),
-    "gsum_draws": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint64, _vp, _vp, _vp, C.c_int32, _vp,
-                             C.c_int32]),
+    "gsum_draws": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int32,
+                             _vp, _vp, C.c_int32]),
     "gsum_credible_interval": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int32, _vp, C.c_int32]),
 }
 

@@ -179,11 +179,14 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
 }
+// The counter is (pair index, GLOBAL draw index = first_draw + row): a shard of the draw axis reproduces the columns the
+// unsharded call would generate.  `scale` (n_draws,) or NULL multiplies draw j's normals (multivariate-t draws).
 __global__ void __launch_bounds__(256) normal_rows_kernel(double *__restrict__ Zn, int64_t ld, int64_t rows_pad, int64_t n_draws, int n,
-                                                          uint64_t seed) {
-    const int64_t row = blockIdx.x;
+                                                          uint64_t seed, int64_t first_draw, const double *__restrict__ scale) {
+    const int64_t row = blockIdx.x, grow = first_draw + row;
+    const double sc = (scale && row < n_draws) ? scale[row] : 1.0;
     for (int64_t pr = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; 2 * pr < ld; pr += (int64_t)gridDim.y * blockDim.x) {
-        uint32_t c[4] = {(uint32_t)pr, (uint32_t)(pr >> 32), (uint32_t)row, (uint32_t)(row >> 32)};
+        uint32_t c[4] = {(uint32_t)pr, (uint32_t)(pr >> 32), (uint32_t)grow, (uint32_t)(grow >> 32)};
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
         const double u1 = ((double)(((uint64_t)c[0] << 21) ^ (c[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);   // (0,1)
         const double u2 = ((double)(((uint64_t)c[2] << 21) ^ (c[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
@@ -192,9 +195,15 @@ __global__ void __launch_bounds__(256) normal_rows_kernel(double *__restrict__ Z
         sincospi(2.0 * u2, &sn, &cs);
         const int64_t x = 2 * pr;
         const bool live = row < n_draws;
-        Zn[row * ld + x] = (live && x < n) ? -(rad * cs) : 0.0;
-        if (x + 1 < ld) Zn[row * ld + x + 1] = (live && x + 1 < n) ? -(rad * sn) : 0.0;
+        Zn[row * ld + x] = (live && x < n) ? -(rad * cs) * sc : 0.0;
+        if (x + 1 < ld) Zn[row * ld + x + 1] = (live && x + 1 < n) ? -(rad * sn) * sc : 0.0;
     }
+}
+// rows of caller-supplied normals scaled per draw (multivariate-t with a caller Z)
+__global__ void __launch_bounds__(256) scale_rows_kernel(double *__restrict__ Zn, int64_t ld, int64_t n_draws, const double *__restrict__ scale) {
+    const int64_t row = blockIdx.y;
+    const double sc = scale[row];
+    for (int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; x < ld; x += (int64_t)gridDim.x * blockDim.x) Zn[row * ld + x] *= sc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -206,7 +215,8 @@ __global__ void __launch_bounds__(256) normal_rows_kernel(double *__restrict__ Z
 #define COVG_MAXA 128
 __global__ void __launch_bounds__(COVG_WARPS * 32) coverage_rows_kernel(const double *__restrict__ Yt, int64_t ld, int64_t n_draws, int n,
                                                                         const double *__restrict__ lower, const double *__restrict__ upper,
-                                                                        int n_alpha, double *__restrict__ out) {
+                                                                        int n_alpha, double *__restrict__ out,
+                                                                        unsigned long long *__restrict__ counts) {
     extern __shared__ __align__(16) double sm[];
     double *lo = sm, *up = sm + (size_t)n_alpha * 32;
     int *cnt = (int *)(up + (size_t)n_alpha * 32);       // [COVG_WARPS][n_alpha]
@@ -232,8 +242,17 @@ __global__ void __launch_bounds__(COVG_WARPS * 32) coverage_rows_kernel(const do
         }
     }
     __syncwarp();
-    if (dr < n_draws)
+    if (out && dr < n_draws)
         for (int a = lane; a < n_alpha; a += 32) out[dr * n_alpha + a] = (double)cnt[w * n_alpha + a] / (double)n;
+    if (counts) {                                        // integer totals over the rows of this launch: order independent
+        __syncthreads();
+        for (int a = tid; a < n_alpha; a += COVG_WARPS * 32) {
+            unsigned long long t = 0;
+            for (int ww = 0; ww < COVG_WARPS; ww++)
+                if ((int64_t)blockIdx.x * COVG_WARPS + ww < n_draws) t += (unsigned long long)cnt[ww * n_alpha + a];
+            if (t) atomicAdd(&counts[a], t);
+        }
+    }
 }
 
 // max-shift normalisation of a log-likelihood grid (notebook cell 54): post = exp(ll - max), lse = max + log(sum post)

@@ -18,8 +18,10 @@
 
 enum {
     WS_X = 0, WS_XS, WS_DY, WS_REF, WS_ORD, WS_LS, WS_Q, WS_DETF, WS_MAT, WS_RHS, WS_GRAM, WS_LOGDET, WS_INFO,
-    WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_MKK, WS_G0, WS_G1, WS_G2, WS_G3, WS_G4, WS_G5
+    WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_MKK, WS_G0, WS_G1, WS_G2, WS_G3, WS_G4, WS_G5,
+    WS_SCALE, WS_COUNTS
 };
+static_assert(WS_COUNTS < GSUM_NWS, "workspace slots");
 
 extern "C" int gsum_version(void) { return 100; }
 
@@ -1260,26 +1262,31 @@ extern "C" int gsum_pc_errors(gsum_ctx *c, const double *Lp, const int32_t *piv,
 }
 
 static int coverage_rows(gsum_ctx *c, const double *dYt, int64_t ld, int64_t n_rows, int64_t n, const double *lower, const double *upper,
-                         int n_alpha, double *coverage_out, int mem_kind) {
+                         int n_alpha, double *coverage_out, int64_t *count_out, int mem_kind) {
     if (n_alpha < 1 || n_alpha > COVG_MAXA) return gsum_fail(c, -1, "coverage: n_alpha must be in 1..%d", COVG_MAXA);
-    const void *dlo, *dup; void *dcov;
+    const void *dlo, *dup; void *dcov = nullptr, *dcnt = nullptr;
     GSUM_TRY(dev_in(c, WS_IO2, lower, sizeof(double) * n_alpha * n, mem_kind, &dlo));
     GSUM_TRY(dev_in(c, WS_IO3, upper, sizeof(double) * n_alpha * n, mem_kind, &dup));
-    GSUM_TRY(dev_out(c, WS_LL, coverage_out, sizeof(double) * n_rows * n_alpha, mem_kind, &dcov));
+    if (coverage_out) GSUM_TRY(dev_out(c, WS_LL, coverage_out, sizeof(double) * n_rows * n_alpha, mem_kind, &dcov));
+    if (count_out) {
+        GSUM_TRY(dev_out(c, WS_COUNTS, count_out, sizeof(int64_t) * n_alpha, mem_kind, &dcnt));
+        GSUM_CUDA(c, cudaMemsetAsync(dcnt, 0, sizeof(int64_t) * n_alpha, c->stream));
+    }
     const size_t smem = sizeof(double) * 2 * n_alpha * 32 + sizeof(int) * COVG_WARPS * n_alpha;
     GSUM_CUDA(c, cudaFuncSetAttribute(coverage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     coverage_rows_kernel<<<(unsigned)((n_rows + COVG_WARPS - 1) / COVG_WARPS), COVG_WARPS * 32, smem, c->stream>>>(
-        dYt, ld, n_rows, (int)n, (const double *)dlo, (const double *)dup, n_alpha, (double *)dcov);
+        dYt, ld, n_rows, (int)n, (const double *)dlo, (const double *)dup, n_alpha, (double *)dcov, (unsigned long long *)dcnt);
     LAUNCHED(c, 1);
-    GSUM_TRY(dev_out_finish(c, coverage_out, dcov, sizeof(double) * n_rows * n_alpha, mem_kind));
+    if (coverage_out) GSUM_TRY(dev_out_finish(c, coverage_out, dcov, sizeof(double) * n_rows * n_alpha, mem_kind));
+    if (count_out) GSUM_TRY(dev_out_finish(c, count_out, dcnt, sizeof(int64_t) * n_alpha, mem_kind));
     return 0;
 }
 
 extern "C" int gsum_draws(gsum_ctx *c, const double *L, int64_t n, const double *mean, const double *Z, int64_t n_draws,
-                          uint64_t seed, double *draws_out, const double *lower, const double *upper, int32_t n_alpha,
-                          double *coverage_out, int32_t mem_kind) {
-    if (!c || !L || n <= 0 || n_draws <= 0) return gsum_fail(c, -1, "gsum_draws: bad argument");
-    if (coverage_out && (!lower || !upper)) return gsum_fail(c, -1, "gsum_draws: coverage needs lower and upper");
+                          uint64_t seed, int64_t first_draw, const double *draw_scale, double *draws_out, const double *lower,
+                          const double *upper, int32_t n_alpha, double *coverage_out, int64_t *count_out, int32_t mem_kind) {
+    if (!c || !L || n <= 0 || n_draws <= 0 || first_draw < 0) return gsum_fail(c, -1, "gsum_draws: bad argument");
+    if ((coverage_out || count_out) && (!lower || !upper)) return gsum_fail(c, -1, "gsum_draws: coverage needs lower and upper");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     GSUM_TRY(chol_set_attrs(c));
     GSUM_CUDA(c, cudaFuncSetAttribute(draws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
@@ -1296,9 +1303,17 @@ extern "C" int gsum_draws(gsum_ctx *c, const double *L, int64_t n, const double 
     // factor with explicit zeros above the diagonal (the TRMM reads whole tiles)
     pad_lower_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)np), 256, 0, c->stream>>>((const double *)dL, n, (double *)dF, np);
     LAUNCHED(c, 1);
-    if (Z) launch_transpose_in(c, (const double *)dZ, n, n_draws, nullptr, nullptr, 0, -1.0, (double *)dZn, np, rp);
-    else {
-        normal_rows_kernel<<<dim3((unsigned)rp, (unsigned)((np / 2 + 255) / 256)), 256, 0, c->stream>>>((double *)dZn, np, rp, n_draws, (int)n, seed);
+    const void *dsc = nullptr;
+    if (draw_scale) GSUM_TRY(dev_in(c, WS_SCALE, draw_scale, sizeof(double) * n_draws, mem_kind, &dsc));
+    if (Z) {
+        launch_transpose_in(c, (const double *)dZ, n, n_draws, nullptr, nullptr, 0, -1.0, (double *)dZn, np, rp);
+        if (dsc) {
+            scale_rows_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)n_draws), 256, 0, c->stream>>>((double *)dZn, np, n_draws, (const double *)dsc);
+            LAUNCHED(c, 1);
+        }
+    } else {
+        normal_rows_kernel<<<dim3((unsigned)rp, (unsigned)((np / 2 + 255) / 256)), 256, 0, c->stream>>>((double *)dZn, np, rp, n_draws, (int)n, seed,
+                                                                                                      first_draw, (const double *)dsc);
         LAUNCHED(c, 1);
     }
     DrawArgs D;
@@ -1311,7 +1326,8 @@ extern "C" int gsum_draws(gsum_ctx *c, const double *L, int64_t n, const double 
         launch_transpose_out(c, (const double *)dYt, np, n, n_draws, 0, 1.0, nullptr, (double *)dD);
         GSUM_TRY(dev_out_finish(c, draws_out, dD, sizeof(double) * n * n_draws, mem_kind));
     }
-    if (coverage_out) GSUM_TRY(coverage_rows(c, (const double *)dYt, np, n_draws, n, lower, upper, n_alpha, coverage_out, mem_kind));
+    if (coverage_out || count_out)
+        GSUM_TRY(coverage_rows(c, (const double *)dYt, np, n_draws, n, lower, upper, n_alpha, coverage_out, count_out, mem_kind));
     return finish(c, mem_kind);
 }
 
@@ -1324,6 +1340,6 @@ extern "C" int gsum_credible_interval(gsum_ctx *c, const double *Y, int64_t n, i
     GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * n_curves, mem_kind, &dY));
     GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * rp * np, &dYt));
     launch_transpose_in(c, (const double *)dY, n, n_curves, nullptr, nullptr, 0, 1.0, (double *)dYt, np, rp);
-    GSUM_TRY(coverage_rows(c, (const double *)dYt, np, n_curves, n, lower, upper, n_alpha, coverage_out, mem_kind));
+    GSUM_TRY(coverage_rows(c, (const double *)dYt, np, n_curves, n, lower, upper, n_alpha, coverage_out, nullptr, mem_kind));
     return finish(c, mem_kind);
 }

@@ -2,7 +2,9 @@
 
 Construction factors the covariance twice on the device (Cholesky and LAPACK-dpstrf-style pivoted
 Cholesky); every method is then a forward solve, a batched `m + L z` draw or a coverage count on the GPU.
-Out of scope here: `df=` (Student-t), `eigen_errors`, `kl`, `variogram`, plotting.
+`df=` selects the Student-t variant (gsum/diagnostics.py:51-55): multivariate-t draws are the Gaussian draws
+scaled per draw by sqrt(df / chi2_df) and the interval end points come from `scipy.stats.t`.
+Out of scope here: `eigen_errors` (needs an eigensolver), `variogram`, plotting.
 """
 from __future__ import annotations
 
@@ -21,19 +23,26 @@ class Diagnostic:
     ----------
     mean : (n_samples,) array
     cov : (n_samples, n_samples) array
-    df : must be None (Gaussian)
+    df : None (Gaussian) or the degrees of freedom of a multivariate t with covariance `cov` (df > 2)
     random_state : int seed used by `samples`
     """
 
     def __init__(self, mean, cov, df=None, random_state=1):
-        if df is not None:
-            raise NotImplementedError("gsum_b200: Student-t diagnostics (df != None) are not implemented on the device path")
         self.mean = np.asarray(mean, dtype=np.float64)
         self.cov = np.asarray(cov, dtype=np.float64)
         self.sd = np.sqrt(np.diag(self.cov))
         self.random_state = random_state
-        self.udist = stats.norm(loc=self.mean, scale=self.sd)       # interval end points only (host, O(N))
-        self.std_udist = stats.norm(loc=0., scale=1.)
+        self.df = None if df is None else float(df)
+        if df is None:
+            self.udist = stats.norm(loc=self.mean, scale=self.sd)   # interval end points only (host, O(N))
+            self.std_udist = stats.norm(loc=0., scale=1.)
+        else:
+            # gsum/diagnostics.py:51-55: MVT(mean, sigma = cov (df - 2) / df, df); the marginals the reference uses for
+            # the intervals are t(loc=mean, scale=sd, df) (scale sd, not sqrt(sigma_ii): mirrored as is)
+            if not self.df > 2:
+                raise ValueError("df must be greater than 2 for the covariance to exist")
+            self.udist = stats.t(loc=self.mean, scale=self.sd, df=self.df)
+            self.std_udist = stats.t(loc=0., scale=1., df=self.df)
         self._chol = ops.cholesky(self.cov)                          # raises LinAlgError like numpy (diagnostics.py:60)
         G, Lp, piv, rank, status = ops.pivoted_cholesky(self.cov)    # diagnostics.py:61 -> helpers.py:185-199
         if status > 0:
@@ -41,25 +50,47 @@ class Diagnostic:
         self._pchol, self._pchol_L, self._piv = G, Lp, piv
 
     # -- draws -------------------------------------------------------------------------------------
+    def _draw_scale(self, n, rs):
+        """Per-draw factor turning N(0, cov) draws into multivariate-t draws with scale matrix cov (df - 2) / df:
+        sqrt((df - 2) / df) / sqrt(chi2_df / df)  (statsmodels `multivariate_t_rvs`: m + z / sqrt(x), x = chi2/df)."""
+        if self.df is None:
+            return None
+        if np.isinf(self.df):
+            return np.ones(int(n))
+        x = rs.chisquare(self.df, int(n)) / self.df
+        return np.sqrt((self.df - 2.0) / self.df) / np.sqrt(x)
+
     def samples(self, n, device_rng=False):
-        """(n_samples, n) draws from N(mean, cov): mean + L z on the device (gsum/diagnostics.py:70-82).
+        """(n_samples, n) draws from N(mean, cov) — or the multivariate t — as mean + s L z on the device
+        (gsum/diagnostics.py:70-82).
 
         z comes from numpy's RandomState(random_state) (or the device Philox generator with `device_rng`);
         the reference's scipy/numpy SVD sampler uses a different factor, so streams differ by construction."""
+        rs = np.random.RandomState(self.random_state)
         if device_rng:
-            d, _ = ops.draws(self._chol, self.mean, n_draws=int(n), seed=int(self.random_state or 0))
+            d, _ = ops.draws(self._chol, self.mean, n_draws=int(n), seed=int(self.random_state or 0),
+                             draw_scale=self._draw_scale(n, rs))
             return d
-        z = np.random.RandomState(self.random_state).standard_normal((self.mean.shape[0], int(n)))
-        d, _ = ops.draws(self._chol, self.mean, Z=z)
+        z = rs.standard_normal((self.mean.shape[0], int(n)))
+        d, _ = ops.draws(self._chol, self.mean, Z=z, draw_scale=self._draw_scale(n, rs))
         return d
 
-    def sample_coverage(self, n, intervals, seed=None):
+    def sample_coverage(self, n, intervals, seed=None, first_draw=0, n_total=None, counts=False):
         """Coverage (n, n_intervals) of `n` fresh device draws, fused with the draw so the (N, n) sample matrix is
-        never copied back (the GraphicalDiagnostic reference bands of gsum/diagnostics.py:557-584)."""
+        never copied back (the GraphicalDiagnostic reference bands of gsum/diagnostics.py:557-584).
+
+        `first_draw` / `n_total` select draws first_draw .. first_draw + n - 1 of a run of n_total draws (one shard of
+        the draw axis, gsum_b200.distributed.sample_coverage_sharded); with `counts` the int64 (n_intervals,) totals of
+        (draw, point) pairs inside each interval are returned as well."""
         lower, upper = self._bounds(intervals)
         seed = int(self.random_state or 0) if seed is None else int(seed)
-        _, cov = ops.draws(self._chol, self.mean, n_draws=int(n), seed=seed, lower=lower, upper=upper, want_draws=False)
-        return cov
+        scale = None
+        if self.df is not None:                                     # the whole run's chi-square stream, then this shard's slice
+            total = int(first_draw) + int(n) if n_total is None else int(n_total)
+            scale = self._draw_scale(total, np.random.RandomState(seed))[int(first_draw):int(first_draw) + int(n)]
+        res = ops.draws(self._chol, self.mean, n_draws=int(n), seed=seed, lower=lower, upper=upper, want_draws=False,
+                        first_draw=int(first_draw), draw_scale=scale, want_counts=counts)
+        return (res[1], res[2]) if counts else res[1]
 
     # -- errors ------------------------------------------------------------------------------------
     def individual_errors(self, y):
@@ -95,7 +126,19 @@ class Diagnostic:
         return md2[0] if single else md2
 
     def kl(self, mean, cov):
-        raise NotImplementedError("gsum_b200: kl is not implemented on the device path")
+        """gsum/diagnostics.py:116-146, term by term as the reference evaluates them: tr(cov_1^{-1} cov_0) from a device
+        cho_solve, the Mahalanobis term, and `logs = 2 sum(log diag(c1)) - logdet(c0)` — the reference takes the
+        diagonal of the covariance c1 itself there (not of its factor), which is kept.  logdet(c0) comes from a device
+        Cholesky of c0 (numpy's `slogdet` is LU based; for a covariance the two agree)."""
+        c0 = np.asarray(cov, dtype=np.float64)
+        tr = float(np.trace(ops.cho_solve(self._chol, c0)))
+        dist = float(self.md_squared(np.asarray(mean, dtype=np.float64)))
+        k = self.cov.shape[-1]
+        _, info, logdet0 = ops.cholesky(c0, return_info=True)
+        if info:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        logs = 2.0 * float(np.sum(np.log(np.diag(self.cov)))) - float(logdet0)
+        return 0.5 * (tr + dist - k + logs)
 
     # -- credible intervals ------------------------------------------------------------------------
     def _bounds(self, intervals):

@@ -1,4 +1,5 @@
-"""Sharding of the (Q, l) likelihood grid over the GPUs of one node.
+"""Sharding of the path over the GPUs of one node: the (Q, l) likelihood grid by length scale, the
+posterior draws of the credible-interval diagnostic by draw, `predict` by test point.
 
 Cells are independent given (X, y) and all the cost is per length scale (one factorisation each), so the
 length scales are dealt round-robin to the ranks of a ``torch.distributed`` process group, every rank
@@ -6,6 +7,13 @@ evaluates its (n_q, n_ls/P) block with the single-GPU path, and ONE all-gather o
 the grid on every rank; the max-shift normalisation then runs on the device.  There is no other exchange.
 Each cell is computed by exactly one rank with the same kernels, so the gathered grid is bit-identical to
 the single-GPU grid.
+
+
+Draws (config C5): every rank holds a replica of the factor, takes a contiguous slice of the draw axis (the device
+generator is counter based, so slice j reproduces exactly the draws the unsharded call would produce there) and the
+ranks exchange ONE all-reduce of the int64 coverage counts — integers, so the sum does not depend on the order.
+Predict (config C3): the fit is replicated, test points are dealt in contiguous blocks and one all-gather rebuilds the
+(M, n_curves) mean and the (M,) standard deviation; a full (M, M) covariance is not sharded.
 
 torch is used for the plumbing only (process group, device buffers for NCCL).
 """
@@ -15,7 +23,7 @@ import numpy as np
 
 from . import ops
 
-__all__ = ["shard_indices", "assemble_blocks", "lml_grid_sharded"]
+__all__ = ["shard_indices", "assemble_blocks", "lml_grid_sharded", "shard_range", "sample_coverage_sharded", "predict_sharded"]
 
 
 def shard_indices(n_ls, world_size, rank):
@@ -120,3 +128,79 @@ def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normaliz
         ops.grid_normalize_device(ctx, full_d, post_d, lse_d)
         return full_d.cpu().numpy(), post_d.cpu().numpy(), float(lse_d.cpu()[0])
     return full_d.cpu().numpy()
+
+
+def shard_range(n, world_size, rank):
+    """Contiguous slice [lo, hi) of n items owned by `rank` (sizes differ by at most one; the first ranks get the extras)."""
+    base, extra = divmod(int(n), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _comm_device(group):
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def sample_coverage_sharded(diagnostic, n_draws, intervals, seed=None, group=None, _evaluator=None):
+    """Credible-interval coverage of `n_draws` fresh posterior draws with the draw axis sharded over the ranks.
+
+    Each rank draws its slice on its GPU (`Diagnostic.sample_coverage(first_draw=lo, n_total=n_draws, counts=True)`) and
+    the only exchange is one all-reduce (sum) of the int64 counts of (draw, point) pairs inside each interval.  Returns the
+    (n_intervals,) mean coverage over all draws on every rank — identical to the 1-GPU value for the same seed."""
+    import torch
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lo, hi = shard_range(n_draws, world, rank)
+    n_alpha = np.atleast_1d(intervals).shape[0]
+    counts = np.zeros(n_alpha, dtype=np.int64)
+    if hi > lo:
+        evaluator = _evaluator or (lambda lo_, n_: diagnostic.sample_coverage(n_, intervals, seed=seed, first_draw=lo_,
+                                                                               n_total=n_draws, counts=True)[1])
+        counts = np.asarray(evaluator(lo, hi - lo), dtype=np.int64)
+    t = torch.from_numpy(counts).to(_comm_device(group))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)    # the single collective of the path
+    n_points = diagnostic.mean.shape[0]
+    return t.cpu().numpy().astype(np.float64) / (float(n_draws) * float(n_points))
+
+
+def predict_sharded(process, X, return_std=False, group=None, **predict_kw):
+    """`process.predict(X, return_std=...)` with the test points sharded over the ranks (contiguous blocks) and one
+    all-gather of the [mean | std] blocks.  `process` is a fitted ConjugateGaussianProcess / ConjugateStudentProcess /
+    TruncationGP / TruncationTP replica on every rank; extra keyword arguments (`order`, `kind`, `Xc`, `y`, ...) are passed
+    through.  A full covariance (`return_cov`) couples all test points and is not sharded."""
+    import torch
+    import torch.distributed as dist
+
+    if predict_kw.get("return_cov"):
+        raise NotImplementedError("gsum_b200: predict_sharded shards test points; a full (M, M) covariance is not sharded")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+    m = X.shape[0]
+    per = -(-m // world)
+    lo, hi = min(rank * per, m), min((rank + 1) * per, m)
+    block = None
+    if hi > lo:
+        res = process.predict(X[lo:hi], return_std=return_std, **predict_kw)
+        mean, std = res if return_std else (res, None)
+        mean2 = mean[:, None] if mean.ndim == 1 else mean
+        block = np.concatenate([mean2, std[:, None]], axis=1) if return_std else mean2
+        shape1d, width = mean.ndim == 1, block.shape[1]
+    else:
+        shape1d, width = False, 0
+    # every rank must agree on the block width even if it owns no points: rank 0 always owns some
+    meta = torch.tensor([width, int(shape1d)], dtype=torch.int64, device=_comm_device(group))
+    dist.broadcast(meta, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    width, shape1d = int(meta[0]), bool(int(meta[1]))
+    send = np.zeros((per, width))
+    if block is not None:
+        send[:hi - lo] = block
+    dev = _comm_device(group)
+    recv = torch.empty((world * per, width), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(recv, torch.from_numpy(send).to(dev), group=group)   # the single data collective
+    full = recv.cpu().numpy()[:m]
+    n_mean = width - 1 if return_std else width
+    mean = full[:, 0] if shape1d else np.ascontiguousarray(full[:, :n_mean])
+    return (mean, np.ascontiguousarray(full[:, n_mean])) if return_std else mean

@@ -310,10 +310,14 @@ def pc_errors(Lp, piv, mean, Y, ctx=None):
     return E
 
 
-def draws(L, mean, Z=None, n_draws=None, seed=0, lower=None, upper=None, want_draws=True, ctx=None):
+def draws(L, mean, Z=None, n_draws=None, seed=0, lower=None, upper=None, want_draws=True, first_draw=0, draw_scale=None,
+          want_coverage=True, want_counts=False, ctx=None):
     """mean + L z for caller-supplied Z (n, n_draws) or device Philox normals; optional fused coverage.
 
-    Returns (draws (n, n_draws) or None, coverage (n_draws, n_alpha) or None)."""
+    `first_draw` places this call's draws at global positions first_draw .. first_draw + n_draws - 1 of the seed's
+    stream (sharding of the draw axis); `draw_scale` (n_draws,) multiplies each draw's normals (multivariate t).
+    Returns (draws (n, n_draws) or None, coverage (n_draws, n_alpha) or None) — and, with `want_counts`, a third item:
+    the int64 (n_alpha,) number of (draw, point) pairs inside each interval."""
     ctx = ctx or default_context()
     L = as_f64(L)
     n = L.shape[0]
@@ -323,14 +327,20 @@ def draws(L, mean, Z=None, n_draws=None, seed=0, lower=None, upper=None, want_dr
         n_draws = Z.shape[1]
     if not n_draws:
         raise ValueError("n_draws must be given when Z is None")
+    draw_scale = _vec(draw_scale, n_draws, "draw_scale")
     out = np.empty((n, n_draws)) if want_draws else None
-    cov, n_alpha = None, 0
+    cov, counts, n_alpha = None, None, 0
     if lower is not None:
         lower, upper = as_f64(np.atleast_2d(lower)), as_f64(np.atleast_2d(upper))
         n_alpha = lower.shape[0]
-        cov = np.empty((n_draws, n_alpha))
-    ctx.check(ctx.lib.gsum_draws(ctx.handle, _p(L), n, _p(mean), _p(Z), n_draws, int(seed), _p(out), _p(lower), _p(upper),
-                                 n_alpha, _p(cov), MEM_HOST), "gsum_draws")
+        cov = np.empty((n_draws, n_alpha)) if want_coverage else None
+        counts = np.zeros(n_alpha, dtype=np.int64) if want_counts else None
+    elif want_counts:
+        raise ValueError("coverage counts need lower and upper")
+    ctx.check(ctx.lib.gsum_draws(ctx.handle, _p(L), n, _p(mean), _p(Z), n_draws, int(seed), int(first_draw), _p(draw_scale),
+                                 _p(out), _p(lower), _p(upper), n_alpha, _p(cov), _p(counts), MEM_HOST), "gsum_draws")
+    if want_counts:
+        return out, cov, counts
     return out, cov
 
 

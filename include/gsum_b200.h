@@ -183,13 +183,19 @@ int gsum_pc_errors(gsum_ctx *ctx, const double *Lp, const int32_t *piv, int64_t 
                    const double *Y, int64_t n_curves, double *E, int32_t mem_kind);
 
 /* gsum_draws: draws = mean + L z (gsum/diagnostics.py:82, models.py:872 up to the sampler's stream).
- *   Z (n, n_draws) caller-supplied standard normals, or NULL to generate them on the device (Philox, `seed`).
+ *   Z (n, n_draws) caller-supplied standard normals, or NULL to generate them on the device (Philox, `seed`;
+ *   draw j of this call is GLOBAL draw first_draw + j of the seed's stream, so the draw axis shards over GPUs,
+ *   SURVEY.md 8e, with every rank reproducing its slice of the unsharded call).
+ *   draw_scale (n_draws,) or NULL multiplies draw j's normals: multivariate-t draws are Gaussian draws times
+ *   sqrt(df / chi2_df) (statsmodels MVT.rvs behind gsum/diagnostics.py:51-55).
  *   draws_out (n, n_draws) or NULL.  Credible-interval coverage fused into the same pass
  *   (gsum/diagnostics.py:148-171): lower, upper (n_alpha, n) interval bounds per point (or NULL to skip);
- *   coverage_out (n_draws, n_alpha) = mean over points of 1[lower < y < upper]. */
+ *   coverage_out (n_draws, n_alpha) or NULL = mean over points of 1[lower < y < upper];
+ *   count_out (n_alpha,) int64 or NULL = number of (draw, point) pairs inside each interval (exact integers: the
+ *   quantity a sharded run all-reduces). */
 int gsum_draws(gsum_ctx *ctx, const double *L, int64_t n, const double *mean, const double *Z, int64_t n_draws,
-               uint64_t seed, double *draws_out, const double *lower, const double *upper, int32_t n_alpha,
-               double *coverage_out, int32_t mem_kind);
+               uint64_t seed, int64_t first_draw, const double *draw_scale, double *draws_out, const double *lower,
+               const double *upper, int32_t n_alpha, double *coverage_out, int64_t *count_out, int32_t mem_kind);
 
 /* gsum_credible_interval: coverage of given curves Y (n, n_curves) (gsum/diagnostics.py:148-171). */
 int gsum_credible_interval(gsum_ctx *ctx, const double *Y, int64_t n, int64_t n_curves, const double *lower,

@@ -625,10 +625,12 @@ def individual_errors(y, mean, cov):
     return ((y.T - mean) / np.sqrt(np.diag(cov))).T
 
 
-def credible_interval(y, mean, cov, intervals):
-    """gsum/diagnostics.py:148-171 (df=None) — fraction of points inside each central interval."""
+def credible_interval(y, mean, cov, intervals, df=None):
+    """gsum/diagnostics.py:148-171 — fraction of points inside each central interval; the marginals are
+    norm(mean, sd) for df=None and t(df, loc=mean, scale=sd) otherwise (gsum/diagnostics.py:48, 54)."""
     sd = np.sqrt(np.diag(cov))
-    lower, upper = st.norm(loc=mean, scale=sd).interval(np.atleast_2d(intervals).T)
+    udist = st.norm(loc=mean, scale=sd) if df is None else st.t(loc=mean, scale=sd, df=df)
+    lower, upper = udist.interval(np.atleast_2d(intervals).T)
 
     def diagnostic(data_, lower_, upper_):
         return np.average((lower_ < data_) & (data_ < upper_), axis=1)
@@ -642,3 +644,22 @@ def draws_from_z(mean, chol, z):
     standard-normal z (N, n).  (The reference draws through numpy's SVD-based legacy sampler, whose
     stream cannot be reproduced off-host; the distribution of m + L z is identical.)"""
     return mean[:, None] + chol @ z
+
+
+def mvt_draws_from_z(mean, cov, df, z, x):
+    """Student-t branch of gsum/diagnostics.py:51-55, 82: `MVT(mean, sigma = cov (df - 2) / df, df).rvs`.  MVT is
+    statsmodels' (not installed here; no version pinned by the reference): its published sampler
+    `multivariate_t_rvs` returns m + z_sigma / sqrt(x) with z_sigma ~ N(0, sigma) and x = chi2_df / df.  Deterministic
+    half for caller-supplied standard normals z (N, n) and x (n,): z_sigma = chol(sigma) z."""
+    sigma = cov * (df - 2.0) / df
+    return mean[:, None] + (np.linalg.cholesky(sigma) @ z) / np.sqrt(x)[None, :]
+
+
+def kl_divergence(mean1, cov1, chol1, mean0, cov0):
+    """gsum/diagnostics.py:116-146 as written: note `logs` uses diag(c1), the covariance's own diagonal (the reference's
+    expression), not the diagonal of its Cholesky factor."""
+    tr = np.trace(cho_solve((chol1, True), cov0))
+    dist = md_squared(mean0, mean1, chol1)
+    k = cov1.shape[-1]
+    logs = 2 * np.sum(np.log(np.diag(cov1))) - np.linalg.slogdet(cov0)[-1]
+    return 0.5 * (tr + dist - k + logs)

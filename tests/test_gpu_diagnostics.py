@@ -161,3 +161,96 @@ def test_c5_full_size_properties(ctx):
     iv = np.linspace(0, 1, 101)
     cv = d.sample_coverage(100000, iv)
     assert cv.shape == (100000, 101) and np.max(np.abs(cv.mean(0) - iv)) < 2e-3
+
+
+def test_c5_student_diag_golden_and_kl(ctx, golden):
+    """Student-t Diagnostic (gsum/diagnostics.py:51-55: multivariate-t draws, t interval end points) and Diagnostic.kl
+    (116-146) against outputs of the reference itself (tests/golden/make_golden_student_diag.py)."""
+    from test_oracle import student_diag_covs
+    g = golden("c5_student_diag")
+    cov, cov0 = student_diag_covs(g)
+    mean, df, Y = g["mean"], float(g["df"]), g["Y"]
+    d = gb.Diagnostic(mean, cov, df=df, random_state=3)
+    # deterministic half of MVT.rvs: m + sqrt((df-2)/df) L z / sqrt(x) with the reference run's own (z, x)
+    scale = np.sqrt((df - 2.0) / df) / np.sqrt(g["x"])
+    Lh = np.linalg.cholesky(cov)
+    D, _ = ops.draws(Lh, mean, Z=g["z"], draw_scale=scale)                             # same factor: isolates the draw pass
+    assert relerr(D, mean[:, None] + (Lh @ g["z"]) * scale[None, :]) < 1e-14
+    assert relerr(D, Y) < 1e-9              # the reference factors sigma = cov (df-2)/df itself: 6e-11 apart at cond 1.4e7
+    D, _ = ops.draws(d._chol, mean, Z=g["z"], draw_scale=scale)                        # device factor: cond(cov) ~ 1e6 * eps
+    assert relerr(D, Y) < 1e-9
+    assert np.array_equal(d.credible_interval(Y, g["intervals"]), g["coverage"])     # t(df, mean, sd) end points, integer counts
+    assert relerr(d.md_squared(Y), g["md2"]) < 1e-10
+    assert relerr(d.cholesky_errors(Y), g["chol_errors"]) < 1e-9
+    assert relerr(d.pivoted_cholesky_errors(Y), g["pc_errors"]) < 1e-8
+    assert relerr(d.individual_errors(Y), g["ind_errors"]) < 1e-15
+    gd = gb.Diagnostic(mean, cov, random_state=1)
+    assert gd.kl(g["mean0"], cov0) == pytest.approx(float(g["kl"]), rel=1e-10)
+    assert gd.kl(mean, cov) == pytest.approx(float(g["kl_self"]), rel=1e-10)
+    # facade draws: numpy stream for (z, chi2) through the same device pass; device generator: heavy tails, covariance = cov
+    rs = np.random.RandomState(3)
+    z = rs.standard_normal((len(mean), 8))
+    x = rs.chisquare(df, 8) / df
+    assert relerr(d.samples(8), o.mvt_draws_from_z(mean, cov, df, z, x)) < 1e-9
+    S = d.samples(20000, device_rng=True)
+    sd = np.sqrt(np.diag(cov))
+    assert np.max(np.abs(S.var(1) / sd ** 2 - 1.0)) < 0.15                           # cov of MVT(sigma = cov (df-2)/df) is cov
+    md2 = d.md_squared(S) / len(mean) * df / (df - 2.0)                                 # ~ F(N, df)
+    assert st.kstest(md2, st.f(len(mean), df).cdf).pvalue > 1e-3
+
+
+def test_draw_axis_shards_reproduce_the_unsharded_run(ctx, golden):
+    """slices of the draw axis generated with `first_draw` equal the unsharded call column for column,
+    and the int64 coverage counts add up exactly — Gaussian and Student-t."""
+    from gsum_b200.distributed import shard_range
+    g = golden("c5_diagnostics")
+    iv = g["intervals"][::10]
+    n, nd = len(g["mean"]), 1000
+    for df in (None, 5.0):
+        d = gb.Diagnostic(g["mean"], g["cov"], df=df, random_state=9)
+        cov_full, cnt_full = d.sample_coverage(nd, iv, counts=True)
+        assert np.array_equal(cnt_full, np.rint(cov_full * n).astype(np.int64).sum(0))
+        parts, cnts = [], np.zeros(len(iv), dtype=np.int64)
+        for r in range(3):
+            lo, hi = shard_range(nd, 3, r)
+            c, k = d.sample_coverage(hi - lo, iv, first_draw=lo, n_total=nd, counts=True)
+            parts.append(c)
+            cnts += k
+        assert np.array_equal(np.concatenate(parts), cov_full) and np.array_equal(cnts, cnt_full)
+    L, mean = d._chol, g["mean"]
+    full, _ = ops.draws(L, mean, n_draws=200, seed=4)
+    part, _ = ops.draws(L, mean, n_draws=70, seed=4, first_draw=130)
+    assert np.array_equal(part, full[:, 130:])
+
+
+def test_sharded_draws_and_predict_nccl_single_rank(ctx, golden):
+    """The NCCL branches of `sample_coverage_sharded` / `predict_sharded` on a one-rank group equal the plain calls."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from gsum_b200.distributed import predict_sharded, sample_coverage_sharded
+    g = golden("c5_diagnostics")
+    iv = g["intervals"][::5]
+    d = gb.Diagnostic(g["mean"], g["cov"], random_state=2)
+    rs = np.random.RandomState(0)
+    X = np.linspace(0, 1, 90)[:, None]
+    y = np.linalg.cholesky(RBF(0.2)(X) + 1e-6 * np.eye(90)) @ rs.randn(90, 3)
+    from sklearn.gaussian_process.kernels import WhiteKernel
+    gp = gb.ConjugateGaussianProcess(RBF(0.2, 'fixed') + WhiteKernel(1e-6, 'fixed'), center=0, disp=0, df=1, scale=1).fit(X, y)
+    Xn = rs.rand(257, 1)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29900 + os.getpid() % 300))
+    torch.cuda.set_device(0)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        cv = sample_coverage_sharded(d, 3000, iv, group=dist.group.WORLD)
+        m, s = predict_sharded(gp, Xn, return_std=True, group=dist.group.WORLD)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    cov1, cnt1 = d.sample_coverage(3000, iv, counts=True)
+    assert np.array_equal(cv, cnt1.astype(np.float64) / (3000.0 * len(g["mean"]))) and relerr(cv, cov1.mean(0)) < 1e-14
+    mw, sw = gp.predict(Xn, return_std=True)
+    assert np.array_equal(m, mw) and np.array_equal(s, sw)

@@ -104,6 +104,63 @@ def test_sharded_grid_gloo_world2():
     assert np.array_equal(res[0], want) and np.array_equal(res[1], want)
 
 
+class _FakeDiagnostic:
+    mean = np.zeros(7)
+
+
+class _FakeProcess:
+    """predict = a known function of the test points (stands in for a fitted replica)."""
+
+    def predict(self, X, return_std=False, order=None):
+        mean = np.stack([X[:, 0] * 2.0 + (order or 0), X[:, 0] ** 2], axis=1)
+        return (mean, np.abs(X[:, 0]) + 0.5) if return_std else mean
+
+
+def _draws_predict_worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from gsum_b200.distributed import predict_sharded, sample_coverage_sharded, shard_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_draws, intervals = 11, np.linspace(0.1, 0.9, 4)
+
+    def evaluator(lo, n):                     # counts a 1-GPU run would produce for draws lo .. lo + n - 1
+        j = np.arange(lo, lo + n)
+        return np.array([(j % (a + 2)).sum() for a in range(4)], dtype=np.int64)
+
+    cov = sample_coverage_sharded(_FakeDiagnostic(), n_draws, intervals, _evaluator=evaluator)
+    X = np.linspace(-1, 1, 9)[:, None]
+    m, s = predict_sharded(_FakeProcess(), X, return_std=True, order=3)
+    m_only = predict_sharded(_FakeProcess(), X[:1])                 # fewer points than ranks: rank 1 owns nothing
+    q.put((rank, cov, m, s, m_only, shard_range(n_draws, world, rank)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_draws_and_predict_gloo_world2():
+    """World-size-2 gloo run of the draw-axis all-reduce and the test-point all-gather."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_draws_predict_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r[0]: r[1:] for r in (q.get(timeout=120) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    j = np.arange(11)
+    want_cov = np.array([(j % (a + 2)).sum() for a in range(4)], dtype=float) / (11 * 7)
+    X = np.linspace(-1, 1, 9)
+    assert res[0][4] == (0, 6) and res[1][4] == (6, 11)
+    for r in range(2):
+        cov, m, s, m_only, _ = res[r]
+        assert np.array_equal(cov, want_cov)
+        assert np.array_equal(m, np.stack([X * 2.0 + 3, X ** 2], axis=1)) and np.array_equal(s, np.abs(X) + 0.5)
+        assert m_only.shape == (1, 2) and np.array_equal(m_only[0], [-2.0, 1.0])
+
+
 def test_facade_rejects_out_of_scope_options():
     from gsum_b200 import ConjugateGaussianProcess, Diagnostic, TruncationGP
     with pytest.raises(NotImplementedError):
@@ -114,8 +171,8 @@ def test_facade_rejects_out_of_scope_options():
     gp = ConjugateGaussianProcess(RBF(0.2, 'fixed'), decomposition='lu')
     with pytest.raises(ValueError):
         gp.fit(np.zeros((3, 1)), np.zeros(3))
-    with pytest.raises(NotImplementedError):
-        Diagnostic(np.zeros(3), np.eye(3), df=5)
+    with pytest.raises(ValueError):
+        Diagnostic(np.zeros(3), np.eye(3), df=2)                           # multivariate t without a covariance
     with pytest.raises(RuntimeError):
         ConjugateGaussianProcess(RBF(0.2, 'fixed')).predict(np.zeros((2, 1)), return_std=True, return_cov=True)
     with pytest.raises(ValueError):

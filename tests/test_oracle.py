@@ -114,6 +114,28 @@ def test_c5_diagnostics(golden):
     assert relerr((g["pc_errors"] ** 2).sum(0), g["md2"]) < 1e-8
 
 
+def student_diag_covs(g):
+    """cov / cov0 of tests/golden/make_golden_student_diag.py rebuilt from the saved (Xd, amp)."""
+    from sklearn.gaussian_process.kernels import RBF
+    n = g["Xd"].shape[0]
+    aa = np.outer(g["amp"], g["amp"])
+    return 1.3 * aa * (RBF(0.2)(g["Xd"]) + 1e-5 * np.eye(n)), 0.9 * aa * (RBF(0.25)(g["Xd"]) + 2e-5 * np.eye(n))
+
+
+def test_c5_student_diagnostics_and_kl(golden):
+    """Student-t Diagnostic (gsum/diagnostics.py:51-55) and Diagnostic.kl (116-146) against the reference's outputs."""
+    g = golden("c5_student_diag")
+    cov, cov0 = student_diag_covs(g)
+    mean, df, Y = g["mean"], float(g["df"]), g["Y"]
+    assert relerr(o.mvt_draws_from_z(mean, cov, df, g["z"], g["x"]), Y) < 1e-14
+    assert np.array_equal(o.credible_interval(Y, mean, cov, g["intervals"], df=df), g["coverage"])
+    ch = np.linalg.cholesky(cov)
+    assert relerr(o.md_squared(Y, mean, ch), g["md2"]) < TOL
+    assert relerr(o.cholesky_errors(Y.T, mean, ch).T, g["chol_errors"]) < TOL
+    assert float(o.kl_divergence(mean, cov, ch, g["mean0"], cov0)) == pytest.approx(float(g["kl"]), rel=1e-12)
+    assert float(o.kl_divergence(mean, cov, ch, mean, cov)) == pytest.approx(float(g["kl_self"]), rel=1e-12)
+
+
 def test_kat_pivoted_cholesky(golden):
     """gsum/tests/test.py:75-122 (tabulated, atol 1e-4) and examples/model_checking_tests.ipynb cell 6 (pivots [4 1 3 2])."""
     g = golden("kat_pivoted_cholesky")
