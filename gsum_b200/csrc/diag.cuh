@@ -21,7 +21,7 @@
 // Output: G = Lb (rows in original order: M = G G^T, the array gsum's pivoted_cholesky returns) and
 // Lp[i] = Lb[piv[i]] (LAPACK's lower factor of P^T M P).
 // ------------------------------------------------------------------------------------------------
-#define PSTRF_THREADS 1024
+#define PSTRF_ROWS 128               // physical rows per CTA of the panel kernel (one row per thread)
 #define PSTRF_NB 64
 
 struct PstrfState {          // device-resident scalars
@@ -29,103 +29,113 @@ struct PstrfState {          // device-resident scalars
     int info;                // 0 ok, 1 = stopped early (matrix not positive definite to working precision)
     double dstop;
 };
+struct PstrfSlot { double v; int i; int pad; };       // one CTA's pivot candidate: value and LOGICAL position
 
-__global__ void pstrf_init_kernel(int32_t *piv, PstrfState *st, int n) {
+__global__ void pstrf_init_kernel(int32_t *piv, int32_t *pos, PstrfState *st, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) piv[i] = i;
+    if (i < n) { piv[i] = i; pos[i] = i; }
     if (i == 0) { st->rank = 0; st->info = 0; st->dstop = 0.0; }
 }
 
-// One block of up to 64 columns starting at logical column k.  Single CTA; shared memory holds the running
-// diagonal (dg), dpstrf's work array, the most recent factor column and the inverse permutation pos[] — all by
-// physical row, so every sweep over the rows is a unit-stride sweep.  Pt (64 x ld, global, L2 resident) keeps the
-// current block's factor columns TRANSPOSED so the per-column dgemv reads it coalesced.
-__global__ void __launch_bounds__(PSTRF_THREADS, 1) pstrf_panel_kernel(const double *__restrict__ Af, double *__restrict__ Lb,
-                                                                       double *__restrict__ Pt, int64_t ld, int n, int k,
-                                                                       int32_t *piv, PstrfState *st) {
-    extern __shared__ __align__(16) double sm[];
-    double *work = sm, *dg = sm + n, *col = sm + 2 * n;
-    double *lrow = sm + 3 * n;                       // 64: the pivot row's factor entries of this block
-    double *redv = lrow + PSTRF_NB;                  // 32
-    int *redi = (int *)(redv + 32);                  // 32
-    int *pos = redi + 32;                            // n: logical position of physical row p
-    __shared__ int s_pvt, s_stop;
-    __shared__ double s_ajj;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (st->info != 0) return;                       // an earlier block already stopped
-    const int jb = min(PSTRF_NB, n - k);
-    for (int p = tid; p < n; p += PSTRF_THREADS) {
-        work[p] = 0.0; dg[p] = Af[(int64_t)p * ld + p]; col[p] = 0.0;
-        pos[piv[p]] = p;
+#define PSTRF_BETTER(v, i, bv, bi) ((v) > (bv) || ((v) == (bv) && (i) < (bi)))   // first maximum in logical order: a total order
+__device__ __forceinline__ void pstrf_block_argmax(double &bv, int &bi, double *redv, int *redi) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (PSTRF_BETTER(ov, oi, bv, bi)) { bv = ov; bi = oi; }
     }
-    if (tid == 0) s_stop = 0;
+    if (lane == 0) { redv[w] = bv; redi[w] = bi; }
+    __syncthreads();
+    bv = redv[0]; bi = redi[0];
+#pragma unroll
+    for (int x = 1; x < PSTRF_ROWS / 32; x++) if (PSTRF_BETTER(redv[x], redi[x], bv, bi)) { bv = redv[x]; bi = redi[x]; }
+    __syncthreads();
+}
+
+// One block of up to 64 columns starting at logical column k: a COOPERATIVE launch of ceil(n / 128) CTAs, each owning 128
+// physical rows (one per thread: running diagonal, dpstrf's work entry, the logical position and the most recent factor
+// entry live in registers; the row's entries of the current block sit in shared memory for the per-column dgemv).
+// Per column: every CTA publishes its best pivot candidate, ONE grid barrier, every CTA reduces the same candidate list
+// to the same pivot (the order is total, so the result does not depend on the reduction tree), swaps its private copy
+// of piv[], fetches the pivot row's block entries from Pt (global, written before the barrier) and updates its rows.
+// The arithmetic per row is sequential in the block column index, exactly as in the single-CTA version this replaces.
+__global__ void __launch_bounds__(PSTRF_ROWS) pstrf_panel_kernel(const double *__restrict__ Af, double *__restrict__ Lb,
+                                                                 double *Pt, int64_t ld, int n, int k, int32_t *piv, int32_t *posg,
+                                                                 PstrfState *st, PstrfSlot *slots) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double sm[];
+    double *ptl = sm;                                  // [64][128]: this CTA's rows of the block's factor columns, transposed
+    int *pivs = (int *)(sm + PSTRF_NB * PSTRF_ROWS);   // [n]: private copy of logical position -> physical row
+    __shared__ double redv[PSTRF_ROWS / 32], lrow[PSTRF_NB];
+    __shared__ int redi[PSTRF_ROWS / 32];
+    const int tid = threadIdx.x, p = blockIdx.x * PSTRF_ROWS + tid, ncta = gridDim.x;
+    const bool live = p < n;
+    if (st->info != 0) return;                         // an earlier block already stopped (uniform over the grid)
+    const int jb = min(PSTRF_NB, n - k);
+    for (int i = tid; i < n; i += PSTRF_ROWS) pivs[i] = piv[i];
+    double work = 0.0, col = 0.0, dstop = st->dstop;
+    const double dg = live ? Af[(int64_t)p * ld + p] : 0.0;
+    int pos = live ? posg[p] : -1;
     __syncthreads();
     for (int j = k; j < k + jb; j++) {
-        // ---- running diagonal + pivot search: first maximum in LOGICAL order among positions >= j ---------------
+        // ---- running diagonal + pivot candidate: first maximum in LOGICAL order among positions >= j -------------
         double bv = -INFINITY; int bi = 0x7fffffff;
-        for (int p = tid; p < n; p += PSTRF_THREADS) {
-            const int i = pos[p];
-            if (i < j) continue;
-            if (j > k) work[p] += col[p] * col[p];
-            const double c = dg[p] - work[p];
-            if (c > bv || (c == bv && i < bi)) { bv = c; bi = i; }
+        if (live && pos >= j) {
+            if (j > k) work += col * col;
+            bv = dg - work; bi = pos;
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        pstrf_block_argmax(bv, bi, redv, redi);
+        PstrfSlot *sl = slots + (j & 1) * ncta;
+        if (tid == 0) { PstrfSlot s; s.v = bv; s.i = bi; s.pad = 0; sl[blockIdx.x] = s; }
+        grid.sync();
+        bv = -INFINITY; bi = 0x7fffffff;
+        for (int x = tid; x < ncta; x += PSTRF_ROWS) {
+            const double ov = __ldcg(&sl[x].v);
+            const int oi = __ldcg(&sl[x].i);
+            if (PSTRF_BETTER(ov, oi, bv, bi)) { bv = ov; bi = oi; }
         }
-        if (lane == 0) { redv[w] = bv; redi[w] = bi; }
+        pstrf_block_argmax(bv, bi, redv, redi);
+        if (j == 0) dstop = (double)n * 1.1102230246251565e-16 * bv;              // N * DLAMCH('Epsilon') * max diag
+        const bool bad = (j == 0) ? !(bv > 0.0) : !(bv > dstop);
+        if (bad || bi == 0x7fffffff) {                                              // uniform: every CTA sees the same pivot
+            if (blockIdx.x == 0 && tid == 0) { st->info = 1; st->rank = j; if (j == 0) st->dstop = dstop; }
+            if (blockIdx.x == 0) for (int i = tid; i < n; i += PSTRF_ROWS) piv[i] = pivs[i];
+            if (live) posg[p] = pos;
+            return;
+        }
+        const int pj = pivs[bi], pold = pivs[j];                                    // interchange logical positions j and pvt
         __syncthreads();
-        if (w == 0) {
-            bv = redv[lane]; bi = redi[lane];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-            }
-            if (lane == 0) {
-                double dstop = st->dstop;
-                if (j == 0) { dstop = (double)n * 1.1102230246251565e-16 * bv; st->dstop = dstop; }   // N * DLAMCH('Epsilon') * max diag
-                const bool bad = (j == 0) ? !(bv > 0.0) : !(bv > dstop);
-                if (bad || bi == 0x7fffffff) { s_stop = 1; st->info = 1; st->rank = j; }
-                else {
-                    const int pj = piv[bi], pold = piv[j];      // interchange logical positions j and pvt
-                    piv[bi] = pold; piv[j] = pj;
-                    pos[pold] = bi; pos[pj] = j;
-                    s_pvt = pj; s_ajj = bv;
-                }
-            }
-        }
-        __syncthreads();
-        if (s_stop) return;
-        const int pj = s_pvt;
-        const double ajj = sqrt(s_ajj), inv = 1.0 / ajj;
+        if (tid == 0) { pivs[bi] = pold; pivs[j] = pj; }
+        if (live) { if (p == pold) pos = bi; if (p == pj) pos = j; }
+        const double ajj = sqrt(bv), inv = 1.0 / ajj;
         const int nprev = j - k;
-        if (tid < nprev) lrow[tid] = Pt[(int64_t)tid * ld + pj];
+        if (tid < nprev) lrow[tid] = __ldcg(Pt + (int64_t)tid * ld + pj);
         __syncthreads();
         // ---- column j (dgemv with the block's previous columns, then dscal by 1/ajj) ---------------------------
-        for (int p = tid; p < n; p += PSTRF_THREADS) {
-            const int i = pos[p];
-            if (i < j) continue;                    // already pivoted: its entry in column j stays an exact 0
+        if (live && pos >= j) {                 // rows already pivoted keep an exact 0 in column j
             double v;
-            if (i == j) v = ajj;
+            if (pos == j) v = ajj;
             else {
                 v = Af[(int64_t)pj * ld + p];
-                const double *pp = Pt + p;
 #pragma unroll 8
-                for (int m = 0; m < nprev; m++) v = fma(-pp[(int64_t)m * ld], lrow[m], v);
+                for (int m = 0; m < nprev; m++) v = fma(-ptl[m * PSTRF_ROWS + tid], lrow[m], v);
                 v *= inv;
             }
+            ptl[nprev * PSTRF_ROWS + tid] = v;
             Pt[(int64_t)nprev * ld + p] = v;
             Lb[(int64_t)p * ld + j] = v;
-            col[p] = (i == j) ? 0.0 : v;
+            col = (pos == j) ? 0.0 : v;
         }
-        __syncthreads();
     }
-    if (tid == 0) st->rank = k + jb;
+    if (blockIdx.x == 0) {
+        __syncthreads();
+        for (int i = tid; i < n; i += PSTRF_ROWS) piv[i] = pivs[i];
+        if (tid == 0) { st->rank = k + jb; if (k == 0) st->dstop = dstop; }
+    }
+    if (live) posg[p] = pos;
 }
 
 // Lp[i][c] = Lb[piv[i]][c] for c <= i (zero above): LAPACK's factor of P^T M P.
@@ -210,18 +220,32 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(double *__restrict__ Zn
 // Credible-interval coverage  (gsum/diagnostics.py:148-171)
 // cov[dr][a] = mean_i 1[lower[a][i] < y[dr][i] < upper[a][i]].  16 draws per CTA share each staged
 // (n_alpha x 32 points) slice of the bounds; counts are integers, so the result is order independent.
+// Central intervals at increasing levels are NESTED at every point (lower non-increasing, upper non-decreasing in a);
+// `coverage_nested_kernel` checks that on the device and the counting kernel then finds, per (draw, point), the first
+// interval containing y by bisection (7 probes instead of n_alpha comparisons) and builds a histogram whose prefix
+// sums are the counts.  Bounds in any other order take the comparison-per-interval path; both give the same integers.
 // ------------------------------------------------------------------------------------------------
 #define COVG_WARPS 16
 #define COVG_MAXA 128
+__global__ void __launch_bounds__(256) coverage_nested_kernel(const double *__restrict__ lower, const double *__restrict__ upper, int n_alpha,
+                                                              int n, int *__restrict__ nested) {
+    const int64_t total = (int64_t)(n_alpha - 1) * n;
+    bool ok = true;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+        ok = ok && (lower[e + n] <= lower[e]) && (upper[e + n] >= upper[e]);          // false for NaN as well
+    if (!ok) *nested = 0;
+}
 __global__ void __launch_bounds__(COVG_WARPS * 32) coverage_rows_kernel(const double *__restrict__ Yt, int64_t ld, int64_t n_draws, int n,
                                                                         const double *__restrict__ lower, const double *__restrict__ upper,
                                                                         int n_alpha, double *__restrict__ out,
-                                                                        unsigned long long *__restrict__ counts) {
+                                                                        unsigned long long *__restrict__ counts,
+                                                                        const int *__restrict__ nested_flag) {
     extern __shared__ __align__(16) double sm[];
     double *lo = sm, *up = sm + (size_t)n_alpha * 32;
     int *cnt = (int *)(up + (size_t)n_alpha * 32);       // [COVG_WARPS][n_alpha]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t dr = (int64_t)blockIdx.x * COVG_WARPS + w;
+    const bool nested = *nested_flag != 0;
     for (int e = tid; e < COVG_WARPS * n_alpha; e += COVG_WARPS * 32) cnt[e] = 0;
     for (int x0 = 0; x0 < n; x0 += 32) {
         __syncthreads();
@@ -234,14 +258,38 @@ __global__ void __launch_bounds__(COVG_WARPS * 32) coverage_rows_kernel(const do
         if (dr < n_draws) {
             const int xx = x0 + lane;
             const double y = xx < n ? Yt[dr * ld + xx] : 0.0;
-            for (int a = 0; a < n_alpha; a++) {
-                const bool in = (lo[a * 32 + lane] < y) && (y < up[a * 32 + lane]);
-                const unsigned m = __ballot_sync(0xffffffffu, in);
-                if (lane == 0) cnt[w * n_alpha + a] += __popc(m);
+            if (nested) {
+                // first a with lower[a] < y < upper[a] (the predicate is monotone in a); n_alpha if there is none
+                int lo_a = 0, hi_a = n_alpha;
+                while (lo_a < hi_a) {
+                    const int mid = (lo_a + hi_a) >> 1;
+                    const bool in = (lo[mid * 32 + lane] < y) && (y < up[mid * 32 + lane]);
+                    if (in) hi_a = mid; else lo_a = mid + 1;
+                }
+                if (xx < n && lo_a < n_alpha) atomicAdd(&cnt[w * n_alpha + lo_a], 1);
+            } else {
+                for (int a = 0; a < n_alpha; a++) {
+                    const bool in = (lo[a * 32 + lane] < y) && (y < up[a * 32 + lane]);
+                    const unsigned m = __ballot_sync(0xffffffffu, in);
+                    if (lane == 0) cnt[w * n_alpha + a] += __popc(m);
+                }
             }
         }
     }
     __syncwarp();
+    if (nested && dr < n_draws) {                        // histogram of first-containing intervals -> counts: inclusive prefix sums
+        int carry = 0;
+        for (int a0 = 0; a0 < n_alpha; a0 += 32) {
+            const int a = a0 + lane;
+            int v = a < n_alpha ? cnt[w * n_alpha + a] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            v += carry;
+            if (a < n_alpha) cnt[w * n_alpha + a] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+        __syncwarp();
+    }
     if (out && dr < n_draws)
         for (int a = lane; a < n_alpha; a += 32) out[dr * n_alpha + a] = (double)cnt[w * n_alpha + a] / (double)n;
     if (counts) {                                        // integer totals over the rows of this launch: order independent

@@ -19,9 +19,9 @@
 enum {
     WS_X = 0, WS_XS, WS_DY, WS_REF, WS_ORD, WS_LS, WS_Q, WS_DETF, WS_MAT, WS_RHS, WS_GRAM, WS_LOGDET, WS_INFO,
     WS_LL, WS_IO0, WS_IO1, WS_IO2, WS_IO3, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_MKK, WS_G0, WS_G1, WS_G2, WS_G3, WS_G4, WS_G5,
-    WS_SCALE, WS_COUNTS
+    WS_SCALE, WS_COUNTS, WS_NESTED
 };
-static_assert(WS_COUNTS < GSUM_NWS, "workspace slots");
+static_assert(WS_NESTED < GSUM_NWS, "workspace slots");
 
 extern "C" int gsum_version(void) { return 100; }
 
@@ -1181,27 +1181,41 @@ extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, con
 extern "C" int gsum_pivoted_cholesky(gsum_ctx *c, const double *M, int64_t n, double *Lp, int32_t *piv, int32_t *rank,
                                      double *G_out, int32_t mem_kind) {
     if (!c || !M || n <= 0) return gsum_fail(c, -1, "gsum_pivoted_cholesky: bad argument");
-    const size_t smem = sizeof(double) * (3 * n + PSTRF_NB + 32) + sizeof(int) * (32 + n);
-    if (smem > 220 * 1024) return gsum_fail(c, -1, "gsum_pivoted_cholesky: n = %lld exceeds the single-CTA panel limit (~8000)", (long long)n);
+    // the panel kernel is a cooperative launch of one CTA per 128 rows (all co-resident: 64.5 KiB + 4 n bytes of shared memory each)
+    const size_t smem = sizeof(double) * PSTRF_NB * PSTRF_ROWS + sizeof(int) * n;
+    const int ncta = (int)((n + PSTRF_ROWS - 1) / PSTRF_ROWS);
     GSUM_CUDA(c, cudaSetDevice(c->device));
     GSUM_TRY(chol_set_attrs(c));
-    GSUM_CUDA(c, cudaFuncSetAttribute(pstrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    GSUM_CUDA(c, cudaFuncSetAttribute(pstrf_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        int per_sm = 0, sms = 0;
+        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pstrf_panel_kernel, PSTRF_ROWS, smem));
+        GSUM_CUDA(c, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+        if (smem > 220 * 1024 || ncta > per_sm * sms)
+            return gsum_fail(c, -1, "gsum_pivoted_cholesky: n = %lld needs %d co-resident CTAs (limit %d)", (long long)n, ncta, per_sm * sms);
+    }
     const int64_t np = gsum_pad64(n);
     const int T = (int)(np / GSUM_TILE);
     const void *dM;
     GSUM_TRY(dev_in(c, WS_IO0, M, sizeof(double) * n * n, mem_kind, &dM));
-    void *dAf, *dLb, *dpiv, *dst, *dPt;
+    void *dAf, *dLb, *dpiv, *dpos, *dst, *dPt, *dslots;
     GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * PSTRF_NB * np, &dPt));
+    GSUM_TRY(gsum_ws(c, WS_MISC1, sizeof(int32_t) * n, &dpos));
+    GSUM_TRY(gsum_ws(c, WS_MISC2, sizeof(PstrfSlot) * 2 * ncta, &dslots));
     GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dAf));
     GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * np * np, &dLb));
     GSUM_TRY(gsum_ws(c, WS_INFO, sizeof(int32_t) * n, &dpiv));
     GSUM_TRY(gsum_ws(c, WS_MISC0, sizeof(PstrfState), &dst));
     pad_in_kernel<<<dim3((unsigned)((np + 255) / 256), (unsigned)np, 1), 256, 0, c->stream>>>((const double *)dM, n, (double *)dAf, np, np * np, np);
     GSUM_CUDA(c, cudaMemsetAsync(dLb, 0, sizeof(double) * np * np, c->stream));
-    pstrf_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int32_t *)dpiv, (PstrfState *)dst, (int)n);
+    pstrf_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int32_t *)dpiv, (int32_t *)dpos, (PstrfState *)dst, (int)n);
     LAUNCHED(c, 2);
     for (int k = 0; k < n; k += PSTRF_NB) {
-        pstrf_panel_kernel<<<1, PSTRF_THREADS, smem, c->stream>>>((const double *)dAf, (double *)dLb, (double *)dPt, np, (int)n, k, (int32_t *)dpiv, (PstrfState *)dst);
+        const double *aAf = (const double *)dAf; double *aLb = (double *)dLb, *aPt = (double *)dPt;
+        int64_t ald = np; int an = (int)n, ak = k;
+        int32_t *apiv = (int32_t *)dpiv, *apos = (int32_t *)dpos; PstrfState *ast = (PstrfState *)dst; PstrfSlot *asl = (PstrfSlot *)dslots;
+        void *args[] = {&aAf, &aLb, &aPt, &ald, &an, &ak, &apiv, &apos, &ast, &asl};
+        GSUM_CUDA(c, cudaLaunchCooperativeKernel((const void *)pstrf_panel_kernel, dim3(ncta), dim3(PSTRF_ROWS), args, smem, c->stream));
         LAUNCHED(c, 1);
         if (k + PSTRF_NB < n) {
             // dsyrk: Af -= Lb[:, k:k+64] Lb[:, k:k+64]^T on the whole (symmetric, physically indexed) matrix
@@ -1272,10 +1286,20 @@ static int coverage_rows(gsum_ctx *c, const double *dYt, int64_t ld, int64_t n_r
         GSUM_TRY(dev_out(c, WS_COUNTS, count_out, sizeof(int64_t) * n_alpha, mem_kind, &dcnt));
         GSUM_CUDA(c, cudaMemsetAsync(dcnt, 0, sizeof(int64_t) * n_alpha, c->stream));
     }
+    void *dnested;
+    GSUM_TRY(gsum_ws(c, WS_NESTED, sizeof(int), &dnested));
+    GSUM_CUDA(c, cudaMemsetAsync(dnested, 0xff, sizeof(int), c->stream));           // nested until a violation is found
+    if (n_alpha > 1) {
+        const int64_t total = (int64_t)(n_alpha - 1) * n;
+        coverage_nested_kernel<<<(unsigned)std::min<int64_t>((total + 255) / 256, 1184), 256, 0, c->stream>>>(
+            (const double *)dlo, (const double *)dup, n_alpha, (int)n, (int *)dnested);
+        LAUNCHED(c, 1);
+    }
     const size_t smem = sizeof(double) * 2 * n_alpha * 32 + sizeof(int) * COVG_WARPS * n_alpha;
     GSUM_CUDA(c, cudaFuncSetAttribute(coverage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     coverage_rows_kernel<<<(unsigned)((n_rows + COVG_WARPS - 1) / COVG_WARPS), COVG_WARPS * 32, smem, c->stream>>>(
-        dYt, ld, n_rows, (int)n, (const double *)dlo, (const double *)dup, n_alpha, (double *)dcov, (unsigned long long *)dcnt);
+        dYt, ld, n_rows, (int)n, (const double *)dlo, (const double *)dup, n_alpha, (double *)dcov, (unsigned long long *)dcnt,
+        (const int *)dnested);
     LAUNCHED(c, 1);
     if (coverage_out) GSUM_TRY(dev_out_finish(c, coverage_out, dcov, sizeof(double) * n_rows * n_alpha, mem_kind));
     if (count_out) GSUM_TRY(dev_out_finish(c, count_out, dcnt, sizeof(int64_t) * n_alpha, mem_kind));

@@ -254,3 +254,23 @@ def test_sharded_draws_and_predict_nccl_single_rank(ctx, golden):
     assert np.array_equal(cv, cnt1.astype(np.float64) / (3000.0 * len(g["mean"]))) and relerr(cv, cov1.mean(0)) < 1e-14
     mw, sw = gp.predict(Xn, return_std=True)
     assert np.array_equal(m, mw) and np.array_equal(s, sw)
+
+
+def test_coverage_nested_and_unordered_intervals_agree(ctx, golden):
+    """Increasing credible levels give nested intervals (bisection + histogram path); the same levels in a shuffled order
+    take the comparison-per-interval path.  Both must reproduce the reference's integer counts."""
+    g = golden("c5_diagnostics")
+    d = gb.Diagnostic(g["mean"], g["cov"], random_state=1)
+    Y, iv = g["Y"], g["intervals"]
+    perm = np.random.RandomState(0).permutation(len(iv))
+    assert np.array_equal(d.credible_interval(Y, iv), g["coverage"])
+    assert np.array_equal(d.credible_interval(Y, iv[perm]), g["coverage"][:, perm])
+    assert np.array_equal(d.credible_interval(Y, iv[perm]), o.credible_interval(Y, g["mean"], g["cov"], iv[perm]))
+    one = d.credible_interval(Y, iv[40:41])                                  # a single interval
+    assert np.array_equal(one[:, 0], g["coverage"][:, 40])
+    # a point exactly on an interval's end is outside (strict inequalities), also on the bisection path
+    lower, upper = d._bounds(iv)
+    Yb = Y.copy()
+    Yb[:, 0] = upper[50]
+    Yb[:, 1] = lower[70]
+    assert np.array_equal(d.credible_interval(Yb, iv), o.credible_interval(Yb, g["mean"], g["cov"], iv))

@@ -1,7 +1,7 @@
 """Dev tool: wall-clock of the other BASELINE.json configurations at full size through the public API (numpy in / out),
 with the oracle (reference algorithm on the host) timed beside it on a bounded sample.
 
-    python tools/perf_configs.py [c2] [c3] [c5]
+    python tools/perf_configs.py [c2] [c3] [c4x] [c5]
 """
 import os, sys, time
 import numpy as np
@@ -12,7 +12,7 @@ import gsum_b200 as gb
 from gsum_b200 import ops, _lib
 from oracle import gsum_oracle as o
 
-which = [a for a in sys.argv[1:] if a in ("c2", "c3", "c5")] or ["c2", "c3", "c5"]
+which = [a for a in sys.argv[1:] if a in ("c2", "c3", "c4x", "c5")] or ["c2", "c3", "c4x", "c5"]
 ctx = _lib.default_context()
 
 def timed(f, reps=3):
@@ -57,6 +57,33 @@ if "c3" in which:
     print(f"C3 N=2500 -> M=10000: fit {ms_fit:.1f} ms | coeffs_process.predict(std) {ms_cp:.1f} ms ({flops_std / ms_cp * 1e-9:.2f} TFLOP/s on the N^2 M forward solve) | "
           f"TruncationGP.predict(both, std) {ms_tp:.1f} ms | predict(cov) M=4096 {ms_cov:.1f} ms")
     print(f"   oracle predict(std) on 1000 of the points {cpu_cp * 1e3:.0f} ms (reference forms the M x M matrix: ~{cpu_cp * 1e3 * 100:.0f} ms extrapolated to 10000 by M^2) | rel err mean {e_m:.2e} std {e_s:.2e}")
+
+if "c4x" in which:
+    # second C4 variant of SURVEY.md 8(d): x-dependent Q(x) = q(x) / Lambda — one block of 6 right-hand sides per Lambda, so the
+    # border of every factorisation carries 256 * 6 + 1 = 1537 rows (F_trsm = 128 * 1024^2 * 1537 = 206 GFLOP, GEMM shaped)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    from util import c4_inputs
+    X, y, orders = c4_inputs()
+    n = len(X)
+    ls_vals, lams = np.geomspace(0.005, 0.5, 128), np.linspace(0.8, 1.6, 256)
+    kern = RBF(0.05) + WhiteKernel(1e-6, 'fixed')
+    ratio = lambda X, lam: np.linspace(0.2, 0.6, len(X)) / lam
+    gp = gb.TruncationGP(kern, ratio=ratio, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None, ratio_kws=dict(lam=1.0)).fit(X, y, orders=orders)
+    kws = [dict(lam=l) for l in lams]
+    ctx.profile(True)
+    ms, ll = timed(lambda: gp.log_marginal_likelihood_grid(ls_vals, ratio_kws_list=kws))
+    ctx.profile_read()
+    gp.log_marginal_likelihood_grid(ls_vals, ratio_kws_list=kws); ctx.synchronize()
+    fact_ms, fact_flops, n_br = ctx.profile_read()
+    ctx.profile(False)
+    t0 = time.perf_counter()
+    cells = [(a, b) for a in (0, 100, 255) for b in (10, 64, 120)]
+    ref = np.array([o.truncation_lml(kern, [np.log(ls_vals[b])], X, y, orders, ratio(X, lams[a]), np.ones(n), o.Priors(0, 0, 1, 1)) for a, b in cells])
+    cpu = (time.perf_counter() - t0) / len(cells)
+    got = np.array([ll[a, b] for a, b in cells])
+    print(f"C4x 128 l x 256 Lambda, x-dependent Q, N=1024 (1537 border rows): grid {ms:.1f} ms through the numpy API ({128 * 256 / ms * 1e3:.3g} evals/s) | "
+          f"factorisation + forward solves {fact_ms:.2f} ms over {n_br} brackets, {fact_flops / fact_ms * 1e-9:.2f} TFLOP/s algorithmic | "
+          f"reference algorithm on host {cpu * 1e3:.0f} ms per cell ({1 / cpu:.2f} evals/s) | max rel err on {len(cells)} cells {np.max(np.abs(got - ref) / np.abs(ref)):.2e}")
 
 if "c5" in which:
     n = 4096
