@@ -31,6 +31,9 @@ _SIGNATURES = {
     "gsum_ctx_synchronize": (C.c_int, [_vp]),
     "gsum_last_error": (C.c_char_p, [_vp]),
     "gsum_launch_count": (C.c_int64, [_vp]),
+    "gsum_device_malloc": (C.c_int, [_vp, C.c_size_t, C.POINTER(_vp)]),
+    "gsum_device_free": (C.c_int, [_vp, _vp]),
+    "gsum_device_copy": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_int32]),
     "gsum_ctx_profile": (C.c_int, [_vp, C.c_int]),
     "gsum_ctx_profile_read": (C.c_int, [_vp, _vp, _vp, _vp]),
     "gsum_kernel_matrix": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, C.c_double,
@@ -147,6 +150,46 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.gsum_launch_count(self.handle))
+
+
+class DeviceBuffer:
+    """A caller-held buffer in HBM (``gsum_device_malloc``): factors that stay resident between calls.
+
+    `shape` / `dtype` describe the array it holds; `.get()` copies it back to a new numpy array."""
+
+    def __init__(self, ctx, shape, dtype=np.float64):
+        self.ctx, self.shape, self.dtype = ctx, tuple(int(s) for s in shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = _vp()
+        ctx.check(ctx.lib.gsum_device_malloc(ctx.handle, self.nbytes, C.byref(p)), "gsum_device_malloc")
+        self.ptr = p.value
+
+    def put(self, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        if a.shape != self.shape:
+            raise ValueError(f"expected shape {self.shape}, got {a.shape}")
+        self.ctx.check(self.ctx.lib.gsum_device_copy(self.ctx.handle, self.ptr, a.ctypes.data, self.nbytes, 0), "gsum_device_copy")
+        return self
+
+    def copy_from(self, other):
+        self.ctx.check(self.ctx.lib.gsum_device_copy(self.ctx.handle, self.ptr, other.ptr, self.nbytes, 2), "gsum_device_copy")
+        return self
+
+    def get(self):
+        out = np.empty(self.shape, dtype=self.dtype)
+        self.ctx.check(self.ctx.lib.gsum_device_copy(self.ctx.handle, out.ctypes.data, self.ptr, self.nbytes, 1), "gsum_device_copy")
+        return out
+
+    def free(self):
+        if getattr(self, "ptr", None) and self.ctx.handle is not None:
+            self.ctx.lib.gsum_device_free(self.ctx.handle, self.ptr)
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 _default_ctx = {}

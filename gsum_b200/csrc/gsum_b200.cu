@@ -105,6 +105,31 @@ extern "C" int gsum_ctx_profile_read(gsum_ctx *c, double *ms_total, double *flop
     return 0;
 }
 
+// ---- caller-held device buffers (factors that stay in HBM between calls) -----------------------------------------
+extern "C" int gsum_device_malloc(gsum_ctx *c, size_t bytes, void **out) {
+    if (!c || !out || bytes == 0) return gsum_fail(c, -1, "gsum_device_malloc: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    GSUM_CUDA(c, cudaMalloc(out, bytes));
+    return 0;
+}
+extern "C" int gsum_device_free(gsum_ctx *c, void *p) {
+    if (!c) return -1;
+    if (!p) return 0;
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // work enqueued on the buffer must have drained
+    GSUM_CUDA(c, cudaFree(p));
+    return 0;
+}
+// direction: 0 host -> device, 1 device -> host, 2 device -> device; ordered on the context's stream, returns when done
+extern "C" int gsum_device_copy(gsum_ctx *c, void *dst, const void *src, size_t bytes, int32_t direction) {
+    if (!c || !dst || !src || direction < 0 || direction > 2) return gsum_fail(c, -1, "gsum_device_copy: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const cudaMemcpyKind kind = direction == 0 ? cudaMemcpyHostToDevice : direction == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    GSUM_CUDA(c, cudaMemcpyAsync(dst, src, bytes, kind, c->stream));
+    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 extern "C" const char *gsum_last_error(const gsum_ctx *c) { return c ? c->err : "null context"; }
 extern "C" int64_t gsum_launch_count(const gsum_ctx *c) { return c ? c->launches : 0; }
 
@@ -123,6 +148,12 @@ static int dev_in(gsum_ctx *c, int slot, const void *p, size_t bytes, int mem_ki
     } else GSUM_CUDA(c, cudaMemcpyAsync(d, p, bytes, cudaMemcpyHostToDevice, c->stream));
     *out = d;
     return 0;
+}
+// GSUM_MEM_FACTOR_DEVICE: the factor argument of a call is a device pointer while the other buffers are host pointers
+static inline int factor_kind(int32_t &mem_kind) {
+    const int fk = (mem_kind & GSUM_MEM_FACTOR_DEVICE) ? GSUM_MEM_DEVICE : (mem_kind & 1);
+    mem_kind &= 1;
+    return fk;
 }
 // Output: device buffer to write into (the caller's when it is a device pointer, workspace otherwise).
 static int dev_out(gsum_ctx *c, int slot, void *p, size_t bytes, int mem_kind, void **out) {
@@ -738,10 +769,11 @@ extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B
                               int32_t mem_kind) {
     if (!c || !L || !B || n <= 0 || nrhs <= 0) return gsum_fail(c, -1, "gsum_cho_solve: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int fk = factor_kind(mem_kind);
     const int64_t np = gsum_pad64(n), rp = gsum_pad64(nrhs);
     const int T = (int)(np / GSUM_TILE);
     const void *dL, *dB;
-    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, mem_kind, &dL));
+    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, fk, &dL));
     GSUM_TRY(dev_in(c, WS_IO1, B, sizeof(double) * n * nrhs, mem_kind, &dB));
     void *dF, *dW;
     GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * np * np, &dF));
@@ -1150,10 +1182,11 @@ extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, con
                                     int64_t n_curves, double *E, double *md2, int32_t mem_kind) {
     if (!c || !L || !Y || n <= 0 || n_curves <= 0 || (!E && !md2)) return gsum_fail(c, -1, "gsum_cholesky_errors: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int fk = factor_kind(mem_kind);
     const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_curves);
     const int T = (int)(np / GSUM_TILE);
     const void *dL, *dmean, *dY;
-    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, mem_kind, &dL));
+    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, fk, &dL));
     GSUM_TRY(dev_in(c, WS_REF, mean, sizeof(double) * n, mem_kind, &dmean));
     GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * n_curves, mem_kind, &dY));
     void *dF, *dW;
@@ -1255,11 +1288,12 @@ extern "C" int gsum_pc_errors(gsum_ctx *c, const double *Lp, const int32_t *piv,
                               const double *Y, int64_t n_curves, double *E, int32_t mem_kind) {
     if (!c || !Lp || !piv || !Y || !E || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_pc_errors: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int fk = factor_kind(mem_kind);
     const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_curves);
     const int T = (int)(np / GSUM_TILE);
     const void *dL, *dpiv, *dmean, *dY;
-    GSUM_TRY(dev_in(c, WS_IO0, Lp, sizeof(double) * n * n, mem_kind, &dL));
-    GSUM_TRY(dev_in(c, WS_INFO, piv, sizeof(int32_t) * n, mem_kind, &dpiv));
+    GSUM_TRY(dev_in(c, WS_IO0, Lp, sizeof(double) * n * n, fk, &dL));
+    GSUM_TRY(dev_in(c, WS_INFO, piv, sizeof(int32_t) * n, fk, &dpiv));
     GSUM_TRY(dev_in(c, WS_REF, mean, sizeof(double) * n, mem_kind, &dmean));
     GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * n_curves, mem_kind, &dY));
     void *dF, *dW, *dE;
@@ -1314,10 +1348,11 @@ extern "C" int gsum_draws(gsum_ctx *c, const double *L, int64_t n, const double 
     GSUM_CUDA(c, cudaSetDevice(c->device));
     GSUM_TRY(chol_set_attrs(c));
     GSUM_CUDA(c, cudaFuncSetAttribute(draws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+    const int fk = factor_kind(mem_kind);
     const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_draws);
     const int T = (int)(np / GSUM_TILE);
     const void *dL, *dmean, *dZ;
-    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, mem_kind, &dL));
+    GSUM_TRY(dev_in(c, WS_IO0, L, sizeof(double) * n * n, fk, &dL));
     GSUM_TRY(dev_in(c, WS_REF, mean, sizeof(double) * n, mem_kind, &dmean));
     GSUM_TRY(dev_in(c, WS_IO1, Z, sizeof(double) * n * n_draws, mem_kind, &dZ));
     void *dF, *dZn, *dYt;

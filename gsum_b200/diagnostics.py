@@ -43,11 +43,19 @@ class Diagnostic:
                 raise ValueError("df must be greater than 2 for the covariance to exist")
             self.udist = stats.t(loc=self.mean, scale=self.sd, df=self.df)
             self.std_udist = stats.t(loc=0., scale=1., df=self.df)
-        self._chol = ops.cholesky(self.cov)                          # raises LinAlgError like numpy (diagnostics.py:60)
-        G, Lp, piv, rank, status = ops.pivoted_cholesky(self.cov)    # diagnostics.py:61 -> helpers.py:185-199
-        if status > 0:
-            raise np.linalg.LinAlgError('M is not positive-semidefinite')
-        self._pchol, self._pchol_L, self._piv = G, Lp, piv
+        # one upload of cov; Cholesky (diagnostics.py:60) and pivoted Cholesky (diagnostics.py:61 -> helpers.py:185-199)
+        # on the device copy; the factors stay in HBM for every later call
+        self._factors = f = ops.ResidentFactors(self.cov)
+        if f.chol_info:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")        # numpy.linalg.cholesky
+        if f.status > 0:
+            raise np.linalg.LinAlgError('M is not positive-semidefinite')         # helpers.py:189-190
+
+    # factors as numpy arrays (copied back from HBM on first access)
+    _chol = property(lambda self: self._factors.chol)
+    _pchol = property(lambda self: self._factors.pchol)
+    _pchol_L = property(lambda self: self._factors.pchol_L)
+    _piv = property(lambda self: self._factors.piv_host)
 
     # -- draws -------------------------------------------------------------------------------------
     def _draw_scale(self, n, rs):
@@ -68,29 +76,32 @@ class Diagnostic:
         the reference's scipy/numpy SVD sampler uses a different factor, so streams differ by construction."""
         rs = np.random.RandomState(self.random_state)
         if device_rng:
-            d, _ = ops.draws(self._chol, self.mean, n_draws=int(n), seed=int(self.random_state or 0),
+            d, _ = ops.draws(self._factors.L, self.mean, n_draws=int(n), seed=int(self.random_state or 0),
                              draw_scale=self._draw_scale(n, rs))
             return d
         z = rs.standard_normal((self.mean.shape[0], int(n)))
-        d, _ = ops.draws(self._chol, self.mean, Z=z, draw_scale=self._draw_scale(n, rs))
+        d, _ = ops.draws(self._factors.L, self.mean, Z=z, draw_scale=self._draw_scale(n, rs))
         return d
 
-    def sample_coverage(self, n, intervals, seed=None, first_draw=0, n_total=None, counts=False):
+    def sample_coverage(self, n, intervals, seed=None, first_draw=0, n_total=None, counts=False, per_draw=True):
         """Coverage (n, n_intervals) of `n` fresh device draws, fused with the draw so the (N, n) sample matrix is
         never copied back (the GraphicalDiagnostic reference bands of gsum/diagnostics.py:557-584).
 
         `first_draw` / `n_total` select draws first_draw .. first_draw + n - 1 of a run of n_total draws (one shard of
         the draw axis, gsum_b200.distributed.sample_coverage_sharded); with `counts` the int64 (n_intervals,) totals of
-        (draw, point) pairs inside each interval are returned as well."""
+        (draw, point) pairs inside each interval are returned as well (alone, without the (n, n_intervals) matrix, when
+        `per_draw` is False: nothing but n_intervals integers then leaves the device)."""
         lower, upper = self._bounds(intervals)
         seed = int(self.random_state or 0) if seed is None else int(seed)
         scale = None
         if self.df is not None:                                     # the whole run's chi-square stream, then this shard's slice
             total = int(first_draw) + int(n) if n_total is None else int(n_total)
             scale = self._draw_scale(total, np.random.RandomState(seed))[int(first_draw):int(first_draw) + int(n)]
-        res = ops.draws(self._chol, self.mean, n_draws=int(n), seed=seed, lower=lower, upper=upper, want_draws=False,
-                        first_draw=int(first_draw), draw_scale=scale, want_counts=counts)
-        return (res[1], res[2]) if counts else res[1]
+        res = ops.draws(self._factors.L, self.mean, n_draws=int(n), seed=seed, lower=lower, upper=upper, want_draws=False,
+                        first_draw=int(first_draw), draw_scale=scale, want_counts=counts, want_coverage=per_draw or not counts)
+        if counts:
+            return (res[1], res[2]) if per_draw else res[2]
+        return res[1]
 
     # -- errors ------------------------------------------------------------------------------------
     def individual_errors(self, y):
@@ -104,13 +115,13 @@ class Diagnostic:
     def cholesky_errors(self, y):
         """L^{-1}(y - mean) (gsum/diagnostics.py:100-101)."""
         Y, single = self._as_columns(y)
-        E, _ = ops.cholesky_errors(self._chol, self.mean, Y)
+        E, _ = ops.cholesky_errors(self._factors.L, self.mean, Y)
         return E[:, 0] if single else E
 
     def pivoted_cholesky_errors(self, y):
         """solve(G, y - mean) (gsum/diagnostics.py:103-104) via permutation + forward substitution."""
         Y, single = self._as_columns(y)
-        E = ops.pc_errors(self._pchol_L, self._piv, self.mean, Y)
+        E = ops.pc_errors(self._factors.Lp, self._factors.piv, self.mean, Y)
         return E[:, 0] if single else E
 
     def eigen_errors(self, y):
@@ -122,7 +133,7 @@ class Diagnostic:
     def md_squared(self, y):
         """Squared Mahalanobis distance of each curve (gsum/diagnostics.py:112-114)."""
         Y, single = self._as_columns(y)
-        _, md2 = ops.cholesky_errors(self._chol, self.mean, Y, want_errors=False, want_md2=True)
+        _, md2 = ops.cholesky_errors(self._factors.L, self.mean, Y, want_errors=False, want_md2=True)
         return md2[0] if single else md2
 
     def kl(self, mean, cov):
@@ -131,7 +142,7 @@ class Diagnostic:
         diagonal of the covariance c1 itself there (not of its factor), which is kept.  logdet(c0) comes from a device
         Cholesky of c0 (numpy's `slogdet` is LU based; for a covariance the two agree)."""
         c0 = np.asarray(cov, dtype=np.float64)
-        tr = float(np.trace(ops.cho_solve(self._chol, c0)))
+        tr = float(np.trace(ops.cho_solve(self._factors.L, c0)))
         dist = float(self.md_squared(np.asarray(mean, dtype=np.float64)))
         k = self.cov.shape[-1]
         _, info, logdet0 = ops.cholesky(c0, return_info=True)

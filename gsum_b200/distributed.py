@@ -158,7 +158,7 @@ def sample_coverage_sharded(diagnostic, n_draws, intervals, seed=None, group=Non
     counts = np.zeros(n_alpha, dtype=np.int64)
     if hi > lo:
         evaluator = _evaluator or (lambda lo_, n_: diagnostic.sample_coverage(n_, intervals, seed=seed, first_draw=lo_,
-                                                                               n_total=n_draws, counts=True)[1])
+                                                                               n_total=n_draws, counts=True, per_draw=False))
         counts = np.asarray(evaluator(lo, hi - lo), dtype=np.int64)
     t = torch.from_numpy(counts).to(_comm_device(group))
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)    # the single collective of the path

@@ -11,16 +11,26 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import MEM_DEVICE, MEM_HOST, PREDICT_COV, PREDICT_MEAN, PREDICT_VAR, as_f64, default_context
+from ._lib import MEM_DEVICE, MEM_HOST, PREDICT_COV, PREDICT_MEAN, PREDICT_VAR, DeviceBuffer, as_f64, default_context
+
+MEM_FACTOR_DEVICE = 2        # GSUM_MEM_FACTOR_DEVICE: the factor argument is a DeviceBuffer, everything else numpy
 
 __all__ = [
     "kernel_matrix", "cholesky", "cho_solve", "lml_grid", "grid_normalize", "FitHandle", "process_cov",
-    "cholesky_errors", "pivoted_cholesky", "pc_errors", "draws", "credible_interval",
+    "cholesky_errors", "pivoted_cholesky", "pc_errors", "draws", "credible_interval", "ResidentFactors",
 ]
 
 
 def _p(a):
     return None if a is None else a.ctypes.data
+
+
+def _factor(L):
+    """(pointer, n, memory-kind bits) of a factor given as a numpy array or as a DeviceBuffer resident in HBM."""
+    if isinstance(L, DeviceBuffer):
+        return L.ptr, L.shape[0], MEM_HOST | MEM_FACTOR_DEVICE, L
+    L = as_f64(L)
+    return L.ctypes.data, L.shape[0], MEM_HOST, L
 
 
 def _vec(a, n, name):
@@ -73,12 +83,12 @@ def cholesky(A, return_info=False, ctx=None):
 def cho_solve(L, B, forward_only=False, ctx=None):
     """``scipy.linalg.cho_solve((L, True), B)`` or, with forward_only, ``solve_triangular(L, B, lower=True)``."""
     ctx = ctx or default_context()
-    L = as_f64(L)
+    Lp_, _, kind, _keep = _factor(L)
     B = np.asarray(B, dtype=np.float64)
     vec = B.ndim == 1
     X = as_f64(B[:, None] if vec else B, copy=True)
     n, k = X.shape
-    ctx.check(ctx.lib.gsum_cho_solve(ctx.handle, _p(L), n, _p(X), k, 1 if forward_only else 0, MEM_HOST), "gsum_cho_solve")
+    ctx.check(ctx.lib.gsum_cho_solve(ctx.handle, Lp_, n, _p(X), k, 1 if forward_only else 0, kind), "gsum_cho_solve")
     return X[:, 0] if vec else X
 
 
@@ -273,13 +283,12 @@ def process_cov(X1, X2, length_scale, constant=1.0, noise=0.0, factor=1.0, sc1=N
 def cholesky_errors(L, mean, Y, want_errors=True, want_md2=False, ctx=None):
     """L^{-1}(Y - mean) for Y (n, n_curves) and/or the squared Mahalanobis distances (n_curves,)."""
     ctx = ctx or default_context()
-    L = as_f64(L)
-    n = L.shape[0]
+    Lp_, n, kind, _keep = _factor(L)
     Y = as_f64(Y)
     mean = _vec(mean, n, "mean")
     E = np.empty_like(Y) if want_errors else None
     md2 = np.empty(Y.shape[1]) if want_md2 else None
-    ctx.check(ctx.lib.gsum_cholesky_errors(ctx.handle, _p(L), n, _p(mean), _p(Y), Y.shape[1], _p(E), _p(md2), MEM_HOST),
+    ctx.check(ctx.lib.gsum_cholesky_errors(ctx.handle, Lp_, n, _p(mean), _p(Y), Y.shape[1], _p(E), _p(md2), kind),
               "gsum_cholesky_errors")
     return E, md2
 
@@ -300,13 +309,14 @@ def pivoted_cholesky(M, ctx=None):
 def pc_errors(Lp, piv, mean, Y, ctx=None):
     """solve(G, Y - mean) with G = Lp[p_inv] by permutation + forward substitution."""
     ctx = ctx or default_context()
-    Lp = as_f64(Lp)
-    n = Lp.shape[0]
+    Lp_, n, kind, _keep = _factor(Lp)
     Y = as_f64(Y)
-    piv = np.ascontiguousarray(piv, dtype=np.int32)
+    if isinstance(piv, DeviceBuffer) != isinstance(Lp, DeviceBuffer):
+        raise ValueError("Lp and piv must both be numpy arrays or both DeviceBuffers")
+    piv_ = piv.ptr if isinstance(piv, DeviceBuffer) else _p(np.ascontiguousarray(piv, dtype=np.int32))
     mean = _vec(mean, n, "mean")
     E = np.empty_like(Y)
-    ctx.check(ctx.lib.gsum_pc_errors(ctx.handle, _p(Lp), _p(piv), n, _p(mean), _p(Y), Y.shape[1], _p(E), MEM_HOST), "gsum_pc_errors")
+    ctx.check(ctx.lib.gsum_pc_errors(ctx.handle, Lp_, piv_, n, _p(mean), _p(Y), Y.shape[1], _p(E), kind), "gsum_pc_errors")
     return E
 
 
@@ -319,8 +329,7 @@ def draws(L, mean, Z=None, n_draws=None, seed=0, lower=None, upper=None, want_dr
     Returns (draws (n, n_draws) or None, coverage (n_draws, n_alpha) or None) — and, with `want_counts`, a third item:
     the int64 (n_alpha,) number of (draw, point) pairs inside each interval."""
     ctx = ctx or default_context()
-    L = as_f64(L)
-    n = L.shape[0]
+    Lp_, n, kind, _keep = _factor(L)
     mean = _vec(mean, n, "mean")
     if Z is not None:
         Z = as_f64(Z)
@@ -337,11 +346,52 @@ def draws(L, mean, Z=None, n_draws=None, seed=0, lower=None, upper=None, want_dr
         counts = np.zeros(n_alpha, dtype=np.int64) if want_counts else None
     elif want_counts:
         raise ValueError("coverage counts need lower and upper")
-    ctx.check(ctx.lib.gsum_draws(ctx.handle, _p(L), n, _p(mean), _p(Z), n_draws, int(seed), int(first_draw), _p(draw_scale),
-                                 _p(out), _p(lower), _p(upper), n_alpha, _p(cov), _p(counts), MEM_HOST), "gsum_draws")
+    ctx.check(ctx.lib.gsum_draws(ctx.handle, Lp_, n, _p(mean), _p(Z), n_draws, int(seed), int(first_draw), _p(draw_scale),
+                                 _p(out), _p(lower), _p(upper), n_alpha, _p(cov), _p(counts), kind), "gsum_draws")
     if want_counts:
         return out, cov, counts
     return out, cov
+
+
+class ResidentFactors:
+    """Cholesky and pivoted-Cholesky factors of one covariance, computed once and kept in HBM (the state behind
+    `Diagnostic`, gsum/diagnostics.py:60-61): the matrix goes up ONCE, both factorisations run on the device copy, and
+    every later error / draw call passes the resident factors (GSUM_MEM_FACTOR_DEVICE) instead of re-uploading N x N
+    doubles.  `chol`, `pchol` (G = Lp[p_inv], the array gsum's `pivoted_cholesky` returns), `pchol_L` and `piv` are
+    copied back to numpy on first access only."""
+
+    def __init__(self, cov, ctx=None):
+        self.ctx = ctx = ctx or default_context()
+        cov = as_f64(cov)
+        n = self.n = cov.shape[0]
+        if cov.shape != (n, n):
+            raise ValueError("cov must be square")
+        self.L = DeviceBuffer(ctx, (n, n))
+        self.Lp = DeviceBuffer(ctx, (n, n))
+        self.G = DeviceBuffer(ctx, (n, n))
+        self.piv = DeviceBuffer(ctx, (n,), np.int32)
+        scal = DeviceBuffer(ctx, (2,), np.int32)                    # [cholesky info, pivoted-Cholesky rank]
+        M = DeviceBuffer(ctx, (n, n)).put(cov)                      # the only N x N upload
+        try:
+            self.L.copy_from(M)
+            ctx.check(ctx.lib.gsum_cholesky(ctx.handle, self.L.ptr, n, 1, scal.ptr, None, MEM_DEVICE), "gsum_cholesky")
+            self.status = ctx.check(ctx.lib.gsum_pivoted_cholesky(ctx.handle, M.ptr, n, self.Lp.ptr, self.piv.ptr, scal.ptr + 4,
+                                                                  self.G.ptr, MEM_DEVICE), "gsum_pivoted_cholesky")
+            self.chol_info, self.rank = (int(v) for v in scal.get())
+        finally:
+            M.free()
+            scal.free()
+        self._host = {}
+
+    def _lazy(self, name, buf):
+        if name not in self._host:
+            self._host[name] = buf.get()
+        return self._host[name]
+
+    chol = property(lambda self: self._lazy("chol", self.L))
+    pchol = property(lambda self: self._lazy("pchol", self.G))
+    pchol_L = property(lambda self: self._lazy("pchol_L", self.Lp))
+    piv_host = property(lambda self: self._lazy("piv", self.piv))
 
 
 def credible_interval(Y, lower, upper, ctx=None):

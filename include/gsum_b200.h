@@ -29,6 +29,10 @@ extern "C" {
 
 #define GSUM_MEM_HOST 0
 #define GSUM_MEM_DEVICE 1
+/* OR-ed into GSUM_MEM_HOST for the calls that take a factor (gsum_cho_solve, gsum_cholesky_errors, gsum_pc_errors,
+ * gsum_draws): the factor argument (L / Lp and piv) is a DEVICE pointer — a factor the caller keeps resident in HBM
+ * (gsum_device_malloc) — while every other buffer is a host pointer.  Saves re-uploading an N x N factor per call. */
+#define GSUM_MEM_FACTOR_DEVICE 2
 
 #define GSUM_PREDICT_MEAN 0
 #define GSUM_PREDICT_VAR 1
@@ -47,6 +51,14 @@ int gsum_ctx_synchronize(gsum_ctx *ctx);
 const char *gsum_last_error(const gsum_ctx *ctx);
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 int64_t gsum_launch_count(const gsum_ctx *ctx);
+
+/* Caller-held device buffers on the context's GPU — for factors that stay in HBM between calls (GSUM_MEM_DEVICE /
+ * GSUM_MEM_FACTOR_DEVICE arguments) when the host side has no device allocator of its own.  gsum_device_copy is ordered
+ * on the context's stream and returns when the copy is done; direction 0 = host->device, 1 = device->host, 2 = device->device.
+ * gsum_device_free drains the context's stream first. */
+int gsum_device_malloc(gsum_ctx *ctx, size_t bytes, void **out);
+int gsum_device_free(gsum_ctx *ctx, void *ptr);
+int gsum_device_copy(gsum_ctx *ctx, void *dst, const void *src, size_t bytes, int32_t direction);
 
 /* Optional profiling of the factorisation phase (K2+K3: every launch of the bordered Cholesky), used by bench.py for
  * the roofline: CUDA events are recorded on the context's stream around each factorisation while enabled.
