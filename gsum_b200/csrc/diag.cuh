@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(double *__restrict__ Zn
 
 // ------------------------------------------------------------------------------------------------
 // Credible-interval coverage  (gsum/diagnostics.py:148-171)
-// cov[dr][a] = mean_i 1[lower[a][i] < y[dr][i] < upper[a][i]].  16 draws per CTA share each staged
+// cov[dr][a] = mean_i 1[lower[a][i] < y[dr][i] < upper[a][i]].  128 draws per CTA share each staged
 // (n_alpha x 32 points) slice of the bounds; counts are integers, so the result is order independent.
 // Central intervals at increasing levels are NESTED at every point (lower non-increasing, upper non-decreasing in a);
 // `coverage_nested_kernel` checks that on the device and the counting kernel then finds, per (draw, point), the first
@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(256) scale_rows_kernel(double *__restrict__ Zn
 // sums are the counts.  Bounds in any other order take the comparison-per-interval path; both give the same integers.
 // ------------------------------------------------------------------------------------------------
 #define COVG_WARPS 16
+#define COVG_DPW 8               // draws per warp: 128 draws per CTA share each staged slice of the bounds (the bounds would
+                                 // otherwise cost 13x the L2 traffic of the draws themselves at n_alpha = 101)
+#define COVG_ROWS (COVG_WARPS * COVG_DPW)
 #define COVG_MAXA 128
 __global__ void __launch_bounds__(256) coverage_nested_kernel(const double *__restrict__ lower, const double *__restrict__ upper, int n_alpha,
                                                               int n, int *__restrict__ nested) {
@@ -242,11 +245,11 @@ __global__ void __launch_bounds__(COVG_WARPS * 32) coverage_rows_kernel(const do
                                                                         const int *__restrict__ nested_flag) {
     extern __shared__ __align__(16) double sm[];
     double *lo = sm, *up = sm + (size_t)n_alpha * 32;
-    int *cnt = (int *)(up + (size_t)n_alpha * 32);       // [COVG_WARPS][n_alpha]
+    int *cnt = (int *)(up + (size_t)n_alpha * 32);       // [COVG_ROWS][n_alpha]
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int64_t dr = (int64_t)blockIdx.x * COVG_WARPS + w;
+    const int64_t dr0 = ((int64_t)blockIdx.x * COVG_WARPS + w) * COVG_DPW;       // this warp's first draw
     const bool nested = *nested_flag != 0;
-    for (int e = tid; e < COVG_WARPS * n_alpha; e += COVG_WARPS * 32) cnt[e] = 0;
+    for (int e = tid; e < COVG_ROWS * n_alpha; e += COVG_WARPS * 32) cnt[e] = 0;
     for (int x0 = 0; x0 < n; x0 += 32) {
         __syncthreads();
         for (int e = tid; e < n_alpha * 32; e += COVG_WARPS * 32) {
@@ -255,49 +258,60 @@ __global__ void __launch_bounds__(COVG_WARPS * 32) coverage_rows_kernel(const do
             up[e] = xx < n ? upper[(int64_t)a * n + xx] : -INFINITY;
         }
         __syncthreads();
-        if (dr < n_draws) {
-            const int xx = x0 + lane;
-            const double y = xx < n ? Yt[dr * ld + xx] : 0.0;
+        const int xx = x0 + lane;
+        double y[COVG_DPW];
+#pragma unroll
+        for (int u = 0; u < COVG_DPW; u++) y[u] = (xx < n && dr0 + u < n_draws) ? Yt[(dr0 + u) * ld + xx] : 0.0;
+#pragma unroll
+        for (int u = 0; u < COVG_DPW; u++) {
+            if (dr0 + u >= n_draws) break;
+            int *c = cnt + (w * COVG_DPW + u) * n_alpha;
             if (nested) {
                 // first a with lower[a] < y < upper[a] (the predicate is monotone in a); n_alpha if there is none
                 int lo_a = 0, hi_a = n_alpha;
                 while (lo_a < hi_a) {
                     const int mid = (lo_a + hi_a) >> 1;
-                    const bool in = (lo[mid * 32 + lane] < y) && (y < up[mid * 32 + lane]);
+                    const bool in = (lo[mid * 32 + lane] < y[u]) && (y[u] < up[mid * 32 + lane]);
                     if (in) hi_a = mid; else lo_a = mid + 1;
                 }
-                if (xx < n && lo_a < n_alpha) atomicAdd(&cnt[w * n_alpha + lo_a], 1);
+                if (xx < n && lo_a < n_alpha) atomicAdd(&c[lo_a], 1);
             } else {
                 for (int a = 0; a < n_alpha; a++) {
-                    const bool in = (lo[a * 32 + lane] < y) && (y < up[a * 32 + lane]);
+                    const bool in = (lo[a * 32 + lane] < y[u]) && (y[u] < up[a * 32 + lane]);
                     const unsigned m = __ballot_sync(0xffffffffu, in);
-                    if (lane == 0) cnt[w * n_alpha + a] += __popc(m);
+                    if (lane == 0) c[a] += __popc(m);
                 }
             }
         }
     }
     __syncwarp();
-    if (nested && dr < n_draws) {                        // histogram of first-containing intervals -> counts: inclusive prefix sums
-        int carry = 0;
-        for (int a0 = 0; a0 < n_alpha; a0 += 32) {
-            const int a = a0 + lane;
-            int v = a < n_alpha ? cnt[w * n_alpha + a] : 0;
+    for (int u = 0; u < COVG_DPW; u++) {
+        const int64_t dr = dr0 + u;
+        if (dr >= n_draws) break;
+        int *c = cnt + (w * COVG_DPW + u) * n_alpha;
+        if (nested) {                                    // histogram of first-containing intervals -> counts: inclusive prefix sums
+            int carry = 0;
+            for (int a0 = 0; a0 < n_alpha; a0 += 32) {
+                const int a = a0 + lane;
+                int v = a < n_alpha ? c[a] : 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-            v += carry;
-            if (a < n_alpha) cnt[w * n_alpha + a] = v;
-            carry = __shfl_sync(0xffffffffu, v, 31);
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+                v += carry;
+                if (a < n_alpha) c[a] = v;
+                carry = __shfl_sync(0xffffffffu, v, 31);
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        if (out)
+            for (int a = lane; a < n_alpha; a += 32) out[dr * n_alpha + a] = (double)c[a] / (double)n;
     }
-    if (out && dr < n_draws)
-        for (int a = lane; a < n_alpha; a += 32) out[dr * n_alpha + a] = (double)cnt[w * n_alpha + a] / (double)n;
     if (counts) {                                        // integer totals over the rows of this launch: order independent
         __syncthreads();
+        const int64_t first = (int64_t)blockIdx.x * COVG_ROWS;
         for (int a = tid; a < n_alpha; a += COVG_WARPS * 32) {
             unsigned long long t = 0;
-            for (int ww = 0; ww < COVG_WARPS; ww++)
-                if ((int64_t)blockIdx.x * COVG_WARPS + ww < n_draws) t += (unsigned long long)cnt[ww * n_alpha + a];
+            for (int rr = 0; rr < COVG_ROWS; rr++)
+                if (first + rr < n_draws) t += (unsigned long long)cnt[rr * n_alpha + a];
             if (t) atomicAdd(&counts[a], t);
         }
     }

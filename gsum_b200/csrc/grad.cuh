@@ -19,7 +19,9 @@
 
 #define GRAD_MAXR 16
 
-// Y_p[i][b] = sum_j dR_p(i,j) Z[j][b];  trow_p[i] = sum_j Rinv[j][i] dR_p(i,j).   grid (ceil(n/128), P), block 128.
+// Y_p[i][b] = sum_j dR_p(i,j) Z[j][b];  trow_p[i] = sum_j Rinv[j][i] dR_p(i,j).   grid (ceil(n/128), P, ceil(n/128)), block 128:
+// blockIdx.z is a chunk of 128 columns j — every CTA writes the PARTIAL sums of its chunk (Y[jc][p][i][b], trow[jc][p][i])
+// and grad_reduce_kernel adds the chunks in a fixed order (deterministic, and (n/128)^2 P CTAs instead of (n/128) P).
 __global__ void __launch_bounds__(128) grad_rows_kernel(const double *__restrict__ XS, int64_t n, int d, int ls_dim, double constant,
                                                         double noise, const double *__restrict__ Zall, int64_t ldz, int r,
                                                         double *__restrict__ Y, double *__restrict__ trow) {
@@ -35,8 +37,9 @@ __global__ void __launch_bounds__(128) grad_rows_kernel(const double *__restrict
     for (int b = 0; b < GRAD_MAXR; b++) acc[b] = 0.0;
     double tacc = 0.0;
     const double *Rinv = Zall + r;                 // columns r .. r + n - 1 of [Z | R^{-1}]
-    for (int64_t j0 = 0; j0 < n; j0 += 128) {
-        __syncthreads();
+    const int64_t jc = blockIdx.z, nP = gridDim.y;
+    {
+        const int64_t j0 = jc * 128;
         for (int e = threadIdx.x; e < 128 * d; e += 128) {
             const int64_t j = j0 + e / d;
             xs_j[(e / d) * COV_MAXD + e % d] = j < n ? XS[j * d + e % d] : 0.0;
@@ -46,8 +49,7 @@ __global__ void __launch_bounds__(128) grad_rows_kernel(const double *__restrict
             z_j[(e / r) * GRAD_MAXR + e % r] = j < n ? Zall[j * ldz + e % r] : 0.0;
         }
         __syncthreads();
-        if (!live) continue;
-        const int jn = (int)((n - j0 < 128) ? (n - j0) : 128);
+        const int jn = live ? (int)((n - j0 < 128) ? (n - j0) : 128) : 0;
         for (int jj = 0; jj < jn; jj++) {
             const int64_t j = j0 + jj;
             double w;
@@ -71,30 +73,38 @@ __global__ void __launch_bounds__(128) grad_rows_kernel(const double *__restrict
         }
     }
     if (live) {
-        for (int b = 0; b < r; b++) Y[((int64_t)p * n + i) * GRAD_MAXR + b] = acc[b];
-        trow[(int64_t)p * n + i] = tacc;
+        for (int b = 0; b < r; b++) Y[(((int64_t)jc * nP + p) * n + i) * GRAD_MAXR + b] = acc[b];
+        trow[((int64_t)jc * nP + p) * n + i] = tacc;
     }
 }
-// H_p[a][b] = sum_i Z[i][a] Y_p[i][b],  t_p = sum_i trow_p[i];  G[a][b] = sum_i RHS[i][a] Z[i][b]  (block P handles G).
-// One block per p (and one more for G), fixed summation order.
+// H_p[a][b] = sum_i Z[i][a] Y_p[i][b],  t_p = sum_i trow_p[i];  G[a][b] = sum_i RHS[i][a] Z[i][b]  (blockIdx.x = P handles G).
+// One block per (p, a, b); Y_p[i][b] and trow_p[i] are the sums of their `nchunk` partials, added in chunk order: fixed
+// summation order throughout.
 __global__ void __launch_bounds__(256) grad_reduce_kernel(const double *__restrict__ Zall, int64_t ldz, const double *__restrict__ RHS,
                                                           const double *__restrict__ Y, const double *__restrict__ trow, int64_t n, int r,
-                                                          int P, double *__restrict__ H, double *__restrict__ tr, double *__restrict__ G) {
+                                                          int P, int nchunk, double *__restrict__ H, double *__restrict__ tr,
+                                                          double *__restrict__ G) {
     __shared__ double red[32];
-    const int p = blockIdx.x;
-    for (int ab = 0; ab < r * r; ab++) {
-        const int a = ab / r, b = ab % r;
-        double s = 0.0;
-        for (int64_t i = threadIdx.x; i < n; i += 256)
-            s += (p < P) ? Zall[i * ldz + a] * Y[((int64_t)p * n + i) * GRAD_MAXR + b] : RHS[i * r + a] * Zall[i * ldz + b];
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) { if (p < P) H[((int64_t)p * r + a) * r + b] = s; else G[a * r + b] = s; }
+    const int p = blockIdx.x, ab = blockIdx.y, a = ab / r, b = ab % r;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) {
+        if (p < P) {
+            double y = 0.0;
+            for (int jc = 0; jc < nchunk; jc++) y += Y[(((int64_t)jc * P + p) * n + i) * GRAD_MAXR + b];
+            s += Zall[i * ldz + a] * y;
+        } else s += RHS[i * r + a] * Zall[i * ldz + b];
     }
-    if (p < P) {
-        double s = 0.0;
-        for (int64_t i = threadIdx.x; i < n; i += 256) s += trow[(int64_t)p * n + i];
-        s = block_sum(s, red);
-        if (threadIdx.x == 0) tr[p] = s;
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) { if (p < P) H[((int64_t)p * r + a) * r + b] = s; else G[a * r + b] = s; }
+    if (p < P && ab == 0) {
+        double t = 0.0;
+        for (int64_t i = threadIdx.x; i < n; i += 256) {
+            double y = 0.0;
+            for (int jc = 0; jc < nchunk; jc++) y += trow[((int64_t)jc * P + p) * n + i];
+            t += y;
+        }
+        t = block_sum(t, red);
+        if (threadIdx.x == 0) tr[p] = t;
     }
 }
 // B = [RHS | I]  (n x (r + n), row major)

@@ -817,12 +817,14 @@ extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int3
     const int64_t ldz = r + n;
     GSUM_TRY(gsum_ws(c, WS_G3, sizeof(double) * n * n, &dR));
     GSUM_TRY(gsum_ws(c, WS_G4, sizeof(double) * n * ldz, &dB));
-    // small outputs and per-row partials: G (r*r) | H (P*r*r) | tr (P) | logdet (1) | Y (P*n*GRAD_MAXR) | trow (P*n) | info
-    const size_t nsmall = (size_t)r * r + (size_t)P * r * r + P + 1;
-    GSUM_TRY(gsum_ws(c, WS_G5, sizeof(double) * (nsmall + (size_t)P * n * GRAD_MAXR + (size_t)P * n) + 64, &dsm));
+    // small outputs and per-row partials (one set per chunk of 128 columns):
+    // G (r*r) | H (P*r*r) | tr (P) | logdet (1) | Y (nchunk*P*n*GRAD_MAXR) | trow (nchunk*P*n) | info
+    const int nchunk = (int)((n + 127) / 128);
+    const size_t nsmall = (size_t)r * r + (size_t)P * r * r + P + 1, nrows = (size_t)nchunk * P * n;
+    GSUM_TRY(gsum_ws(c, WS_G5, sizeof(double) * (nsmall + nrows * GRAD_MAXR + nrows) + 64, &dsm));
     double *dG = (double *)dsm, *dH = dG + r * r, *dtr = dH + (size_t)P * r * r, *dld = dtr + P, *dY = dld + 1,
-           *dtrow = dY + (size_t)P * n * GRAD_MAXR;
-    int32_t *dinfo = (int32_t *)(dtrow + (size_t)P * n);
+           *dtrow = dY + nrows * GRAD_MAXR;
+    int32_t *dinfo = (int32_t *)(dtrow + nrows);
     // R = c * rbf + noise I (diagonal exactly c + noise), then + nugget, as gsum/models.py:960-963
     GSUM_TRY(gsum_kernel_matrix(c, (const double *)dX, n, nullptr, 0, d, (const double *)dls, ls_dim, constant, noise, (double *)dR, GSUM_MEM_DEVICE));
     add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((double *)dR, n, n, nugget);
@@ -834,9 +836,10 @@ extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int3
     // scaled coordinates (gsum_kernel_matrix left X / ls in WS_XS)
     const double *dXS = (const double *)c->ws[WS_XS];
     const size_t shbytes = sizeof(double) * (128 * COV_MAXD + 128 * GRAD_MAXR);
-    grad_rows_kernel<<<dim3((unsigned)((n + 127) / 128), (unsigned)P), 128, shbytes, c->stream>>>(dXS, n, d, ls_dim, constant, noise, (const double *)dB,
-                                                                                               ldz, r, dY, dtrow);
-    grad_reduce_kernel<<<P + 1, 256, 0, c->stream>>>((const double *)dB, ldz, (const double *)dRHS, dY, dtrow, n, r, P, dH, dtr, dG);
+    grad_rows_kernel<<<dim3((unsigned)nchunk, (unsigned)P, (unsigned)nchunk), 128, shbytes, c->stream>>>(dXS, n, d, ls_dim, constant, noise,
+                                                                                                      (const double *)dB, ldz, r, dY, dtrow);
+    grad_reduce_kernel<<<dim3((unsigned)(P + 1), (unsigned)(r * r)), 256, 0, c->stream>>>((const double *)dB, ldz, (const double *)dRHS, dY, dtrow, n, r,
+                                                                                          P, nchunk, dH, dtr, dG);
     LAUNCHED(c, 2);
     if (mem_kind == GSUM_MEM_DEVICE) {
         GSUM_CUDA(c, cudaMemcpyAsync(G, dG, sizeof(double) * r * r, cudaMemcpyDeviceToDevice, c->stream));
@@ -1329,9 +1332,9 @@ static int coverage_rows(gsum_ctx *c, const double *dYt, int64_t ld, int64_t n_r
             (const double *)dlo, (const double *)dup, n_alpha, (int)n, (int *)dnested);
         LAUNCHED(c, 1);
     }
-    const size_t smem = sizeof(double) * 2 * n_alpha * 32 + sizeof(int) * COVG_WARPS * n_alpha;
+    const size_t smem = sizeof(double) * 2 * n_alpha * 32 + sizeof(int) * COVG_ROWS * n_alpha;
     GSUM_CUDA(c, cudaFuncSetAttribute(coverage_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    coverage_rows_kernel<<<(unsigned)((n_rows + COVG_WARPS - 1) / COVG_WARPS), COVG_WARPS * 32, smem, c->stream>>>(
+    coverage_rows_kernel<<<(unsigned)((n_rows + COVG_ROWS - 1) / COVG_ROWS), COVG_WARPS * 32, smem, c->stream>>>(
         dYt, ld, n_rows, (int)n, (const double *)dlo, (const double *)dup, n_alpha, (double *)dcov, (unsigned long long *)dcnt,
         (const int *)dnested);
     LAUNCHED(c, 1);

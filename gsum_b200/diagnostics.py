@@ -153,7 +153,14 @@ class Diagnostic:
 
     # -- credible intervals ------------------------------------------------------------------------
     def _bounds(self, intervals):
-        lower, upper = self.udist.interval(np.atleast_2d(intervals).T)
+        """End points (n_intervals, n_samples) of the central credible intervals of the marginals — what the reference gets
+        from `self.udist.interval(np.atleast_2d(intervals).T)` (gsum/diagnostics.py:161).  scipy evaluates
+        `ppf(q) * scale + loc` element by element; the quantile depends on the level only, so it is computed once per level
+        (n_intervals calls of the inverse CDF instead of n_intervals * n_samples) and expanded with the same multiply and
+        add: bit-identical end points (tests/test_host_logic.py::test_interval_bounds_match_scipy)."""
+        zl, zu = self.std_udist.interval(np.atleast_1d(np.asarray(intervals, dtype=np.float64)))
+        lower = zl[:, None] * self.sd[None, :] + self.mean[None, :]
+        upper = zu[:, None] * self.sd[None, :] + self.mean[None, :]
         return np.ascontiguousarray(lower), np.ascontiguousarray(upper)
 
     def credible_interval(self, y, intervals):

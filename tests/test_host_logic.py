@@ -161,6 +161,23 @@ def test_sharded_draws_and_predict_gloo_world2():
         assert m_only.shape == (1, 2) and np.array_equal(m_only[0], [-2.0, 1.0])
 
 
+@pytest.mark.parametrize("df", [None, 7.0])
+def test_interval_bounds_match_scipy(df):
+    """Diagnostic._bounds (one inverse-CDF call per level, expanded by multiply + add) is bit-identical to the reference's
+    `udist.interval(np.atleast_2d(intervals).T)` (gsum/diagnostics.py:161), Gaussian and Student-t, end levels included."""
+    import scipy.stats as st
+    from gsum_b200.diagnostics import Diagnostic
+    rs = np.random.RandomState(0)
+    d = Diagnostic.__new__(Diagnostic)                      # host-side pieces only: no device factorisation here
+    d.mean, d.sd = rs.randn(300), 0.5 + rs.rand(300)
+    d.std_udist = st.norm(loc=0., scale=1.) if df is None else st.t(loc=0., scale=1., df=df)
+    udist = st.norm(loc=d.mean, scale=d.sd) if df is None else st.t(loc=d.mean, scale=d.sd, df=df)
+    iv = np.concatenate([np.linspace(0, 1, 101), [0.6827, 0.9545]])
+    lower, upper = d._bounds(iv)
+    want_lower, want_upper = udist.interval(np.atleast_2d(iv).T)
+    assert np.array_equal(lower, want_lower) and np.array_equal(upper, want_upper)
+
+
 def test_facade_rejects_out_of_scope_options():
     from gsum_b200 import ConjugateGaussianProcess, Diagnostic, TruncationGP
     with pytest.raises(NotImplementedError):

@@ -11,7 +11,8 @@ KEYS = [
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput % of peak"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots active %"),
-    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 pipe active % (of active cycles)"),
+    ("sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active", "DMMA (FP64 tensor) pipe active %"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 (DFMA) pipe active %"),
     ("sm__inst_executed_pipe_fp64.sum", "FP64-pipe warp instructions"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("launch__grid_size", "grid"), ("launch__block_size", "block"), ("launch__registers_per_thread", "regs/thread"),
