@@ -19,4 +19,5 @@ cap draws          c5   '^draws_kernel'            1
 cap coverage       c5   '^coverage_rows_kernel'    0
 cap normal_rows    c5   '^normal_rows_kernel'      0
 cap grad_rows      grad '^grad_rows_kernel'        0
+cap grad_reduce    grad '^grad_reduce_kernel'      0
 python tools/ncu_summary.py gpurun_out/side_*.csv | tee gpurun_out/side_summary.txt
