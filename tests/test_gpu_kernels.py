@@ -108,3 +108,25 @@ def test_factorisation_schedules_agree(schedule, monkeypatch):
         assert relerr(ll, ll0) < 1e-10
     finally:
         c.close()
+
+
+def test_large_single_matrix_8192(ctx):
+    """Beyond the BASELINE sizes: one N = 8192 matrix (128 tile columns) through kernel build, Cholesky, solve and the
+    cooperative pivoted Cholesky (64 CTAs) — checked through residuals, which need no O(N^3) host work."""
+    from sklearn.gaussian_process.kernels import RBF
+    n = 8192
+    X = np.sort(np.random.RandomState(7).rand(n))[:, None]
+    A = ops.kernel_matrix(X, None, 0.01, constant=1.0, noise=1e-3)
+    ref = RBF(0.01)(X[4000:4200], X[100:400])
+    assert np.max(np.abs(A[4000:4200, 100:400] - ref)) < 1e-15
+    L = ops.cholesky(A)
+    assert np.all(np.triu(L, 1) == 0)
+    v = np.random.RandomState(0).randn(n, 3)
+    Av = A @ v
+    assert np.max(np.abs(L @ (L.T @ v) - Av)) / np.max(np.abs(Av)) < 1e-13
+    assert np.max(np.abs(ops.cho_solve(L, Av) - v)) < 1e-8
+    G, Lp, piv, rank, status = ops.pivoted_cholesky(A)
+    assert status == 0 and rank == n and sorted(piv.tolist()) == list(range(n))
+    assert np.max(np.abs(G @ (G.T @ v) - Av)) / np.max(np.abs(Av)) < 1e-13
+    d = np.diag(Lp)
+    assert np.all(d[:-1] >= d[1:] * (1 - 1e-9))                 # pivoted Cholesky invariant: non-increasing diagonal
