@@ -54,6 +54,33 @@ def test_interpolation_property(ctx):
     np.testing.assert_almost_equal(np.diag(y_cov), 0., decimal=10)
 
 
+@pytest.mark.parametrize("kernel", [
+    RBF(length_scale=1.0),
+    RBF(length_scale=1.0, length_scale_bounds=(1e-3, 1e3)),
+    C(1.0, (1e-2, 1e2)) * RBF(length_scale=1.0, length_scale_bounds=(1e-3, 1e3)),
+], ids=["rbf", "rbf_bounds", "const_rbf"])
+def test_interpolation_property_free_theta(ctx, kernel):
+    """gsum/tests/test.py:63-72 with the reference's non-fixed kernels (`kernels[0], [2], [3]`): the hyper-parameters go
+    through the L-BFGS driver on the device gradient first (the reference's own driver crashes on numpy >= 1.24,
+    gsum/models.py:664), then the same interpolation assertions.  `kernels[4]` adds a ConstantKernel term, which the
+    descriptor {c, l, sigma^2} cannot express: that one must raise instead of falling back."""
+    X = np.atleast_2d([1., 3., 5., 6., 7., 8.]).T
+    y = (X * np.sin(X)).ravel()
+    gpr = gb.ConjugateGaussianProcess(kernel=kernel, nugget=0).fit(X, y)
+    y_pred, y_cov = gpr.predict(X, return_cov=True)
+    np.testing.assert_almost_equal(y_pred, y)
+    np.testing.assert_almost_equal(np.diag(y_cov), 0., decimal=10)
+    assert np.all(np.isfinite(gpr.kernel_.theta))
+
+
+def test_interpolation_additive_constant_kernel_raises(ctx):
+    X = np.atleast_2d([1., 3., 5., 6., 7., 8.]).T
+    y = (X * np.sin(X)).ravel()
+    k4 = C(1.0, (1e-2, 1e2)) * RBF(length_scale=1.0, length_scale_bounds=(1e-3, 1e3)) + C(1e-5, (1e-5, 1e2))
+    with pytest.raises(NotImplementedError):
+        gb.ConjugateGaussianProcess(kernel=k4, nugget=0).fit(X, y)
+
+
 def test_prior_predict_and_cov_before_fit(ctx):
     gp = gb.ConjugateGaussianProcess(C(2.0) * RBF(0.3) + WhiteKernel(1e-3), center=0.4, df=5, scale=1.5)
     X = np.linspace(0, 1, 30)[:, None]
