@@ -59,6 +59,9 @@ _SIGNATURES = {
     "gsum_draws": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int32,
                              _vp, _vp, C.c_int32]),
     "gsum_credible_interval": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, _vp, _vp, C.c_int32, _vp, C.c_int32]),
+    "gsum_eigh": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int32]),
+    "gsum_eig_conditional": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, _vp, C.c_int32]),
+    "gsum_eig_solve": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, _vp, C.c_int32, C.c_int32]),
 }
 
 _lib = None

@@ -1,0 +1,235 @@
+// decomposition='eig' route: a symmetric FP64 eigensolver and the solves built on it.
+//
+//   reference call sites: scipy `eigh(R)` at gsum/models.py:714, 811, 974, 1166, 1216; numpy `eigh(cov)` at
+//   gsum/diagnostics.py:63; `solve_sqrt(..., 'eig')` = Q diag(1/eig) Q^T y at models.py:480-484;
+//   `eigen_errors` = solve(Q diag(sqrt(eig)), y - mean) at diagnostics.py:106-107.
+//
+// Eigensolver: one-sided (Hestenes) Jacobi on G = A V.  G and V are kept TRANSPOSED (row j = column j), so a plane
+// rotation of columns (p, q) touches four contiguous rows; A is symmetric, so G starts as a plain copy of A.  One launch
+// per round of the round-robin tournament: n/2 disjoint pairs, one CTA per pair, which
+//   (1) reads rows g_p, g_q once for alpha = |g_p|^2, beta = |g_q|^2, gamma = g_p . g_q,
+//   (2) skips the pair when |gamma| <= tol sqrt(alpha beta)  (tol = sqrt(n) eps, the LAPACK dgesvj criterion) or
+//       |gamma| <= 0.1 eps |A|_F min(|g_p|, |g_q|)  (below the eps |A| accuracy any eigensolver delivers),
+//   (3) otherwise rotates rows p, q of G and of V^T and counts the rotation.
+// A sweep is n - 1 rounds; the iteration stops after a sweep without rotations.  On exit the rows of G are orthogonal:
+// |lambda_j| = |g_j|, sign from v_j . g_j, eigenvector j = row j of V^T.  Accuracy is that of LAPACK's eigh: eigenvalues
+// to eps |A| absolute, residuals |A v - lambda v| <= O(eps |A|).  (Scope: the covariance / correlation matrices of
+// the reference's call sites, i.e. positive semi-definite up to rounding.  An indefinite matrix with a pair of eigenvalues
+// +lambda, -lambda has a repeated SINGULAR value whose vectors the one-sided iteration cannot separate; gsum_eigh detects
+// that through the Rayleigh quotients and reports it instead of returning wrong vectors.)
+// Measured dead ends (profiles/r01_notes.md, session 5): de Rijk column ordering inside the rotation (more sweeps, not
+// fewer, with the round-robin tournament) and iterating on the Cholesky / pivoted-Cholesky factor of A (same 17-22 sweeps
+// on RBF + noise matrices — the large cluster of eigenvalues at the noise level converges linearly either way — and no
+// convergence at cond 1e8).
+// HBM/L2-bound: each round streams G and V^T once (4 n^2 x 8 B read+write when every pair rotates).
+#pragma once
+#include "common.cuh"
+
+#define JAC_THREADS 256
+#define JAC_MAX_SWEEPS 40
+
+// Round-robin pairing (circle method) of np indices (np even): round r in [0, np-1), slot k in [0, np/2).
+__device__ __forceinline__ void jacobi_pair(int np, int r, int k, int &p, int &q) {
+    const int m = np - 1;
+    if (k == 0) { p = m; q = r; }
+    else { p = (r + k) % m; q = (r - k + m) % m; }
+    if (p > q) { int t = p; p = q; q = t; }
+}
+
+// G <- A (n x n, leading dimension ld), Vt <- I
+__global__ void __launch_bounds__(256) jacobi_init_kernel(const double *__restrict__ A, double *__restrict__ G, double *__restrict__ Vt,
+                                                          int n, int64_t ld) {
+    const int64_t r = blockIdx.x;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        G[r * ld + c] = A[r * (int64_t)n + c];
+        Vt[r * ld + c] = (c == r) ? 1.0 : 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(double *__restrict__ G, double *__restrict__ Vt, int n, int64_t ld, int np,
+                                                                   int round, double tol, double tol_abs, unsigned int *__restrict__ rotations) {
+    __shared__ double red[3][JAC_THREADS / 32];
+    int p, q;
+    jacobi_pair(np, round, blockIdx.x, p, q);
+    if (q >= n) return;                                   // the padding index of an odd n sits this round out
+    double *gp = G + p * ld, *gq = G + q * ld;
+    double a = 0.0, b = 0.0, g = 0.0;
+    for (int i = threadIdx.x; i < n; i += JAC_THREADS) {
+        const double x = gp[i], y = gq[i];
+        a = fma(x, x, a); b = fma(y, y, b); g = fma(x, y, g);
+    }
+    a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { red[0][w] = a; red[1][w] = b; red[2][w] = g; }
+    __syncthreads();
+    a = b = g = 0.0;
+#pragma unroll
+    for (int i = 0; i < JAC_THREADS / 32; i++) { a += red[0][i]; b += red[1][i]; g += red[2][i]; }
+    // rotate when the pair is non-orthogonal relatively (|gamma| > tol |g_p| |g_q|, the dgesvj criterion) and, if an
+    // absolute tolerance is set, also on the scale of eps |A| (|gamma| > tol_abs min(|g_p|, |g_q|): ignoring gamma moves a
+    // singular value by gamma / (2 sigma) at most).  Measured on RBF + noise matrices (N = 1024): tol_abs = eps |A|_F saves a
+    // quarter of the sweeps (24 -> 18) but triples the residual of R^-1 y; 0.1 eps |A|_F (the default) takes 19 sweeps
+    // with the residual of the purely relative criterion (3e-10 vs 6e-10).
+    // The negated form also catches a zero column and NaN.
+    if (!(fabs(g) > tol * sqrt(a) * sqrt(b)) || !(fabs(g) > tol_abs * sqrt(fmin(a, b)))) return;
+    if (threadIdx.x == 0) atomicAdd(rotations, 1u);
+    const double zeta = (b - a) / (2.0 * g);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+    double *vp = Vt + p * ld, *vq = Vt + q * ld;
+    for (int i = threadIdx.x; i < n; i += JAC_THREADS) {
+        const double x = gp[i], y = gq[i];
+        gp[i] = cs * x - sn * y; gq[i] = sn * x + cs * y;
+        const double u = vp[i], v = vq[i];
+        vp[i] = cs * u - sn * v; vq[i] = sn * u + cs * v;
+    }
+}
+
+// w[j] = sign(v_j . g_j) |g_j|;  rq[j] = v_j . g_j (the Rayleigh quotient: equals w[j] when v_j is an eigenvector);  flip[j] = -1 when the largest-magnitude component of v_j is negative (the eigenvector is
+// returned with that component positive), else +1.  One CTA per row.
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_finish_kernel(const double *__restrict__ G, const double *__restrict__ Vt, int n, int64_t ld,
+                                                                    double *__restrict__ w, double *__restrict__ flip, double *__restrict__ rq) {
+    __shared__ double red[4][JAC_THREADS / 32];
+    const int64_t j = blockIdx.x;
+    const double *g = G + j * ld, *v = Vt + j * ld;
+    double nn = 0.0, dot = 0.0, big = -1.0, bigv = 0.0;
+    for (int i = threadIdx.x; i < n; i += JAC_THREADS) {
+        const double x = g[i], y = v[i];
+        nn = fma(x, x, nn); dot = fma(x, y, dot);
+        if (fabs(y) > big) { big = fabs(y); bigv = y; }
+    }
+    nn = warp_sum(nn); dot = warp_sum(dot);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, big, o), ov = __shfl_xor_sync(0xffffffffu, bigv, o);
+        if (ob > big) { big = ob; bigv = ov; }
+    }
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][wp] = nn; red[1][wp] = dot; red[2][wp] = big; red[3][wp] = bigv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        nn = dot = 0.0; big = -1.0; bigv = 0.0;
+        for (int i = 0; i < JAC_THREADS / 32; i++) {
+            nn += red[0][i]; dot += red[1][i];
+            if (red[2][i] > big) { big = red[2][i]; bigv = red[3][i]; }
+        }
+        w[j] = copysign(sqrt(nn), dot);
+        rq[j] = dot;
+        flip[j] = bigv < 0.0 ? -1.0 : 1.0;
+    }
+}
+
+// V[i][k] = flip[perm[k]] * Vt[perm[k]][i]      (eigenvectors as COLUMNS of a row-major (n, n) array, LAPACK order)
+__global__ void __launch_bounds__(256) jacobi_gather_kernel(const double *__restrict__ Vt, int64_t ld, const int32_t *__restrict__ perm,
+                                                            const double *__restrict__ flip, int n, double *__restrict__ V) {
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, i = i0 + tx;
+        double v = 0.0;
+        if (k < n && i < n) { const int src = perm[k]; v = flip[src] * Vt[src * ld + i]; }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, k = k0 + tx;
+        if (i < n && k < n) V[(int64_t)i * n + k] = tile[tx][r];
+    }
+}
+
+// ---- C (M x N) = op(A) (M x K) . diag(1/bdiv) (B (K x N) - bsub[k]) with an optional row scaling --------------------------------
+// Row-major operands; op(A) = A (lda >= K) or A^T (A stored K x M, lda >= M).  64 x 64 tile per CTA, four warps of
+// 32 x 32, FP64 tensor-core MMA (DMMA 8x8x4) on fragments read from padded shared memory (stride 36: conflict-free).
+// row_mode: 0 none, 1 C[m][:] /= rs[m], 2 C[m][:] /= sqrt(|rs[m]|).
+struct EigGemmArgs {
+    const double *A; int64_t lda; int transA;
+    const double *B; int64_t ldb;
+    double *C; int64_t ldc;
+    int64_t M, N, K;
+    const double *bsub;                 // B[k][:] - bsub[k]
+    const double *bdiv;                 // (B[k][:] - bsub[k]) / bdiv[k]
+    const double *rs; int row_mode;
+};
+
+__global__ void __launch_bounds__(128) eig_gemm_kernel(EigGemmArgs P) {
+    __shared__ double As[64][GSUM_LDH];
+    __shared__ double Bs[64][GSUM_LDH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+    const int64_t m0 = (int64_t)blockIdx.y * 64, n0 = (int64_t)blockIdx.x * 64;
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int64_t k0 = 0; k0 < P.K; k0 += GSUM_KH) {
+        if (P.transA) {
+#pragma unroll 4
+            for (int e = tid; e < 64 * GSUM_KH; e += 128) {
+                const int m = e & 63, k = e >> 6;
+                const int64_t gm = m0 + m, gk = k0 + k;
+                As[m][k] = (gm < P.M && gk < P.K) ? P.A[gk * P.lda + gm] : 0.0;
+            }
+        } else {
+#pragma unroll 4
+            for (int e = tid; e < 64 * GSUM_KH; e += 128) {
+                const int k = e & (GSUM_KH - 1), m = e / GSUM_KH;
+                const int64_t gm = m0 + m, gk = k0 + k;
+                As[m][k] = (gm < P.M && gk < P.K) ? P.A[gm * P.lda + gk] : 0.0;
+            }
+        }
+#pragma unroll 4
+        for (int e = tid; e < 64 * GSUM_KH; e += 128) {
+            const int n = e & 63, k = e >> 6;
+            const int64_t gn = n0 + n, gk = k0 + k;
+            double v = 0.0;
+            if (gn < P.N && gk < P.K) {
+                v = P.B[gk * P.ldb + gn];
+                if (P.bsub) v -= P.bsub[gk];
+                if (P.bdiv) v *= 1.0 / P.bdiv[gk];
+            }
+            Bs[n][k] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GSUM_KH; kk += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[wm + 8 * i + g][kk + t];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[wn + 8 * j + g][kk + t];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int64_t gm = m0 + wm + 8 * i + g;
+        if (gm >= P.M) continue;
+        double s = 1.0;
+        if (P.row_mode == 1) s = 1.0 / P.rs[gm];
+        else if (P.row_mode == 2) s = 1.0 / sqrt(fabs(P.rs[gm]));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t gn = n0 + wn + 8 * j + 2 * t;
+            if (gn < P.N) P.C[gm * P.ldc + gn] = s * acc[i][j][0];
+            if (gn + 1 < P.N) P.C[gm * P.ldc + gn + 1] = s * acc[i][j][1];
+        }
+    }
+}
+
+// out[j] = sum_k U[k][j]^2 / w[k]      (diag of U^T diag(1/w) U; U is (n x m) row-major: coalesced over j)
+__global__ void __launch_bounds__(256) eig_colquad_kernel(const double *__restrict__ U, int64_t n, int64_t m, const double *__restrict__ w,
+                                                          double *__restrict__ out) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    double s = 0.0;
+    for (int64_t k = 0; k < n; k++) { const double u = U[k * m + j]; s = fma(u * (1.0 / w[k]), u, s); }
+    out[j] = s;
+}

@@ -1405,3 +1405,203 @@ extern "C" int gsum_credible_interval(gsum_ctx *c, const double *Y, int64_t n, i
     GSUM_TRY(coverage_rows(c, (const double *)dYt, np, n_curves, n, lower, upper, n_alpha, coverage_out, nullptr, mem_kind));
     return finish(c, mem_kind);
 }
+
+// ---- decomposition='eig' route (eig.cuh) -------------------------------------------------------------------------
+#include "eig.cuh"
+#include <vector>
+#include <algorithm>
+#include <numeric>
+
+extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, double *V, int32_t *sweeps_out, int32_t mem_kind) {
+    if (!c || !A || !w || n <= 0 || n > (1 << 20)) return gsum_fail(c, -1, "gsum_eigh: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    mem_kind &= 1;
+    const int ni = (int)n, np = ni + (ni & 1);
+    const int64_t ld = n;
+    const void *dA;
+    void *dG, *dVt, *dw, *dflip, *dperm, *dcnt;
+    GSUM_TRY(dev_in(c, WS_IO0, A, sizeof(double) * n * n, mem_kind, &dA));
+    std::vector<double> hw(n), hs(n), hrq(n);
+    const double eps = 2.220446049250313e-16;
+    const double tol = sqrt((double)n) * eps;
+    double tol_abs = 0.0;
+
+    GSUM_TRY(gsum_ws(c, WS_IO1, sizeof(double) * n * ld, &dG));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * n * ld, &dVt));
+    GSUM_TRY(gsum_ws(c, WS_LL, sizeof(double) * n, &dw));
+    GSUM_TRY(gsum_ws(c, WS_SCALE, sizeof(double) * 2 * n, &dflip));
+    GSUM_TRY(gsum_ws(c, WS_ORD, sizeof(int32_t) * n, &dperm));
+    GSUM_TRY(gsum_ws(c, WS_COUNTS, sizeof(unsigned int) * (JAC_MAX_SWEEPS + 1), &dcnt));
+    GSUM_CUDA(c, cudaMemsetAsync(dcnt, 0, sizeof(unsigned int) * (JAC_MAX_SWEEPS + 1), c->stream));
+    dim3 gt((unsigned)((n + 31) / 32), (unsigned)((n + 31) / 32));
+    // G <- A, V <- I; |A|_F scales the optional absolute part of the rotation criterion (eig.cuh; GSUM_B200_EIGH_ABS = c
+    // skips pairs with |gamma| <= c eps |A|_F min(|g_p|, |g_q|); default c = 0.1, c = 0: relative criterion only)
+    jacobi_init_kernel<<<(unsigned)n, 256, 0, c->stream>>>((const double *)dA, (double *)dG, (double *)dVt, ni, ld);
+    rows_sqnorm_kernel<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>((const double *)dG, ld, n, n, (double *)dw);
+    LAUNCHED(c, 2);
+    GSUM_CUDA(c, cudaMemcpyAsync(hw.data(), dw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    double fro2 = 0.0;
+    for (int64_t i = 0; i < n; i++) fro2 += hw[i];
+    tol_abs = 0.1 * eps * sqrt(fro2);
+    if (const char *e = getenv("GSUM_B200_EIGH_ABS")) tol_abs = atof(e) * eps * sqrt(fro2);
+    // One sweep = n - 1 dependent launches of a few microseconds each: launch-bound, so the sweep is captured once as a
+    // CUDA graph (counter reset + the rounds) and replayed until a sweep makes no rotation.
+    int sweeps = 0;
+    bool converged = (n == 1);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    if (!converged) {
+        GSUM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        cudaMemsetAsync(dcnt, 0, sizeof(unsigned int), c->stream);
+        for (int r = 0; r < np - 1; r++)
+            jacobi_round_kernel<<<np / 2, JAC_THREADS, 0, c->stream>>>((double *)dG, (double *)dVt, ni, ld, np, r, tol, tol_abs,
+                                                                      (unsigned int *)dcnt);
+        GSUM_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
+        GSUM_CUDA(c, cudaGraphInstantiate(&gexec, graph, 0));
+    }
+    int rc_loop = 0;
+    while (!converged && sweeps < JAC_MAX_SWEEPS) {
+        unsigned int rot = 0;
+        if (cudaGraphLaunch(gexec, c->stream) != cudaSuccess ||
+            cudaMemcpyAsync(&rot, dcnt, sizeof(rot), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+            cudaStreamSynchronize(c->stream) != cudaSuccess) { rc_loop = -100; break; }
+        LAUNCHED(c, np - 1);
+        sweeps++;
+        converged = (rot == 0);
+    }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    if (rc_loop) return gsum_fail(c, -100, "gsum_eigh: CUDA error in the sweep graph (%s)", cudaGetErrorString(cudaGetLastError()));
+    if (sweeps_out) *sweeps_out = sweeps;
+    jacobi_finish_kernel<<<(unsigned)n, JAC_THREADS, 0, c->stream>>>((const double *)dG, (const double *)dVt, ni, ld, (double *)dw, (double *)dflip,
+                                                                     (double *)dflip + n);
+    GSUM_CUDA(c, cudaMemcpyAsync(hrq.data(), (double *)dflip + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    LAUNCHED(c, 1);
+    std::vector<int32_t> perm(n);
+    GSUM_CUDA(c, cudaMemcpyAsync(hw.data(), dw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::iota(perm.begin(), perm.end(), 0);
+    std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return hw[a] < hw[b]; });
+    for (int64_t i = 0; i < n; i++) hs[i] = hw[perm[i]];
+    // v_j is an eigenvector iff its Rayleigh quotient reproduces |g_j| (see eig.cuh: +/- lambda pairs of an indefinite matrix)
+    bool mixed = false;
+    const double wmax = std::max(fabs(hs[0]), fabs(hs[n - 1]));
+    for (int64_t i = 0; i < n; i++)
+        if (fabs(hw[i]) - fabs(hrq[i]) > 1e-6 * fabs(hw[i]) + 1e-10 * wmax) mixed = true;
+    if (mem_kind == GSUM_MEM_DEVICE) GSUM_CUDA(c, cudaMemcpy(w, hs.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+    else memcpy(w, hs.data(), sizeof(double) * n);
+    if (V) {
+        GSUM_CUDA(c, cudaMemcpy(dperm, perm.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+        void *dV;
+        GSUM_TRY(dev_out(c, WS_IO2, V, sizeof(double) * n * n, mem_kind, &dV));
+        jacobi_gather_kernel<<<gt, 256, 0, c->stream>>>((const double *)dVt, ld, (const int32_t *)dperm,
+                                                       (const double *)dflip, ni, (double *)dV);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, V, dV, sizeof(double) * n * n, mem_kind));
+    }
+    GSUM_TRY(finish(c, mem_kind));
+    if (!converged) {
+        gsum_fail(c, 1, "gsum_eigh: Jacobi iteration did not converge in %d sweeps", JAC_MAX_SWEEPS);
+        return 1;
+    }
+    if (mixed) {
+        gsum_fail(c, 2, "gsum_eigh: indefinite matrix with eigenvalues of equal magnitude and opposite sign (not separable by one-sided Jacobi)");
+        return 2;
+    }
+    return 0;
+}
+
+static void launch_eig_gemm(gsum_ctx *c, const EigGemmArgs &g) {
+    dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64));
+    eig_gemm_kernel<<<grid, 128, 0, c->stream>>>(g);
+    LAUNCHED(c, 1);
+}
+
+extern "C" int gsum_eig_solve(gsum_ctx *c, const double *w, const double *V, int64_t n, const double *Y, int64_t nrhs,
+                              const double *mean, double *X, int32_t mode, int32_t mem_kind) {
+    if (!c || !w || !V || !Y || !X || n <= 0 || nrhs <= 0 || (mode != 0 && mode != 1)) return gsum_fail(c, -1, "gsum_eig_solve: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int fk = factor_kind(mem_kind);
+    const void *dw, *dV, *dY, *dmean;
+    void *dT, *dX;
+    GSUM_TRY(dev_in(c, WS_LOGDET, w, sizeof(double) * n, fk, &dw));
+    GSUM_TRY(dev_in(c, WS_IO0, V, sizeof(double) * n * n, fk, &dV));
+    GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * nrhs, mem_kind, &dY));
+    GSUM_TRY(dev_in(c, WS_REF, mean, sizeof(double) * n, mem_kind, &dmean));
+    GSUM_TRY(dev_out(c, WS_IO2, X, sizeof(double) * n * nrhs, mem_kind, &dX));
+    EigGemmArgs g1{};
+    g1.A = (const double *)dV; g1.lda = n; g1.transA = 1;                  // T = diag(f(w)) V^T (Y - mean)
+    g1.B = (const double *)dY; g1.ldb = nrhs; g1.bsub = (const double *)dmean;
+    g1.M = n; g1.N = nrhs; g1.K = n;
+    g1.rs = (const double *)dw; g1.row_mode = mode == 0 ? 1 : 2;
+    if (mode == 1) {
+        g1.C = (double *)dX; g1.ldc = nrhs;
+        launch_eig_gemm(c, g1);
+    } else {
+        GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * n * nrhs, &dT));
+        g1.C = (double *)dT; g1.ldc = nrhs;
+        launch_eig_gemm(c, g1);
+        EigGemmArgs g2{};
+        g2.A = (const double *)dV; g2.lda = n; g2.transA = 0;              // X = V T
+        g2.B = (const double *)dT; g2.ldb = nrhs; g2.bsub = nullptr;
+        g2.C = (double *)dX; g2.ldc = nrhs;
+        g2.M = n; g2.N = nrhs; g2.K = n;
+        g2.rs = nullptr; g2.row_mode = 0;
+        launch_eig_gemm(c, g2);
+    }
+    GSUM_TRY(dev_out_finish(c, X, dX, sizeof(double) * n * nrhs, mem_kind));
+    return finish(c, mem_kind);
+}
+
+extern "C" int gsum_eig_conditional(gsum_ctx *c, const double *w, const double *V, int64_t n, const double *R_on, int64_t m,
+                                    const double *D, int64_t k, double *lin_out, double *var_out, double *cov_out, int32_t mem_kind) {
+    if (!c || !w || !V || !R_on || n <= 0 || m <= 0 || (lin_out && (!D || k <= 0)) || (!lin_out && !var_out && !cov_out))
+        return gsum_fail(c, -1, "gsum_eig_conditional: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int fk = factor_kind(mem_kind);
+    const void *dw, *dV, *dR, *dD = nullptr;
+    void *dU;
+    GSUM_TRY(dev_in(c, WS_LOGDET, w, sizeof(double) * n, fk, &dw));
+    GSUM_TRY(dev_in(c, WS_IO0, V, sizeof(double) * n * n, fk, &dV));
+    GSUM_TRY(dev_in(c, WS_IO1, R_on, sizeof(double) * n * m, mem_kind, &dR));
+    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * n * m, &dU));
+    EigGemmArgs g{};
+    g.A = (const double *)dV; g.lda = n; g.transA = 1;                     // U = V^T R_on
+    g.B = (const double *)dR; g.ldb = m; g.C = (double *)dU; g.ldc = m;
+    g.M = n; g.N = m; g.K = n;
+    launch_eig_gemm(c, g);
+    if (lin_out) {
+        void *dUD, *dlin;
+        GSUM_TRY(dev_in(c, WS_IO3, D, sizeof(double) * n * k, mem_kind, &dD));
+        GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * n * k, &dUD));
+        GSUM_TRY(dev_out(c, WS_LL, lin_out, sizeof(double) * m * k, mem_kind, &dlin));
+        EigGemmArgs h = g;                                                 // UD = V^T D
+        h.B = (const double *)dD; h.ldb = k; h.C = (double *)dUD; h.ldc = k; h.N = k;
+        launch_eig_gemm(c, h);
+        EigGemmArgs l{};                                                   // lin = U^T diag(1/w) UD
+        l.A = (const double *)dU; l.lda = m; l.transA = 1;
+        l.B = (const double *)dUD; l.ldb = k; l.bdiv = (const double *)dw;
+        l.C = (double *)dlin; l.ldc = k; l.M = m; l.N = k; l.K = n;
+        launch_eig_gemm(c, l);
+        GSUM_TRY(dev_out_finish(c, lin_out, dlin, sizeof(double) * m * k, mem_kind));
+    }
+    if (var_out) {
+        void *dvar;
+        GSUM_TRY(dev_out(c, WS_MISC0, var_out, sizeof(double) * m, mem_kind, &dvar));
+        eig_colquad_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>((const double *)dU, n, m, (const double *)dw, (double *)dvar);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, var_out, dvar, sizeof(double) * m, mem_kind));
+    }
+    if (cov_out) {
+        void *dcov;
+        GSUM_TRY(dev_out(c, WS_IO2, cov_out, sizeof(double) * m * m, mem_kind, &dcov));
+        EigGemmArgs q{};                                                   // cov = U^T diag(1/w) U
+        q.A = (const double *)dU; q.lda = m; q.transA = 1;
+        q.B = (const double *)dU; q.ldb = m; q.bdiv = (const double *)dw;
+        q.C = (double *)dcov; q.ldc = m; q.M = m; q.N = m; q.K = n;
+        launch_eig_gemm(c, q);
+        GSUM_TRY(dev_out_finish(c, cov_out, dcov, sizeof(double) * m * m, mem_kind));
+    }
+    return finish(c, mem_kind);
+}

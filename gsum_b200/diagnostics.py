@@ -4,7 +4,8 @@ Construction factors the covariance twice on the device (Cholesky and LAPACK-dps
 Cholesky); every method is then a forward solve, a batched `m + L z` draw or a coverage count on the GPU.
 `df=` selects the Student-t variant (gsum/diagnostics.py:51-55): multivariate-t draws are the Gaussian draws
 scaled per draw by sqrt(df / chi2_df) and the interval end points come from `scipy.stats.t`.
-Out of scope here: `eigen_errors` (needs an eigensolver), `variogram`, plotting.
+`eigen_errors` runs on a device Jacobi eigendecomposition of `cov`, computed at its first call.
+Out of scope here: `variogram`, plotting.
 """
 from __future__ import annotations
 
@@ -45,6 +46,7 @@ class Diagnostic:
             self.std_udist = stats.t(loc=0., scale=1., df=self.df)
         # one upload of cov; Cholesky (diagnostics.py:60) and pivoted Cholesky (diagnostics.py:61 -> helpers.py:185-199)
         # on the device copy; the factors stay in HBM for every later call
+        self._eigen = None          # eigendecomposition for eigen_errors, computed on first use
         self._factors = f = ops.ResidentFactors(self.cov)
         if f.chol_info:
             raise np.linalg.LinAlgError("Matrix is not positive definite")        # numpy.linalg.cholesky
@@ -125,7 +127,22 @@ class Diagnostic:
         return E[:, 0] if single else E
 
     def eigen_errors(self, y):
-        raise NotImplementedError("gsum_b200: eigen_errors needs an eigensolver (SURVEY.md §8f item 2)")
+        """solve(Q diag(sqrt(eig)), y - mean) with the eigenvalues ordered from largest to smallest
+        (gsum/diagnostics.py:63-68, 106-107) = diag(eig^-1/2) Q^T (y - mean): the eigendecomposition of `cov` is
+        computed on the device at the first call (Jacobi) and kept in HBM.  Each row carries the arbitrary sign of its
+        eigenvector (numpy's `eigh` fixes none either)."""
+        if self._eigen is None:
+            self._eigen = ops.ResidentEigen(self.cov)
+        Y, single = self._as_columns(y)
+        E = self._eigen.solve(Y, mean=self.mean, mode=1)[::-1]
+        return np.ascontiguousarray(E[:, 0] if single else E)
+
+    @property
+    def _eig(self):
+        """Q diag(sqrt(eig)), largest eigenvalue first (gsum/diagnostics.py:63-68)."""
+        if self._eigen is None:
+            self._eigen = ops.ResidentEigen(self.cov)
+        return (self._eigen.V * np.sqrt(self._eigen.w)[None, :])[:, ::-1]
 
     def chi2(self, y):
         return np.sum(self.individual_errors(y), axis=0)

@@ -38,6 +38,50 @@ def _scalar_prior(value, name):
     return float(a.reshape(-1)[0])
 
 
+def _conjugate_from_gram(G, logdet, N, nc, pri, student):
+    """Conjugate posterior and log-likelihood from the Gram G = RHS^T R^-1 RHS of RHS = [basis | y_1..y_nc] and log|R|.
+
+    compute_center gsum/models.py:201-221, compute_disp 260-271, compute_df 296, compute_scale_sq 419-448,
+    compute_cov_factor 501-503; Gaussian likelihood 1010-1040, Student-t evidence 1241-1258.  Every vector the
+    reference solves against R is RHS a for a short coefficient vector a, so each term is a quadratic form in G."""
+    eta0, V0, df0, scale0 = pri["center0"], pri["disp0"], pri["df0"], pri["scale0"]
+    r = nc + 1
+    eB = np.zeros(r); eB[0] = 1.0
+    eavg = np.zeros(r); eavg[1:] = 1.0 / nc
+    E = np.eye(r)[1:]
+    if V0 == 0:
+        V, eta = 0.0, eta0
+    else:
+        V = 1.0 / (1.0 / V0 + nc * G[0, 0])
+        eta = V * (eta0 / V0 + nc * (eB @ G @ eavg))
+    df = df0 + N * nc
+    if np.isinf(df0):
+        scale2 = scale0 ** 2
+    else:
+        Ec = E - eavg[None, :]
+        quad = sum(e @ G @ e for e in Ec)
+        ac = eavg - eta0 * eB
+        aw = nc * (ac - nc * V * (eB @ G @ ac) * eB)
+        scale2 = (df0 * scale0 ** 2 + quad + ac @ G @ aw) / df
+    var = scale2 if np.isinf(df) else df * scale2 / (df - 2)
+    if student:
+        from scipy.special import loggamma
+
+        def log_norm(df_, scale2_, disp_):
+            norm = loggamma(df_ / 2.0) - df_ / 2.0 * np.log(df_ * scale2_ / 2.0)
+            if disp_ > 0:
+                norm += 0.5 * np.log(2 * np.pi * disp_)
+            return norm
+
+        with np.errstate(invalid='ignore'):
+            ll = log_norm(df, scale2, V) - log_norm(df0, scale0 ** 2, V0) - nc / 2.0 * (N * np.log(2 * np.pi) + logdet)
+    else:
+        Bk = E - eta * eB[None, :]
+        yKy = sum(b @ G @ b for b in Bk) / var
+        ll = -0.5 * yKy - 0.5 * nc * (N * np.log(var) + logdet) - 0.5 * nc * N * np.log(2 * np.pi)
+    return dict(center=float(eta), disp=float(V), df=df, scale_sq=float(scale2), cov_factor=float(var), lml=float(ll))
+
+
 class BaseConjugateProcess:
     """Stochastic process with a normal-inverse-chi^2 conjugate prior (gsum/models.py:29-900).
 
@@ -64,6 +108,7 @@ class BaseConjugateProcess:
         self.kernel_ = None
         self._rng = None
         self._handle = None
+        self._eig = None                # ops.ResidentEigen of corr_ + nugget I (decomposition='eig')
         self._corr_L = self._corr = None
         self.nugget = nugget
         self.copy_X_train = copy_X_train
@@ -103,8 +148,12 @@ class BaseConjugateProcess:
         if self.decomposition == 'cholesky':
             return
         if self.decomposition == 'eig':
-            raise NotImplementedError("gsum_b200: decomposition='eig' is not available on the device path")
+            return
         raise ValueError('decomposition must be "cholesky" or "eig"')
+
+    def _eig_route(self):
+        self._check_decomposition()
+        return self.decomposition == "eig"
 
     def _active_kernel(self):
         if self.kernel_ is not None:
@@ -114,7 +163,12 @@ class BaseConjugateProcess:
     # ---- fitted quantities ----
     @property
     def corr_L_(self):
-        """Lower Cholesky factor of corr_ + nugget*I (fetched from the device on first access)."""
+        """Lower Cholesky factor of corr_ + nugget*I (fetched from the device on first access); on the 'eig' route the
+        symmetric-eigenvector square root Q diag(sqrt(eig)) (gsum/models.py:717)."""
+        if self._eig is not None:
+            if self._corr_L is None:
+                self._corr_L = self._eig.V * np.sqrt(self._eig.w)[None, :]
+            return self._corr_L
         if self._handle is None:
             return None
         if self._corr_L is None:
@@ -124,8 +178,13 @@ class BaseConjugateProcess:
     corr_sqrt_ = corr_L_
 
     @property
+    def _eigh_tuple_(self):
+        """(eig, Q) of corr_ + nugget*I on the 'eig' route (gsum/models.py:714-716), else None."""
+        return None if self._eig is None else (self._eig.w, self._eig.V)
+
+    @property
     def corr_(self):
-        if self._handle is None:
+        if self._handle is None and self._eig is None:
             return None
         if self._corr is None:
             k = flatten_kernel(self.kernel_)
@@ -199,6 +258,9 @@ class BaseConjugateProcess:
         self._corr_L = self._corr = None
         self._fit = False
         self._calibrate_kernel()
+        if self._eig_route():
+            return self._fit_eig()
+        self._eig = None
         h = self._refit()
         self.center_ = np.array([h.center])
         self.disp_ = np.array([[h.disp]])
@@ -208,6 +270,90 @@ class BaseConjugateProcess:
         self.log_marginal_likelihood_value_ = h.lml if self._lml_from_optimizer is None else self._lml_from_optimizer
         self._fit = True
         return self
+
+    # ---- decomposition='eig' (gsum/models.py:713-717, 480-484, 973-974, 1016-1019, 1215-1216, 1251-1253) ----
+    def _eig_gram(self, X, y, kernel):
+        """(ResidentEigen of R = kernel(X) + nugget I, Gram G = RHS^T R^-1 RHS of RHS = [basis | y], logdet R).
+
+        R is built (K1), diagonalised (Jacobi) and applied (two DMMA GEMMs) on the device; the (n_c+1)^2 Gram of the
+        returned R^-1 RHS against RHS is the only product formed on the host."""
+        k = flatten_kernel(kernel)
+        R = ops.kernel_matrix(X, None, k.ls_for(X.shape[1]), k.constant, k.noise)
+        R[np.diag_indices_from(R)] += self.nugget
+        eig = ops.ResidentEigen(R)
+        rhs = np.concatenate([np.ones((X.shape[0], 1)), y], axis=1)
+        G = rhs.T @ eig.solve(rhs)
+        with np.errstate(invalid='ignore', divide='ignore'):
+            logdet = float(np.sum(np.log(eig.w)))                                 # models.py:1019, 1253
+        return eig, 0.5 * (G + G.T), logdet
+
+    def _fit_eig(self):
+        X, y = np.atleast_2d(self.X_train_), self.y_train_
+        y2 = y[:, None] if y.ndim == 1 else y
+        if self._handle is not None:
+            self._handle.close()
+            self._handle = None
+        self._eig, G, logdet = self._eig_gram(X, y2, self.kernel_)
+        post = _conjugate_from_gram(G, logdet, X.shape[0], y2.shape[1], self._priors(), self._student)
+        self.center_ = np.array([post["center"]])
+        self.disp_ = np.array([[post["disp"]]])
+        self.df_ = post["df"]
+        self.scale_ = np.sqrt(post["scale_sq"])
+        self.cov_factor_ = self.cbar_sq_mean_ = post["cov_factor"]
+        self.log_marginal_likelihood_value_ = post["lml"] if self._lml_from_optimizer is None else self._lml_from_optimizer
+        self._fit = True
+        return self
+
+    def _lml_eig(self, theta, X, y):
+        kernel = self._active_kernel().clone_with_theta(theta)
+        X = self.X_train_ if X is None else X
+        y = self.y_train_ if y is None else y
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None]
+        _, G, logdet = self._eig_gram(X, y, kernel)
+        return float(_conjugate_from_gram(G, logdet, X.shape[0], y.shape[1], self._priors(), self._student)["lml"])
+
+    def _predict_parts_eig(self, X, want, Xc, y, pred_noise, want_cond_basis):
+        """`_predict_parts` on the 'eig' route: R_no R^-1 [y - m | B], and R_no R^-1 R_on (or its diagonal), from one
+        device call on the resident eigendecomposition (gsum/models.py:797-845, 1150-1174)."""
+        k = flatten_kernel(self.kernel_)
+        d = X.shape[1]
+        ls = k.ls_for(d)
+        center = float(self.center_[0])
+        if Xc is None:
+            Xc, eig = np.atleast_2d(self.X_train_), self._eig
+            if y is None:
+                y = self.y_train_
+        else:
+            Xc = np.atleast_2d(np.asarray(Xc, dtype=np.float64))
+            R = ops.kernel_matrix(Xc, None, ls, k.constant, k.noise)
+            R[np.diag_indices_from(R)] += self.nugget
+            eig = ops.ResidentEigen(R)                                            # models.py:811
+            if y is None:
+                y = self.y_train_
+        y = np.asarray(y, dtype=np.float64)
+        if y.ndim == 1:
+            y = y[:, None]
+        ny = y.shape[1]
+        D = y - center
+        if want_cond_basis:
+            D = np.concatenate([D, np.ones((Xc.shape[0], 1))], axis=1)
+        R_on = ops.kernel_matrix(Xc, X, ls, k.constant, 0.0)
+        lin, qd, qc = eig.conditional(R_on, D, want_var=want == PREDICT_VAR, want_cov=want == PREDICT_COV)
+        mean = center + lin[:, :ny]
+        cond_basis = (1.0 - lin[:, ny]) if want_cond_basis else None
+        extra = self.nugget if pred_noise else 0.0
+        var = None
+        if want == PREDICT_VAR:
+            var = self.cov_factor_ * ((k.constant + k.noise + extra) - qd)
+        elif want == PREDICT_COV:
+            qc *= -1.0
+            qc += ops.kernel_matrix(X, None, ls, k.constant, k.noise + extra)
+            qc *= self.cov_factor_
+            var = qc
+        return mean, var, cond_basis
 
     def _calibrate_kernel(self):
         """gsum/models.py:630-669: L-BFGS on -log_marginal_likelihood with the analytic gradient (device contractions,
@@ -336,9 +482,13 @@ class BaseConjugateProcess:
         return float(ll), grad
 
     def _lml(self, theta, eval_gradient, X, y):
+        if self._eig_route():
+            if eval_gradient:
+                raise NotImplementedError("gsum_b200: the analytic likelihood gradient is built on the Cholesky factor; "
+                                          "with decomposition='eig' use optimizer=None or fixed hyperparameter bounds")
+            return self._lml_eig(theta, X, y)
         if eval_gradient:
             return self._lml_gradient(theta, X, y)
-        self._check_decomposition()
         kernel = self._active_kernel().clone_with_theta(theta)
         X = self.X_train_ if X is None else X
         y = self.y_train_ if y is None else y
@@ -362,6 +512,8 @@ class BaseConjugateProcess:
         Xc=None conditions at the training inputs with the factor kept on the device by `fit` (gsum/models.py:797-803);
         an explicit Xc is factored afresh with the nugget (models.py:806-809).  y=None means the y of `fit`."""
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        if self._eig_route():
+            return self._predict_parts_eig(X, want, Xc, y, pred_noise, want_cond_basis)
         m = X.shape[0]
         center = float(self.center_[0])
         if Xc is not None and y is None:
@@ -573,6 +725,8 @@ class TruncationProcess:
         b_old = b_new = None
         if want_cond_basis:
             b_old, b_new = self.basis(Xc, start=start, end=end)[:, 0], self.basis(X, start=start, end=end)[:, 0]
+        if cp._handle is None:
+            cp._refit()            # 'eig' route: this predict is decomposition-independent in the reference (LU, models.py:1449)
         mean, var, cb = cp._handle.predict(
             X, want=want, Xc=Xc, yc=np.asarray(yc, dtype=np.float64), mean_old=self.mean(Xc, start=start, end=end),
             mean_new=self.mean(X, start=start, end=end), basis_old=b_old, basis_new=b_new, sc_old=s_old, sc_new=s_new,
@@ -660,13 +814,16 @@ class TruncationProcess:
         Like the reference (models.py:1498-1507), only the scalar is returned even when eval_gradient=True is
         requested: the reference computes the coefficient process' gradient and drops it."""
         cp = self.coeffs_process
-        cp._check_decomposition()
         X, dy, orders_in = self._grid_inputs(X, y, orders)
         kernel = cp._active_kernel().clone_with_theta(theta)
         k = flatten_kernel(kernel)
         ref = np.asarray(self.ref(X), dtype=np.float64)
         ratio = np.asarray(self.ratio(X, **ratio_kws), dtype=np.float64)
         det_factor = np.sum(len(orders_in) * np.log(np.abs(ref)) + np.sum(orders_in) * np.log(np.abs(ratio)))
+        if cp._eig_route():
+            # coefficients (gsum/helpers.py:71-101) on the host, then the coefficient process' 'eig' likelihood
+            coeffs = dy / (ref[:, None] * ratio[:, None] ** orders_in[None, :])
+            return cp._lml_eig(theta, X, coeffs) - float(det_factor)
         ll = ops.lml_grid(X, dy, ref, orders_in, k.ls_for(X.shape[1])[None, :], ratio[None, :], q_x_dependent=True,
                           detf=np.array([det_factor]), constant=k.constant, noise=k.noise, nugget=cp.nugget,
                           student=cp._student, **cp._priors())
@@ -685,7 +842,9 @@ class TruncationProcess:
         Returns ll with shape (n_q, n_ls), i.e. ``ll[i_ratio][i_ls]`` as in the notebook.
         """
         cp = self.coeffs_process
-        cp._check_decomposition()
+        if cp._eig_route():
+            raise NotImplementedError("gsum_b200: the (Q, l) grid kernel factors by Cholesky; with decomposition='eig' "
+                                      "evaluate log_marginal_likelihood cell by cell")
         X, dy, orders_in = self._grid_inputs(X, y, orders)
         n = X.shape[0]
         k = flatten_kernel(cp._active_kernel())

@@ -18,6 +18,7 @@ MEM_FACTOR_DEVICE = 2        # GSUM_MEM_FACTOR_DEVICE: the factor argument is a 
 __all__ = [
     "kernel_matrix", "cholesky", "cho_solve", "lml_grid", "grid_normalize", "FitHandle", "process_cov",
     "cholesky_errors", "pivoted_cholesky", "pc_errors", "draws", "credible_interval", "ResidentFactors",
+    "eigh", "eig_solve", "eig_conditional", "ResidentEigen",
 ]
 
 
@@ -404,6 +405,119 @@ def credible_interval(Y, lower, upper, ctx=None):
     ctx.check(ctx.lib.gsum_credible_interval(ctx.handle, _p(Y), n, k, _p(lower), _p(upper), lower.shape[0], _p(out), MEM_HOST),
               "gsum_credible_interval")
     return out
+
+
+def _eigh_message(ctx):
+    msg = ctx.lib.gsum_last_error(ctx.handle)
+    return msg.decode() if msg else "Eigenvalues did not converge"
+
+
+class ResidentEigen:
+    """Eigendecomposition A = V diag(w) V^T computed on the device and kept in HBM (the `_eigh_tuple_` of
+    gsum/models.py:714-716 and the `_eig` factor of gsum/diagnostics.py:63-68): A goes up once, every later
+    `eig_solve` passes the resident (w, V) (GSUM_MEM_FACTOR_DEVICE).  `w` is a numpy array; `V` is copied back on
+    first access only."""
+
+    def __init__(self, A, ctx=None):
+        self.ctx = ctx = ctx or default_context()
+        A = as_f64(A)
+        n = self.n = A.shape[0]
+        if A.shape != (n, n):
+            raise ValueError("A must be square")
+        self.w_dev = DeviceBuffer(ctx, (n,))
+        self.V_dev = DeviceBuffer(ctx, (n, n))
+        M = DeviceBuffer(ctx, (n, n)).put(A)
+        sweeps = C.c_int32(0)
+        try:
+            self.status = ctx.check(ctx.lib.gsum_eigh(ctx.handle, M.ptr, n, self.w_dev.ptr, self.V_dev.ptr, C.addressof(sweeps),
+                                                      MEM_DEVICE), "gsum_eigh")
+        finally:
+            M.free()
+        ctx.synchronize()
+        if self.status:
+            raise np.linalg.LinAlgError(_eigh_message(ctx))                       # numpy / scipy eigh: LinAlgError
+        self.sweeps = int(sweeps.value)
+        self.w = self.w_dev.get()
+        self._V = None
+
+    @property
+    def V(self):
+        if self._V is None:
+            self._V = self.V_dev.get()
+        return self._V
+
+    def solve(self, Y, mean=None, mode=0):
+        return eig_solve((self.w_dev, self.V_dev), Y, mean=mean, mode=mode, ctx=self.ctx)
+
+    def conditional(self, R_on, D=None, want_var=False, want_cov=False):
+        return eig_conditional((self.w_dev, self.V_dev), R_on, D, want_var=want_var, want_cov=want_cov, ctx=self.ctx)
+
+
+def eigh(A, return_sweeps=False, ctx=None):
+    """(w, V) with A = V diag(w) V^T, w ascending, eigenvectors in the columns of V — ``scipy.linalg.eigh(A)`` up to the
+    sign of each eigenvector (largest-magnitude component positive here)."""
+    ctx = ctx or default_context()
+    A = as_f64(A)
+    n = A.shape[0]
+    if A.shape != (n, n):
+        raise ValueError("A must be square")
+    w, V = np.empty(n), np.empty((n, n))
+    sweeps = C.c_int32(0)
+    rc = ctx.check(ctx.lib.gsum_eigh(ctx.handle, _p(A), n, _p(w), _p(V), C.addressof(sweeps), MEM_HOST), "gsum_eigh")
+    if rc:
+        raise np.linalg.LinAlgError(_eigh_message(ctx))
+    return (w, V, int(sweeps.value)) if return_sweeps else (w, V)
+
+
+def eig_solve(eig, Y, mean=None, mode=0, ctx=None):
+    """mode 0: V diag(1/w) V^T (Y - mean) (``solve_sqrt(..., decomposition='eig')``, gsum/models.py:480-484);
+    mode 1: diag(|w|^-1/2) V^T (Y - mean) (``eigen_errors``, rows in the order of w).  `eig` = (w, V) as numpy arrays
+    or as DeviceBuffers resident in HBM."""
+    ctx = ctx or default_context()
+    w, V = eig
+    if isinstance(V, DeviceBuffer) != isinstance(w, DeviceBuffer):
+        raise ValueError("w and V must both be numpy arrays or both DeviceBuffers")
+    if isinstance(V, DeviceBuffer):
+        wp, Vp, n, kind = w.ptr, V.ptr, V.shape[0], MEM_HOST | MEM_FACTOR_DEVICE
+    else:
+        w, V = as_f64(w), as_f64(V)
+        wp, Vp, n, kind = _p(w), _p(V), V.shape[0], MEM_HOST
+    Y = np.asarray(Y, dtype=np.float64)
+    vec = Y.ndim == 1
+    Yc = as_f64(Y[:, None] if vec else Y)
+    if Yc.shape[0] != n:
+        raise ValueError(f"Y must have {n} rows")
+    mean = _vec(mean, n, "mean")
+    X = np.empty_like(Yc)
+    ctx.check(ctx.lib.gsum_eig_solve(ctx.handle, wp, Vp, n, _p(Yc), Yc.shape[1], _p(mean), _p(X), int(mode), kind), "gsum_eig_solve")
+    return X[:, 0] if vec else X
+
+
+def eig_conditional(eig, R_on, D=None, want_var=False, want_cov=False, ctx=None):
+    """(R_no R^-1 D (m, k) | None, diag(R_no R^-1 R_on) (m,) | None, R_no R^-1 R_on (m, m) | None) with
+    R^-1 = V diag(1/w) V^T — the products `predict` needs on the 'eig' route (gsum/models.py:826-836)."""
+    ctx = ctx or default_context()
+    w, V = eig
+    if isinstance(V, DeviceBuffer):
+        wp, Vp, n, kind = w.ptr, V.ptr, V.shape[0], MEM_HOST | MEM_FACTOR_DEVICE
+    else:
+        w, V = as_f64(w), as_f64(V)
+        wp, Vp, n, kind = _p(w), _p(V), V.shape[0], MEM_HOST
+    R_on = as_f64(R_on)
+    m = R_on.shape[1]
+    lin = var = cov = None
+    k = 0
+    if D is not None:
+        D = as_f64(D)
+        k = D.shape[1]
+        lin = np.empty((m, k))
+    if want_var:
+        var = np.empty(m)
+    if want_cov:
+        cov = np.empty((m, m))
+    ctx.check(ctx.lib.gsum_eig_conditional(ctx.handle, wp, Vp, n, _p(R_on), m, _p(D), k, _p(lin), _p(var), _p(cov), kind),
+              "gsum_eig_conditional")
+    return lin, var, cov
 
 
 def lml_grid_device(ctx, X, dy, ref, orders, ls, Q, detf, ll_out, q_x_dependent=False, constant=1.0, noise=0.0,

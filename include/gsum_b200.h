@@ -213,6 +213,34 @@ int gsum_draws(gsum_ctx *ctx, const double *L, int64_t n, const double *mean, co
 int gsum_credible_interval(gsum_ctx *ctx, const double *Y, int64_t n, int64_t n_curves, const double *lower,
                            const double *upper, int32_t n_alpha, double *coverage_out, int32_t mem_kind);
 
+/* decomposition='eig' route.
+ * gsum_eigh: symmetric eigendecomposition A = V diag(w) V^T — scipy `eigh(R)` at gsum/models.py:714, 811, 974, 1166,
+ *   1216 and numpy `eigh(cov)` at gsum/diagnostics.py:63.  A (n,n) symmetric (only read); w (n,) ascending;
+ *   V (n,n) row-major with the eigenvectors in its COLUMNS, each returned with its largest-magnitude component
+ *   positive (LAPACK fixes no sign; compare up to sign).  One-sided Jacobi on the device; sweeps_out (host int32, or
+ *   NULL) receives the number of sweeps.  Returns 1 when the iteration did not converge within its sweep limit and 2
+ *   for an indefinite A holding a pair of eigenvalues +lambda, -lambda (the one-sided iteration cannot separate those;
+ *   the covariance / correlation matrices of the cited call sites are positive semi-definite up to rounding). */
+int gsum_eigh(gsum_ctx *ctx, const double *A, int64_t n, double *w, double *V, int32_t *sweeps_out, int32_t mem_kind);
+
+/* gsum_eig_solve: with (w, V) from gsum_eigh and Y (n, nrhs), mean (n,) or NULL (subtracted from every column of Y):
+ *   mode 0: X = V diag(1/w) V^T (Y - mean)            `solve_sqrt(..., decomposition='eig')`, gsum/models.py:480-484
+ *   mode 1: X = diag(|w|^-1/2) V^T (Y - mean)         `eigen_errors`, gsum/diagnostics.py:63-68, 106-107 (row k of X
+ *           belongs to w[k]: the caller reverses the rows for the reference's largest-first order)
+ *   X (n, nrhs).  With GSUM_MEM_FACTOR_DEVICE, w and V are device pointers and Y / mean / X host pointers. */
+int gsum_eig_solve(gsum_ctx *ctx, const double *w, const double *V, int64_t n, const double *Y, int64_t nrhs,
+                   const double *mean, double *X, int32_t mode, int32_t mem_kind);
+
+/* gsum_eig_conditional: the conditioning products of `predict` on the 'eig' route (gsum/models.py:826-836, 1174):
+ *   with R^-1 = V diag(1/w) V^T, R_on (n, m) the cross-correlation and D (n, k) the columns to condition on
+ *   (y - mean_old and, for the Student-t process, the old basis):
+ *     lin_out (m, k)  = R_no R^-1 D                        (or NULL)
+ *     var_out (m,)    = diag(R_no R^-1 R_on)               (or NULL)
+ *     cov_out (m, m)  = R_no R^-1 R_on                     (or NULL)
+ *   computed as U = V^T R_on once, then U^T diag(1/w) [V^T D | U].  GSUM_MEM_FACTOR_DEVICE as for gsum_eig_solve. */
+int gsum_eig_conditional(gsum_ctx *ctx, const double *w, const double *V, int64_t n, const double *R_on, int64_t m,
+                         const double *D, int64_t k, double *lin_out, double *var_out, double *cov_out, int32_t mem_kind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import numpy as np
 from numpy.linalg import cholesky, solve
-from scipy.linalg import cho_solve, inv, solve_triangular
+from scipy.linalg import cho_solve, eigh, inv, solve_triangular
 from scipy.special import loggamma
 import scipy.stats as st
 
@@ -33,7 +33,7 @@ __all__ = [
     "fit_conjugate", "predict_conjugate", "predict_student", "truncation_cov", "truncation_mean",
     "truncation_basis", "predict_truncation",
     "pivoted_cholesky", "dpstrf_restated", "cholesky_errors", "mahalanobis", "md_squared",
-    "pivoted_cholesky_errors", "credible_interval", "draws_from_z", "individual_errors",
+    "pivoted_cholesky_errors", "credible_interval", "draws_from_z", "individual_errors", "eigen_factor", "eigen_errors",
 ]
 
 
@@ -109,8 +109,22 @@ def _ones_basis(X):
 
 
 def solve_sqrt(L, y):
-    """gsum/models.py:459-479 (decomposition='cholesky') — R^{-1} y from the lower factor."""
+    """gsum/models.py:459-487 — R^{-1} y from the lower factor (decomposition='cholesky', :479), or from the
+    tuple (eig, Q) of `eigh(R)` as Q diag(1/eig) Qᵀ y (decomposition='eig', :480-484)."""
+    if isinstance(L, tuple):
+        eig, Q = L
+        inv_mat = Q @ np.diag(1. / eig) @ Q.T                   # :483
+        return inv_mat @ y
     return cho_solve((L, True), y)
+
+
+def _sqrt_R(R, decomposition):
+    """gsum/models.py:966-976 / 710-719: `cholesky(R)` or the tuple `eigh(R)`."""
+    if decomposition == "cholesky":
+        return cholesky(R)
+    if decomposition == "eig":
+        return eigh(R)
+    raise ValueError('decomposition must be "cholesky" or "eig"')
 
 
 def _num_y(y):
@@ -171,8 +185,8 @@ def compute_cov_factor(scale_sq, df):
 # Marginal likelihoods  (gsum/models.py:912-1057, 1184-1273, 1485-1507)
 # ----------------------------------------------------------------------------------------------
 
-def gaussian_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis):
-    """gsum/models.py:912-1057 (eval_gradient=False, decomposition='cholesky').
+def gaussian_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis, decomposition="cholesky"):
+    """gsum/models.py:912-1057 (eval_gradient=False; decomposition 'cholesky' or 'eig').
 
     Gaussian log-likelihood of the curves at the plug-in posterior-mean variance.  `kernel` is an
     sklearn kernel object; `theta` its log-hyperparameters (models.py:953).
@@ -180,7 +194,7 @@ def gaussian_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis
     R = kernel.clone_with_theta(theta)(X)                       # :953-960
     R[np.diag_indices_from(R)] += nugget                        # :963
     try:
-        L_R = cholesky(R)                                       # :969
+        L_R = _sqrt_R(R, decomposition)                         # :969 / :974
     except np.linalg.LinAlgError:
         return -np.inf                                          # :970-972
     if y.ndim == 1:
@@ -192,8 +206,13 @@ def gaussian_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis
     scale2 = compute_scale_sq(y, L_R, basis, p.center0, p.disp0, p.df0, p.scale0)  # :1002
     mean = basis @ center
     var = compute_cov_factor(scale2, df)                        # :1008
-    L = np.sqrt(var) * L_R                                      # :1014
-    logdet_K = 2 * np.log(np.diag(L)).sum()                     # :1015
+    if decomposition == "cholesky":
+        L = np.sqrt(var) * L_R                                  # :1014
+        logdet_K = 2 * np.log(np.diag(L)).sum()                 # :1015
+    else:
+        eig, Q = L_R                                            # :1017
+        L = var * eig, Q                                        # :1018
+        logdet_K = np.log(var * eig).sum()                      # :1019
     _K = var * R                                                # :1023 (unused temp, kept for timing fidelity)
     y_train = y - mean[:, None]
     N = R.shape[0]
@@ -264,14 +283,14 @@ def gaussian_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_o
     return ll.sum(-1), grad_dims.sum(-1)                        # :1056
 
 
-def student_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis):
+def student_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis, decomposition="cholesky"):
     """gsum/models.py:1184-1273 (eval_gradient=False) — exact normal-inverse-χ² evidence."""
     ny = _num_y(y)
     R = kernel.clone_with_theta(theta)(X)
     R[np.diag_indices_from(R)] += nugget
     N = R.shape[0]
     try:
-        L_R = cholesky(R)
+        L_R = _sqrt_R(R, decomposition)                          # :1211 / :1216
     except np.linalg.LinAlgError:
         return -np.inf
     p = priors
@@ -287,7 +306,10 @@ def student_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis)
             norm += 0.5 * log_det
         return norm
 
-    logdet_R = 2 * np.log(np.diag(L_R)).sum()                    # :1250
+    if decomposition == "cholesky":
+        logdet_R = 2 * np.log(np.diag(L_R)).sum()                # :1250
+    else:
+        logdet_R = np.log(L_R[0]).sum()                          # :1252-1253
     return log_norm(df, scale, disp) - log_norm(p.df0, p.scale0, p.disp0) \
         - ny / 2.0 * (N * np.log(2 * np.pi) + logdet_R)          # :1257-1258
 
@@ -345,7 +367,7 @@ def student_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_on
 
 
 def truncation_lml(kernel, theta, X, y, orders, ratio, ref, priors, nugget=1e-10, excluded=None,
-                   student=False):
+                   student=False, decomposition="cholesky"):
     """gsum/models.py:1485-1507 — ll_y = ll_c(coefficients(y; Q, ref)) − Σ_x[n log|ref| + (Σ orders) log|Q|].
 
     `ratio` and `ref` are length-N arrays (the reference's `self.ratio(X, **ratio_kws)` / `self.ref(X)`).
@@ -354,7 +376,7 @@ def truncation_lml(kernel, theta, X, y, orders, ratio, ref, priors, nugget=1e-10
     mask = ~np.isin(orders, excluded)
     coeffs = coefficients(y=y, ratio=ratio, ref=ref, orders=orders)[:, mask]
     lml = student_lml if student else gaussian_lml
-    ll = lml(kernel, theta, X, coeffs, priors, nugget=nugget)
+    ll = lml(kernel, theta, X, coeffs, priors, nugget=nugget, decomposition=decomposition)
     orders_in = orders[mask]
     det_factor = np.sum(len(orders_in) * np.log(np.abs(ref)) + np.sum(orders_in) * np.log(np.abs(ratio)))
     return ll - det_factor
@@ -383,21 +405,22 @@ def lml_grid(kernel, X, y, orders, ls_vals, ratio_vals, ref, priors, nugget=1e-1
 # fit / predict  (gsum/models.py:671-738, 753-845, 1128-1182, 1337-1354, 1389-1483)
 # ----------------------------------------------------------------------------------------------
 
-def fit_conjugate(kernel, X, y, priors, nugget=1e-10, basis_fn=_ones_basis, student=False):
-    """gsum/models.py:671-738 with the kernel hyperparameters held fixed (optimizer=None / 'fixed')."""
+def fit_conjugate(kernel, X, y, priors, nugget=1e-10, basis_fn=_ones_basis, student=False, decomposition="cholesky"):
+    """gsum/models.py:671-738 with the kernel hyperparameters held fixed (optimizer=None / 'fixed').
+    With decomposition='eig', `corr_L` is the tuple (eig, Q) the reference keeps as `_eigh_tuple_` (:714-716)."""
     X, y = X.copy(), y.copy()                                    # :692-701 (copy_X_train=True)
     corr = kernel(X)                                             # :708
-    L = cholesky(corr + nugget * np.eye(len(X)))                 # :711
+    L = _sqrt_R(corr + nugget * np.eye(len(X)), decomposition)   # :711 / :714
     basis = basis_fn(X)
     p = priors
     center = compute_center(y, L, basis, p.center0, p.disp0)     # :721
     disp = compute_disp(y, L, basis, p.disp0)                    # :725
     df = compute_df(y, p.df0)                                    # :729
     scale_sq = compute_scale_sq(y, L, basis, p.center0, p.disp0, p.df0, p.scale0)   # :730
-    lml = (student_lml if student else gaussian_lml)(kernel, kernel.theta, X, y, p, nugget, basis_fn)  # :668-669
+    lml = (student_lml if student else gaussian_lml)(kernel, kernel.theta, X, y, p, nugget, basis_fn, decomposition)  # :668-669
     return dict(kernel=kernel, X=X, y=y, basis=basis, corr=corr, corr_L=L, center=center, disp=disp, df=df,
                 scale=np.sqrt(scale_sq), cov_factor=compute_cov_factor(scale_sq, df), lml=lml,
-                nugget=nugget, basis_fn=basis_fn)
+                nugget=nugget, basis_fn=basis_fn, decomposition=decomposition)
 
 
 def predict_conjugate(f, Xnew, return_std=False, return_cov=False, Xc=None, y=None, pred_noise=False):
@@ -408,7 +431,7 @@ def predict_conjugate(f, Xnew, return_std=False, return_cov=False, Xc=None, y=No
     if Xc is None:
         Xc, L = f["X"], f["corr_L"]
     else:
-        L = cholesky(kern(Xc) + nugget * np.eye(len(Xc)))        # :807-809
+        L = _sqrt_R(kern(Xc) + nugget * np.eye(len(Xc)), f.get("decomposition", "cholesky"))   # :807-811
     if y is None:
         y = f["y"]
     m_old = f["basis_fn"](Xc) @ f["center"]                      # :818
@@ -441,7 +464,7 @@ def predict_student(f, Xnew, return_std=False, return_cov=False, Xc=None, y=None
         basis_old, L, R_no = f["basis"], f["corr_L"], kern(Xnew, f["X"])
     else:
         basis_old, R_no = f["basis_fn"](Xc), kern(Xnew, Xc)
-        L = cholesky(kern(Xc) + nugget * np.eye(len(Xc)))
+        L = _sqrt_R(kern(Xc) + nugget * np.eye(len(Xc)), f.get("decomposition", "cholesky"))   # :1163-1166
     basis = basis_new - R_no @ solve_sqrt(L, basis_old)          # :1171
     mean_cov = f["cov_factor"] * (basis @ f["disp"] @ basis.T)   # :1173
     if return_std:
@@ -653,6 +676,18 @@ def mvt_draws_from_z(mean, cov, df, z, x):
     half for caller-supplied standard normals z (N, n) and x (n,): z_sigma = chol(sigma) z."""
     sigma = cov * (df - 2.0) / df
     return mean[:, None] + (np.linalg.cholesky(sigma) @ z) / np.sqrt(x)[None, :]
+
+
+def eigen_factor(cov):
+    """gsum/diagnostics.py:63-68 — `_eig` = Q diag(sqrt(eig)) with the eigenvalues ordered from largest to smallest."""
+    e, v = np.linalg.eigh(cov)
+    e, v = e[::-1], v[:, ::-1]
+    return v @ np.diag(np.sqrt(e))
+
+
+def eigen_errors(y, mean, eig_factor):
+    """gsum/diagnostics.py:106-107 — solve(_eig, (y.T - mean).T); y (N, n_curves)."""
+    return solve(eig_factor, (y.T - mean).T)
 
 
 def kl_divergence(mean1, cov1, chol1, mean0, cov0):

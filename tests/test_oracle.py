@@ -235,3 +235,45 @@ def test_student_gradient_oracle_is_the_derivative(golden, ip):
         tm[i] -= 1e-4
         fd = (o.student_lml(kern, tp, g["X"], g["y"], p, 1e-10) - o.student_lml(kern, tm, g["X"], g["y"], p, 1e-10)) / 2e-4
         assert gr[i] == pytest.approx(fd, rel=1e-3, abs=1e-3)
+
+
+# ---- decomposition='eig' route: oracle restatement vs the real reference ----
+@pytest.mark.parametrize("ip", range(3))
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_eig_route_oracle(golden, ip, tag):
+    g = golden("eig_route")
+    p = o.Priors(**prior_kwargs(g["priors"][ip]))
+    student = tag == "t"
+    kern = C(1.5, 'fixed') * RBF(0.2, 'fixed') + WhiteKernel(1e-4, 'fixed')
+    f = o.fit_conjugate(kern, g["X"], g["y"], p, nugget=1e-10, student=student, decomposition="eig")
+    post = np.array([f["center"][0], f["disp"][0, 0], f["df"], f["scale"], f["cov_factor"]])
+    want = g[f"{tag}{ip}_post"]
+    ok = np.isfinite(want)
+    assert np.array_equal(np.isnan(post), np.isnan(want)) and relerr(post[ok], want[ok]) < TOL
+    kfree = C(1.5, 'fixed') * RBF(0.2) + WhiteKernel(1e-4, 'fixed')
+    lml_fn = o.student_lml if student else o.gaussian_lml
+    lml = np.array([lml_fn(kfree, [t], g["X"], g["y"], p, 1e-10, decomposition="eig") for t in g["thetas"]])
+    wl = g[f"{tag}{ip}_lml"]
+    assert np.array_equal(np.isnan(lml), np.isnan(wl))
+    if np.isfinite(wl).all():
+        assert relerr(lml, wl) < TOL
+    if f"{tag}{ip}_mean" in g:
+        pf = o.predict_student if student else o.predict_conjugate
+        m, s = pf(f, g["Xn"], return_std=True)
+        assert relerr(m, g[f"{tag}{ip}_mean"]) < TOL and relerr(s, g[f"{tag}{ip}_std"]) < 1e-9
+        _, cv = pf(f, g["Xn"][::4], return_cov=True, pred_noise=True)
+        assert relerr(cv, g[f"{tag}{ip}_cov"]) < 1e-9
+        m, s = pf(f, g["Xn"], return_std=True, Xc=g["Xc"], y=g["yc"])
+        assert relerr(m, g[f"{tag}{ip}_mean_c"]) < TOL and relerr(s, g[f"{tag}{ip}_std_c"]) < 1e-9
+
+
+def test_eig_route_truncation_and_eigen_errors_oracle(golden):
+    g = golden("eig_route")
+    kern = RBF(0.2) + WhiteKernel(1e-6, 'fixed')
+    n = len(g["Xt"])
+    ll = np.array([[o.truncation_lml(kern, [np.log(l)], g["Xt"], g["yt"], g["orders"], q * np.ones(n), np.ones(n),
+                                     o.Priors(0, 0, 1, 1), decomposition="eig") for l in g["ls_vals"]] for q in g["q_vals"]])
+    assert relerr(ll, g["t_ll"]) < TOL
+    cov = 1.3 * np.outer(g["amp"], g["amp"]) * (RBF(0.2)(g["Xd"]) + 1e-5 * np.eye(len(g["Xd"])))
+    E = o.eigen_errors(g["Yd"], g["d_mean"], o.eigen_factor(cov))
+    assert relerr(E, g["eigen_errors"]) < 1e-9
