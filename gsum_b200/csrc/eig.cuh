@@ -18,9 +18,10 @@
 // +lambda, -lambda has a repeated SINGULAR value whose vectors the one-sided iteration cannot separate; gsum_eigh detects
 // that through the Rayleigh quotients and reports it instead of returning wrong vectors.)
 // Measured dead ends (profiles/r01_notes.md, session 5): de Rijk column ordering inside the rotation (more sweeps, not
-// fewer, with the round-robin tournament) and iterating on the Cholesky / pivoted-Cholesky factor of A (same 17-22 sweeps
-// on RBF + noise matrices — the large cluster of eigenvalues at the noise level converges linearly either way — and no
-// convergence at cond 1e8).
+// fewer, with the round-robin tournament); iterating on the Cholesky / pivoted-Cholesky factor of A (same 17-22 sweeps on
+// RBF + noise matrices: the ~n-member cluster of eigenvalues at the noise level converges linearly either way, the
+// rotation count falling by ~0.75 per sweep); a block variant (8 + 8 columns per CTA, 16 x 16 Gram diagonalised in shared
+// memory, 1/8 of the rounds) — as many sweeps, and each round still streams all of G and V^T: 153 vs 99 ms at N = 1024.
 // HBM/L2-bound: each round streams G and V^T once (4 n^2 x 8 B read+write when every pair rotates).
 #pragma once
 #include "common.cuh"

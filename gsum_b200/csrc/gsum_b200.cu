@@ -1447,6 +1447,8 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     if (const char *e = getenv("GSUM_B200_EIGH_ABS")) tol_abs = atof(e) * eps * sqrt(fro2);
     // One sweep = n - 1 dependent launches of a few microseconds each: launch-bound, so the sweep is captured once as a
     // CUDA graph (counter reset + the rounds) and replayed until a sweep makes no rotation.
+    const bool trace = getenv("GSUM_B200_EIGH_TRACE") != nullptr;      // rotations per sweep on stderr
+    const int rounds = np - 1;
     int sweeps = 0;
     bool converged = (n == 1);
     cudaGraph_t graph = nullptr;
@@ -1466,7 +1468,8 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
         if (cudaGraphLaunch(gexec, c->stream) != cudaSuccess ||
             cudaMemcpyAsync(&rot, dcnt, sizeof(rot), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { rc_loop = -100; break; }
-        LAUNCHED(c, np - 1);
+        LAUNCHED(c, rounds);
+        if (trace) fprintf(stderr, "[gsum_eigh] n=%d sweep %d: %u rotations\n", ni, sweeps, rot);
         sweeps++;
         converged = (rot == 0);
     }
