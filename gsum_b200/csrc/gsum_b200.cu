@@ -1412,6 +1412,12 @@ extern "C" int gsum_credible_interval(gsum_ctx *c, const double *Y, int64_t n, i
 #include <algorithm>
 #include <numeric>
 
+static void launch_eig_gemm(gsum_ctx *c, const EigGemmArgs &g) {
+    dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64));
+    eig_gemm_kernel<<<grid, 128, 0, c->stream>>>(g);
+    LAUNCHED(c, 1);
+}
+
 extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, double *V, int32_t *sweeps_out, int32_t mem_kind) {
     if (!c || !A || !w || n <= 0 || n > (1 << 20)) return gsum_fail(c, -1, "gsum_eigh: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
@@ -1426,6 +1432,17 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     const double tol = sqrt((double)n) * eps;
     double tol_abs = 0.0;
 
+    // factor mode (eig.cuh): pivoted Cholesky A = F F^T first; full rank -> iterate on F, no V
+    bool factor_mode = false;
+    double tol_gamma = 0.0;
+    void *dGp;
+    GSUM_TRY(gsum_ws(c, WS_IO3, sizeof(double) * n * n, &dGp));
+    if (getenv("GSUM_B200_EIGH_FACTOR")) {                  // opt-in: faster, looser (see eig.cuh "factor mode")
+        const int rc = gsum_pivoted_cholesky(c, (const double *)dA, n, nullptr, nullptr, nullptr, (double *)dGp, GSUM_MEM_DEVICE);
+        if (rc <= -100) return rc;
+        factor_mode = (rc == 0);
+        if (!factor_mode) c->err[0] = 0;
+    }
     GSUM_TRY(gsum_ws(c, WS_IO1, sizeof(double) * n * ld, &dG));
     GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * n * ld, &dVt));
     GSUM_TRY(gsum_ws(c, WS_LL, sizeof(double) * n, &dw));
@@ -1445,6 +1462,12 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     for (int64_t i = 0; i < n; i++) fro2 += hw[i];
     tol_abs = 0.1 * eps * sqrt(fro2);
     if (const char *e = getenv("GSUM_B200_EIGH_ABS")) tol_abs = atof(e) * eps * sqrt(fro2);
+    if (factor_mode) {
+        tol_gamma = tol_abs; tol_abs = 0.0;
+        jacobi_init_factor_kernel<<<gt, 256, 0, c->stream>>>((const double *)dGp, n, (double *)dG, ni, ld);
+        LAUNCHED(c, 1);
+    }
+    double *dVt_it = factor_mode ? nullptr : (double *)dVt;
     // One sweep = n - 1 dependent launches of a few microseconds each: launch-bound, so the sweep is captured once as a
     // CUDA graph (counter reset + the rounds) and replayed until a sweep makes no rotation.
     const bool trace = getenv("GSUM_B200_EIGH_TRACE") != nullptr;      // rotations per sweep on stderr
@@ -1457,7 +1480,7 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
         GSUM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         cudaMemsetAsync(dcnt, 0, sizeof(unsigned int), c->stream);
         for (int r = 0; r < np - 1; r++)
-            jacobi_round_kernel<<<np / 2, JAC_THREADS, 0, c->stream>>>((double *)dG, (double *)dVt, ni, ld, np, r, tol, tol_abs,
+            jacobi_round_kernel<<<np / 2, JAC_THREADS, 0, c->stream>>>((double *)dG, dVt_it, ni, ld, np, r, tol, tol_abs, tol_gamma,
                                                                       (unsigned int *)dcnt);
         GSUM_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
         GSUM_CUDA(c, cudaGraphInstantiate(&gexec, graph, 0));
@@ -1477,9 +1500,14 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     if (graph) cudaGraphDestroy(graph);
     if (rc_loop) return gsum_fail(c, -100, "gsum_eigh: CUDA error in the sweep graph (%s)", cudaGetErrorString(cudaGetLastError()));
     if (sweeps_out) *sweeps_out = sweeps;
-    jacobi_finish_kernel<<<(unsigned)n, JAC_THREADS, 0, c->stream>>>((const double *)dG, (const double *)dVt, ni, ld, (double *)dw, (double *)dflip,
-                                                                     (double *)dflip + n);
-    GSUM_CUDA(c, cudaMemcpyAsync(hrq.data(), (double *)dflip + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (factor_mode) {
+        jacobi_finish_factor_kernel<<<(unsigned)n, JAC_THREADS, 0, c->stream>>>((const double *)dG, ni, ld, (double *)dw, (double *)dflip);
+        dVt = dG;                                          // the gather below reads the eigenvectors from here
+    } else {
+        jacobi_finish_kernel<<<(unsigned)n, JAC_THREADS, 0, c->stream>>>((const double *)dG, (const double *)dVt, ni, ld, (double *)dw, (double *)dflip,
+                                                                         (double *)dflip + n);
+        GSUM_CUDA(c, cudaMemcpyAsync(hrq.data(), (double *)dflip + n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    }
     LAUNCHED(c, 1);
     std::vector<int32_t> perm(n);
     GSUM_CUDA(c, cudaMemcpyAsync(hw.data(), dw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -1490,7 +1518,7 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     // v_j is an eigenvector iff its Rayleigh quotient reproduces |g_j| (see eig.cuh: +/- lambda pairs of an indefinite matrix)
     bool mixed = false;
     const double wmax = std::max(fabs(hs[0]), fabs(hs[n - 1]));
-    for (int64_t i = 0; i < n; i++)
+    for (int64_t i = 0; i < n && !factor_mode; i++)
         if (fabs(hw[i]) - fabs(hrq[i]) > 1e-6 * fabs(hw[i]) + 1e-10 * wmax) mixed = true;
     if (mem_kind == GSUM_MEM_DEVICE) GSUM_CUDA(c, cudaMemcpy(w, hs.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
     else memcpy(w, hs.data(), sizeof(double) * n);
@@ -1498,9 +1526,27 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
         GSUM_CUDA(c, cudaMemcpy(dperm, perm.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
         void *dV;
         GSUM_TRY(dev_out(c, WS_IO2, V, sizeof(double) * n * n, mem_kind, &dV));
-        jacobi_gather_kernel<<<gt, 256, 0, c->stream>>>((const double *)dVt, ld, (const int32_t *)dperm,
-                                                       (const double *)dflip, ni, (double *)dV);
-        LAUNCHED(c, 1);
+        if (factor_mode && n > 1) {
+            // eigenvectors = normalised rows of G, orthogonal to ~1e-10 (eig.cuh): one Newton-Schulz step V <- V (3 I - V^T V) / 2
+            void *dV0, *dS;
+            GSUM_TRY(gsum_ws(c, WS_MAT, sizeof(double) * n * n, &dV0));
+            GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * n * n, &dS));
+            jacobi_gather_kernel<<<gt, 256, 0, c->stream>>>((const double *)dVt, ld, (const int32_t *)dperm, (const double *)dflip, ni, (double *)dV0);
+            EigGemmArgs g1{};
+            g1.A = (const double *)dV0; g1.lda = n; g1.transA = 1; g1.B = (const double *)dV0; g1.ldb = n;
+            g1.C = (double *)dS; g1.ldc = n; g1.M = n; g1.N = n; g1.K = n;
+            launch_eig_gemm(c, g1);
+            newton_schulz_T_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, c->stream>>>((double *)dS, n);
+            EigGemmArgs g2{};
+            g2.A = (const double *)dV0; g2.lda = n; g2.transA = 0; g2.B = (const double *)dS; g2.ldb = n;
+            g2.C = (double *)dV; g2.ldc = n; g2.M = n; g2.N = n; g2.K = n;
+            launch_eig_gemm(c, g2);
+            LAUNCHED(c, 2);
+        } else {
+            jacobi_gather_kernel<<<gt, 256, 0, c->stream>>>((const double *)dVt, ld, (const int32_t *)dperm,
+                                                           (const double *)dflip, ni, (double *)dV);
+            LAUNCHED(c, 1);
+        }
         GSUM_TRY(dev_out_finish(c, V, dV, sizeof(double) * n * n, mem_kind));
     }
     GSUM_TRY(finish(c, mem_kind));
@@ -1515,11 +1561,6 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     return 0;
 }
 
-static void launch_eig_gemm(gsum_ctx *c, const EigGemmArgs &g) {
-    dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64));
-    eig_gemm_kernel<<<grid, 128, 0, c->stream>>>(g);
-    LAUNCHED(c, 1);
-}
 
 extern "C" int gsum_eig_solve(gsum_ctx *c, const double *w, const double *V, int64_t n, const double *Y, int64_t nrhs,
                               const double *mean, double *X, int32_t mode, int32_t mem_kind) {
