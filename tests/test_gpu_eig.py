@@ -54,6 +54,23 @@ def test_eigh_graded_matrix(ctx):
     assert np.max(np.abs(V.T @ V - np.eye(n))) < 1e-13
 
 
+def test_eigh_factor_mode_opt_in(ctx, monkeypatch):
+    """GSUM_B200_EIGH_FACTOR=1 iterates on the pivoted-Cholesky factor with an eigenvalue-scale rotation criterion and a
+    Newton-Schulz polish: fewer sweeps, same spectrum to eps |A|, orthogonal vectors, looser R^-1 (documented in eig.cuh)."""
+    A = _spd(300, 11, noise=1e-4)
+    w1, V1, s1 = ops.eigh(A, return_sweeps=True)
+    monkeypatch.setenv("GSUM_B200_EIGH_FACTOR", "1")
+    w2, V2, s2 = ops.eigh(A, return_sweeps=True)
+    assert s2 < s1
+    assert np.max(np.abs(w1 - w2)) < 1e-13 * w1[-1]
+    for V, w in ((V1, w1), (V2, w2)):
+        assert np.max(np.abs(V.T @ V - np.eye(300))) < 1e-12
+        assert np.max(np.abs(A @ V - V * w[None, :])) < 1e-12 * w[-1]
+    Y = np.random.RandomState(0).randn(300, 5)
+    Xs = np.linalg.solve(A, Y)
+    assert relerr(ops.eig_solve((w1, V1), Y), Xs) < 1e-8 and relerr(ops.eig_solve((w2, V2), Y), Xs) < 1e-5
+
+
 def test_eigh_indefinite_and_repeated(ctx):
     rs = np.random.RandomState(3)
     Q, _ = np.linalg.qr(rs.randn(50, 50))
