@@ -94,6 +94,62 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(double *__res
     }
 }
 
+// Register-resident round for n <= 256 * EPT (used for n <= 1024, see gsum_eigh): every thread loads its EPT elements of the four rows up front (all loads
+// in flight at once, one memory round trip instead of two dependent passes), the CTA reduces alpha / beta / gamma, and the
+// rotation is applied from registers.  Rows of pairs that do not rotate are only read.  The V^T rows are fetched together
+// with the G rows — they are needed unless the pair is skipped, and the early fetch hides their latency behind the
+// reduction (skipped pairs pay 2x the read, which the L2 absorbs: late sweeps are launch-bound, not bandwidth-bound).
+template <int EPT>
+__global__ void __launch_bounds__(JAC_THREADS) jacobi_round_reg_kernel(double *__restrict__ G, double *__restrict__ Vt, int n, int64_t ld, int np,
+                                                                       int round, double tol, double tol_abs, double tol_gamma,
+                                                                       unsigned int *__restrict__ rotations) {
+    __shared__ double red[3][JAC_THREADS / 32];
+    int p, q;
+    jacobi_pair(np, round, blockIdx.x, p, q);
+    if (q >= n) return;
+    double *gp = G + p * ld, *gq = G + q * ld;
+    double x[EPT], y[EPT], u[EPT], v[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+        const int i = threadIdx.x + e * JAC_THREADS;
+        x[e] = i < n ? gp[i] : 0.0;
+        y[e] = i < n ? gq[i] : 0.0;
+    }
+    double *vp = nullptr, *vq = nullptr;
+    if (Vt) {
+        vp = Vt + p * ld; vq = Vt + q * ld;
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const int i = threadIdx.x + e * JAC_THREADS;
+            u[e] = i < n ? vp[i] : 0.0;
+            v[e] = i < n ? vq[i] : 0.0;
+        }
+    }
+    double a = 0.0, b = 0.0, g = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) { a = fma(x[e], x[e], a); b = fma(y[e], y[e], b); g = fma(x[e], y[e], g); }
+    a = warp_sum(a); b = warp_sum(b); g = warp_sum(g);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { red[0][w] = a; red[1][w] = b; red[2][w] = g; }
+    __syncthreads();
+    a = b = g = 0.0;
+#pragma unroll
+    for (int i = 0; i < JAC_THREADS / 32; i++) { a += red[0][i]; b += red[1][i]; g += red[2][i]; }
+    if (!(fabs(g) > tol * sqrt(a) * sqrt(b)) || !(fabs(g) > tol_abs * sqrt(fmin(a, b))) || !(fabs(g) > tol_gamma)) return;
+    if (threadIdx.x == 0) atomicAdd(rotations, 1u);
+    const double zeta = (b - a) / (2.0 * g);
+    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+#pragma unroll
+    for (int e = 0; e < EPT; e++) {
+        const int i = threadIdx.x + e * JAC_THREADS;
+        if (i < n) {
+            gp[i] = cs * x[e] - sn * y[e]; gq[i] = sn * x[e] + cs * y[e];
+            if (Vt) { vp[i] = cs * u[e] - sn * v[e]; vq[i] = sn * u[e] + cs * v[e]; }
+        }
+    }
+}
+
 // w[j] = sign(v_j . g_j) |g_j|;  rq[j] = v_j . g_j (the Rayleigh quotient: equals w[j] when v_j is an eigenvector);  flip[j] = -1 when the largest-magnitude component of v_j is negative (the eigenvector is
 // returned with that component positive), else +1.  One CTA per row.
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_finish_kernel(const double *__restrict__ G, const double *__restrict__ Vt, int n, int64_t ld,
@@ -234,13 +290,23 @@ __global__ void __launch_bounds__(128) eig_gemm_kernel(EigGemmArgs P) {
 }
 
 // out[j] = sum_k U[k][j]^2 / w[k]      (diag of U^T diag(1/w) U; U is (n x m) row-major: coalesced over j)
-__global__ void __launch_bounds__(256) eig_colquad_kernel(const double *__restrict__ U, int64_t n, int64_t m, const double *__restrict__ w,
-                                                          double *__restrict__ out) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
+// 32 columns per CTA, 32 slices of the k range per column, fixed-order reduction through shared memory (deterministic).
+__global__ void __launch_bounds__(1024) eig_colquad_kernel(const double *__restrict__ U, int64_t n, int64_t m, const double *__restrict__ w,
+                                                           double *__restrict__ out) {
+    __shared__ double part[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t j = (int64_t)blockIdx.x * 32 + tx;
     double s = 0.0;
-    for (int64_t k = 0; k < n; k++) { const double u = U[k * m + j]; s = fma(u * (1.0 / w[k]), u, s); }
-    out[j] = s;
+    if (j < m)
+        for (int64_t k = ty; k < n; k += 32) { const double u = U[k * m + j]; s = fma(u * (1.0 / w[k]), u, s); }
+    part[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && j < m) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 32; r++) t += part[r][tx];
+        out[j] = t;
+    }
 }
 
 // ---- factor mode ------------------------------------------------------------------------------------------------------

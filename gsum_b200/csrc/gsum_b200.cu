@@ -1479,9 +1479,18 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     if (!converged) {
         GSUM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         cudaMemsetAsync(dcnt, 0, sizeof(unsigned int), c->stream);
+        // register-resident round for n <= 1024 (G and V^T sit in L2 and the round is latency-bound: 99 -> 89 ms at
+        // N = 1024); beyond, its unconditional fetch of the V^T rows costs more than the second pass it saves
+        // (measured: N = 2048 385 -> 1548 ms), so the two-pass kernel stays
+        void (*round_fn)(double *, double *, int, int64_t, int, int, double, double, double, unsigned int *) = jacobi_round_kernel;
+        if (!getenv("GSUM_B200_EIGH_TWOPASS")) {
+            if (ni <= 1 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<1>;
+            else if (ni <= 2 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<2>;
+            else if (ni <= 4 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<4>;
+        }
         for (int r = 0; r < np - 1; r++)
-            jacobi_round_kernel<<<np / 2, JAC_THREADS, 0, c->stream>>>((double *)dG, dVt_it, ni, ld, np, r, tol, tol_abs, tol_gamma,
-                                                                      (unsigned int *)dcnt);
+            round_fn<<<np / 2, JAC_THREADS, 0, c->stream>>>((double *)dG, dVt_it, ni, ld, np, r, tol, tol_abs, tol_gamma,
+                                                           (unsigned int *)dcnt);
         GSUM_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
         GSUM_CUDA(c, cudaGraphInstantiate(&gexec, graph, 0));
     }
@@ -1633,7 +1642,7 @@ extern "C" int gsum_eig_conditional(gsum_ctx *c, const double *w, const double *
     if (var_out) {
         void *dvar;
         GSUM_TRY(dev_out(c, WS_MISC0, var_out, sizeof(double) * m, mem_kind, &dvar));
-        eig_colquad_kernel<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>((const double *)dU, n, m, (const double *)dw, (double *)dvar);
+        eig_colquad_kernel<<<(unsigned)((m + 31) / 32), 1024, 0, c->stream>>>((const double *)dU, n, m, (const double *)dw, (double *)dvar);
         LAUNCHED(c, 1);
         GSUM_TRY(dev_out_finish(c, var_out, dvar, sizeof(double) * m, mem_kind));
     }
