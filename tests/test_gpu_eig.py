@@ -217,3 +217,43 @@ def test_eigh_larger_matrix_properties(ctx):
     Y = rs.randn(n, 7)
     assert relerr(A @ res.solve(Y), Y) < 1e-8
     assert abs(np.sum(np.log(w)) - np.linalg.slogdet(A)[1]) < 1e-8 * abs(np.linalg.slogdet(A)[1])
+
+
+def test_c3_size_eig_route_agrees_with_cholesky_route(ctx):
+    """BASELINE config 3 size (2-D inputs, 50 x 50 = 2500 training points, anisotropic RBF): the 'eig' route's posterior,
+    likelihood and predictive mean / std against the Cholesky route on the same device (size-independent property:
+    both decompositions represent the same R)."""
+    g1 = np.linspace(0, 1, 50)
+    X = o.cartesian(g1, g1)
+    n = len(X)
+    rs = np.random.RandomState(2)
+    kern = RBF([0.02, 0.03], 'fixed') + WhiteKernel(1e-4, 'fixed')
+    y = np.linalg.cholesky(RBF([0.02, 0.03])(X) + 1e-8 * np.eye(n)) @ rs.randn(n, 3)
+    Xt = rs.rand(1500, 2)
+    pri = dict(center=0.1, disp=2.0, df=3, scale=0.8, nugget=1e-10)
+    a = gb.ConjugateGaussianProcess(kern, decomposition='eig', **pri).fit(X, y)
+    b = gb.ConjugateGaussianProcess(kern, **pri).fit(X, y)
+    for name in ("center_", "disp_", "scale_", "cov_factor_", "log_marginal_likelihood_value_"):
+        assert relerr(np.asarray(getattr(a, name)), np.asarray(getattr(b, name))) < 1e-9, name
+    ma, sa = a.predict(Xt, return_std=True)
+    mb, sb = b.predict(Xt, return_std=True)
+    assert relerr(ma, mb) < 1e-8 and relerr(sa, sb) < 1e-6
+    w, V = a._eigh_tuple_
+    assert w[0] > 0.9e-4 and abs(np.sum(np.log(w)) - 2 * np.sum(np.log(np.diag(b.corr_L_)))) < 1e-8 * n
+
+
+def test_c5_size_eigen_errors_properties(ctx):
+    """BASELINE config 5 size (N = 4096): eigen_errors of 16 held-out curves; the sign-free invariant
+    sum_k e_k^2 = squared Mahalanobis distance ties the Jacobi eigendecomposition to the Cholesky factor."""
+    n = 4096
+    Xd = np.linspace(0, 1, n)[:, None]
+    cov = 1.3 * (RBF(0.2)(Xd) + 1e-5 * np.eye(n))
+    d = gb.Diagnostic(np.zeros(n), cov, random_state=1)
+    Y = d.samples(16)
+    E = d.eigen_errors(Y)
+    assert E.shape == (n, 16) and np.all(np.isfinite(E))
+    assert relerr(np.sum(E ** 2, axis=0), d.md_squared(Y)) < 1e-7
+    w = d._eigen.w
+    assert np.all(np.diff(w) >= 0) and abs(w.sum() - np.trace(cov)) < 1e-10 * np.trace(cov)
+    # draws from N(0, cov): the errors are standard normal whatever the basis
+    assert abs(np.mean(E)) < 0.02 and abs(np.std(E) - 1.0) < 0.02
