@@ -46,6 +46,8 @@ _SIGNATURES = {
     "gsum_grid_normalize": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int32]),
     "gsum_lml_grad_terms": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double,
                                       C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int32]),
+    "gsum_lml_grad_terms_eig": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double,
+                                          C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int32]),
     "gsum_fit_create": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_double,
                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
                                   _vp, _vp, C.c_int32, C.POINTER(_vp)]),

@@ -13,6 +13,7 @@
 #include "hetero.cuh"
 #include "hetero_tma.cuh"
 #include <cstdlib>
+#include <vector>
 
 #define LAUNCHED(ctx, n) ((ctx)->launches += (n))
 
@@ -800,9 +801,13 @@ extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B
 }
 
 // ---- gradient terms of the likelihood (gsum/models.py:957-1056) ------------------------------------------------
-extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
-                                   const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
-                                   double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind) {
+extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, double *V, int32_t *sweeps_out, int32_t mem_kind);
+extern "C" int gsum_eig_solve(gsum_ctx *c, const double *w, const double *V, int64_t n, const double *Y, int64_t nrhs,
+                              const double *mean, double *X, int32_t mode, int32_t mem_kind);
+
+static int lml_grad_terms_impl(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
+                               const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                               double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind, int use_eig) {
     if (!c || !X || !RHS || !ls || !G || !H || !tr || !logdet || !info)
         return gsum_fail(c, -1, "gsum_lml_grad_terms: null argument");
     if (n <= 0 || d <= 0 || d > COV_MAXD || r < 1 || r > GRAD_MAXR || (ls_dim != 1 && ls_dim != d))
@@ -829,10 +834,28 @@ extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int3
     GSUM_TRY(gsum_kernel_matrix(c, (const double *)dX, n, nullptr, 0, d, (const double *)dls, ls_dim, constant, noise, (double *)dR, GSUM_MEM_DEVICE));
     add_diag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((double *)dR, n, n, nugget);
     LAUNCHED(c, 1);
-    GSUM_TRY(gsum_cholesky(c, (double *)dR, n, 1, dinfo, dld, GSUM_MEM_DEVICE));
     grad_stage_kernel<<<dim3((unsigned)((ldz + 255) / 256), (unsigned)n), 256, 0, c->stream>>>((const double *)dRHS, n, r, (double *)dB);
     LAUNCHED(c, 1);
-    GSUM_TRY(gsum_cho_solve(c, (const double *)dR, n, (double *)dB, ldz, 0, GSUM_MEM_DEVICE));       // [Z | R^{-1}]
+    if (!use_eig) {
+        GSUM_TRY(gsum_cholesky(c, (double *)dR, n, 1, dinfo, dld, GSUM_MEM_DEVICE));
+        GSUM_TRY(gsum_cho_solve(c, (const double *)dR, n, (double *)dB, ldz, 0, GSUM_MEM_DEVICE));   // [Z | R^{-1}]
+    } else {
+        // decomposition='eig' (gsum/models.py:973-974, 480-484, 1019): R = Q diag(eig) Q^T on the device,
+        // [Z | R^{-1}] = Q diag(1/eig) Q^T [RHS | I], logdet R = sum log eig (NaN for a non-positive eigenvalue, as numpy's)
+        void *dwv, *dVv;
+        GSUM_TRY(gsum_ws(c, WS_DETF, sizeof(double) * n, &dwv));
+        GSUM_TRY(gsum_ws(c, WS_MKK, sizeof(double) * n * n, &dVv));
+        const int rc = gsum_eigh(c, (const double *)dR, n, (double *)dwv, (double *)dVv, nullptr, GSUM_MEM_DEVICE);
+        if (rc != 0) return rc;
+        GSUM_TRY(gsum_eig_solve(c, (const double *)dwv, (const double *)dVv, n, (const double *)dB, ldz, nullptr, (double *)dB, 0, GSUM_MEM_DEVICE));
+        std::vector<double> hwv(n);
+        GSUM_CUDA(c, cudaMemcpyAsync(hwv.data(), dwv, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        double ld_host = 0.0;
+        for (int64_t i = 0; i < n; i++) ld_host += log(hwv[i]);
+        GSUM_CUDA(c, cudaMemcpy(dld, &ld_host, sizeof(double), cudaMemcpyHostToDevice));
+        GSUM_CUDA(c, cudaMemsetAsync(dinfo, 0, sizeof(int32_t), c->stream));
+    }
     // scaled coordinates (gsum_kernel_matrix left X / ls in WS_XS)
     const double *dXS = (const double *)c->ws[WS_XS];
     const size_t shbytes = sizeof(double) * (128 * COV_MAXD + 128 * GRAD_MAXR);
@@ -855,6 +878,17 @@ extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int3
         GSUM_CUDA(c, cudaMemcpyAsync(info, dinfo, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     }
     return finish(c, mem_kind);
+}
+
+extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
+                                   const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                                   double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind) {
+    return lml_grad_terms_impl(c, X, n, d, RHS, r, ls, ls_dim, constant, noise, nugget, G, H, tr, logdet, info, mem_kind, 0);
+}
+extern "C" int gsum_lml_grad_terms_eig(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
+                                       const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                                       double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind) {
+    return lml_grad_terms_impl(c, X, n, d, RHS, r, ls, ls_dim, constant, noise, nugget, G, H, tr, logdet, info, mem_kind, 1);
 }
 
 // ---- fit --------------------------------------------------------------------------------------------------

@@ -419,7 +419,8 @@ class BaseConjugateProcess:
         if len(layout) != len(theta):
             raise ValueError("theta does not match the kernel's free hyperparameters")
         rhs = np.concatenate([np.ones((N, 1)), y], axis=1)
-        G, H, tr, logdet, info = ops.lml_grad_terms(X, rhs, k.ls_for(X.shape[1]), constant=k.constant, noise=k.noise, nugget=self.nugget)
+        G, H, tr, logdet, info = ops.lml_grad_terms(X, rhs, k.ls_for(X.shape[1]), constant=k.constant, noise=k.noise, nugget=self.nugget,
+                                                    decomposition=self.decomposition)
         if info != 0:
             return -np.inf, np.zeros_like(theta)                                  # models.py:970-972
         pri = self._priors()
@@ -482,13 +483,10 @@ class BaseConjugateProcess:
         return float(ll), grad
 
     def _lml(self, theta, eval_gradient, X, y):
-        if self._eig_route():
-            if eval_gradient:
-                raise NotImplementedError("gsum_b200: the analytic likelihood gradient is built on the Cholesky factor; "
-                                          "with decomposition='eig' use optimizer=None or fixed hyperparameter bounds")
-            return self._lml_eig(theta, X, y)
         if eval_gradient:
             return self._lml_gradient(theta, X, y)
+        if self._eig_route():
+            return self._lml_eig(theta, X, y)
         kernel = self._active_kernel().clone_with_theta(theta)
         X = self.X_train_ if X is None else X
         y = self.y_train_ if y is None else y

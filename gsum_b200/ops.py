@@ -124,7 +124,7 @@ def lml_grid(X, dy, ref, orders, ls, Q, q_x_dependent=False, detf=None, constant
     return (ll, logdet, status) if return_status else ll
 
 
-def lml_grad_terms(X, rhs, ls, constant=1.0, noise=0.0, nugget=1e-10, ctx=None):
+def lml_grad_terms(X, rhs, ls, constant=1.0, noise=0.0, nugget=1e-10, decomposition="cholesky", ctx=None):
     """Device half of the analytic likelihood gradient (gsum/models.py:957-1056): with RHS = [basis | curves] (n, r),
     Z = R^-1 RHS and dR_p = dR/dlog(theta_p) for theta = [constant, length scale(s), noise level]:
     returns G = RHS^T Z (r, r), H (P, r, r) = Z^T dR_p Z, tr (P,) = trace(R^-1 dR_p), logdet R, info."""
@@ -137,8 +137,11 @@ def lml_grad_terms(X, rhs, ls, constant=1.0, noise=0.0, nugget=1e-10, ctx=None):
     P = ls.shape[0] + 2
     G, H, tr = np.empty((r, r)), np.empty((P, r, r)), np.empty(P)
     logdet, info = np.zeros(1), np.zeros(1, dtype=np.int32)
-    ctx.check(ctx.lib.gsum_lml_grad_terms(ctx.handle, _p(X), n, d, _p(rhs), r, _p(ls), ls.shape[0], float(constant), float(noise),
-                                          float(nugget), _p(G), _p(H), _p(tr), _p(logdet), _p(info), MEM_HOST), "gsum_lml_grad_terms")
+    fn = ctx.lib.gsum_lml_grad_terms_eig if decomposition == "eig" else ctx.lib.gsum_lml_grad_terms
+    rc = ctx.check(fn(ctx.handle, _p(X), n, d, _p(rhs), r, _p(ls), ls.shape[0], float(constant), float(noise),
+                      float(nugget), _p(G), _p(H), _p(tr), _p(logdet), _p(info), MEM_HOST), "gsum_lml_grad_terms")
+    if rc:
+        raise np.linalg.LinAlgError(_eigh_message(ctx))
     return G, H, tr, float(logdet[0]), int(info[0])
 
 

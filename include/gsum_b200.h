@@ -223,6 +223,13 @@ int gsum_credible_interval(gsum_ctx *ctx, const double *Y, int64_t n, int64_t n_
  *   the covariance / correlation matrices of the cited call sites are positive semi-definite up to rounding). */
 int gsum_eigh(gsum_ctx *ctx, const double *A, int64_t n, double *w, double *V, int32_t *sweeps_out, int32_t mem_kind);
 
+/* gsum_lml_grad_terms_eig: gsum_lml_grad_terms on the 'eig' route — the same outputs with R^-1 taken from the device
+ *   eigendecomposition (Q diag(1/eig) Q^T, gsum/models.py:480-484, 1043) and logdet R = sum log eig (models.py:1019);
+ *   info is always 0 (the reference's 'eig' branch has no failure exit, models.py:973-974). */
+int gsum_lml_grad_terms_eig(gsum_ctx *ctx, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
+                            const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
+                            double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind);
+
 /* gsum_eig_solve: with (w, V) from gsum_eigh and Y (n, nrhs), mean (n,) or NULL (subtracted from every column of Y):
  *   mode 0: X = V diag(1/w) V^T (Y - mean)            `solve_sqrt(..., decomposition='eig')`, gsum/models.py:480-484
  *   mode 1: X = diag(|w|^-1/2) V^T (Y - mean)         `eigen_errors`, gsum/diagnostics.py:63-68, 106-107 (row k of X

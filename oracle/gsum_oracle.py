@@ -223,8 +223,8 @@ def gaussian_lml(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis
     return ll.sum(-1)                                           # :1039
 
 
-def gaussian_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis):
-    """gsum/models.py:912-1057 with eval_gradient=True (decomposition='cholesky'): (log-likelihood, d/dtheta).
+def gaussian_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_ones_basis, decomposition="cholesky"):
+    """gsum/models.py:912-1057 with eval_gradient=True (decomposition 'cholesky' or 'eig'): (log-likelihood, d/dtheta).
 
     The kernel gradient comes from sklearn (`kernel(X, eval_gradient=True)`, models.py:957-958); the conjugate updates
     carry their own derivatives: compute_center (models.py:222-230), compute_scale_sq (450-455), compute_cov_factor
@@ -233,7 +233,7 @@ def gaussian_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_o
     R, dR = k(X, eval_gradient=True)                            # :957-958
     R[np.diag_indices_from(R)] += nugget                        # :963
     try:
-        L_R = cholesky(R)
+        L_R = _sqrt_R(R, decomposition)                         # :969 / :974
     except np.linalg.LinAlgError:
         return -np.inf, np.zeros_like(theta)                    # :970-972
     if y.ndim == 1:
@@ -270,8 +270,12 @@ def gaussian_lml_gradient(kernel, theta, X, y, priors, nugget=1e-10, basis_fn=_o
     grad_mean = basis @ grad_center                             # :999
     mean = basis @ center
     var = compute_cov_factor(scale2, df)
-    L = np.sqrt(var) * L_R
-    logdet_K = 2 * np.log(np.diag(L)).sum()
+    if decomposition == "cholesky":
+        L = np.sqrt(var) * L_R
+        logdet_K = 2 * np.log(np.diag(L)).sum()
+    else:
+        L = var * L_R[0], L_R[1]                                # :1017-1018
+        logdet_K = np.log(var * L_R[0]).sum()                   # :1019
     K_gradient = var * dR + grad_var * R[:, :, None]            # :1024-1025
     y_train = y - mean[:, None]
     alpha = solve_sqrt(L, y_train)

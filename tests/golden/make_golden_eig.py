@@ -55,6 +55,15 @@ def main():
             if ip == 0 and tag == "g":
                 out["eigvals"] = gp._eigh_tuple_[0]
                 out["corr_sqrt"] = gp.corr_sqrt_
+    # ---- analytic gradient on the 'eig' route (models.py:1041-1056 through solve_sqrt(..., 'eig')), all hyperparameters free ----
+    gthetas = np.log(np.array([[1.5, 0.2, 1e-4], [0.7, 0.1, 1e-3], [2.5, 0.35, 1e-5]]))
+    out["grad_thetas"] = gthetas
+    for ip, p in enumerate(PRIORS):
+        gp = models.ConjugateGaussianProcess(C(1.5) * RBF(0.2) + WhiteKernel(1e-4), nugget=1e-10, optimizer=None,
+                                             decomposition='eig', **p).fit(X, y)
+        res = [gp.log_marginal_likelihood(theta=t, eval_gradient=True) for t in gthetas]
+        out[f"g{ip}_glml"] = np.array([r[0] for r in res])
+        out[f"g{ip}_grad"] = np.array([r[1] for r in res])
     # ---- TruncationGP likelihood cells with decomposition='eig', N = 120, orders 0..4 ----
     Nt = 120
     Xt = np.linspace(0, 1, Nt)[:, None]
@@ -83,6 +92,7 @@ def main():
     np.savez_compressed(path, **out)
     print(f"eig_route: {os.path.getsize(path) / 1024:.1f} KiB; keys={len(out)}; t_ll=\n{out['t_ll']}")
     print("g0 post", out["g0_post"], "lml", out["g0_lml"])
+    print("g1 grad", out["g1_grad"])
 
 
 if __name__ == "__main__":

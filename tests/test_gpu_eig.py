@@ -139,8 +139,12 @@ def test_eig_route_fit_lml_predict_golden(ctx, golden, ip, tag):
     assert np.array_equal(np.isnan(lml), np.isnan(wl))
     if np.isfinite(wl).all():
         assert relerr(lml, wl) < 1e-9
-    with pytest.raises(NotImplementedError):
-        gpf.log_marginal_likelihood(theta=[g["thetas"][0]], eval_gradient=True)
+    if tag == "g":
+        # analytic gradient on the 'eig' route against the reference's (models.py:1041-1056 through solve_sqrt(..., 'eig'))
+        gpg = cls(C(1.5) * RBF(0.2) + WhiteKernel(1e-4), nugget=1e-10, optimizer=None, decomposition='eig', **pri).fit(g["X"], g["y"])
+        res = [gpg.log_marginal_likelihood(theta=t, eval_gradient=True) for t in g["grad_thetas"]]
+        assert relerr(np.array([r[0] for r in res]), g[f"g{ip}_glml"]) < 1e-9
+        assert relerr(np.array([r[1] for r in res]), g[f"g{ip}_grad"]) < 1e-7
     if ip == 0 and tag == "g":
         w, V = gp._eigh_tuple_
         assert np.max(np.abs(w - g["eigvals"])) < 1e-13 * g["eigvals"][-1]
@@ -257,3 +261,17 @@ def test_c5_size_eigen_errors_properties(ctx):
     assert np.all(np.diff(w) >= 0) and abs(w.sum() - np.trace(cov)) < 1e-10 * np.trace(cov)
     # draws from N(0, cov): the errors are standard normal whatever the basis
     assert abs(np.mean(E)) < 0.02 and abs(np.std(E) - 1.0) < 0.02
+
+
+def test_eig_route_fit_with_free_length_scale(ctx):
+    """`fit` with the default optimizer on the 'eig' route (L-BFGS on the analytic gradient, gsum/models.py:630-669):
+    same optimum as the Cholesky route."""
+    rs = np.random.RandomState(4)
+    X = np.linspace(0, 1, 80)[:, None]
+    y = np.linalg.cholesky(RBF(0.17)(X) + 1e-6 * np.eye(80)) @ rs.randn(80, 4)
+    kw = dict(center=0, disp=0, df=3, scale=1, nugget=1e-10)
+    a = gb.ConjugateGaussianProcess(RBF(0.4) + WhiteKernel(1e-4, 'fixed'), decomposition='eig', **kw).fit(X, y)
+    b = gb.ConjugateGaussianProcess(RBF(0.4) + WhiteKernel(1e-4, 'fixed'), **kw).fit(X, y)
+    la, lb = np.exp(a.kernel_.theta[0]), np.exp(b.kernel_.theta[0])
+    assert 0.1 < la < 0.3 and abs(la - lb) < 1e-4 * lb
+    assert relerr(np.array(a.log_marginal_likelihood_value_), np.array(b.log_marginal_likelihood_value_)) < 1e-7

@@ -182,10 +182,6 @@ def test_facade_rejects_out_of_scope_options():
     from gsum_b200 import ConjugateGaussianProcess, Diagnostic, TruncationGP
     with pytest.raises(NotImplementedError):
         ConjugateGaussianProcess(RBF(0.2), basis=lambda X: X)
-    gp = ConjugateGaussianProcess(RBF(0.2), decomposition='eig')
-    gp.kernel_ = gp.kernel
-    with pytest.raises(NotImplementedError):                                # 'eig' route: no analytic gradient (documented)
-        gp.log_marginal_likelihood(theta=[0.0], eval_gradient=True, X=np.zeros((3, 1)), y=np.zeros(3))
     gp = ConjugateGaussianProcess(RBF(0.2, 'fixed'), decomposition='lu')
     with pytest.raises(ValueError):
         gp.fit(np.zeros((3, 1)), np.zeros(3))

@@ -277,3 +277,13 @@ def test_eig_route_truncation_and_eigen_errors_oracle(golden):
     cov = 1.3 * np.outer(g["amp"], g["amp"]) * (RBF(0.2)(g["Xd"]) + 1e-5 * np.eye(len(g["Xd"])))
     E = o.eigen_errors(g["Yd"], g["d_mean"], o.eigen_factor(cov))
     assert relerr(E, g["eigen_errors"]) < 1e-9
+
+
+@pytest.mark.parametrize("ip", range(3))
+def test_eig_route_gradient_oracle(golden, ip):
+    g = golden("eig_route")
+    p = o.Priors(**prior_kwargs(g["priors"][ip]))
+    kern = C(1.5) * RBF(0.2) + WhiteKernel(1e-4)
+    res = [o.gaussian_lml_gradient(kern, t, g["X"], g["y"], p, 1e-10, decomposition="eig") for t in g["grad_thetas"]]
+    assert relerr(np.array([r[0] for r in res]), g[f"g{ip}_glml"]) < TOL
+    assert relerr(np.array([r[1] for r in res]), g[f"g{ip}_grad"]) < 1e-9
