@@ -840,9 +840,6 @@ class TruncationProcess:
         Returns ll with shape (n_q, n_ls), i.e. ``ll[i_ratio][i_ls]`` as in the notebook.
         """
         cp = self.coeffs_process
-        if cp._eig_route():
-            raise NotImplementedError("gsum_b200: the (Q, l) grid kernel factors by Cholesky; with decomposition='eig' "
-                                      "evaluate log_marginal_likelihood cell by cell")
         X, dy, orders_in = self._grid_inputs(X, y, orders)
         n = X.shape[0]
         k = flatten_kernel(cp._active_kernel())
@@ -862,12 +859,55 @@ class TruncationProcess:
             Q = np.stack([np.asarray(self.ratio(X, **kw), dtype=np.float64) for kw in ratio_kws_list])
             detf = np.sum(n_c * np.log(np.abs(ref))) + so * np.sum(np.log(np.abs(Q)), axis=1)
             xdep = True
+        if cp._eig_route():
+            if group is not None:
+                raise NotImplementedError("gsum_b200: the sharded grid runs the Cholesky kernel; decomposition='eig' is single-GPU")
+            ll = self._lml_grid_eig(X, dy, ref, orders_in, ls, Q, xdep, np.broadcast_to(detf, (Q.shape[0],)), k)
+            return (ll, np.zeros(ls.shape[0], dtype=np.int32)) if return_status else ll
         kw = dict(q_x_dependent=xdep, detf=detf, constant=k.constant, noise=k.noise, nugget=cp.nugget, student=cp._student,
                   **cp._priors())
         if group is not None:
             from .distributed import lml_grid_sharded
             return lml_grid_sharded(X, dy, ref, orders_in, ls, Q, group=group, **kw)
         return ops.lml_grid(X, dy, ref, orders_in, ls, Q, return_status=return_status, **kw)
+
+
+    def _lml_grid_eig(self, X, dy, ref, orders_in, ls, Q, xdep, detf, k):
+        """The (Q, l) surface on the 'eig' route: per length scale ONE device eigendecomposition and ONE device solve, reused
+        for every Q — for a scalar Q the coefficients are dy / (ref Q^order) (gsum/helpers.py:71-101), so the Gram of
+        [basis | c(Q)] is S(Q) G S(Q) with G the Gram of [basis | dy / ref] and S = diag(1, Q^-order); for an x-dependent
+        Q all right-hand-side blocks go through the same solve.  The O(n_c^2) cell algebra is `_conjugate_from_gram`."""
+        cp = self.coeffs_process
+        n, nc = dy.shape
+        n_q = Q.shape[0]
+        pri = cp._priors()
+        base = dy / ref[:, None]
+        if xdep:
+            blocks = [base / Q[i][:, None] ** orders_in[None, :] for i in range(n_q)]
+            rhs = np.concatenate([np.ones((n, 1))] + blocks, axis=1)
+        else:
+            rhs = np.concatenate([np.ones((n, 1)), base], axis=1)
+        ll = np.empty((n_q, ls.shape[0]))
+        for j in range(ls.shape[0]):
+            R = ops.kernel_matrix(X, None, ls[j], k.constant, k.noise)
+            R[np.diag_indices_from(R)] += cp.nugget
+            eig = ops.ResidentEigen(R)
+            W = eig.solve(rhs)
+            with np.errstate(invalid='ignore', divide='ignore'):
+                logdet = float(np.sum(np.log(eig.w)))
+            if not xdep:
+                G0 = rhs.T @ W
+                G0 = 0.5 * (G0 + G0.T)
+            for i in range(n_q):
+                if xdep:
+                    cols = np.r_[0, 1 + i * nc:1 + (i + 1) * nc]
+                    G = rhs[:, cols].T @ W[:, cols]
+                    G = 0.5 * (G + G.T)
+                else:
+                    sc = np.r_[1.0, Q[i] ** (-orders_in.astype(np.float64))]
+                    G = G0 * np.outer(sc, sc)
+                ll[i, j] = _conjugate_from_gram(G, logdet, n, nc, pri, cp._student)["lml"] - detf[i]
+        return ll
 
 
 class TruncationGP(TruncationProcess):

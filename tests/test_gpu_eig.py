@@ -184,8 +184,13 @@ def test_eig_route_truncation_lml_golden(ctx, golden):
     ll = np.array([[tgp.log_marginal_likelihood(theta=[np.log(l)], ratio=q) for l in g["ls_vals"]] for q in g["q_vals"]])
     # noise 1e-6: the explicit inverse of the reference's eig route sits at cond * eps ~ 1e-8 of the quadratic forms
     assert relerr(ll, g["t_ll"]) < 1e-7
-    with pytest.raises(NotImplementedError):
-        tgp.log_marginal_likelihood_grid(g["ls_vals"], g["q_vals"])
+    # the whole surface in one call (one eigendecomposition per length scale, reused for every Q), scalar and x-dependent Q
+    grid = tgp.log_marginal_likelihood_grid(g["ls_vals"], g["q_vals"])
+    assert grid.shape == ll.shape and relerr(grid, g["t_ll"]) < 1e-7 and relerr(grid, ll) < 1e-9
+    tq = gb.TruncationGP(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=lambda X, q=0.5: q * np.ones(len(X)), ref=1, center=0, disp=0,
+                         df=1, scale=1, optimizer=None, decomposition='eig').fit(g["Xt"], g["yt"], orders=g["orders"])
+    gx = tq.log_marginal_likelihood_grid(g["ls_vals"], ratio_kws_list=[dict(q=q) for q in g["q_vals"]])
+    assert relerr(gx, g["t_ll"]) < 1e-7
 
 
 def test_diagnostic_eigen_errors_golden(ctx, golden):
