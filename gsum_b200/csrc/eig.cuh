@@ -315,10 +315,12 @@ __global__ void __launch_bounds__(1024) eig_colquad_kernel(const double *__restr
 // pivoting makes strongly graded and diagonally dominant, and needs no V — with F V = U Sigma, A = U Sigma^2 U^T, so
 // lambda_j = |g_j|^2 and eigenvector j = g_j / |g_j|.  Here gamma is already on the scale of the eigenvalues: pairs with
 // |gamma| <= tol_gamma = c eps |A|_F are skipped, and one Newton-Schulz step restores orthogonality afterwards.
-// Measured (RBF(0.05) + 1e-4 I, c = 0.1): 11-13 sweeps instead of 19-20 and no V^T to rotate — N = 1024 / 2048 / 4096 in
-// 69 / 185 / 1340 ms against 99 / 385 / 3070 ms for the default mode and 61 / 290 / 2284 ms for LAPACK on the host — but
-// the skipped in-cluster couplings add up over the ~n^2 pairs of the noise-level cluster: the residual of R^-1 y is
-// 2e-8 ... 1e-7 instead of 3e-10 ... 1e-9.  Parity comes first, so this mode is OPT-IN (GSUM_B200_EIGH_FACTOR=1).
+// Measured (RBF(0.05) + 1e-4 I; profiles/r01_eig_probe.txt): with c = 0.01, 12-14 sweeps instead of 19-20 and no V^T to
+// rotate — N = 1024 / 2048 / 4096 in 55-67 / 197 / 1810 ms against 89 / 385 / 3070 ms for the default mode and
+// 61 / 290 / 2330 ms for LAPACK on the host — but the skipped in-cluster couplings add up over the ~n^2 pairs of the
+// noise-level cluster: the residual of R^-1 y is 2e-9 / 7e-9 / 1.4e-8 where both the default mode and LAPACK's own
+// Q diag(1/eig) Q^T y give 3e-10 / 4e-10 / 9e-10 (c = 0.1: 2e-8 ... 1e-7 at the same sweep count; c <= 0.001: 21-28
+// sweeps).  Parity comes first, so this mode is OPT-IN (GSUM_B200_EIGH_FACTOR=1).
 __global__ void __launch_bounds__(256) jacobi_init_factor_kernel(const double *__restrict__ F, int64_t ldf, double *__restrict__ G, int n, int64_t ld) {
     __shared__ double tile[32][33];
     const int j0 = blockIdx.y * 32, i0 = blockIdx.x * 32;           // G[j][i] = F[i][j]

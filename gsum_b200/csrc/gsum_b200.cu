@@ -1497,7 +1497,8 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     tol_abs = 0.1 * eps * sqrt(fro2);
     if (const char *e = getenv("GSUM_B200_EIGH_ABS")) tol_abs = atof(e) * eps * sqrt(fro2);
     if (factor_mode) {
-        tol_gamma = tol_abs; tol_abs = 0.0;
+        tol_gamma = getenv("GSUM_B200_EIGH_ABS") ? tol_abs : 0.01 * eps * sqrt(fro2);      // c = 0.01: best measured trade (eig.cuh)
+        tol_abs = 0.0;
         jacobi_init_factor_kernel<<<gt, 256, 0, c->stream>>>((const double *)dGp, n, (double *)dG, ni, ld);
         LAUNCHED(c, 1);
     }
