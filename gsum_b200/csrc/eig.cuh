@@ -207,6 +207,9 @@ __global__ void __launch_bounds__(256) jacobi_gather_kernel(const double *__rest
 // Row-major operands; op(A) = A (lda >= K) or A^T (A stored K x M, lda >= M).  64 x 64 tile per CTA, four warps of
 // 32 x 32, FP64 tensor-core MMA (DMMA 8x8x4) on fragments read from padded shared memory (stride 36: conflict-free).
 // row_mode: 0 none, 1 C[m][:] /= rs[m], 2 C[m][:] /= sqrt(|rs[m]|).
+// Measured: 16-19 TFLOP/s (0.46-0.54 of the DGEMM peak; DMMA pipe 45-54 %).  A register-staged prefetch of the next K slab
+// (16 + 16 doubles per thread) pushed the kernel to 255 registers with spills and HALVED the rate (M = N = 4096, K = 1024:
+// 1.92 -> 4.34 ms) — the next step is cp.async double buffering in shared memory, as the factorisation kernel does.
 struct EigGemmArgs {
     const double *A; int64_t lda; int transA;
     const double *B; int64_t ldb;
