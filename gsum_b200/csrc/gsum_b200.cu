@@ -1511,29 +1511,37 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     bool converged = (n == 1);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t gexec = nullptr;
-    if (!converged) {
-        GSUM_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    // register-resident round for n <= 1024 (G and V^T sit in L2 and the round is latency-bound: 99 -> 89 ms at
+    // N = 1024); beyond, its unconditional fetch of the V^T rows costs more than the second pass it saves
+    // (measured: N = 2048 385 -> 1548 ms), so the two-pass kernel stays
+    void (*round_fn)(double *, double *, int, int64_t, int, int, double, double, double, unsigned int *) = jacobi_round_kernel;
+    if (!getenv("GSUM_B200_EIGH_TWOPASS")) {
+        if (ni <= 1 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<1>;
+        else if (ni <= 2 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<2>;
+        else if (ni <= 4 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<4>;
+    }
+    auto enqueue_sweep = [&]() {
         cudaMemsetAsync(dcnt, 0, sizeof(unsigned int), c->stream);
-        // register-resident round for n <= 1024 (G and V^T sit in L2 and the round is latency-bound: 99 -> 89 ms at
-        // N = 1024); beyond, its unconditional fetch of the V^T rows costs more than the second pass it saves
-        // (measured: N = 2048 385 -> 1548 ms), so the two-pass kernel stays
-        void (*round_fn)(double *, double *, int, int64_t, int, int, double, double, double, unsigned int *) = jacobi_round_kernel;
-        if (!getenv("GSUM_B200_EIGH_TWOPASS")) {
-            if (ni <= 1 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<1>;
-            else if (ni <= 2 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<2>;
-            else if (ni <= 4 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<4>;
-        }
         for (int r = 0; r < np - 1; r++)
             round_fn<<<np / 2, JAC_THREADS, 0, c->stream>>>((double *)dG, dVt_it, ni, ld, np, r, tol, tol_abs, tol_gamma,
                                                            (unsigned int *)dcnt);
-        GSUM_CUDA(c, cudaStreamEndCapture(c->stream, &graph));
-        GSUM_CUDA(c, cudaGraphInstantiate(&gexec, graph, 0));
+    };
+    // a caller-provided stream may not be capturable (legacy default stream): plain launches then
+    if (!converged && !getenv("GSUM_B200_EIGH_NOGRAPH") &&
+        cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        enqueue_sweep();
+        if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            graph = nullptr; gexec = nullptr;
+        }
     }
+    cudaGetLastError();
     int rc_loop = 0;
     while (!converged && sweeps < JAC_MAX_SWEEPS) {
         unsigned int rot = 0;
-        if (cudaGraphLaunch(gexec, c->stream) != cudaSuccess ||
-            cudaMemcpyAsync(&rot, dcnt, sizeof(rot), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        if (gexec) { if (cudaGraphLaunch(gexec, c->stream) != cudaSuccess) { rc_loop = -100; break; } }
+        else enqueue_sweep();
+        if (cudaMemcpyAsync(&rot, dcnt, sizeof(rot), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { rc_loop = -100; break; }
         LAUNCHED(c, rounds);
         if (trace) fprintf(stderr, "[gsum_eigh] n=%d sweep %d: %u rotations\n", ni, sweeps, rot);

@@ -71,6 +71,19 @@ def test_eigh_factor_mode_opt_in(ctx, monkeypatch):
     assert relerr(ops.eig_solve((w1, V1), Y), Xs) < 1e-8 and relerr(ops.eig_solve((w2, V2), Y), Xs) < 1e-5
 
 
+def test_eigh_without_graph_is_bit_identical(ctx, monkeypatch):
+    """The CUDA-graph replay of a sweep and plain stream launches (the fallback for a non-capturable caller stream) run the
+    same kernels in the same order: bit-identical output."""
+    A = _spd(130, 5)
+    w1, V1 = ops.eigh(A)
+    monkeypatch.setenv("GSUM_B200_EIGH_NOGRAPH", "1")
+    w2, V2 = ops.eigh(A)
+    assert np.array_equal(w1, w2) and np.array_equal(V1, V2)
+    monkeypatch.setenv("GSUM_B200_EIGH_TWOPASS", "1")
+    w3, V3 = ops.eigh(A)
+    assert np.max(np.abs(w3 - w1)) < 1e-14 * w1[-1]
+
+
 def test_eigh_indefinite_and_repeated(ctx):
     rs = np.random.RandomState(3)
     Q, _ = np.linalg.qr(rs.randn(50, 50))
