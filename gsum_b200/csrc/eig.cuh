@@ -207,9 +207,9 @@ __global__ void __launch_bounds__(256) jacobi_gather_kernel(const double *__rest
 // Row-major operands; op(A) = A (lda >= K) or A^T (A stored K x M, lda >= M).  64 x 64 tile per CTA, four warps of
 // 32 x 32, FP64 tensor-core MMA (DMMA 8x8x4) on fragments read from padded shared memory (stride 36: conflict-free).
 // row_mode: 0 none, 1 C[m][:] /= rs[m], 2 C[m][:] /= sqrt(|rs[m]|).
-// Measured: 16-19 TFLOP/s (0.46-0.54 of the DGEMM peak; DMMA pipe 45-54 %).  A register-staged prefetch of the next K slab
-// (16 + 16 doubles per thread) pushed the kernel to 255 registers with spills and HALVED the rate (M = N = 4096, K = 1024:
-// 1.92 -> 4.34 ms) — the next step is cp.async double buffering in shared memory, as the factorisation kernel does.
+// History: the single-buffered version ran at 16-19 TFLOP/s (0.46-0.54 of the DGEMM peak); a register-staged prefetch of the
+// next K slab (16 + 16 doubles per thread) pushed it to 255 registers with spills and HALVED the rate (M = N = 4096,
+// K = 1024: 1.92 -> 4.34 ms); the shipped kernel double-buffers through cp.async instead.
 struct EigGemmArgs {
     const double *A; int64_t lda; int transA;
     const double *B; int64_t ldb;
@@ -220,9 +220,24 @@ struct EigGemmArgs {
     const double *rs; int row_mode;
 };
 
+#define EG_LDN 68                                   // row stride of the [k][64] tiles: 68 % 16 == 4 -> conflict-free fragments
+#define EG_A_ELEMS (64 * GSUM_LDH)                  // A tile: [64 m][36] (op(A) = A) or [32 k][68] (op(A) = A^T); 2304 >= 2176
+#define EG_B_ELEMS (GSUM_KH * EG_LDN)
+#define EG_STAGE (EG_A_ELEMS + EG_B_ELEMS + 2 * GSUM_KH)
+#define EG_SMEM_BYTES (2 * EG_STAGE * sizeof(double))
+
+// 8-byte cp.async with zero fill (src_bytes = 0 copies nothing and writes zeros)
+__device__ __forceinline__ void cp_async8_zfill(void *smem_dst, const void *gmem_src, int src_bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gmem_src), "r"(src_bytes));
+}
+
+// Two-stage cp.async pipeline: K slab k + 1 streams into shared memory while the DMMA loop runs on slab k.  Tiles keep the
+// global layout's contiguous direction ([m][k] for A, [k][m] for A^T, [k][n] for B), so every copy is a plain 8-byte
+// cp.async; the per-k transforms of B (subtract bsub[k], divide by bdiv[k]) are applied to the fragments from two small
+// per-slab vectors.  (The single-buffered first version ran the DMMA pipe at 45-54 %, profiles/r01_ncu_eig.txt.)
 __global__ void __launch_bounds__(128) eig_gemm_kernel(EigGemmArgs P) {
-    __shared__ double As[64][GSUM_LDH];
-    __shared__ double Bs[64][GSUM_LDH];
+    extern __shared__ __align__(16) double eg_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
@@ -233,42 +248,55 @@ __global__ void __launch_bounds__(128) eig_gemm_kernel(EigGemmArgs P) {
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    for (int64_t k0 = 0; k0 < P.K; k0 += GSUM_KH) {
-        if (P.transA) {
-#pragma unroll 4
-            for (int e = tid; e < 64 * GSUM_KH; e += 128) {
-                const int m = e & 63, k = e >> 6;
-                const int64_t gm = m0 + m, gk = k0 + k;
-                As[m][k] = (gm < P.M && gk < P.K) ? P.A[gk * P.lda + gm] : 0.0;
-            }
-        } else {
-#pragma unroll 4
-            for (int e = tid; e < 64 * GSUM_KH; e += 128) {
-                const int k = e & (GSUM_KH - 1), m = e / GSUM_KH;
-                const int64_t gm = m0 + m, gk = k0 + k;
-                As[m][k] = (gm < P.M && gk < P.K) ? P.A[gm * P.lda + gk] : 0.0;
-            }
-        }
+    auto issue = [&](int stage, int64_t k0) {
+        double *As = eg_smem + (size_t)stage * EG_STAGE, *Bs = As + EG_A_ELEMS, *sub = Bs + EG_B_ELEMS, *inv = sub + GSUM_KH;
 #pragma unroll 4
         for (int e = tid; e < 64 * GSUM_KH; e += 128) {
+            if (P.transA) {
+                const int m = e & 63, k = e >> 6;
+                const int64_t gm = m0 + m, gk = k0 + k;
+                const bool ok = gm < P.M && gk < P.K;
+                cp_async8_zfill(As + k * EG_LDN + m, ok ? P.A + gk * P.lda + gm : P.A, ok ? 8 : 0);
+            } else {
+                const int k = e & (GSUM_KH - 1), m = e / GSUM_KH;
+                const int64_t gm = m0 + m, gk = k0 + k;
+                const bool ok = gm < P.M && gk < P.K;
+                cp_async8_zfill(As + m * GSUM_LDH + k, ok ? P.A + gm * P.lda + gk : P.A, ok ? 8 : 0);
+            }
             const int n = e & 63, k = e >> 6;
             const int64_t gn = n0 + n, gk = k0 + k;
-            double v = 0.0;
-            if (gn < P.N && gk < P.K) {
-                v = P.B[gk * P.ldb + gn];
-                if (P.bsub) v -= P.bsub[gk];
-                if (P.bdiv) v *= 1.0 / P.bdiv[gk];
-            }
-            Bs[n][k] = v;
+            const bool ok = gn < P.N && gk < P.K;
+            cp_async8_zfill(Bs + k * EG_LDN + n, ok ? P.B + gk * P.ldb + gn : P.B, ok ? 8 : 0);
         }
+        if (tid < GSUM_KH) {
+            const int64_t gk = k0 + tid;
+            const bool ok = gk < P.K;
+            sub[tid] = (ok && P.bsub) ? P.bsub[gk] : 0.0;
+            inv[tid] = (ok && P.bdiv) ? 1.0 / P.bdiv[gk] : 1.0;
+        }
+        cp_async_commit();
+    };
+
+    const int64_t nk = (P.K + GSUM_KH - 1) / GSUM_KH;
+    issue(0, 0);
+    for (int64_t it = 0; it < nk; it++) {
+        if (it + 1 < nk) { issue((int)((it + 1) & 1), (it + 1) * GSUM_KH); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncthreads();
+        const double *As = eg_smem + (size_t)(it & 1) * EG_STAGE, *Bs = As + EG_A_ELEMS, *sub = Bs + EG_B_ELEMS, *inv = sub + GSUM_KH;
 #pragma unroll
         for (int kk = 0; kk < GSUM_KH; kk += 4) {
             double a[4], b[4];
+            if (P.transA) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) a[i] = As[wm + 8 * i + g][kk + t];
+                for (int i = 0; i < 4; i++) a[i] = As[(kk + t) * EG_LDN + wm + 8 * i + g];
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) b[j] = Bs[wn + 8 * j + g][kk + t];
+                for (int i = 0; i < 4; i++) a[i] = As[(wm + 8 * i + g) * GSUM_LDH + kk + t];
+            }
+            const double sb = sub[kk + t], iv = inv[kk + t];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = (Bs[(kk + t) * EG_LDN + wn + 8 * j + g] - sb) * iv;
 #pragma unroll
             for (int i = 0; i < 4; i++)
 #pragma unroll

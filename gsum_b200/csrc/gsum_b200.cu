@@ -1448,7 +1448,8 @@ extern "C" int gsum_credible_interval(gsum_ctx *c, const double *Y, int64_t n, i
 
 static void launch_eig_gemm(gsum_ctx *c, const EigGemmArgs &g) {
     dim3 grid((unsigned)((g.N + 63) / 64), (unsigned)((g.M + 63) / 64));
-    eig_gemm_kernel<<<grid, 128, 0, c->stream>>>(g);
+    cudaFuncSetAttribute(eig_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EG_SMEM_BYTES);   // 72.7 KB: two stages
+    eig_gemm_kernel<<<grid, 128, EG_SMEM_BYTES, c->stream>>>(g);
     LAUNCHED(c, 1);
 }
 
