@@ -191,3 +191,34 @@ def test_facade_rejects_out_of_scope_options():
         ConjugateGaussianProcess(RBF(0.2, 'fixed')).predict(np.zeros((2, 1)), return_std=True, return_cov=True)
     with pytest.raises(ValueError):
         ConjugateGaussianProcess(RBF(0.2), df=1).cov(np.zeros((2, 1)))      # df <= 2: covariance does not exist
+
+
+@pytest.mark.parametrize("student", [False, True])
+@pytest.mark.parametrize("prior", [(0, 0, 1, 1), (0.3, 1, 3, 0.7), (0.1, 0, np.inf, 1.3), (-0.2, 0.5, 5, 2.0)])
+def test_conjugate_from_gram_matches_oracle(student, prior):
+    """The host half of the 'eig' route (gsum_b200.models._conjugate_from_gram: posterior and likelihood as quadratic forms
+    in the Gram of R^-1 [1 | y]) against the oracle's step-by-step restatement of the reference (no device involved: the
+    Gram is formed here with numpy)."""
+    from gsum_b200.models import _conjugate_from_gram
+    rs = np.random.RandomState(3)
+    n, nc = 40, 4
+    X = np.linspace(0, 1, n)[:, None]
+    kern = C(1.5, 'fixed') * RBF(0.2, 'fixed') + WhiteKernel(1e-4, 'fixed')
+    y = np.linalg.cholesky(RBF(0.2)(X) + 1e-6 * np.eye(n)) @ rs.randn(n, nc) + 0.2
+    R = kern(X) + 1e-10 * np.eye(n)
+    rhs = np.concatenate([np.ones((n, 1)), y], axis=1)
+    G = rhs.T @ np.linalg.solve(R, rhs)
+    logdet = np.linalg.slogdet(R)[1]
+    center, disp, df, scale = prior
+    pri = dict(center0=float(center), disp0=float(disp), df0=float(df), scale0=float(scale))
+    got = _conjugate_from_gram(0.5 * (G + G.T), logdet, n, nc, pri, student)
+    p = o.Priors(center, disp, df, scale)
+    f = o.fit_conjugate(kern, X, y, p, nugget=1e-10, student=student)
+    want = dict(center=f["center"][0], disp=f["disp"][0, 0], df=f["df"], scale_sq=f["scale"] ** 2, cov_factor=f["cov_factor"], lml=f["lml"])
+    for key, w in want.items():
+        if np.isnan(w):
+            assert np.isnan(got[key]), key
+        elif w == 0 or np.isinf(w):
+            assert got[key] == w, key
+        else:
+            assert abs(got[key] - w) <= 1e-9 * abs(w), (key, got[key], w)

@@ -9,8 +9,8 @@ cap() {  # name, kernel regex, launches to skip
   ncu -i "/tmp/eig_$1.ncu-rep" --page raw --csv > "gpurun_out/eig_$1.csv" 2>/dev/null || echo "export $1 failed"
 }
 python tools/ncu_targets.py eig > gpurun_out/eig_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/eig_plain.log; exit 1; }
-cap jacobi_early  '^jacobi_round_kernel'  500
-cap jacobi_late   '^jacobi_round_kernel'  15000
+cap jacobi_early  '^jacobi_round'  500
+cap jacobi_late   '^jacobi_round'  15000
 cap gemm_vt_y     '^eig_gemm_kernel'      0
 cap gemm_v_t      '^eig_gemm_kernel'      1
 cap gemm_cov      '^eig_gemm_kernel'      5
