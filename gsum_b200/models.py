@@ -860,9 +860,14 @@ class TruncationProcess:
             detf = np.sum(n_c * np.log(np.abs(ref))) + so * np.sum(np.log(np.abs(Q)), axis=1)
             xdep = True
         if cp._eig_route():
+            detf_q = np.broadcast_to(detf, (Q.shape[0],))
             if group is not None:
-                raise NotImplementedError("gsum_b200: the sharded grid runs the Cholesky kernel; decomposition='eig' is single-GPU")
-            ll = self._lml_grid_eig(X, dy, ref, orders_in, ls, Q, xdep, np.broadcast_to(detf, (Q.shape[0],)), k)
+                # same sharding as the Cholesky grid: length scales dealt round-robin, one all-gather
+                from .distributed import lml_grid_sharded
+                return lml_grid_sharded(X, dy, ref, orders_in, ls, Q, group=group,
+                                        _evaluator=lambda X_, dy_, ref_, o_, ls_, Q_, **_kw:
+                                        self._lml_grid_eig(X_, dy_, ref_, o_, ls_, Q_, xdep, detf_q, k))
+            ll = self._lml_grid_eig(X, dy, ref, orders_in, ls, Q, xdep, detf_q, k)
             return (ll, np.zeros(ls.shape[0], dtype=np.int32)) if return_status else ll
         kw = dict(q_x_dependent=xdep, detf=detf, constant=k.constant, noise=k.noise, nugget=cp.nugget, student=cp._student,
                   **cp._priors())

@@ -293,3 +293,27 @@ def test_eig_route_fit_with_free_length_scale(ctx):
     la, lb = np.exp(a.kernel_.theta[0]), np.exp(b.kernel_.theta[0])
     assert 0.1 < la < 0.3 and abs(la - lb) < 1e-4 * lb
     assert relerr(np.array(a.log_marginal_likelihood_value_), np.array(b.log_marginal_likelihood_value_)) < 1e-7
+
+
+def test_eig_route_grid_sharded_nccl_single_rank(ctx, golden):
+    """The 'eig' grid through the sharded path (length scales dealt over the ranks, one all-gather) on a one-rank NCCL
+    group: identical to the plain call."""
+    import os
+    import torch
+    import torch.distributed as dist
+    g = golden("eig_route")
+    tgp = gb.TruncationGP(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1,
+                          optimizer=None, decomposition='eig').fit(g["Xt"], g["yt"], orders=g["orders"])
+    want = tgp.log_marginal_likelihood_grid(g["ls_vals"], g["q_vals"])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", str(29900 + os.getpid() % 90))
+    torch.cuda.set_device(0)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", rank=0, world_size=1)
+    try:
+        got = tgp.log_marginal_likelihood_grid(g["ls_vals"], g["q_vals"], group=dist.group.WORLD)
+    finally:
+        if created:
+            dist.destroy_process_group()
+    assert np.array_equal(got, want)
