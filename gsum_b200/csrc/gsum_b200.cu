@@ -1565,6 +1565,8 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     std::vector<int32_t> perm(n);
     GSUM_CUDA(c, cudaMemcpyAsync(hw.data(), dw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
     GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < n; i++)
+        if (!std::isfinite(hw[i])) return gsum_fail(c, 1, "gsum_eigh: non-finite eigenvalue (NaN or Inf in the input matrix)");
     std::iota(perm.begin(), perm.end(), 0);
     std::stable_sort(perm.begin(), perm.end(), [&](int32_t a, int32_t b) { return hw[a] < hw[b]; });
     for (int64_t i = 0; i < n; i++) hs[i] = hw[perm[i]];

@@ -93,6 +93,10 @@ def test_eigh_indefinite_and_repeated(ctx):
     w, V = ops.eigh(A)
     assert np.max(np.abs(w - np.sort(lam))) < 1e-13 * 5
     assert np.max(np.abs(A @ V - V * w[None, :])) < 1e-13 * 5 * 10
+    # non-finite input is reported (numpy raises LinAlgError as well)
+    C_ = A.copy(); C_[3, 4] = C_[4, 3] = np.nan
+    with pytest.raises(np.linalg.LinAlgError):
+        ops.eigh(C_)
     # a +lambda / -lambda pair is outside the solver's scope and is reported, not mis-solved
     lam[-1] = 2.0
     B = (Q * lam[None, :]) @ Q.T
