@@ -237,6 +237,18 @@ def measure_fp64_peak(torch, n=4096, reps=6):
     return 2.0 * n ** 3 / best * 1e-9
 
 
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    """Write the result line to the process' original stdout (see run_ours)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(line, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (line + "\n").encode())
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -245,7 +257,13 @@ def run_ours(args, rank, world, local_rank):
     from gsum_b200 import _lib, ops
     from gsum_b200.helpers import _order_differences
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("GSUM_NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout (one JSON line)
+    os.environ["NCCL_DEBUG"] = os.environ.get("GSUM_NCCL_DEBUG", "WARN")
+    # NCCL prints its version banner on the C-level stdout at WARN: the process' fd 1 is pointed at stderr for the whole
+    # run and the ONE JSON line goes to a saved duplicate of the real stdout (_emit)
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -383,7 +401,7 @@ def run_ours(args, rank, world, local_rank):
                                              "sample": f"{len(serial_cells)} cells, {serial_s:.1f} s"}},
             "clocks": clocks, "parity_spot_check_rel": parity,
         }
-        print(json.dumps(out), flush=True)
+        _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
