@@ -3,9 +3,10 @@
 Same class names, constructor arguments, methods, fitted attributes and error behaviour as the
 reference on the hot path, but every linear-algebra step (kernel matrix, Cholesky, triangular solves,
 conjugate updates, likelihood, posterior moments) is one call into the C ABI / CUDA library — the
-Python here only marshals arguments.  What the device path does not cover raises NotImplementedError
-(`decomposition='eig'`, custom `basis`, analytic gradients, kernels other than [Constant*]RBF[+White]);
-nothing falls back to numpy/scipy.
+Python here only marshals arguments and evaluates the O(n_c^2) closed forms of the gradient / 'eig' routes on the
+small Gram matrices the device returns.  What the device path does not cover raises NotImplementedError
+(custom `basis`, kernels other than [Constant*]RBF[+White]); nothing falls back to numpy/scipy.
+`decomposition='eig'` runs on the device Jacobi eigensolver (csrc/eig.cuh).
 
 New, additive: ``TruncationProcess.log_marginal_likelihood_grid`` evaluates the whole (Q, l) grid of
 docs/notebooks/correlated_EFT_publication.ipynb cell 53 in one device call (optionally sharded over the
