@@ -37,6 +37,23 @@ __device__ __forceinline__ void jacobi_pair(int np, int r, int k, int &p, int &q
     if (p > q) { int t = p; p = q; q = t; }
 }
 
+// Pair of one CTA in one round.  order == nullptr: round-robin tournament over np indices (np / 2 CTAs, np - 1 rounds).
+// order != nullptr: MODULUS ordering on SORTED positions — round s pairs the positions (i, j) with i + j = s (mod n), i < j
+// (n CTAs, one per position i, half of them idle; n rounds), and order[] maps a position to its row, rows ranked by
+// decreasing norm at the start of the sweep.  Emulated in numpy on RBF + 1e-4 I at N = 512 (profiles/r01_notes.md): strict
+// relative criterion, iteration on the pivoted-Cholesky factor: round-robin 18 sweeps, modulus 16, modulus + sorted
+// positions 13; iteration on A: 24 / 24 / 17.
+__device__ __forceinline__ bool jacobi_select(int n, int np, int round, const int32_t *__restrict__ order, int &p, int &q) {
+    if (order) {
+        const int i = blockIdx.x, j = (round - i + n) % n;
+        if (i >= j) return false;
+        p = order[i]; q = order[j];
+        return true;
+    }
+    jacobi_pair(np, round, blockIdx.x, p, q);
+    return q < n;                                         // the padding index of an odd n sits this round out
+}
+
 // G <- A (n x n, leading dimension ld), Vt <- I
 __global__ void __launch_bounds__(256) jacobi_init_kernel(const double *__restrict__ A, double *__restrict__ G, double *__restrict__ Vt,
                                                           int n, int64_t ld) {
@@ -49,11 +66,10 @@ __global__ void __launch_bounds__(256) jacobi_init_kernel(const double *__restri
 
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(double *__restrict__ G, double *__restrict__ Vt, int n, int64_t ld, int np,
                                                                    int round, double tol, double tol_abs, double tol_gamma,
-                                                                   unsigned int *__restrict__ rotations) {
+                                                                   unsigned int *__restrict__ rotations, const int32_t *__restrict__ order) {
     __shared__ double red[3][JAC_THREADS / 32];
     int p, q;
-    jacobi_pair(np, round, blockIdx.x, p, q);
-    if (q >= n) return;                                   // the padding index of an odd n sits this round out
+    if (!jacobi_select(n, np, round, order, p, q)) return;
     double *gp = G + p * ld, *gq = G + q * ld;
     double a = 0.0, b = 0.0, g = 0.0;
     for (int i = threadIdx.x; i < n; i += JAC_THREADS) {
@@ -102,11 +118,10 @@ __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_kernel(double *__res
 template <int EPT>
 __global__ void __launch_bounds__(JAC_THREADS) jacobi_round_reg_kernel(double *__restrict__ G, double *__restrict__ Vt, int n, int64_t ld, int np,
                                                                        int round, double tol, double tol_abs, double tol_gamma,
-                                                                       unsigned int *__restrict__ rotations) {
+                                                                       unsigned int *__restrict__ rotations, const int32_t *__restrict__ order) {
     __shared__ double red[3][JAC_THREADS / 32];
     int p, q;
-    jacobi_pair(np, round, blockIdx.x, p, q);
-    if (q >= n) return;
+    if (!jacobi_select(n, np, round, order, p, q)) return;
     double *gp = G + p * ld, *gq = G + q * ld;
     double x[EPT], y[EPT], u[EPT], v[EPT];
 #pragma unroll

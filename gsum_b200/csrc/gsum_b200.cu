@@ -1499,6 +1499,7 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     if (const char *e = getenv("GSUM_B200_EIGH_ABS")) tol_abs = atof(e) * eps * sqrt(fro2);
     if (factor_mode) {
         tol_gamma = getenv("GSUM_B200_EIGH_ABS") ? tol_abs : 0.01 * eps * sqrt(fro2);      // c = 0.01: best measured trade (eig.cuh)
+        if (getenv("GSUM_B200_EIGH_STRICT")) tol_gamma = 0.0;                               // relative criterion only
         tol_abs = 0.0;
         jacobi_init_factor_kernel<<<gt, 256, 0, c->stream>>>((const double *)dGp, n, (double *)dG, ni, ld);
         LAUNCHED(c, 1);
@@ -1507,7 +1508,6 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     // One sweep = n - 1 dependent launches of a few microseconds each: launch-bound, so the sweep is captured once as a
     // CUDA graph (counter reset + the rounds) and replayed until a sweep makes no rotation.
     const bool trace = getenv("GSUM_B200_EIGH_TRACE") != nullptr;      // rotations per sweep on stderr
-    const int rounds = np - 1;
     int sweeps = 0;
     bool converged = (n == 1);
     cudaGraph_t graph = nullptr;
@@ -1515,17 +1515,34 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     // register-resident round for n <= 1024 (G and V^T sit in L2 and the round is latency-bound: 99 -> 89 ms at
     // N = 1024); beyond, its unconditional fetch of the V^T rows costs more than the second pass it saves
     // (measured: N = 2048 385 -> 1548 ms), so the two-pass kernel stays
-    void (*round_fn)(double *, double *, int, int64_t, int, int, double, double, double, unsigned int *) = jacobi_round_kernel;
+    void (*round_fn)(double *, double *, int, int64_t, int, int, double, double, double, unsigned int *, const int32_t *) = jacobi_round_kernel;
     if (!getenv("GSUM_B200_EIGH_TWOPASS")) {
         if (ni <= 1 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<1>;
         else if (ni <= 2 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<2>;
         else if (ni <= 4 * JAC_THREADS) round_fn = jacobi_round_reg_kernel<4>;
     }
+    // GSUM_B200_EIGH_ORDER=modulus: modulus ordering on positions sorted by decreasing row norm (eig.cuh, jacobi_select);
+    // the ranking is refreshed on the host before every sweep (one row-norm kernel, n doubles down, n ints up)
+    const bool modulus = getenv("GSUM_B200_EIGH_ORDER") && !strcmp(getenv("GSUM_B200_EIGH_ORDER"), "modulus");
+    void *dorder = nullptr;
+    std::vector<int32_t> horder(n);
+    if (modulus) GSUM_TRY(gsum_ws(c, WS_Q, sizeof(int32_t) * n, &dorder));
+    const int rounds_sweep = modulus ? ni : np - 1, ctas = modulus ? ni : np / 2;
     auto enqueue_sweep = [&]() {
         cudaMemsetAsync(dcnt, 0, sizeof(unsigned int), c->stream);
-        for (int r = 0; r < np - 1; r++)
-            round_fn<<<np / 2, JAC_THREADS, 0, c->stream>>>((double *)dG, dVt_it, ni, ld, np, r, tol, tol_abs, tol_gamma,
-                                                           (unsigned int *)dcnt);
+        for (int r = 0; r < rounds_sweep; r++)
+            round_fn<<<ctas, JAC_THREADS, 0, c->stream>>>((double *)dG, dVt_it, ni, ld, np, r, tol, tol_abs, tol_gamma,
+                                                         (unsigned int *)dcnt, (const int32_t *)dorder);
+    };
+    auto refresh_order = [&]() -> int {
+        rows_sqnorm_kernel<<<(unsigned)((n + 7) / 8), 256, 0, c->stream>>>((const double *)dG, ld, n, n, (double *)dw);
+        LAUNCHED(c, 1);
+        GSUM_CUDA(c, cudaMemcpyAsync(hw.data(), dw, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        std::iota(horder.begin(), horder.end(), 0);
+        std::stable_sort(horder.begin(), horder.end(), [&](int32_t a, int32_t b) { return hw[a] > hw[b]; });
+        GSUM_CUDA(c, cudaMemcpyAsync(dorder, horder.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, c->stream));
+        return 0;
     };
     // a caller-provided stream may not be capturable (legacy default stream): plain launches then
     if (!converged && !getenv("GSUM_B200_EIGH_NOGRAPH") &&
@@ -1540,11 +1557,12 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     int rc_loop = 0;
     while (!converged && sweeps < JAC_MAX_SWEEPS) {
         unsigned int rot = 0;
+        if (modulus) GSUM_TRY(refresh_order());
         if (gexec) { if (cudaGraphLaunch(gexec, c->stream) != cudaSuccess) { rc_loop = -100; break; } }
         else enqueue_sweep();
         if (cudaMemcpyAsync(&rot, dcnt, sizeof(rot), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
             cudaStreamSynchronize(c->stream) != cudaSuccess) { rc_loop = -100; break; }
-        LAUNCHED(c, rounds);
+        LAUNCHED(c, rounds_sweep);
         if (trace) fprintf(stderr, "[gsum_eigh] n=%d sweep %d: %u rotations\n", ni, sweeps, rot);
         sweeps++;
         converged = (rot == 0);
