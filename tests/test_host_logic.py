@@ -222,3 +222,82 @@ def test_conjugate_from_gram_matches_oracle(student, prior):
             assert got[key] == w, key
         else:
             assert abs(got[key] - w) <= 1e-9 * abs(w), (key, got[key], w)
+
+
+class _NumpyEigen:
+    """Test stand-in for ops.ResidentEigen (numpy `eigh`): lets the HOST half of the 'eig' route — Gram assembly, closed
+    forms, conditioning algebra, the per-length-scale reuse of the grid — run without a device."""
+
+    def __init__(self, A, ctx=None):
+        self.w, self.V = np.linalg.eigh(A)
+        self.sweeps = 0
+
+    def solve(self, Y, mean=None, mode=0):
+        Y = np.asarray(Y, dtype=float)
+        vec = Y.ndim == 1
+        Y2 = Y[:, None] if vec else Y
+        if mean is not None:
+            Y2 = Y2 - mean[:, None]
+        T = self.V.T @ Y2
+        X = self.V @ (T / self.w[:, None]) if mode == 0 else T / np.sqrt(self.w)[:, None]
+        return X[:, 0] if vec else X
+
+    def conditional(self, R_on, D=None, want_var=False, want_cov=False):
+        U = self.V.T @ R_on
+        lin = U.T @ ((self.V.T @ D) / self.w[:, None]) if D is not None else None
+        cov = U.T @ (U / self.w[:, None])
+        return lin, (np.diag(cov).copy() if want_var else None), (cov if want_cov else None)
+
+
+def _numpy_kernel_matrix(X1, X2, ls, constant=1.0, noise=0.0, ctx=None):
+    X1, ls = np.atleast_2d(X1), np.atleast_1d(ls)
+    k = RBF(ls if len(ls) > 1 else ls[0])
+    if X2 is None:
+        return constant * k(X1) + noise * np.eye(len(X1))
+    return constant * k(X1, np.atleast_2d(X2))
+
+
+@pytest.mark.parametrize("tag", ["g", "t"])
+def test_eig_route_host_logic_against_reference_golden(monkeypatch, golden, tag):
+    """fit / likelihood / predict / grid of the facade's 'eig' route with the two device calls replaced by numpy stand-ins,
+    against the golden vectors of the real reference (the device kernels themselves are covered by tests/test_gpu_eig.py)."""
+    import gsum_b200 as gb
+    from gsum_b200 import ops
+    from util import prior_kwargs
+    monkeypatch.setattr(ops, "kernel_matrix", _numpy_kernel_matrix)
+    monkeypatch.setattr(ops, "ResidentEigen", _NumpyEigen)
+    g = golden("eig_route")
+    cls = gb.ConjugateGaussianProcess if tag == "g" else gb.ConjugateStudentProcess
+    for ip in range(3):
+        pri = prior_kwargs(g["priors"][ip])
+        kern = C(1.5, 'fixed') * RBF(0.2, 'fixed') + WhiteKernel(1e-4, 'fixed')
+        gp = cls(kern, nugget=1e-10, decomposition='eig', **pri).fit(g["X"], g["y"])
+        post = np.array([gp.center_[0], gp.disp_[0, 0], gp.df_, gp.scale_, gp.cov_factor_])
+        want = g[f"{tag}{ip}_post"]
+        ok = np.isfinite(want) & (want != 0)
+        assert np.array_equal(np.isnan(post), np.isnan(want)) and np.max(np.abs(post[ok] - want[ok]) / np.abs(want[ok])) < 1e-9
+        kfree = C(1.5, 'fixed') * RBF(0.2) + WhiteKernel(1e-4, 'fixed')
+        gpf = cls(kfree, nugget=1e-10, optimizer=None, decomposition='eig', **pri).fit(g["X"], g["y"])
+        lml = np.array([gpf.log_marginal_likelihood(theta=[t]) for t in g["thetas"]])
+        wl = g[f"{tag}{ip}_lml"]
+        assert np.array_equal(np.isnan(lml), np.isnan(wl))
+        if np.isfinite(wl).all():
+            assert relerr(lml, wl) < 1e-9
+        if f"{tag}{ip}_mean" in g:
+            m, s = gp.predict(g["Xn"], return_std=True)
+            assert relerr(m, g[f"{tag}{ip}_mean"]) < 1e-9 and relerr(s, g[f"{tag}{ip}_std"]) < 1e-6
+            _, cv = gp.predict(g["Xn"][::4], return_cov=True, pred_noise=True)
+            assert relerr(cv, g[f"{tag}{ip}_cov"]) < 2e-6
+            m, s = gp.predict(g["Xn"], return_std=True, Xc=g["Xc"], y=g["yc"])
+            assert relerr(m, g[f"{tag}{ip}_mean_c"]) < 1e-9 and relerr(s, g[f"{tag}{ip}_std_c"]) < 1e-6
+    if tag == "g":
+        tgp = gb.TruncationGP(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1,
+                              optimizer=None, decomposition='eig').fit(g["Xt"], g["yt"], orders=g["orders"])
+        grid = tgp.log_marginal_likelihood_grid(g["ls_vals"], g["q_vals"])
+        assert relerr(grid, g["t_ll"]) < 1e-7
+        cell = tgp.log_marginal_likelihood(theta=[np.log(g["ls_vals"][1])], ratio=g["q_vals"][2])
+        assert abs(cell - g["t_ll"][2, 1]) < 1e-7 * abs(g["t_ll"][2, 1])
+        tq = gb.TruncationGP(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=lambda X, q=0.5: q * np.ones(len(X)), ref=1, center=0,
+                             disp=0, df=1, scale=1, optimizer=None, decomposition='eig').fit(g["Xt"], g["yt"], orders=g["orders"])
+        gx = tq.log_marginal_likelihood_grid(g["ls_vals"], ratio_kws_list=[dict(q=q) for q in g["q_vals"]])
+        assert relerr(gx, g["t_ll"]) < 1e-7
