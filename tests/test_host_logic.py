@@ -301,3 +301,33 @@ def test_eig_route_host_logic_against_reference_golden(monkeypatch, golden, tag)
                              disp=0, df=1, scale=1, optimizer=None, decomposition='eig').fit(g["Xt"], g["yt"], orders=g["orders"])
         gx = tq.log_marginal_likelihood_grid(g["ls_vals"], ratio_kws_list=[dict(q=q) for q in g["q_vals"]])
         assert relerr(gx, g["t_ll"]) < 1e-7
+
+
+def _jacobi_pair(np_, r, k):
+    """Python mirror of `jacobi_pair` in gsum_b200/csrc/eig.cuh (round-robin / circle method)."""
+    m = np_ - 1
+    p, q = (m, r) if k == 0 else ((r + k) % m, (r - k + m) % m)
+    return (p, q) if p < q else (q, p)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 7, 16, 33])
+def test_jacobi_schedules_cover_every_pair_once_with_disjoint_rounds(n):
+    """The two pair schedules of gsum_eigh (eig.cuh: round-robin tournament; `jacobi_select`'s modulus ordering i + j = s
+    mod n): every round's pairs are disjoint (CTAs of one launch never share a row) and a sweep visits each pair once."""
+    want = {(i, j) for i in range(n) for j in range(i + 1, n)}
+    np_ = n + (n & 1)
+    seen = []
+    for r in range(np_ - 1):
+        pairs = [_jacobi_pair(np_, r, k) for k in range(np_ // 2)]
+        pairs = [pq for pq in pairs if pq[1] < n]                     # the padding index of an odd n sits out
+        flat = [x for pq in pairs for x in pq]
+        assert len(flat) == len(set(flat))
+        seen += pairs
+    assert sorted(seen) == sorted(want)
+    seen = []
+    for s in range(n):
+        pairs = [(i, (s - i + n) % n) for i in range(n) if i < (s - i + n) % n]
+        flat = [x for pq in pairs for x in pq]
+        assert len(flat) == len(set(flat))
+        seen += pairs
+    assert sorted(seen) == sorted(want)
