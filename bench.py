@@ -2,10 +2,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-A step is one pass of the hot path over one grid: 128 length scales x 256 expansion parameters per GPU (config C4;
-weak scaling: with N GPUs the grid has 128*N length scales, dealt round-robin, one all-gather of the FP64 blocks and an
-on-device max-shift normalisation per step).  `value` times the device-resident call with CUDA events; `e2e` times the
-public API (TruncationGP.log_marginal_likelihood_grid) with host buffers in and out.  One JSON line on stdout.
+A step is one pass of the hot path over THE grid BASELINE.json names (configs[3]): 128 length scales x 256 expansion
+parameters at N = 1024, 6 orders.  With N GPUs that fixed grid is sharded (strong scaling): the 128 length scales are dealt
+round-robin, 128/N per rank, one all-gather of the FP64 blocks and an on-device max-shift normalisation per step.  `value`
+times the device-resident call with CUDA events; `e2e` times the public API (TruncationGP.log_marginal_likelihood_grid) with
+host buffers in and out.  The weak-scaling figure (128 length scales PER GPU) is reported beside it under "weak".  One JSON
+line on stdout.
 """
 import argparse
 import json
@@ -20,9 +22,13 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_POINTS, N_ORDERS, N_LS_PER_GPU, N_Q = 1024, 6, 128, 256
+N_POINTS, N_ORDERS, N_LS, N_Q = 1024, 6, 128, 256
+N_LS_PER_GPU = N_LS                                  # the weak-scaling side figure
 METRIC = "(l,Q) grid log-likelihood evals/sec at N=1024, 6 orders"
-NCU_TRAFFIC_BYTES = 4.518408e9 + 660.972288e6      # profiles/r01_ncu_hetero_tma.txt
+WORKLOAD = "C4: N=1024, 6 orders, 128 l x 256 Q grid (configs[3] of BASELINE.json), length scales sharded over the GPUs"
+# DRAM bytes of ONE factorisation launch at 128 length scales, recorded from an `ncu --set full` capture (not measured in
+# this run): {profile file: dram__bytes_read.sum + dram__bytes_write.sum}
+NCU_TRAFFIC = {"file": "profiles/r01_ncu_hetero_tma.txt", "bytes": 4.518408e9 + 660.972288e6, "n_ls": 128}
 
 
 def make_inputs(n_ls):
@@ -103,18 +109,29 @@ def cpu_reference_cells(X, y, orders, ls_vals, q_vals, cells):
 _W = {}
 
 
+_ONE_THREAD_ENV = ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS", "VECLIB_MAXIMUM_THREADS")
+
+
 def _cpu_worker_init(n_ls):
-    try:
-        from threadpoolctl import threadpool_limits
-        _W["limit"] = threadpool_limits(limits=1)
-    except Exception:
-        pass
+    # the parent exported *_NUM_THREADS=1 before the spawn; import everything that owns a thread pool FIRST, then limit
+    # whatever is loaded and verify that every pool really is at one thread (one worker process per core)
+    import scipy.linalg  # noqa: F401
+    import sklearn.gaussian_process.kernels  # noqa: F401
+    from oracle import gsum_oracle  # noqa: F401
     _W["inputs"] = make_inputs(n_ls)
+    from threadpoolctl import threadpool_limits, threadpool_info
+    _W["limit"] = threadpool_limits(limits=1)
+    _W["pools"] = [int(p.get("num_threads", 1)) for p in threadpool_info()]
+    assert all(t == 1 for t in _W["pools"]), f"CPU worker BLAS pools not limited to one thread: {_W['pools']}"
 
 
 def _cpu_worker_cells(cells):
     X, y, orders, ls_vals, q_vals = _W["inputs"]
     return cpu_reference_cells(X, y, orders, ls_vals, q_vals, cells)[1]
+
+
+def _cpu_worker_pools(_):
+    return _W.get("pools", [])
 
 
 class CellPool:
@@ -124,8 +141,20 @@ class CellPool:
     def __init__(self, n_ls, workers):
         import multiprocessing as mp
         self.workers = workers
-        self.pool = mp.get_context("spawn").Pool(workers, initializer=_cpu_worker_init, initargs=(n_ls,))
-        self.pool.map(_cpu_worker_cells, [[(0, 0)]] * workers)           # imports, inputs and one warm cell per worker
+        saved = {k: os.environ.get(k) for k in _ONE_THREAD_ENV}
+        os.environ.update({k: "1" for k in _ONE_THREAD_ENV})             # inherited by the spawned workers
+        try:
+            self.pool = mp.get_context("spawn").Pool(workers, initializer=_cpu_worker_init, initargs=(n_ls,))
+            self.pool.map(_cpu_worker_cells, [[(0, 0)]] * workers)       # imports, inputs and one warm cell per worker
+            pools = self.pool.map(_cpu_worker_pools, range(workers))
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        self.blas_threads_per_worker = max([t for p in pools for t in p] + [1])
+        assert self.blas_threads_per_worker == 1
 
     def run(self, cells):
         chunks = [cells[i::self.workers] for i in range(self.workers) if cells[i::self.workers]]
@@ -182,17 +211,23 @@ class best_blas_setting:
             self.ctx.__exit__(*a)
 
 
+def base_config(world):
+    return {"workload": WORKLOAD, "n_points": N_POINTS, "n_orders": N_ORDERS, "n_ls": N_LS, "n_q": N_Q,
+            "n_ls_per_gpu": N_LS // world, "grid_cells_per_step": N_LS * N_Q}
+
+
 def run_reference(args, rank, world):
-    """The reference algorithm alone on the host cores.  `value` is the cell-parallel arm (one process per core); the serial
-    loop of the notebook (one cell after the other, BLAS threads at their best setting) is reported beside it."""
+    """The reference algorithm alone on the host cores (rank 0 only; the other ranks exit without work).  `value` is the
+    cell-parallel arm (one process per core, one BLAS thread each — verified inside the workers); the serial loop of the
+    notebook (one cell after the other, BLAS threads at their best setting) is reported beside it."""
     if rank != 0:
         return
-    X, y, orders, ls_vals, q_vals = make_inputs(N_LS_PER_GPU)
+    X, y, orders, ls_vals, q_vals = make_inputs(N_LS)
     workers = os.cpu_count() or 1
     per_step = 2 * workers                                        # cells per step: two per core (~0.1-0.2 s of wall time)
     k = int(np.ceil(np.sqrt(per_step)))
-    cells = stratified_cells(N_Q, N_LS_PER_GPU, k)[:per_step]
-    pool = CellPool(N_LS_PER_GPU, workers)
+    cells = stratified_cells(N_Q, N_LS, k)[:per_step]
+    pool = CellPool(N_LS, workers)
     try:
         for _ in range(args.warmup):
             pool.run(cells[:workers])
@@ -203,17 +238,16 @@ def run_reference(args, rank, world):
     finally:
         pool.close()
     value = len(cells) * args.steps / total
-    serial_cells = stratified_cells(N_Q, N_LS_PER_GPU, 3)[:8]
+    serial_cells = stratified_cells(N_Q, N_LS, 3)[:8]
     with best_blas_setting(lambda: cpu_reference_cells(X, y, orders, ls_vals, q_vals, serial_cells[:4])[0]) as blas:
         dt_serial, _ = cpu_reference_cells(X, y, orders, ls_vals, q_vals, serial_cells)
-    sample = (f"{len(cells)} cells/step of the 256x128 grid (stratified), {args.steps} steps, {workers} worker processes x 1 BLAS thread; "
-              f"one Cholesky + 4 cho_solve per cell as in the reference")
+    sample = (f"{len(cells)} cells/step of the 256x128 grid (stratified), {args.steps} steps, {workers} worker processes x "
+              f"{pool.blas_threads_per_worker} BLAS thread (threadpool_info checked in every worker); one Cholesky + 4 cho_solve per "
+              f"cell as in the reference")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C4: N=1024, 6 orders, 128 l x 256 Q per GPU (CPU arm: bounded sample of cells)", "n_points": N_POINTS,
-                   "n_orders": N_ORDERS, "n_ls_per_gpu": N_LS_PER_GPU, "n_q": N_Q},
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": base_config(max(args.gpus, 1)),
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": workers, "kind": "port", "sample": sample,
                          "host_cpus": os.cpu_count(),
                          "serial_loop": {"value": len(serial_cells) / dt_serial, "unit": "evals/s", "blas_threads": blas.threads,
@@ -249,17 +283,50 @@ def _emit(line):
         os.write(_REAL_STDOUT, (line + "\n").encode())
 
 
+class DeviceGrid:
+    """Device-resident inputs and outputs of this rank's share of an (n_ls_total x N_Q) grid: one `step()` = K1..K4 on the
+    rank's length scales, the all-gather of the blocks and the on-device normalisation."""
+
+    def __init__(self, torch, dist, ctx, dev, rank, world, n_ls_total):
+        from gsum_b200 import ops
+        from gsum_b200.helpers import _order_differences
+        self.torch, self.dist, self.ops, self.ctx, self.world = torch, dist, ops, ctx, world
+        self.inputs = make_inputs(n_ls_total)
+        X, y, orders, ls_vals, q_vals = self.inputs
+        self.mine = np.arange(rank, n_ls_total, world)
+        self.dy = np.ascontiguousarray(_order_differences(y))
+        detf = N_POINTS * float(orders.sum()) * np.log(np.abs(q_vals))
+        t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+        self.dX, self.ddy, self.dref, self.dord = t(X), t(self.dy), t(np.ones(N_POINTS)), t(orders.astype(np.int32), torch.int32)
+        self.dls, self.dQ, self.ddetf = t(ls_vals[self.mine][:, None]), t(q_vals), t(detf)
+        self.ll_block = torch.empty((N_Q, len(self.mine)), dtype=torch.float64, device=dev)
+        self.gathered = torch.empty((world * N_Q, len(self.mine)), dtype=torch.float64, device=dev)
+        self.post = torch.empty_like(self.gathered)
+        self.lse = torch.empty(1, dtype=torch.float64, device=dev)
+        self.kw = dict(constant=1.0, noise=1e-6, nugget=1e-10, center0=0.0, disp0=0.0, df0=1.0, scale0=1.0)
+
+    def step(self):
+        self.ops.lml_grid_device(self.ctx, self.dX, self.ddy, self.dref, self.dord, self.dls, self.dQ, self.ddetf, self.ll_block, **self.kw)
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered, self.ll_block)
+            self.ops.grid_normalize_device(self.ctx, self.gathered, self.post, self.lse)
+        else:
+            self.ops.grid_normalize_device(self.ctx, self.ll_block, self.post, self.lse)
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from sklearn.gaussian_process.kernels import RBF, WhiteKernel
     import gsum_b200 as gb
-    from gsum_b200 import _lib, ops
-    from gsum_b200.helpers import _order_differences
+    from gsum_b200 import _lib
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("GSUM_NCCL_DEBUG", "WARN")
-    # NCCL prints its version banner on the C-level stdout at WARN: the process' fd 1 is pointed at stderr for the whole
-    # run and the ONE JSON line goes to a saved duplicate of the real stdout (_emit)
+    if N_LS % world:
+        raise SystemExit(f"--gpus must divide {N_LS}")
+    # NCCL's communicator lines stay visible (INFO unless the caller chose otherwise).  NCCL logs on the C-level stdout, so
+    # the process' fd 1 is pointed at stderr for the whole run and the ONE JSON line goes to a saved duplicate of the real
+    # stdout (_emit): the log is on stderr, the result line alone on stdout.
+    os.environ.setdefault("NCCL_DEBUG", "INFO")
     global _REAL_STDOUT
     sys.stdout.flush()
     _REAL_STDOUT = os.dup(1)
@@ -268,69 +335,73 @@ def run_ours(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_ls_total = N_LS_PER_GPU * world
-    X, y, orders, ls_vals, q_vals = make_inputs(n_ls_total)
-    mine = np.arange(rank, n_ls_total, world)
     stream = torch.cuda.Stream(device=dev)                     # one non-default stream for torch, NCCL and the library
     torch.cuda.set_stream(stream)
     ctx = _lib.Context(local_rank, stream.cuda_stream)         # library work is enqueued on torch's current stream
     assert stream.cuda_stream != 0
-
-    # ---- device-resident inputs (the `value` arm) ----
-    dy = np.ascontiguousarray(_order_differences(y))
-    detf = N_POINTS * float(orders.sum()) * np.log(np.abs(q_vals))
-    t = lambda a, dt=torch.float64: torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
-    dX, ddy, dref, dord = t(X), t(dy), t(np.ones(N_POINTS)), t(orders.astype(np.int32), torch.int32)
-    dls, dQ, ddetf = t(ls_vals[mine][:, None]), t(q_vals), t(detf)
-    ll_block = torch.empty((N_Q, len(mine)), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world * N_Q, len(mine)), dtype=torch.float64, device=dev)
-    post = torch.empty_like(gathered)
-    lse = torch.empty(1, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    kw = dict(constant=1.0, noise=1e-6, nugget=1e-10, center0=0.0, disp0=0.0, df0=1.0, scale0=1.0)
-
-    def step_device():
-        ops.lml_grid_device(ctx, dX, ddy, dref, dord, dls, dQ, ddetf, ll_block, **kw)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, ll_block)
-            ops.grid_normalize_device(ctx, gathered, post, lse)
-        else:
-            ops.grid_normalize_device(ctx, ll_block, post, lse)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_max_sum(vals):
+        tt = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world == 1:
+            return list(vals), list(vals)
+        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        return [float(v) for v in mx], [float(v) for v in sm]
+
+    def time_device(grid, steps, warmup, sampler=None):
+        """`steps` device-resident steps, each bracketed by CUDA events on the launch stream, L2 flushed before each (untimed);
+        returns (ms summed over the steps: max over ranks, launches: sum over ranks, this rank's factorisation bracket)."""
+        for _ in range(warmup):
+            grid.step()
+        barrier()
+        ctx.profile(True)
+        launches0 = ctx.launch_count
+        evs = []
+        barrier()
+        if sampler:
+            sampler.mark_start()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); grid.step(); e1.record(stream)
+            evs.append((e0, e1))
+        barrier()
+        if sampler:
+            sampler.mark_end()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        launches = ctx.launch_count - launches0
+        fact_ms, fact_flops, _ = ctx.profile_read()
+        ctx.profile(False)
+        mx, sm = reduce_max_sum([ms, float(launches)])
+        return mx[0], int(sm[1]), fact_ms, fact_flops
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    barrier()
-    ctx.profile(True)
-    launches0 = ctx.launch_count
-    evs = []
-    barrier()
-    sampler.mark_start()
-    for _ in range(args.steps):
-        flush.zero_()                                                       # L2 flush between timed iterations (untimed)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream); step_device(); e1.record(stream)
-        evs.append((e0, e1))
-    barrier()
-    sampler.mark_end()
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
-    launches = ctx.launch_count - launches0
-    fact_ms, fact_flops, n_br = ctx.profile_read()
-    ctx.profile(False)
-    tt = torch.tensor([ms_total, float(launches)], dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_total, launches = float(mx[0]), int(sm[1])
-    cells_per_step = N_Q * n_ls_total
+
+    # ---- the metric: the fixed 128 x 256 grid, length scales sharded over the ranks (strong scaling) ----
+    grid = DeviceGrid(torch, dist, ctx, dev, rank, world, N_LS)
+    X, y, orders, ls_vals, q_vals = grid.inputs
+    ms_total, launches, fact_ms, fact_flops = time_device(grid, args.steps, max(args.warmup, 3), sampler)
+    cells_per_step = N_Q * N_LS
     value = cells_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- side figure: weak scaling, 128 length scales PER GPU (the round-1 bench line) ----
+    weak = None
+    if world > 1:
+        wgrid = DeviceGrid(torch, dist, ctx, dev, rank, world, N_LS_PER_GPU * world)
+        wsteps = max(3, min(args.steps, 10))
+        wms, _, wf_ms, wf_flops = time_device(wgrid, wsteps, 3)
+        weak = {"value": N_Q * N_LS_PER_GPU * world * wsteps / (wms * 1e-3), "unit": "evals/s", "ms_per_step": wms / wsteps, "steps": wsteps,
+                "n_ls_per_gpu": N_LS_PER_GPU, "grid": f"{N_LS_PER_GPU * world} l x {N_Q} Q",
+                "factorisation_tflops_rank0": wf_flops / (wf_ms * 1e-3) * 1e-12 if wf_ms > 0 else None}
+        del wgrid
 
     # ---- end-to-end arm: the public API with host buffers (H2D of inputs and D2H of the grid inside the timed region) ----
     gp = gb.TruncationGP(RBF(0.05) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None)
@@ -347,62 +418,79 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
-    if world > 1:
-        te = torch.tensor([e2e_s], dtype=torch.float64, device=dev); dist.all_reduce(te, op=dist.ReduceOp.MAX); e2e_s = float(te[0])
+    e2e_s = reduce_max_sum([e2e_s])[0][0]
     e2e_value = cells_per_step * args.steps / e2e_s
-    h2d = 8 * (X.size + dy.size + N_POINTS + len(mine) + N_Q + N_Q) + 4 * N_ORDERS
-    d2h = 8 * (N_Q * len(mine) + len(mine)) + 4 * len(mine)
-    assert np.isfinite(ll_host).all() and ll_host.shape == (N_Q, n_ls_total)
+    n_mine = len(grid.mine)
+    # per rank and step: the packed inputs go up once; every rank reads the WHOLE gathered grid back (world > 1), or its
+    # grid + log-determinants + status (1 GPU, C ABI with host buffers)
+    h2d_rank = 8 * (X.size + grid.dy.size + N_POINTS + n_mine + N_Q + N_Q) + 4 * N_ORDERS + (4 if world > 1 and N_ORDERS % 2 else 0)
+    d2h_rank = 8 * N_Q * N_LS if world > 1 else 8 * (N_Q * N_LS + N_LS) + 4 * N_LS
+    assert np.isfinite(ll_host).all() and ll_host.shape == (N_Q, N_LS)
+
+    # ---- untimed: the sharded grid against the same grid computed by ONE GPU alone (whole grid, bit for bit) ----
+    sharded_equal = None
+    if world > 1 and rank == 0:
+        single = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals)
+        sharded_equal = bool(np.array_equal(single, ll_host))
 
     if rank == 0:
         # parity spot check of the timed configuration (not timed)
-        dt_cpu, want = cpu_reference_cells(X, y, orders, ls_vals, q_vals, [(0, 0), (100, 40 * world)])
-        got = [ll_host[0, 0], ll_host[100, 40 * world]]
+        dt_cpu, want = cpu_reference_cells(X, y, orders, ls_vals, q_vals, [(0, 0), (100, 40), (255, 127)])
+        got = [ll_host[0, 0], ll_host[100, 40], ll_host[255, 127]]
         parity = max(abs(g - w) / abs(w) for g, w in zip(got, want))
-        # roofline of the dominant kernel (the bordered Cholesky launch, chol_hetero_tma_kernel)
+        # roofline of the dominant kernel (the bordered Cholesky launch, chol_hetero_tma_kernel), this rank's launches
         peak = measure_fp64_peak(torch)
         achieved = fact_flops / (fact_ms * 1e-3) * 1e-12 if fact_ms > 0 else 0.0
         # CPU baseline on a bounded sample (~10-20 s of CPU work in total): cell-parallel over all host cores, and the
         # notebook's serial loop beside it
         workers = os.cpu_count() or 1
-        cells = stratified_cells(N_Q, n_ls_total, 16)
-        pool = CellPool(n_ls_total, workers)
+        cells = stratified_cells(N_Q, N_LS, 16)
+        pool = CellPool(N_LS, workers)
         try:
             cpu_s, _ = pool.run(cells)
         finally:
             pool.close()
-        cpu_cores = workers
-        serial_cells = stratified_cells(N_Q, n_ls_total, 5)
+        serial_cells = stratified_cells(N_Q, N_LS, 5)
         with best_blas_setting(lambda: cpu_reference_cells(X, y, orders, ls_vals, q_vals, serial_cells[:4])[0]) as blas:
             serial_s, _ = cpu_reference_cells(X, y, orders, ls_vals, q_vals, serial_cells)
+        same_launch = (n_mine == NCU_TRAFFIC["n_ls"])
+        cfg = base_config(world)
+        cfg.update({"timing": "CUDA events on the launch stream per step, max over ranks; L2 flushed (256 MB memset) between steps",
+                    "collective": "one NCCL all-gather of the FP64 blocks + device logsumexp" if world > 1 else "none (1 GPU); device logsumexp"})
         out = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": "C4: N=1024, 6 orders, 128 l x 256 Q per GPU (configs[3] of BASELINE.json)", "n_points": N_POINTS,
-                       "n_orders": N_ORDERS, "n_ls_per_gpu": N_LS_PER_GPU, "n_q": N_Q, "grid_cells_per_step": cells_per_step,
-                       "timing": "CUDA events on the launch stream per step, max over ranks; L2 flushed (256 MB memset) between steps; "
-                                 "working set 1.1 GB/GPU > L2", "collective": "one NCCL all-gather of the FP64 blocks + device logsumexp" if world > 1 else "none (1 GPU); device logsumexp"},
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "TruncationGP.log_marginal_likelihood_grid (numpy in, numpy out; pageable host buffers)", "ms_per_step": 1e3 * e2e_s / args.steps},
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(h2d_rank) * world, "d2h_bytes_per_step": int(d2h_rank) * world,
+                    "h2d_bytes_per_step_per_rank": int(h2d_rank), "d2h_bytes_per_step_per_rank": int(d2h_rank),
+                    "api": "TruncationGP.log_marginal_likelihood_grid (numpy in, numpy out on every rank; staged through pinned host buffers)",
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                         "traffic": NCU_TRAFFIC_BYTES * (n_ls_total // world) / 128.0,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one chol_hetero_tma_kernel launch at 128 l per GPU, "
-                                           "ncu --set full (profiles/r01_ncu_hetero_tma.txt)",
-                         "kernel": "chol_hetero_tma_kernel (FP64 DMMA bordered Cholesky + forward solves, K2+K3; one cooperative launch per step)",
+                         "traffic": NCU_TRAFFIC["bytes"] if same_launch else None,
+                         "traffic_source": (f"RECORDED constant, not measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                            f"factorisation launch at {NCU_TRAFFIC['n_ls']} length scales, ncu --set full ({NCU_TRAFFIC['file']})")
+                         if same_launch else f"no ncu capture of the {n_mine}-length-scale launch",
+                         "kernel": "chol_hetero_tma_kernel (FP64 DMMA bordered Cholesky + forward solves, K2+K3; one cooperative launch per step "
+                                   f"over this rank's {n_mine} length scales)",
                          "flops_per_step": fact_flops / max(args.steps, 1), "kernel_ms_per_step": fact_ms / max(args.steps, 1),
                          "peak_source": "cuBLAS DGEMM 4096^3 measured live in this run (MEASURED_PEAKS.json has no FP64 figure; "
                                         "profiles/r01_dgemm_peak.json: 35.5 TFLOP/s at 8192^3)"},
-            "cpu_baseline": {"value": len(cells) / cpu_s, "unit": "evals/s", "cores": cpu_cores, "kind": "port", "host_cpus": os.cpu_count(),
-                             "sample": f"{len(cells)} stratified cells of the {N_Q}x{n_ls_total} grid, per-cell reference algorithm "
-                                       f"(numpy/scipy/sklearn), {workers} worker processes x 1 BLAS thread, {cpu_s:.1f} s wall",
+            "cpu_baseline": {"value": len(cells) / cpu_s, "unit": "evals/s", "cores": workers, "kind": "port", "host_cpus": os.cpu_count(),
+                             "sample": f"{len(cells)} stratified cells of the {N_Q}x{N_LS} grid, per-cell reference algorithm "
+                                       f"(numpy/scipy/sklearn), {workers} worker processes x {pool.blas_threads_per_worker} BLAS thread "
+                                       f"(threadpool_info checked in every worker), {cpu_s:.1f} s wall",
                              "serial_loop": {"value": len(serial_cells) / serial_s, "unit": "evals/s", "blas_threads": blas.threads,
                                              "sample": f"{len(serial_cells)} cells, {serial_s:.1f} s"}},
             "clocks": clocks, "parity_spot_check_rel": parity,
         }
+        if weak is not None:
+            out["weak"] = weak
+        if sharded_equal is not None:
+            out["sharded_equals_single_gpu"] = sharded_equal
         _emit(json.dumps(out))
     if world > 1:
+        barrier()
         dist.destroy_process_group()
 
 

@@ -74,12 +74,37 @@ def lml_grid_sharded(X, dy, ref, orders, ls, Q, group=None, normalize=False, **k
 
 
 _stream_ctx = {}
+_grid_plans = {}
+
+
+class _GridPlan:
+    """Persistent staging of one sharded-grid shape: a pinned host buffer and its device twin for the packed inputs, the
+    send / receive buffers of the all-gather, the grid in its final layout and a pinned host buffer for the result.
+    Nothing is allocated and no pageable buffer is touched by the device on the per-call path."""
+
+    def __init__(self, dev, sizes, n_q, per, world, n_ls, n_mine):
+        import torch
+        self.offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        words = int(self.offs[-1])
+        self.h_in = torch.empty(words, dtype=torch.float64, pin_memory=True)
+        self.h_in_np = self.h_in.numpy()
+        self.d_in = torch.empty(words, dtype=torch.float64, device=dev)
+        self.v = [self.d_in[int(self.offs[i]):int(self.offs[i + 1])] for i in range(len(sizes))]
+        self.send = torch.full((n_q, per), float("-inf"), dtype=torch.float64, device=dev)
+        self.out = self.send if n_mine == per else torch.empty((n_q, max(n_mine, 1)), dtype=torch.float64, device=dev)
+        self.recv = torch.empty((world * n_q, per), dtype=torch.float64, device=dev)   # rank-major concatenation along dim 0
+        self.full = torch.empty((n_q, per * world), dtype=torch.float64, device=dev)
+        self.post = torch.empty((n_q, n_ls), dtype=torch.float64, device=dev)
+        self.lse = torch.empty(1, dtype=torch.float64, device=dev)
+        self.h_out = torch.empty((2, n_q, per * world), dtype=torch.float64, pin_memory=True)
+        self.h_lse = torch.empty(1, dtype=torch.float64, pin_memory=True)
 
 
 def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normalize, kw):
-    """NCCL path: this rank's block never leaves the device between the likelihood kernels and the all-gather — inputs go
-    up once, the kernels and the collective are enqueued on torch's current stream, the round-robin deal is undone by a
-    permute on the device, and ONE device-to-host copy returns the grid."""
+    """NCCL path: this rank's block never leaves the device between the likelihood kernels and the all-gather — the inputs
+    go up in ONE copy from a persistent pinned buffer, the kernels and the collective are enqueued on torch's current
+    stream, the round-robin deal is undone by one strided copy on the device into the final layout, and ONE device-to-host
+    copy into pinned memory returns the grid (`_GridPlan`: no allocation on the per-call path)."""
     import torch
     import torch.distributed as dist
     from . import _lib
@@ -95,39 +120,49 @@ def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normaliz
     Q = np.asarray(Q, dtype=np.float64)
     n_q, n_ls = Q.shape[0], ls.shape[0]
     detf = kw.get("detf")
-    send = torch.full((n_q, per), float("-inf"), dtype=torch.float64, device=dev)
-    if len(mine):
-        # every input in ONE host buffer -> one host-to-device copy; the device tensors are views into it
-        orders32 = np.asarray(orders, dtype=np.int32)
-        parts = [X.ravel(), np.asarray(dy, dtype=np.float64).ravel(), np.broadcast_to(np.asarray(ref, dtype=np.float64), (n,)),
-                 ls[mine].ravel(), Q.ravel(),
-                 np.zeros(n_q) if detf is None else np.broadcast_to(np.asarray(detf, dtype=np.float64), (n_q,))]
-        sizes = [p.size for p in parts] + [(orders32.size + 1) // 2]
-        offs = np.concatenate([[0], np.cumsum(sizes)])
-        host = np.empty(int(offs[-1]), dtype=np.float64)
-        for p_, o in zip(parts, offs):
-            host[o:o + p_.size] = p_
-        host[offs[6]:].view(np.int32)[:orders32.size] = orders32
-        buf = torch.from_numpy(host).to(dev)
-        v = [buf[int(offs[i]):int(offs[i + 1])] for i in range(7)]
-        out = send if len(mine) == per else torch.empty((n_q, len(mine)), dtype=torch.float64, device=dev)
-        ops.lml_grid_device(ctx, v[0].view(n, -1), v[1].view(n, -1), v[2], v[6].view(torch.int32)[:orders32.size], v[3].view(len(mine), -1),
-                            v[4].view(Q.shape), None if detf is None else v[5], out,
-                            q_x_dependent=bool(kw.get("q_x_dependent", False)), constant=kw.get("constant", 1.0),
+    orders32 = np.asarray(orders, dtype=np.int32)
+    dy = np.asarray(dy, dtype=np.float64)
+    n_mine = len(mine)
+    sizes = (X.size, dy.size, n, max(n_mine, 1) * ls.shape[1], Q.size, n_q, (orders32.size + 1) // 2)
+    pkey = key + sizes + (per, world, n_ls, id(group))
+    plan = _grid_plans.get(pkey)
+    if plan is None:
+        if len(_grid_plans) > 8:
+            _grid_plans.clear()
+        plan = _grid_plans[pkey] = _GridPlan(dev, sizes, n_q, per, world, n_ls, n_mine)
+    if n_mine:
+        h, o = plan.h_in_np, plan.offs
+        h[o[0]:o[1]] = X.ravel()
+        h[o[1]:o[2]] = dy.ravel()
+        h[o[2]:o[3]] = np.asarray(ref, dtype=np.float64)          # broadcasts a scalar
+        h[o[3]:o[3] + n_mine * ls.shape[1]] = ls[mine].ravel()
+        h[o[4]:o[5]] = Q.ravel()
+        h[o[5]:o[6]] = 0.0 if detf is None else np.asarray(detf, dtype=np.float64)
+        h[o[6]:o[7]].view(np.int32)[:orders32.size] = orders32
+        plan.d_in.copy_(plan.h_in, non_blocking=True)
+        v = plan.v
+        ops.lml_grid_device(ctx, v[0].view(n, -1), v[1].view(n, -1), v[2], v[6].view(torch.int32)[:orders32.size],
+                            v[3][:n_mine * ls.shape[1]].view(n_mine, -1), v[4].view(Q.shape), None if detf is None else v[5],
+                            plan.out, q_x_dependent=bool(kw.get("q_x_dependent", False)), constant=kw.get("constant", 1.0),
                             noise=kw.get("noise", 0.0), nugget=kw.get("nugget", 1e-10), center0=kw.get("center0", 0.0),
                             disp0=kw.get("disp0", 0.0), df0=kw.get("df0", 1.0), scale0=kw.get("scale0", 1.0),
                             student=bool(kw.get("student", False)))
-        if out is not send:
-            send[:, :len(mine)] = out
-    recv = torch.empty((world * n_q, per), dtype=torch.float64, device=dev)   # rank-major concatenation along dim 0
-    dist.all_gather_into_tensor(recv, send, group=group)                      # the single collective of the path
-    # rank r's local column j is length scale r + j * world: (world, n_q, per) -> (n_q, per, world) -> (n_q, per * world)
-    full_d = recv.view(world, n_q, per).permute(1, 2, 0).reshape(n_q, per * world)[:, :n_ls].contiguous()
+        if plan.out is not plan.send:
+            plan.send[:, :n_mine] = plan.out[:, :n_mine]
+    dist.all_gather_into_tensor(plan.recv, plan.send, group=group)            # the single collective of the path
+    # rank r's local column j is length scale r + j * world: (world, n_q, per) -> (n_q, per, world), one strided copy
+    plan.full.view(n_q, per, world).copy_(plan.recv.view(world, n_q, per).permute(1, 2, 0))
+    plan.h_out[0].copy_(plan.full, non_blocking=True)
     if normalize:
-        post_d, lse_d = torch.empty_like(full_d), torch.empty(1, dtype=torch.float64, device=dev)
-        ops.grid_normalize_device(ctx, full_d, post_d, lse_d)
-        return full_d.cpu().numpy(), post_d.cpu().numpy(), float(lse_d.cpu()[0])
-    return full_d.cpu().numpy()
+        full_d = plan.full if per * world == n_ls else plan.full[:, :n_ls].contiguous()
+        ops.grid_normalize_device(ctx, full_d, plan.post, plan.lse)
+        plan.h_out[1, :, :n_ls].copy_(plan.post, non_blocking=True)
+        plan.h_lse.copy_(plan.lse, non_blocking=True)
+    stream.synchronize()
+    full = plan.h_out[0].numpy()[:, :n_ls].copy()
+    if normalize:
+        return full, plan.h_out[1].numpy()[:, :n_ls].copy(), float(plan.h_lse[0])
+    return full
 
 
 def shard_range(n, world_size, rank):
