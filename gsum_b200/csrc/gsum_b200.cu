@@ -55,6 +55,8 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     c->use_tma = (!sched || strcmp(sched, "hetero_tma") == 0) ? 1 : 0;
     const char *fc = getenv("GSUM_B200_FACTOR_CTAS");
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
+    const char *chn = getenv("GSUM_B200_CHAIN_MAX");
+    c->ht_chain_max = chn ? atoi(chn) : HT_CHAIN_MAX;
     const char *thin = getenv("GSUM_B200_THIN");
     c->use_thin = (thin && strcmp(thin, "0") == 0) ? 0 : 1;
     *out = c;
@@ -353,17 +355,20 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     const bool thin_last = c->use_thin && nbt > 0 && P.border_used > 0 && P.border_used - (nbt - 1) * GSUM_TILE <= 8 &&
                            P.border_used > (nbt - 1) * GSUM_TILE;
     const int delay = getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : HT_DIAG_DELAY;
-    const int key[5] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0), delay};
+    // few matrices: chain mode (chain.cuh) — one chain worker CTA per matrix owns the diagonal band
+    const bool chain = !solve_only && c->use_tma && batch <= c->ht_chain_max;
+    const int key[5] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0) | (chain ? 4 : 0), delay};
     if (memcmp(key, c->ht_key, sizeof(key)) != 0 || !c->ht_gtasks) {
         std::vector<int4> gt, ft;
-        ht_build_tasks(gt, ft, P.T, P.Trows, batch, solve_only, thin_last, delay);
+        if (chain) ht_build_chain_tasks(gt, P.T, P.Trows, batch, thin_last);
+        else ht_build_tasks(gt, ft, P.T, P.Trows, batch, solve_only, thin_last, delay);
         GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // the previous lists may still be in use
         GSUM_TRY(ht_upload(c, &c->ht_gtasks, &c->ht_gcap, gt));
         GSUM_TRY(ht_upload(c, &c->ht_ftasks, &c->ht_fcap, ft));
         memcpy(c->ht_key, key, sizeof(key));
         c->ht_ng = (int)gt.size(); c->ht_nf = (int)ft.size();
     }
-    const size_t fbytes = sizeof(int) * (size_t)batch * P.Trows * P.T;
+    const size_t fbytes = sizeof(int) * ((size_t)batch * P.Trows * P.T + (size_t)batch * P.T);       // tile flags + pre flags
     if (c->df_flags_cap < fbytes) {
         GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
         if (c->df_flags) GSUM_CUDA(c, cudaFree(c->df_flags));
@@ -376,7 +381,7 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     }
     void *dM;
     GSUM_TRY(gsum_ws(c, WS_MKK, sizeof(double) * (size_t)batch * P.T * GSUM_TILE * GSUM_TILE, &dM));
-    const int64_t nflags = (int64_t)batch * P.Trows * P.T;
+    const int64_t nflags = (int64_t)batch * P.Trows * P.T + (int64_t)batch * P.T;
     ht_init_kernel<<<(unsigned)((nflags + 255) / 256 + 1), 256, 0, c->stream>>>((int *)c->df_flags, c->df_ctl, batch, P.Trows, P.T, solve_only ? 1 : 0);
     c->launches += 1;
     if (solve_only) {
@@ -385,8 +390,9 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     }
     HeteroArgs D;
     D.P = P; D.gtasks = (const int4 *)c->ht_gtasks; D.ngtasks = c->ht_ng; D.ftasks = (const int4 *)c->ht_ftasks; D.nftasks = c->ht_nf;
-    D.nf0 = (!solve_only && c->ht_nf >= batch) ? batch : 0;          // df_build_tasks emits the column-0 diagonal tiles first
+    D.nf0 = (!solve_only && !chain && c->ht_nf >= batch) ? batch : 0;          // df_build_tasks emits the column-0 diagonal tiles first
     D.ctl = c->df_ctl; D.flags = (int *)c->df_flags; D.M = (double *)dM; D.stats = nullptr;
+    D.chain = chain ? 1 : 0; D.pre = (int *)c->df_flags + (int64_t)batch * P.Trows * P.T;
     // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
     int nf = 0;
     int nwk = getenv("GSUM_B200_FACTOR_WORKERS") ? atoi(getenv("GSUM_B200_FACTOR_WORKERS")) : 3;
@@ -400,6 +406,7 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         if (nf > c->sm_count / 2) nf = c->sm_count / 2;
         if (nf < 1) nf = 1;
     }
+    if (chain) { nf = batch; D.nworkers = 1; }
     int ng = c->sm_count - nf;
     if (ng > c->ht_ng) ng = c->ht_ng;
     D.nfactor_ctas = nf;
@@ -445,6 +452,13 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         const int ngrp = c->use_tma ? HX_NG : HT_NG;
         for (int g = 0; g < nf; g++) for (int wk = 0; wk < nwk; wk++) for (int q = 0; q < 6; q++) f[q] += (double)h[HT_NSTAT * g + wk * 6 + q];
         for (int g = nf; g < grid; g++) for (int grp = 0; grp < ngrp; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
+        if (chain) {
+            double ch[8] = {0};
+            for (int g = 0; g < nf; g++) for (int q = 0; q < 7; q++) ch[q] += (double)h[HT_NSTAT * g + q];
+            const double cols = ch[6] > 0 ? ch[6] : 1;
+            fprintf(stderr, "[ht] chain workers %d: cycles/worker %.0f | per column: wait_pre %.0f potrf %.0f invert %.0f solve %.0f update %.0f (sum %.0f)\n",
+                    nf, ch[0] / nf, ch[1] / cols, ch[2] / cols, ch[3] / cols, ch[4] / cols, ch[5] / cols, (ch[1] + ch[2] + ch[3] + ch[4] + ch[5]) / cols);
+        } else
         if (nf) fprintf(stderr, "[ht] factor CTAs %d: cycles/worker %.0f | wait_S %.1f%% | busy %.1f%% (%.0f cycles per diagonal tile: load %.0f, potrf %.0f; %.1f tiles per worker)\n",
                         nf, f[0] / (nwk * nf), 100 * f[1] / f[0], 100 * f[2] / f[0], f[2] / (f[3] + 1e-9), f[4] / (f[3] + 1e-9), f[5] / (f[3] + 1e-9), f[3] / (nwk * nf));
         if (ng) fprintf(stderr, "[ht] GEMM CTAs %d x %d groups: cycles/group %.0f, tasks/group %.1f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% wait_Mkk %.1f%% | math: wait_queue %.1f%% wait_operands %.1f%% wait_Mkk %.1f%% trsm %.1f%% fence+flag %.1f%%\n",

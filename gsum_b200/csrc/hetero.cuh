@@ -55,6 +55,9 @@
 #ifndef HT_FACTOR_CTAS
 #define HT_FACTOR_CTAS 12               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
 #endif
+#ifndef HT_CHAIN_MAX
+#define HT_CHAIN_MAX 40                 // batches up to this many matrices run in chain mode (chain.cuh)
+#endif
 #ifndef HT_DIAG_DELAY
 #define HT_DIAG_DELAY 0
 #endif
@@ -72,6 +75,8 @@ struct HeteroArgs {
     int nfactor_ctas;       // CTAs [0, nfactor_ctas) are factor CTAs
     int nworkers;           // 128-thread workers per factor CTA (1..3)
     long long *stats;       // optional per-CTA cycle counters [grid][HT_NSTAT]
+    int chain;              // chain mode (chain.cuh): CTA c < nfactor_ctas is the chain worker of matrix c
+    int *pre;               // chain mode, per (b, k): 1 = the pre-panel tile (k+1, k) holds S' (everything but the triangular solve)
 };
 
 __device__ __forceinline__ bool flag_wait_ge(const int *flag, int want, int *abort_flag) {
@@ -700,7 +705,10 @@ __global__ void ht_init_kernel(int *flags, int *ctl, int64_t batch, int Trows, i
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < 2) ctl[idx] = 0;
     if (idx == 3 || idx == 4) ctl[idx] = 0;
-    if (idx >= batch * Trows * T) return;
+    if (idx >= batch * Trows * T) {
+        if (idx < batch * Trows * T + batch * T) flags[idx] = 0;      // the pre flags of chain mode
+        return;
+    }
     const int k = (int)(idx % T), i = (int)((idx / T) % Trows);
     flags[idx] = (factor_done && i < T) ? (i == k ? 2 : 1) : 0;
 }
@@ -717,6 +725,22 @@ __global__ void __launch_bounds__(CHOL_THREADS) ht_mkk_from_factor_kernel(Border
     if (tid < GSUM_TILE) dg[tid] = C[(int64_t)tid * P.ld + tid];
     __syncthreads();
     ht_write_mkk(S, dg, M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), false);
+}
+
+// Chain mode (chain.cuh): the diagonal band belongs to the chain workers; the GEMM list holds, per column k, the two pre
+// tasks of the next band step first (flag bit 1: pre-panel (k+1, k) without triangular solve, pre-diag (k+1, k+1) without
+// its last term — neither depends on column k), then the panel tasks of rows >= k+2 and of the border rows.
+static inline void ht_build_chain_tasks(std::vector<int4> &gemm, int T, int Trows, int batch, bool thin_last) {
+    gemm.clear();
+    auto fl = [&](int i) { return (thin_last && i == Trows - 1 && i >= T) ? 1 : 0; };
+    for (int k = 0; k < T; k++) {
+        if (k + 1 < T && k >= 1) {
+            for (int b = 0; b < batch; b++) gemm.push_back(make_int4(k + 1, k, b, 2));
+            for (int b = 0; b < batch; b++) gemm.push_back(make_int4(k + 1, k + 1, b, 2));
+        }
+        for (int i = (k + 1 < T ? k + 2 : k + 1); i < Trows; i++)
+            for (int b = 0; b < batch; b++) gemm.push_back(make_int4(i, k, b, fl(i)));
+    }
 }
 
 // Split the joint topological order into the two claim lists.

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda.h>
 #include "hetero.cuh"
+#include "chain.cuh"
 
 #define HX_NG 3                         // math groups per GEMM CTA (4 warps each, one per sub-partition)
 #define HX_NST 2                        // ring stages per group
@@ -135,6 +136,16 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
         // same register split as in a GEMM CTA: the idle warpgroup hands its registers to the three workers
         if (w >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); return; }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HX_MATH_REGS) ";");
+        if (D.chain) {
+            if (tid >= CH_THREADS) return;
+            if (tid >= 128) { ht_chain_helper(D, smem, (int)blockIdx.x); return; }
+            ht_chain_worker(D, smem, (int)blockIdx.x, st_on ? st : nullptr);
+            if (st_on && tid == 0) {
+                long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT;
+                o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; o[5] = st[4]; o[6] = st[5];
+            }
+            return;
+        }
         if (tid >= 128 * D.nworkers) return;
         ht_factor_worker(D, smem + (tid >> 7) * HT_WORKER_DOUBLES, st_on ? st : nullptr);
         if (st_on && (tid & 127) == 0) {
@@ -189,7 +200,8 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             }
             if (tk.x < 0) break;
             const int i = tk.x, k = tk.y, b = tk.z;
-            const bool diag = (i == k), thin = (tk.w & 1) != 0;
+            const bool diag = (i == k), thin = (tk.w & 1) != 0, pre = (tk.w & 2) != 0;
+            const int nj = (pre && diag) ? k - 1 : k;           // chain mode: a pre-diag tile leaves its last term to the chain worker
             const bool border = (i >= P.T);
             const CUtensorMap *mapI = border ? (thin ? &maps.W8 : &maps.W) : &maps.A;
             const int rowI = border ? b * rowsW + (i - P.T) * GSUM_TILE : b * rowsA + i * GSUM_TILE;
@@ -210,11 +222,11 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             // ---- operand half-slabs ----------------------------------------------------------------------------
             // A finished tile (r, k-1) implies every (r, j < k-1): they were its operands.
             bool done_i = true, done_k = true;
-            if (k > 0) {
-                done_i = ld_relaxed(frow_i + k - 1) >= 1;
-                done_k = diag ? done_i : (ld_relaxed(frow_k + k - 1) >= 1);
+            if (nj > 0) {
+                done_i = ld_relaxed(frow_i + nj - 1) >= 1;
+                done_k = diag ? done_i : (ld_relaxed(frow_k + nj - 1) >= 1);
             }
-            for (int h = 0; h < 2 * k; h++) {
+            for (int h = 0; h < 2 * nj; h++) {
                 const int j = h >> 1;
                 if ((h & 1) == 0 && !(done_i && done_k)) {
                     HT_T0();
@@ -239,7 +251,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             }
             if (!ok) break;
             // ---- last stage of a panel task: M_kk -----------------------------------------------------------------
-            if (!diag) {
+            if (!diag && !pre) {
                 { HT_T0(); ok = flag_wait_ge(frow_k + k, 2, abort_flag); HT_ACC(3); }
                 if (!ok) break;
                 { HT_T0(); ok = mbar_wait(&emptyb[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
@@ -291,7 +303,8 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             }
             if (!alive || tk.x < 0) break;             // no CTA-level barrier anywhere in this role: a warp may leave alone
             const int i = tk.x, k = tk.y, b = tk.z;
-            const bool diag = (i == k), thin = (tk.w & 1) != 0;
+            const bool diag = (i == k), thin = (tk.w & 1) != 0, pre = (tk.w & 2) != 0;
+            const int nj = (pre && diag) ? k - 1 : k;
             double *Ab = P.A + (int64_t)b * P.bstride;
             double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
                                    : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 hx_ring_advance(ring);
             }
             // ---- main loop ---------------------------------------------------------------------------------------
-            for (int h = 0; h < 2 * k; h++) {
+            for (int h = 0; h < 2 * nj; h++) {
                 { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(1); }
                 if (!alive) break;
                 const double *As = ring_base + ring.stage * HX_STAGE_DOUBLES;
@@ -346,6 +359,15 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                             double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
                             *reinterpret_cast<double2 *>(C + (int64_t)((mt ? row1 : row0) + g) * P.ld + nt * 8 + 2 * t) = v;
                         }
+            } else if (pre) {
+                // ---- chain mode: S' in place, the chain worker does the triangular solve -----------------------------
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
+                        *reinterpret_cast<double2 *>(C + (int64_t)(wg * 16 + mt * 8 + g) * P.ld + nt * 8 + 2 * t) = v;
+                    }
             } else {
                 // ---- the triangular solve, warp-local on the 16 x 64 row block ------------------------------------
                 { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(2); }
@@ -376,7 +398,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&done_cnt[q][slot])) : "memory");
                 if (old == 3) {
                     done_cnt[q][slot] = 0;
-                    st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
+                    st_release((pre && !diag) ? D.pre + (int64_t)b * P.T + k : D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
                 }
             }
             HT_ACC(4); }
