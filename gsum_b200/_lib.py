@@ -56,6 +56,7 @@ _SIGNATURES = {
     "gsum_process_cov": (C.c_int, [_vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double, _vp, C.c_int64, _vp, C.c_int64,
                                    _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, C.c_int32, C.c_double, C.c_double, _vp, C.c_int32]),
     "gsum_cholesky_errors": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32]),
+    "gsum_quadratic_forms": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int32]),
     "gsum_pivoted_cholesky": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int32]),
     "gsum_pc_errors": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int32]),
     "gsum_draws": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int32,

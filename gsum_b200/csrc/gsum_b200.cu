@@ -441,6 +441,10 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         const void *kfn = D.stats ? (const void *)chol_hetero_kernel<true> : (const void *)chol_hetero_kernel<false>;
         GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HT_THREADS), args, HT_SMEM_BYTES, c->stream));
     }
+    if (!solve_only && P.logdet_part) {
+        ht_logdet_kernel<<<dim3(P.T, batch), 32, 0, c->stream>>>(P);
+        c->launches += 1;
+    }
     df_check_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, c->stream>>>(c->df_ctl + 1, P.info, batch, c->df_ctl + 2);
     c->launches += 2;
     GSUM_CUDA(c, cudaPeekAtLastError());
@@ -453,11 +457,11 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         for (int g = 0; g < nf; g++) for (int wk = 0; wk < nwk; wk++) for (int q = 0; q < 6; q++) f[q] += (double)h[HT_NSTAT * g + wk * 6 + q];
         for (int g = nf; g < grid; g++) for (int grp = 0; grp < ngrp; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
         if (chain) {
-            double ch[8] = {0};
-            for (int g = 0; g < nf; g++) for (int q = 0; q < 7; q++) ch[q] += (double)h[HT_NSTAT * g + q];
+            double ch[10] = {0};
+            for (int g = 0; g < nf; g++) for (int q = 0; q < 10; q++) ch[q] += (double)h[HT_NSTAT * g + q];
             const double cols = ch[6] > 0 ? ch[6] : 1;
-            fprintf(stderr, "[ht] chain workers %d: cycles/worker %.0f | per column: wait_pre %.0f potrf %.0f invert %.0f solve %.0f update %.0f (sum %.0f)\n",
-                    nf, ch[0] / nf, ch[1] / cols, ch[2] / cols, ch[3] / cols, ch[4] / cols, ch[5] / cols, (ch[1] + ch[2] + ch[3] + ch[4] + ch[5]) / cols);
+            fprintf(stderr, "[ht] chain workers %d: cycles/worker %.0f | per column: wait_pre %.0f potrf %.0f invert %.0f solve %.0f wait_helper %.0f update %.0f (sum %.0f) | invert compute %.0f, own update %.0f\n",
+                    nf, ch[0] / nf, ch[1] / cols, ch[2] / cols, ch[3] / cols, ch[4] / cols, ch[7] / cols, ch[5] / cols, (ch[1] + ch[2] + ch[3] + ch[4] + ch[5] + ch[7]) / cols, ch[8] / cols, ch[9] / cols);
         } else
         if (nf) fprintf(stderr, "[ht] factor CTAs %d: cycles/worker %.0f | wait_S %.1f%% | busy %.1f%% (%.0f cycles per diagonal tile: load %.0f, potrf %.0f; %.1f tiles per worker)\n",
                         nf, f[0] / (nwk * nf), 100 * f[1] / f[0], 100 * f[2] / f[0], f[2] / (f[3] + 1e-9), f[4] / (f[3] + 1e-9), f[5] / (f[3] + 1e-9), f[3] / (nwk * nf));
@@ -1229,6 +1233,31 @@ extern "C" int gsum_process_cov(gsum_ctx *c, int32_t d, const double *ls, int32_
 }
 
 // ---- diagnostics ---------------------------------------------------------------------------------------------
+extern "C" int gsum_quadratic_forms(gsum_ctx *c, const double *A, int64_t n, const double *mean, const double *Y, int64_t n_curves,
+                                    double *q, int32_t mem_kind) {
+    if (!c || !A || !mean || !Y || !q || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_quadratic_forms: bad argument");
+    if ((size_t)n * QF_C * sizeof(double) > 200 * 1024) return gsum_fail(c, -1, "gsum_quadratic_forms: n <= %d", 200 * 1024 / (QF_C * 8));
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const void *dA, *dm, *dY;
+    GSUM_TRY(dev_in(c, WS_MAT, A, sizeof(double) * n * n, mem_kind, &dA));
+    GSUM_TRY(dev_in(c, WS_IO0, mean, sizeof(double) * n, mem_kind, &dm));
+    GSUM_TRY(dev_in(c, WS_IO1, Y, sizeof(double) * n * n_curves, mem_kind, &dY));
+    void *dq, *dpart;
+    GSUM_TRY(dev_out(c, WS_IO2, q, sizeof(double) * n_curves, mem_kind, &dq));
+    GSUM_TRY(gsum_ws(c, WS_MISC0, sizeof(double) * n * QF_C, &dpart));
+    const size_t smem = sizeof(double) * (size_t)n * QF_C;
+    GSUM_CUDA(c, cudaFuncSetAttribute(quadform_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)((n + QF_WARPS - 1) / QF_WARPS);
+    if (grid > 2 * c->sm_count) grid = 2 * c->sm_count;
+    for (int64_t c0 = 0; c0 < n_curves; c0 += QF_C) {
+        quadform_rows_kernel<<<grid, 32 * QF_WARPS, smem, c->stream>>>((const double *)dA, n, (const double *)dm, (const double *)dY, n_curves, c0, (double *)dpart);
+        quadform_reduce_kernel<<<QF_C, 256, 0, c->stream>>>((const double *)dpart, n, n_curves, c0, (double *)dq);
+        LAUNCHED(c, 2);
+    }
+    GSUM_TRY(dev_out_finish(c, q, dq, sizeof(double) * n_curves, mem_kind));
+    return finish(c, mem_kind);
+}
+
 extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, const double *mean, const double *Y,
                                     int64_t n_curves, double *E, double *md2, int32_t mem_kind) {
     if (!c || !L || !Y || n <= 0 || n_curves <= 0 || (!E && !md2)) return gsum_fail(c, -1, "gsum_cholesky_errors: bad argument");

@@ -47,7 +47,8 @@
 #define HT_STR2(x) #x
 #define HT_STR(x) HT_STR2(x)
 #define HT_SMEM_BYTES (HT_SMEM_DOUBLES * 8)
-#define HT_WORKER_DOUBLES (GSUM_TILE * GSUM_LDS + 3 * GSUM_TILE)     // factor worker: tile + diag + scratch ints
+#define HT_WORKER_DOUBLES (GSUM_TILE * GSUM_LDS + 4 * GSUM_TILE)     // factor worker: tile + diag + scratch + reciprocal pivots
+#define HT_RINV (3 * GSUM_TILE)                                      // offset of the reciprocal pivots 1 / L_jj behind dg
 #define HT_NSTAT 40
 #ifndef HT_LEAN_POTRF
 #define HT_LEAN_POTRF 1
@@ -188,18 +189,21 @@ __device__ __forceinline__ void ht_trsm_dinv(Acc &T, const double *Ms, int g, in
 // diagonal blocks, the INVERSES of the diagonal blocks on them, zeros above.  Threads 64..127 copy the off-diagonal
 // part while thread (cb, j) < 64 solves  L_blk x = e_j  by substitution in registers (reciprocal pivots, one multiply
 // per step on the chain) and stores its column.  S is not modified.
-__device__ __forceinline__ void ht_write_mkk(const double *S, const double *dg, double *Mt, bool fail) {
+__device__ __forceinline__ void ht_write_mkk(const double *S, const double *rinv, double *Mt, bool fail) {
     const int tid = EPI_TID;
     if (tid < 64) {
         const int cb = tid >> 3, j = tid & 7;
         const double *blk = S + (cb * 8) * GSUM_LDS + cb * 8;
-        double x[8];
+        // right-looking: as soon as x[n] is final every later row takes its term (independent FMAs), so the dependent chain
+        // is one multiply and one FMA per row; each row still sums its terms in the order n = 0, 1, ...
+        double x[8], sacc[8];
 #pragma unroll
-        for (int m = 0; m < 8; m++) {
-            double s = (m == j) ? 1.0 : 0.0;
+        for (int m = 0; m < 8; m++) sacc[m] = (m == j) ? 1.0 : 0.0;
 #pragma unroll
-            for (int n = 0; n < m; n++) s = fma(-blk[m * GSUM_LDS + n], x[n], s);
-            x[m] = (m >= j) ? s * (1.0 / dg[cb * 8 + m]) : 0.0;
+        for (int n = 0; n < 8; n++) {
+            x[n] = (n >= j) ? sacc[n] * rinv[cb * 8 + n] : 0.0;
+#pragma unroll
+            for (int m = n + 1; m < 8; m++) sacc[m] = fma(-blk[m * GSUM_LDS + n], x[n], sacc[m]);
         }
 #pragma unroll
         for (int m = 0; m < 8; m++) Mt[(cb * 8 + m) * GSUM_TILE + cb * 8 + j] = fail ? nan("") : x[m];
@@ -226,7 +230,8 @@ __device__ __forceinline__ void ht_write_mkk(const double *S, const double *dg, 
 //   S  one thread per row below the block substitutes its 8 entries against the scratch block (64-cycle steps);
 //   B  rank-8 DMMA update of the trailing 8x8 blocks — with one block of look-ahead: warp 3 updates the NEXT diagonal
 //      block first and factors it (F of the next step) while warps 0-2 update the rest.
-// Scratch behind the tile: dg[0..63] diag(L), dg[64..127] the factored block (row major 8x8), dg[136..143] 1 / L_jj.
+// Scratch behind the tile: dg[0..63] diag(L), dg[64..127] the factored block (row major 8x8), dg[136..143] 1 / L_jj of the
+// current block, dg[192..255] 1 / L_jj of the whole tile (= rsqrt of the pivot: what the block inverses are scaled with).
 // *s_fail: failing column (1-based, LAPACK potrf convention), 0 = ok; zeroed by the caller.
 __device__ __forceinline__ void potrf_lean_factor_block(double *S, double *dg, int *s_fail, int cb, int lane) {
     const int c0 = cb * 8;
@@ -249,7 +254,7 @@ __device__ __forceinline__ void potrf_lean_factor_block(double *S, double *dg, i
         if (!(d > 0.0) && fail == 0) fail = c0 + j + 1;
         const double rs = rsqrt(d);
         a[j][j] = d * rs;
-        if (lane == j) { rsd[j] = rs; dg[c0 + j] = d * rs; }
+        if (lane == j) { rsd[j] = rs; dg[c0 + j] = d * rs; dg[HT_RINV + c0 + j] = rs; }
 #pragma unroll
         for (int m = j + 1; m < 8; m++) a[m][j] *= rs;
 #pragma unroll
@@ -282,7 +287,10 @@ __device__ __forceinline__ void potrf_lean_update_block(double *S, int cb, int r
     double2 o; o.x = c0v; o.y = c1v;
     *reinterpret_cast<double2 *>(S + off) = o;
 }
-__device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fail) {
+#ifndef HT_POTRF_TWO_SITES
+#define HT_POTRF_TWO_SITES 1
+#endif
+__device__ __forceinline__ void tile_potrf_lean_two_sites(double *S, double *dg, int *s_fail) {
     const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
@@ -335,6 +343,66 @@ __device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fa
     CONS_SYNC();
 }
 
+__device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fail) {
+    const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
+#if HT_POTRF_TWO_SITES
+    tile_potrf_lean_two_sites(S, dg, s_fail);
+    return;
+#endif
+    // ONE copy of every phase (the loop is not unrolled and the block factorisation has a single call site): the code of a
+    // tile stays within the 32 KB instruction cache level of the SM — a phase fetched from L2 costs more than it computes.
+#pragma unroll 1
+    for (int cb = 0; cb < 8; cb++) {
+        // ---- B of step cb-1 with look-ahead, then F of block cb ----  blocks (rb, cb2), cb-1 < cb2 <= rb <= 7, numbered row by
+        // row; block 0 = (cb, cb) is warp 3's, which factors it at once while warps 0-2 update the rest
+        if (w == 3) {
+            if (cb > 0) {
+                potrf_lean_update_block(S, cb - 1, cb, cb, g, t);
+                __syncwarp();
+            }
+            potrf_lean_factor_block(S, dg, s_fail, cb, lane);
+        } else if (cb > 0) {
+            const int nt = 8 - cb, nblk = nt * (nt + 1) / 2;
+#pragma unroll 1
+            for (int blk = 1 + w; blk < nblk; blk += 3) {
+                int rbi = 0, rem = blk;
+                while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
+                potrf_lean_update_block(S, cb - 1, cb + rbi, cb + rem, g, t);
+            }
+        }
+        CONS_SYNC();
+        if (cb == 7) break;
+        {
+            // ---- S ----  row rr = c0 + 8 + tid
+            const int c0 = cb * 8, rr = c0 + 8 + tid;
+            if (rr < GSUM_TILE) {
+                double *row = S + rr * GSUM_LDS + c0;
+                double x[8];
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(row + c);
+                    x[c] = v.x; x[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double v = x[c];
+#pragma unroll
+                    for (int m = 0; m < c; m++) v = fma(-x[m], wb[c * 8 + m], v);
+                    x[c] = v * rsd[c];
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    double2 v; v.x = x[c]; v.y = x[c + 1];
+                    *reinterpret_cast<double2 *>(row + c) = v;
+                }
+            }
+        }
+        CONS_SYNC();
+    }
+}
+
 // ---- factor worker: one 128-thread group of a factor CTA ------------------------------------------------------------
 // The first nf0 entries of the factor list are the column-0 tiles: nothing precedes them, so at the start of the launch
 // EVERY CTA can take some (phase 0, own counter; `helper` = a math group of a GEMM CTA, which leaves after that phase)
@@ -382,7 +450,7 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
         const int fail = *s_fail;
         // Critical path first: M_kk (what the panel tasks of this column wait for), then the flag; L_kk itself, the
         // log-determinant and the status are outputs nobody inside the launch reads.
-        ht_write_mkk(S, dg, D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), fail != 0);
+        ht_write_mkk(S, dg + HT_RINV, D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), fail != 0);
         CONS_SYNC();                                  // every thread's M stores are ordered before the release below
         if (tid == 0) st_release(flag, 2);
         if (fail && tid == 0 && P.info[b] == 0) P.info[b] = k * GSUM_TILE + fail;
@@ -394,14 +462,6 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
             v.y = (c + 1 <= r) ? S[r * GSUM_LDS + c + 1] : 0.0;
             if (fail) { v.x = v.y = nan(""); }
             *reinterpret_cast<double2 *>(C + (int64_t)r * P.ld + c) = v;
-        }
-        if (P.logdet_part && tid < 32) {
-            // 2 * sum log(L_jj), same form as gsum/models.py:1015,1250; padding columns (>= n) contribute log 1 = 0
-            double v = 0.0;
-            for (int j = tid; j < GSUM_TILE; j += 32)
-                if (k * GSUM_TILE + j < P.n) v += log(dg[j]);
-            v = warp_sum(v);
-            if (tid == 0) P.logdet_part[(int64_t)b * P.T + k] = fail ? nan("") : 2.0 * v;
         }
         CONS_SYNC();                                  // S and dg are reused by the next tile
         if (st && tid == 0) { st[0] += t1 - t0; st[1] += clock64() - t1; st[2] += 1; st[3] += t2 - t1; st[4] += t3 - t2; }
@@ -712,6 +772,18 @@ __global__ void ht_init_kernel(int *flags, int *ctl, int64_t batch, int Trows, i
     const int k = (int)(idx % T), i = (int)((idx / T) % Trows);
     flags[idx] = (factor_done && i < T) ? (i == k ? 2 : 1) : 0;
 }
+// Log-determinant parts from the finished factor: (batch, T) entries 2 * sum_j log(L_jj) over the 64 columns of diagonal tile
+// k — same form as gsum/models.py:1015,1250; padding columns (>= n) contribute log 1 = 0; a failed tile was written as NaN and
+// gives NaN.  A kernel of its own so that log() is not part of the factor / chain workers' code (instruction-cache footprint).
+__global__ void __launch_bounds__(32) ht_logdet_kernel(BorderedBatch P) {
+    const int k = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const double *C = P.A + (int64_t)b * P.bstride + (int64_t)k * GSUM_TILE * P.ld + k * GSUM_TILE;
+    double v = 0.0;
+    for (int j = tid; j < GSUM_TILE; j += 32)
+        if (k * GSUM_TILE + j < P.n) v += log(C[(int64_t)j * P.ld + j]);
+    v = warp_sum(v);
+    if (tid == 0) P.logdet_part[(int64_t)b * P.T + k] = 2.0 * v;
+}
 // M_kk tiles from an existing factor (solve_only calls): one 128-thread CTA per diagonal tile
 __global__ void __launch_bounds__(CHOL_THREADS) ht_mkk_from_factor_kernel(BorderedBatch P, double *M) {
     __shared__ __align__(16) double S[GSUM_TILE * GSUM_LDS];
@@ -722,24 +794,27 @@ __global__ void __launch_bounds__(CHOL_THREADS) ht_mkk_from_factor_kernel(Border
         const int r = e >> 6, c = e & 63;
         S[r * GSUM_LDS + c] = C[(int64_t)r * P.ld + c];
     }
-    if (tid < GSUM_TILE) dg[tid] = C[(int64_t)tid * P.ld + tid];
+    if (tid < GSUM_TILE) dg[tid] = 1.0 / C[(int64_t)tid * P.ld + tid];
     __syncthreads();
     ht_write_mkk(S, dg, M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE), false);
 }
 
-// Chain mode (chain.cuh): the diagonal band belongs to the chain workers; the GEMM list holds, per column k, the two pre
-// tasks of the next band step first (flag bit 1: pre-panel (k+1, k) without triangular solve, pre-diag (k+1, k+1) without
-// its last term — neither depends on column k), then the panel tasks of rows >= k+2 and of the border rows.
+// Chain mode (chain.cuh): the diagonal band belongs to the chain CTAs; the GEMM list holds the panel tasks of rows >= k+2
+// and of the border rows, and the pre tasks (flag bit 1) that prepare the band tiles without their last two terms.
 static inline void ht_build_chain_tasks(std::vector<int4> &gemm, int T, int Trows, int batch, bool thin_last) {
     gemm.clear();
     auto fl = [&](int i) { return (thin_last && i == Trows - 1 && i >= T) ? 1 : 0; };
     for (int k = 0; k < T; k++) {
-        if (k + 1 < T && k >= 1) {
-            for (int b = 0; b < batch; b++) gemm.push_back(make_int4(k + 1, k, b, 2));
-            for (int b = 0; b < batch; b++) gemm.push_back(make_int4(k + 1, k + 1, b, 2));
-        }
-        for (int i = (k + 1 < T ? k + 2 : k + 1); i < Trows; i++)
+        // panel tasks of column k: rows >= k+2 (row k+1 is the chain CTA's) and the border rows.  Right behind tile (k+3, k)
+        // — the youngest operand they need — come the two pre tasks of the band step k+2 -> k+3, tiles (k+3, k+2) and
+        // (k+3, k+3) without their last two terms: claimed two columns ahead of their use.
+        for (int i = (k + 1 < T ? k + 2 : k + 1); i < Trows; i++) {
             for (int b = 0; b < batch; b++) gemm.push_back(make_int4(i, k, b, fl(i)));
+            if (i == k + 3 && k + 3 < T) {
+                for (int b = 0; b < batch; b++) gemm.push_back(make_int4(k + 3, k + 2, b, 2));
+                for (int b = 0; b < batch; b++) gemm.push_back(make_int4(k + 3, k + 3, b, 2));
+            }
+        }
     }
 }
 

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
     const BorderedBatch &P = D.P;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool st_on = STATS && D.stats != nullptr;
-    long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long st[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     const long long st_t0 = STATS ? clock64() : 0;
 #define HT_T0() const long long _t = st_on ? clock64() : 0
 #define HT_ACC(q) do { if (st_on) st[q] += clock64() - _t; } while (0)
@@ -137,12 +137,13 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
         if (w >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); return; }
         asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HX_MATH_REGS) ";");
         if (D.chain) {
-            if (tid >= CH_THREADS) return;
+            if (tid >= CH_THREADS + 32) return;
+            if (tid >= CH_THREADS) { ht_chain_publisher(D, smem, (int)blockIdx.x); return; }
             if (tid >= 128) { ht_chain_helper(D, smem, (int)blockIdx.x); return; }
             ht_chain_worker(D, smem, (int)blockIdx.x, st_on ? st : nullptr);
             if (st_on && tid == 0) {
                 long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT;
-                o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; o[5] = st[4]; o[6] = st[5];
+                o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; o[5] = st[4]; o[6] = st[5]; o[7] = st[6]; o[8] = st[7]; o[9] = st[8];
             }
             return;
         }
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             if (tk.x < 0) break;
             const int i = tk.x, k = tk.y, b = tk.z;
             const bool diag = (i == k), thin = (tk.w & 1) != 0, pre = (tk.w & 2) != 0;
-            const int nj = (pre && diag) ? k - 1 : k;           // chain mode: a pre-diag tile leaves its last term to the chain worker
+            const int nj = pre ? (diag ? k - 2 : k - 1) : k;    // chain mode: a pre tile leaves its last two terms to the chain CTA
             const bool border = (i >= P.T);
             const CUtensorMap *mapI = border ? (thin ? &maps.W8 : &maps.W) : &maps.A;
             const int rowI = border ? b * rowsW + (i - P.T) * GSUM_TILE : b * rowsA + i * GSUM_TILE;
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             if (!alive || tk.x < 0) break;             // no CTA-level barrier anywhere in this role: a warp may leave alone
             const int i = tk.x, k = tk.y, b = tk.z;
             const bool diag = (i == k), thin = (tk.w & 1) != 0, pre = (tk.w & 2) != 0;
-            const int nj = (pre && diag) ? k - 1 : k;
+            const int nj = pre ? (diag ? k - 2 : k - 1) : k;
             double *Ab = P.A + (int64_t)b * P.bstride;
             double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
                                    : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;

@@ -123,3 +123,47 @@ __global__ void __launch_bounds__(256) scale_cov_kernel(double *K, int64_t ld, i
         K[r * ld + c] = (ref_mat * ratio_sum) * (factor * (K[r * ld + c] + kadd));
     }
 }
+
+// q_c = d_c^T A d_c, d_c = y_c - mean (mahalanobis(inv=...), gsum/helpers.py:521-522).  One warp per row i of A: the lanes
+// stride over the columns (coalesced row reads), each accumulating (A d)_i for QF_C curves at a time; the centred curves of
+// the chunk sit in shared memory.  part[(i, c)] = d_ic (A d_c)_i is written per row and summed in a fixed order by
+// quadform_reduce_kernel: deterministic, no floating-point atomics.  HBM traffic: A once per QF_C curves.
+#define QF_C 8
+#define QF_WARPS 8
+__global__ void __launch_bounds__(32 * QF_WARPS) quadform_rows_kernel(const double *__restrict__ A, int64_t n, const double *__restrict__ mean,
+                                                                        const double *__restrict__ Y, int64_t n_curves, int64_t c0,
+                                                                        double *__restrict__ part) {
+    extern __shared__ double qf_d[];                 // (n, QF_C) centred curves of this chunk
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nc = (int)((n_curves - c0) < QF_C ? (n_curves - c0) : QF_C);
+    for (int64_t e = tid; e < n * QF_C; e += blockDim.x) {
+        const int64_t j = e / QF_C; const int c = (int)(e % QF_C);
+        qf_d[e] = c < nc ? Y[j * n_curves + c0 + c] - mean[j] : 0.0;
+    }
+    __syncthreads();
+    for (int64_t i = (int64_t)blockIdx.x * QF_WARPS + w; i < n; i += (int64_t)gridDim.x * QF_WARPS) {
+        double acc[QF_C];
+#pragma unroll
+        for (int c = 0; c < QF_C; c++) acc[c] = 0.0;
+        const double *row = A + i * n;
+        for (int64_t j = lane; j < n; j += 32) {
+            const double a = row[j];
+#pragma unroll
+            for (int c = 0; c < QF_C; c++) acc[c] = fma(a, qf_d[j * QF_C + c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < QF_C; c++) {
+            const double v = warp_sum(acc[c]);
+            if (lane == 0 && c < nc) part[i * QF_C + c] = qf_d[i * QF_C + c] * v;
+        }
+    }
+}
+__global__ void quadform_reduce_kernel(const double *__restrict__ part, int64_t n, int64_t n_curves, int64_t c0, double *__restrict__ q) {
+    __shared__ double red[32];
+    const int c = blockIdx.x;
+    if (c0 + c >= n_curves) return;
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += part[i * QF_C + c];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) q[c0 + c] = s;
+}

@@ -91,11 +91,22 @@ def cholesky_errors(y, mean, chol):
 
 
 def mahalanobis(y, mean, chol=None, inv=None, sqrt_mat=None):
-    """Mahalanobis distance of each curve in y (n_curves, N) (gsum/helpers.py:512-522, `chol` branch)."""
+    """Mahalanobis distance of each curve in y (n_curves, N) (gsum/helpers.py:512-522).
+
+    `chol`: norms of L^{-1}(y - mean) (forward solve on the device).  `inv`: sqrt of (y - mean)^T inv (y - mean) per curve
+    (quadratic forms on the device; the reference's np.diag of the full product).  `sqrt_mat`: the reference calls
+    `numpy.linalg.solve(sqrt_mat, ..., lower=True)` (helpers.py:508-509), which raises TypeError on every numpy — the
+    same error is raised here, there is no result to reproduce."""
     if (chol is not None) and (inv is not None) and (sqrt_mat is not None):
         raise ValueError("Only one of chol, inv, or sqrt_mat can be given")
+    if chol is None and sqrt_mat is not None:
+        raise TypeError("solve() got an unexpected keyword argument 'lower'")
     if chol is None:
-        raise NotImplementedError("gsum_b200: mahalanobis is implemented for the `chol` argument only")
+        if inv is None:
+            raise TypeError("mahalanobis needs one of chol, inv, sqrt_mat")
+        y2 = np.atleast_2d(np.asarray(y, dtype=np.float64))
+        q = ops.quadratic_forms(inv, mean, np.ascontiguousarray(y2.T))
+        return np.squeeze(np.sqrt(q))
     y = np.asarray(y, dtype=np.float64)
     single = y.ndim == 1
     _, md2 = ops.cholesky_errors(chol, mean, np.ascontiguousarray(np.atleast_2d(y).T), want_errors=False, want_md2=True)

@@ -297,6 +297,19 @@ def cholesky_errors(L, mean, Y, want_errors=True, want_md2=False, ctx=None):
     return E, md2
 
 
+def quadratic_forms(A, mean, Y, ctx=None):
+    """(y_c - mean)^T A (y_c - mean) for every column of Y (n, n_curves) — the diagonal of mahalanobis(inv=...)'s product."""
+    ctx = ctx or default_context()
+    A, Y = as_f64(A), as_f64(Y)
+    n = A.shape[0]
+    if A.shape != (n, n) or Y.shape[0] != n:
+        raise ValueError("quadratic_forms: A must be (n, n) and Y (n, n_curves)")
+    mean = _vec(mean, n, "mean")
+    q = np.empty(Y.shape[1])
+    ctx.check(ctx.lib.gsum_quadratic_forms(ctx.handle, _p(A), n, _p(mean), _p(Y), Y.shape[1], _p(q), MEM_HOST), "gsum_quadratic_forms")
+    return q
+
+
 def pivoted_cholesky(M, ctx=None):
     """LAPACK dpstrf(lower) on the device: returns (G, Lp, piv, rank, status); M = G G^T, P^T M P = Lp Lp^T."""
     ctx = ctx or default_context()

@@ -184,6 +184,12 @@ int gsum_process_cov(gsum_ctx *ctx, int32_t d, const double *ls, int32_t ls_dim,
 int gsum_cholesky_errors(gsum_ctx *ctx, const double *L, int64_t n, const double *mean, const double *Y,
                          int64_t n_curves, double *E, double *md2, int32_t mem_kind);
 
+/* gsum_quadratic_forms: q_c = (y_c - mean)^T A (y_c - mean) for every column c of Y (n, n_curves); A (n, n) row-major,
+ *   not required to be symmetric.  Replaces np.diag((y - mean) @ inv @ (y - mean).T) of mahalanobis(inv=...)
+ *   (gsum/helpers.py:521-522) without forming the (n_curves, n_curves) product. */
+int gsum_quadratic_forms(gsum_ctx *ctx, const double *A, int64_t n, const double *mean, const double *Y, int64_t n_curves,
+                         double *q, int32_t mem_kind);
+
 /* gsum_pivoted_cholesky: LAPACK dpstrf(lower) semantics (gsum/helpers.py:185-199): M (n,n) symmetric PSD ->
  *   Lp (n,n) lower factor of P^T M P, piv (n,) 0-based, rank; G_out (n,n) or NULL = Lp[p_inv] (M = G G^T).
  *   Returns 1 (LinAlgError 'M is not positive-semidefinite') when rank < n, like helpers.py:189-190. */

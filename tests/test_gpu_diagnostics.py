@@ -274,3 +274,25 @@ def test_coverage_nested_and_unordered_intervals_agree(ctx, golden):
     Yb[:, 0] = upper[50]
     Yb[:, 1] = lower[70]
     assert np.array_equal(d.credible_interval(Yb, iv), o.credible_interval(Yb, g["mean"], g["cov"], iv))
+
+
+@pytest.mark.gpu
+def test_mahalanobis_inv_and_sqrt_mat():
+    """mahalanobis(inv=...) (gsum/helpers.py:521-522; the notebook's Mahalanobis identity uses it) against the numpy expression
+    of the reference and against the `chol` route; sqrt_mat raises the reference's own TypeError (helpers.py:508-509)."""
+    import gsum_b200 as gb
+    rs = np.random.RandomState(5)
+    for n, k in [(7, 1), (64, 3), (301, 11)]:
+        X = np.linspace(0, 1, n)[:, None]
+        cov = 1.3 * (RBF(0.2)(X) + 1e-5 * np.eye(n))
+        mean = rs.randn(n)
+        L = np.linalg.cholesky(cov)
+        y = mean + (L @ rs.randn(n, k)).T
+        inv = np.linalg.inv(cov)
+        got = gb.mahalanobis(y, mean, inv=inv)
+        want = np.squeeze(np.sqrt(np.diag((y - mean) @ inv @ (y - mean).T)))
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-10       # entries of inv ~ 1e5: the sum cancels five digits
+        via_chol = gb.mahalanobis(y, mean, chol=L)
+        assert np.max(np.abs(np.atleast_1d(got) - via_chol) / via_chol) < 1e-6        # cond(cov) ~ 1e5 in inv
+    with pytest.raises(TypeError):
+        gb.mahalanobis(y, mean, sqrt_mat=L)
