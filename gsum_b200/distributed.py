@@ -21,9 +21,12 @@ from __future__ import annotations
 
 import numpy as np
 
+import os
+
 from . import ops
 
-__all__ = ["shard_indices", "assemble_blocks", "lml_grid_sharded", "shard_range", "sample_coverage_sharded", "predict_sharded"]
+__all__ = ["shard_indices", "assemble_blocks", "lml_grid_sharded", "shard_range", "sample_coverage_sharded", "predict_sharded",
+           "release_graphs"]
 
 
 def shard_indices(n_ls, world_size, rank):
@@ -75,6 +78,29 @@ def lml_grid_sharded(X, dy, ref, orders, ls, Q, group=None, normalize=False, **k
 
 _stream_ctx = {}
 _grid_plans = {}
+_USE_GRAPH = os.environ.get("GSUM_B200_GRID_GRAPH", "1") != "0"       # replay the sharded grid's device sequence as one CUDA graph (GSUM_B200_GRID_GRAPH=0 disables)
+_PROF = None            # dev probe (tools/e2e_sharded_breakdown.py): dict of accumulated host seconds per section
+
+
+def release_graphs():
+    """Drop the cached staging plans and their CUDA graphs.  Call it BEFORE `torch.distributed.destroy_process_group()`:
+    a captured graph holds the NCCL communicator's kernels, and destroying the communicator first blocks (observed with
+    NCCL 2.28 / torch 2.11 at world size 2)."""
+    if _grid_plans:
+        import torch
+        torch.cuda.synchronize()
+        for plan in list(_grid_plans.values()):
+            plan.graphs.clear()
+        _grid_plans.clear()
+        torch.cuda.synchronize()
+
+
+def _tick(name, t0):
+    import time
+    t1 = time.perf_counter()
+    if _PROF is not None:
+        _PROF[name] = _PROF.get(name, 0.0) + (t1 - t0)
+    return t1
 
 
 class _GridPlan:
@@ -98,17 +124,24 @@ class _GridPlan:
         self.lse = torch.empty(1, dtype=torch.float64, device=dev)
         self.h_out = torch.empty((2, n_q, per * world), dtype=torch.float64, pin_memory=True)
         self.h_lse = torch.empty(1, dtype=torch.float64, pin_memory=True)
+        self.graphs = {}        # scalar arguments -> 1 (seen once, eager) | torch.cuda.CUDAGraph | -1 (capture failed)
 
 
 def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normalize, kw):
     """NCCL path: this rank's block never leaves the device between the likelihood kernels and the all-gather — the inputs
     go up in ONE copy from a persistent pinned buffer, the kernels and the collective are enqueued on torch's current
     stream, the round-robin deal is undone by one strided copy on the device into the final layout, and ONE device-to-host
-    copy into pinned memory returns the grid (`_GridPlan`: no allocation on the per-call path)."""
+    copy into pinned memory returns the grid (`_GridPlan`: no allocation on the per-call path).
+
+    From the third call with the same shapes and scalar arguments on, the whole device sequence (upload, kernels, all-gather,
+    permute, download) is replayed as ONE CUDA graph captured from the second call: with the grid sharded eight ways the
+    kernels take less time than the host needs to enqueue them one by one."""
+    import time
     import torch
     import torch.distributed as dist
     from . import _lib
 
+    t0 = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device())
     stream = torch.cuda.current_stream(dev)
     key = (dev.index, stream.cuda_stream)
@@ -123,43 +156,78 @@ def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normaliz
     orders32 = np.asarray(orders, dtype=np.int32)
     dy = np.asarray(dy, dtype=np.float64)
     n_mine = len(mine)
-    sizes = (X.size, dy.size, n, max(n_mine, 1) * ls.shape[1], Q.size, n_q, (orders32.size + 1) // 2)
+    ls_dim = ls.shape[1]
+    sizes = (X.size, dy.size, n, max(n_mine, 1) * ls_dim, Q.size, n_q, (orders32.size + 1) // 2)
     pkey = key + sizes + (per, world, n_ls, id(group))
     plan = _grid_plans.get(pkey)
     if plan is None:
         if len(_grid_plans) > 8:
             _grid_plans.clear()
         plan = _grid_plans[pkey] = _GridPlan(dev, sizes, n_q, per, world, n_ls, n_mine)
+    scalars = (bool(kw.get("q_x_dependent", False)), float(kw.get("constant", 1.0)), float(kw.get("noise", 0.0)),
+               float(kw.get("nugget", 1e-10)), float(kw.get("center0", 0.0)), float(kw.get("disp0", 0.0)), float(kw.get("df0", 1.0)),
+               float(kw.get("scale0", 1.0)), bool(kw.get("student", False)), detf is None, bool(normalize), Q.shape, orders32.size)
     if n_mine:
         h, o = plan.h_in_np, plan.offs
         h[o[0]:o[1]] = X.ravel()
         h[o[1]:o[2]] = dy.ravel()
         h[o[2]:o[3]] = np.asarray(ref, dtype=np.float64)          # broadcasts a scalar
-        h[o[3]:o[3] + n_mine * ls.shape[1]] = ls[mine].ravel()
+        h[o[3]:o[3] + n_mine * ls_dim] = ls[mine].ravel()
         h[o[4]:o[5]] = Q.ravel()
         h[o[5]:o[6]] = 0.0 if detf is None else np.asarray(detf, dtype=np.float64)
         h[o[6]:o[7]].view(np.int32)[:orders32.size] = orders32
-        plan.d_in.copy_(plan.h_in, non_blocking=True)
-        v = plan.v
-        ops.lml_grid_device(ctx, v[0].view(n, -1), v[1].view(n, -1), v[2], v[6].view(torch.int32)[:orders32.size],
-                            v[3][:n_mine * ls.shape[1]].view(n_mine, -1), v[4].view(Q.shape), None if detf is None else v[5],
-                            plan.out, q_x_dependent=bool(kw.get("q_x_dependent", False)), constant=kw.get("constant", 1.0),
-                            noise=kw.get("noise", 0.0), nugget=kw.get("nugget", 1e-10), center0=kw.get("center0", 0.0),
-                            disp0=kw.get("disp0", 0.0), df0=kw.get("df0", 1.0), scale0=kw.get("scale0", 1.0),
-                            student=bool(kw.get("student", False)))
-        if plan.out is not plan.send:
-            plan.send[:, :n_mine] = plan.out[:, :n_mine]
-    dist.all_gather_into_tensor(plan.recv, plan.send, group=group)            # the single collective of the path
-    # rank r's local column j is length scale r + j * world: (world, n_q, per) -> (n_q, per, world), one strided copy
-    plan.full.view(n_q, per, world).copy_(plan.recv.view(world, n_q, per).permute(1, 2, 0))
-    plan.h_out[0].copy_(plan.full, non_blocking=True)
-    if normalize:
-        full_d = plan.full if per * world == n_ls else plan.full[:, :n_ls].contiguous()
-        ops.grid_normalize_device(ctx, full_d, plan.post, plan.lse)
-        plan.h_out[1, :, :n_ls].copy_(plan.post, non_blocking=True)
-        plan.h_lse.copy_(plan.lse, non_blocking=True)
+    t0 = _tick("pack", t0)
+
+    def enqueue():
+        if n_mine:
+            plan.d_in.copy_(plan.h_in, non_blocking=True)
+            v = plan.v
+            ops.lml_grid_device(ctx, v[0].view(n, -1), v[1].view(n, -1), v[2], v[6].view(torch.int32)[:scalars[12]],
+                                v[3][:n_mine * ls_dim].view(n_mine, -1), v[4].view(scalars[11]), None if scalars[9] else v[5],
+                                plan.out, q_x_dependent=scalars[0], constant=scalars[1], noise=scalars[2], nugget=scalars[3],
+                                center0=scalars[4], disp0=scalars[5], df0=scalars[6], scale0=scalars[7], student=scalars[8])
+            if plan.out is not plan.send:
+                plan.send[:, :n_mine] = plan.out[:, :n_mine]
+        dist.all_gather_into_tensor(plan.recv, plan.send, group=group)            # the single collective of the path
+        # rank r's local column j is length scale r + j * world: (world, n_q, per) -> (n_q, per, world), one strided copy
+        plan.full.view(n_q, per, world).copy_(plan.recv.view(world, n_q, per).permute(1, 2, 0))
+        plan.h_out[0].copy_(plan.full, non_blocking=True)
+        if normalize:
+            full_d = plan.full if per * world == n_ls else plan.full[:, :n_ls].contiguous()
+            ops.grid_normalize_device(ctx, full_d, plan.post, plan.lse)
+            plan.h_out[1, :, :n_ls].copy_(plan.post, non_blocking=True)
+            plan.h_lse.copy_(plan.lse, non_blocking=True)
+
+    g = plan.graphs.get(scalars)
+    if isinstance(g, torch.cuda.CUDAGraph):
+        g.replay()
+    else:
+        # first call: eager (workspaces are allocated, task lists uploaded); second: capture; failures keep the eager path
+        if g == 1 and _USE_GRAPH and stream.cuda_stream != 0:
+            try:
+                stream.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    enqueue()
+                plan.graphs[scalars] = graph
+                graph.replay()
+            except Exception as e:                          # noqa: BLE001 — any capture problem: stay on direct launches
+                import warnings
+                warnings.warn(f"gsum_b200: CUDA-graph capture of the sharded grid failed ({e!r}); using direct launches")
+                plan.graphs[scalars] = -1
+                torch.cuda.synchronize()
+                enqueue()
+        else:
+            if g is None:
+                if len(plan.graphs) > 4:
+                    plan.graphs.clear()
+                plan.graphs[scalars] = 1
+            enqueue()
+    t0 = _tick("enqueue", t0)
     stream.synchronize()
+    t0 = _tick("synchronize", t0)
     full = plan.h_out[0].numpy()[:, :n_ls].copy()
+    t0 = _tick("copy out", t0)
     if normalize:
         return full, plan.h_out[1].numpy()[:, :n_ls].copy(), float(plan.h_lse[0])
     return full

@@ -195,7 +195,11 @@ def test_sharded_nccl_path_single_rank(ctx):
         dist.init_process_group("nccl", rank=0, world_size=1)
     try:
         got = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=dist.group.WORLD)
+        # the third call replays the CUDA graph captured by the second (distributed._sharded_device)
+        again = [gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=dist.group.WORLD) for _ in range(3)]
     finally:
+        from gsum_b200 import distributed as gdist
+        gdist.release_graphs()
         if created:
             dist.destroy_process_group()
-    assert np.array_equal(got, want)
+    assert np.array_equal(got, want) and all(np.array_equal(a, want) for a in again)
