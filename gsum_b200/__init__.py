@@ -1,7 +1,7 @@
 """gsum_b200 — B200-native conjugate-GP likelihood / prediction / diagnostics path of buqeye/gsum.
 
 Drop-in for the reference's hot path: same class and function names (``ConjugateGaussianProcess``,
-``ConjugateStudentProcess``, ``TruncationGP``, ``TruncationTP``, ``Diagnostic``, ``coefficients``,
+``ConjugateStudentProcess``, ``TruncationGP``, ``TruncationTP``, ``TruncationPointwise``, ``Diagnostic``, ``VariogramFourthRoot``, ``coefficients``,
 ``partials``, ``geometric_sum``, ``pivoted_cholesky``, ``cholesky_errors``, ``mahalanobis``,
 ``cartesian``); the arithmetic runs in hand-written sm_100a CUDA behind the C ABI of
 ``include/gsum_b200.h`` (``libgsum_b200.so``).  No CPU fallback: importing is cheap, the first numerical
@@ -12,10 +12,12 @@ from .helpers import (cartesian, cholesky_errors, coefficients, geometric_sum, m
 from .models import (BaseConjugateProcess, ConjugateGaussianProcess, ConjugateStudentProcess, TruncationGP,
                      TruncationProcess, TruncationTP)
 from .diagnostics import Diagnostic
+from .pointwise import TruncationPointwise
+from .variogram import VariogramFourthRoot
 
 __version__ = "0.1.0"
 __all__ = [
     "ConjugateGaussianProcess", "ConjugateStudentProcess", "TruncationGP", "TruncationTP", "TruncationProcess",
-    "BaseConjugateProcess", "Diagnostic", "cartesian", "coefficients", "partials", "geometric_sum",
+    "BaseConjugateProcess", "Diagnostic", "TruncationPointwise", "VariogramFourthRoot", "cartesian", "coefficients", "partials", "geometric_sum",
     "pivoted_cholesky", "cholesky_errors", "mahalanobis",
 ]

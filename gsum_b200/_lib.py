@@ -57,6 +57,14 @@ _SIGNATURES = {
                                    _vp, _vp, _vp, _vp, C.c_double, C.c_double, _vp, C.c_int32, C.c_double, C.c_double, _vp, C.c_int32]),
     "gsum_cholesky_errors": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, _vp, C.c_int32]),
     "gsum_quadratic_forms": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int32]),
+    "gsum_pointwise_fit": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp, C.c_double, C.c_double,
+                                     _vp, _vp, _vp, C.c_int32]),
+    "gsum_pointwise_loglike": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, _vp, _vp, C.c_int64, C.c_int64, _vp, C.c_int64,
+                                         C.c_double, C.c_double, _vp, _vp, C.c_int32]),
+    "gsum_variogram_bins": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, C.c_int32]),
+    "gsum_variogram_cov": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int32, C.c_int32, _vp,
+                                     C.c_double, C.c_double, C.c_int32, _vp, C.c_int32]),
     "gsum_pivoted_cholesky": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, C.c_int32]),
     "gsum_pc_errors": (C.c_int, [_vp, _vp, _vp, C.c_int64, _vp, _vp, C.c_int64, _vp, C.c_int32]),
     "gsum_draws": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int64, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, C.c_int32,

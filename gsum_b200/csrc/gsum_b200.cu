@@ -8,6 +8,7 @@
 #include "solve.cuh"
 #include "diag.cuh"
 #include "grad.cuh"
+#include "pointwise.cuh"
 #include "dataflow.cuh"
 #include "pipeline.cuh"
 #include "hetero.cuh"
@@ -1233,6 +1234,148 @@ extern "C" int gsum_process_cov(gsum_ctx *c, int32_t d, const double *ls, int32_
 }
 
 // ---- diagnostics ---------------------------------------------------------------------------------------------
+// ---- SURVEY.md 8(f).4 -------------------------------------------------------------------------------------------------
+static int pw_args(gsum_ctx *c, PointwiseArgs &P, const double *y, int64_t n, int n_o, const int32_t *orders, const int32_t *mask,
+                   const int32_t *excluded, int n_ex, double df0, double scale0, int mem_kind, int *n_m_out) {
+    const void *dy, *dord, *dmask, *dex = nullptr;
+    GSUM_TRY(dev_in(c, WS_DY, y, sizeof(double) * n * n_o, mem_kind, &dy));
+    GSUM_TRY(dev_in(c, WS_ORD, orders, sizeof(int) * n_o, mem_kind, &dord));
+    GSUM_TRY(dev_in(c, WS_MISC0, mask, sizeof(int) * n_o, mem_kind, &dmask));
+    if (n_ex > 0) GSUM_TRY(dev_in(c, WS_MISC1, excluded, sizeof(int) * n_ex, mem_kind, &dex));
+    P.y = (const double *)dy; P.orders = (const int *)dord; P.mask = (const int *)dmask; P.excluded = (const int *)dex; P.n_ex = n_ex;
+    P.n = n; P.n_o = n_o; P.df0 = df0; P.scale0 = scale0;
+    int n_m = 0;
+    if (mem_kind == GSUM_MEM_HOST) { for (int k = 0; k < n_o; k++) n_m += mask[k] ? 1 : 0; }
+    else {
+        int hm[PW_MAXO];
+        GSUM_CUDA(c, cudaMemcpyAsync(hm, mask, sizeof(int) * n_o, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < n_o; k++) n_m += hm[k] ? 1 : 0;
+    }
+    *n_m_out = n_m;
+    return 0;
+}
+extern "C" int gsum_pointwise_fit(gsum_ctx *c, const double *y, int64_t n, int32_t n_o, const int32_t *orders, const int32_t *mask,
+                                  const int32_t *excluded, int32_t n_ex, const double *ratio, const double *ref, double df0,
+                                  double scale0, double *coeffs, double *scale, double *trunc_scale, int32_t mem_kind) {
+    if (!c || !y || !orders || !mask || !ratio || !ref || !coeffs || !scale || !trunc_scale || n <= 0 || n_o <= 0 || n_o > PW_MAXO || n_ex < 0 ||
+        (n_ex > 0 && !excluded))
+        return gsum_fail(c, -1, "gsum_pointwise_fit: bad argument (n_o <= %d)", PW_MAXO);
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    PointwiseArgs P; int n_m;
+    GSUM_TRY(pw_args(c, P, y, n, n_o, orders, mask, excluded, n_ex, df0, scale0, mem_kind, &n_m));
+    if (n_m == 0) return gsum_fail(c, -1, "gsum_pointwise_fit: every order is excluded");
+    const void *dq, *dr;
+    GSUM_TRY(dev_in(c, WS_Q, ratio, sizeof(double) * n, mem_kind, &dq));
+    GSUM_TRY(dev_in(c, WS_REF, ref, sizeof(double) * n, mem_kind, &dr));
+    void *dc, *ds, *dt;
+    GSUM_TRY(dev_out(c, WS_IO0, coeffs, sizeof(double) * n * n_m, mem_kind, &dc));
+    GSUM_TRY(dev_out(c, WS_IO1, scale, sizeof(double) * n, mem_kind, &ds));
+    GSUM_TRY(dev_out(c, WS_IO2, trunc_scale, sizeof(double) * n * n_m, mem_kind, &dt));
+    pointwise_fit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(P, (const double *)dq, (const double *)dr, (double *)dc, (double *)ds,
+                                                                             (double *)dt, n_m);
+    LAUNCHED(c, 1);
+    GSUM_TRY(dev_out_finish(c, coeffs, dc, sizeof(double) * n * n_m, mem_kind));
+    GSUM_TRY(dev_out_finish(c, scale, ds, sizeof(double) * n, mem_kind));
+    GSUM_TRY(dev_out_finish(c, trunc_scale, dt, sizeof(double) * n * n_m, mem_kind));
+    return finish(c, mem_kind);
+}
+extern "C" int gsum_pointwise_loglike(gsum_ctx *c, const double *y, int64_t n, int32_t n_o, const int32_t *orders, const int32_t *mask,
+                                      const double *ratios, int64_t n_r, int64_t n_rat, const double *ref, int64_t n_ref, double df0,
+                                      double scale0, double *S1, double *S2, int32_t mem_kind) {
+    if (!c || !y || !orders || !mask || !ratios || !ref || !S1 || !S2 || n <= 0 || n_o <= 0 || n_o > PW_MAXO || n_r <= 0 ||
+        (n_rat != 1 && n_rat != n) || (n_ref != 1 && n_ref != n))
+        return gsum_fail(c, -1, "gsum_pointwise_loglike: bad argument (ratio / ref must have 1 or n entries)");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    PointwiseArgs P; int n_m;
+    GSUM_TRY(pw_args(c, P, y, n, n_o, orders, mask, nullptr, 0, df0, scale0, mem_kind, &n_m));
+    const void *dq, *dr, *dord_h = nullptr;
+    (void)dord_h;
+    GSUM_TRY(dev_in(c, WS_Q, ratios, sizeof(double) * n_r * n_rat, mem_kind, &dq));
+    GSUM_TRY(dev_in(c, WS_REF, ref, sizeof(double) * n_ref, mem_kind, &dr));
+    // sum of the kept orders (host copy of the two small arrays when they live on the device)
+    int ho[PW_MAXO], hm[PW_MAXO];
+    if (mem_kind == GSUM_MEM_HOST) { memcpy(ho, orders, sizeof(int) * n_o); memcpy(hm, mask, sizeof(int) * n_o); }
+    else {
+        GSUM_CUDA(c, cudaMemcpyAsync(ho, orders, sizeof(int) * n_o, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaMemcpyAsync(hm, mask, sizeof(int) * n_o, cudaMemcpyDeviceToHost, c->stream));
+        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    double so = 0.0;
+    for (int k = 0; k < n_o; k++) if (hm[k]) so += (double)ho[k];
+    void *d1, *d2;
+    GSUM_TRY(dev_out(c, WS_IO0, S1, sizeof(double) * n_r, mem_kind, &d1));
+    GSUM_TRY(dev_out(c, WS_IO1, S2, sizeof(double) * n_r, mem_kind, &d2));
+    pointwise_loglike_kernel<<<(unsigned)n_r, 256, 0, c->stream>>>(P, (const double *)dq, (int)n_rat, (const double *)dr, (int)n_ref, n_m, so,
+                                                                   (double *)d1, (double *)d2);
+    LAUNCHED(c, 1);
+    GSUM_TRY(dev_out_finish(c, S1, d1, sizeof(double) * n_r, mem_kind));
+    GSUM_TRY(dev_out_finish(c, S2, d2, sizeof(double) * n_r, mem_kind));
+    return finish(c, mem_kind);
+}
+extern "C" int gsum_variogram_bins(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *z, int32_t ncurves,
+                                   const double *bounds, int32_t nbnd, int32_t *bin_grid, double *hij, int32_t *bin_idx, double *dij,
+                                   int64_t *counts, double *hsum, double *dsum, int32_t mem_kind) {
+    if (!c || !X || !z || !bounds || !bin_grid || !hij || !bin_idx || !dij || !counts || !hsum || !dsum || n < 2 || d <= 0 || ncurves <= 0 || nbnd <= 0)
+        return gsum_fail(c, -1, "gsum_variogram_bins: bad argument");
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const int64_t np_ = n * (n - 1) / 2;
+    const int nb = nbnd + 1;
+    const void *dX, *dz, *db;
+    GSUM_TRY(dev_in(c, WS_X, X, sizeof(double) * n * d, mem_kind, &dX));
+    GSUM_TRY(dev_in(c, WS_DY, z, sizeof(double) * n * ncurves, mem_kind, &dz));
+    GSUM_TRY(dev_in(c, WS_Q, bounds, sizeof(double) * nbnd, mem_kind, &db));
+    void *dgrid, *dh, *dbi, *dd, *dcnt, *dhs, *dds;
+    GSUM_TRY(dev_out(c, WS_MAT, bin_grid, sizeof(int) * n * n, mem_kind, &dgrid));
+    GSUM_TRY(dev_out(c, WS_IO0, hij, sizeof(double) * np_, mem_kind, &dh));
+    GSUM_TRY(dev_out(c, WS_IO1, bin_idx, sizeof(int) * np_, mem_kind, &dbi));
+    GSUM_TRY(dev_out(c, WS_IO2, dij, sizeof(double) * np_ * ncurves, mem_kind, &dd));
+    GSUM_TRY(dev_out(c, WS_MISC0, counts, sizeof(long long) * nb, mem_kind, &dcnt));
+    GSUM_TRY(dev_out(c, WS_MISC1, hsum, sizeof(double) * nb, mem_kind, &dhs));
+    GSUM_TRY(dev_out(c, WS_MISC2, dsum, sizeof(double) * nb * ncurves, mem_kind, &dds));
+    variogram_grid_kernel<<<(unsigned)((n * n + 255) / 256), 256, 0, c->stream>>>((const double *)dX, n, d, (const double *)db, nbnd, (int *)dgrid);
+    variogram_pairs_kernel<<<(unsigned)((np_ + 255) / 256), 256, 0, c->stream>>>((const double *)dX, (const double *)dz, n, d, ncurves, (const double *)db,
+                                                                                 nbnd, (double *)dh, (int *)dbi, (double *)dd);
+    variogram_binsum_kernel<<<nb, 256, 0, c->stream>>>((const double *)dh, (const int *)dbi, (const double *)dd, np_, ncurves, (long long *)dcnt,
+                                                       (double *)dhs, (double *)dds);
+    LAUNCHED(c, 3);
+    GSUM_TRY(dev_out_finish(c, bin_grid, dgrid, sizeof(int) * n * n, mem_kind));
+    GSUM_TRY(dev_out_finish(c, hij, dh, sizeof(double) * np_, mem_kind));
+    GSUM_TRY(dev_out_finish(c, bin_idx, dbi, sizeof(int) * np_, mem_kind));
+    GSUM_TRY(dev_out_finish(c, dij, dd, sizeof(double) * np_ * ncurves, mem_kind));
+    GSUM_TRY(dev_out_finish(c, counts, dcnt, sizeof(long long) * nb, mem_kind));
+    GSUM_TRY(dev_out_finish(c, hsum, dhs, sizeof(double) * nb, mem_kind));
+    GSUM_TRY(dev_out_finish(c, dsum, dds, sizeof(double) * nb * ncurves, mem_kind));
+    return finish(c, mem_kind);
+}
+extern "C" int gsum_variogram_cov(gsum_ctx *c, const int32_t *i1, const int32_t *j1, int64_t nb1, const int32_t *i2, const int32_t *j2,
+                                  int64_t nb2, const int32_t *bin_grid, int64_t n, const double *gamma_tilde, int32_t nbins, int32_t ncurves,
+                                  const double *tab, double var_factor, double corr_factor, int32_t same_is_one, double *out, int32_t mem_kind) {
+    if (!c || !i1 || !j1 || !i2 || !j2 || !bin_grid || !gamma_tilde || !tab || !out || nb1 <= 0 || nb2 <= 0 || n < 2 || nbins <= 0 ||
+        ncurves <= 0 || ncurves > VG_MAXC)
+        return gsum_fail(c, -1, "gsum_variogram_cov: bad argument (1 <= ncurves <= %d, non-empty bins)", VG_MAXC);
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    VarioCovArgs P;
+    const void *p;
+    GSUM_TRY(dev_in(c, WS_IO0, i1, sizeof(int) * nb1, mem_kind, &p)); P.i1 = (const int *)p;
+    GSUM_TRY(dev_in(c, WS_IO1, j1, sizeof(int) * nb1, mem_kind, &p)); P.j1 = (const int *)p;
+    GSUM_TRY(dev_in(c, WS_IO2, i2, sizeof(int) * nb2, mem_kind, &p)); P.i2 = (const int *)p;
+    GSUM_TRY(dev_in(c, WS_IO3, j2, sizeof(int) * nb2, mem_kind, &p)); P.j2 = (const int *)p;
+    GSUM_TRY(dev_in(c, WS_MAT, bin_grid, sizeof(int) * n * n, mem_kind, &p)); P.bin_grid = (const int *)p;
+    GSUM_TRY(dev_in(c, WS_MISC0, gamma_tilde, sizeof(double) * nbins * ncurves, mem_kind, &p)); P.gamma_tilde = (const double *)p;
+    GSUM_TRY(dev_in(c, WS_MISC1, tab, sizeof(double) * (3 * VG_NT + 2), mem_kind, &p)); P.tab = (const double *)p;
+    P.nb1 = nb1; P.nb2 = nb2; P.n = n; P.ncurves = ncurves; P.var_factor = var_factor; P.corr_factor = corr_factor; P.same_is_one = same_is_one ? 1 : 0;
+    const int64_t nblocks = (nb1 + 15) / 16;
+    void *dpart, *dout;
+    GSUM_TRY(gsum_ws(c, WS_MISC2, sizeof(double) * nblocks * ncurves, &dpart));
+    GSUM_TRY(dev_out(c, WS_MISC3, out, sizeof(double) * ncurves, mem_kind, &dout));
+    variogram_cov_kernel<<<(unsigned)nblocks, 256, 0, c->stream>>>(P, (double *)dpart);
+    variogram_cov_reduce_kernel<<<ncurves, 256, 0, c->stream>>>((const double *)dpart, nblocks, ncurves, (double)nb1 * (double)nb2, (double *)dout);
+    LAUNCHED(c, 2);
+    GSUM_TRY(dev_out_finish(c, out, dout, sizeof(double) * ncurves, mem_kind));
+    return finish(c, mem_kind);
+}
+
 extern "C" int gsum_quadratic_forms(gsum_ctx *c, const double *A, int64_t n, const double *mean, const double *Y, int64_t n_curves,
                                     double *q, int32_t mem_kind) {
     if (!c || !A || !mean || !Y || !q || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_quadratic_forms: bad argument");

@@ -310,6 +310,65 @@ def quadratic_forms(A, mean, Y, ctx=None):
     return q
 
 
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def pointwise_fit(y, orders, mask, excluded, ratio, ref, df0, scale0, ctx=None):
+    """TruncationPointwise.fit on the device: (coeffs (n, n_m), scale (n,), trunc_scale (n, n_m)); ratio, ref (n,)."""
+    ctx = ctx or default_context()
+    y = as_f64(y)
+    n, n_o = y.shape
+    orders, mask, excluded = _i32(orders), _i32(mask), _i32(excluded)
+    n_m = int(mask.sum())
+    ratio, ref = _vec(ratio, n, "ratio"), _vec(ref, n, "ref")
+    coeffs, scale, trunc = np.empty((n, n_m)), np.empty(n), np.empty((n, n_m))
+    ctx.check(ctx.lib.gsum_pointwise_fit(ctx.handle, _p(y), n, n_o, _p(orders), _p(mask), _p(excluded) if excluded.size else None,
+                                         excluded.size, _p(ratio), _p(ref), float(df0), float(scale0), _p(coeffs), _p(scale), _p(trunc),
+                                         MEM_HOST), "gsum_pointwise_fit")
+    return coeffs, scale, trunc
+
+
+def pointwise_loglike_sums(y, orders, mask, ratios, ref, df0, scale0, ctx=None):
+    """The two point sums of TruncationPointwise.log_likelihood for every row of `ratios` (n_r, 1 or n); ref (1 or n,)."""
+    ctx = ctx or default_context()
+    y = as_f64(y)
+    n, n_o = y.shape
+    ratios, ref = as_f64(np.atleast_2d(ratios)), as_f64(np.atleast_1d(ref))
+    orders, mask = _i32(orders), _i32(mask)              # named: the arrays must outlive the call
+    n_r = ratios.shape[0]
+    S1, S2 = np.empty(n_r), np.empty(n_r)
+    ctx.check(ctx.lib.gsum_pointwise_loglike(ctx.handle, _p(y), n, n_o, _p(orders), _p(mask), _p(ratios), n_r, ratios.shape[1],
+                                             _p(ref), ref.shape[0], float(df0), float(scale0), _p(S1), _p(S2), MEM_HOST),
+              "gsum_pointwise_loglike")
+    return S1, S2
+
+
+def variogram_bins(X, z, bounds, ctx=None):
+    """Pairs (np.tril_indices order), their bins and the per-bin sums of VariogramFourthRoot.__init__; z (ncurves, n)."""
+    ctx = ctx or default_context()
+    X, z, bounds = as_f64(X), as_f64(z), as_f64(bounds)
+    n, d = X.shape
+    nc, nb, npairs = z.shape[0], bounds.shape[0] + 1, n * (n - 1) // 2
+    grid, hij, bidx = np.empty((n, n), np.int32), np.empty(npairs), np.empty(npairs, np.int32)
+    dij, counts, hsum, dsum = np.empty((npairs, nc)), np.empty(nb, np.int64), np.empty(nb), np.empty((nb, nc))
+    ctx.check(ctx.lib.gsum_variogram_bins(ctx.handle, _p(X), n, d, _p(z), nc, _p(bounds), bounds.shape[0], _p(grid), _p(hij), _p(bidx),
+                                          _p(dij), _p(counts), _p(hsum), _p(dsum), MEM_HOST), "gsum_variogram_bins")
+    return grid, hij, bidx, dij, counts, hsum, dsum
+
+
+def variogram_cov(i1, j1, i2, j2, bin_grid, gamma_tilde, tab, var_factor, corr_factor, same_is_one=True, ctx=None):
+    """VariogramFourthRoot.cov of two bins given their pair lists; gamma_tilde (nbins, ncurves <= 8) -> (ncurves,)."""
+    ctx = ctx or default_context()
+    i1, j1, i2, j2, bin_grid = _i32(i1), _i32(j1), _i32(i2), _i32(j2), _i32(bin_grid)
+    gamma_tilde, tab = as_f64(gamma_tilde), as_f64(tab)
+    out = np.empty(gamma_tilde.shape[1])
+    ctx.check(ctx.lib.gsum_variogram_cov(ctx.handle, _p(i1), _p(j1), i1.shape[0], _p(i2), _p(j2), i2.shape[0], _p(bin_grid),
+                                         bin_grid.shape[0], _p(gamma_tilde), gamma_tilde.shape[0], gamma_tilde.shape[1], _p(tab),
+                                         float(var_factor), float(corr_factor), 1 if same_is_one else 0, _p(out), MEM_HOST), "gsum_variogram_cov")
+    return out
+
+
 def pivoted_cholesky(M, ctx=None):
     """LAPACK dpstrf(lower) on the device: returns (G, Lp, piv, rank, status); M = G G^T, P^T M P = Lp Lp^T."""
     ctx = ctx or default_context()
@@ -330,7 +389,8 @@ def pc_errors(Lp, piv, mean, Y, ctx=None):
     Y = as_f64(Y)
     if isinstance(piv, DeviceBuffer) != isinstance(Lp, DeviceBuffer):
         raise ValueError("Lp and piv must both be numpy arrays or both DeviceBuffers")
-    piv_ = piv.ptr if isinstance(piv, DeviceBuffer) else _p(np.ascontiguousarray(piv, dtype=np.int32))
+    piv_host = None if isinstance(piv, DeviceBuffer) else np.ascontiguousarray(piv, dtype=np.int32)   # named: outlives the call
+    piv_ = piv.ptr if piv_host is None else _p(piv_host)
     mean = _vec(mean, n, "mean")
     E = np.empty_like(Y)
     ctx.check(ctx.lib.gsum_pc_errors(ctx.handle, Lp_, piv_, n, _p(mean), _p(Y), Y.shape[1], _p(E), kind), "gsum_pc_errors")

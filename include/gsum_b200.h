@@ -215,6 +215,35 @@ int gsum_draws(gsum_ctx *ctx, const double *L, int64_t n, const double *mean, co
                uint64_t seed, int64_t first_draw, const double *draw_scale, double *draws_out, const double *lower,
                const double *upper, int32_t n_alpha, double *coverage_out, int64_t *count_out, int32_t mem_kind);
 
+/* ---- TruncationPointwise (gsum/models.py:1573-1836) and VariogramFourthRoot (gsum/helpers.py:525-730) ----
+ * gsum_pointwise_fit: per point x of y (n, n_o): coefficients of the kept orders (mask[k] = 1; helpers.py:71-101), the
+ *   posterior scale sqrt((df0 scale0^2 + sum c^2) / (df0 + n_m)) (models.py:1630-1634) and the truncation-error scale
+ *   ref * sqrt(geometric_sum(ratio^2, order+1, inf, excluded)) * scale per kept order (models.py:1683-1685).
+ *   ratio, ref (n,); coeffs, trunc_scale (n, n_m); scale (n,); n_m = number of kept orders. */
+int gsum_pointwise_fit(gsum_ctx *ctx, const double *y, int64_t n, int32_t n_o, const int32_t *orders, const int32_t *mask,
+                       const int32_t *excluded, int32_t n_ex, const double *ratio, const double *ref, double df0, double scale0,
+                       double *coeffs, double *scale, double *trunc_scale, int32_t mem_kind);
+/* gsum_pointwise_loglike: the two sums over points of TruncationPointwise.log_likelihood (models.py:1796-1803) for n_r
+ *   ratio sets at once: S1[r] = sum_x log(df scale_x^2 / 2), S2[r] = sum_b (log|ref_b| + sum(kept orders) log(ratio_b)),
+ *   b over the numpy broadcast of ref (n_ref = 1 or n) and ratios[r] (n_rat = 1 or n). */
+int gsum_pointwise_loglike(gsum_ctx *ctx, const double *y, int64_t n, int32_t n_o, const int32_t *orders, const int32_t *mask,
+                           const double *ratios, int64_t n_r, int64_t n_rat, const double *ref, int64_t n_ref, double df0,
+                           double scale0, double *S1, double *S2, int32_t mem_kind);
+/* gsum_variogram_bins: distances and sqrt|z_i - z_j| of all pairs j < i (np.tril_indices order), their distance bins
+ *   (np.digitize with `bounds`), the (n, n) grid of bins and the per-bin count / sum of distances / sum of sqrt|dz| per curve
+ *   (helpers.py:547-600).  z (ncurves, n); hij, bin_idx (n(n-1)/2,), dij (n(n-1)/2, ncurves); counts (nbnd+1,) int64. */
+int gsum_variogram_bins(gsum_ctx *ctx, const double *X, int64_t n, int32_t d, const double *z, int32_t ncurves,
+                        const double *bounds, int32_t nbnd, int32_t *bin_grid, double *hij, int32_t *bin_idx, double *dij,
+                        int64_t *counts, double *hsum, double *dsum, int32_t mem_kind);
+/* gsum_variogram_cov: VariogramFourthRoot.cov(bin1, bin2) (helpers.py:640-696): mean over (pair in bin 1) x (pair in bin 2) of
+ *   corr_ijkl sqrt(var_ij var_kl) with the fourth-root correlation (1 - rho^2) 2F1(3/4, 3/4; 1/2; rho^2) - 1 (helpers.py:625-638).
+ *   (i1, j1), (i2, j2): the pairs of the two bins; gamma_tilde (nbins, ncurves), ncurves <= 8; tab: 3 * 56 + 2 series
+ *   coefficients of the hypergeometric function (see csrc/pointwise.cuh); same_is_one: a pair with itself has correlation 1
+ *   (cov_ijkl, helpers.py:655-657) or the formula's value (corr_ijkl); out (ncurves,). */
+int gsum_variogram_cov(gsum_ctx *ctx, const int32_t *i1, const int32_t *j1, int64_t nb1, const int32_t *i2, const int32_t *j2,
+                       int64_t nb2, const int32_t *bin_grid, int64_t n, const double *gamma_tilde, int32_t nbins, int32_t ncurves,
+                       const double *tab, double var_factor, double corr_factor, int32_t same_is_one, double *out, int32_t mem_kind);
+
 /* gsum_credible_interval: coverage of given curves Y (n, n_curves) (gsum/diagnostics.py:148-171). */
 int gsum_credible_interval(gsum_ctx *ctx, const double *Y, int64_t n, int64_t n_curves, const double *lower,
                            const double *upper, int32_t n_alpha, double *coverage_out, int32_t mem_kind);
