@@ -49,6 +49,7 @@ struct gsum_ctx {
     struct { void *dst; const void *src; size_t bytes; } pend[16];
     int npend;
     int ht_factor_ctas;         // GSUM_B200_FACTOR_CTAS (default HT_FACTOR_CTAS)
+    int use_smalln, sn_ready;   // small-N one-CTA grid path (smalln.cuh); GSUM_B200_SMALLN=0 disables
     int ht_chain_max;           // batches up to this size run in chain mode (chain.cuh); GSUM_B200_CHAIN_MAX, 0 disables
 };
 

@@ -9,6 +9,7 @@
 #include "diag.cuh"
 #include "grad.cuh"
 #include "pointwise.cuh"
+#include "smalln.cuh"
 #include "dataflow.cuh"
 #include "pipeline.cuh"
 #include "hetero.cuh"
@@ -58,6 +59,8 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
     const char *chn = getenv("GSUM_B200_CHAIN_MAX");
     c->ht_chain_max = chn ? atoi(chn) : HT_CHAIN_MAX;
+    const char *sn = getenv("GSUM_B200_SMALLN");
+    c->use_smalln = (sn && strcmp(sn, "0") == 0) ? 0 : 1;
     const char *thin = getenv("GSUM_B200_THIN");
     c->use_thin = (thin && strcmp(thin, "0") == 0) ? 0 : 1;
     *out = c;
@@ -650,10 +653,11 @@ extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d,
     GSUM_TRY(dev_in(c, WS_Q, Q, sizeof(double) * n_q * (q_x_dependent ? n : 1), mem_kind, &dQ));
     GSUM_TRY(dev_in(c, WS_DETF, detf, sizeof(double) * n_q, mem_kind, &ddetf));
 
+    const bool small = c->use_smalln && !q_x_dependent && n <= SN_MAXN && R <= SN_MAXR && d <= SN_MAXD;
     // RHS rows (shared by every length scale): basis + coefficients, transposed
-    void *drhs;
-    GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * r_rhs * n, &drhs));
-    {
+    void *drhs = nullptr;
+    if (!small) {
+        GSUM_TRY(gsum_ws(c, WS_RHS, sizeof(double) * r_rhs * n, &drhs));
         dim3 grid((unsigned)((n + 255) / 256), (unsigned)r_rhs);
         stage_rhs_kernel<<<grid, 256, 0, c->stream>>>((double *)drhs, n, (const double *)ddy, (const double *)dref,
                                                       q_x_dependent ? (const double *)dQ : nullptr, (const int32_t *)dord, n,
@@ -664,6 +668,39 @@ extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d,
     GSUM_TRY(dev_out(c, WS_LL, ll, sizeof(double) * n_q * n_ls, mem_kind, &dll));
     void *dlogdet = nullptr;
     if (logdet) GSUM_TRY(dev_out(c, WS_MISC0, logdet, sizeof(double) * n_ls, mem_kind, &dlogdet));
+
+    // ---- small N, scalar Q: one CTA per length scale, everything in shared memory (smalln.cuh) ---------------------------
+    if (small) {
+        void *dgram, *dld, *dinfo;
+        GSUM_TRY(gsum_ws(c, WS_GRAM, sizeof(double) * n_ls * R * R, &dgram));
+        GSUM_TRY(gsum_ws(c, WS_LOGDET, sizeof(double) * n_ls, &dld));
+        GSUM_TRY(gsum_ws(c, WS_MISC1, sizeof(int) * n_ls, &dinfo));
+        SmallNArgs SA;
+        SA.X = (const double *)dX; SA.ls = (const double *)dls; SA.dy = (const double *)ddy; SA.ref = (const double *)dref;
+        SA.n = n; SA.d = d; SA.ls_dim = ls_dim; SA.n_c = n_c; SA.constant = constant; SA.noise = noise; SA.nugget = nugget;
+        SA.G = (double *)dgram; SA.logdet = (double *)dld; SA.info = (int *)dinfo;
+        const size_t smem = smalln_smem_bytes(n);
+        if (!c->sn_ready) {
+            GSUM_CUDA(c, cudaFuncSetAttribute(smalln_lml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smalln_smem_bytes(SN_MAXN)));
+            c->sn_ready = 1;
+        }
+        smalln_lml_kernel<<<(unsigned)n_ls, SN_THREADS, smem, c->stream>>>(SA);
+        LmlCellArgs LA;
+        LA.G = (const double *)dgram; LA.logdet_part = (const double *)dld; LA.info = (const int *)dinfo; LA.T = 1; LA.R = R;
+        LA.n = n; LA.n_l = n_ls; LA.n_q = n_q; LA.separable = 1;
+        LA.Q = (const double *)dQ; LA.orders = (const int32_t *)dord; LA.detf = (const double *)ddetf;
+        LA.center0 = center0; LA.disp0 = disp0; LA.df0 = df0; LA.scale0 = scale0; LA.student = student;
+        LA.ll = (double *)dll; LA.logdet_out = (double *)dlogdet; LA.post = nullptr;
+        lml_cell_chunk_kernel<<<(unsigned)((n_ls * n_q + 127) / 128), 128, 0, c->stream>>>(LA, 0, n_ls);
+        LAUNCHED(c, 2);
+        GSUM_TRY(dev_out_finish(c, ll, dll, sizeof(double) * n_q * n_ls, mem_kind));
+        GSUM_TRY(dev_out_finish(c, logdet, dlogdet, sizeof(double) * n_ls, mem_kind));
+        if (status) {
+            GSUM_CUDA(c, cudaMemcpyAsync(status, dinfo, sizeof(int) * n_ls,
+                                         mem_kind == GSUM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+        }
+        return finish(c, mem_kind);
+    }
 
     // length scales are processed in chunks sized to a fixed HBM budget (whole grid at once for the BASELINE configs)
     const int64_t per_mat = (int64_t)Trows * GSUM_TILE * np;                     // doubles

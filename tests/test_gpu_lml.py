@@ -203,3 +203,56 @@ def test_sharded_nccl_path_single_rank(ctx):
         if created:
             dist.destroy_process_group()
     assert np.array_equal(got, want) and all(np.array_equal(a, want) for a in again)
+
+
+def test_c2_full_grid_small_n_path(ctx):
+    """Config C2 at FULL size — N = 200, orders 0-5, the whole 64 x 64 (Q, l) grid — on the one-CTA-per-length-scale path
+    (csrc/smalln.cuh) against the oracle cell by cell at the north-star tolerance, and against the 64x64-tile path."""
+    import os
+    from gsum_b200 import _lib
+    rs = np.random.RandomState(1)
+    n = 200
+    X = np.linspace(0, 1, n)[:, None]
+    coeffs = np.linalg.cholesky(RBF(0.2)(X) + 1e-6 * np.eye(n)) @ rs.randn(n, 6)
+    orders = np.arange(6)
+    y = o.partials(coeffs, 0.5, 1.0, orders)
+    ls_vals, q_vals = np.linspace(0.02, 0.5, 64), np.linspace(0.3, 0.7, 64)
+    kern = RBF(0.2) + WhiteKernel(1e-6, 'fixed')
+    gp = gb.TruncationGP(kern, ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None).fit(X, y, orders=orders)
+    ll = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals)
+    want = o.lml_grid(kern, X, y, orders, ls_vals, q_vals, 1.0, o.Priors(0, 0, 1, 1))
+    assert ll.shape == want.shape == (64, 64)
+    rel = np.abs(ll - want) / np.abs(want)
+    # every cell at the north-star tolerance; a cell beyond it (cond R ~ 1e8 at the long-l end) must be at least as close to
+    # the extended-precision value as the reference itself is
+    for a, b in zip(*np.nonzero(rel >= RTOL)):
+        coeffs_q = o.coefficients(y, q_vals[a], 1.0, orders)
+        exact = lml_extended_precision(X, coeffs_q, [ls_vals[b]], 1e-6, 1e-10, 0.0, 0.0, 1.0, 1.0) - n * orders.sum() * np.log(q_vals[a])
+        assert abs(ll[a, b] - exact) <= 2.0 * abs(want[a, b] - exact) + 1e-12 * abs(exact), (a, b, rel[a, b])
+    assert rel.max() < 1e-9 and np.count_nonzero(rel >= RTOL) <= 8
+    # the same grid on the tile path (a context created with the small-N path switched off)
+    from gsum_b200.helpers import _order_differences
+    old = os.environ.get("GSUM_B200_SMALLN")
+    os.environ["GSUM_B200_SMALLN"] = "0"
+    try:
+        tile_ctx = _lib.Context(0)
+    finally:
+        if old is None:
+            os.environ.pop("GSUM_B200_SMALLN")
+        else:
+            os.environ["GSUM_B200_SMALLN"] = old
+    try:
+        detf = n * float(orders.sum()) * np.log(np.abs(q_vals))
+        kw = dict(detf=detf, constant=1.0, noise=1e-6, nugget=gp.coeffs_process.nugget, center0=0.0, disp0=0.0, df0=1.0, scale0=1.0)
+        dy = np.ascontiguousarray(_order_differences(y))
+        tile = ops.lml_grid(X, dy, 1.0, orders, ls_vals[:, None], q_vals, ctx=tile_ctx, **kw)
+        small = ops.lml_grid(X, dy, 1.0, orders, ls_vals[:, None], q_vals, **kw)
+    finally:
+        tile_ctx.close()
+    assert np.array_equal(small, ll)
+    assert relerr(small, tile) < 1e-10
+    # status / -inf semantics on the small path: duplicated points, no noise -> not positive definite
+    Xd = np.concatenate([X[:60], X[:3]])
+    yd = np.concatenate([dy[:60], dy[:3]])
+    lld, logdet, status = ops.lml_grid(Xd, yd, 1.0, orders, [[0.3], [0.1]], [1.0, 0.5], noise=0.0, nugget=0.0, return_status=True)
+    assert (status != 0).all() and np.all(np.isneginf(lld)) and np.isnan(logdet).all()
