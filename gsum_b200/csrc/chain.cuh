@@ -34,7 +34,7 @@
 #define CH_NTILES 5                                     // L_kk | next diagonal tile | sub-diagonal tile | previous sub-diagonal tile | Y
 #define CH_SMEM_DOUBLES (CH_NTILES * CH_TILE_DOUBLES + 2 * CH_SCR_DOUBLES + 8)
 #define CH_THREADS 256                                  // warps 0-3: the chain; warps 4-7: the output helper
-#define CH_BAR_POTRF 4                                  // chain -> helper: L_kk, diag(L) and the inverted blocks are in shared memory
+#define CH_BAR_POTRF 3                                  // chain -> helper: L_kk, diag(L) and the inverted blocks are in shared memory
 #define CH_BAR_LOADED 5                                 // helper -> chain: the two pre tiles of the column are in shared memory
 #define CH_BAR_X 6                                      // both: L_{k+1,k} is complete in shared memory
 #define CH_BAR_UPD 7                                    // both: the next diagonal tile is updated, Pt and the old L_kk buffer are free
@@ -75,8 +75,9 @@ __device__ __forceinline__ void chain_invert_blocks(const double *S, const doubl
     }
 }
 
-// ht_trsm_dinv with the inverted diagonal blocks in Dv and the blocks below them in the factored tile Ls (stride GSUM_LDS):
-// the register-resident form (quad shuffles for the C -> A re-layouts, everything unrolled: 11 KB of code).
+// hx_trsm_dinv (hetero_tma.cuh) with the inverted diagonal blocks in Dv and the blocks below them in the factored tile Ls (stride GSUM_LDS):
+// register-resident (quad shuffles for the C -> A re-layouts).  A loop form working from shared memory (1.5 KB of code instead
+// of 11) was measured slower: 6.2k instead of 4.7k cycles per tile (profiles/r02_notes.md).
 template <int MT>
 __device__ __forceinline__ void chain_trsm(Acc &T, const double *Ls, const double *Dv, int g, int t) {
     const unsigned FULLMASK = 0xffffffffu;
@@ -120,57 +121,6 @@ __device__ __forceinline__ void chain_trsm(Acc &T, const double *Ls, const doubl
         }
     }
 }
-#ifndef CH_TRSM_SMEM
-#define CH_TRSM_SMEM 0                                  // 1: the loop form below (1.5 KB of code; measured 6.2k instead of 4.7k cycles per tile)
-#endif
-
-// X = S L_kk^{-T} in place on the tile Pm (shared memory), rows 16 w .. 16 w + 15 of warp w, and to global memory (Cg, ld).
-// Same operations on every element, in the same order, as the block substitution of ht_trsm_dinv / hx_trsm_dinv
-// (S_j -= X_cb L[j, cb]^T for cb = 0 .. j-1, two DMMAs each, then X_j = S_j Dinv_j^T, two DMMAs from zero), but arranged
-// LEFT-looking over the target block j: its accumulator stays in registers for the whole cb loop (one dependent DMMA chain
-// per 8-row block, 27 cycles a link), the finished X blocks are read back from shared memory as A fragments (a store and a
-// load replace the quad shuffles), and neither loop is unrolled — ~1.5 KB of code instead of 11.  That matters here: chain
-// code that does not stay in the SM's 32 KB instruction-cache level is fetched from L2 again every column (measured: a
-// straight-line phase of 120 instructions took 3200 cycles cold and 300 warm).
-__device__ __forceinline__ void chain_trsm_smem(double *Pm, const double *Ls, const double *Dv, double *Cg, int64_t ld, int w, int g, int t) {
-    double *row0 = Pm + (w * 16 + g) * GSUM_LDS, *row1 = row0 + 8 * GSUM_LDS;
-    double *g0 = Cg + (int64_t)(w * 16 + g) * ld, *g1 = g0 + 8 * ld;
-#pragma unroll 1
-    for (int j = 0; j < 8; j++) {
-        double2 q0 = *reinterpret_cast<const double2 *>(row0 + j * 8 + 2 * t);
-        double2 q1 = *reinterpret_cast<const double2 *>(row1 + j * 8 + 2 * t);
-        const double *lrow = Ls + (j * 8 + g) * GSUM_LDS + t;
-#pragma unroll 2
-        for (int cb = 0; cb < j; cb++) {
-            const int c0 = cb * 8;
-            const double l0 = lrow[c0], l1 = lrow[c0 + 4];
-            const double n00 = -row0[c0 + t], n01 = -row0[c0 + 4 + t], n10 = -row1[c0 + t], n11 = -row1[c0 + 4 + t];
-            dmma884(q0.x, q0.y, n00, l0);
-            dmma884(q1.x, q1.y, n10, l0);
-            dmma884(q0.x, q0.y, n01, l1);
-            dmma884(q1.x, q1.y, n11, l1);
-        }
-        // C -> A fragments through the tile itself (every lane's S_j entries are its own until here)
-        *reinterpret_cast<double2 *>(row0 + j * 8 + 2 * t) = q0;
-        *reinterpret_cast<double2 *>(row1 + j * 8 + 2 * t) = q1;
-        __syncwarp();
-        const double a00 = row0[j * 8 + t], a01 = row0[j * 8 + 4 + t], a10 = row1[j * 8 + t], a11 = row1[j * 8 + 4 + t];
-        const double b0 = Dv[j * CH_DV_BLOCK + g * CH_DV_LD + t], b1 = Dv[j * CH_DV_BLOCK + g * CH_DV_LD + 4 + t];
-        double2 x0, x1;
-        x0.x = 0.0; x0.y = 0.0; x1.x = 0.0; x1.y = 0.0;
-        dmma884(x0.x, x0.y, a00, b0);
-        dmma884(x1.x, x1.y, a10, b0);
-        dmma884(x0.x, x0.y, a01, b1);
-        dmma884(x1.x, x1.y, a11, b1);
-        __syncwarp();                                 // every lane has read S_j
-        *reinterpret_cast<double2 *>(row0 + j * 8 + 2 * t) = x0;
-        *reinterpret_cast<double2 *>(row1 + j * 8 + 2 * t) = x1;
-        *reinterpret_cast<double2 *>(g0 + j * 8 + 2 * t) = x0;
-        *reinterpret_cast<double2 *>(g1 + j * 8 + 2 * t) = x1;
-        __syncwarp();
-    }
-}
-
 // Dn -= X X^T on the 36 blocks on and below the diagonal, dealt over the eight warps of the chain CTA: chain warp v takes
 // blocks 0..4 of block row 7 - v, helper warp v the rest of that row and block row v (5 and 4 blocks).
 // The contraction runs in EXACTLY the order of a GEMM CTA's diagonal task (hetero_tma.cuh: 16-column boxes in sequence,
@@ -388,9 +338,6 @@ __device__ __forceinline__ void ht_chain_worker(const HeteroArgs &D, double *sme
         }
         long long t3 = st ? clock64() : 0;
         // ---- L_{k+1,k} = S' L_kk^{-T}: warp w owns rows 16 w .. 16 w + 15 ------------------------------------------------
-#if CH_TRSM_SMEM
-        chain_trsm_smem(Pt, Dk, Dv, Ab + (int64_t)(k + 1) * GSUM_TILE * P.ld + k * GSUM_TILE, P.ld, w, g, t);
-#else
         {
             Acc acc;
 #pragma unroll
@@ -411,7 +358,6 @@ __device__ __forceinline__ void ht_chain_worker(const HeteroArgs &D, double *sme
                     *reinterpret_cast<double2 *>(C + (int64_t)(w * 16 + mt * 8 + g) * P.ld + nt * 8 + 2 * t) = q;
                 }
         }
-#endif
         long long t3b = st ? clock64() : 0;
         __syncwarp();
         asm volatile("bar.arrive %0, 160;" ::"r"(CH_BAR_XPUB) : "memory");      // the publisher warp releases the flag of L_{k+1,k}

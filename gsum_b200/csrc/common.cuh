@@ -29,20 +29,12 @@ struct gsum_ctx {
     cudaEvent_t prof_ev[2 * 256];
     double prof_flops;          // algorithmic flops of the bracketed factorisations
     int64_t prof_border_rows;   // right-hand sides riding along with the current factorisation
-    // dataflow schedule: cached task list (device) and its key, flags, sticky abort indicator
-    void *df_tasks; size_t df_tasks_cap; int df_key[4]; int df_ntasks;
+    // factorisation schedule (hetero.cuh): cached claim lists and their key, tile flags, counters / sticky abort indicator
     void *df_flags; size_t df_flags_cap;
-    int *df_ctl;                // [0] task counter, [1] abort flag, [2] sticky abort (device)
-    int df_grid;                // co-resident CTAs of the dataflow kernel (0 = not yet queried)
-    int use_multilaunch;        // GSUM_B200_SCHEDULE=multilaunch: per-column launches instead (debug / comparison)
-    int use_pipeline;           // GSUM_B200_SCHEDULE=pipeline: warp-specialised one-CTA-per-SM schedule (pipeline.cuh)
-    int pl_grid;                // co-resident CTAs of the pipeline kernel (0 = not yet queried)
+    int *df_ctl;                // [0] GEMM task counter, [1] abort flag, [2] sticky abort, [3], [4] factor task counters (device)
     int use_thin;               // GSUM_B200_THIN=0 disables the 8-row border tasks (debug / comparison)
-    // heterogeneous schedule (hetero.cuh, the default): two cached claim lists
-    int use_hetero;
     void *ht_gtasks, *ht_ftasks; size_t ht_gcap, ht_fcap; int ht_key[5]; int ht_ng, ht_nf;
-    int ht_ready;               // function attributes set / co-residency checked
-    int use_tma, hx_ready;      // GSUM_B200_SCHEDULE=hetero_tma: TMA-fed variant (hetero_tma.cuh)
+    int hx_ready;               // function attributes of the factorisation kernel set
     // pinned staging arena for host-memory callers: small inputs go host -> pinned -> device with a truly asynchronous copy,
     // outputs come back device -> pinned and are handed to the caller after the call's single stream synchronisation
     char *pin; size_t pin_cap, pin_off;

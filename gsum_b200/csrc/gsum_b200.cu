@@ -10,8 +10,6 @@
 #include "grad.cuh"
 #include "pointwise.cuh"
 #include "smalln.cuh"
-#include "dataflow.cuh"
-#include "pipeline.cuh"
 #include "hetero.cuh"
 #include "hetero_tma.cuh"
 #include <cstdlib>
@@ -46,15 +44,6 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaMallocHost((void **)&c->pin, (size_t)8 << 20) == cudaSuccess) c->pin_cap = (size_t)8 << 20; else { c->pin = nullptr; cudaGetLastError(); }
-    const char *sched = getenv("GSUM_B200_SCHEDULE");
-    c->use_multilaunch = (sched && strcmp(sched, "multilaunch") == 0) ? 1 : 0;
-    // default: the warp-specialised pipeline kernel; "dataflow" (two all-in-one CTAs per SM) and "multilaunch" (one launch
-    // per tile column) are kept for comparison and as cross-checks of one another
-    c->use_pipeline = (sched && (strcmp(sched, "dataflow") == 0 || strcmp(sched, "multilaunch") == 0)) ? 0 : 1;
-    // default schedule: heterogeneous (hetero.cuh); "pipeline" / "dataflow" / "multilaunch" select the older ones
-    c->use_hetero = (!sched || strcmp(sched, "hetero") == 0 || strcmp(sched, "hetero_tma") == 0) ? 1 : 0;
-    // the TMA-fed variant (hetero_tma.cuh) is the default; "hetero" selects the cp.async-fed one
-    c->use_tma = (!sched || strcmp(sched, "hetero_tma") == 0) ? 1 : 0;
     const char *fc = getenv("GSUM_B200_FACTOR_CTAS");
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
     const char *chn = getenv("GSUM_B200_CHAIN_MAX");
@@ -72,7 +61,6 @@ extern "C" int gsum_ctx_destroy(gsum_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     for (int i = 0; i < GSUM_NWS; i++) if (c->ws[i]) cudaFree(c->ws[i]);
-    if (c->df_tasks) cudaFree(c->df_tasks);
     if (c->ht_gtasks) cudaFree(c->ht_gtasks);
     if (c->ht_ftasks) cudaFree(c->ht_ftasks);
     if (c->df_flags) cudaFree(c->df_flags);
@@ -210,106 +198,6 @@ static int scale_coords(gsum_ctx *c, const double *dX, const double *dls, double
     return 0;
 }
 
-// ---- dataflow schedule of the bordered factorisation / border solve (one cooperative launch) ------------------------
-static int dataflow_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
-    GSUM_TRY(chol_set_attrs(c));
-    if (c->use_pipeline && c->pl_grid == 0) {
-        GSUM_CUDA(c, cudaFuncSetAttribute(chol_pipeline_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES));
-        GSUM_CUDA(c, cudaFuncSetAttribute(chol_pipeline_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM_BYTES));
-        int per_sm = 0;
-        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_pipeline_kernel<false>, PL_THREADS, PL_SMEM_BYTES));
-        if (per_sm < 1) return gsum_fail(c, -102, "pipeline kernel does not fit on an SM");
-        c->pl_grid = per_sm * c->sm_count;
-    }
-    if (c->df_grid == 0) {
-        GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
-        GSUM_CUDA(c, cudaFuncSetAttribute(chol_dataflow_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
-        int per_sm = 0, per_sm_stats = 0;
-        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_dataflow_kernel<false>, DF_THREADS, CHOL_SMEM_BYTES));
-        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_stats, chol_dataflow_kernel<true>, DF_THREADS, CHOL_SMEM_BYTES));
-        if (per_sm_stats < per_sm) per_sm = per_sm_stats;
-        if (per_sm < 1) return gsum_fail(c, -102, "dataflow kernel does not fit on an SM");
-        c->df_grid = per_sm * c->sm_count;
-    }
-    // a last border tile row with at most 8 rows in use runs as thin (8 x 64) tasks
-    const int nbt = P.Trows - P.T;
-    const bool thin_last = c->use_thin && nbt > 0 && P.border_used > 0 && P.border_used - (nbt - 1) * GSUM_TILE <= 8 &&
-                           P.border_used > (nbt - 1) * GSUM_TILE;
-    const int key[4] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0)};
-    if (memcmp(key, c->df_key, sizeof(key)) != 0 || !c->df_tasks) {
-        std::vector<int4> tasks;
-        df_build_tasks(tasks, P.T, P.Trows, batch, solve_only, thin_last, getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : DF_DIAG_DELAY);
-        const size_t bytes = tasks.size() * sizeof(int4);
-        if (c->df_tasks_cap < bytes) {
-            GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
-            if (c->df_tasks) GSUM_CUDA(c, cudaFree(c->df_tasks));
-            GSUM_CUDA(c, cudaMalloc(&c->df_tasks, bytes + 4096));
-            c->df_tasks_cap = bytes + 4096;
-        }
-        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // the previous list may still be in use
-        GSUM_CUDA(c, cudaMemcpy(c->df_tasks, tasks.data(), bytes, cudaMemcpyHostToDevice));
-        memcpy(c->df_key, key, sizeof(key));
-        c->df_ntasks = (int)tasks.size();
-    }
-    const size_t fbytes = sizeof(int) * (size_t)batch * P.Trows * P.T;
-    if (c->df_flags_cap < fbytes) {
-        GSUM_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (c->df_flags) GSUM_CUDA(c, cudaFree(c->df_flags));
-        GSUM_CUDA(c, cudaMalloc(&c->df_flags, fbytes + 4096));
-        c->df_flags_cap = fbytes + 4096;
-    }
-    if (!c->df_ctl) {
-        GSUM_CUDA(c, cudaMalloc((void **)&c->df_ctl, 8 * sizeof(int)));
-        GSUM_CUDA(c, cudaMemsetAsync(c->df_ctl, 0, 8 * sizeof(int), c->stream));
-    }
-    const int64_t nflags = (int64_t)batch * P.Trows * P.T;
-    df_init_kernel<<<(unsigned)((nflags + 255) / 256 + 1), 256, 0, c->stream>>>((int *)c->df_flags, c->df_ctl, batch, P.Trows, P.T, solve_only ? 1 : 0);
-    DataflowArgs D;
-    D.P = P; D.tasks = (const int4 *)c->df_tasks; D.ntasks = c->df_ntasks; D.counter = c->df_ctl; D.flags = (int *)c->df_flags;
-    D.abort_flag = c->df_ctl + 1;
-    D.stats = nullptr;
-    static long long *dbg_stats = nullptr;
-    if (getenv("GSUM_B200_DF_STATS")) {
-        if (!dbg_stats) cudaMalloc((void **)&dbg_stats, sizeof(long long) * DF_NSTAT * 1024);
-        cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * DF_NSTAT * 1024, c->stream);
-        D.stats = dbg_stats;
-    }
-    int grid = c->df_grid < D.ntasks ? c->df_grid : D.ntasks;
-    void *args[] = {&D};
-    if (c->use_pipeline) {
-        grid = c->pl_grid < D.ntasks ? c->pl_grid : D.ntasks;
-        const void *kfn = D.stats ? (const void *)chol_pipeline_kernel<true> : (const void *)chol_pipeline_kernel<false>;
-        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(PL_THREADS), args, PL_SMEM_BYTES, c->stream));
-    } else {
-        const void *kfn = D.stats ? (const void *)chol_dataflow_kernel<true> : (const void *)chol_dataflow_kernel<false>;
-        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(DF_THREADS), args, CHOL_SMEM_BYTES, c->stream));
-    }
-    df_check_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, c->stream>>>(c->df_ctl + 1, P.info, batch, c->df_ctl + 2);
-    c->launches += 3;
-    GSUM_CUDA(c, cudaPeekAtLastError());
-    if (D.stats) {       // dev instrumentation: print the per-CTA cycle split of this launch
-        std::vector<long long> h(DF_NSTAT * grid);
-        cudaStreamSynchronize(c->stream);
-        cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * DF_NSTAT * grid, cudaMemcpyDeviceToHost);
-        double a[DF_NSTAT] = {0};
-        for (int g = 0; g < grid; g++) for (int q = 0; q < DF_NSTAT; q++) a[q] += (double)h[DF_NSTAT * g + q];
-        const double tot = a[0];
-        if (c->use_pipeline) {
-            fprintf(stderr, "[pl] grid %d cycles/CTA %.0f | producer: wait_queue %.1f%% wait_flag %.1f%% wait_ring %.1f%% | math (P tasks/CTA %.1f): wait_queue %.1f%% wait_operands %.1f%% wait_pbuf %.1f%%\n",
-                    grid, a[0] / grid, 100 * a[1] / a[0], 100 * a[2] / a[0], 100 * a[3] / a[0], a[8] / grid, 100 * a[5] / a[4], 100 * a[6] / a[4], 100 * a[7] / a[4]);
-            fprintf(stderr, "[pl]   math wait_operands split: first stage of a full task %.1f%%, thin tasks %.1f%%, later stages of diagonal tasks %.1f%%, of panel tasks %.1f%%\n",
-                    100 * a[18] / a[4], 100 * a[19] / a[4], 100 * a[20] / a[4], 100 * (a[6] - a[18] - a[19] - a[20]) / a[4]);
-            fprintf(stderr, "[pl]   epilogue: wait_queue %.1f%% wait_Lkk_flag %.1f%% wait_product %.1f%% | diag %.1f%% (%.0f cyc/task) panel %.1f%% thin %.1f%% fence+flag %.1f%%\n",
-                    100 * a[10] / a[9], 100 * a[11] / a[9], 100 * a[12] / a[9], 100 * a[13] / a[9], a[13] / (a[16] + 1e-9), 100 * a[14] / a[9], 100 * a[15] / a[9], 100 * a[17] / a[9]);
-        } else {
-        fprintf(stderr, "[df] grid %d tasks %.0f  avg cycles/CTA: total %.0f | math: claim %.1f%% acc_load %.1f%% wait_full %.1f%% epilogue %.1f%% fence+flag %.1f%% | producer: wait_flag %.1f%% wait_empty %.1f%%\n",
-                grid, a[3], tot / grid, 100 * a[8] / tot, 100 * a[4] / tot, 100 * a[1] / tot, 100 * a[2] / tot, 100 * a[7] / tot, 100 * a[5] / tot, 100 * a[6] / tot);
-        fprintf(stderr, "[df]   epilogue cycles/task: diag (n=%.0f) store %.0f potrf %.0f write %.0f | panel (n=%.0f) store %.0f trsm %.0f write %.0f\n",
-                a[12], a[9] / (a[12] + 1e-9), a[10] / (a[12] + 1e-9), a[11] / (a[12] + 1e-9), a[16], a[13] / (a[16] + 1e-9), a[14] / (a[16] + 1e-9), a[15] / (a[16] + 1e-9));
-        }
-    }
-    return 0;
-}
 // ---- heterogeneous schedule (hetero.cuh): GEMM CTAs + factor CTAs in one cooperative launch --------------------------
 static int ht_upload(gsum_ctx *c, void **buf, size_t *cap, const std::vector<int4> &v) {
     const size_t bytes = v.size() * sizeof(int4);
@@ -347,20 +235,12 @@ static int ht_make_map(gsum_ctx *c, CUtensorMap *m, const void *base, uint64_t r
 }
 
 static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
-    if (!c->ht_ready) {
-        GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
-        GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM_BYTES));
-        int per_sm = 0;
-        GSUM_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_hetero_kernel<false>, HT_THREADS, HT_SMEM_BYTES));
-        if (per_sm < 1) return gsum_fail(c, -102, "hetero kernel does not fit on an SM");
-        c->ht_ready = 1;
-    }
     const int nbt = P.Trows - P.T;
     const bool thin_last = c->use_thin && nbt > 0 && P.border_used > 0 && P.border_used - (nbt - 1) * GSUM_TILE <= 8 &&
                            P.border_used > (nbt - 1) * GSUM_TILE;
     const int delay = getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : HT_DIAG_DELAY;
     // few matrices: chain mode (chain.cuh) — one chain worker CTA per matrix owns the diagonal band
-    const bool chain = !solve_only && c->use_tma && batch <= c->ht_chain_max;
+    const bool chain = !solve_only && batch <= c->ht_chain_max;
     const int key[5] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0) | (chain ? 4 : 0), delay};
     if (memcmp(key, c->ht_key, sizeof(key)) != 0 || !c->ht_gtasks) {
         std::vector<int4> gt, ft;
@@ -422,28 +302,24 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * HT_NSTAT * 1024, c->stream);
         D.stats = dbg_stats;
     }
-    if (c->use_tma) {
-        if (!c->hx_ready) {
-            GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HX_SMEM_BYTES));
-            GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HX_SMEM_BYTES));
-            c->hx_ready = 1;
-        }
-        HeteroMaps maps;
-        const uint64_t rowsA = (uint64_t)(P.bstride / P.ld), rowsW = (uint64_t)(P.wstride / P.ld);
-        GSUM_TRY(ht_make_map(c, &maps.A, P.A, (uint64_t)(batch - 1) * rowsA + (uint64_t)P.T * GSUM_TILE, (uint64_t)P.ld, (uint64_t)P.ld, GSUM_TILE));
-        if (P.Trows > P.T) {
-            const uint64_t wr = (uint64_t)(batch - 1) * rowsW + (uint64_t)(P.Trows - P.T) * GSUM_TILE;
-            GSUM_TRY(ht_make_map(c, &maps.W, P.W, wr, (uint64_t)P.ld, (uint64_t)P.ld, GSUM_TILE));
-            GSUM_TRY(ht_make_map(c, &maps.W8, P.W, wr, (uint64_t)P.ld, (uint64_t)P.ld, 8));
-        } else { maps.W = maps.A; maps.W8 = maps.A; }
-        GSUM_TRY(ht_make_map(c, &maps.M, dM, (uint64_t)batch * P.T * GSUM_TILE, GSUM_TILE, GSUM_TILE, GSUM_TILE));
-        void *args[] = {&D, &maps};
-        const void *kfn = D.stats ? (const void *)chol_hetero_tma_kernel<true> : (const void *)chol_hetero_tma_kernel<false>;
-        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HX_THREADS), args, HX_SMEM_BYTES, c->stream));
-    } else {
-        void *args[] = {&D};
-        const void *kfn = D.stats ? (const void *)chol_hetero_kernel<true> : (const void *)chol_hetero_kernel<false>;
-        GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HT_THREADS), args, HT_SMEM_BYTES, c->stream));
+    {
+    if (!c->hx_ready) {
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HX_SMEM_BYTES));
+        GSUM_CUDA(c, cudaFuncSetAttribute(chol_hetero_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HX_SMEM_BYTES));
+        c->hx_ready = 1;
+    }
+    HeteroMaps maps;
+    const uint64_t rowsA = (uint64_t)(P.bstride / P.ld), rowsW = (uint64_t)(P.wstride / P.ld);
+    GSUM_TRY(ht_make_map(c, &maps.A, P.A, (uint64_t)(batch - 1) * rowsA + (uint64_t)P.T * GSUM_TILE, (uint64_t)P.ld, (uint64_t)P.ld, GSUM_TILE));
+    if (P.Trows > P.T) {
+        const uint64_t wr = (uint64_t)(batch - 1) * rowsW + (uint64_t)(P.Trows - P.T) * GSUM_TILE;
+        GSUM_TRY(ht_make_map(c, &maps.W, P.W, wr, (uint64_t)P.ld, (uint64_t)P.ld, GSUM_TILE));
+        GSUM_TRY(ht_make_map(c, &maps.W8, P.W, wr, (uint64_t)P.ld, (uint64_t)P.ld, 8));
+    } else { maps.W = maps.A; maps.W8 = maps.A; }
+    GSUM_TRY(ht_make_map(c, &maps.M, dM, (uint64_t)batch * P.T * GSUM_TILE, GSUM_TILE, GSUM_TILE, GSUM_TILE));
+    void *args[] = {&D, &maps};
+    const void *kfn = D.stats ? (const void *)chol_hetero_tma_kernel<true> : (const void *)chol_hetero_tma_kernel<false>;
+    GSUM_CUDA(c, cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(HX_THREADS), args, HX_SMEM_BYTES, c->stream));
     }
     if (!solve_only && P.logdet_part) {
         ht_logdet_kernel<<<dim3(P.T, batch), 32, 0, c->stream>>>(P);
@@ -457,7 +333,7 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         cudaStreamSynchronize(c->stream);
         cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * HT_NSTAT * grid, cudaMemcpyDeviceToHost);
         double f[6] = {0, 0, 0, 0, 0, 0}, a[HT_NSTAT] = {0};
-        const int ngrp = c->use_tma ? HX_NG : HT_NG;
+        const int ngrp = HX_NG;
         for (int g = 0; g < nf; g++) for (int wk = 0; wk < nwk; wk++) for (int q = 0; q < 6; q++) f[q] += (double)h[HT_NSTAT * g + wk * 6 + q];
         for (int g = nf; g < grid; g++) for (int grp = 0; grp < ngrp; grp++) for (int q = 0; q < 12; q++) a[q] += (double)h[HT_NSTAT * g + grp * 12 + q];
         if (chain) {
@@ -475,14 +351,10 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     }
     return 0;
 }
-static int factor_run(gsum_ctx *c, const BorderedBatch &P, int batch) {
-    if (c->use_multilaunch) return chol_bordered_run(c, P, batch);
-    return c->use_hetero ? hetero_run(c, P, batch, false) : dataflow_run(c, P, batch, false);
-}
+static int factor_run(gsum_ctx *c, const BorderedBatch &P, int batch) { return hetero_run(c, P, batch, false); }
 static int solve_run(gsum_ctx *c, const BorderedBatch &P, int batch) {
     if (P.Trows - P.T <= 0) return 0;
-    if (c->use_multilaunch) return chol_solve_border_run(c, P, batch);
-    return c->use_hetero ? hetero_run(c, P, batch, true) : dataflow_run(c, P, batch, true);
+    return hetero_run(c, P, batch, true);
 }
 
 // ---- K1 ---------------------------------------------------------------------------------------------
@@ -724,7 +596,7 @@ extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d,
         cov_sym_kernel<<<gcov, 256, 0, c->stream>>>(CA);
         // a last border tile row that runs as thin (8-row) tasks is only ever touched in its first 8 rows
         int64_t fill_rows = rp;
-        if (c->use_thin && !c->use_multilaunch && r_rhs - (rp - GSUM_TILE) <= 8) fill_rows = rp - GSUM_TILE + 8;
+        if (c->use_thin && r_rhs - (rp - GSUM_TILE) <= 8) fill_rows = rp - GSUM_TILE + 8;
         dim3 gb((unsigned)fill_rows, (unsigned)((np + 255) / 256), (unsigned)nb);
         border_fill_kernel<<<gb, 256, 0, c->stream>>>((double *)dmat, np, per_mat, T, (int)fill_rows, (const double *)drhs, (int)r_rhs, n, n);
         LAUNCHED(c, 2);

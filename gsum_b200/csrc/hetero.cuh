@@ -1,14 +1,15 @@
-// Heterogeneous persistent schedule of the bordered Cholesky (K2 + K3 in ONE launch): the default factorisation kernel.
+// Heterogeneous persistent schedule of the bordered Cholesky (K2 + K3 in ONE launch): roles, task lists and the factor
+// workers.  The kernel itself is chol_hetero_tma_kernel (hetero_tma.cuh); the few-matrices regime is chain.cuh.
 //
-// What the measurements of the earlier schedules say (profiles/r01_notes.md, tools/fp64_latency.cu, tools/mma_bench.cu):
+// What the measurements say (profiles/r01_notes.md, r02_notes.md, tools/fp64_latency.cu, tools/mma_bench.cu, tools/fp64_hog_ilp.cu):
 //   * one DMMA-streaming warp per SM sub-partition reaches 84 % of the FP64 tensor issue rate, two reach 99.5 %;
-//   * any FP64 dependency chain (POTRF, row substitution) that shares a sub-partition with a streaming warp is starved
-//     (275 cycles per dependent instruction beside one stream, ~10^4 beside two).
+//   * any FP64 dependency chain (POTRF, row substitution) that shares a sub-partition with a warp streaming INDEPENDENT
+//     DMMAs is starved (275 cycles per dependent instruction beside one stream, ~10^4 beside two) — a warp running ONE
+//     dependent DMMA chain (27 cycles a link) leaves it alone.
 // So the latency chains and the streams must not share an SM, and whatever stays next to the streams must itself be DMMA:
 //
-//   GEMM CTAs   (most SMs; 8 math warps = two per sub-partition, 4 producer warps).  A task (i, k, b) runs
-//               S = C_ik - sum_j L_ij L_kj^T with 16x32 warp tiles, operands streamed by the producers through an
-//               mbarrier ring (cp.async.cg), then
+//   GEMM CTAs   (most SMs; three math groups of four warps, one per sub-partition).  A task (i, k, b) runs
+//               S = C_ik - sum_j L_ij L_kj^T with 16x64 warp tiles, operands streamed by TMA through an mbarrier ring, then
 //                 i >  k : the triangular solve X = S L_kk^{-T} as DMMAs only — block substitution over 8-column blocks
 //                          against M_kk, the tile L_kk whose 8x8 diagonal blocks were replaced by their inverses (8
 //                          dependent steps of two DMMAs each, warp-local on an 8x64 row block, no FP64 scalar chain).
@@ -17,42 +18,21 @@
 //                          digit);
 //                 i == k : S goes back to global memory, flag := 1 (the SYRK half of a diagonal task).
 //   factor CTAs (a few SMs, three independent 128-thread workers each) take the diagonal tiles: wait for S, POTRF in
-//               shared memory (chol.cuh), write L_kk, invert the eight 8x8 diagonal blocks, write M_kk, flag := 2.
+//               shared memory, write L_kk, invert the eight 8x8 diagonal blocks, write M_kk, flag := 2.
 //               Nothing else runs on their SM, so the chain sees the bare 32-cycle DFMA latency.
 //
 // Both roles claim their tasks in order from two lists derived from ONE topologically ordered list (df_build_tasks), so
 // the earliest unfinished task of the joint order is always claimed and never waits: no deadlock with all CTAs
-// co-resident (cooperative launch).  Every wait is bounded by the watchdog / abort flag of dataflow.cuh.
+// co-resident (cooperative launch).  Every wait is bounded by the watchdog / abort flag of flags.cuh.
 #pragma once
-#include "dataflow.cuh"
+#include "flags.cuh"
 
-#ifndef HT_NG
-#define HT_NG 2                         // independent math groups per GEMM CTA (each: 4 math warps, one per sub-partition)
-#endif
-#ifndef HT_PW
-#define HT_PW 2                         // producer warps per group
-#endif
-#define HT_MATH_WARPS (4 * HT_NG)
-// GEMM CTA: HT_NG x (4 math warps + HT_PW producer warps), rounded up to whole warpgroups;  factor CTA: 3 workers x 128 threads
-#define HT_THREADS (128 * ((HT_MATH_WARPS + HT_NG * HT_PW + 3) / 4))
-#ifndef HT_NST
-#define HT_NST 3                        // ring stages per group (36 KiB each: an operand half-slab pair, or one whole 64x64 tile)
-#endif
 #define HT_QD 4                         // task queue depth
-#define HT_STAGE_DOUBLES CHOL_STAGE_DOUBLES
-#define HT_SMEM_DOUBLES (HT_NG * HT_NST * HT_STAGE_DOUBLES)
-#if HT_NG != 2
-#error "the cp.async-fed variant runs two math groups (three need the TMA-fed kernel, hetero_tma.cuh)"
-#endif
 #define HT_STR2(x) #x
 #define HT_STR(x) HT_STR2(x)
-#define HT_SMEM_BYTES (HT_SMEM_DOUBLES * 8)
 #define HT_WORKER_DOUBLES (GSUM_TILE * GSUM_LDS + 4 * GSUM_TILE)     // factor worker: tile + diag + scratch + reciprocal pivots
 #define HT_RINV (3 * GSUM_TILE)                                      // offset of the reciprocal pivots 1 / L_jj behind dg
 #define HT_NSTAT 40
-#ifndef HT_LEAN_POTRF
-#define HT_LEAN_POTRF 1
-#endif
 #ifndef HT_FACTOR_CTAS
 #define HT_FACTOR_CTAS 12               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
 #endif
@@ -90,101 +70,6 @@ __device__ __forceinline__ bool flag_wait_ge(const int *flag, int want, int *abo
     }
     return true;
 }
-__device__ __forceinline__ void ht_ring_advance(RingState &r) {
-    if (++r.stage == HT_NST) { r.stage = 0; r.phase ^= 1u; }
-}
-
-// One ring stage (K depth 32) on a 16 x 64 warp tile (chol.cuh Acc): acc += A[rows 16 wg ..] * B[8 ntm rows]^T.  The sign
-// is the caller's business (the accumulator starts at -C), so the loop is loads and DMMAs only.
-template <int MT, bool FULL>
-__device__ __forceinline__ void ht_stage_mma(Acc &acc, const double *As, const double *Bs, int wg, int ntm, int g, int t) {
-    const double *ap = As + (wg * 16 + g) * GSUM_LDH + t;
-    const double *bp = Bs + g * GSUM_LDH + t;
-#pragma unroll
-    for (int ks = 0; ks < GSUM_KH / 4; ks++) {
-        double a[MT], b[8];
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) a[mt] = ap[mt * 8 * GSUM_LDH + ks * 4];
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++) if (FULL || nt < ntm) b[nt] = bp[nt * 8 * GSUM_LDH + ks * 4];
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++)
-            if (FULL || nt < ntm) {
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
-            }
-    }
-}
-
-// Diagonal (SYRK) task: only the 36 blocks on and below the diagonal are needed.  Warp wg takes the block rows wg and
-// 7 - wg (wg + 1 and 8 - wg blocks: nine per warp, so the four sub-partitions carry the same load):
-//     acc[0][nt] <-> block (wg, nt), nt <= wg;      acc[1][nt] <-> block (7 - wg, nt), nt <= 7 - wg.
-__device__ __forceinline__ void ht_stage_syrk(Acc &acc, const double *As, int wg, int g, int t) {
-    const double *ap0 = As + (wg * 8 + g) * GSUM_LDH + t;
-    const double *ap1 = As + ((7 - wg) * 8 + g) * GSUM_LDH + t;
-    const double *bp = As + g * GSUM_LDH + t;
-#pragma unroll
-    for (int ks = 0; ks < GSUM_KH / 4; ks++) {
-        double b[8];
-        const double a0 = ap0[ks * 4], a1 = ap1[ks * 4];
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++) if (nt <= 4 || nt <= 7 - wg) b[nt] = bp[nt * 8 * GSUM_LDH + ks * 4];
-#pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            if (nt <= 3 && nt <= wg) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
-            if (nt <= 4 || nt <= 7 - wg) dmma884(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
-        }
-    }
-}
-
-// X = S * L_kk^{-T} on this warp's MT row blocks of 8 x 64, held as C fragments  T[mt][nt][e] <-> row 8 mt + g, column
-// 8 nt + 2t + e.  Ms: M_kk in shared memory (row stride GSUM_LDS).  Right-looking over 8-column blocks:
-//   X_cb = S_cb * Dinv_cb^T  (two DMMAs),   S_j -= X_cb * L[j, cb]^T  for the later blocks j (two DMMAs each, independent).
-// The C -> A fragment re-layouts are quad shuffles; the MT row blocks are independent chains that interleave.
-template <int MT>
-__device__ __forceinline__ void ht_trsm_dinv(Acc &T, const double *Ms, int g, int t) {
-    const unsigned FULLMASK = 0xffffffffu;
-    const int s0 = t >> 1, s1 = 2 + (t >> 1);
-    const bool odd = (t & 1) != 0;
-#pragma unroll
-    for (int cb = 0; cb < 8; cb++) {
-        const int c0 = cb * 8;
-        const double b0 = Ms[(c0 + g) * GSUM_LDS + c0 + t], b1 = Ms[(c0 + g) * GSUM_LDS + c0 + 4 + t];
-        double a0[MT], a1[MT];
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-            const double p0 = __shfl_sync(FULLMASK, T[mt][cb][0], s0, 4), p1 = __shfl_sync(FULLMASK, T[mt][cb][1], s0, 4);
-            const double q0 = __shfl_sync(FULLMASK, T[mt][cb][0], s1, 4), q1 = __shfl_sync(FULLMASK, T[mt][cb][1], s1, 4);
-            a0[mt] = odd ? p1 : p0;
-            a1[mt] = odd ? q1 : q0;
-        }
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-            double x0 = 0.0, x1 = 0.0;
-            dmma884(x0, x1, a0[mt], b0);
-            dmma884(x0, x1, a1[mt], b1);
-            T[mt][cb][0] = x0; T[mt][cb][1] = x1;
-        }
-        if (cb == 7) break;
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-            const double p0 = __shfl_sync(FULLMASK, T[mt][cb][0], s0, 4), p1 = __shfl_sync(FULLMASK, T[mt][cb][1], s0, 4);
-            const double q0 = __shfl_sync(FULLMASK, T[mt][cb][0], s1, 4), q1 = __shfl_sync(FULLMASK, T[mt][cb][1], s1, 4);
-            a0[mt] = -(odd ? p1 : p0);
-            a1[mt] = -(odd ? q1 : q0);
-        }
-#pragma unroll
-        for (int j = cb + 1; j < 8; j++) {
-            const double l0 = Ms[(j * 8 + g) * GSUM_LDS + c0 + t], l1 = Ms[(j * 8 + g) * GSUM_LDS + c0 + 4 + t];
-#pragma unroll
-            for (int mt = 0; mt < MT; mt++) {
-                dmma884(T[mt][j][0], T[mt][j][1], a0[mt], l0);
-                dmma884(T[mt][j][0], T[mt][j][1], a1[mt], l1);
-            }
-        }
-    }
-}
-
 // M_kk (dense 64 x 64, ld 64) from the factored tile S (smem, stride GSUM_LDS; dg[j] = L_jj): L_kk below the 8x8
 // diagonal blocks, the INVERSES of the diagonal blocks on them, zeros above.  Threads 64..127 copy the off-diagonal
 // part while thread (cb, j) < 64 solves  L_blk x = e_j  by substitution in registers (reciprocal pivots, one multiply
@@ -222,7 +107,7 @@ __device__ __forceinline__ void ht_write_mkk(const double *S, const double *rinv
 }
 
 // POTRF of a 64x64 tile in shared memory (stride GSUM_LDS) by one 128-thread group, blocked by 8 columns, written so
-// that neither its speed nor its correctness depends on how ptxas schedules it (tile_potrf_blocked_inl keeps 36 + 8
+// that neither its speed nor its correctness depends on how ptxas schedules it (an earlier version kept 36 + 8
 // doubles live per thread and wants ~180 registers; in a kernel whose register target is lower, ptxas serialises its
 // dependency chain and the tile takes 2x longer).  Per 8-column block:
 //   F  warp 3 factors the 8x8 diagonal block in registers (every lane redundantly; chain rsqrt -> mul -> fma per column)
@@ -287,10 +172,7 @@ __device__ __forceinline__ void potrf_lean_update_block(double *S, int cb, int r
     double2 o; o.x = c0v; o.y = c1v;
     *reinterpret_cast<double2 *>(S + off) = o;
 }
-#ifndef HT_POTRF_TWO_SITES
-#define HT_POTRF_TWO_SITES 1
-#endif
-__device__ __forceinline__ void tile_potrf_lean_two_sites(double *S, double *dg, int *s_fail) {
+__device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fail) {
     const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
@@ -343,66 +225,6 @@ __device__ __forceinline__ void tile_potrf_lean_two_sites(double *S, double *dg,
     CONS_SYNC();
 }
 
-__device__ __forceinline__ void tile_potrf_lean(double *S, double *dg, int *s_fail) {
-    const int tid = EPI_TID, lane = tid & 31, w = tid >> 5;
-    const int g = lane >> 2, t = lane & 3;
-    const double *wb = dg + GSUM_TILE, *rsd = dg + 2 * GSUM_TILE + 8;
-#if HT_POTRF_TWO_SITES
-    tile_potrf_lean_two_sites(S, dg, s_fail);
-    return;
-#endif
-    // ONE copy of every phase (the loop is not unrolled and the block factorisation has a single call site): the code of a
-    // tile stays within the 32 KB instruction cache level of the SM — a phase fetched from L2 costs more than it computes.
-#pragma unroll 1
-    for (int cb = 0; cb < 8; cb++) {
-        // ---- B of step cb-1 with look-ahead, then F of block cb ----  blocks (rb, cb2), cb-1 < cb2 <= rb <= 7, numbered row by
-        // row; block 0 = (cb, cb) is warp 3's, which factors it at once while warps 0-2 update the rest
-        if (w == 3) {
-            if (cb > 0) {
-                potrf_lean_update_block(S, cb - 1, cb, cb, g, t);
-                __syncwarp();
-            }
-            potrf_lean_factor_block(S, dg, s_fail, cb, lane);
-        } else if (cb > 0) {
-            const int nt = 8 - cb, nblk = nt * (nt + 1) / 2;
-#pragma unroll 1
-            for (int blk = 1 + w; blk < nblk; blk += 3) {
-                int rbi = 0, rem = blk;
-                while (rem > rbi) { rem -= rbi + 1; rbi++; }        // blk -> (rbi, rem) with rem <= rbi
-                potrf_lean_update_block(S, cb - 1, cb + rbi, cb + rem, g, t);
-            }
-        }
-        CONS_SYNC();
-        if (cb == 7) break;
-        {
-            // ---- S ----  row rr = c0 + 8 + tid
-            const int c0 = cb * 8, rr = c0 + 8 + tid;
-            if (rr < GSUM_TILE) {
-                double *row = S + rr * GSUM_LDS + c0;
-                double x[8];
-#pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(row + c);
-                    x[c] = v.x; x[c + 1] = v.y;
-                }
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    double v = x[c];
-#pragma unroll
-                    for (int m = 0; m < c; m++) v = fma(-x[m], wb[c * 8 + m], v);
-                    x[c] = v * rsd[c];
-                }
-#pragma unroll
-                for (int c = 0; c < 8; c += 2) {
-                    double2 v; v.x = x[c]; v.y = x[c + 1];
-                    *reinterpret_cast<double2 *>(row + c) = v;
-                }
-            }
-        }
-        CONS_SYNC();
-    }
-}
-
 // ---- factor worker: one 128-thread group of a factor CTA ------------------------------------------------------------
 // The first nf0 entries of the factor list are the column-0 tiles: nothing precedes them, so at the start of the launch
 // EVERY CTA can take some (phase 0, own counter; `helper` = a math group of a GEMM CTA, which leaves after that phase)
@@ -441,11 +263,7 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
         if (tid == 0) *s_fail = 0;
         CONS_SYNC();
         const long long t2 = st ? clock64() : 0;
-#if HT_LEAN_POTRF
         tile_potrf_lean(S, dg, s_fail);
-#else
-        tile_potrf_blocked_inl(S, dg, s_fail);
-#endif
         const long long t3 = st ? clock64() : 0;
         const int fail = *s_fail;
         // Critical path first: M_kk (what the panel tasks of this column wait for), then the flag; L_kk itself, the
@@ -466,296 +284,6 @@ __device__ __forceinline__ void ht_factor_worker(const HeteroArgs &D, double *S,
         CONS_SYNC();                                  // S and dg are reused by the next tile
         if (st && tid == 0) { st[0] += t1 - t0; st[1] += clock64() - t1; st[2] += 1; st[3] += t2 - t1; st[4] += t3 - t2; }
     }
-}
-
-template <bool STATS>
-__global__ void __launch_bounds__(HT_THREADS, 1) chol_hetero_kernel(HeteroArgs D) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t full_bar[HT_NG][HT_NST], empty_bar[HT_NG][HT_NST], tq_full[HT_NG][HT_QD], tq_empty[HT_NG][HT_QD];
-    __shared__ int4 tq[HT_NG][HT_QD];
-    __shared__ int done_cnt[HT_NG][HT_QD];
-    const BorderedBatch &P = D.P;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const bool st_on = STATS && D.stats != nullptr;
-    long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long st_t0 = STATS ? clock64() : 0;
-#define HT_T0() const long long _t = st_on ? clock64() : 0
-#define HT_ACC(q) do { if (st_on) st[q] += clock64() - _t; } while (0)
-
-    if ((int)blockIdx.x < D.nfactor_ctas) {
-        // ============================ factor CTA ================================================================
-        if (tid >= 128 * D.nworkers) return;         // up to three 128-thread workers
-        ht_factor_worker(D, smem + (tid >> 7) * HT_WORKER_DOUBLES, st_on ? st : nullptr);
-        if (st_on && (tid & 127) == 0) {
-            long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + (tid >> 7) * 6;
-            o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; o[5] = st[4];
-        }
-        return;
-    }
-
-    // ============================ GEMM CTA: two independent groups ==============================================
-    // Group q = 4 math warps (one per sub-partition: warps 4q .. 4q+3) + HT_PW producer warps, with its own task queue
-    // and operand ring.  The groups run different tasks and drift apart, so while one sits in a task's latency-bound
-    // parts (accumulator load, triangular solve, stores, fence, flag) the other keeps the FP64 tensor pipe streaming.
-    const int q = (w < HT_MATH_WARPS) ? (w >> 2) : ((w - HT_MATH_WARPS) / HT_PW);
-    double *ring_base = smem + q * (HT_NST * HT_STAGE_DOUBLES);
-    uint64_t *fullb = full_bar[q], *emptyb = empty_bar[q], *tqf = tq_full[q], *tqe = tq_empty[q];
-    int4 *tqs = tq[q];
-    if (tid == 0) {
-        for (int qq = 0; qq < HT_NG; qq++) {
-            for (int s = 0; s < HT_QD; s++) done_cnt[qq][s] = 0;
-            for (int s = 0; s < HT_NST; s++) { mbar_init(&full_bar[qq][s], 32 * HT_PW); mbar_init(&empty_bar[qq][s], 4); }
-            for (int s = 0; s < HT_QD; s++) { mbar_init(&tq_full[qq][s], 1); mbar_init(&tq_empty[qq][s], 4 + HT_PW - 1); }
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    int *abort_flag = D.ctl + 1;
-
-    if (w >= HT_MATH_WARPS) {
-        if (w >= HT_MATH_WARPS + HT_NG * HT_PW) return;      // padding warps of the last warpgroup
-        // ============================ producer warps =========================================================
-        const int pw = (w - HT_MATH_WARPS) % HT_PW;
-        RingState ring = {0, 0u};
-        for (int n = 0;; n++) {
-            const int slot = n % HT_QD;
-            int4 tk = make_int4(-1, 0, 0, 0);
-            int ok = 1;
-            if (pw == 0) {
-                if (lane == 0) {
-                    { HT_T0(); ok = mbar_wait(&tqe[slot], (((unsigned)(n / HT_QD)) & 1u) ^ 1u, abort_flag); HT_ACC(0); }
-                    if (ok) {
-                        const int tix = atomicAdd(D.ctl, 1);
-                        if (tix < D.ngtasks) tk = D.gtasks[tix];
-                        tqs[slot] = tk;
-                        mbar_arrive(&tqf[slot]);
-                    }
-                }
-                ok = __shfl_sync(0xffffffffu, ok, 0);
-                tk.x = __shfl_sync(0xffffffffu, tk.x, 0); tk.y = __shfl_sync(0xffffffffu, tk.y, 0);
-                tk.z = __shfl_sync(0xffffffffu, tk.z, 0); tk.w = __shfl_sync(0xffffffffu, tk.w, 0);
-            } else {
-                ok = mbar_wait(&tqf[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag);
-                if (ok) {
-                    tk = tqs[slot];
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tqe[slot]);
-                }
-            }
-            if (!ok || tk.x < 0) break;
-            const int i = tk.x, k = tk.y, b = tk.z;
-            const bool diag = (i == k), thin = (tk.w & 1) != 0;
-            const double *Ab = P.A + (int64_t)b * P.bstride;
-            const double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
-                                         : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
-            const double *Ak = Ab + (int64_t)k * GSUM_TILE * P.ld;
-            const int *frow_i = D.flags + ((int64_t)b * P.Trows + i) * P.T;
-            const int *frow_k = D.flags + ((int64_t)b * P.Trows + k) * P.T;
-            constexpr int RPW = GSUM_TILE / HT_PW;          // tile rows per producer warp
-            bool alive = true;
-            // ---- stage 0 of the task: the C tile (original data, written before the launch) ----------------------
-            {
-                int good = 1;
-                if (lane == 0) { HT_T0(); good = mbar_wait(&emptyb[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
-                alive = __shfl_sync(0xffffffffu, good, 0) != 0;
-                if (!alive) break;
-                double *Cs = ring_base + ring.stage * HT_STAGE_DOUBLES;
-                const double *C = Ri + k * GSUM_TILE;
-                if (!thin) {
-#pragma unroll 8
-                    for (int r = 0; r < RPW; r++) {
-                        const int row = pw * RPW + r;
-                        cp_async16(Cs + row * GSUM_LDS + lane * 2, C + (int64_t)row * P.ld + lane * 2);
-                    }
-                } else if (pw == 0) {
-#pragma unroll
-                    for (int r = 0; r < 8; r++) cp_async16(Cs + r * GSUM_LDS + lane * 2, C + (int64_t)r * P.ld + lane * 2);
-                }
-                cp_async_mbar_arrive(&fullb[ring.stage]);
-                ht_ring_advance(ring);
-            }
-            // ---- operand half-slabs: a warp-wide copy moves two rows of 256 bytes -------------------------------
-            const int r0 = pw * RPW + (lane >> 4), ch = (lane & 15) * 2;
-            // A finished tile (r, k-1) implies every (r, j < k-1): they were its operands.
-            int done_i = 1, done_k = 1;
-            if (lane == 0 && k > 0) {
-                done_i = ld_relaxed(frow_i + k - 1) >= 1;
-                done_k = diag ? done_i : (ld_relaxed(frow_k + k - 1) >= 1);
-            }
-            for (int h = 0; h < 2 * k && alive; h++) {
-                const int j = h >> 1;
-                int good = 1;
-                if (lane == 0) {
-                    if ((h & 1) == 0 && !(done_i && done_k)) {
-                        HT_T0();
-                        good = (done_i || flag_wait(frow_i + j, abort_flag)) && (diag || done_k || flag_wait(frow_k + j, abort_flag));
-                        HT_ACC(1);
-                    }
-                    if (good) { HT_T0(); good = mbar_wait(&emptyb[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
-                }
-                alive = __shfl_sync(0xffffffffu, good, 0) != 0;
-                if (!alive) break;
-                double *As = ring_base + ring.stage * HT_STAGE_DOUBLES, *Bs = As + GSUM_TILE * GSUM_LDH;
-                const int col0 = j * GSUM_TILE + (h & 1) * GSUM_KH;
-                if (!thin) {
-#pragma unroll 8
-                    for (int r = 0; r < RPW / 2; r++) {
-                        const int row = r0 + 2 * r;
-                        cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
-                    }
-                } else if (pw == 0) {                      // thin task: rows 0..7 of the A operand only
-#pragma unroll
-                    for (int r = 0; r < 4; r++) {
-                        const int row = (lane >> 4) + 2 * r;
-                        cp_async16(As + row * GSUM_LDH + ch, Ri + (int64_t)row * P.ld + col0 + ch);
-                    }
-                }
-                if (!diag) {
-#pragma unroll 8
-                    for (int r = 0; r < RPW / 2; r++) {
-                        const int row = r0 + 2 * r;
-                        cp_async16(Bs + row * GSUM_LDH + ch, Ak + (int64_t)row * P.ld + col0 + ch);
-                    }
-                }
-                cp_async_mbar_arrive(&fullb[ring.stage]);
-                ht_ring_advance(ring);
-            }
-            if (!alive) break;
-            // ---- last stage of a panel task: M_kk -----------------------------------------------------------------
-            if (!diag) {
-                int good = 1;
-                if (lane == 0) {
-                    { HT_T0(); good = flag_wait_ge(frow_k + k, 2, abort_flag) ? 1 : 0; HT_ACC(3); }
-                    if (good) { HT_T0(); good = mbar_wait(&emptyb[ring.stage], ring.phase ^ 1u, abort_flag); HT_ACC(2); }
-                }
-                alive = __shfl_sync(0xffffffffu, good, 0) != 0;
-                if (!alive) break;
-                double *Ms = ring_base + ring.stage * HT_STAGE_DOUBLES;
-                const double *Mg = D.M + ((int64_t)b * P.T + k) * (GSUM_TILE * GSUM_TILE);
-#pragma unroll 8
-                for (int r = 0; r < RPW; r++) {
-                    const int row = pw * RPW + r;
-                    cp_async16(Ms + row * GSUM_LDS + lane * 2, Mg + row * GSUM_TILE + lane * 2);
-                }
-                cp_async_mbar_arrive(&fullb[ring.stage]);
-                ht_ring_advance(ring);
-            }
-        }
-        cp_async_wait<0>();
-        if (st_on && pw == 0 && lane == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[0] = clock64() - st_t0; o[1] = st[0]; o[2] = st[1]; o[3] = st[2]; o[4] = st[3]; }
-    } else {
-        // ============================ math warps ============================================================
-        const int g = lane >> 2, t = lane & 3, wg = w & 3;
-        RingState ring = {0, 0u};
-        for (int n = 0;; n++) {
-            const int slot = n % HT_QD;
-            bool alive;
-            { HT_T0(); alive = mbar_wait(&tqf[slot], ((unsigned)(n / HT_QD)) & 1u, abort_flag); HT_ACC(0); }
-            int4 tk = make_int4(-1, 0, 0, 0);
-            if (alive) {
-                tk = tqs[slot];
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tqe[slot]);
-            }
-            if (!alive || tk.x < 0) break;             // no CTA-level barrier anywhere in this role: a warp may leave alone
-            const int i = tk.x, k = tk.y, b = tk.z;
-            const bool diag = (i == k), thin = (tk.w & 1) != 0;
-            double *Ab = P.A + (int64_t)b * P.bstride;
-            double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
-                                   : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
-            double *C = Ri + k * GSUM_TILE;
-            const bool active = !thin || wg == 0;           // thin task (rows 0..7 in use): warp 0 of the group alone
-            // rows of this warp's two m tiles: 16 wg, 16 wg + 8 — or, on a diagonal task, the block rows wg and 7 - wg
-            const int row0 = diag ? wg * 8 : wg * 16, row1 = diag ? (7 - wg) * 8 : wg * 16 + 8;
-            const int n0 = diag ? wg + 1 : 8, n1 = diag ? 8 - wg : 8;           // n tiles in use per m tile
-            // ---- acc = -C ------------------------------------------------------------------------------------------
-            Acc acc;
-            {
-                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(1); }
-                if (!alive) break;
-                const double *Cs = ring_base + ring.stage * HT_STAGE_DOUBLES;
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++) {
-                        if (nt < (mt ? n1 : n0) && active && (!thin || mt == 0)) {
-                            const double2 v = *reinterpret_cast<const double2 *>(Cs + ((mt ? row1 : row0) + g) * GSUM_LDS + nt * 8 + 2 * t);
-                            acc[mt][nt][0] = -v.x; acc[mt][nt][1] = -v.y;
-                        } else { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
-                    }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
-                ht_ring_advance(ring);
-            }
-            // ---- main loop ---------------------------------------------------------------------------------------
-            for (int h = 0; h < 2 * k; h++) {
-                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(1); }
-                if (!alive) break;
-                const double *As = ring_base + ring.stage * HT_STAGE_DOUBLES;
-                if (thin) { if (active) ht_stage_mma<1, true>(acc, As, As + GSUM_TILE * GSUM_LDH, wg, 8, g, t); }
-                else if (diag) ht_stage_syrk(acc, As, wg, g, t);
-                else ht_stage_mma<2, true>(acc, As, As + GSUM_TILE * GSUM_LDH, wg, 8, g, t);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
-                ht_ring_advance(ring);
-            }
-            if (!alive) break;
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int nt = 0; nt < 8; nt++) { acc[mt][nt][0] = -acc[mt][nt][0]; acc[mt][nt][1] = -acc[mt][nt][1]; }
-            if (diag) {
-                // ---- S back in place; the factor CTAs take it from there ------------------------------------------
-#pragma unroll
-                for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                    for (int nt = 0; nt < 8; nt++)
-                        if (nt < (mt ? n1 : n0)) {
-                            double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
-                            *reinterpret_cast<double2 *>(C + (int64_t)((mt ? row1 : row0) + g) * P.ld + nt * 8 + 2 * t) = v;
-                        }
-            } else {
-                // ---- the triangular solve, warp-local on the 16 x 64 row block ------------------------------------
-                { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(2); }
-                if (!alive) break;
-                if (active) {
-                    HT_T0();
-                    const double *Ms = ring_base + ring.stage * HT_STAGE_DOUBLES;
-                    if (thin) ht_trsm_dinv<1>(acc, Ms, g, t); else ht_trsm_dinv<2>(acc, Ms, g, t);
-                    HT_ACC(3);
-#pragma unroll
-                    for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                        for (int nt = 0; nt < 8; nt++)
-                            if (!thin || mt == 0) {
-                                double2 v; v.x = acc[mt][nt][0]; v.y = acc[mt][nt][1];
-                                *reinterpret_cast<double2 *>(C + (int64_t)(wg * 16 + mt * 8 + g) * P.ld + nt * 8 + 2 * t) = v;
-                            }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
-                ht_ring_advance(ring);
-            }
-            // ---- publish the tile: no barrier — the last of the four warps to get here stores the flag.  Each warp's lane 0
-            // joins with an acq_rel atomic at CTA scope (after __syncwarp: the warp's stores happen-before it), so the
-            // release store of the last arriver is cumulative over the tile stores of all four warps.
-            { HT_T0();
-            __syncwarp();
-            if (lane == 0) {
-                int old;
-                asm volatile("atom.acq_rel.cta.shared.add.s32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&done_cnt[q][slot])) : "memory");
-                if (old == 3) {
-                    done_cnt[q][slot] = 0;
-                    st_release(D.flags + ((int64_t)b * P.Trows + i) * P.T + k, 1);
-                }
-            }
-            HT_ACC(4); }
-            st[5] += 1;
-        }
-        if (st_on && (tid & 127) == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[5] = clock64() - st_t0; o[6] = st[0]; o[7] = st[1]; o[8] = st[2]; o[9] = st[3]; o[10] = st[4]; o[11] = st[5]; }
-    }
-#undef HT_T0
-#undef HT_ACC
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------

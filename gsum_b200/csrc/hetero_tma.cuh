@@ -1,8 +1,9 @@
-// TMA-fed variant of the heterogeneous schedule (hetero.cuh): same task lists, flags, factor CTAs and DMMA-only
-// triangular solve, but the operand rings of the GEMM CTAs are filled by the TMA unit instead of cp.async warps.
+// The factorisation kernel: the heterogeneous schedule of hetero.cuh with the operand rings of the GEMM CTAs filled by the
+// TMA unit.
 //
-// Why: beside DMMA-streaming warps a producer warp gets few issue slots (measured: one cp.async warp per group left the
-// math warps waiting 16 % of the time; two per group is what fits in 384 threads and caps the CTA at two math groups).
+// Why TMA: beside DMMA-streaming warps a producer warp gets few issue slots (measured in round 1: one cp.async warp per
+// group left the math warps waiting 16 % of the time; two per group is what fits in 384 threads and caps the CTA at two
+// math groups — that variant ran the C4 launch in 2.04 ms against 1.91 ms here).
 // A tiled tensor-map copy (cp.async.bulk.tensor.2d, SASS UTMALDG) moves a 64 x 16 FP64 box (8 KiB) per instruction, so
 // ONE elected lane per group feeds its ring and the CTA can run THREE math groups = three DMMA warps per sub-partition.
 //
@@ -66,7 +67,10 @@ __device__ __forceinline__ void hx_stage_mma(Acc &acc, const double *As, const d
         }
 }
 
-// X = S * L_kk^{-T}: as ht_trsm_dinv, with M_kk in the swizzled tile layout.  om[p][h] = this lane's offset inside a
+// X = S * L_kk^{-T} on this warp's MT row blocks of 8 x 64, held as C fragments  T[mt][nt][e] <-> row 8 mt + g, column
+// 8 nt + 2t + e, with M_kk in the swizzled tile layout.  Right-looking over 8-column blocks:
+//   X_cb = S_cb * Dinv_cb^T  (two DMMAs),   S_j -= X_cb * L[j, cb]^T  for the later blocks j (two DMMAs each, independent).
+// The C -> A fragment re-layouts are quad shuffles; the MT row blocks are independent chains that interleave.  om[p][h] = this lane's offset inside a
 // 128-byte row for column  8 (2 p' + p) + 4 h + t  (p = cb & 1 selects the half of the 16-column box).
 template <int MT>
 __device__ __forceinline__ void hx_trsm_dinv(Acc &T, const double *Ms, int g, int t, const int (&om)[2][2]) {

@@ -85,29 +85,42 @@ def test_cholesky_batch_under_contention_is_deterministic(ctx):
     assert not info.any() and relerr(L @ np.swapaxes(L, 1, 2), A) < 5e-15
 
 
-@pytest.mark.parametrize("schedule", ["hetero_tma", "hetero", "pipeline", "dataflow", "multilaunch"])
-def test_factorisation_schedules_agree(schedule, monkeypatch):
-    """Every schedule of the bordered factorisation (GSUM_B200_SCHEDULE) gives the same factor, solve and likelihood grid
-    to rounding: they are cross-checks of one another."""
+@pytest.mark.parametrize("n", [300, 1024])
+def test_chain_mode_is_bit_identical_to_many_matrices_schedule(n, monkeypatch):
+    """The two regimes of the factorisation — chain mode (few matrices: one chain CTA per matrix owns the diagonal band,
+    csrc/chain.cuh) and the many-matrices schedule (factor CTAs claim diagonal tiles) — perform the same operations on every
+    element in the same order: factor, forward solve and likelihood grid are bit-identical, so a cell does not depend on how
+    many length scales share its launch (a shard of 16 and the 1-GPU grid of 128 give the same numbers)."""
     from gsum_b200 import _lib
-    monkeypatch.setenv("GSUM_B200_SCHEDULE", schedule)
-    c = _lib.Context(0)
+    monkeypatch.setenv("GSUM_B200_CHAIN_MAX", "0")
+    many = _lib.Context(0)
+    monkeypatch.delenv("GSUM_B200_CHAIN_MAX")
+    chain = _lib.Context(0)
     try:
         rs = np.random.RandomState(3)
-        n = 300
         X = np.sort(rs.rand(n))[:, None]
         A = np.stack([RBF(0.05 * (b + 1))(X) + 1e-5 * np.eye(n) for b in range(5)])
-        L, info, logdet = ops.cholesky(A, return_info=True, ctx=c)
-        Lr = np.linalg.cholesky(A)
-        assert not info.any() and relerr(L, Lr) < 1e-10
+        Lc, info, logdet_c = ops.cholesky(A, return_info=True, ctx=chain)
+        Lm, info_m, logdet_m = ops.cholesky(A, return_info=True, ctx=many)
+        assert not info.any() and not info_m.any()
+        assert np.array_equal(Lc, Lm) and np.array_equal(logdet_c, logdet_m)
+        assert relerr(Lc, np.linalg.cholesky(A)) < 1e-10
         B = rs.randn(n, 70)
-        assert relerr(ops.cho_solve(Lr[0], B, ctx=c), cho_solve((Lr[0], True), B)) < 1e-10
+        assert relerr(ops.cho_solve(Lc[0], B, ctx=chain), cho_solve((Lc[0], True), B)) < 1e-10
         dy = rs.randn(n, 4)
-        ll = ops.lml_grid(X, dy, 1.0, np.arange(4), np.array([[0.05], [0.2]]), np.array([0.3, 0.5, 0.7]), noise=1e-5, nugget=1e-10, ctx=c)
-        ll0 = ops.lml_grid(X, dy, 1.0, np.arange(4), np.array([[0.05], [0.2]]), np.array([0.3, 0.5, 0.7]), noise=1e-5, nugget=1e-10)
-        assert relerr(ll, ll0) < 1e-10
+        args = (X, dy, 1.0, np.arange(4), np.array([[0.05], [0.2], [0.11]]), np.array([0.3, 0.5, 0.7]))
+        ll_c = ops.lml_grid(*args, noise=1e-5, nugget=1e-10, ctx=chain)
+        ll_m = ops.lml_grid(*args, noise=1e-5, nugget=1e-10, ctx=many)
+        assert np.array_equal(ll_c, ll_m)
+        # a failing matrix (negative diagonal entry) in the batch: same status, the healthy ones untouched
+        A2 = A.copy()
+        A2[2, 100, 100] = -1.0
+        Lc2, info_c2, _ = ops.cholesky(A2, return_info=True, ctx=chain)
+        Lm2, info_m2, _ = ops.cholesky(A2, return_info=True, ctx=many)
+        assert np.array_equal(info_c2, info_m2) and info_c2[2] != 0 and np.array_equal(Lc2[[0, 1, 3, 4]], Lc[[0, 1, 3, 4]])
     finally:
-        c.close()
+        many.close()
+        chain.close()
 
 
 def test_large_single_matrix_8192(ctx):

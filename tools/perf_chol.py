@@ -1,6 +1,6 @@
-"""Dev tool: time the C4 grid (device-resident inputs) and its factorisation bracket under each schedule.
+"""Dev tool: time the C4 grid (device-resident inputs) and its factorisation bracket.
 
-    python tools/perf_chol.py [dataflow] [multilaunch] [--reps 10] [--stats]
+    python tools/perf_chol.py [--nls 128] [--reps 10] [--stats] [nochain]      (nochain: GSUM_B200_CHAIN_MAX=0 beside the default)
 """
 import os
 import sys
@@ -12,7 +12,7 @@ from bench import make_inputs, N_POINTS, N_Q
 from gsum_b200 import _lib, ops
 from gsum_b200.helpers import _order_differences
 
-modes = [a for a in sys.argv[1:] if a in ("dataflow", "multilaunch", "pipeline", "hetero", "hetero_tma")] or ["dataflow", "multilaunch"]
+modes = ["default"] + (["nochain"] if "nochain" in sys.argv[1:] else [])
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 10
 n_ls = int(sys.argv[sys.argv.index("--nls") + 1]) if "--nls" in sys.argv else 128
 dev = torch.device("cuda", 0)
@@ -26,8 +26,11 @@ kw = dict(constant=1.0, noise=1e-6, nugget=1e-10, center0=0.0, disp0=0.0, df0=1.
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 results = {}
 for mode in modes:
-    os.environ["GSUM_B200_SCHEDULE"] = mode
-    if "--stats" in sys.argv and mode in ("dataflow", "pipeline", "hetero", "hetero_tma"):
+    if mode == "nochain":
+        os.environ["GSUM_B200_CHAIN_MAX"] = "0"
+    else:
+        os.environ.pop("GSUM_B200_CHAIN_MAX", None)
+    if "--stats" in sys.argv:
         os.environ["GSUM_B200_DF_STATS"] = "1"
     else:
         os.environ.pop("GSUM_B200_DF_STATS", None)
