@@ -726,12 +726,45 @@ class TruncationProcess:
             b_old, b_new = self.basis(Xc, start=start, end=end)[:, 0], self.basis(X, start=start, end=end)[:, 0]
         if cp._handle is None:
             cp._refit()            # 'eig' route: this predict is decomposition-independent in the reference (LU, models.py:1449)
-        mean, var, cb = cp._handle.predict(
-            X, want=want, Xc=Xc, yc=np.asarray(yc, dtype=np.float64), mean_old=self.mean(Xc, start=start, end=end),
-            mean_new=self.mean(X, start=start, end=end), basis_old=b_old, basis_new=b_new, sc_old=s_old, sc_new=s_new,
-            q_old=q_old, q_new=q_new, gs_start=start, gs_end=end, excluded=self.excluded, truncation=True,
-            want_cond_basis=want_cond_basis, kernel_add=self._kernel_add())
-        return mean[:, 0], var, cb
+        try:
+            mean, var, cb = cp._handle.predict(
+                X, want=want, Xc=Xc, yc=np.asarray(yc, dtype=np.float64), mean_old=self.mean(Xc, start=start, end=end),
+                mean_new=self.mean(X, start=start, end=end), basis_old=b_old, basis_new=b_new, sc_old=s_old, sc_new=s_new,
+                q_old=q_old, q_new=q_new, gs_start=start, gs_end=end, excluded=self.excluded, truncation=True,
+                want_cond_basis=want_cond_basis, kernel_add=self._kernel_add())
+            return mean[:, 0], var, cb
+        except np.linalg.LinAlgError:
+            # K_oo carries neither white noise nor a nugget here (gsum/models.py:1443-1449): beyond a few tens of smooth points
+            # it is not numerically positive definite and has no Cholesky factor, while the reference's LU solve still returns
+            # a result.  Same products through the symmetric eigendecomposition of K_oo on the device instead.
+            return self._conditional_eig(X, Xc, yc, start, end, want, b_old, b_new)
+
+    def _conditional_eig(self, X, Xc, yc, start, end, want, b_old, b_new):
+        """`_conditional` for a K_oo without a Cholesky factor: K_no K_oo^-1 [y - m | basis | K_on] with
+        K_oo^-1 = V diag(1/w) V^T from the device eigensolver (gsum_eigh + gsum_eig_conditional)."""
+        K_oo = self.cov(Xc, Xc, start=start, end=end)
+        K_on = np.ascontiguousarray(self.cov(Xc, X, start=start, end=end))
+        eig = ops.ResidentEigen(K_oo)
+        # eigenvalues at the rounding level of the largest one carry no information (they come out with either sign): they are
+        # left out of the inverse — w = inf makes their 1/w vanish on the device — which is the pseudo-inverse the LU result
+        # scatters around (measured on 60 points, l = 0.5: the data are reproduced to 2e-4 where the reference's LU gives 3e-3)
+        w = eig.w.copy()
+        w[w <= w.shape[0] * np.finfo(np.float64).eps * np.max(w)] = np.inf
+        eig.w_dev.put(w)
+        yc = np.asarray(yc, dtype=np.float64)
+        D = (yc if yc.ndim == 2 else yc[:, None]) - self.mean(Xc, start=start, end=end)[:, None]
+        n_y = D.shape[1]
+        if b_old is not None:
+            D = np.concatenate([D, np.asarray(b_old, dtype=np.float64)[:, None]], axis=1)
+        lin, vterm, cterm = eig.conditional(K_on, np.ascontiguousarray(D), want_var=(want == PREDICT_VAR), want_cov=(want == PREDICT_COV))
+        mean = self.mean(X, start=start, end=end) + lin[:, 0]
+        cb = None if b_old is None else np.asarray(b_new, dtype=np.float64) - lin[:, n_y]
+        var = None
+        if want == PREDICT_VAR:
+            var = self._prior_part(X, start, end, PREDICT_VAR)[1] - vterm
+        elif want == PREDICT_COV:
+            var = self.cov(X, X, start=start, end=end) - cterm
+        return mean, var, cb
 
     def _prior_part(self, X, start, end, want):
         """Unconditioned truncation-error process: mean and (diagonal of the) covariance with Xp = X given

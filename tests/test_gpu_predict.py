@@ -194,3 +194,30 @@ def test_c3_full_size_properties(ctx):
     assert mt.shape == (10000,) and np.isfinite(mt).all() and np.isfinite(st_).all()
     mt2, st2 = gp.predict(Xt[:128], order=5, return_std=True, kind='both')
     assert np.array_equal(mt2, mt[:128]) and np.array_equal(st2, st_[:128])
+
+
+def test_truncation_predict_without_cholesky_factor(ctx):
+    """K_oo of TruncationGP.predict has neither white noise nor nugget (gsum/models.py:1443-1449); with 60 smooth
+    points and a long length scale it is not numerically positive definite, the reference solves it with LU and returns a
+    result.  The device path falls back from the Cholesky factor to the symmetric eigendecomposition of K_oo
+    (models.TruncationProcess._conditional_eig) instead of raising.  The solve is noise-dominated in ANY arithmetic
+    (cond K_oo >> 1/eps), so the comparison is the interpolation property both share and a loose agreement of the means."""
+    rs = np.random.RandomState(11)
+    n = 60
+    X = np.linspace(0, 1, n)[:, None]
+    kern = RBF(0.5, 'fixed') + WhiteKernel(1e-8, 'fixed')
+    coeffs = np.linalg.cholesky(RBF(0.5)(X) + 1e-8 * np.eye(n)) @ rs.randn(n, 4)
+    orders = np.arange(4)
+    y = o.partials(coeffs, 0.4, 1.0, orders)
+    gp = gb.TruncationGP(kern, ratio=0.4, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None).fit(X, y, orders=orders)
+    assert np.linalg.cond(RBF(0.5)(X)) > 1e15                        # no Cholesky factor in FP64
+    Xn = np.linspace(0.05, 0.95, 37)[:, None]
+    for kind in ("interp", "both"):
+        m, s = gp.predict(Xn, order=3, return_std=True, kind=kind)
+        assert m.shape == (37,) and np.isfinite(m).all()
+        f = o.fit_conjugate(kern, X, o.coefficients(y, 0.4, 1.0, orders), o.Priors(0, 0, 1, 1))
+        mr = o.predict_truncation(f, Xn, 3, y[:, 3], lambda X_: 0.4 * np.ones(len(X_)), lambda X_: np.ones(len(X_)), kind=kind)
+        assert np.max(np.abs(m - mr)) < 1e-2 * np.max(np.abs(mr))       # the LU result itself scatters by ~3e-3 here
+    # at the conditioning points themselves the interpolant reproduces the data (both routes)
+    m0 = gp.predict(X, order=3, kind="interp")
+    assert np.max(np.abs(m0 - y[:, 3])) < 1e-3 * np.max(np.abs(y[:, 3]))
