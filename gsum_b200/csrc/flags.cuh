@@ -97,6 +97,7 @@ __global__ void df_check_kernel(const int *abort_flag, int *info, int64_t batch,
 }
 
 #include <vector>
+#include <algorithm>
 // Task list in dependency order with one column of look-ahead.  Column k: first the sub-diagonal tiles (k+1, k, b) of
 // every matrix — the only fresh operand of the next diagonal tile — then `DF_DIAG_DELAY` of the other tiles of the
 // column, then the diagonal tiles (k+1, k+1, b), then the rest.  The diagonal tiles thus start as early as they can

@@ -48,6 +48,9 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
     const char *chn = getenv("GSUM_B200_CHAIN_MAX");
     c->ht_chain_max = chn ? atoi(chn) : HT_CHAIN_MAX;
+    const char *wv = getenv("GSUM_B200_WAVES"), *sg = getenv("GSUM_B200_STAGGER");
+    c->ht_waves = wv ? atoi(wv) : HT_WAVES;
+    c->ht_stagger = sg ? atof(sg) : HT_STAGGER;
     const char *sn = getenv("GSUM_B200_SMALLN");
     c->use_smalln = (sn && strcmp(sn, "0") == 0) ? 0 : 1;
     const char *thin = getenv("GSUM_B200_THIN");
@@ -241,11 +244,12 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     const int delay = getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : HT_DIAG_DELAY;
     // few matrices: chain mode (chain.cuh) — one chain worker CTA per matrix owns the diagonal band
     const bool chain = !solve_only && batch <= c->ht_chain_max;
-    const int key[5] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0) | (chain ? 4 : 0), delay};
+    const int key[7] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0) | (chain ? 4 : 0), delay, c->ht_waves,
+                        (int)lround(c->ht_stagger * 1e6)};
     if (memcmp(key, c->ht_key, sizeof(key)) != 0 || !c->ht_gtasks) {
         std::vector<int4> gt, ft;
         if (chain) ht_build_chain_tasks(gt, P.T, P.Trows, batch, thin_last);
-        else ht_build_tasks(gt, ft, P.T, P.Trows, batch, solve_only, thin_last, delay);
+        else ht_build_tasks(gt, ft, P.T, P.Trows, batch, solve_only, thin_last, delay, c->ht_waves, c->ht_stagger);
         GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // the previous lists may still be in use
         GSUM_TRY(ht_upload(c, &c->ht_gtasks, &c->ht_gcap, gt));
         GSUM_TRY(ht_upload(c, &c->ht_ftasks, &c->ht_fcap, ft));
@@ -276,6 +280,9 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     D.P = P; D.gtasks = (const int4 *)c->ht_gtasks; D.ngtasks = c->ht_ng; D.ftasks = (const int4 *)c->ht_ftasks; D.nftasks = c->ht_nf;
     D.nf0 = (!solve_only && !chain && c->ht_nf >= batch) ? batch : 0;          // df_build_tasks emits the column-0 diagonal tiles first
     D.ctl = c->df_ctl; D.flags = (int *)c->df_flags; D.M = (double *)dM; D.stats = nullptr;
+    D.ngroups = getenv("GSUM_B200_NGROUPS") ? atoi(getenv("GSUM_B200_NGROUPS")) : 3;
+    D.desync = getenv("GSUM_B200_DESYNC") ? atoi(getenv("GSUM_B200_DESYNC")) : 0;
+    D.desync_at = getenv("GSUM_B200_DESYNC_AT") ? atoi(getenv("GSUM_B200_DESYNC_AT")) : 1;
     D.chain = chain ? 1 : 0; D.pre = (int *)c->df_flags + (int64_t)batch * P.Trows * P.T;
     // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
     int nf = 0;
@@ -301,6 +308,13 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         if (!dbg_stats) cudaMalloc((void **)&dbg_stats, sizeof(long long) * HT_NSTAT * 1024);
         cudaMemsetAsync(dbg_stats, 0, sizeof(long long) * HT_NSTAT * 1024, c->stream);
         D.stats = dbg_stats;
+    }
+    static long long *dbg_trace = nullptr;
+    D.trace = nullptr; D.trace_cta = -1;
+    if (D.stats && getenv("GSUM_B200_TRACE_CTA")) {
+        if (!dbg_trace) cudaMalloc((void **)&dbg_trace, sizeof(long long) * 3 * 64 * 8);
+        cudaMemsetAsync(dbg_trace, 0, sizeof(long long) * 3 * 64 * 8, c->stream);
+        D.trace = dbg_trace; D.trace_cta = atoi(getenv("GSUM_B200_TRACE_CTA"));
     }
     {
     if (!c->hx_ready) {
@@ -332,6 +346,14 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
         std::vector<long long> h(HT_NSTAT * grid);
         cudaStreamSynchronize(c->stream);
         cudaMemcpy(h.data(), dbg_stats, sizeof(long long) * HT_NSTAT * grid, cudaMemcpyDeviceToHost);
+        if (D.trace) {
+            std::vector<long long> tr(3 * 64 * 8);
+            cudaMemcpy(tr.data(), dbg_trace, sizeof(long long) * tr.size(), cudaMemcpyDeviceToHost);
+            for (int q = 0; q < 3; q++) for (int n = 0; n < 64; n++) {
+                const long long *e = tr.data() + (q * 64 + n) * 8;
+                if (e[0]) fprintf(stderr, "[trace] %d %d %lld %lld %lld %lld %lld %lld %lld %lld\n", q, n, e[0], e[1], e[2], e[3], e[4], e[5], e[6], e[7]);
+            }
+        }
         double f[6] = {0, 0, 0, 0, 0, 0}, a[HT_NSTAT] = {0};
         const int ngrp = HX_NG;
         for (int g = 0; g < nf; g++) for (int wk = 0; wk < nwk; wk++) for (int q = 0; q < 6; q++) f[q] += (double)h[HT_NSTAT * g + wk * 6 + q];

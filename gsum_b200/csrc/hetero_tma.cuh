@@ -23,7 +23,8 @@
 #define HX_THREADS 512                  // warps 0-11 math (3 groups), 12-14 producers (one elected lane each), 15 idle
 #define HX_BOX_DOUBLES 1024             // 64 rows x 16 doubles
 #define HX_STAGE_DOUBLES (4 * HX_BOX_DOUBLES)
-#define HX_SMEM_BYTES (HX_NG * HX_NST * HX_STAGE_DOUBLES * 8 + 1024)          // + alignment slack (swizzle atoms: 1024 B)
+#define HX_THINX_DOUBLES 1024            // per group: two 8 x 64 exchange buffers of the thin tasks (see hx_stage_mma_thin)
+#define HX_SMEM_BYTES ((HX_NG * HX_NST * HX_STAGE_DOUBLES + HX_NG * HX_THINX_DOUBLES) * 8 + 1024)      // + alignment slack (swizzle atoms: 1024 B)
 #define HX_MATH_REGS 160                // 384 * 160 + 128 * 32 = 65536
 
 struct HeteroMaps {
@@ -64,6 +65,51 @@ __device__ __forceinline__ void hx_stage_mma(Acc &acc, const double *As, const d
                 if (FULL || nt < n0) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
                 if (MT == 2 && (FULL || nt < n1)) dmma884(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
             }
+        }
+}
+
+// The same stage on a DIAGONAL task (SYRK half: only the 36 blocks on or below the diagonal).  Warp wg owns the block rows
+// wg (N0 = wg + 1 blocks) and 7 - wg (9 - N0 blocks): nine blocks per warp, the same load on every sub-partition.  N0 is a
+// template parameter so that the code is straight-line: a DMMA under a run-time predicate costs a WARPSYNC.ALL + NOP pair
+// each (SASS), and beside two groups streaming unconditional DMMAs such a warp falls far behind its share of the pipe
+// (measured: 15-19k cycles per K = 64 step for 9/16 of the work of a full step, which takes 11.5k; profiles/r02_notes.md).
+template <int N0>
+__device__ __forceinline__ void hx_stage_mma_diag(Acc &acc, const double *As, int g, const int (&oa)[4]) {
+    constexpr int N1 = 9 - N0, ROW0 = (N0 - 1) * 8, ROW1 = (8 - N0) * 8;
+    const double *a0p = As + (ROW0 + g) * 16, *a1p = As + (ROW1 + g) * 16, *bp = As + g * 16;
+#pragma unroll
+    for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int off = kb * HX_BOX_DOUBLES + oa[a];
+            double b[N1];
+            const double a0 = a0p[off], a1 = a1p[off];
+#pragma unroll
+            for (int nt = 0; nt < N1; nt++) b[nt] = bp[nt * 128 + off];
+#pragma unroll
+            for (int nt = 0; nt < N1; nt++) {
+                if (nt < N0) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
+                dmma884(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
+            }
+        }
+}
+
+// The same stage on a THIN task (a border tile row with <= 8 right-hand sides: an 8 x 64 row block).  The 64 columns are
+// dealt over the group's four warps — n tiles 2 wg and 2 wg + 1, accumulated in acc[0][0] and acc[0][1] — so the task costs
+// a quarter of a full-height DMMA stream on every sub-partition instead of one warp's worth on sub-partition 0 alone (which
+// shares that sub-partition with two streaming groups: measured 7-10k cycles per K = 64 step for 1/8 of the work of a
+// full step).  After the main loop the row block is gathered in warp 0 through shared memory for the warp-local
+// triangular solve; every element is still accumulated by one warp over k in the same order, so the result is unchanged.
+__device__ __forceinline__ void hx_stage_mma_thin(Acc &acc, const double *As, const double *Bs, int wg, int g, const int (&oa)[4]) {
+    const double *ap = As + g * 16, *bp = Bs + (16 * wg + g) * 16;
+#pragma unroll
+    for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int off = kb * HX_BOX_DOUBLES + oa[a];
+            const double a0 = ap[off], b0 = bp[off], b1 = bp[128 + off];
+            dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+            dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
         }
 }
 
@@ -123,6 +169,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
     __shared__ int4 tq[HX_NG][HT_QD];
     __shared__ int done_cnt[HX_NG][HT_QD];
     __shared__ int helper_done;
+    __shared__ int thin_cnt[HX_NG];
     const BorderedBatch &P = D.P;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const bool st_on = STATS && D.stats != nullptr;
@@ -130,6 +177,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
     const long long st_t0 = STATS ? clock64() : 0;
 #define HT_T0() const long long _t = st_on ? clock64() : 0
 #define HT_ACC(q) do { if (st_on) st[q] += clock64() - _t; } while (0)
+#define HT_TRACE(e) do { if (STATS && D.trace && (int)blockIdx.x == D.trace_cta && (w & 3) == 0 && lane == 0 && n < 64) D.trace[(q * 64 + n) * 8 + (e)] = clock64(); } while (0)
     // 1024-byte aligned base (128B-swizzle atoms)
     // (index arithmetic on the __shared__ array, not integer casts: the compiler must keep seeing shared-space pointers,
     // or every fragment load turns into a generic LD.E)
@@ -165,6 +213,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
     if (tid == 0) {
         for (int qq = 0; qq < HX_NG; qq++) {
             helper_done = 0;
+            thin_cnt[qq] = 0;
             for (int s = 0; s < HT_QD; s++) done_cnt[qq][s] = 0;
             for (int s = 0; s < HX_NST; s++) { mbar_init(&full_bar[qq][s], 1); mbar_init(&empty_bar[qq][s], 4); }
             for (int s = 0; s < HT_QD; s++) { mbar_init(&tq_full[qq][s], 1); mbar_init(&tq_empty[qq][s], 4); }
@@ -198,7 +247,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             { HT_T0(); ok = mbar_wait(&tqe[slot], (((unsigned)(n / HT_QD)) & 1u) ^ 1u, abort_flag); HT_ACC(0); }
             if (!ok) break;
             {
-                const int tix = atomicAdd(D.ctl, 1);
+                const int tix = (q < D.ngroups) ? atomicAdd(D.ctl, 1) : D.ngtasks;
                 if (tix < D.ngtasks) tk = D.gtasks[tix];
                 tqs[slot] = tk;
                 mbar_arrive(&tqf[slot]);
@@ -296,6 +345,8 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             }
         }
         RingState ring = {0, 0u};
+        double *thin_x = smem + HX_NG * HX_NST * HX_STAGE_DOUBLES + q * HX_THINX_DOUBLES;
+        int thin_n = 0;                                      // thin tasks this warp has seen (buffer parity, arrival target)
         for (int n = 0;; n++) {
             const int slot = n % HT_QD;
             bool alive;
@@ -307,6 +358,10 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 if (lane == 0) mbar_arrive(&tqe[slot]);
             }
             if (!alive || tk.x < 0) break;             // no CTA-level barrier anywhere in this role: a warp may leave alone
+            if (n == D.desync_at && q > 0 && D.desync > 0) {
+                const long long t0 = clock64();
+                while (clock64() - t0 < (long long)q * D.desync) __nanosleep(100);
+            }
             const int i = tk.x, k = tk.y, b = tk.z;
             const bool diag = (i == k), thin = (tk.w & 1) != 0, pre = (tk.w & 2) != 0;
             const int nj = pre ? (diag ? k - 2 : k - 1) : k;
@@ -314,6 +369,8 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             double *Ri = (i < P.T) ? Ab + (int64_t)i * GSUM_TILE * P.ld
                                    : P.W + (int64_t)b * P.wstride + (int64_t)(i - P.T) * GSUM_TILE * P.ld;
             double *C = Ri + k * GSUM_TILE;
+            HT_TRACE(0);
+            if (STATS && D.trace && (int)blockIdx.x == D.trace_cta && (w & 3) == 0 && lane == 0 && n < 64) { D.trace[(q * 64 + n) * 8 + 6] = i * 1000 + k; D.trace[(q * 64 + n) * 8 + 7] = b; }
             const bool active = !thin || wg == 0;           // thin task (rows 0..7 in use): warp 0 of the group alone
             // rows of this warp's two m tiles: 16 wg, 16 wg + 8 — or, on a diagonal task, the block rows wg and 7 - wg
             const int row0 = diag ? wg * 8 : wg * 16, row1 = diag ? (7 - wg) * 8 : wg * 16 + 8;
@@ -323,12 +380,24 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             {
                 { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(1); }
                 if (!alive) break;
+                HT_TRACE(1);
                 const double *Cs = ring_base + ring.stage * HX_STAGE_DOUBLES;
+                if (thin) {
+#pragma unroll
+                    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < 8; nt++) { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const double2 v = *reinterpret_cast<const double2 *>(Cs + wg * HX_BOX_DOUBLES + g * 16 + oc[e]);
+                        acc[0][e][0] = -v.x; acc[0][e][1] = -v.y;
+                    }
+                } else
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                     for (int nt = 0; nt < 8; nt++) {
-                        if (nt < (mt ? n1 : n0) && active && (!thin || mt == 0)) {
+                        if (nt < (mt ? n1 : n0)) {
                             const double2 v = *reinterpret_cast<const double2 *>(Cs + (nt >> 1) * HX_BOX_DOUBLES + ((mt ? row1 : row0) + g) * 16 + oc[nt & 1]);
                             acc[mt][nt][0] = -v.x; acc[mt][nt][1] = -v.y;
                         } else { acc[mt][nt][0] = 0.0; acc[mt][nt][1] = 0.0; }
@@ -342,18 +411,62 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(1); }
                 if (!alive) break;
                 const double *As = ring_base + ring.stage * HX_STAGE_DOUBLES;
-                if (thin) { if (active) hx_stage_mma<1, true>(acc, As, As + 2 * HX_BOX_DOUBLES, 0, 0, 8, 8, g, oa); }
-                else if (diag) hx_stage_mma<2, false>(acc, As, As, row0, row1, n0, n1, g, oa);
+                if (thin) hx_stage_mma_thin(acc, As, As + 2 * HX_BOX_DOUBLES, wg, g, oa);
+                else if (diag) {
+                    if (wg == 0) hx_stage_mma_diag<1>(acc, As, g, oa);
+                    else if (wg == 1) hx_stage_mma_diag<2>(acc, As, g, oa);
+                    else if (wg == 2) hx_stage_mma_diag<3>(acc, As, g, oa);
+                    else hx_stage_mma_diag<4>(acc, As, g, oa);
+                }
                 else hx_stage_mma<2, true>(acc, As, As + 2 * HX_BOX_DOUBLES, row0, row1, 8, 8, g, oa);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 hx_ring_advance(ring);
             }
             if (!alive) break;
+            HT_TRACE(2);
 #pragma unroll
             for (int mt = 0; mt < 2; mt++)
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++) { acc[mt][nt][0] = -acc[mt][nt][0]; acc[mt][nt][1] = -acc[mt][nt][1]; }
+            if (thin) {
+                // ---- gather the 8 x 64 row block in warp 0.  Two buffers (task parity): the other warps can run at most one
+                // task ahead of warp 0 — a task takes at least two ring stages and warp 0's arrival frees each of them.
+                double *xb = thin_x + (thin_n & 1) * (HX_THINX_DOUBLES / 2);
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    double2 v; v.x = acc[0][e][0]; v.y = acc[0][e][1];
+                    *reinterpret_cast<double2 *>(xb + g * 64 + (2 * wg + e) * 8 + 2 * t) = v;
+                }
+                thin_n++;
+                __syncwarp();
+                if (wg != 0) {
+                    if (lane == 0) asm volatile("red.release.cta.shared.add.s32 [%0], 1;" ::"r"(smem_u32(&thin_cnt[q])) : "memory");
+                } else {
+                    int ok = 1;
+                    if (lane == 0) {
+                        const int want = 3 * thin_n;
+                        int v, spins = 0;
+                        long long t0 = 0;
+                        for (;;) {
+                            asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(&thin_cnt[q])) : "memory");
+                            if (v >= want) break;
+                            if ((++spins & 255) == 0) {
+                                if (ld_relaxed(abort_flag)) { ok = 0; break; }
+                                if (t0 == 0) t0 = clock64();
+                                else if (clock64() - t0 > DF_WATCHDOG_CYCLES) { atomicExch(abort_flag, 1); ok = 0; break; }
+                            }
+                        }
+                    }
+                    ok = __shfl_sync(0xffffffffu, ok, 0);
+                    if (!ok) break;
+#pragma unroll
+                    for (int nt = 0; nt < 8; nt++) {
+                        const double2 v = *reinterpret_cast<const double2 *>(xb + g * 64 + nt * 8 + 2 * t);
+                        acc[0][nt][0] = v.x; acc[0][nt][1] = v.y;
+                    }
+                }
+            }
             if (diag) {
                 // ---- S back in place; the factor CTAs take it from there ------------------------------------------
 #pragma unroll
@@ -377,6 +490,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 // ---- the triangular solve, warp-local on the 16 x 64 row block ------------------------------------
                 { HT_T0(); alive = mbar_wait(&fullb[ring.stage], ring.phase, abort_flag); HT_ACC(2); }
                 if (!alive) break;
+                HT_TRACE(3);
                 if (active) {
                     HT_T0();
                     const double *Ms = ring_base + ring.stage * HX_STAGE_DOUBLES;
@@ -395,6 +509,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 hx_ring_advance(ring);
             }
+            HT_TRACE(4);
             // ---- publish the tile: the last of the four warps to get here stores the flag (see hetero.cuh) ---------------
             { HT_T0();
             __syncwarp();
@@ -407,10 +522,12 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 }
             }
             HT_ACC(4); }
+            HT_TRACE(5);
             st[5] += 1;
         }
         if (st_on && (tid & 127) == 0) { long long *o = D.stats + (int64_t)blockIdx.x * HT_NSTAT + q * 12; o[5] = clock64() - st_t0; o[6] = st[0]; o[7] = st[1]; o[8] = st[2]; o[9] = st[3]; o[10] = st[4]; o[11] = st[5]; }
     }
 #undef HT_T0
 #undef HT_ACC
+#undef HT_TRACE
 }

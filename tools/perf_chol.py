@@ -52,6 +52,8 @@ for mode in modes:
             tot.append(e0.elapsed_time(e1))
         ms, fl, nb = ctx.profile_read()
         results[mode] = ll.cpu().numpy().copy()
+        import hashlib
+        print("ll sha1", hashlib.sha1(results[mode].tobytes()).hexdigest()[:12], flush=True)
         print(f"{mode:12s} grid ms: min {min(tot):.3f} med {np.median(tot):.3f} | factor bracket {ms / nb:.3f} ms  "
               f"{fl / ms * 1e-9:.2f} TFLOP/s (algorithmic)  launches/step {ctx.launch_count // (reps + 3)}", flush=True)
         ctx.close()
