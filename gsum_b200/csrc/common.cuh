@@ -33,7 +33,7 @@ struct gsum_ctx {
     void *df_flags; size_t df_flags_cap;
     int *df_ctl;                // [0] GEMM task counter, [1] abort flag, [2] sticky abort, [3], [4] factor task counters (device)
     int use_thin;               // GSUM_B200_THIN=0 disables the 8-row border tasks (debug / comparison)
-    void *ht_gtasks, *ht_ftasks; size_t ht_gcap, ht_fcap; int ht_key[7]; int ht_ng, ht_nf;
+    void *ht_gtasks, *ht_ftasks; size_t ht_gcap, ht_fcap; int ht_key[5]; int ht_ng, ht_nf;
     int hx_ready;               // function attributes of the factorisation kernel set
     // pinned staging arena for host-memory callers: small inputs go host -> pinned -> device with a truly asynchronous copy,
     // outputs come back device -> pinned and are handed to the caller after the call's single stream synchronisation
@@ -42,7 +42,6 @@ struct gsum_ctx {
     int npend;
     int ht_factor_ctas;         // GSUM_B200_FACTOR_CTAS (default HT_FACTOR_CTAS)
     int use_smalln, sn_ready;   // small-N one-CTA grid path (smalln.cuh); GSUM_B200_SMALLN=0 disables
-    int ht_waves; double ht_stagger;      // staggered groups of the many-matrices schedule (hetero.cuh: ht_build_tasks)
     int ht_chain_max;           // batches up to this size run in chain mode (chain.cuh); GSUM_B200_CHAIN_MAX, 0 disables
 };
 

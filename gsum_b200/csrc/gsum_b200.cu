@@ -48,9 +48,6 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
     const char *chn = getenv("GSUM_B200_CHAIN_MAX");
     c->ht_chain_max = chn ? atoi(chn) : HT_CHAIN_MAX;
-    const char *wv = getenv("GSUM_B200_WAVES"), *sg = getenv("GSUM_B200_STAGGER");
-    c->ht_waves = wv ? atoi(wv) : HT_WAVES;
-    c->ht_stagger = sg ? atof(sg) : HT_STAGGER;
     const char *sn = getenv("GSUM_B200_SMALLN");
     c->use_smalln = (sn && strcmp(sn, "0") == 0) ? 0 : 1;
     const char *thin = getenv("GSUM_B200_THIN");
@@ -244,12 +241,11 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     const int delay = getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : HT_DIAG_DELAY;
     // few matrices: chain mode (chain.cuh) — one chain worker CTA per matrix owns the diagonal band
     const bool chain = !solve_only && batch <= c->ht_chain_max;
-    const int key[7] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0) | (chain ? 4 : 0), delay, c->ht_waves,
-                        (int)lround(c->ht_stagger * 1e6)};
+    const int key[5] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0) | (chain ? 4 : 0), delay};
     if (memcmp(key, c->ht_key, sizeof(key)) != 0 || !c->ht_gtasks) {
         std::vector<int4> gt, ft;
         if (chain) ht_build_chain_tasks(gt, P.T, P.Trows, batch, thin_last);
-        else ht_build_tasks(gt, ft, P.T, P.Trows, batch, solve_only, thin_last, delay, c->ht_waves, c->ht_stagger);
+        else ht_build_tasks(gt, ft, P.T, P.Trows, batch, solve_only, thin_last, delay);
         GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // the previous lists may still be in use
         GSUM_TRY(ht_upload(c, &c->ht_gtasks, &c->ht_gcap, gt));
         GSUM_TRY(ht_upload(c, &c->ht_ftasks, &c->ht_fcap, ft));
@@ -280,15 +276,12 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     D.P = P; D.gtasks = (const int4 *)c->ht_gtasks; D.ngtasks = c->ht_ng; D.ftasks = (const int4 *)c->ht_ftasks; D.nftasks = c->ht_nf;
     D.nf0 = (!solve_only && !chain && c->ht_nf >= batch) ? batch : 0;          // df_build_tasks emits the column-0 diagonal tiles first
     D.ctl = c->df_ctl; D.flags = (int *)c->df_flags; D.M = (double *)dM; D.stats = nullptr;
-    D.ngroups = getenv("GSUM_B200_NGROUPS") ? atoi(getenv("GSUM_B200_NGROUPS")) : 3;
-    D.desync = getenv("GSUM_B200_DESYNC") ? atoi(getenv("GSUM_B200_DESYNC")) : 0;
-    D.desync_at = getenv("GSUM_B200_DESYNC_AT") ? atoi(getenv("GSUM_B200_DESYNC_AT")) : 1;
     D.chain = chain ? 1 : 0; D.pre = (int *)c->df_flags + (int64_t)batch * P.Trows * P.T;
     // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
     int nf = 0;
-    int nwk = getenv("GSUM_B200_FACTOR_WORKERS") ? atoi(getenv("GSUM_B200_FACTOR_WORKERS")) : 3;
+    int nwk = getenv("GSUM_B200_FACTOR_WORKERS") ? atoi(getenv("GSUM_B200_FACTOR_WORKERS")) : HT_FACTOR_WORKERS;
     if (nwk < 1) nwk = 1;
-    if (nwk > 3) nwk = 3;
+    if (nwk > 4) nwk = 4;
     D.nworkers = nwk;
     if (c->ht_nf > 0) {
         nf = c->ht_factor_ctas;

@@ -36,12 +36,11 @@
 #ifndef HT_FACTOR_CTAS
 #define HT_FACTOR_CTAS 12               // SMs given to the diagonal tiles (GSUM_B200_FACTOR_CTAS overrides)
 #endif
+#ifndef HT_FACTOR_WORKERS
+#define HT_FACTOR_WORKERS 4             // 128-thread workers per factor CTA (measured on C4: 3 -> 1.740 ms, 4 -> 1.723 ms)
+#endif
 #ifndef HT_CHAIN_MAX
 #define HT_CHAIN_MAX 40                 // batches up to this many matrices run in chain mode (chain.cuh)
-#endif
-#ifndef HT_WAVES
-#define HT_WAVES 1                      // staggered groups of matrices in the many-matrices schedule (GSUM_B200_WAVES)
-#define HT_STAGGER 0.0                  // start offset between consecutive groups, fraction of one group's work (GSUM_B200_STAGGER)
 #endif
 #ifndef HT_DIAG_DELAY
 #define HT_DIAG_DELAY 0
@@ -58,12 +57,10 @@ struct HeteroArgs {
     int *flags;             // per (b, i, k): index (b * Trows + i) * T + k.  i > k: 1 = tile final.  i == k: 1 = S ready, 2 = L_kk and M_kk final
     double *M;              // (batch, T, 64, 64): L_kk with its 8x8 diagonal blocks inverted
     int nfactor_ctas;       // CTAs [0, nfactor_ctas) are factor CTAs
-    int nworkers;           // 128-thread workers per factor CTA (1..3)
+    int nworkers;           // 128-thread workers per factor CTA (1..4)
     long long *stats;       // optional per-CTA cycle counters [grid][HT_NSTAT]
     int chain;              // chain mode (chain.cuh): CTA c < nfactor_ctas is the chain worker of matrix c
     long long *trace; int trace_cta;      // STATS build: phase timestamps of one GEMM CTA's groups (tools/group_trace.py)
-    int ngroups;            // experiment: math groups of a GEMM CTA that take tasks (1..3)
-    int desync, desync_at;  // experiment: group q of a GEMM CTA pauses q * desync cycles before its task number desync_at
     int *pre;               // chain mode, per (b, k): 1 = the pre-panel tile (k+1, k) holds S' (everything but the triangular solve)
 };
 
@@ -354,37 +351,13 @@ static inline void ht_build_chain_tasks(std::vector<int4> &gemm, int T, int Trow
 }
 
 // Split the joint topological order into the two claim lists.
-//
-// `waves` > 1: the batch is cut into that many contiguous groups of matrices whose factorisations start `stagger` (a fraction
-// of one group's work) apart: every group keeps the lock-step order of df_build_tasks internally and the groups' lists are
-// merged by virtual time (cumulative tile-steps of the group's own list / its total + the group's offset).  While one group
-// sits in its last tile columns — few, long tasks behind the POTRF -> TRSM -> SYRK chain, where the workers would wait — the
-// next one is in its wide middle columns; the burst of POTRFs per column is a group's, not the whole batch's.  Any merge of
-// per-matrix topological orders is a topological order of the whole batch, so the deadlock argument above is unchanged.
-// The column-0 diagonal tiles (no dependencies) stay at the head of the factor list: phase 0 of ht_factor_worker.
+// (Tried in round 2 and dropped: cutting the batch into groups of matrices that start a fraction of a factorisation apart,
+// lists merged by cumulative work.  Workers claim in list order and block on the claimed task, so a group's tail tasks
+// just park workers: 1 % at best, 5 % slower with four groups a quarter apart; profiles/r02_notes.md.)
 static inline void ht_build_tasks(std::vector<int4> &gemm, std::vector<int4> &fact, int T, int Trows, int batch, bool solve_only,
-                                  bool thin_last, int diag_delay, int waves = 1, double stagger = 0.0) {
+                                  bool thin_last, int diag_delay) {
     std::vector<int4> all;
-    if (solve_only || waves <= 1 || batch < 2 * waves) df_build_tasks(all, T, Trows, batch, solve_only, thin_last, diag_delay);
-    else {
-        struct Item { double v; int4 tk; };
-        std::vector<Item> items;
-        std::vector<int4> part;
-        for (int g = 0; g < waves; g++) {
-            const int b0 = (int)((int64_t)batch * g / waves), b1 = (int)((int64_t)batch * (g + 1) / waves);
-            df_build_tasks(part, T, Trows, b1 - b0, false, thin_last, diag_delay);
-            double total = 0.0;
-            for (const int4 &tk : part) total += tk.y + 1;
-            double cum = 0.0;
-            for (const int4 &tk : part) {
-                items.push_back({g * stagger + cum / total, make_int4(tk.x, tk.y, tk.z + b0, tk.w)});
-                cum += tk.y + 1;
-            }
-        }
-        std::stable_sort(items.begin(), items.end(), [](const Item &a, const Item &b) { return a.v < b.v; });
-        for (const Item &it : items) if (it.tk.x == 0 && it.tk.y == 0) all.push_back(it.tk);
-        for (const Item &it : items) if (!(it.tk.x == 0 && it.tk.y == 0)) all.push_back(it.tk);
-    }
+    df_build_tasks(all, T, Trows, batch, solve_only, thin_last, diag_delay);
     gemm.clear(); fact.clear();
     for (const int4 &tk : all) {
         if (tk.x == tk.y) {

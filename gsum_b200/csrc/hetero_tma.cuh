@@ -44,10 +44,7 @@ __device__ __forceinline__ void hx_ring_advance(RingState &r) {
 
 // One ring stage on a warp's two m tiles (rows row0 + g, row1 + g; 8-aligned) against n tiles 0..7 of the B boxes.
 // oa[a] = 2 (a ^ g ^ 4(t >> 1)) + (t & 1): this lane's offset inside a 128-byte row for k-step a.
-// N0 / N1: n tiles in use for m tile 0 / 1 when !FULL (diagonal task); MT = 1 uses m tile 0 only.
-template <int MT, bool FULL>
-__device__ __forceinline__ void hx_stage_mma(Acc &acc, const double *As, const double *Bs, int row0, int row1, int n0, int n1,
-                                             int g, const int (&oa)[4]) {
+__device__ __forceinline__ void hx_stage_mma(Acc &acc, const double *As, const double *Bs, int row0, int row1, int g, const int (&oa)[4]) {
     const double *a0p = As + (row0 + g) * 16, *a1p = As + (row1 + g) * 16, *bp = Bs + g * 16;
 #pragma unroll
     for (int kb = 0; kb < 2; kb++)
@@ -55,15 +52,13 @@ __device__ __forceinline__ void hx_stage_mma(Acc &acc, const double *As, const d
         for (int a = 0; a < 4; a++) {
             const int off = kb * HX_BOX_DOUBLES + oa[a];
             double b[8];
-            const double a0 = a0p[off];
-            double a1 = 0.0;
-            if (MT == 2) a1 = a1p[off];
+            const double a0 = a0p[off], a1 = a1p[off];
 #pragma unroll
-            for (int nt = 0; nt < 8; nt++) if (FULL || nt < n0 || nt < n1) b[nt] = bp[nt * 128 + off];
+            for (int nt = 0; nt < 8; nt++) b[nt] = bp[nt * 128 + off];
 #pragma unroll
             for (int nt = 0; nt < 8; nt++) {
-                if (FULL || nt < n0) dmma884(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
-                if (MT == 2 && (FULL || nt < n1)) dmma884(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
+                dmma884(acc[0][nt][0], acc[0][nt][1], a0, b[nt]);
+                dmma884(acc[1][nt][0], acc[1][nt][1], a1, b[nt]);
             }
         }
 }
@@ -186,8 +181,11 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
     if ((int)blockIdx.x < D.nfactor_ctas) {
         // ============================ factor CTA ================================================================
         // same register split as in a GEMM CTA: the idle warpgroup hands its registers to the three workers
-        if (w >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); return; }
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HX_MATH_REGS) ";");
+        // (four factor workers: every warpgroup keeps the 128 registers of the launch)
+        if (D.chain || D.nworkers < 4) {
+            if (w >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); return; }
+            asm volatile("setmaxnreg.inc.sync.aligned.u32 " HT_STR(HX_MATH_REGS) ";");
+        }
         if (D.chain) {
             if (tid >= CH_THREADS + 32) return;
             if (tid >= CH_THREADS) { ht_chain_publisher(D, smem, (int)blockIdx.x); return; }
@@ -247,7 +245,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
             { HT_T0(); ok = mbar_wait(&tqe[slot], (((unsigned)(n / HT_QD)) & 1u) ^ 1u, abort_flag); HT_ACC(0); }
             if (!ok) break;
             {
-                const int tix = (q < D.ngroups) ? atomicAdd(D.ctl, 1) : D.ngtasks;
+                const int tix = atomicAdd(D.ctl, 1);
                 if (tix < D.ngtasks) tk = D.gtasks[tix];
                 tqs[slot] = tk;
                 mbar_arrive(&tqf[slot]);
@@ -358,10 +356,6 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                 if (lane == 0) mbar_arrive(&tqe[slot]);
             }
             if (!alive || tk.x < 0) break;             // no CTA-level barrier anywhere in this role: a warp may leave alone
-            if (n == D.desync_at && q > 0 && D.desync > 0) {
-                const long long t0 = clock64();
-                while (clock64() - t0 < (long long)q * D.desync) __nanosleep(100);
-            }
             const int i = tk.x, k = tk.y, b = tk.z;
             const bool diag = (i == k), thin = (tk.w & 1) != 0, pre = (tk.w & 2) != 0;
             const int nj = pre ? (diag ? k - 2 : k - 1) : k;
@@ -418,7 +412,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
                     else if (wg == 2) hx_stage_mma_diag<3>(acc, As, g, oa);
                     else hx_stage_mma_diag<4>(acc, As, g, oa);
                 }
-                else hx_stage_mma<2, true>(acc, As, As + 2 * HX_BOX_DOUBLES, row0, row1, 8, 8, g, oa);
+                else hx_stage_mma(acc, As, As + 2 * HX_BOX_DOUBLES, row0, row1, g, oa);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&emptyb[ring.stage]);
                 hx_ring_advance(ring);
