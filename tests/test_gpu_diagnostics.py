@@ -88,6 +88,19 @@ def test_symmetric_grid_ties_documented(ctx):
     assert relerr(G @ G.T, cov) < 1e-14
     d = np.diag(Lp)
     assert np.all(d[:-1] >= d[1:] * (1 - 1e-9))          # pivoted Cholesky invariant: non-increasing diagonal
+    # Where exactly the order can leave LAPACK's: the device mirrors dpstrf's algorithm (block size 64, the
+    # running diagonal work(i) += a(j,i)^2 inside a block, first maximum wins), but the SUMMATION ORDER inside LAPACK's DGEMV /
+    # DSYRK calls belongs to the BLAS build (SIMD partial sums) and cannot be mirrored.  So: either the pivots are dpstrf's, or at
+    # the first position where they differ the two candidates' Schur-complement diagonals are equal to rounding (a tie of the
+    # symmetric grid, x <-> 1 - x), and the two orders are mirror images of each other from there on.
+    Gr, pr = o.pivoted_cholesky(cov, return_pivots=True)
+    if not np.array_equal(piv, pr):
+        j = int(np.nonzero(piv != pr)[0][0])
+        pos = np.argsort(piv)                                               # original index -> position in the device order
+        schur = lambda c: cov[c, c] - np.sum(Lp[pos[c], :j].astype(np.longdouble) ** 2)
+        da, db = schur(piv[j]), schur(pr[j])
+        assert abs(da - db) <= 1e-9 * abs(da), (j, piv[j], pr[j], da, db)
+        assert piv[j] + pr[j] == n - 1                                      # the mirror point of the same tie
 
 
 def test_draws_with_supplied_z_and_helpers(ctx, golden):
