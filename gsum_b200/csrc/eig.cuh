@@ -27,7 +27,7 @@
 #include "common.cuh"
 
 #define JAC_THREADS 256
-#define JAC_MAX_SWEEPS 40
+#define JAC_MAX_SWEEPS 120
 
 // Round-robin pairing (circle method) of np indices (np even): round r in [0, np-1), slot k in [0, np/2).
 __device__ __forceinline__ void jacobi_pair(int np, int r, int k, int &p, int &q) {

@@ -77,6 +77,7 @@ def lml_grid_sharded(X, dy, ref, orders, ls, Q, group=None, normalize=False, **k
 
 
 _stream_ctx = {}
+_side_streams = {}        # device index -> the stream the sharded grid runs on when torch's current stream is the default one
 _grid_plans = {}
 _USE_GRAPH = os.environ.get("GSUM_B200_GRID_GRAPH", "1") != "0"       # replay the sharded grid's device sequence as one CUDA graph (GSUM_B200_GRID_GRAPH=0 disables)
 _PROF = None            # dev probe (tools/e2e_sharded_breakdown.py): dict of accumulated host seconds per section
@@ -144,6 +145,17 @@ def _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normaliz
     t0 = time.perf_counter()
     dev = torch.device("cuda", torch.cuda.current_device())
     stream = torch.cuda.current_stream(dev)
+    if stream.cuda_stream == 0:
+        # The legacy default stream cannot be handed to the library (gsum_ctx_create takes 0 as "create your own", and that
+        # stream does not synchronise with torch's): the kernels would race the all-gather that torch enqueues on ITS current
+        # stream (seen at world size 2: the first call of a shape gathered a block whose kernels had not finished).  Everything
+        # of the call — staging buffers, kernels, collective, copies — runs on one side stream per device instead.
+        side = _side_streams.get(dev.index)
+        if side is None:
+            side = _side_streams[dev.index] = torch.cuda.Stream(device=dev)
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            return _sharded_device(X, dy, ref, orders, ls, Q, mine, per, world, group, normalize, kw)
     key = (dev.index, stream.cuda_stream)
     ctx = _stream_ctx.get(key)
     if ctx is None:

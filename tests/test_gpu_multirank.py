@@ -27,10 +27,13 @@ def test_shardings_are_bit_identical_to_one_gpu(world):
            "--master-port", str(port), os.path.join(HERE, "nccl_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    out = os.path.join(os.path.dirname(HERE), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    if r.returncode != 0 or not lines:
+        with open(os.path.join(out, f"r02_multirank_{world}gpu_fail.txt"), "w") as f:
+            f.write(r.stdout[-6000:] + "\n---- stderr ----\n" + r.stderr[-12000:])
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-4000:])
     rep = json.loads(lines[-1])
     assert rep["all_ranks_ok"] and rep["world"] == world and "failed" not in rep, rep
-    out = os.path.join(os.path.dirname(HERE), "gpurun_out")
-    os.makedirs(out, exist_ok=True)
     with open(os.path.join(out, f"r02_multirank_{world}gpu.json"), "w") as f:
         json.dump(rep, f, indent=1)
