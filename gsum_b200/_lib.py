@@ -44,6 +44,11 @@ _SIGNATURES = {
                                 _vp, C.c_int64, C.c_int32, _vp, C.c_double, C.c_double, C.c_double, C.c_double,
                                 C.c_double, C.c_double, C.c_double, C.c_int32, _vp, _vp, _vp, C.c_int32]),
     "gsum_grid_normalize": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, C.c_int32]),
+    "gsum_comm_unique_id": (C.c_int, [_vp, _vp]),
+    "gsum_comm_init": (C.c_int, [_vp, C.c_int32, C.c_int32, _vp]),
+    "gsum_comm_destroy": (C.c_int, [_vp]),
+    "gsum_grid_allgather": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int64, _vp, _vp, _vp, C.c_int32]),
+    "gsum_comm_allreduce_counts": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32]),
     "gsum_lml_grad_terms": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double,
                                       C.c_double, _vp, _vp, _vp, _vp, _vp, C.c_int32]),
     "gsum_lml_grad_terms_eig": (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_double, C.c_double,

@@ -6,6 +6,15 @@
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
+#include <nvtx3/nvToolsExt.h>
+
+// NVTX range per C-ABI call and around the factorisation launch: visible in Nsight Systems / ncu --nvtx, free
+// when no tool is attached (NVTX v3 is header-only and resolves its injection library lazily).
+struct GsumRange {
+    explicit GsumRange(const char *name) { nvtxRangePushA(name); }
+    ~GsumRange() { nvtxRangePop(); }
+};
+#define GSUM_RANGE(name) GsumRange gsum_range_guard_(name)
 
 #define GSUM_TILE 64            // tile edge of the blocked FP64 factorisation / solves
 #define GSUM_LDS 68             // padded smem row stride (doubles) for 64-wide tiles: 68 % 16 == 4 -> conflict-free DMMA fragment loads
@@ -43,6 +52,8 @@ struct gsum_ctx {
     int ht_factor_ctas;         // GSUM_B200_FACTOR_CTAS (default HT_FACTOR_CTAS)
     int use_smalln, sn_ready;   // small-N one-CTA grid path (smalln.cuh); GSUM_B200_SMALLN=0 disables
     int ht_chain_max;           // batches up to this size run in chain mode (chain.cuh); GSUM_B200_CHAIN_MAX, 0 disables
+    // collective of the sharded grid (gsum_comm_init): an NCCL communicator owned by this context, NCCL resolved with dlopen
+    void *comm; int comm_nranks, comm_rank;
 };
 
 static inline int gsum_fail(gsum_ctx *c, int code, const char *fmt, ...) {

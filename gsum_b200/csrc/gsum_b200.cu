@@ -60,6 +60,7 @@ extern "C" int gsum_ctx_destroy(gsum_ctx *c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->comm) gsum_comm_destroy(c);
     for (int i = 0; i < GSUM_NWS; i++) if (c->ws[i]) cudaFree(c->ws[i]);
     if (c->ht_gtasks) cudaFree(c->ht_gtasks);
     if (c->ht_ftasks) cudaFree(c->ht_ftasks);
@@ -235,6 +236,7 @@ static int ht_make_map(gsum_ctx *c, CUtensorMap *m, const void *base, uint64_t r
 }
 
 static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve_only) {
+    GSUM_RANGE(solve_only ? "border solve (chol_hetero_tma_kernel)" : "factorisation (chol_hetero_tma_kernel)");
     const int nbt = P.Trows - P.T;
     const bool thin_last = c->use_thin && nbt > 0 && P.border_used > 0 && P.border_used - (nbt - 1) * GSUM_TILE <= 8 &&
                            P.border_used > (nbt - 1) * GSUM_TILE;
@@ -376,6 +378,7 @@ static int solve_run(gsum_ctx *c, const BorderedBatch &P, int batch) {
 extern "C" int gsum_kernel_matrix(gsum_ctx *c, const double *X1, int64_t n1, const double *X2, int64_t n2, int32_t d,
                                   const double *ls, int32_t ls_dim, double constant, double noise, double *out,
                                   int32_t mem_kind) {
+    GSUM_RANGE("gsum_kernel_matrix");
     if (!c || !X1 || !ls || !out || n1 <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d))
         return gsum_fail(c, -1, "gsum_kernel_matrix: bad argument (d must be 1..%d, ls_dim 1 or d)", COV_MAXD);
     GSUM_CUDA(c, cudaSetDevice(c->device));
@@ -473,6 +476,7 @@ static int factor_bordered(gsum_ctx *c, double *dA, int64_t n, int Trows, int64_
 
 extern "C" int gsum_cholesky(gsum_ctx *c, double *A, int64_t n, int64_t batch, int32_t *info, double *logdet,
                              int32_t mem_kind) {
+    GSUM_RANGE("gsum_cholesky");
     if (!c || !A || n <= 0 || batch <= 0) return gsum_fail(c, -1, "gsum_cholesky: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     const int64_t np = gsum_pad64(n);
@@ -518,6 +522,7 @@ extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d,
                              const double *Q, int64_t n_q, int32_t q_x_dependent, const double *detf, double constant,
                              double noise, double nugget, double center0, double disp0, double df0, double scale0,
                              int32_t student, double *ll, double *logdet, int32_t *status, int32_t mem_kind) {
+    GSUM_RANGE("gsum_lml_grid");
     if (!c || !X || !dy || !ref || !orders || !ls || !Q || !ll)
         return gsum_fail(c, -1, "gsum_lml_grid: null argument");
     if (n <= 0 || n_ls <= 0 || n_q <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d) || n_c < 1 || n_c + 1 > LML_MAXR)
@@ -652,6 +657,7 @@ extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d,
 
 
 extern "C" int gsum_grid_normalize(gsum_ctx *c, const double *ll, int64_t count, double *post, double *lse, int32_t mem_kind) {
+    GSUM_RANGE("gsum_grid_normalize");
     if (!c || !ll || count <= 0) return gsum_fail(c, -1, "gsum_grid_normalize: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     const void *dll; void *dpost, *dlse;
@@ -665,6 +671,137 @@ extern "C" int gsum_grid_normalize(gsum_ctx *c, const double *ll, int64_t count,
     LAUNCHED(c, 1);
     GSUM_TRY(dev_out_finish(c, post, dpost, sizeof(double) * count, mem_kind));
     GSUM_TRY(dev_out_finish(c, lse, dlse, sizeof(double), mem_kind));
+    return finish(c, mem_kind);
+}
+
+// ---- the collective of the sharded grid through the C ABI (SURVEY.md 8b lower face; north_star: ONE all-gather + device logsumexp) ----
+// NCCL is resolved at run time (dlopen of the libnccl.so.2 the process already carries, e.g. torch's, else the system one), so the
+// library has no link-time dependency on it and single-GPU hosts never touch it.
+#include <dlfcn.h>
+#include <nccl.h>                   // types and enums only; no symbol of it is linked
+struct GsumNccl {
+    void *lib;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+};
+static GsumNccl *gsum_nccl(gsum_ctx *c) {
+    static GsumNccl N = {};
+    if (N.lib) return &N;
+    const char *names[] = {getenv("GSUM_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *nm : names) if (nm && !h) h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { gsum_fail(c, -110, "gsum_comm: libnccl.so.2 not found (%s); set GSUM_B200_NCCL_LIB", dlerror()); return nullptr; }
+    N.GetUniqueId = (decltype(N.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    N.CommInitRank = (decltype(N.CommInitRank))dlsym(h, "ncclCommInitRank");
+    N.CommDestroy = (decltype(N.CommDestroy))dlsym(h, "ncclCommDestroy");
+    N.AllGather = (decltype(N.AllGather))dlsym(h, "ncclAllGather");
+    N.AllReduce = (decltype(N.AllReduce))dlsym(h, "ncclAllReduce");
+    N.GetErrorString = (decltype(N.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!N.GetUniqueId || !N.CommInitRank || !N.CommDestroy || !N.AllGather || !N.AllReduce || !N.GetErrorString) {
+        gsum_fail(c, -110, "gsum_comm: the NCCL library lacks an expected entry point");
+        return nullptr;
+    }
+    N.lib = h;
+    return &N;
+}
+#define GSUM_NCCL(ctx, N, call)                                                                                      \
+    do {                                                                                                             \
+        ncclResult_t _r = (call);                                                                                    \
+        if (_r != ncclSuccess) return gsum_fail((ctx), -111, "NCCL error at %s:%d (%s)", __FILE__, __LINE__, (N)->GetErrorString(_r)); \
+    } while (0)
+
+extern "C" int gsum_comm_unique_id(gsum_ctx *c, void *id_out) {
+    if (!c || !id_out) return gsum_fail(c, -1, "gsum_comm_unique_id: bad argument");
+    GsumNccl *N = gsum_nccl(c);
+    if (!N) return -110;
+    ncclUniqueId id;
+    GSUM_NCCL(c, N, N->GetUniqueId(&id));
+    memcpy(id_out, &id, sizeof(id));                    // GSUM_COMM_ID_BYTES = 128
+    return 0;
+}
+extern "C" int gsum_comm_init(gsum_ctx *c, int32_t nranks, int32_t rank, const void *nccl_unique_id) {
+    GSUM_RANGE("gsum_comm_init");
+    if (!c || nranks < 1 || rank < 0 || rank >= nranks || !nccl_unique_id) return gsum_fail(c, -1, "gsum_comm_init: bad argument");
+    if (c->comm) return gsum_fail(c, -1, "gsum_comm_init: this context already has a communicator");
+    GsumNccl *N = gsum_nccl(c);
+    if (!N) return -110;
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    ncclUniqueId id;
+    memcpy(&id, nccl_unique_id, sizeof(id));
+    ncclComm_t comm;
+    GSUM_NCCL(c, N, N->CommInitRank(&comm, nranks, id, rank));
+    c->comm = comm; c->comm_nranks = nranks; c->comm_rank = rank;
+    return 0;
+}
+extern "C" int gsum_comm_destroy(gsum_ctx *c) {
+    if (!c) return -1;
+    if (!c->comm) return 0;
+    GsumNccl *N = gsum_nccl(c);
+    if (!N) return -110;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    N->CommDestroy((ncclComm_t)c->comm);
+    c->comm = nullptr; c->comm_nranks = 0; c->comm_rank = 0;
+    return 0;
+}
+// full[q][r + j * P] = recv[r][q][j]: undo the round-robin deal of the length scales (rank r owns l = r, r + P, ...)
+__global__ void grid_unshard_kernel(const double *__restrict__ recv, int64_t n_q, int64_t per, int nranks, int64_t n_ls, double *__restrict__ full) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_q * n_ls) return;
+    const int64_t q = idx / n_ls, l = idx % n_ls;
+    const int64_t r = l % nranks, j = l / nranks;
+    full[idx] = recv[(r * n_q + q) * per + j];
+}
+extern "C" int gsum_grid_allgather(gsum_ctx *c, const double *block, int64_t n_q, int64_t per, int64_t n_ls, double *ll_full, double *post,
+                                   double *lse, int32_t mem_kind) {
+    GSUM_RANGE("gsum_grid_allgather");
+    if (!c || !block || !ll_full || n_q <= 0 || per <= 0 || n_ls <= 0) return gsum_fail(c, -1, "gsum_grid_allgather: bad argument");
+    if (!c->comm) return gsum_fail(c, -1, "gsum_grid_allgather: no communicator (gsum_comm_init)");
+    const int P = c->comm_nranks;
+    if (per != (n_ls + P - 1) / P) return gsum_fail(c, -1, "gsum_grid_allgather: per must be ceil(n_ls / nranks)");
+    GsumNccl *N = gsum_nccl(c);
+    if (!N) return -110;
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const void *dblock; void *drecv, *dfull, *dpost = nullptr, *dlse = nullptr;
+    GSUM_TRY(dev_in(c, WS_IO0, block, sizeof(double) * n_q * per, mem_kind, &dblock));
+    GSUM_TRY(gsum_ws(c, WS_IO1, sizeof(double) * P * n_q * per, &drecv));
+    GSUM_TRY(dev_out(c, WS_IO2, ll_full, sizeof(double) * n_q * n_ls, mem_kind, &dfull));
+    GSUM_NCCL(c, N, N->AllGather(dblock, drecv, (size_t)(n_q * per), ncclDouble, (ncclComm_t)c->comm, c->stream));   // the single collective
+    grid_unshard_kernel<<<(unsigned)((n_q * n_ls + 255) / 256), 256, 0, c->stream>>>((const double *)drecv, n_q, per, P, n_ls, (double *)dfull);
+    LAUNCHED(c, 1);
+    if (post || lse) {
+        const int64_t count = n_q * n_ls;
+        GSUM_TRY(dev_out(c, WS_IO3, post, sizeof(double) * count, mem_kind, &dpost));
+        if (!dpost) GSUM_TRY(gsum_ws(c, WS_IO3, sizeof(double) * count, &dpost));
+        GSUM_TRY(dev_out(c, WS_MISC0, lse, sizeof(double), mem_kind, &dlse));
+        if (!dlse) GSUM_TRY(gsum_ws(c, WS_MISC0, sizeof(double), &dlse));
+        if (count >= 8192)
+            grid_normalize_cluster_kernel<<<GN_CLUSTER, 1024, 0, c->stream>>>((const double *)dfull, count, (double *)dpost, (double *)dlse);
+        else
+            grid_normalize_kernel<<<1, 1024, 0, c->stream>>>((const double *)dfull, count, (double *)dpost, (double *)dlse);
+        LAUNCHED(c, 1);
+        GSUM_TRY(dev_out_finish(c, post, dpost, sizeof(double) * count, mem_kind));
+        GSUM_TRY(dev_out_finish(c, lse, dlse, sizeof(double), mem_kind));
+    }
+    GSUM_TRY(dev_out_finish(c, ll_full, dfull, sizeof(double) * n_q * n_ls, mem_kind));
+    return finish(c, mem_kind);
+}
+// Sum of int64 counts over the ranks (coverage counts of sharded posterior draws, gsum/diagnostics.py:161-171): in place.
+extern "C" int gsum_comm_allreduce_counts(gsum_ctx *c, int64_t *counts, int64_t n, int32_t mem_kind) {
+    GSUM_RANGE("gsum_comm_allreduce_counts");
+    if (!c || !counts || n <= 0) return gsum_fail(c, -1, "gsum_comm_allreduce_counts: bad argument");
+    if (!c->comm) return gsum_fail(c, -1, "gsum_comm_allreduce_counts: no communicator (gsum_comm_init)");
+    GsumNccl *N = gsum_nccl(c);
+    if (!N) return -110;
+    GSUM_CUDA(c, cudaSetDevice(c->device));
+    const void *din;
+    GSUM_TRY(dev_in(c, WS_IO0, counts, sizeof(int64_t) * n, mem_kind, &din));
+    GSUM_NCCL(c, N, N->AllReduce(din, (void *)din, (size_t)n, ncclInt64, ncclSum, (ncclComm_t)c->comm, c->stream));
+    GSUM_TRY(dev_out_finish(c, counts, din, sizeof(int64_t) * n, mem_kind));
     return finish(c, mem_kind);
 }
 
@@ -711,6 +848,7 @@ __global__ void flip_rows_kernel(const double *__restrict__ src, double *__restr
 // ---- K3 -------------------------------------------------------------------------------------------------
 extern "C" int gsum_cho_solve(gsum_ctx *c, const double *L, int64_t n, double *B, int64_t nrhs, int32_t forward_only,
                               int32_t mem_kind) {
+    GSUM_RANGE("gsum_cho_solve");
     if (!c || !L || !B || n <= 0 || nrhs <= 0) return gsum_fail(c, -1, "gsum_cho_solve: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     const int fk = factor_kind(mem_kind);
@@ -826,11 +964,13 @@ static int lml_grad_terms_impl(gsum_ctx *c, const double *X, int64_t n, int32_t 
 extern "C" int gsum_lml_grad_terms(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
                                    const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
                                    double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind) {
+    GSUM_RANGE("gsum_lml_grad_terms");
     return lml_grad_terms_impl(c, X, n, d, RHS, r, ls, ls_dim, constant, noise, nugget, G, H, tr, logdet, info, mem_kind, 0);
 }
 extern "C" int gsum_lml_grad_terms_eig(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *RHS, int32_t r,
                                        const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
                                        double *G, double *H, double *tr, double *logdet, int32_t *info, int32_t mem_kind) {
+    GSUM_RANGE("gsum_lml_grad_terms_eig");
     return lml_grad_terms_impl(c, X, n, d, RHS, r, ls, ls_dim, constant, noise, nugget, G, H, tr, logdet, info, mem_kind, 1);
 }
 
@@ -857,6 +997,7 @@ extern "C" int gsum_fit_create(gsum_ctx *c, const double *X, int64_t n, int32_t 
                                const double *ls, int32_t ls_dim, double constant, double noise, double nugget,
                                double center0, double disp0, double df0, double scale0, int32_t student, double *out7,
                                double *L_out, int32_t mem_kind, gsum_fit **fit) {
+    GSUM_RANGE("gsum_fit_create");
     if (!c || !X || !y || !ls || !fit || n <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d) || n_c < 1 || n_c + 1 > LML_MAXR)
         return gsum_fail(c, -1, "gsum_fit_create: bad argument");
     *fit = nullptr;
@@ -995,6 +1136,7 @@ __global__ void cov_out_kernel(const double *__restrict__ C, int64_t ldc, int64_
 }
 
 extern "C" int gsum_predict(gsum_ctx *c, gsum_fit *f, const gsum_predict_args *a, int32_t mem_kind) {
+    GSUM_RANGE("gsum_predict");
     if (!c || !f || !a || !a->Xnew || a->m <= 0) return gsum_fail(c, -1, "gsum_predict: bad argument");
     if (a->want != GSUM_PREDICT_MEAN && a->want != GSUM_PREDICT_VAR && a->want != GSUM_PREDICT_COV)
         return gsum_fail(c, -1, "gsum_predict: bad `want`");
@@ -1130,6 +1272,7 @@ extern "C" int gsum_process_cov(gsum_ctx *c, int32_t d, const double *ls, int32_
                                 const double *X1, int64_t n1, const double *X2, int64_t n2, const double *sc1, const double *sc2, const double *q1, const double *q2, double gs_start,
                                 double gs_end, const int32_t *excluded, int32_t n_excluded, double factor, double kernel_add,
                                 double *out, int32_t mem_kind) {
+    GSUM_RANGE("gsum_process_cov");
     if (!c || !ls || !X1 || !out || n1 <= 0 || d <= 0 || d > COV_MAXD || (ls_dim != 1 && ls_dim != d))
         return gsum_fail(c, -1, "gsum_process_cov: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
@@ -1182,6 +1325,7 @@ static int pw_args(gsum_ctx *c, PointwiseArgs &P, const double *y, int64_t n, in
 extern "C" int gsum_pointwise_fit(gsum_ctx *c, const double *y, int64_t n, int32_t n_o, const int32_t *orders, const int32_t *mask,
                                   const int32_t *excluded, int32_t n_ex, const double *ratio, const double *ref, double df0,
                                   double scale0, double *coeffs, double *scale, double *trunc_scale, int32_t mem_kind) {
+    GSUM_RANGE("gsum_pointwise_fit");
     if (!c || !y || !orders || !mask || !ratio || !ref || !coeffs || !scale || !trunc_scale || n <= 0 || n_o <= 0 || n_o > PW_MAXO || n_ex < 0 ||
         (n_ex > 0 && !excluded))
         return gsum_fail(c, -1, "gsum_pointwise_fit: bad argument (n_o <= %d)", PW_MAXO);
@@ -1207,6 +1351,7 @@ extern "C" int gsum_pointwise_fit(gsum_ctx *c, const double *y, int64_t n, int32
 extern "C" int gsum_pointwise_loglike(gsum_ctx *c, const double *y, int64_t n, int32_t n_o, const int32_t *orders, const int32_t *mask,
                                       const double *ratios, int64_t n_r, int64_t n_rat, const double *ref, int64_t n_ref, double df0,
                                       double scale0, double *S1, double *S2, int32_t mem_kind) {
+    GSUM_RANGE("gsum_pointwise_loglike");
     if (!c || !y || !orders || !mask || !ratios || !ref || !S1 || !S2 || n <= 0 || n_o <= 0 || n_o > PW_MAXO || n_r <= 0 ||
         (n_rat != 1 && n_rat != n) || (n_ref != 1 && n_ref != n))
         return gsum_fail(c, -1, "gsum_pointwise_loglike: bad argument (ratio / ref must have 1 or n entries)");
@@ -1240,6 +1385,7 @@ extern "C" int gsum_pointwise_loglike(gsum_ctx *c, const double *y, int64_t n, i
 extern "C" int gsum_variogram_bins(gsum_ctx *c, const double *X, int64_t n, int32_t d, const double *z, int32_t ncurves,
                                    const double *bounds, int32_t nbnd, int32_t *bin_grid, double *hij, int32_t *bin_idx, double *dij,
                                    int64_t *counts, double *hsum, double *dsum, int32_t mem_kind) {
+    GSUM_RANGE("gsum_variogram_bins");
     if (!c || !X || !z || !bounds || !bin_grid || !hij || !bin_idx || !dij || !counts || !hsum || !dsum || n < 2 || d <= 0 || ncurves <= 0 || nbnd <= 0)
         return gsum_fail(c, -1, "gsum_variogram_bins: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
@@ -1275,6 +1421,7 @@ extern "C" int gsum_variogram_bins(gsum_ctx *c, const double *X, int64_t n, int3
 extern "C" int gsum_variogram_cov(gsum_ctx *c, const int32_t *i1, const int32_t *j1, int64_t nb1, const int32_t *i2, const int32_t *j2,
                                   int64_t nb2, const int32_t *bin_grid, int64_t n, const double *gamma_tilde, int32_t nbins, int32_t ncurves,
                                   const double *tab, double var_factor, double corr_factor, int32_t same_is_one, double *out, int32_t mem_kind) {
+    GSUM_RANGE("gsum_variogram_cov");
     if (!c || !i1 || !j1 || !i2 || !j2 || !bin_grid || !gamma_tilde || !tab || !out || nb1 <= 0 || nb2 <= 0 || n < 2 || nbins <= 0 ||
         ncurves <= 0 || ncurves > VG_MAXC)
         return gsum_fail(c, -1, "gsum_variogram_cov: bad argument (1 <= ncurves <= %d, non-empty bins)", VG_MAXC);
@@ -1302,6 +1449,7 @@ extern "C" int gsum_variogram_cov(gsum_ctx *c, const int32_t *i1, const int32_t 
 
 extern "C" int gsum_quadratic_forms(gsum_ctx *c, const double *A, int64_t n, const double *mean, const double *Y, int64_t n_curves,
                                     double *q, int32_t mem_kind) {
+    GSUM_RANGE("gsum_quadratic_forms");
     if (!c || !A || !mean || !Y || !q || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_quadratic_forms: bad argument");
     if ((size_t)n * QF_C * sizeof(double) > 200 * 1024) return gsum_fail(c, -1, "gsum_quadratic_forms: n <= %d", 200 * 1024 / (QF_C * 8));
     GSUM_CUDA(c, cudaSetDevice(c->device));
@@ -1327,6 +1475,7 @@ extern "C" int gsum_quadratic_forms(gsum_ctx *c, const double *A, int64_t n, con
 
 extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, const double *mean, const double *Y,
                                     int64_t n_curves, double *E, double *md2, int32_t mem_kind) {
+    GSUM_RANGE("gsum_cholesky_errors");
     if (!c || !L || !Y || n <= 0 || n_curves <= 0 || (!E && !md2)) return gsum_fail(c, -1, "gsum_cholesky_errors: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     const int fk = factor_kind(mem_kind);
@@ -1360,6 +1509,7 @@ extern "C" int gsum_cholesky_errors(gsum_ctx *c, const double *L, int64_t n, con
 
 extern "C" int gsum_pivoted_cholesky(gsum_ctx *c, const double *M, int64_t n, double *Lp, int32_t *piv, int32_t *rank,
                                      double *G_out, int32_t mem_kind) {
+    GSUM_RANGE("gsum_pivoted_cholesky");
     if (!c || !M || n <= 0) return gsum_fail(c, -1, "gsum_pivoted_cholesky: bad argument");
     // the panel kernel is a cooperative launch of one CTA per 128 rows (all co-resident: 64.5 KiB + 4 n bytes of shared memory each)
     const size_t smem = sizeof(double) * PSTRF_NB * PSTRF_ROWS + sizeof(int) * n;
@@ -1433,6 +1583,7 @@ extern "C" int gsum_pivoted_cholesky(gsum_ctx *c, const double *M, int64_t n, do
 
 extern "C" int gsum_pc_errors(gsum_ctx *c, const double *Lp, const int32_t *piv, int64_t n, const double *mean,
                               const double *Y, int64_t n_curves, double *E, int32_t mem_kind) {
+    GSUM_RANGE("gsum_pc_errors");
     if (!c || !Lp || !piv || !Y || !E || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_pc_errors: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     const int fk = factor_kind(mem_kind);
@@ -1490,6 +1641,7 @@ static int coverage_rows(gsum_ctx *c, const double *dYt, int64_t ld, int64_t n_r
 extern "C" int gsum_draws(gsum_ctx *c, const double *L, int64_t n, const double *mean, const double *Z, int64_t n_draws,
                           uint64_t seed, int64_t first_draw, const double *draw_scale, double *draws_out, const double *lower,
                           const double *upper, int32_t n_alpha, double *coverage_out, int64_t *count_out, int32_t mem_kind) {
+    GSUM_RANGE("gsum_draws");
     if (!c || !L || n <= 0 || n_draws <= 0 || first_draw < 0) return gsum_fail(c, -1, "gsum_draws: bad argument");
     if ((coverage_out || count_out) && (!lower || !upper)) return gsum_fail(c, -1, "gsum_draws: coverage needs lower and upper");
     GSUM_CUDA(c, cudaSetDevice(c->device));
@@ -1539,6 +1691,7 @@ extern "C" int gsum_draws(gsum_ctx *c, const double *L, int64_t n, const double 
 
 extern "C" int gsum_credible_interval(gsum_ctx *c, const double *Y, int64_t n, int64_t n_curves, const double *lower,
                                       const double *upper, int32_t n_alpha, double *coverage_out, int32_t mem_kind) {
+    GSUM_RANGE("gsum_credible_interval");
     if (!c || !Y || !lower || !upper || !coverage_out || n <= 0 || n_curves <= 0) return gsum_fail(c, -1, "gsum_credible_interval: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     const int64_t np = gsum_pad64(n), rp = gsum_pad64(n_curves);
@@ -1564,6 +1717,7 @@ static void launch_eig_gemm(gsum_ctx *c, const EigGemmArgs &g) {
 }
 
 extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, double *V, int32_t *sweeps_out, int32_t mem_kind) {
+    GSUM_RANGE("gsum_eigh");
     if (!c || !A || !w || n <= 0 || n > (1 << 20)) return gsum_fail(c, -1, "gsum_eigh: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     mem_kind &= 1;
@@ -1747,6 +1901,7 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
 
 extern "C" int gsum_eig_solve(gsum_ctx *c, const double *w, const double *V, int64_t n, const double *Y, int64_t nrhs,
                               const double *mean, double *X, int32_t mode, int32_t mem_kind) {
+    GSUM_RANGE("gsum_eig_solve");
     if (!c || !w || !V || !Y || !X || n <= 0 || nrhs <= 0 || (mode != 0 && mode != 1)) return gsum_fail(c, -1, "gsum_eig_solve: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
     const int fk = factor_kind(mem_kind);
@@ -1783,6 +1938,7 @@ extern "C" int gsum_eig_solve(gsum_ctx *c, const double *w, const double *V, int
 
 extern "C" int gsum_eig_conditional(gsum_ctx *c, const double *w, const double *V, int64_t n, const double *R_on, int64_t m,
                                     const double *D, int64_t k, double *lin_out, double *var_out, double *cov_out, int32_t mem_kind) {
+    GSUM_RANGE("gsum_eig_conditional");
     if (!c || !w || !V || !R_on || n <= 0 || m <= 0 || (lin_out && (!D || k <= 0)) || (!lin_out && !var_out && !cov_out))
         return gsum_fail(c, -1, "gsum_eig_conditional: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));

@@ -319,3 +319,51 @@ def predict_sharded(process, X, return_std=False, group=None, **predict_kw):
     n_mean = width - 1 if return_std else width
     mean = full[:, 0] if shape1d else np.ascontiguousarray(full[:, :n_mean])
     return (mean, np.ascontiguousarray(full[:, n_mean])) if return_std else mean
+
+
+# ---- the same sharding through the library's OWN communicator (C ABI: gsum_comm_init / gsum_grid_allgather) -------------------
+# For hosts without torch.distributed: libgsum_b200.so resolves NCCL itself (dlopen) and owns the communicator; only the 128-byte
+# id has to travel between the processes, by whatever channel the host has.  Here that channel is a torch process group (any
+# backend) because the test harness has one; an MPI_Bcast or a socket does the same job.
+def cabi_comm_init(ctx=None, group=None):
+    """Create the library's NCCL communicator on `ctx` for the ranks of `group`; returns (nranks, rank)."""
+    import ctypes as C
+    import torch.distributed as dist
+    from ._lib import default_context
+    ctx = ctx or default_context()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    ident = C.create_string_buffer(128)
+    if rank == 0:
+        ctx.check(ctx.lib.gsum_comm_unique_id(ctx.handle, ident), "gsum_comm_unique_id")
+    box = [ident.raw]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = C.create_string_buffer(box[0], 128)
+    ctx.check(ctx.lib.gsum_comm_init(ctx.handle, world, rank, ident), "gsum_comm_init")
+    return world, rank
+
+
+def cabi_comm_destroy(ctx=None):
+    from ._lib import default_context
+    ctx = ctx or default_context()
+    ctx.check(ctx.lib.gsum_comm_destroy(ctx.handle), "gsum_comm_destroy")
+
+
+def lml_grid_sharded_cabi(X, dy, ref, orders, ls, Q, world, rank, normalize=False, ctx=None, **kw):
+    """The sharded grid with host buffers and nothing but C-ABI calls: gsum_lml_grid on this rank's length scales, then
+    gsum_grid_allgather (one ncclAllGather + the un-deal + optionally the normalisation, on the device)."""
+    from ._lib import MEM_HOST, default_context
+    ctx = ctx or default_context()
+    ls = np.asarray(ls, dtype=np.float64).reshape(len(ls), -1)
+    Q = np.asarray(Q, dtype=np.float64)
+    n_ls, n_q = ls.shape[0], Q.shape[0]
+    mine = shard_indices(n_ls, world, rank)
+    per = -(-n_ls // world)
+    block = np.full((n_q, per), -np.inf)
+    if len(mine):
+        block[:, :len(mine)] = ops.lml_grid(X, dy, ref, orders, ls[mine], Q, ctx=ctx, **kw)
+    full = np.empty((n_q, n_ls))
+    post = np.empty((n_q, n_ls)) if normalize else None
+    lse = np.empty(1) if normalize else None
+    p = lambda a: None if a is None else a.ctypes.data
+    ctx.check(ctx.lib.gsum_grid_allgather(ctx.handle, p(block), n_q, per, n_ls, p(full), p(post), p(lse), MEM_HOST), "gsum_grid_allgather")
+    return (full, post, float(lse[0])) if normalize else full

@@ -124,6 +124,26 @@ int gsum_lml_grad_terms(gsum_ctx *ctx, const double *X, int64_t n, int32_t d, co
  * post = exp(ll - max(ll)); lse = log(sum(exp(ll))).  ll, post: (count,); lse: 1 double or NULL. */
 int gsum_grid_normalize(gsum_ctx *ctx, const double *ll, int64_t count, double *post, double *lse, int32_t mem_kind);
 
+/* ---- the collective of the sharded grid (gsum_comm_init / _destroy) --------------------------------------------
+ * One process per GPU, one context per process.  Rank 0 obtains an id (GSUM_COMM_ID_BYTES bytes, an ncclUniqueId) and hands it
+ * to the other ranks by the host's own means (MPI, a socket, torch.distributed); every rank then calls gsum_comm_init.  NCCL is
+ * resolved with dlopen("libnccl.so.2") at the first of these calls (GSUM_B200_NCCL_LIB overrides the name): libgsum_b200.so
+ * does not link against it.  Replaces the Python list comprehension over `ls_vals` of
+ * docs/notebooks/correlated_EFT_publication.ipynb cell 53 when the length scales are dealt over several GPUs.
+ *
+ * gsum_grid_allgather: this rank evaluated gsum_lml_grid on the length scales  rank, rank + nranks, rank + 2 nranks, ...  into
+ * `block` (n_q, per), per = ceil(n_ls / nranks) (columns beyond the rank's share are ignored).  ONE ncclAllGather on the
+ * context's stream, the deal undone on the device into `ll_full` (n_q, n_ls), and — if `post` or `lse` is given — the
+ * normalisation of gsum_grid_normalize on the gathered grid (notebook cell 54), all without leaving the device.
+ * gsum_comm_allreduce_counts: in-place sum over the ranks of int64 counts (coverage counts of sharded posterior draws). */
+#define GSUM_COMM_ID_BYTES 128
+int gsum_comm_unique_id(gsum_ctx *ctx, void *id_out);
+int gsum_comm_init(gsum_ctx *ctx, int32_t nranks, int32_t rank, const void *nccl_unique_id);
+int gsum_comm_destroy(gsum_ctx *ctx);
+int gsum_grid_allgather(gsum_ctx *ctx, const double *block, int64_t n_q, int64_t per, int64_t n_ls, double *ll_full, double *post,
+                        double *lse, int32_t mem_kind);
+int gsum_comm_allreduce_counts(gsum_ctx *ctx, int64_t *counts, int64_t n, int32_t mem_kind);
+
 /* fit with fixed kernel hyperparameters (gsum/models.py:671-738, optimizer=None / 'fixed' bounds):
  * factor R = c*RBF(X) + (noise + nugget) I once, keep X, y, L resident on the device, return the posterior
  * hyperparameters out7 = [center, disp, df, scale, cov_factor, log_marginal_likelihood, logdet R].

@@ -78,6 +78,28 @@ def main():
             # it is dealt into; the forward solve of a row does not depend on its neighbours, so the values are identical
             assert np.array_equal(gm, wm) and np.array_equal(gs, ws), "sharded predict differs from the 1-GPU predict"
         report["predict"] = "mean/std at 1001 points (coeffs_process and TruncationGP kind=both) identical to 1 GPU"
+        # ---- (4) the same grid through the library's own communicator: gsum_comm_init + gsum_grid_allgather, C ABI only
+        n, n_ls, n_q = 300, 2 * world + 3, 9
+        rs = np.random.RandomState(n)
+        X = np.linspace(0, 1, n)[:, None]
+        dy = rs.randn(n, 4)
+        ls_vals, q_vals = np.linspace(0.05, 0.4, n_ls), np.linspace(0.3, 0.7, n_q)
+        from gsum_b200 import ops
+        kw = dict(constant=1.0, noise=1e-6, nugget=1e-10, center0=0.1, disp0=0.5, df0=3.0, scale0=1.2)
+        want = ops.lml_grid(X, dy, 1.0, np.arange(4), ls_vals[:, None], q_vals, **kw)
+        wpost, wlse = ops.grid_normalize(want)
+        w_, r_ = gdist.cabi_comm_init(group=dist.group.WORLD)
+        assert (w_, r_) == (world, rank)
+        for _ in range(2):
+            got, post, lse = gdist.lml_grid_sharded_cabi(X, dy, 1.0, np.arange(4), ls_vals[:, None], q_vals, world, rank, normalize=True, **kw)
+            assert np.array_equal(got, want) and np.array_equal(post, wpost) and lse == wlse, "C-ABI sharded grid differs from the 1-GPU grid"
+        counts = np.arange(5, dtype=np.int64) * (rank + 1)
+        from gsum_b200 import _lib as glib
+        ctx = glib.default_context()
+        ctx.check(ctx.lib.gsum_comm_allreduce_counts(ctx.handle, counts.ctypes.data, 5, 0), "gsum_comm_allreduce_counts")
+        assert np.array_equal(counts, np.arange(5) * (world * (world + 1) // 2))
+        gdist.cabi_comm_destroy()
+        report["cabi"] = "gsum_comm_init + gsum_grid_allgather (+ normalisation) bit-identical to 1 GPU; int64 all-reduce exact"
         ok = 1
     except AssertionError as e:
         report["failed"] = str(e)
