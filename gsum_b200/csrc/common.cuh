@@ -56,6 +56,40 @@ struct gsum_ctx {
     void *comm; int comm_nranks, comm_rank;
 };
 
+// exp(a) for the RBF kernel's argument a = -d^2 / 2 <= 0, straight-line (K1 is bound by instruction issue: the library exp() with its
+// branches was 48 of the 73 instructions per matrix entry; this one is ~25).  n = rint(a / ln 2) by the shift trick, Cody-Waite
+// reduction with FMAs (|r| <= ln 2 / 2), Taylor polynomial of degree 13 by Horner (truncation 4e-18), scaling by 2^n through the
+// exponent field — in two factors so that results below 2^-1022 round once, into the subnormal range or to zero exactly as exp()
+// does.  Maximum error 0.85 ulp (CUDA's exp(): 1 ulp); against numpy's exp on 12 M arguments the product c * exp differs by at
+// most one ulp (tools: tests/test_gpu_kernels.py::test_kernel_matrix keeps its 4e-16 bound).  NaN propagates; a > 0 is not supported.
+__device__ __forceinline__ double rbf_exp_neg(double a) {
+    const double ac = a < -750.0 ? -750.0 : a;                    // exp(-750) = 0 in FP64; keeps n inside the int range (NaN stays NaN)
+    const double t = __fma_rn(ac, 1.4426950408889634, 6755399441055744.0);
+    const int ni = __double2loint(t);
+    const double n = t - 6755399441055744.0;
+    double r = __fma_rn(n, -6.93147180369123816490e-01, ac);
+    r = __fma_rn(n, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = __fma_rn(p, r, 1.0 / 479001600.0);
+    p = __fma_rn(p, r, 1.0 / 39916800.0);
+    p = __fma_rn(p, r, 1.0 / 3628800.0);
+    p = __fma_rn(p, r, 1.0 / 362880.0);
+    p = __fma_rn(p, r, 1.0 / 40320.0);
+    p = __fma_rn(p, r, 1.0 / 5040.0);
+    p = __fma_rn(p, r, 1.0 / 720.0);
+    p = __fma_rn(p, r, 1.0 / 120.0);
+    p = __fma_rn(p, r, 1.0 / 24.0);
+    p = __fma_rn(p, r, 1.0 / 6.0);
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    p = __fma_rn(p, r, 1.0);
+    const int n1 = ni < -1021 ? -1021 : ni;                       // p in [0.70, 1.42): p * 2^n1 is a normal number
+    const double big = __hiloint2double(__double2hiint(p) + (n1 << 20), __double2loint(p));
+    const double rest = __hiloint2double((1023 + (ni - n1)) << 20, 0);      // 2^(ni - n1), 1.0 unless the result is subnormal
+    const double v = big * rest;
+    return a != a ? a : v;
+}
+
 static inline int gsum_fail(gsum_ctx *c, int code, const char *fmt, ...) {
     if (c) {
         c->npend = 0; c->pin_off = 0;           // a failed call delivers nothing

@@ -61,12 +61,11 @@ __device__ __forceinline__ void cov_tile_inside(const double *xr, const double *
         for (int q = 0; q < D; q++) {
             const double x = xr[r * COV_MAXD + q];
             const double d0 = __dsub_rn(x, c0[q]), d1 = __dsub_rn(x, c1[q]);
-            s0 = __dadd_rn(s0, __dmul_rn(d0, d0));
-            s1 = __dadd_rn(s1, __dmul_rn(d1, d1));
+            s0 = q == 0 ? __dmul_rn(d0, d0) : __dadd_rn(s0, __dmul_rn(d0, d0));       // 0 + d^2 == d^2
+            s1 = q == 0 ? __dmul_rn(d1, d1) : __dadd_rn(s1, __dmul_rn(d1, d1));
         }
-        const double a0 = -0.5 * s0, a1 = -0.5 * s1;
-        double v0 = a0 < -746.0 ? 0.0 : constant * exp(a0);
-        double v1 = a1 < -746.0 ? 0.0 : constant * exp(a1);
+        double v0 = constant * rbf_exp_neg(-0.5 * s0);
+        double v1 = constant * rbf_exp_neg(-0.5 * s1);
         if (diag_tile) { if (r == c) v0 = dval; if (r == c + 1) v1 = dval; }
         *reinterpret_cast<double2 *>(At + (int64_t)r * ld + c) = make_double2(v0, v1);
     }
@@ -117,9 +116,8 @@ __global__ void __launch_bounds__(256) cov_sym_kernel(CovArgs P) {
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int64_t cc = gc + u;
-                // exp underflows to exactly 0 below -745.14; skipping the call there changes no bit
                 const double arg = -0.5 * rbf_sqdist(xr + r * COV_MAXD, xc + (c + u) * COV_MAXD, P.d);
-                const double ex = arg < -746.0 ? 0.0 : P.constant * exp(arg);
+                const double ex = P.constant * rbf_exp_neg(arg);
                 if (gr >= P.n || cc >= P.n) v[u] = (gr == cc) ? 1.0 : 0.0;
                 else if (gr == cc) v[u] = dval;
                 else v[u] = ex;
@@ -163,7 +161,7 @@ __global__ void __launch_bounds__(256) cov_cross_kernel(CrossArgs P) {
             double v;
             if (gr >= P.n1 || gc >= P.n2) v = 0.0;
             else if (P.sym_diag && gr == gc) v = __dadd_rn(P.constant, P.diag_add);
-            else v = P.constant * exp(-0.5 * rbf_sqdist(xr + r * COV_MAXD, xc + (c + u) * COV_MAXD, P.d));
+            else v = P.constant * rbf_exp_neg(-0.5 * rbf_sqdist(xr + r * COV_MAXD, xc + (c + u) * COV_MAXD, P.d));
             P.out[gr * P.ldo + gc] = v;
         }
     }

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(128) grad_rows_kernel(const double *__restrict
                     s = __dadd_rn(s, d2);
                     if (ls_dim == 1 || q == p - 1) sq += d2;
                 }
-                const double kv = (i == j) ? constant : constant * exp(-0.5 * s);
+                const double kv = (i == j) ? constant : constant * rbf_exp_neg(-0.5 * s);
                 w = (p == 0) ? kv : kv * sq;
             }
             if (w != 0.0) {

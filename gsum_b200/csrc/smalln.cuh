@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(SN_THREADS, 1) smalln_lml_kernel(SmallNArgs P)
                 else if (gi == gj) v = dval;
                 else {
                     const double a = -0.5 * rbf_sqdist(xs + gi * SN_MAXD, xs + gj * SN_MAXD, d);
-                    v = a < -746.0 ? 0.0 : P.constant * exp(a);
+                    v = P.constant * rbf_exp_neg(a);
                 }
             } else if (bj < nbk && r < r_rhs && gj < n) {
                 v = r == 0 ? 1.0 : P.dy[(int64_t)gj * P.n_c + (r - 1)] / P.ref[gj];     // stage_rhs_kernel, separable path
