@@ -28,7 +28,7 @@ METRIC = "(l,Q) grid log-likelihood evals/sec at N=1024, 6 orders"
 WORKLOAD = "C4: N=1024, 6 orders, 128 l x 256 Q grid (configs[3] of BASELINE.json), length scales sharded over the GPUs"
 # DRAM bytes of ONE factorisation launch at 128 length scales, recorded from an `ncu --set full` capture (not measured in
 # this run): {profile file: dram__bytes_read.sum + dram__bytes_write.sum}
-NCU_TRAFFIC = {"file": "profiles/r02_ncu_hetero_tma.txt", "bytes": 4.301953e9 + 657.248512e6, "n_ls": 128}
+NCU_TRAFFIC = {"file": "profiles/r02_ncu_hetero_tma.txt", "bytes": 4.291450e9 + 660.052736e6, "n_ls": 128}
 
 
 def make_inputs(n_ls):

@@ -42,6 +42,7 @@ struct CovArgs {
     double *A;            // bordered batch base
     int64_t ld, bstride;
     int T;                // tile rows/cols of the factor part (n padded to 64)
+    int tiles_per_cta;    // lower tiles handled by one CTA (cov_tiles_per_cta)
 };
 
 // One 64x64 tile with every row and column inside the matrix.  Thread = two adjacent columns (kept in registers) x eight
@@ -74,9 +75,16 @@ __device__ __forceinline__ void cov_tile_inside(const double *xr, const double *
 // Symmetric build: lower tiles (i >= k) of each matrix in the batch; identity in the padding.
 // One CTA (256 threads) per 64x64 tile; each thread produces 8 adjacent pairs -> 16-byte coalesced stores.
 // Tiles per CTA (measured on C4: 1 -> 0.30 ms with the general loop, 4 -> 0.185 ms, 8 -> 0.195, 34 -> 0.24)
+// With few matrices (a strong-scaled shard) four tiles per CTA leave the launch a single under-filled wave of long CTAs
+// (16 length scales: 27 us); the count adapts so that the grid keeps at least ~2 waves of 8 resident CTAs per SM.
 #ifndef COV_TILES_PER_CTA
 #define COV_TILES_PER_CTA 4
 #endif
+static inline int cov_tiles_per_cta(int64_t tiles_per_matrix, int64_t batch, int sm_count) {
+    int t = COV_TILES_PER_CTA;
+    while (t > 1 && tiles_per_matrix * batch / t < (int64_t)2 * 8 * sm_count) t >>= 1;
+    return t;
+}
 __global__ void __launch_bounds__(256) cov_sym_kernel(CovArgs P) {
     __shared__ double xr[GSUM_TILE * COV_MAXD], xc[GSUM_TILE * COV_MAXD];
     const int64_t b = blockIdx.y;
@@ -85,7 +93,7 @@ __global__ void __launch_bounds__(256) cov_sym_kernel(CovArgs P) {
     double *A = P.A + b * P.bstride;
     const double dval = __dadd_rn(__dadd_rn(P.constant, P.noise), P.nugget);
     const int ntri = P.T * (P.T + 1) / 2;
-    for (int tix = blockIdx.x * COV_TILES_PER_CTA; tix < ntri && tix < (blockIdx.x + 1) * COV_TILES_PER_CTA; tix++) {
+    for (int tix = blockIdx.x * P.tiles_per_cta; tix < ntri && tix < (blockIdx.x + 1) * P.tiles_per_cta; tix++) {
         // decode lower-triangular tile index
         int i = (int)((sqrt(8.0 * tix + 1.0) - 1.0) * 0.5);
         while ((i + 1) * (i + 2) / 2 <= tix) i++;

@@ -612,7 +612,8 @@ extern "C" int gsum_lml_grid(gsum_ctx *c, const double *X, int64_t n, int32_t d,
         CovArgs CA;
         CA.XS = (const double *)dxs; CA.n = n; CA.d = d; CA.constant = constant; CA.noise = noise; CA.nugget = nugget;
         CA.A = (double *)dmat; CA.ld = np; CA.bstride = per_mat; CA.T = T;
-        dim3 gcov((unsigned)((T * (T + 1) / 2 + COV_TILES_PER_CTA - 1) / COV_TILES_PER_CTA), (unsigned)nb);
+        CA.tiles_per_cta = cov_tiles_per_cta(T * (T + 1) / 2, nb, c->sm_count);
+        dim3 gcov((unsigned)((T * (T + 1) / 2 + CA.tiles_per_cta - 1) / CA.tiles_per_cta), (unsigned)nb);
         cov_sym_kernel<<<gcov, 256, 0, c->stream>>>(CA);
         // a last border tile row that runs as thin (8-row) tasks is only ever touched in its first 8 rows
         int64_t fill_rows = rp;
@@ -1024,7 +1025,8 @@ extern "C" int gsum_fit_create(gsum_ctx *c, const double *X, int64_t n, int32_t 
     CovArgs CA;
     CA.XS = f->dXS; CA.n = n; CA.d = d; CA.constant = constant; CA.noise = noise; CA.nugget = nugget;
     CA.A = f->dL; CA.ld = np; CA.bstride = (np + GSUM_TILE) * np; CA.T = T;
-    cov_sym_kernel<<<dim3((unsigned)((T * (T + 1) / 2 + COV_TILES_PER_CTA - 1) / COV_TILES_PER_CTA), 1), 256, 0, c->stream>>>(CA);
+    CA.tiles_per_cta = cov_tiles_per_cta(T * (T + 1) / 2, 1, c->sm_count);
+    cov_sym_kernel<<<dim3((unsigned)((T * (T + 1) / 2 + CA.tiles_per_cta - 1) / CA.tiles_per_cta), 1), 256, 0, c->stream>>>(CA);
     // border rows: basis (ones) then the n_c curves, transposed — same staging as the grid path with ref = 1, Q absent
     void *dones, *dord, *drhs, *dgram, *dll, *dpost;
     GSUM_TRY(gsum_ws(c, WS_REF, sizeof(double) * n, &dones));

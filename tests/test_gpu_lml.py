@@ -275,3 +275,30 @@ def test_c2_full_grid_small_n_path(ctx):
     yd = np.concatenate([dy[:60], dy[:3]])
     lld, logdet, status = ops.lml_grid(Xd, yd, 1.0, orders, [[0.3], [0.1]], [1.0, 0.5], noise=0.0, nugget=0.0, return_status=True)
     assert (status != 0).all() and np.all(np.isneginf(lld)) and np.isnan(logdet).all()
+
+
+def test_strongly_correlated_curves_keep_the_tolerance(ctx):
+    """the cell kernel forms the centred quadratic as tr(G) - n_c ybar^T R^-1 ybar, a difference of Gram entries,
+    where the reference centres the curves first.  Curves that share a common component 100 x their individual part at
+    cond(R) ~ 1e8 make that difference cancel two digits: every cell must still match the reference at rtol 1e-10, or be as close
+    to the extended-precision value as the reference itself is."""
+    rs = np.random.RandomState(21)
+    n = 200
+    X = np.linspace(0, 1, n)[:, None]
+    Lk = np.linalg.cholesky(RBF(0.2)(X) + 1e-6 * np.eye(n))
+    common = Lk @ rs.randn(n)
+    coeffs = 100.0 * common[:, None] + Lk @ rs.randn(n, 5)
+    orders = np.arange(5)
+    y = o.partials(coeffs, 0.5, 1.0, orders)
+    ls_vals, q_vals = np.array([0.05, 0.15, 0.3, 0.5]), np.array([0.35, 0.5, 0.65])
+    kern = RBF(0.2) + WhiteKernel(1e-6, 'fixed')
+    for pri in (dict(center=0, disp=0, df=1, scale=1), dict(center=0.3, disp=2.0, df=4, scale=1.5)):
+        gp = gb.TruncationGP(kern, ratio=0.5, ref=1, optimizer=None, **pri).fit(X, y, orders=orders)
+        ll = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals)
+        want = o.lml_grid(kern, X, y, orders, ls_vals, q_vals, 1.0, o.Priors(pri["center"], pri["disp"], pri["df"], pri["scale"]))
+        rel = np.abs(ll - want) / np.abs(want)
+        for a, b in zip(*np.nonzero(rel >= RTOL)):
+            coeffs_q = o.coefficients(y, q_vals[a], 1.0, orders)
+            exact = lml_extended_precision(X, coeffs_q, [ls_vals[b]], 1e-6, 1e-10, pri["center"], pri["disp"], pri["df"], pri["scale"]) \
+                - n * orders.sum() * np.log(q_vals[a])
+            assert abs(ll[a, b] - exact) <= 3.0 * abs(want[a, b] - exact) + RTOL * abs(exact), (a, b, rel[a, b], ll[a, b], want[a, b], exact)

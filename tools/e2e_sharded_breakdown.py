@@ -16,7 +16,7 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
-X, y, orders, ls_vals, q_vals = make_inputs(128)
+X, y, orders, ls_vals, q_vals = make_inputs(int(os.environ.get("GSUM_PROBE_NLS", "128")))
 gp = gb.TruncationGP(RBF(0.05) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=1, center=0, disp=0, df=1, scale=1, optimizer=None).fit(X, y, orders=orders)
 for i in range(5):
     gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals, group=dist.group.WORLD)
