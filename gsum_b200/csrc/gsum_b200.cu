@@ -43,6 +43,16 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
         c->own_stream = true;
     }
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    {   // caller-held buffers (fit handles, resident factors) come from the device's stream-ordered pool and go back to it without a
+        // device-wide synchronisation; the pool keeps what it has been given (a fit / Diagnostic per call would otherwise pay
+        // 5-10 ms of cudaMalloc + cudaFree around 1 ms of kernels)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     if (cudaMallocHost((void **)&c->pin, (size_t)8 << 20) == cudaSuccess) c->pin_cap = (size_t)8 << 20; else { c->pin = nullptr; cudaGetLastError(); }
     const char *fc = getenv("GSUM_B200_FACTOR_CTAS");
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
@@ -105,15 +115,14 @@ extern "C" int gsum_ctx_profile_read(gsum_ctx *c, double *ms_total, double *flop
 extern "C" int gsum_device_malloc(gsum_ctx *c, size_t bytes, void **out) {
     if (!c || !out || bytes == 0) return gsum_fail(c, -1, "gsum_device_malloc: bad argument");
     GSUM_CUDA(c, cudaSetDevice(c->device));
-    GSUM_CUDA(c, cudaMalloc(out, bytes));
+    GSUM_CUDA(c, cudaMallocAsync(out, bytes, c->stream));
     return 0;
 }
 extern "C" int gsum_device_free(gsum_ctx *c, void *p) {
     if (!c) return -1;
     if (!p) return 0;
     GSUM_CUDA(c, cudaSetDevice(c->device));
-    GSUM_CUDA(c, cudaStreamSynchronize(c->stream));          // work enqueued on the buffer must have drained
-    GSUM_CUDA(c, cudaFree(p));
+    GSUM_CUDA(c, cudaFreeAsync(p, c->stream));               // stream-ordered: work enqueued on the buffer drains first
     return 0;
 }
 // direction: 0 host -> device, 1 device -> host, 2 device -> device; ordered on the context's stream, returns when done
@@ -988,8 +997,12 @@ struct gsum_fit {
 extern "C" int gsum_fit_destroy(gsum_fit *f) {
     if (!f) return 0;
     cudaSetDevice(f->ctx->device);
-    cudaStreamSynchronize(f->ctx->stream);
-    cudaFree(f->dX); cudaFree(f->dXS); cudaFree(f->dy); cudaFree(f->dL); cudaFree(f->dls);
+    cudaStream_t st = f->ctx->stream;
+    if (f->dX) cudaFreeAsync(f->dX, st);
+    if (f->dXS) cudaFreeAsync(f->dXS, st);
+    if (f->dy) cudaFreeAsync(f->dy, st);
+    if (f->dL) cudaFreeAsync(f->dL, st);
+    if (f->dls) cudaFreeAsync(f->dls, st);
     delete f;
     return 0;
 }
@@ -1010,11 +1023,11 @@ extern "C" int gsum_fit_create(gsum_ctx *c, const double *X, int64_t n, int32_t 
     f->ctx = c; f->n = n; f->np = np; f->d = d; f->n_c = n_c; f->T = T; f->ls_dim = ls_dim;
     f->constant = constant; f->noise = noise; f->nugget = nugget;
 #define FIT_CUDA(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { gsum_fit_destroy(f); return gsum_fail(c, -100, "CUDA error %s in gsum_fit_create", cudaGetErrorName(_e)); } } while (0)
-    FIT_CUDA(cudaMalloc(&f->dX, sizeof(double) * n * d));
-    FIT_CUDA(cudaMalloc(&f->dXS, sizeof(double) * n * d));
-    FIT_CUDA(cudaMalloc(&f->dy, sizeof(double) * n * n_c));
-    FIT_CUDA(cudaMalloc(&f->dls, sizeof(double) * ls_dim));
-    FIT_CUDA(cudaMalloc(&f->dL, sizeof(double) * (np + GSUM_TILE) * np));      // factor + one border tile row (basis, y)
+    FIT_CUDA(cudaMallocAsync((void **)&f->dX, sizeof(double) * n * d, c->stream));
+    FIT_CUDA(cudaMallocAsync((void **)&f->dXS, sizeof(double) * n * d, c->stream));
+    FIT_CUDA(cudaMallocAsync((void **)&f->dy, sizeof(double) * n * n_c, c->stream));
+    FIT_CUDA(cudaMallocAsync((void **)&f->dls, sizeof(double) * ls_dim, c->stream));
+    FIT_CUDA(cudaMallocAsync((void **)&f->dL, sizeof(double) * (np + GSUM_TILE) * np, c->stream));      // factor + one border tile row (basis, y)
     const cudaMemcpyKind kin = mem_kind == GSUM_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     FIT_CUDA(cudaMemcpyAsync(f->dX, X, sizeof(double) * n * d, kin, c->stream));
     FIT_CUDA(cudaMemcpyAsync(f->dy, y, sizeof(double) * n * n_c, kin, c->stream));
