@@ -50,6 +50,7 @@ struct gsum_ctx {
     struct { void *dst; const void *src; size_t bytes; } pend[16];
     int npend;
     int ht_factor_ctas;         // GSUM_B200_FACTOR_CTAS (default HT_FACTOR_CTAS)
+    int ht_factor_workers, ht_diag_delay;       // GSUM_B200_FACTOR_WORKERS, GSUM_B200_DIAG_DELAY (read at context creation)
     int use_smalln, sn_ready;   // small-N one-CTA grid path (smalln.cuh); GSUM_B200_SMALLN=0 disables
     int ht_chain_max;           // batches up to this size run in chain mode (chain.cuh); GSUM_B200_CHAIN_MAX, 0 disables
     // collective of the sharded grid (gsum_comm_init): an NCCL communicator owned by this context, NCCL resolved with dlopen

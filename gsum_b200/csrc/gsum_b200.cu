@@ -56,6 +56,10 @@ extern "C" int gsum_ctx_create(int device, void *cuda_stream, gsum_ctx **out) {
     if (cudaMallocHost((void **)&c->pin, (size_t)8 << 20) == cudaSuccess) c->pin_cap = (size_t)8 << 20; else { c->pin = nullptr; cudaGetLastError(); }
     const char *fc = getenv("GSUM_B200_FACTOR_CTAS");
     c->ht_factor_ctas = fc ? atoi(fc) : HT_FACTOR_CTAS;
+    // schedule knobs are read ONCE, here; the per-call path reads no environment (GSUM_B200_DF_STATS, the instrumented build of the
+    // factorisation kernel, is the one exception: a debugging switch tools/perf_chol.py flips between calls)
+    c->ht_diag_delay = getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : HT_DIAG_DELAY;
+    c->ht_factor_workers = getenv("GSUM_B200_FACTOR_WORKERS") ? atoi(getenv("GSUM_B200_FACTOR_WORKERS")) : HT_FACTOR_WORKERS;
     const char *chn = getenv("GSUM_B200_CHAIN_MAX");
     c->ht_chain_max = chn ? atoi(chn) : HT_CHAIN_MAX;
     const char *sn = getenv("GSUM_B200_SMALLN");
@@ -249,7 +253,7 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     const int nbt = P.Trows - P.T;
     const bool thin_last = c->use_thin && nbt > 0 && P.border_used > 0 && P.border_used - (nbt - 1) * GSUM_TILE <= 8 &&
                            P.border_used > (nbt - 1) * GSUM_TILE;
-    const int delay = getenv("GSUM_B200_DIAG_DELAY") ? atoi(getenv("GSUM_B200_DIAG_DELAY")) : HT_DIAG_DELAY;
+    const int delay = c->ht_diag_delay;
     // few matrices: chain mode (chain.cuh) — one chain worker CTA per matrix owns the diagonal band
     const bool chain = !solve_only && batch <= c->ht_chain_max;
     const int key[5] = {P.T, P.Trows, batch, (solve_only ? 1 : 0) | (thin_last ? 2 : 0) | (chain ? 4 : 0), delay};
@@ -290,7 +294,7 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     D.chain = chain ? 1 : 0; D.pre = (int *)c->df_flags + (int64_t)batch * P.Trows * P.T;
     // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
     int nf = 0;
-    int nwk = getenv("GSUM_B200_FACTOR_WORKERS") ? atoi(getenv("GSUM_B200_FACTOR_WORKERS")) : HT_FACTOR_WORKERS;
+    int nwk = c->ht_factor_workers;
     if (nwk < 1) nwk = 1;
     if (nwk > 4) nwk = 4;
     D.nworkers = nwk;
