@@ -1806,7 +1806,10 @@ extern "C" int gsum_eigh(gsum_ctx *c, const double *A, int64_t n, double *w, dou
     }
     // GSUM_B200_EIGH_ORDER=modulus: modulus ordering on positions sorted by decreasing row norm (eig.cuh, jacobi_select);
     // the ranking is refreshed on the host before every sweep (one row-norm kernel, n doubles down, n ints up)
-    const bool modulus = getenv("GSUM_B200_EIGH_ORDER") && !strcmp(getenv("GSUM_B200_EIGH_ORDER"), "modulus");
+    // Default since round 2: the whole GPU suite is green under it and it needs 12-13 instead of 19-20 sweeps at the same residual
+    // (N = 1024 / 2048: 62 / 224 ms against 87 / 384 ms; LAPACK on the host 65 / 284 ms; profiles/r02_eig_probe.txt).
+    // GSUM_B200_EIGH_ORDER=roundrobin selects the tournament order of round 1.
+    const bool modulus = !(getenv("GSUM_B200_EIGH_ORDER") && !strcmp(getenv("GSUM_B200_EIGH_ORDER"), "roundrobin"));
     void *dorder = nullptr;
     std::vector<int32_t> horder(n);
     if (modulus) GSUM_TRY(gsum_ws(c, WS_Q, sizeof(int32_t) * n, &dorder));
