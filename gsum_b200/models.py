@@ -874,6 +874,7 @@ class TruncationProcess:
         Returns ll with shape (n_q, n_ls), i.e. ``ll[i_ratio][i_ls]`` as in the notebook.
         """
         cp = self.coeffs_process
+        on_training_data = X is None and y is None and orders is None
         X, dy, orders_in = self._grid_inputs(X, y, orders)
         n = X.shape[0]
         k = flatten_kernel(cp._active_kernel())
@@ -881,17 +882,25 @@ class TruncationProcess:
         ls = ls.reshape(ls.shape[0], -1)
         if ls.shape[1] not in (1, X.shape[1]):
             raise ValueError("ls_vals must have shape (n_ls,) or (n_ls, n_features)")
-        ref = np.asarray(self.ref(X), dtype=np.float64)
         n_c, so = len(orders_in), float(np.sum(orders_in))
+        # ref(X) and its log-Jacobian term on the training data: evaluated once per fit, like the order differences
+        rc = getattr(self, "_grid_ref_cache", None) if on_training_data else None
+        if rc is not None and rc[0] is X and rc[1] == n_c and rc[4] is self.ref:
+            ref, ref_logsum = rc[2], rc[3]
+        else:
+            ref = np.asarray(self.ref(X), dtype=np.float64)
+            ref_logsum = np.sum(n_c * np.log(np.abs(ref)))
+            if on_training_data:
+                self._grid_ref_cache = (X, n_c, ref, ref_logsum, self.ref)
         if (ratio_vals is None) == (ratio_kws_list is None):
             raise ValueError("give exactly one of ratio_vals and ratio_kws_list")
         if ratio_vals is not None:
             Q = np.asarray(ratio_vals, dtype=np.float64)
-            detf = np.sum(n_c * np.log(np.abs(ref))) + n * so * np.log(np.abs(Q))
+            detf = ref_logsum + n * so * np.log(np.abs(Q))
             xdep = False
         else:
             Q = np.stack([np.asarray(self.ratio(X, **kw), dtype=np.float64) for kw in ratio_kws_list])
-            detf = np.sum(n_c * np.log(np.abs(ref))) + so * np.sum(np.log(np.abs(Q)), axis=1)
+            detf = ref_logsum + so * np.sum(np.log(np.abs(Q)), axis=1)
             xdep = True
         if cp._eig_route():
             detf_q = np.broadcast_to(detf, (Q.shape[0],))
