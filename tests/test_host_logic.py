@@ -331,3 +331,22 @@ def test_jacobi_schedules_cover_every_pair_once_with_disjoint_rounds(n):
         assert len(flat) == len(set(flat))
         seen += pairs
     assert sorted(seen) == sorted(want)
+
+
+def test_factorisation_claim_lists_are_topologically_ordered(tmp_path):
+    """The deadlock-freedom argument of chol_hetero_tma_kernel (csrc/hetero.cuh): workers claim in list order and a task waits only
+    for tasks EARLIER in the joint order.  tests/native/task_order_check.cu rebuilds the host-side lists (many-matrices schedule with
+    and without thin border rows / diagonal delay, and the chain-mode lists with their `pre` tasks) for 270 shapes and checks exactly
+    that, plus: every tile once, column-0 diagonal tiles at the head of the factor list, the split preserves the order."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which(os.environ.get("NVCC", "nvcc"))
+    if nvcc is None:
+        pytest.skip("nvcc not on PATH")
+    here = os.path.dirname(os.path.abspath(__file__))
+    exe = str(tmp_path / "task_order_check")
+    r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O1", "-o", exe,
+                        os.path.join(here, "native", "task_order_check.cu")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "0 violations" in r.stdout, r.stdout[-2000:]
