@@ -724,9 +724,13 @@ class TruncationProcess:
         b_old = b_new = None
         if want_cond_basis:
             b_old, b_new = self.basis(Xc, start=start, end=end)[:, 0], self.basis(X, start=start, end=end)[:, 0]
-        if cp._handle is None:
-            cp._refit()            # 'eig' route: this predict is decomposition-independent in the reference (LU, models.py:1449)
         try:
+            if cp._handle is None:
+                # 'eig' route: this predict is decomposition-independent in the reference (LU, models.py:1449).  The truncation branch
+                # of gsum_predict builds its own factor of K_oo; the Cholesky fit here only provides the handle, and a training
+                # correlation matrix without a Cholesky factor — the case the eig route exists for — goes to the eigen path below
+                # (ADVICE r1), which needs nothing but the posterior the eig-route fit already holds.
+                cp._refit()
             mean, var, cb = cp._handle.predict(
                 X, want=want, Xc=Xc, yc=np.asarray(yc, dtype=np.float64), mean_old=self.mean(Xc, start=start, end=end),
                 mean_new=self.mean(X, start=start, end=end), basis_old=b_old, basis_new=b_new, sc_old=s_old, sc_new=s_new,
