@@ -57,3 +57,21 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("gsum_oracle_free", ""), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/gsum_b200.h compiles as C (gcc -std=c99 -pedantic), a C program links against libgsum_b200.so and runs: without a
+    CUDA device `gsum_ctx_create` refuses (-2), with one the program evaluates a 3 x 3 kernel matrix through the C ABI."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not on PATH")
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), "-o", exe,
+           os.path.join(ROOT, "tests", "native", "abi_smoke.c"), "-L", libdir, "-lgsum_b200", f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "version 100" in r.stdout, (r.stdout, r.stderr)
