@@ -292,7 +292,7 @@ static int hetero_run(gsum_ctx *c, const BorderedBatch &P, int batch, bool solve
     D.nf0 = (!solve_only && !chain && c->ht_nf >= batch) ? batch : 0;          // df_build_tasks emits the column-0 diagonal tiles first
     D.ctl = c->df_ctl; D.flags = (int *)c->df_flags; D.M = (double *)dM; D.stats = nullptr;
     D.chain = chain ? 1 : 0; D.pre = (int *)c->df_flags + (int64_t)batch * P.Trows * P.T;
-    // factor CTAs: three workers each; never more than the diagonal tiles can use, never all of the SMs
+    // factor CTAs: HT_FACTOR_WORKERS (four) workers each; never more than the diagonal tiles can use, never all of the SMs
     int nf = 0;
     int nwk = c->ht_factor_workers;
     if (nwk < 1) nwk = 1;

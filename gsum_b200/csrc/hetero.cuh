@@ -17,7 +17,7 @@
 //                          against extended precision: same error as LAPACK's dtrsm, where a full 64x64 inverse loses a
 //                          digit);
 //                 i == k : S goes back to global memory, flag := 1 (the SYRK half of a diagonal task).
-//   factor CTAs (a few SMs, three independent 128-thread workers each) take the diagonal tiles: wait for S, POTRF in
+//   factor CTAs (a few SMs, four independent 128-thread workers each) take the diagonal tiles: wait for S, POTRF in
 //               shared memory, write L_kk, invert the eight 8x8 diagonal blocks, write M_kk, flag := 2.
 //               Nothing else runs on their SM, so the chain sees the bare 32-cycle DFMA latency.
 //

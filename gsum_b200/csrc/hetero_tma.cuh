@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(HX_THREADS, 1) chol_hetero_tma_kernel(HeteroAr
 
     if ((int)blockIdx.x < D.nfactor_ctas) {
         // ============================ factor CTA ================================================================
-        // same register split as in a GEMM CTA: the idle warpgroup hands its registers to the three workers
+        // fewer than four workers (or chain mode): the idle warpgroup parks at 32 registers, as the producers of a GEMM CTA do
         // (four factor workers: every warpgroup keeps the 128 registers of the launch)
         if (D.chain || D.nworkers < 4) {
             if (w >= 12) { asm volatile("setmaxnreg.dec.sync.aligned.u32 32;"); return; }
