@@ -119,7 +119,9 @@ __global__ void __launch_bounds__(PSTRF_ROWS) pstrf_panel_kernel(const double *_
             double v;
             if (pos == j) v = ajj;
             else {
-                v = Af[(int64_t)pj * ld + p];
+                // the trailing update maintains the LOWER triangle only (half the rank-64 update's flops and bytes): entry (pj, p) of the
+                // symmetric matrix is read where it is kept — coalesced along row pj for the rows above it, one strided element otherwise
+                v = pj >= p ? Af[(int64_t)pj * ld + p] : Af[(int64_t)p * ld + pj];
 #pragma unroll 8
                 for (int m = 0; m < nprev; m++) v = fma(-ptl[m * PSTRF_ROWS + tid], lrow[m], v);
                 v *= inv;

@@ -1567,9 +1567,9 @@ extern "C" int gsum_pivoted_cholesky(gsum_ctx *c, const double *M, int64_t n, do
         GSUM_CUDA(c, cudaLaunchCooperativeKernel((const void *)pstrf_panel_kernel, dim3(ncta), dim3(PSTRF_ROWS), args, smem, c->stream));
         LAUNCHED(c, 1);
         if (k + PSTRF_NB < n) {
-            // dsyrk: Af -= Lb[:, k:k+64] Lb[:, k:k+64]^T on the whole (symmetric, physically indexed) matrix
+            // dsyrk: Af -= Lb[:, k:k+64] Lb[:, k:k+64]^T on the lower triangle of the (symmetric, physically indexed) matrix
             SchurArgs S;
-            S.W = (const double *)dLb + k; S.ld = np; S.bstride = 0; S.T = 1; S.C = (double *)dAf; S.ldc = np; S.cstride = 0; S.lower_only = 0;
+            S.W = (const double *)dLb + k; S.ld = np; S.bstride = 0; S.T = 1; S.C = (double *)dAf; S.ldc = np; S.cstride = 0; S.lower_only = 1;
             GSUM_TRY(schur_run(c, S, T, 1));
         }
     }
