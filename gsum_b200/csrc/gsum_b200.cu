@@ -1559,12 +1559,40 @@ extern "C" int gsum_pivoted_cholesky(gsum_ctx *c, const double *M, int64_t n, do
     GSUM_CUDA(c, cudaMemsetAsync(dLb, 0, sizeof(double) * np * np, c->stream));
     pstrf_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((int32_t *)dpiv, (int32_t *)dpos, (PstrfState *)dst, (int)n);
     LAUNCHED(c, 2);
+    // n <= 4096: the panel as ONE thread-block cluster (DSMEM candidate exchange, hardware cluster barrier per column) when the device
+    // can co-schedule it; otherwise the cooperative-grid kernel
+    int cl = 0;
+    size_t smem_c = 0;
+    if (n <= (int64_t)PSTRF_CMAX * PSTRF_CROWS && !getenv("GSUM_B200_PSTRF_GRID")) {
+        cl = 1;
+        while (cl * PSTRF_CROWS < n) cl <<= 1;
+        smem_c = sizeof(double) * PSTRF_NB * PSTRF_CROWS + sizeof(int) * n;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3(cl); cfg.blockDim = dim3(PSTRF_CROWS); cfg.dynamicSmemBytes = smem_c; cfg.stream = c->stream; cfg.attrs = at; cfg.numAttrs = 1;
+        int nclusters = 0;
+        if (cudaFuncSetAttribute(pstrf_panel_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c) != cudaSuccess ||
+            (cl > 8 && cudaFuncSetAttribute(pstrf_panel_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ||
+            cudaOccupancyMaxActiveClusters(&nclusters, pstrf_panel_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+            cl = 0;
+            cudaGetLastError();
+        }
+    }
     for (int k = 0; k < n; k += PSTRF_NB) {
         const double *aAf = (const double *)dAf; double *aLb = (double *)dLb, *aPt = (double *)dPt;
         int64_t ald = np; int an = (int)n, ak = k;
         int32_t *apiv = (int32_t *)dpiv, *apos = (int32_t *)dpos; PstrfState *ast = (PstrfState *)dst; PstrfSlot *asl = (PstrfSlot *)dslots;
-        void *args[] = {&aAf, &aLb, &aPt, &ald, &an, &ak, &apiv, &apos, &ast, &asl};
-        GSUM_CUDA(c, cudaLaunchCooperativeKernel((const void *)pstrf_panel_kernel, dim3(ncta), dim3(PSTRF_ROWS), args, smem, c->stream));
+        if (cl) {
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.gridDim = dim3(cl); cfg.blockDim = dim3(PSTRF_CROWS); cfg.dynamicSmemBytes = smem_c; cfg.stream = c->stream; cfg.attrs = at; cfg.numAttrs = 1;
+            GSUM_CUDA(c, cudaLaunchKernelEx(&cfg, pstrf_panel_cluster_kernel, aAf, aLb, aPt, ald, an, ak, apiv, apos, ast));
+        } else {
+            void *args[] = {&aAf, &aLb, &aPt, &ald, &an, &ak, &apiv, &apos, &ast, &asl};
+            GSUM_CUDA(c, cudaLaunchCooperativeKernel((const void *)pstrf_panel_kernel, dim3(ncta), dim3(PSTRF_ROWS), args, smem, c->stream));
+        }
         LAUNCHED(c, 1);
         if (k + PSTRF_NB < n) {
             // dsyrk: Af -= Lb[:, k:k+64] Lb[:, k:k+64]^T on the lower triangle of the (symmetric, physically indexed) matrix
