@@ -55,7 +55,9 @@ int64_t gsum_launch_count(const gsum_ctx *ctx);
 /* Caller-held device buffers on the context's GPU — for factors that stay in HBM between calls (GSUM_MEM_DEVICE /
  * GSUM_MEM_FACTOR_DEVICE arguments) when the host side has no device allocator of its own.  gsum_device_copy is ordered
  * on the context's stream and returns when the copy is done; direction 0 = host->device, 1 = device->host, 2 = device->device.
- * gsum_device_free drains the context's stream first. */
+ * The buffers come from the device's stream-ordered pool (cudaMallocAsync on the context's stream; the pool keeps what it is
+ * given): use them with this context only.  gsum_device_free is stream-ordered as well: work already enqueued on the buffer
+ * completes before the memory is reused, and the call does not synchronise. */
 int gsum_device_malloc(gsum_ctx *ctx, size_t bytes, void **out);
 int gsum_device_free(gsum_ctx *ctx, void *ptr);
 int gsum_device_copy(gsum_ctx *ctx, void *dst, const void *src, size_t bytes, int32_t direction);
