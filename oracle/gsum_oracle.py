@@ -702,3 +702,161 @@ def kl_divergence(mean1, cov1, chol1, mean0, cov0):
     k = cov1.shape[-1]
     logs = 2 * np.sum(np.log(np.diag(cov1))) - np.linalg.slogdet(cov0)[-1]
     return 0.5 * (tr + dist - k + logs)
+
+
+# ----------------------------------------------------------------------------------------------
+# TruncationPointwise (gsum/models.py:1573-1836), VariogramFourthRoot (gsum/helpers.py:525-730)
+# Pinned on tests/golden/pointwise_variogram.npz (outputs of the real classes; make_golden_pointwise.py).
+# ----------------------------------------------------------------------------------------------
+def pointwise_fit(y, ratio, ref, orders, df0=1, scale0=1, excluded=None):
+    """gsum/models.py:1643-1683 — coefficients of the unmasked orders, nu = nu0 + n_orders (:1624-1626), tau (:1628-1632), and the
+    Student-t truncation-error distribution per (point, order): loc = y_k, scale = ref sqrt(sum_{n>k} Q^2n) tau (:1676-1680)."""
+    y = np.asarray(y, dtype=float)
+    if y.ndim == 1:
+        y = y[:, None]
+    ratio, ref = np.atleast_1d(ratio, ref)
+    orders = np.arange(y.shape[-1]) if orders is None else np.asarray(orders)
+    if y.shape[-1] != orders.size:
+        raise ValueError('The last dimension of `y` must have the same size as `orders`')
+    mask = ~np.isin(orders, excluded)
+    c = coefficients(y, ratio, ref, orders)[:, mask]
+    df = df0 + c.shape[-1]
+    scale = np.sqrt((df0 * scale0 ** 2 + (c ** 2).sum(-1)) / df)
+    om = orders[mask]
+    ratio_sums = np.array([geometric_sum(ratio ** 2, k + 1, np.inf, excluded=excluded) for k in om]).T
+    trunc_scale = ref[:, None] * np.sqrt(ratio_sums) * scale[:, None]
+    return dict(y=y, ratio=ratio, ref=ref, orders=orders, mask=mask, orders_masked=om, coeffs=c, df=df, scale=scale,
+                trunc_scale=trunc_scale, dist=st.t(loc=y[:, mask], scale=trunc_scale, df=df), df0=df0, scale0=scale0)
+
+
+def _pointwise_idx(f, orders):
+    """gsum/models.py:1640-1644 — positions of `orders` among the unmasked orders (squeezed, as the reference does)."""
+    if orders is None:
+        return slice(None)
+    return np.squeeze([np.nonzero(f["orders_masked"] == o) for o in np.atleast_1d(orders)])
+
+
+def pointwise_interval(f, alpha, orders=None):
+    """gsum/models.py:1685-1707."""
+    alpha = np.array(alpha)
+    if alpha.ndim == 1:
+        alpha = alpha[:, None, None]
+    return np.array(f["dist"].interval(alpha))[..., _pointwise_idx(f, orders)]
+
+
+def pointwise_pdf(f, y, orders=None, log=False):
+    """gsum/models.py:1709-1741 (pdf / logpdf)."""
+    y = np.atleast_1d(y)
+    if y.ndim == 1:
+        y = y[:, None, None]
+    d = f["dist"]
+    return (d.logpdf(y) if log else d.pdf(y))[..., _pointwise_idx(f, orders)]
+
+
+def pointwise_log_likelihood(f, ratio=None, ref=None):
+    """gsum/models.py:1748-1793 as written: the Gamma-function and 2 pi terms enter ONCE (not once per point), the tau terms are summed
+    over the points, and the change-of-variables term is summed over the broadcast shape of `ref` and `ratio`."""
+    ratio = f["ratio"] if ratio is None else ratio
+    ref = f["ref"] if ref is None else ref
+    c = coefficients(f["y"], ratio, ref, f["orders"])[:, f["mask"]]
+    df0, scale0 = f["df0"], f["scale0"]
+    df = df0 + c.shape[-1]
+    scale = np.sqrt((df0 * scale0 ** 2 + (c ** 2).sum(-1)) / df)
+    n = c.shape[-1]
+    ll = loggamma(df / 2.) - 0.5 * n * np.log(2 * np.pi)
+    if df0 > 0:
+        ll += 0.5 * np.sum(df0 * np.log(df0 * scale0 ** 2 / 2.)) - loggamma(df0 / 2.)
+    ll -= 0.5 * np.sum(df * np.log(df * scale ** 2 / 2.))
+    ll -= np.sum(np.log(np.abs(ref)) + np.sum(f["orders"][f["mask"]]) * np.log(ratio))
+    return ll
+
+
+def pointwise_credible_diagnostic(f, data, dobs):
+    """gsum/models.py:1795-1810 — fraction of points inside each central interval, per order."""
+    dobs = np.atleast_1d(dobs)
+    data = np.asarray(data)
+    if data.ndim == 1:
+        data = data[:, None]
+    lower, upper = f["dist"].interval(dobs[:, None, None])
+    return np.average((lower < data) & (data < upper), axis=1)
+
+
+class VariogramOracle:
+    """gsum/helpers.py:525-730 restated with plain arrays instead of record arrays: pairs (i > j) in `np.tril_indices` order,
+    distance bins by `np.digitize`, per-bin means of sqrt|z_i - z_j| (gamma*_hat), the fourth-root transform
+    gamma~ = (gamma*_hat / mean_factor)^4, and the covariance of two bin means from the correlation of sqrt-differences
+    (Cressie & Hawkins: (1 - rho^2) 2F1(3/4, 3/4; 1/2; rho^2) - 1, clipped at |rho| >= 1)."""
+    from scipy.special import gamma as _g
+    mean_factor = np.sqrt(2 / np.pi) * _g(0.75)
+    var_factor = 2. / np.pi * (np.sqrt(np.pi) - _g(0.75) ** 2)
+    corr_factor = _g(0.75) ** 2 / (np.sqrt(np.pi) - _g(0.75) ** 2)
+
+    def __init__(self, X, z, bin_bounds):                                            # :546-611
+        X = np.asarray(X, dtype=float)
+        bin_bounds = np.asarray(bin_bounds, dtype=float)
+        N = len(X)
+        hij = np.linalg.norm(X[:, None, :] - X, axis=-1)
+        self.bin_grid = np.digitize(hij, bin_bounds)
+        z = np.atleast_2d(z)
+        self.Ncurves = z.shape[0]
+        dij = np.sqrt(np.abs(z.T[:, None, :] - z.T[None, :, :]))
+        ti, tj = np.tril_indices(N, -1)
+        self.i, self.j, self.hij, self.dij = ti, tj, hij[ti, tj], dij[ti, tj]
+        self.Nb = Nb = len(bin_bounds) + 1
+        self.gamma_star_hat = np.full((Nb, self.Ncurves), np.nan)
+        loc = np.zeros(Nb)
+        loc[1:-1] = (bin_bounds[1:] + bin_bounds[:-1]) / 2
+        loc[0] = 2 * bin_bounds[0] - loc[1]
+        loc[-1] = 2 * bin_bounds[-1] - loc[-2]
+        self.bin_idx = np.digitize(self.hij, bin_bounds)
+        self.bin_mask = np.arange(Nb)[:, None] == self.bin_idx
+        self.bin_counts = self.bin_mask.sum(-1)
+        for b, m in enumerate(self.bin_mask):
+            if np.any(m):
+                loc[b] = np.average(self.hij[m], axis=0)
+                self.gamma_star_hat[b] = np.average(self.dij[m], axis=0)
+        self.bin_locations = loc
+        self.gamma_tilde = (self.gamma_star_hat / self.mean_factor) ** 4
+        self.gamma_tilde_grid = self.gamma_tilde[self.bin_grid]
+        self.gamma_star_mean = self.mean_factor * self.gamma_star_hat
+
+    def rho_ijkl(self, i, j, k, l):                                                  # :613-623
+        g = self.gamma_tilde_grid
+        return (g[j, k] + g[i, l] - g[i, k] - g[j, l]) / (2 * np.sqrt(g[i, j] * g[k, l]))
+
+    def corr_ijkl(self, i, j, k, l):                                                 # :625-637
+        from scipy.special import hyp2f1
+        rho = self.rho_ijkl(i, j, k, l)
+        corr = ((1 - rho ** 2) * hyp2f1(0.75, 0.75, 0.5, rho ** 2) - 1) * self.corr_factor
+        corr[rho >= 1.] = 1.
+        corr[rho <= -1.] = -1.
+        return corr
+
+    def var_ij(self, i, j):                                                          # :652-654
+        return self.var_factor * np.sqrt(self.gamma_tilde_grid[i, j])
+
+    def cov_ijkl(self, i, j, k, l):                                                  # :639-650
+        i, j, k, l = np.atleast_1d(i, j, k, l)
+        n = i.shape[0], self.Ncurves
+        corr = np.where((i == k) & (j == l), np.ones(n).T, self.corr_ijkl(i, j, k, l).T).T
+        return corr * np.sqrt(self.var_ij(i, j) * self.var_ij(k, l))
+
+    def cov(self, bin1, bin2=None):                                                  # :656-681
+        m1 = self.bin_mask[bin1]
+        m2 = m1 if (bin2 is None or bin2 == bin1) else self.bin_mask[bin2]
+        nb1, nb2 = m1.sum(), m2.sum()
+        if nb1 * nb2 == 0:
+            return 0.
+        a, b = np.nonzero(m1)[0], np.nonzero(m2)[0]
+        A, B = np.repeat(a, len(b)), np.tile(b, len(a))                              # `cartesian` of the two pair lists
+        return np.sum(self.cov_ijkl(self.i[A], self.j[A], self.i[B], self.j[B]), axis=0) / (nb1 * nb2)
+
+    def compute(self, rt_scale=False):                                               # :689-715
+        gam = self.gamma_star_mean if rt_scale else self.gamma_tilde
+        sd = np.zeros((self.Nb, self.Ncurves))
+        for b in range(self.Nb):
+            sd[b] = np.sqrt(self.cov(b))
+        lower, upper = self.gamma_star_mean - sd, self.gamma_star_mean + sd
+        if not rt_scale:
+            lower, upper = (lower / self.mean_factor) ** 4, (upper / self.mean_factor) ** 4
+        return gam, lower, upper

@@ -97,3 +97,41 @@ def test_variogram_hypergeometric_series():
         return out
     ref = (1 - z) * hyp2f1(0.75, 0.75, 0.5, z)
     assert np.max(np.abs(F(z) - ref) / np.abs(ref)) < 1e-13
+
+
+def test_pointwise_and_variogram_against_the_oracle_on_fresh_inputs():
+    """Beyond the fixtures: seeded inputs of another size through the device classes and through the oracle's restatements
+    (oracle/gsum_oracle.py: pointwise_*, VariogramOracle — themselves pinned on the real reference's outputs in tests/test_oracle.py)."""
+    from oracle import gsum_oracle as o
+    rs = np.random.RandomState(101)
+    n, n_o = 300, 8
+    orders = np.arange(n_o)
+    x = np.linspace(0.05, 0.95, n)
+    ratio, ref = 0.25 + 0.5 * x, 1.5 - x
+    y = o.partials(rs.randn(n, n_o) * 0.8, ratio, ref, orders)
+    tp = gb.TruncationPointwise(df=2.5, scale=1.3, excluded=[2]).fit(y, ratio, ref, orders)
+    f = o.pointwise_fit(y, ratio, ref, orders, 2.5, 1.3, [2])
+    close(tp.coeffs_, f["coeffs"])
+    close(tp.scale_, f["scale"])
+    close(tp.dist_.kwds["scale"], f["trunc_scale"])
+    alpha = np.array([0.3, 0.9])
+    close(tp.interval(alpha), o.pointwise_interval(f, alpha))
+    yg = np.linspace(-1.0, 2.0, 5)
+    close(tp.pdf(yg), o.pointwise_pdf(f, yg))
+    close(tp.log_likelihood(), o.pointwise_log_likelihood(f))
+    grid = np.linspace(0.3, 0.7, 9)
+    close(tp.log_likelihood_grid(grid), [o.pointwise_log_likelihood(f, ratio=q) for q in grid])
+    data = y[:, -1] + 0.2 * rs.randn(n)
+    dobs = np.linspace(0.1, 0.9, 7)
+    assert np.array_equal(tp.credible_diagnostic(data, dobs), o.pointwise_credible_diagnostic(f, data, dobs))
+    # variogram: 60 points in 2-D, two curves
+    X = rs.rand(60, 2)
+    z = rs.randn(2, 60)
+    bounds = np.linspace(0.15, 0.95, 7)
+    vg, vo = gb.VariogramFourthRoot(X, z, bounds), o.VariogramOracle(X, z, bounds)
+    assert np.array_equal(vg.bin_counts, vo.bin_counts) and np.array_equal(vg.bin_idx, vo.bin_idx)
+    close(vg.gamma_star_hat, vo.gamma_star_hat)
+    close(vg.gamma_tilde, vo.gamma_tilde)
+    for b in (0, 2, 5):
+        close(np.atleast_1d(vg.cov(b)), np.atleast_1d(vo.cov(b)), rtol=1e-8)
+    close(np.atleast_1d(vg.cov(1, 3)), np.atleast_1d(vo.cov(1, 3)), rtol=1e-8)

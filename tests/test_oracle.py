@@ -287,3 +287,57 @@ def test_eig_route_gradient_oracle(golden, ip):
     res = [o.gaussian_lml_gradient(kern, t, g["X"], g["y"], p, 1e-10, decomposition="eig") for t in g["grad_thetas"]]
     assert relerr(np.array([r[0] for r in res]), g[f"g{ip}_glml"]) < TOL
     assert relerr(np.array([r[1] for r in res]), g[f"g{ip}_grad"]) < 1e-9
+
+
+@pytest.mark.parametrize("case", ["scalar", "xdep", "df0"])
+def test_pointwise_oracle(golden, case):
+    """the oracle's restatement of TruncationPointwise against the real class' outputs."""
+    g = golden("pointwise_variogram")
+    p = "pw_" + case + "_"
+    ratio, ref = g[p + "ratio"], g[p + "ref"]
+    ratio = ratio[0] if ratio.size == 1 else ratio
+    ref = ref[0] if ref.size == 1 else ref
+    df0, scale0 = g[p + "prior"]
+    excluded = g[p + "excluded"].tolist() or None
+    f = o.pointwise_fit(g[p + "y"], ratio, ref, g["pw_orders"], df0, scale0, excluded)
+    tight = dict(rtol=1e-13, atol=0)
+    np.testing.assert_allclose(f["coeffs"], g[p + "coeffs"], **tight)
+    assert f["df"] == float(g[p + "df"])
+    np.testing.assert_allclose(f["scale"], g[p + "scale"], **tight)
+    np.testing.assert_allclose(f["trunc_scale"], g[p + "dist_scale"], **tight)
+    np.testing.assert_allclose(o.pointwise_interval(f, g["pw_alpha"]), g[p + "interval"], rtol=1e-12)
+    np.testing.assert_allclose(o.pointwise_interval(f, g["pw_alpha"], orders=f["orders_masked"][-2:]), g[p + "interval_sel"], rtol=1e-12)
+    np.testing.assert_allclose(o.pointwise_pdf(f, g["pw_ygrid"]), g[p + "pdf"], rtol=1e-12)
+    np.testing.assert_allclose(o.pointwise_pdf(f, g["pw_ygrid"], orders=f["orders_masked"][:1], log=True), g[p + "logpdf"], rtol=1e-12)
+    np.testing.assert_allclose(f["dist"].std(), g[p + "std"], rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(o.pointwise_log_likelihood(f), g[p + "ll"], rtol=1e-13)
+    np.testing.assert_allclose([o.pointwise_log_likelihood(f, ratio=q) for q in g["pw_ratio_grid"]], g[p + "ll_grid"], rtol=1e-13)
+    n = g[p + "y"].shape[0]
+    x = np.linspace(0.1, 1.0, n)
+    ref_full = np.atleast_1d(ref) * np.ones(n)
+    np.testing.assert_allclose([o.pointwise_log_likelihood(f, ratio=q * (0.5 + x), ref=ref_full) for q in g["pw_ratio_grid"]],
+                               g[p + "ll_grid_x"], rtol=1e-13)
+    assert np.array_equal(o.pointwise_credible_diagnostic(f, g[p + "data"], g["pw_dobs"]), g[p + "dci"])
+
+
+@pytest.mark.parametrize("case", ["1d", "2d"])
+def test_variogram_oracle(golden, case):
+    """the oracle's restatement of VariogramFourthRoot against the real class' outputs."""
+    g = golden("pointwise_variogram")
+    p = "vg_" + case + "_"
+    z = g[p + "z"]
+    vg = o.VariogramOracle(g[p + "X"], z if z.shape[0] > 1 else z[0], g[p + "bounds"])
+    assert np.array_equal(vg.bin_counts, g[p + "bin_counts"]) and np.array_equal(vg.bin_idx, g[p + "bin_idx"])
+    tight = dict(rtol=1e-13, atol=0, equal_nan=True)
+    np.testing.assert_allclose(vg.bin_locations, g[p + "bin_locations"], **tight)
+    np.testing.assert_allclose(vg.gamma_star_hat, g[p + "gamma_star_hat"], **tight)
+    np.testing.assert_allclose(vg.gamma_tilde, g[p + "gamma_tilde"], **tight)
+    nc = z.shape[0]
+    np.testing.assert_allclose(np.array([np.atleast_1d(vg.cov(b)) * np.ones(nc) for b in range(vg.Nb)]), g[p + "cov_diag"], rtol=1e-11, equal_nan=True)
+    np.testing.assert_allclose(np.atleast_1d(vg.cov(1, 2)), g[p + "cov_01"], rtol=1e-11)
+    for rt in (False, True):
+        np.testing.assert_allclose(np.stack(vg.compute(rt_scale=rt)), g[p + f"compute_{int(rt)}"], rtol=1e-11, equal_nan=True)
+    i, j, k, l = g[p + "ijkl"].T
+    np.testing.assert_allclose(vg.rho_ijkl(i, j, k, l), g[p + "rho"], **tight)
+    np.testing.assert_allclose(vg.corr_ijkl(i, j, k, l), g[p + "corr"], rtol=1e-12)
+    np.testing.assert_allclose(vg.cov_ijkl(i, j, k, l), g[p + "cov_ijkl"], rtol=1e-12)
