@@ -117,12 +117,18 @@ def test_c3_truncation_predict(ctx, golden, tag, variant):
     Xn = g["Xn"]
     for kind in (("both", "interp", "trunc") if tag == "g" else ("both",)):
         m, s = gp.predict(Xn, order=5, return_std=True, kind=kind)
-        assert relerr(m, g[pre + kind + "_mean"]) < tol and relerr(s, g[pre + kind + "_std"]) < max(tol, 1e-9)
+        assert relerr(m, g[pre + kind + "_mean"]) < tol and relerr(s, g[pre + kind + "_std"]) < max(tol, RTOL)
         m3, cv = gp.predict(Xn[:40], order=3, return_cov=True, kind=kind)
-        assert relerr(m3, g[pre + kind + "_mean3"]) < tol and relerr(cv, g[pre + kind + "_cov3"]) < max(tol, 1e-9)
+        assert relerr(m3, g[pre + kind + "_mean3"]) < tol and relerr(cv, g[pre + kind + "_cov3"]) < max(tol, RTOL)
         assert relerr(gp.predict(Xn, order=5, kind=kind), g[pre + kind + "_mean"]) < tol
     m, s = gp.coeffs_process.predict(Xn, return_std=True)
-    assert relerr(m, g[pre + "cp_mean"]) < RTOL and relerr(s, g[pre + "cp_std"]) < 1e-9
+    assert relerr(m, g[pre + "cp_mean"]) < RTOL
+    if relerr(s, g[pre + "cp_std"]) >= RTOL:        # beyond 1e-10: arbitrated in extended precision, not given a wider bound
+        pk = prior_kwargs(g["prior"])
+        coeffs = o.coefficients(g["y"], gp.ratio(g["X"]), gp.ref(g["X"]), g["orders"])[:, ~np.isin(g["orders"], gp.excluded)]
+        ex = conjugate_extended_precision(g["X"], coeffs, [0.05, 0.07], 1.0, 1e-6, 1e-10, pk["center"], pk["disp"], pk["df"], pk["scale"], Xn,
+                                          student=(tag == "t"))
+        assert as_close_as_reference(s, g[pre + "cp_std"], ex["std"], RTOL)
     assert relerr(gp.cov(Xn[:30], start=2, end=np.inf), g[pre + "cov_sym"]) < 1e-13
     assert relerr(gp.cov(Xn[:30], Xp=g["X"][:25], start=0, end=4), g[pre + "cov_cross"]) < 1e-13
     assert relerr(gp.mean(Xn, start=1, end=4), g[pre + "mean_fn"]) < 1e-13
@@ -141,7 +147,7 @@ def test_c3_constrained_truncation_error(ctx, golden, tag):
     kern = RBF([0.05, 0.07], 'fixed') + WhiteKernel(1e-6, 'fixed')
     gp = cls(kern, optimizer=None, ratio=0.4, ref=1.0, **prior_kwargs(g["prior"])).fit(g["X"], g["y"], orders=g["orders"], dX=g["dX"], dy=g["dy"])
     m, s = gp.predict(g["Xn"], order=4, return_std=True, kind='both')
-    assert relerr(m, g[f"{tag}_constr_mean"]) < 1e-9 and relerr(s, g[f"{tag}_constr_std"]) < 1e-9
+    assert relerr(m, g[f"{tag}_constr_mean"]) < RTOL and relerr(s, g[f"{tag}_constr_std"]) < RTOL
 
 
 def test_fit_with_optimizer_recovers_length_scale(ctx):
@@ -191,7 +197,7 @@ def test_c3_full_size_properties(ctx):
     assert m.shape == (10000, 6) and s.shape == (10000,) and np.isfinite(m).all() and np.isfinite(s).all() and (s >= 0).all()
     f = o.fit_conjugate(kern, X, o.coefficients(y, 0.4, 1.0, orders), o.Priors(0, 0, 1, 1))
     mr, sr = o.predict_conjugate(f, Xt[:256], return_std=True)
-    assert relerr(m[:256], mr) < RTOL and relerr(s[:256], sr) < 1e-9
+    assert relerr(m[:256], mr) < RTOL and relerr(s[:256], sr) < RTOL
     m2, s2 = gp.coeffs_process.predict(Xt[4000:4256], return_std=True)
     assert np.array_equal(m2, m[4000:4256]) and np.array_equal(s2, s[4000:4256])          # pointwise
     mi, si = gp.coeffs_process.predict(X[::7], return_std=True)                              # interpolation (noise 1e-6)
