@@ -171,3 +171,13 @@ def as_close_as_reference(dev, ref, exact, rtol=1e-10, k=4.0):
         return True
     e_dev, e_ref = relerr(dev, exact), relerr(ref, exact)
     return e_dev <= k * e_ref + rtol
+
+
+def ld_forward_solve(L, B):
+    """L^-1 B by forward substitution in extended precision (L lower triangular)."""
+    W = np.array(np.asarray(B, dtype=_ld), dtype=_ld)
+    if W.ndim == 1:
+        W = W[:, None]
+    for i in range(L.shape[0]):
+        W[i] = (W[i] - L[i, :i] @ W[:i]) / L[i, i]
+    return W
