@@ -860,3 +860,80 @@ class VariogramOracle:
         if not rt_scale:
             lower, upper = (lower / self.mean_factor) ** 4, (upper / self.mean_factor) ** 4
         return gam, lower, upper
+
+
+# ----------------------------------------------------------------------------------------------
+# Free helpers either side of the path: correlation functions, Gaussian KL, pdf summaries, data generator
+# (gsum/helpers.py:202-368, gsum/datasets.py:8-72)
+# ----------------------------------------------------------------------------------------------
+
+def gaussian_corr(X, Xp=None, ls=1):
+    """gsum/helpers.py:233-251 — exp(-sqd/2) with sqd from the expanded square |x|^2 + |x'|^2 - 2 x.x', clipped at 0."""
+    X = X * 1.0 / ls
+    Xp = X if Xp is None else Xp                 # NB (helpers.py:244-246): Xp is NOT rescaled by ls when given
+    sqd = -2.0 * np.dot(X, Xp.T) + (np.sum(X ** 2, axis=1)[:, None] + np.sum(Xp ** 2, axis=1)[None, :])
+    return np.exp(-0.5 * np.clip(sqd, 0.0, np.inf))
+
+
+def rbf_corr(X, Xp=None, ls=1):
+    """gsum/helpers.py:254-261 — exp(-|x - x'|^2 / (2 ls^2)); the indicator of coinciding points for ls == 0."""
+    Xp = X if Xp is None else Xp
+    dist = np.linalg.norm(X[:, None, ...] - Xp[None, ...], axis=-1)
+    if ls == 0:
+        return np.where(dist == 0, 1., 0.)
+    return np.exp(-0.5 * dist ** 2 / ls ** 2)
+
+
+def kl_gauss(mu0, cov0, mu1, cov1=None, chol1=None):
+    """gsum/helpers.py:310-368 — KL(N0 || N1); cov1 is factored after adding 1e-5 I (helpers.py:202-203, 357)."""
+    mu0, mu1 = np.atleast_1d(mu0), np.atleast_1d(mu1)
+    cov0 = np.atleast_2d(cov0)
+    if (cov1 is None) == (chol1 is None):
+        raise ValueError('Exactly one of cov1 or chol1 must be given.')
+    if chol1 is None:
+        cov1 = np.atleast_2d(cov1)
+        chol1 = cholesky(cov1 + 1e-5 * np.eye(*cov1.shape))
+    chol1 = np.atleast_2d(chol1)
+    k = cov0.shape[0]
+    logdet0 = np.linalg.slogdet(cov0)[1]
+    logdet1 = 2 * np.sum(np.log(np.diag(chol1)))
+    rq = solve(chol1, mu1 - mu0)
+    return 0.5 * (np.trace(cho_solve((chol1, True), cov0)) + rq @ rq - k + logdet1 - logdet0)
+
+
+def hpd(dist, alpha):
+    """gsum/helpers.py:264-278 — narrowest CDF window of mass alpha (Nelder-Mead from 1 - alpha, ftol 1e-8)."""
+    from scipy.optimize import fmin
+    start = fmin(lambda s: dist.ppf(s + alpha) - dist.ppf(s), 1 - alpha, ftol=1e-8, disp=False)[0]
+    return dist.ppf([start, alpha + start])
+
+
+def hpd_pdf(pdf, alpha, x):
+    """gsum/helpers.py:281-295."""
+    heights = np.unique(pdf)
+    errs = np.array([(np.trapezoid(pdf[pdf >= p], x=x[pdf >= p]) - alpha) ** 2 for p in heights])
+    interval = np.asarray(x)[pdf > heights[np.argmin(errs)]]
+    return np.array([np.min(interval), np.max(interval)])
+
+
+def median_pdf(pdf, x):
+    """gsum/helpers.py:298-307."""
+    i = 0
+    for i in range(len(x)):
+        if np.trapezoid(pdf[:i + 1], x[:i + 1]) > 0.5:
+            break
+    return x[i]
+
+
+def predictions(dist, dob=None):
+    """gsum/helpers.py:206-230."""
+    mean = dist.mean()
+    if dob is None:
+        return mean
+    return mean, np.squeeze(np.asarray(dist.interval(np.atleast_2d(dob).T)).transpose((1, 0, 2)))
+
+
+def gaussian_partial_sums_cov(kernel, X, nugget=0):
+    """gsum/datasets.py:64-66 — the covariance the coefficient curves are drawn from: kernel(X) + nugget I."""
+    K = kernel(X)
+    return K + nugget * np.eye(K.shape[0])

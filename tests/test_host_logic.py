@@ -369,3 +369,115 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "1 BLAS thread" in d["cpu_baseline"]["sample"]
+
+
+# ---- free helpers and data generators either side of the path (gsum/helpers.py:202-368, gsum/datasets.py) ---------------------
+def test_host_only_helpers_match_reference_golden(golden):
+    """`stabilize`, `predictions`, `hpd`, `hpd_pdf`, `median_pdf`, `rbf(ls=0)`: no device work; outputs of the real reference."""
+    import scipy.stats as st
+    import gsum_b200 as gb
+    g = golden("helpers_datasets")
+    assert np.array_equal(gb.stabilize(g["stabilize_in"]), g["stabilize_out"])
+    x, pdf, alphas = g["pdf_x"], g["pdf_vals"], g["pdf_alphas"]
+    assert np.array_equal(np.array([gb.hpd_pdf(pdf, a, x) for a in alphas]), g["hpd_pdf"])
+    assert gb.median_pdf(pdf, x) == float(g["median_pdf"])
+    assert gb.median_pdf(0.01 * np.ones(5), np.arange(5.0)) == 4.0                       # never reaches 1/2: the last grid point
+    assert np.allclose(np.array([gb.hpd(st.norm(0.3, 1.1), a) for a in alphas]), g["hpd_norm"], rtol=0, atol=1e-12)
+    assert np.allclose(np.array([gb.hpd(st.gamma, a, 2.0) for a in alphas]), g["hpd_gamma"], rtol=0, atol=1e-12)
+    assert np.allclose(np.array([gb.hpd(st.t(4.5, loc=-1.0, scale=0.6), a) for a in alphas]), g["hpd_t"], rtol=0, atol=1e-12)
+    dist = st.norm(np.linspace(-1, 1, 7), np.linspace(0.5, 2.0, 7))
+    assert np.array_equal(gb.predictions(dist), g["pred_mean"])
+    m, iv = gb.predictions(dist, dob=[0.68, 0.95])
+    assert np.array_equal(m, g["pred_mean"]) and np.array_equal(iv, g["pred_intervals"])
+    assert np.array_equal(gb.predictions(dist, dob=0.5)[1], g["pred_interval_single"])
+    assert np.array_equal(gb.rbf(g["rbf_ls0_X"], ls=0), g["rbf_ls0"])
+    with pytest.raises(ValueError):
+        gb.kl_gauss(0.0, 1.0, 0.0)                                                        # neither cov1 nor chol1
+    with pytest.raises(ValueError):
+        gb.kl_gauss(0.0, 1.0, 0.0, cov1=1.0, chol1=1.0)
+
+
+def _numpy_pivoted_cholesky(M):
+    """Stand-in for ops.pivoted_cholesky: LAPACK dpstrf itself, (G, Lp, piv, rank, status) with the device call's conventions."""
+    from scipy.linalg.lapack import dpstrf
+    c, p, rank, info = dpstrf(np.array(M, dtype=float), lower=1)
+    Lp, piv = np.tril(c), (p - 1).astype(np.int32)
+    G = np.empty_like(Lp)
+    G[piv] = np.where(np.arange(len(piv))[None, :] < rank, Lp, 0.0)
+    return G, Lp, piv, int(rank), int(info)
+
+
+def _numpy_draws(L, mean, Z=None, **kw):
+    return np.asarray(mean)[:, None] + np.tril(L) @ Z, None
+
+
+def test_partial_sum_generators_host_logic(monkeypatch, golden):
+    """The generators with the three device calls replaced by numpy stand-ins: shapes, the order bookkeeping, the un-pivoting
+    of the factor (the draws must have covariance K, not P^T K P) and the inputs of the `_uniform` / `_on_grid` variants.
+    The device calls themselves: tests/test_gpu_helpers.py."""
+    import gsum_b200 as gb
+    from gsum_b200 import datasets as ds, ops
+    g = golden("helpers_datasets")
+    monkeypatch.setattr(ops, "kernel_matrix", _numpy_kernel_matrix)
+    monkeypatch.setattr(ops, "pivoted_cholesky", _numpy_pivoted_cholesky)
+    monkeypatch.setattr(ops, "draws", _numpy_draws)
+    kern = C(1.5) * RBF(0.25) + WhiteKernel(1e-3)
+    X, K = g["ds_X"], g["ds_K"]
+    n_draw = 4000
+    big = gb.make_gaussian_partial_sums(X, orders=n_draw, kernel=kern, mean=lambda X: 0.5 * np.ones(len(X)), ratio=1.0, ref=1.0,
+                                        nugget=1e-4, random_state=5)
+    coeffs = gb.coefficients(big, 1.0, 1.0)
+    sd = np.sqrt((K ** 2 + np.outer(np.diag(K), np.diag(K))) / (n_draw - 1))
+    assert np.max(np.abs(np.cov(coeffs) - K) / sd) < 5.0                                   # same bound the reference's draws meet
+    assert np.max(np.abs(coeffs.mean(axis=1) - 0.5) / np.sqrt(np.diag(K) / n_draw)) < 5.0
+    ratio_fn, ref_fn = (lambda X: 0.3 + 0.2 * X[:, 0]), (lambda X: 2.0 - X[:, 0])
+    y = gb.make_gaussian_partial_sums(X, orders=g["ds_orders"], kernel=kern, ratio=ratio_fn, ref=ref_fn, nugget=1e-4, random_state=5)
+    assert y.shape == tuple(g["ds_y_shape"])
+    y2 = gb.make_gaussian_partial_sums(X, orders=g["ds_orders"], kernel=kern, ratio=ratio_fn, ref=ref_fn, nugget=1e-4, random_state=5)
+    assert np.array_equal(y, y2)                                                           # seeded: reproducible
+    c = gb.coefficients(y, ratio_fn(X), ref_fn(X), g["ds_orders"])
+    z = np.random.RandomState(5).standard_normal((len(X), 4))
+    G = o.pivoted_cholesky(K)
+    assert relerr(c, G @ z) < 1e-9                                                         # coefficients = G z for the seed's normals
+    Xu, yu = gb.make_gaussian_partial_sums_uniform(n_samples=12, n_features=2, orders=3, random_state=9)
+    assert np.array_equal(Xu, g["ds_uniform_X"]) and yu.shape == tuple(g["ds_uniform_y_shape"])
+    Xg, yg = gb.make_gaussian_partial_sums_on_grid(n_samples=9, n_features=1, orders=4, random_state=9)
+    assert np.array_equal(Xg, g["ds_grid_X"]) and yg.shape == tuple(g["ds_grid_y_shape"])
+    Xg2, yg2 = gb.make_gaussian_partial_sums_on_grid(n_samples=5, n_features=2, orders=2, nugget=1e-6)
+    assert Xg2.shape == (25, 2) and yg2.shape == (25, 2) and np.array_equal(Xg2, gb.cartesian(np.linspace(0, 1, 5), np.linspace(0, 1, 5)))
+    # a singular covariance (two coinciding inputs, no noise): accepted by default, scipy's LinAlgError when not allowed
+    Xs = np.array([[0.0], [0.5], [0.5], [1.0]])
+    ys = gb.make_gaussian_partial_sums(Xs, orders=3, kernel=RBF(0.3))
+    assert ys.shape == (4, 3) and np.allclose(ys[1], ys[2], rtol=0, atol=1e-7)
+    with pytest.raises(np.linalg.LinAlgError):
+        gb.make_gaussian_partial_sums(Xs, orders=3, kernel=RBF(0.3), allow_singular=False)
+    with pytest.raises(NotImplementedError):
+        gb.make_gaussian_partial_sums(X, kernel=Matern(0.3))
+    with pytest.raises(ValueError):
+        ds.make_gaussian_partial_sums(np.linspace(0, 1, 5))                               # X must be 2d
+
+
+def test_device_backed_helpers_host_logic(monkeypatch, golden):
+    """`gaussian` / `rbf` / `kl_gauss` with the device calls replaced by numpy stand-ins, against the real reference's outputs:
+    the argument handling (the un-rescaled Xp of `gaussian`, the broadcast prior mean and the `stabilize`d cov1 of `kl_gauss`)."""
+    import scipy.linalg as sl
+    import gsum_b200 as gb
+    from gsum_b200 import ops
+    g = golden("helpers_datasets")
+    monkeypatch.setattr(ops, "kernel_matrix", _numpy_kernel_matrix)
+    monkeypatch.setattr(ops, "cholesky", lambda A, return_info=False, ctx=None:
+                        (np.linalg.cholesky(A), 0, 2 * np.sum(np.log(np.diag(np.linalg.cholesky(A))))) if return_info else np.linalg.cholesky(A))
+    monkeypatch.setattr(ops, "cho_solve", lambda L, B, forward_only=False, ctx=None: sl.cho_solve((L, True), B))
+
+    def errors(L, mean, Y, want_errors=True, want_md2=False, ctx=None):
+        E = sl.solve_triangular(L, Y - np.broadcast_to(mean, (L.shape[0],))[:, None], lower=True)
+        return (E if want_errors else None), (np.sum(E * E, axis=0) if want_md2 else None)
+    monkeypatch.setattr(ops, "cholesky_errors", errors)
+    for i, ls in enumerate(g["corr_ls"]):
+        for tag, X, Xp in (("1d", g["corr_X1"], None), ("3d", g["corr_X2"], None), ("3d_cross", g["corr_X2"], g["corr_Xp2"])):
+            assert np.allclose(gb.rbf(X, Xp, ls=ls), g[f"rbf_{tag}_{i}"], rtol=1e-10, atol=1e-300)
+            assert np.allclose(gb.gaussian(X, Xp, ls=ls), g[f"gauss_{tag}_{i}"], rtol=1e-10, atol=1e-300)
+    assert gb.kl_gauss(g["kl_mu0"], g["kl_cov0"], g["kl_mu1"], cov1=g["kl_cov1"]) == pytest.approx(float(g["kl_from_cov"]), rel=1e-11)
+    assert gb.kl_gauss(g["kl_mu0"], g["kl_cov0"], g["kl_mu1"], chol1=g["kl_chol1"]) == pytest.approx(float(g["kl_from_chol"]), rel=1e-11)
+    assert gb.kl_gauss(0.2, 1.3, -0.4, cov1=0.9) == pytest.approx(float(g["kl_scalar"]), rel=1e-12)
+    assert gb.kl_gauss(np.zeros(60), g["kl_cov0"], 0.25, chol1=g["kl_chol1"]) == pytest.approx(float(g["kl_scalar_mean1"]), rel=1e-11)

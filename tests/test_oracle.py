@@ -341,3 +341,50 @@ def test_variogram_oracle(golden, case):
     np.testing.assert_allclose(vg.rho_ijkl(i, j, k, l), g[p + "rho"], **tight)
     np.testing.assert_allclose(vg.corr_ijkl(i, j, k, l), g[p + "corr"], rtol=1e-12)
     np.testing.assert_allclose(vg.cov_ijkl(i, j, k, l), g[p + "cov_ijkl"], rtol=1e-12)
+
+
+# ---- free helpers either side of the path (gsum/helpers.py:202-368, gsum/datasets.py:64-66) --------------------------------
+def test_correlation_helpers_oracle(golden):
+    g = golden("helpers_datasets")
+    for i, ls in enumerate(g["corr_ls"]):
+        for tag, X, Xp in (("1d", g["corr_X1"], None), ("3d", g["corr_X2"], None), ("3d_cross", g["corr_X2"], g["corr_Xp2"])):
+            assert np.array_equal(o.rbf_corr(X, Xp, ls=ls), g[f"rbf_{tag}_{i}"])
+            assert np.array_equal(o.gaussian_corr(X, Xp, ls=ls), g[f"gauss_{tag}_{i}"])
+    assert np.array_equal(o.rbf_corr(g["rbf_ls0_X"], ls=0), g["rbf_ls0"])
+
+
+def test_kl_gauss_oracle(golden):
+    g = golden("helpers_datasets")
+    assert o.kl_gauss(g["kl_mu0"], g["kl_cov0"], g["kl_mu1"], cov1=g["kl_cov1"]) == pytest.approx(float(g["kl_from_cov"]), rel=1e-13)
+    assert o.kl_gauss(g["kl_mu0"], g["kl_cov0"], g["kl_mu1"], chol1=g["kl_chol1"]) == pytest.approx(float(g["kl_from_chol"]), rel=1e-13)
+    assert o.kl_gauss(0.2, 1.3, -0.4, cov1=0.9) == pytest.approx(float(g["kl_scalar"]), rel=1e-13)
+    assert o.kl_gauss(np.zeros(60), g["kl_cov0"], 0.25, chol1=g["kl_chol1"]) == pytest.approx(float(g["kl_scalar_mean1"]), rel=1e-13)
+    with pytest.raises(ValueError):
+        o.kl_gauss(0.0, 1.0, 0.0)
+
+
+def test_pdf_summaries_oracle(golden):
+    import scipy.stats as st
+    g = golden("helpers_datasets")
+    x, pdf, alphas = g["pdf_x"], g["pdf_vals"], g["pdf_alphas"]
+    assert np.array_equal(np.array([o.hpd_pdf(pdf, a, x) for a in alphas]), g["hpd_pdf"])
+    assert o.median_pdf(pdf, x) == float(g["median_pdf"])
+    assert np.allclose(np.array([o.hpd(st.norm(0.3, 1.1), a) for a in alphas]), g["hpd_norm"], rtol=0, atol=1e-12)
+    assert np.allclose(np.array([o.hpd(st.t(4.5, loc=-1.0, scale=0.6), a) for a in alphas]), g["hpd_t"], rtol=0, atol=1e-12)
+    dist = st.norm(np.linspace(-1, 1, 7), np.linspace(0.5, 2.0, 7))
+    m, iv = o.predictions(dist, dob=[0.68, 0.95])
+    assert np.array_equal(m, g["pred_mean"]) and np.array_equal(iv, g["pred_intervals"])
+    assert np.array_equal(o.predictions(dist, dob=0.5)[1], g["pred_interval_single"])
+
+
+def test_partial_sums_covariance_oracle(golden):
+    """The covariance `make_gaussian_partial_sums` draws from (gsum/datasets.py:64-66), and the reference's own 4000 draws
+    against it: the sample covariance sits where a Wishart sample of that size must (the same bound the device draws meet)."""
+    from sklearn.gaussian_process.kernels import RBF, ConstantKernel, WhiteKernel
+    g = golden("helpers_datasets")
+    K = o.gaussian_partial_sums_cov(ConstantKernel(1.5) * RBF(0.25) + WhiteKernel(1e-3), g["ds_X"], nugget=1e-4)
+    assert np.array_equal(K, g["ds_K"])
+    n_draw = 4000
+    sd = np.sqrt((K ** 2 + np.outer(np.diag(K), np.diag(K))) / (n_draw - 1))       # std of a sample-covariance entry
+    assert np.max(np.abs(g["ds_ref_sample_cov"] - K) / sd) < 5.0
+    assert np.max(np.abs(g["ds_ref_sample_mean"] - 0.5) / np.sqrt(np.diag(K) / n_draw)) < 5.0
