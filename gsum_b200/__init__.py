@@ -7,9 +7,10 @@ Drop-in for the reference's hot path: same class and function names (``Conjugate
 ``include/gsum_b200.h`` (``libgsum_b200.so``).  No CPU fallback: importing is cheap, the first numerical
 call raises if the library is not built or no GPU is visible.
 """
-from .helpers import (cartesian, cholesky_errors, coefficients, gaussian, geometric_sum, hpd, hpd_pdf, kl_gauss, mahalanobis,
-                      median_pdf, partials, pivoted_cholesky, predictions, rbf, stabilize)
-from .datasets import (make_gaussian_partial_sums, make_gaussian_partial_sums_on_grid, make_gaussian_partial_sums_uniform)
+from .helpers import (cartesian, cholesky_errors, coefficients, default_attributes, gaussian, geometric_sum, hpd, hpd_pdf,
+                      kl_gauss, lazy_property, mahalanobis, median_pdf, partials, pivoted_cholesky, predictions, rbf, stabilize)
+from .datasets import (generate_coefficients, make_gaussian_partial_sums, make_gaussian_partial_sums_on_grid,
+                       make_gaussian_partial_sums_uniform, toy_data)
 from .models import (BaseConjugateProcess, ConjugateGaussianProcess, ConjugateStudentProcess, TruncationGP,
                      TruncationProcess, TruncationTP)
 from .diagnostics import Diagnostic
@@ -22,4 +23,5 @@ __all__ = [
     "BaseConjugateProcess", "Diagnostic", "TruncationPointwise", "VariogramFourthRoot", "cartesian", "coefficients", "partials", "geometric_sum",
     "pivoted_cholesky", "cholesky_errors", "mahalanobis", "stabilize", "rbf", "gaussian", "kl_gauss", "predictions", "hpd", "hpd_pdf",
     "median_pdf", "make_gaussian_partial_sums", "make_gaussian_partial_sums_uniform", "make_gaussian_partial_sums_on_grid",
+    "toy_data", "generate_coefficients", "lazy_property", "default_attributes",
 ]

@@ -17,10 +17,11 @@ from sklearn.gaussian_process.kernels import RBF
 from sklearn.utils import check_random_state
 
 from . import ops
-from .helpers import cartesian, partials
+from .helpers import cartesian, gaussian, partials
 from .kernels import flatten_kernel
 
-__all__ = ["make_gaussian_partial_sums", "make_gaussian_partial_sums_uniform", "make_gaussian_partial_sums_on_grid"]
+__all__ = ["make_gaussian_partial_sums", "make_gaussian_partial_sums_uniform", "make_gaussian_partial_sums_on_grid", "toy_data",
+           "generate_coefficients"]
 
 
 def _gaussian_draws(mean, K, n_draws, rng, allow_singular=True):
@@ -95,3 +96,23 @@ def make_gaussian_partial_sums_on_grid(n_samples=100, n_features=1, orders=5, ke
     y = make_gaussian_partial_sums(X=X, orders=orders, kernel=kernel, mean=mean, ratio=ratio, ref=ref, nugget=nugget,
                                    random_state=random_state, allow_singular=allow_singular)
     return X, y
+
+
+def generate_coefficients(X, size=1, basis=None, corr=None, beta=0, sd=1, noise=1e-5, **corr_kwargs):
+    """`size` curves ~ N(basis(X) beta, sd^2 corr(X, **corr_kwargs) + noise^2 I), shape (size, n_samples) — the legacy generator
+    of gsum/helpers.py:55-68.  `corr` is a callable returning the correlation matrix (default: `gaussian`, on the device); the
+    factorisation and the draws run on the device, the normals come from numpy's global generator as in the reference."""
+    X = np.asarray(X, dtype=np.float64)
+    K = sd ** 2 * np.asarray((gaussian if corr is None else corr)(X, **corr_kwargs), dtype=np.float64)
+    K[np.diag_indices_from(K)] += noise ** 2
+    B = np.ones((len(X), 1)) if basis is None else basis(X)
+    mean = np.dot(B, np.atleast_1d(beta))
+    return _gaussian_draws(mean, K, size, np.random.mtrand._rand).T
+
+
+def toy_data(X, orders, basis=None, corr=None, beta=0, sd=1, ratio=0.5, ref=1, noise=1e-5, **corr_kwargs):
+    """Partial sums of len(orders) curves from `generate_coefficients` (gsum/helpers.py:36-52).  As in the reference the curves are
+    the ROWS here — coefficients of shape (len(orders), n_samples) go to `partials` unchanged, which sums along the last axis
+    with powers `orders` — so the call is meaningful for len(orders) == n_samples only; kept for import compatibility."""
+    coeffs = generate_coefficients(X, size=len(orders), basis=basis, corr=corr, beta=beta, sd=sd, noise=noise, **corr_kwargs)
+    return partials(coeffs=coeffs, ratio=ratio, ref=ref, orders=orders)

@@ -10,12 +10,16 @@ no array arithmetic to move to the device, kept so that `from gsum import ...` l
 """
 from __future__ import annotations
 
+import functools
+import inspect
+
 import numpy as np
 
 from . import ops
 
 __all__ = ["cartesian", "coefficients", "partials", "geometric_sum", "pivoted_cholesky", "cholesky_errors",
-           "mahalanobis", "stabilize", "rbf", "gaussian", "kl_gauss", "predictions", "hpd", "hpd_pdf", "median_pdf"]
+           "mahalanobis", "stabilize", "rbf", "gaussian", "kl_gauss", "predictions", "hpd", "hpd_pdf", "median_pdf",
+           "lazy_property", "default_attributes"]
 
 
 def cartesian(*arrays):
@@ -221,3 +225,47 @@ def median_pdf(pdf, x):
     cdf = np.concatenate([[0.0], np.cumsum(0.5 * (pdf[1:] + pdf[:-1]) * np.diff(x))])
     above = np.nonzero(cdf > 0.5)[0]
     return x[above[0]] if above.size else x[-1]
+
+
+def lazy_property(function):
+    """Read-only property evaluated on first access and kept on the instance as `_cache_<name>` (gsum/helpers.py:371-386)."""
+    slot = "_cache_" + function.__name__
+
+    @functools.wraps(function)
+    def getter(self):
+        try:
+            return getattr(self, slot)
+        except AttributeError:
+            value = function(self)
+            setattr(self, slot, value)
+            return value
+    return property(getter)
+
+
+def default_attributes(**kws):
+    """Method decorator: an argument left at None (or an empty *args / **kwargs) is replaced by the instance attribute named
+    in `kws` for that parameter — `@default_attributes(x='x', y='_y')` makes `def f(self, x=None, y=None)` default to
+    `self.x`, `self._y` at call time (gsum/helpers.py:416-501).  numpy arrays are never treated as missing."""
+    def decorator(function):
+        sig = inspect.signature(function)
+        P = inspect.Parameter
+
+        def missing(value, kind):
+            if isinstance(value, np.ndarray):
+                return False
+            if kind in (P.POSITIONAL_OR_KEYWORD, P.KEYWORD_ONLY):
+                return value is None
+            if kind == P.VAR_POSITIONAL:
+                return value == ()
+            return kind == P.VAR_KEYWORD and value == {}
+
+        @functools.wraps(function)
+        def wrapper(self, *args, **kwargs):
+            bound = sig.bind(self, *args, **kwargs)
+            bound.apply_defaults()
+            for name in list(bound.arguments):
+                if name in kws and missing(bound.arguments[name], sig.parameters[name].kind):
+                    bound.arguments[name] = getattr(self, kws[name])
+            return function(*bound.args, **bound.kwargs)
+        return wrapper
+    return decorator

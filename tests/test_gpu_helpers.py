@@ -123,3 +123,17 @@ def test_partial_sum_generator_variants_and_errors(ctx, golden):
     ll = gp.log_marginal_likelihood_grid(ls_vals, ratio_vals=q_vals)
     iq, il = np.unravel_index(np.argmax(ll), ll.shape)
     assert abs(q_vals[iq] - 0.5) <= 0.1 and abs(ls_vals[il] - 0.15) <= 0.05
+
+
+def test_legacy_generators(ctx):
+    """`generate_coefficients` / `toy_data` (gsum/helpers.py:36-68): device correlation matrix, factor and draws; normals from
+    numpy's global generator as in the reference."""
+    X = np.linspace(0, 1, 12)[:, None]
+    np.random.seed(4)
+    c = gb.generate_coefficients(X, size=3000, beta=0.7, sd=1.5, noise=0.05, ls=0.3)
+    assert c.shape == (3000, 12)
+    K = 1.5 ** 2 * o.rbf_corr(X, ls=0.3) + 0.05 ** 2 * np.eye(12)
+    sd = np.sqrt((K ** 2 + np.outer(np.diag(K), np.diag(K))) / 2999)
+    assert np.max(np.abs(np.cov(c.T) - K) / sd) < 5.0 and np.max(np.abs(c.mean(axis=0) - 0.7) / np.sqrt(np.diag(K) / 3000)) < 5.0
+    np.random.seed(4)
+    assert gb.toy_data(X, orders=np.arange(12), ls=0.3).shape == (12, 12)

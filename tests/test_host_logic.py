@@ -481,3 +481,60 @@ def test_device_backed_helpers_host_logic(monkeypatch, golden):
     assert gb.kl_gauss(g["kl_mu0"], g["kl_cov0"], g["kl_mu1"], chol1=g["kl_chol1"]) == pytest.approx(float(g["kl_from_chol"]), rel=1e-11)
     assert gb.kl_gauss(0.2, 1.3, -0.4, cov1=0.9) == pytest.approx(float(g["kl_scalar"]), rel=1e-12)
     assert gb.kl_gauss(np.zeros(60), g["kl_cov0"], 0.25, chol1=g["kl_chol1"]) == pytest.approx(float(g["kl_scalar_mean1"]), rel=1e-11)
+
+
+def test_decorator_helpers():
+    """`lazy_property` / `default_attributes` (gsum/helpers.py:371-386, 416-501): the docstring example of the reference."""
+    import gsum_b200 as gb
+
+    class T:
+        calls = 0
+
+        def __init__(self, x, y):
+            self.x, self._y = x, y
+
+        @gb.lazy_property
+        def total(self):
+            """doc"""
+            T.calls += 1
+            return self.x + self._y
+
+        @gb.default_attributes(x='x', y='_y')
+        def add(self, x=None, y=None):
+            return x + y
+
+        @gb.default_attributes(args='x', kw='_y')
+        def star(self, *args, **kw):
+            return args, kw
+
+    t = T(2, 3)
+    assert t.total == 5 and t.total == 5 and T.calls == 1 and t._cache_total == 5 and T.total.__doc__ == "doc"
+    assert t.add() == 5 and t.add(10) == 13 and t.add(y=1) == 3
+    t.x = 20
+    assert t.add() == 23 and t.total == 5                               # defaults are read at call time; the cache is not
+    assert t.add(np.zeros(2), np.ones(2)).tolist() == [1.0, 1.0]        # arrays are never "missing"
+    t.x, t._y = (1, 2), dict(a=1)
+    assert t.star() == ((1, 2), dict(a=1)) and t.star(7) == ((7,), dict(a=1)) and t.star(b=2) == ((1, 2), dict(b=2))
+
+
+def test_legacy_generators_host_logic(monkeypatch):
+    """`generate_coefficients` / `toy_data` (gsum/helpers.py:36-68) with numpy stand-ins for the device calls."""
+    import gsum_b200 as gb
+    from gsum_b200 import ops
+    monkeypatch.setattr(ops, "kernel_matrix", _numpy_kernel_matrix)
+    monkeypatch.setattr(ops, "pivoted_cholesky", _numpy_pivoted_cholesky)
+    monkeypatch.setattr(ops, "draws", _numpy_draws)
+    X = np.linspace(0, 1, 12)[:, None]
+    np.random.seed(4)
+    c = gb.generate_coefficients(X, size=3000, beta=0.7, sd=1.5, noise=0.05, ls=0.3)
+    assert c.shape == (3000, 12)
+    K = 1.5 ** 2 * o.rbf_corr(X, ls=0.3) + 0.05 ** 2 * np.eye(12)
+    sd = np.sqrt((K ** 2 + np.outer(np.diag(K), np.diag(K))) / 2999)
+    assert np.max(np.abs(np.cov(c.T) - K) / sd) < 5.0 and np.max(np.abs(c.mean(axis=0) - 0.7) / np.sqrt(np.diag(K) / 3000)) < 5.0
+    np.random.seed(4)
+    c2 = gb.generate_coefficients(X, size=2, corr=lambda X, ls: o.rbf_corr(X, ls=ls), basis=lambda X: np.c_[np.ones(len(X)), X[:, 0]],
+                                  beta=[0.7, 0.0], sd=1.5, noise=0.05, ls=0.3)
+    assert c2.shape == (2, 12) and np.isfinite(c2).all()
+    np.random.seed(4)
+    y = gb.toy_data(X, orders=np.arange(12), ls=0.3)                    # curves are rows: square case only, as in the reference
+    assert y.shape == (12, 12)
