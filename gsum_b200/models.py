@@ -701,6 +701,8 @@ class TruncationProcess:
     # ---- fit (gsum/models.py:1367-1387) ----
     def fit(self, X, y, orders, dX=None, dy=None):
         self.X_train_, self.y_train_, self.orders_ = X, y, orders
+        # the grid caches are keyed by object identity: a later array may reuse the address of one that has been freed
+        self._grid_inputs_cache = self._grid_ref_cache = None
         orders_mask = ~np.isin(orders, self.excluded)
         self.dX_, self.dy_ = dX, dy
         ratio, ref = self.ratio(X, **self.ratio_kws), self.ref(X)

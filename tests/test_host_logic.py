@@ -538,3 +538,38 @@ def test_legacy_generators_host_logic(monkeypatch):
     np.random.seed(4)
     y = gb.toy_data(X, orders=np.arange(12), ls=0.3)                    # curves are rows: square case only, as in the reference
     assert y.shape == (12, 12)
+
+
+def test_grid_input_caches_do_not_outlive_a_fit(monkeypatch):
+    """The per-fit caches of `log_marginal_likelihood_grid` (order differences, ref(X)) are keyed by object identity; `fit` must
+    drop them, because a later array can reuse the address of a freed one.  Device calls replaced by recorders."""
+    import gsum_b200 as gb
+    from gsum_b200 import ops
+
+    class _Handle:
+        center = disp = 0.0
+        df = scale = cov_factor = 1.0
+        lml = 0.0
+
+        def __init__(self, *a, **k):
+            pass
+
+        def close(self):
+            pass
+    seen = []
+    monkeypatch.setattr(ops, "FitHandle", _Handle)
+    monkeypatch.setattr(ops, "lml_grid", lambda X, dy, ref, orders, ls, Q, **kw: seen.append((dy.copy(), np.array(ref, copy=True))) or np.zeros((len(Q), len(ls))))
+    X = np.linspace(0, 1, 7)[:, None]
+    gp = gb.TruncationGP(RBF(0.2) + WhiteKernel(1e-6, 'fixed'), ratio=0.5, ref=lambda X: 1.0 + X[:, 0], optimizer=None)
+    y1 = np.cumsum(np.ones((7, 3)), axis=1)
+    gp.fit(X, y1, orders=np.arange(3))
+    gp.log_marginal_likelihood_grid([0.1, 0.2], ratio_vals=[0.4, 0.5])
+    cached = gp._grid_inputs_cache
+    gp.log_marginal_likelihood_grid([0.1, 0.2], ratio_vals=[0.4, 0.5])
+    assert gp._grid_inputs_cache is cached                                 # reused between calls on the same fit
+    y2 = np.cumsum(2.0 * np.ones((7, 3)), axis=1)
+    gp.fit(X, y2, orders=np.arange(3))
+    assert gp._grid_inputs_cache is None and gp._grid_ref_cache is None
+    gp.log_marginal_likelihood_grid([0.1, 0.2], ratio_vals=[0.4, 0.5])
+    assert np.array_equal(seen[0][0], np.ones((7, 3))) and np.array_equal(seen[-1][0], 2.0 * np.ones((7, 3)))
+    assert np.array_equal(seen[-1][1], 1.0 + X[:, 0])
